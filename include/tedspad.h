@@ -1,0 +1,150 @@
+/*
+ * tedspad.h -- C ABI of the B200-native TeD-SPAD snippet feature-extraction hot path.
+ *
+ * The reference (UCF-CRCV/TeD-SPAD) is pure Python/PyTorch and has no FFI of its own: every
+ * GPU kernel on this path is an ATen/cuDNN library call made from an nn.Module.forward body.
+ * Each entry point below therefore cites the reference call site(s) whose library kernels it
+ * replaces.  The host side that binds these symbols (ctypes) lives in ted-spad_b200/_lib.py and
+ * mirrors aux_code/model_loaders.py; see INTEGRATION.md for the stub a reference maintainer adds.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless stated otherwise;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *   - every function returns 0 on success, non-zero on error; tedspad_last_error() then returns
+ *     a thread-local, NUL-terminated description (the Python host raises RuntimeError with it);
+ *   - functions are re-entrant per (device, stream); the library keeps no mutable global state
+ *     except the lazily resolved driver entry point for tensor-map encoding;
+ *   - activations are channels-last bf16: [N][D+2pd][H+2ph][W+2pw][ld] with a zero halo of
+ *     (pd,ph,pw) pixels on every side (2-D tensors use D=1, pd=0).  A `tedspad_tensor` is a view
+ *     of channels [coff, coff+C) of such a buffer, which is how skip/branch concatenation
+ *     (unet_parts.py:67, i3d.py:149) is done without a copy.
+ */
+#ifndef TEDSPAD_H_
+#define TEDSPAD_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TEDSPAD_ABI_VERSION 1
+
+enum { TEDSPAD_ACT_NONE = 0, TEDSPAD_ACT_RELU = 1, TEDSPAD_ACT_SIGMOID = 2 };
+/* A-operand feed of the implicit GEMM: AUTO picks FLAT when legal. */
+enum { TEDSPAD_FEED_AUTO = 0, TEDSPAD_FEED_FLAT_TMA = 1, TEDSPAD_FEED_GATHER = 2 };
+/* resampling filters of tedspad_preprocess */
+enum { TEDSPAD_RESAMPLE_AA_FLOAT = 0, TEDSPAD_RESAMPLE_PIL_U8 = 1 };
+
+typedef struct tedspad_tensor {
+  void* ptr;                /* base of the allocation (halo included) */
+  int32_t N, D, H, W, C;    /* logical extents of the view */
+  int32_t pd, ph, pw;       /* zero halo on each side of D, H, W */
+  int32_t ld;               /* channel stride of the allocation, elements */
+  int32_t coff;             /* first channel of the view */
+} tedspad_tensor;
+
+/*
+ * Convolution + folded BatchNorm + bias + optional residual add + activation, as an implicit
+ * GEMM on tcgen05 tensor cores (fp32 accumulate in TMEM).
+ * Replaces: nn.Conv2d+BatchNorm2d+ReLU of DoubleConv (aux_code/models/unet_parts.py:15-22),
+ *           Unit3D.forward incl. TF-SAME padding (aux_code/models/i3d.py:89-120),
+ *           Bottleneck.forward convs/BN/residual/ReLU (aux_code/models/large_i3d.py:61-84),
+ *           I3Res50 conv1/bn1/relu (large_i3d.py:251-253), torchvision VideoResNet
+ *           BasicStem/BasicBlock convs (video/resnet.py:87-121,173-181), and the Linear head of
+ *           wrapper_r3d_18 (aux_code/model_loaders.py:204-213) as a 1x1x1 convolution.
+ * Weights `w` are bf16 [Cout_pad][K_pad], K-major, K ordered (kd,kh,kw,cin) with cin padded to
+ * Cin_pad = x.C; BN scale is folded into them in fp32 before rounding; `bias` is fp32 [Cout_pad].
+ * Padding is given as FRONT pads; the back pad is implied by the output extents (this is what
+ * expresses the asymmetric TF-SAME padding of i3d.py:82-109).
+ * FLAT feed requires stride 1, x.C % 64 == 0, symmetric pads equal to the kernel half-width,
+ * y with the same (N,D,H,W) and halo as x and halo >= pads; it keeps the zero halo of y intact.
+ */
+typedef struct tedspad_conv {
+  tedspad_tensor x;         /* bf16 input view */
+  tedspad_tensor y;         /* output view: bf16, or fp32 when y_fp32 != 0 */
+  const void* w;
+  const float* bias;
+  const void* res;          /* optional bf16 residual with y's geometry/halo; NULL = none */
+  int32_t res_ld, res_coff;
+  int32_t Cout, Cout_pad, K_pad;
+  int32_t kd, kh, kw;
+  int32_t sd, sh, sw;
+  int32_t pd, ph, pw;       /* front pads */
+  int32_t act;              /* TEDSPAD_ACT_* */
+  int32_t y_fp32;
+  int32_t feed;             /* TEDSPAD_FEED_* */
+  int32_t n_tile;           /* UMMA N per tile; 0 = auto */
+  int32_t max_ctas;         /* persistent grid cap; 0 = number of SMs */
+} tedspad_conv;
+
+int tedspad_conv_forward(const tedspad_conv* p, void* stream);
+
+/*
+ * Max pooling over (D,H,W) windows, channels-last.  Out-of-range taps contribute `0` when
+ * zero_pad != 0 (MaxPool3dSamePadding pads with zeros: aux_code/models/i3d.py:21-45) and are
+ * ignored otherwise.  Replaces nn.MaxPool2d(2) (unet_parts.py:33), MaxPool3dSamePadding
+ * (i3d.py:13-45), I3Res50.maxpool1/maxpool2 (large_i3d.py:138-139).  Writes only the interior of
+ * y (its halo must already be zero).
+ */
+int tedspad_maxpool(const tedspad_tensor* x, const tedspad_tensor* y, int32_t kd, int32_t kh, int32_t kw,
+                    int32_t sd, int32_t sh, int32_t sw, int32_t pd, int32_t ph, int32_t pw, int32_t zero_pad,
+                    void* stream);
+
+/*
+ * x2 bilinear up-sampling with align_corners=True written into a channel slice of the
+ * concatenation buffer, centred with F.pad when sizes differ.
+ * Replaces Up.forward's nn.Upsample + F.pad + torch.cat (aux_code/models/unet_parts.py:50,57-67).
+ */
+int tedspad_upsample2x(const tedspad_tensor* x, const tedspad_tensor* y, void* stream);
+
+/*
+ * OutConv (1x1, C->3) + sigmoid + the anonymizer->encoder raw-reshape glue: plane p = 3*t + c of
+ * frame t lands at encoder channel p / T, time p % T.
+ * Replaces OutConv.forward + nn.Sigmoid (unet_parts.py:71-77, unet_model.py:36-37) and the
+ * view/reshape at feature_extraction/dali_extraction.py:171-173.
+ * x: [B*T frames] view with C input channels; w: fp32 [3][C]; b: fp32 [3];
+ * y: encoder input view [B][T][H][W] with >=3 channels (bf16).  When `frames_out` is non-NULL the
+ * un-scattered fp32 anonymized frames [B*T][3][H][W] (NCHW, the fa_model return value) are also
+ * written.
+ */
+int tedspad_outconv_sigmoid(const tedspad_tensor* x, const float* w, const float* b, const tedspad_tensor* y,
+                            int32_t T, float* frames_out, void* stream);
+
+/*
+ * Mean over a (kd, H, W) window sliding over D with stride 1 -> fp32 features [N][D-kd+1][C].
+ * kd <= 0 means kd = D (global pooling).
+ * Replaces nn.AvgPool3d([2,7,7]) (i3d.py:293-294,340) and AdaptiveAvgPool3d(1) (large_i3d.py:262,
+ * torchvision video/resnet.py:261).
+ */
+int tedspad_avgpool_features(const tedspad_tensor* x, int32_t kd, float* out, void* stream);
+
+/*
+ * Crop + resize + normalise decoded uint8 frames into the anonymizer's bf16 input layout.
+ * Replaces DALIDataloader.val_augmentations (feature_extraction/dali_extraction.py:38-50) with
+ * TEDSPAD_RESAMPLE_AA_FLOAT (antialiased bilinear on /255 floats) and
+ * shanghai_frames_dataset.augmentation (feature_extraction/shanghai_dl.py:27-40) with
+ * TEDSPAD_RESAMPLE_PIL_U8 (Pillow's 8-bit two-pass bilinear, re-quantised, then /255).
+ * frames: uint8 [F][Hs][Ws][3]; desc: int32 [n_out][4] = {src_frame (<0: all-zero image, DALI
+ * pad_sequences), top, left, hflip} (hflip: crop taken from the horizontally flipped frame, as
+ * torchvision ten_crop does); all images of one call share the crop size crop_h x crop_w;
+ * y: bf16 view [n_out][1][Ho][Wo] with >= 3 channels (extra channels are written as zero).
+ * `frames_f32` (optional) receives the fp32 NCHW [n_out][3][Ho][Wo] result for parity tests.
+ */
+int tedspad_preprocess(const uint8_t* frames, int32_t F, int32_t Hs, int32_t Ws, const int32_t* desc,
+                       int32_t n_out, int32_t crop_h, int32_t crop_w, const tedspad_tensor* y, int32_t resample,
+                       float* frames_f32, void* stream);
+
+/* fp32 NCHW / NCDHW tensor -> bf16 channels-last view (module-boundary adapter used when a caller
+ * hands the nn.Module an fp32 torch tensor, e.g. dali_extraction.py:173,176).  x has Cx channels;
+ * channels [Cx, y.C) of the view are written as zero. */
+int tedspad_nchw_to_cl(const float* x, int32_t Cx, const tedspad_tensor* y, void* stream);
+
+int tedspad_abi_version(void);
+int tedspad_num_sms(void);
+const char* tedspad_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TEDSPAD_H_ */

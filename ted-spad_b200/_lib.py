@@ -1,0 +1,75 @@
+"""ctypes binding of the C ABI declared in include/tedspad.h.
+
+The shared library is built in-tree (`make -C ted-spad_b200/csrc`, or `__graft_entry__.build()`)
+as `ted-spad_b200/libtedspad.so`.  There is deliberately no fallback: if the library is missing
+or a call fails, a Python exception is raised.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtedspad.so")
+
+ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
+FEED_AUTO, FEED_FLAT_TMA, FEED_GATHER = 0, 1, 2
+RESAMPLE_AA_FLOAT, RESAMPLE_PIL_U8 = 0, 1
+ABI_VERSION = 1
+
+
+class TensorDesc(C.Structure):
+    """struct tedspad_tensor"""
+    _fields_ = [("ptr", C.c_void_p)] + [(n, C.c_int32) for n in
+                                        ("N", "D", "H", "W", "C", "pd", "ph", "pw", "ld", "coff")]
+
+
+class ConvDesc(C.Structure):
+    """struct tedspad_conv"""
+    _fields_ = [("x", TensorDesc), ("y", TensorDesc), ("w", C.c_void_p), ("bias", C.c_void_p),
+                ("res", C.c_void_p)] + [(n, C.c_int32) for n in (
+                    "res_ld", "res_coff", "Cout", "Cout_pad", "K_pad", "kd", "kh", "kw", "sd", "sh", "sw",
+                    "pd", "ph", "pw", "act", "y_fp32", "feed", "n_tile", "max_ctas")]
+
+
+# every symbol include/tedspad.h declares: (name, restype, argtypes)
+_TP = C.POINTER(TensorDesc)
+_I = C.c_int32
+_V = C.c_void_p
+SYMBOLS = {
+    "tedspad_conv_forward": (C.c_int, [C.POINTER(ConvDesc), _V]),
+    "tedspad_maxpool": (C.c_int, [_TP, _TP, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _V]),
+    "tedspad_upsample2x": (C.c_int, [_TP, _TP, _V]),
+    "tedspad_outconv_sigmoid": (C.c_int, [_TP, _V, _V, _TP, _I, _V, _V]),
+    "tedspad_avgpool_features": (C.c_int, [_TP, _I, _V, _V]),
+    "tedspad_preprocess": (C.c_int, [_V, _I, _I, _I, _V, _I, _I, _I, _TP, _I, _V, _V]),
+    "tedspad_nchw_to_cl": (C.c_int, [_V, _I, _TP, _V]),
+    "tedspad_abi_version": (C.c_int, []),
+    "tedspad_num_sms": (C.c_int, []),
+    "tedspad_last_error": (C.c_char_p, []),
+}
+
+_lib = None
+
+
+def lib():
+    """Load (once) and return the C-ABI library; raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} not found: build it with `make -C {os.path.join(_HERE, 'csrc')}` "
+                "(or `python -c 'import __graft_entry__ as g; g.build()'`). There is no CPU fallback.")
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        if l.tedspad_abi_version() != ABI_VERSION:
+            raise ImportError(f"{LIB_PATH}: ABI version {l.tedspad_abi_version()} != {ABI_VERSION}; rebuild")
+        _lib = l
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().tedspad_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (rc={rc}): {msg}")

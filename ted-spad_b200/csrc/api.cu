@@ -1,0 +1,84 @@
+// C-ABI plumbing: error text, tensor checks, SM count, TMA tensor-map encoding.
+#include <cstdarg>
+#include <cstdio>
+#include <mutex>
+
+#include "common.h"
+
+namespace tsp {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_tensor(const tedspad_tensor& t, const char* name, int elem_align) {
+  TSP_CHECK(t.ptr != nullptr, "%s: null pointer", name);
+  TSP_CHECK(t.N >= 1 && t.D >= 1 && t.H >= 1 && t.W >= 1 && t.C >= 1, "%s: bad extents [%d,%d,%d,%d,%d]", name, t.N,
+            t.D, t.H, t.W, t.C);
+  TSP_CHECK(t.pd >= 0 && t.ph >= 0 && t.pw >= 0, "%s: negative halo", name);
+  TSP_CHECK(t.coff >= 0 && t.coff + t.C <= t.ld, "%s: channel view [%d,%d) exceeds ld=%d", name, t.coff, t.coff + t.C,
+            t.ld);
+  TSP_CHECK(t.ld % elem_align == 0 && t.coff % elem_align == 0, "%s: ld=%d / coff=%d must be multiples of %d", name,
+            t.ld, t.coff, elem_align);
+  return 0;
+}
+
+int num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 1;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 1;
+    sms = prop.multiProcessorCount;
+  }
+  return sms;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres);
+    if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiledFn>(f);
+  });
+  return fn;
+}
+
+int encode_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
+                        uint32_t box_inner, uint32_t box_outer) {
+  EncodeTiledFn fn = get_encode_fn();
+  TSP_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+  TSP_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0 && pitch_bytes % 16 == 0,
+            "tensor map: base/pitch must be 16-byte aligned (base=%p pitch=%llu)", base,
+            (unsigned long long)pitch_bytes);
+  TSP_CHECK(box_inner * 2 == 128 && box_outer >= 1 && box_outer <= 256, "tensor map: bad box %ux%u", box_inner,
+            box_outer);
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {pitch_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  TSP_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (dims %llu x %llu pitch %llu)", (int)r,
+            (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)pitch_bytes);
+  return 0;
+}
+
+}  // namespace tsp
+
+extern "C" int tedspad_abi_version(void) { return TEDSPAD_ABI_VERSION; }
+extern "C" int tedspad_num_sms(void) { return tsp::num_sms(); }
+extern "C" const char* tedspad_last_error(void) { return tsp::g_err; }

@@ -1,0 +1,48 @@
+// Host-side helpers shared by the C-ABI translation units: thread-local error text, checks,
+// and the lazily resolved driver entry point used to encode TMA tensor maps (resolved through
+// cudart so that the library has no link-time dependency on libcuda and loads on a CPU-only box).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/tedspad.h"
+
+namespace tsp {
+
+void set_error(const char* fmt, ...);
+
+#define TSP_CHECK(cond, ...)        \
+  do {                              \
+    if (!(cond)) {                  \
+      ::tsp::set_error(__VA_ARGS__); \
+      return 1;                     \
+    }                               \
+  } while (0)
+
+#define TSP_CUDA(expr)                                                              \
+  do {                                                                              \
+    cudaError_t e__ = (expr);                                                       \
+    if (e__ != cudaSuccess) {                                                       \
+      ::tsp::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return 2;                                                                     \
+    }                                                                               \
+  } while (0)
+
+// 2-D bf16 tensor map: dims {inner, outer}, row pitch in bytes, box {box_inner, box_outer},
+// 128-byte swizzle, zero fill out of bounds.  Returns 0 on success.
+int encode_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
+                        uint32_t box_inner, uint32_t box_outer);
+
+int num_sms();
+
+inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+
+// byte address of element (n, d, h, w, c=coff) of the LOGICAL view (halo skipped)
+inline int64_t tensor_pixels(const tedspad_tensor& t) {
+  return (int64_t)t.N * (t.D + 2 * t.pd) * (t.H + 2 * t.ph) * (t.W + 2 * t.pw);
+}
+
+int check_tensor(const tedspad_tensor& t, const char* name, int elem_align);
+
+}  // namespace tsp

@@ -1,0 +1,533 @@
+// HBM-bound side kernels of the hot path: pooling, up-sampling into concat slices, the OutConv +
+// sigmoid + raw-reshape scatter, feature mean-pooling, uint8 preprocessing and layout adapters.
+// All activations are channels-last bf16; every kernel moves 16 bytes (8 channels) per access.
+#include <cstdio>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace tsp {
+
+struct TView {  // device-side copy of tedspad_tensor with derived padded extents
+  uint8_t* ptr;
+  int N, D, H, W, C, pd, ph, pw, ld, coff, Dp, Hp, Wp;
+};
+
+static TView make_view(const tedspad_tensor& t) {
+  TView v;
+  v.ptr = reinterpret_cast<uint8_t*>(t.ptr);
+  v.N = t.N; v.D = t.D; v.H = t.H; v.W = t.W; v.C = t.C;
+  v.pd = t.pd; v.ph = t.ph; v.pw = t.pw; v.ld = t.ld; v.coff = t.coff;
+  v.Dp = t.D + 2 * t.pd; v.Hp = t.H + 2 * t.ph; v.Wp = t.W + 2 * t.pw;
+  return v;
+}
+
+__device__ __forceinline__ long long pix_index(const TView& v, int n, int d, int h, int w) {
+  return ((static_cast<long long>(n) * v.Dp + d + v.pd) * v.Hp + h + v.ph) * v.Wp + w + v.pw;
+}
+__device__ __forceinline__ const __nv_bfloat16* elem_ptr(const TView& v, long long pix, int c) {
+  return reinterpret_cast<const __nv_bfloat16*>(v.ptr) + pix * v.ld + v.coff + c;
+}
+__device__ __forceinline__ __nv_bfloat16* elem_ptr_w(const TView& v, long long pix, int c) {
+  return reinterpret_cast<__nv_bfloat16*>(v.ptr) + pix * v.ld + v.coff + c;
+}
+
+__device__ __forceinline__ void unpack8(const uint4& q, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 q;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&q);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return q;
+}
+
+// ------------------------------------------------------------------ max pool
+struct PoolP {
+  TView x, y;
+  int kd, kh, kw, sd, sh, sw, pd, ph, pw, zero_pad;
+  long long total;  // N*OD*OH*OW*(C/8)
+};
+
+__global__ void __launch_bounds__(256) maxpool_kernel(const PoolP p) {
+  const int c8n = p.y.C >> 3;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < p.total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    long long t = idx;
+    const int c8 = static_cast<int>(t % c8n); t /= c8n;
+    const int ow = static_cast<int>(t % p.y.W); t /= p.y.W;
+    const int oh = static_cast<int>(t % p.y.H); t /= p.y.H;
+    const int od = static_cast<int>(t % p.y.D);
+    const int n = static_cast<int>(t / p.y.D);
+    float m[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m[i] = -INFINITY;
+    bool any_oob = false;
+    for (int a = 0; a < p.kd; ++a) {
+      const int id = od * p.sd - p.pd + a;
+      for (int b = 0; b < p.kh; ++b) {
+        const int ih = oh * p.sh - p.ph + b;
+        for (int c = 0; c < p.kw; ++c) {
+          const int iw = ow * p.sw - p.pw + c;
+          if (static_cast<unsigned>(id) < static_cast<unsigned>(p.x.D) &&
+              static_cast<unsigned>(ih) < static_cast<unsigned>(p.x.H) &&
+              static_cast<unsigned>(iw) < static_cast<unsigned>(p.x.W)) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(elem_ptr(p.x, pix_index(p.x, n, id, ih, iw), c8 * 8)));
+            float f[8];
+            unpack8(q, f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], f[i]);
+          } else {
+            any_oob = true;
+          }
+        }
+      }
+    }
+    if (any_oob && p.zero_pad) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], 0.f);
+    }
+    *reinterpret_cast<uint4*>(elem_ptr_w(p.y, pix_index(p.y, n, od, oh, ow), c8 * 8)) = pack8(m);
+  }
+}
+
+// ------------------------------------------------- bilinear x2, align_corners
+struct UpP {
+  TView x, y;
+  int UH, UW, offy, offx;  // up-sampled size and F.pad offsets inside y
+  float sy, sx;
+  long long total;  // N*H*W*(C/8) over y's interior
+};
+
+__global__ void __launch_bounds__(256) upsample2x_kernel(const UpP p) {
+  const int c8n = p.y.C >> 3;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < p.total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    long long t = idx;
+    const int c8 = static_cast<int>(t % c8n); t /= c8n;
+    const int ow = static_cast<int>(t % p.y.W); t /= p.y.W;
+    const int oh = static_cast<int>(t % p.y.H);
+    const int n = static_cast<int>(t / p.y.H);
+    float o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = 0.f;
+    const int uy = oh - p.offy, ux = ow - p.offx;
+    if (uy >= 0 && uy < p.UH && ux >= 0 && ux < p.UW) {
+      const float fy = p.sy * uy, fx = p.sx * ux;
+      const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+      const int y1 = y0 + (y0 < p.x.H - 1 ? 1 : 0), x1 = x0 + (x0 < p.x.W - 1 ? 1 : 0);
+      const float ly1 = fy - y0, lx1 = fx - x0;
+      const float ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+      float a[8], b[8], c[8], d[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(elem_ptr(p.x, pix_index(p.x, n, 0, y0, x0), c8 * 8))), a);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(elem_ptr(p.x, pix_index(p.x, n, 0, y0, x1), c8 * 8))), b);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(elem_ptr(p.x, pix_index(p.x, n, 0, y1, x0), c8 * 8))), c);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(elem_ptr(p.x, pix_index(p.x, n, 0, y1, x1), c8 * 8))), d);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = ly0 * (lx0 * a[i] + lx1 * b[i]) + ly1 * (lx0 * c[i] + lx1 * d[i]);
+    }
+    *reinterpret_cast<uint4*>(elem_ptr_w(p.y, pix_index(p.y, n, 0, oh, ow), c8 * 8)) = pack8(o);
+  }
+}
+
+// --------------------------------- OutConv 1x1 (C->3) + sigmoid + plane scatter
+struct OutP {
+  TView x, y;
+  const float* w;
+  const float* b;
+  float* frames;
+  int T;
+  long long total;  // frames*H*W pixels
+};
+
+// 8 lanes per pixel: each lane owns 16-byte channel chunks lane, lane+8, ...; partial dot products
+// are combined with warp shuffles.
+__global__ void __launch_bounds__(256) outconv_sigmoid_kernel(const OutP p) {
+  extern __shared__ float sw[];  // [3][C]
+  for (int i = threadIdx.x; i < 3 * p.x.C; i += blockDim.x) sw[i] = p.w[i];
+  __syncthreads();
+  const int sub = threadIdx.x & 7;
+  const int chunks = p.x.C >> 3;
+  const long long gstride = static_cast<long long>(gridDim.x) * (blockDim.x >> 3);
+  const long long iters = (p.total + gstride - 1) / gstride;
+  long long pixi = blockIdx.x * static_cast<long long>(blockDim.x >> 3) + (threadIdx.x >> 3);
+  for (long long it = 0; it < iters; ++it, pixi += gstride) {
+    const bool ok = pixi < p.total;
+    float acc[3] = {0.f, 0.f, 0.f};
+    int w_ = 0, h_ = 0, fr = 0;
+    if (ok) {
+      long long t = pixi;
+      w_ = static_cast<int>(t % p.x.W); t /= p.x.W;
+      h_ = static_cast<int>(t % p.x.H);
+      fr = static_cast<int>(t / p.x.H);
+      const long long pin = pix_index(p.x, fr, 0, h_, w_);
+      for (int ch = sub; ch < chunks; ch += 8) {
+        float f[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(elem_ptr(p.x, pin, ch * 8))), f);
+#pragma unroll
+        for (int o = 0; o < 3; ++o) {
+          const float* wr = sw + o * p.x.C + ch * 8;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[o] = fmaf(f[i], wr[i], acc[o]);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < 3; ++o) {
+      acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], 4);
+      acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], 2);
+      acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], 1);
+    }
+    if (ok && sub < 3) {
+      const float v = 1.f / (1.f + __expf(-(acc[sub] + p.b[sub])));
+      const int bclip = fr / p.T, tf = fr - bclip * p.T;
+      const int plane = 3 * tf + sub;            // dali_extraction.py:173 raw reshape
+      const int ce = plane / p.T, te = plane - ce * p.T;
+      *elem_ptr_w(p.y, pix_index(p.y, bclip, te, h_, w_), ce) = __float2bfloat16_rn(v);
+      if (p.frames) p.frames[((static_cast<long long>(fr) * 3 + sub) * p.x.H + h_) * p.x.W + w_] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------ feature mean pool
+struct AvgP {
+  TView x;
+  int kd, OD;
+  float* out;
+};
+
+// one block per (n, od); thread -> 8 channels; loops over the kd*H*W window (coalesced 16-byte loads)
+__global__ void __launch_bounds__(256) avgpool_kernel(const AvgP p) {
+  const int n = blockIdx.x / p.OD, od = blockIdx.x - n * p.OD;
+  const float inv = 1.f / static_cast<float>(p.kd * p.x.H * p.x.W);
+  for (int c8 = threadIdx.x; c8 < (p.x.C >> 3); c8 += blockDim.x) {
+    float s[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = 0.f;
+    for (int a = 0; a < p.kd; ++a)
+      for (int h = 0; h < p.x.H; ++h)
+        for (int w = 0; w < p.x.W; ++w) {
+          float f[8];
+          unpack8(__ldg(reinterpret_cast<const uint4*>(elem_ptr(p.x, pix_index(p.x, n, od + a, h, w), c8 * 8))), f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) s[i] += f[i];
+        }
+    float* o = p.out + (static_cast<long long>(n) * p.OD + od) * p.x.C + c8 * 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = s[i] * inv;
+  }
+}
+
+// ----------------------------------------------------------------- preprocess
+constexpr int PP_KMAX = 8;
+constexpr int PP_MAXOUT = 512;
+
+struct PrepP {
+  const uint8_t* frames;
+  int F, Hs, Ws;
+  const int32_t* desc;
+  int n_out, crop_h, crop_w, resample;
+  TView y;
+  float* frames_f32;
+};
+
+// Resampling tables for one axis, built by the block in shared memory.
+// AA_FLOAT follows aten's _upsample_bilinear2d_aa (align_corners=False): support = max(scale,1),
+// taps j in [lo,hi) with w = 1 - |(j - center + 0.5)/support|, normalised.
+// PIL_U8 follows Pillow's precompute_coeffs + normalize_coeffs_8bpc (double weights -> 22-bit fixed).
+__device__ void build_axis_table(int in, int out, int resample, int* lo, int* cnt, float* wf, int* wi) {
+  for (int i = threadIdx.x; i < out; i += blockDim.x) {
+    if (resample == TEDSPAD_RESAMPLE_PIL_U8) {
+      const double scale = static_cast<double>(in) / out;
+      const double fscale = scale < 1.0 ? 1.0 : scale;
+      const double support = 1.0 * fscale;
+      const double center = (i + 0.5) * scale;
+      const double ss = 1.0 / fscale;
+      int xmin = static_cast<int>(center - support + 0.5);
+      if (xmin < 0) xmin = 0;
+      int xmax = static_cast<int>(center + support + 0.5);
+      if (xmax > in) xmax = in;
+      xmax -= xmin;
+      if (xmax > PP_KMAX) xmax = PP_KMAX;
+      double k[PP_KMAX];
+      double ww = 0.0;
+      for (int x = 0; x < xmax; ++x) {
+        double a = (x + xmin - center + 0.5) * ss;
+        if (a < 0.0) a = -a;
+        const double w = a < 1.0 ? 1.0 - a : 0.0;
+        k[x] = w;
+        ww += w;
+      }
+      for (int x = 0; x < xmax; ++x) {
+        if (ww != 0.0) k[x] /= ww;
+        const double v = k[x] * static_cast<double>(1 << 22);
+        wi[i * PP_KMAX + x] = static_cast<int>(k[x] < 0 ? -0.5 + v : 0.5 + v);
+      }
+      lo[i] = xmin;
+      cnt[i] = xmax;
+    } else {
+      const float scale = static_cast<float>(in) / static_cast<float>(out);
+      const float support = scale >= 1.f ? scale : 1.f;
+      const float invscale = scale >= 1.f ? 1.f / scale : 1.f;
+      const float center = scale * (i + 0.5f);
+      int xmin = static_cast<int>(center - support + 0.5f);
+      if (xmin < 0) xmin = 0;
+      int xmax = static_cast<int>(center + support + 0.5f);
+      if (xmax > in) xmax = in;
+      int n = xmax - xmin;
+      if (n > PP_KMAX) n = PP_KMAX;
+      float tot = 0.f;
+      for (int x = 0; x < n; ++x) {
+        float a = (x + xmin - center + 0.5f) * invscale;
+        if (a < 0.f) a = -a;
+        const float w = a < 1.f ? 1.f - a : 0.f;
+        wf[i * PP_KMAX + x] = w;
+        tot += w;
+      }
+      for (int x = 0; x < n; ++x)
+        if (tot != 0.f) wf[i * PP_KMAX + x] /= tot;
+      lo[i] = xmin;
+      cnt[i] = n;
+    }
+  }
+}
+
+__device__ __forceinline__ int clip8_fixed(int v) {
+  v >>= 22;
+  return v < 0 ? 0 : (v > 255 ? 255 : v);
+}
+
+// grid: (row bands, n_out); block: 256 threads; thread -> one output pixel (3 channels),
+// one 16-byte store of 8 bf16 channels (3 real + zeros).
+__global__ void __launch_bounds__(256) preprocess_kernel(const PrepP p) {
+  extern __shared__ uint8_t pp_smem[];
+  const int Ho = p.y.H, Wo = p.y.W;
+  int* xlo = reinterpret_cast<int*>(pp_smem);
+  int* xcnt = xlo + Wo;
+  int* ylo = xcnt + Wo;
+  int* ycnt = ylo + Ho;
+  float* xwf = reinterpret_cast<float*>(ycnt + Ho);
+  float* ywf = xwf + Wo * PP_KMAX;
+  int* xwi = reinterpret_cast<int*>(xwf);
+  int* ywi = reinterpret_cast<int*>(ywf);
+  float* lut = ywf + Ho * PP_KMAX;
+  build_axis_table(p.crop_w, Wo, p.resample, xlo, xcnt, xwf, xwi);
+  build_axis_table(p.crop_h, Ho, p.resample, ylo, ycnt, ywf, ywi);
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = static_cast<float>(i) / 255.f;
+  __syncthreads();
+
+  const int n = blockIdx.y;
+  const int32_t* d = p.desc + n * 4;
+  const int src = d[0], top = d[1], left = d[2], flip = d[3];
+  const long long band = (static_cast<long long>(Ho) * Wo + gridDim.x - 1) / gridDim.x;
+  const long long p0 = blockIdx.x * band;
+  const long long p1 = min(p0 + band, static_cast<long long>(Ho) * Wo);
+  const uint8_t* img = p.frames + static_cast<long long>(src < 0 ? 0 : src) * p.Hs * p.Ws * 3;
+  for (long long q = p0 + threadIdx.x; q < p1; q += blockDim.x) {
+    const int oy = static_cast<int>(q / Wo), ox = static_cast<int>(q - static_cast<long long>(oy) * Wo);
+    float o[3] = {0.f, 0.f, 0.f};
+    if (src >= 0) {
+      const int yl = ylo[oy], yn = ycnt[oy], xl = xlo[ox], xn = xcnt[ox];
+      if (p.resample == TEDSPAD_RESAMPLE_PIL_U8) {
+        int acc[3] = {1 << 21, 1 << 21, 1 << 21};
+        for (int a = 0; a < yn; ++a) {
+          const uint8_t* rowp = img + static_cast<long long>(top + yl + a) * p.Ws * 3;
+          int h[3] = {1 << 21, 1 << 21, 1 << 21};
+          for (int b = 0; b < xn; ++b) {
+            const int cx = left + xl + b;
+            const uint8_t* px = rowp + (flip ? (p.Ws - 1 - cx) : cx) * 3;
+            const int k = xwi[ox * PP_KMAX + b];
+            h[0] += px[0] * k; h[1] += px[1] * k; h[2] += px[2] * k;
+          }
+          const int ky = ywi[oy * PP_KMAX + a];
+          acc[0] += clip8_fixed(h[0]) * ky; acc[1] += clip8_fixed(h[1]) * ky; acc[2] += clip8_fixed(h[2]) * ky;
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) o[c] = lut[clip8_fixed(acc[c])];
+      } else {
+        for (int a = 0; a < yn; ++a) {
+          const uint8_t* rowp = img + static_cast<long long>(top + yl + a) * p.Ws * 3;
+          const float wy = ywf[oy * PP_KMAX + a];
+          float h[3] = {0.f, 0.f, 0.f};
+          for (int b = 0; b < xn; ++b) {
+            const int cx = left + xl + b;
+            const uint8_t* px = rowp + (flip ? (p.Ws - 1 - cx) : cx) * 3;
+            const float wx = xwf[ox * PP_KMAX + b];
+            h[0] = fmaf(wx, lut[px[0]], h[0]); h[1] = fmaf(wx, lut[px[1]], h[1]); h[2] = fmaf(wx, lut[px[2]], h[2]);
+          }
+          o[0] = fmaf(wy, h[0], o[0]); o[1] = fmaf(wy, h[1], o[1]); o[2] = fmaf(wy, h[2], o[2]);
+        }
+      }
+    }
+    float f[8] = {o[0], o[1], o[2], 0.f, 0.f, 0.f, 0.f, 0.f};
+    __nv_bfloat16* yp = elem_ptr_w(p.y, pix_index(p.y, n, 0, oy, ox), 0);
+    if (p.y.C >= 8 && ((p.y.ld | p.y.coff) & 7) == 0) {
+      *reinterpret_cast<uint4*>(yp) = pack8(f);
+      for (int c = 8; c < p.y.C; ++c) yp[c] = __float2bfloat16_rn(0.f);
+    } else {
+      for (int c = 0; c < p.y.C; ++c) yp[c] = __float2bfloat16_rn(c < 3 ? o[c] : 0.f);
+    }
+    if (p.frames_f32) {
+      const long long plane = static_cast<long long>(Ho) * Wo;
+      float* fo = p.frames_f32 + static_cast<long long>(n) * 3 * plane + q;
+      fo[0] = o[0]; fo[plane] = o[1]; fo[2 * plane] = o[2];
+    }
+  }
+}
+
+// --------------------------------------------------- fp32 NC(D)HW -> bf16 channels-last
+struct CvtP {
+  const float* x;
+  int Cx;
+  TView y;
+  long long total;  // N*D*H*W*(y.C/8)
+};
+
+__global__ void __launch_bounds__(256) nchw_to_cl_kernel(const CvtP p) {
+  const int c8n = p.y.C >> 3;
+  const long long plane = static_cast<long long>(p.y.D) * p.y.H * p.y.W;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < p.total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    // pixel fastest so that the fp32 plane reads are coalesced
+    const long long pixl = idx % (plane * p.y.N);
+    const int c8 = static_cast<int>(idx / (plane * p.y.N));
+    const int n = static_cast<int>(pixl / plane);
+    long long r = pixl - n * plane;
+    const int w = static_cast<int>(r % p.y.W); r /= p.y.W;
+    const int h = static_cast<int>(r % p.y.H);
+    const int d = static_cast<int>(r / p.y.H);
+    float f[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = c8 * 8 + i;
+      f[i] = c < p.Cx ? __ldg(p.x + (static_cast<long long>(n) * p.Cx + c) * plane + (pixl - n * plane)) : 0.f;
+    }
+    *reinterpret_cast<uint4*>(elem_ptr_w(p.y, pix_index(p.y, n, d, h, w), c8 * 8)) = pack8(f);
+  }
+  (void)c8n;
+}
+
+static int grid_for(long long total, int threads) {
+  const long long blocks = (total + threads - 1) / threads;
+  const long long cap = static_cast<long long>(num_sms()) * 16;
+  return static_cast<int>(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
+}
+
+}  // namespace tsp
+
+using namespace tsp;
+
+extern "C" int tedspad_maxpool(const tedspad_tensor* x, const tedspad_tensor* y, int32_t kd, int32_t kh, int32_t kw,
+                               int32_t sd, int32_t sh, int32_t sw, int32_t pd, int32_t ph, int32_t pw, int32_t zero_pad,
+                               void* stream) {
+  TSP_CHECK(x && y, "maxpool: null tensor");
+  if (check_tensor(*x, "maxpool.x", 8) || check_tensor(*y, "maxpool.y", 8)) return 1;
+  TSP_CHECK(x->C == y->C && x->C % 8 == 0 && x->N == y->N, "maxpool: channel/batch mismatch");
+  TSP_CHECK(kd >= 1 && kh >= 1 && kw >= 1 && sd >= 1 && sh >= 1 && sw >= 1, "maxpool: bad window");
+  TSP_CHECK((y->D - 1) * sd - pd < x->D && (y->H - 1) * sh - ph < x->H && (y->W - 1) * sw - pw < x->W,
+            "maxpool: output extents exceed input");
+  PoolP p;
+  p.x = make_view(*x); p.y = make_view(*y);
+  p.kd = kd; p.kh = kh; p.kw = kw; p.sd = sd; p.sh = sh; p.sw = sw; p.pd = pd; p.ph = ph; p.pw = pw;
+  p.zero_pad = zero_pad;
+  p.total = static_cast<long long>(y->N) * y->D * y->H * y->W * (y->C / 8);
+  maxpool_kernel<<<grid_for(p.total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  TSP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tedspad_upsample2x(const tedspad_tensor* x, const tedspad_tensor* y, void* stream) {
+  TSP_CHECK(x && y, "upsample2x: null tensor");
+  if (check_tensor(*x, "upsample2x.x", 8) || check_tensor(*y, "upsample2x.y", 8)) return 1;
+  TSP_CHECK(x->C == y->C && x->C % 8 == 0 && x->N == y->N && x->D == 1 && y->D == 1, "upsample2x: shape mismatch");
+  UpP p;
+  p.x = make_view(*x); p.y = make_view(*y);
+  p.UH = 2 * x->H; p.UW = 2 * x->W;
+  TSP_CHECK(y->H >= p.UH && y->W >= p.UW, "upsample2x: target smaller than 2x source");
+  p.offy = (y->H - p.UH) / 2; p.offx = (y->W - p.UW) / 2;  // F.pad(diff//2, diff - diff//2)
+  p.sy = p.UH > 1 ? static_cast<float>(x->H - 1) / static_cast<float>(p.UH - 1) : 0.f;
+  p.sx = p.UW > 1 ? static_cast<float>(x->W - 1) / static_cast<float>(p.UW - 1) : 0.f;
+  p.total = static_cast<long long>(y->N) * y->H * y->W * (y->C / 8);
+  upsample2x_kernel<<<grid_for(p.total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  TSP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tedspad_outconv_sigmoid(const tedspad_tensor* x, const float* w, const float* b,
+                                       const tedspad_tensor* y, int32_t T, float* frames_out, void* stream) {
+  TSP_CHECK(x && y && w && b, "outconv: null argument");
+  if (check_tensor(*x, "outconv.x", 8) || check_tensor(*y, "outconv.y", 1)) return 1;
+  TSP_CHECK(x->C % 8 == 0 && x->D == 1, "outconv: x must be 2-D with C %% 8 == 0");
+  TSP_CHECK(T >= 1 && x->N % T == 0 && y->N == x->N / T && y->D == T && y->H == x->H && y->W == x->W && y->C >= 3,
+            "outconv: encoder input view [%d,%d,%d,%d,%d] does not match %d frames of T=%d", y->N, y->D, y->H, y->W,
+            y->C, x->N, T);
+  OutP p;
+  p.x = make_view(*x); p.y = make_view(*y);
+  p.w = w; p.b = b; p.frames = frames_out; p.T = T;
+  p.total = static_cast<long long>(x->N) * x->H * x->W;
+  const int blocks = grid_for(p.total * 8, 256);
+  outconv_sigmoid_kernel<<<blocks, 256, 3 * x->C * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  TSP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tedspad_avgpool_features(const tedspad_tensor* x, int32_t kd, float* out, void* stream) {
+  TSP_CHECK(x && out, "avgpool: null argument");
+  if (check_tensor(*x, "avgpool.x", 8)) return 1;
+  TSP_CHECK(x->C % 8 == 0, "avgpool: C %% 8 != 0");
+  AvgP p;
+  p.x = make_view(*x);
+  p.kd = kd <= 0 ? x->D : kd;
+  TSP_CHECK(p.kd <= x->D, "avgpool: window %d larger than D=%d", p.kd, x->D);
+  p.OD = x->D - p.kd + 1;
+  p.out = out;
+  avgpool_kernel<<<x->N * p.OD, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  TSP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tedspad_preprocess(const uint8_t* frames, int32_t F, int32_t Hs, int32_t Ws, const int32_t* desc,
+                                  int32_t n_out, int32_t crop_h, int32_t crop_w, const tedspad_tensor* y,
+                                  int32_t resample, float* frames_f32, void* stream) {
+  TSP_CHECK(frames && desc && y, "preprocess: null argument");
+  if (check_tensor(*y, "preprocess.y", 1)) return 1;
+  TSP_CHECK(n_out >= 1 && y->N == n_out && y->D == 1 && y->C >= 3, "preprocess: y must be [n_out,1,Ho,Wo,>=3]");
+  TSP_CHECK(y->H <= PP_MAXOUT && y->W <= PP_MAXOUT, "preprocess: output larger than %d", PP_MAXOUT);
+  TSP_CHECK(resample == TEDSPAD_RESAMPLE_AA_FLOAT || resample == TEDSPAD_RESAMPLE_PIL_U8, "preprocess: bad resample");
+  TSP_CHECK(crop_h >= 1 && crop_w >= 1 && crop_h <= Hs && crop_w <= Ws, "preprocess: bad crop %dx%d of %dx%d", crop_h,
+            crop_w, Hs, Ws);
+  const double sy = static_cast<double>(crop_h) / y->H, sx = static_cast<double>(crop_w) / y->W;
+  TSP_CHECK(2 * static_cast<int>(ceil(sy < 1 ? 1 : sy)) + 1 <= PP_KMAX + 1 &&
+                2 * static_cast<int>(ceil(sx < 1 ? 1 : sx)) + 1 <= PP_KMAX + 1,
+            "preprocess: down-scale factor too large for the %d-tap table", PP_KMAX);
+  PrepP p;
+  p.frames = frames; p.F = F; p.Hs = Hs; p.Ws = Ws; p.desc = desc; p.n_out = n_out;
+  p.crop_h = crop_h; p.crop_w = crop_w; p.resample = resample;
+  p.y = make_view(*y);
+  p.frames_f32 = frames_f32;
+  const size_t smem = (2 * y->W + 2 * y->H) * sizeof(int) + (y->W + y->H) * PP_KMAX * sizeof(float) + 256 * sizeof(float);
+  const int bands = std::max(1, std::min(64, (y->H * y->W + 2047) / 2048));
+  dim3 grid(bands, n_out);
+  preprocess_kernel<<<grid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  TSP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tedspad_nchw_to_cl(const float* x, int32_t Cx, const tedspad_tensor* y, void* stream) {
+  TSP_CHECK(x && y, "nchw_to_cl: null argument");
+  if (check_tensor(*y, "nchw_to_cl.y", 8)) return 1;
+  TSP_CHECK(y->C % 8 == 0 && Cx >= 1 && Cx <= y->C, "nchw_to_cl: Cx=%d vs y.C=%d", Cx, y->C);
+  CvtP p;
+  p.x = x; p.Cx = Cx; p.y = make_view(*y);
+  p.total = static_cast<long long>(y->N) * y->D * y->H * y->W * (y->C / 8);
+  nchw_to_cl_kernel<<<grid_for(p.total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  TSP_CUDA(cudaGetLastError());
+  return 0;
+}

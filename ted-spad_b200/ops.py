@@ -1,0 +1,196 @@
+"""Host-side wrappers of the C-ABI operators: channels-last activation buffers, weight packing
+and one Python function per entry point of include/tedspad.h.
+
+PyTorch is used here for device memory and streams only; all arithmetic is in libtedspad.so.
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib as L
+
+BF16 = torch.bfloat16
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda(t, what):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda):
+        raise RuntimeError(f"{what}: a CUDA tensor is required - this framework has no CPU path")
+
+
+class CLTensor:
+    """Channels-last activation buffer [N][D+2pd][H+2ph][W+2pw][ld] with a zero halo, or a channel
+    slice [coff, coff+C) of one (zero-copy concatenation)."""
+
+    def __init__(self, N, D, H, W, C_, halo=(0, 0, 0), device="cuda", dtype=BF16, ld=None, buf=None, coff=0):
+        self.N, self.D, self.H, self.W, self.C = int(N), int(D), int(H), int(W), int(C_)
+        self.pd, self.ph, self.pw = (int(h) for h in halo)
+        self.ld = int(ld) if ld is not None else self.C
+        self.coff = int(coff)
+        shape = (self.N, self.D + 2 * self.pd, self.H + 2 * self.ph, self.W + 2 * self.pw, self.ld)
+        if buf is None:
+            has_halo = (self.pd + self.ph + self.pw) > 0
+            buf = (torch.zeros if has_halo else torch.empty)(shape, device=device, dtype=dtype)
+        assert tuple(buf.shape) == shape and buf.is_contiguous(), (tuple(buf.shape), shape)
+        self.buf = buf
+
+    @property
+    def halo(self):
+        return (self.pd, self.ph, self.pw)
+
+    def slice(self, coff, C_):
+        assert 0 <= coff and coff + C_ <= self.ld
+        return CLTensor(self.N, self.D, self.H, self.W, C_, self.halo, ld=self.ld, buf=self.buf, coff=coff)
+
+    def desc(self):
+        return L.TensorDesc(self.buf.data_ptr(), self.N, self.D, self.H, self.W, self.C, self.pd, self.ph, self.pw,
+                            self.ld, self.coff)
+
+    def interior(self):
+        """torch view [N, D, H, W, C] of the logical tensor (no copy)."""
+        return self.buf[:, self.pd:self.pd + self.D, self.ph:self.ph + self.H, self.pw:self.pw + self.W,
+                        self.coff:self.coff + self.C]
+
+    def to_ncdhw(self):
+        return self.interior().permute(0, 4, 1, 2, 3).float()
+
+    @staticmethod
+    def from_ncdhw(t, halo=(0, 0, 0), c_pad=8, ld=None):
+        """Test/adapter helper: fp32 [N,C,D,H,W] (or [N,C,H,W]) torch tensor -> CLTensor (via torch copy)."""
+        if t.dim() == 4:
+            t = t.unsqueeze(2)
+        N, C_, D, H, W = t.shape
+        Cp = int(math.ceil(C_ / c_pad) * c_pad)
+        out = CLTensor(N, D, H, W, Cp, halo, device=t.device, ld=ld)
+        out.buf.zero_()
+        out.interior()[..., :C_] = t.permute(0, 2, 3, 4, 1).to(BF16)
+        return out
+
+
+def n_tiling(cout):
+    """(n_tile, Cout_pad) the conv kernel uses for `cout` output channels."""
+    c16 = (cout + 15) // 16 * 16
+    nt = (c16 + 255) // 256
+    n_tile = ((c16 + nt - 1) // nt + 15) // 16 * 16
+    return n_tile, n_tile * nt
+
+
+class PackedConv:
+    """Convolution weights in the kernel's layout: bf16 [Cout_pad][K_pad] K-major with K ordered
+    (kd,kh,kw,cin_pad); BatchNorm (eval) folded in fp32 before rounding; fp32 bias [Cout_pad]."""
+
+    def __init__(self, weight, bias=None, bn=None, stride=(1, 1, 1), pad_front=(0, 0, 0), cin_pad=None,
+                 device="cuda"):
+        w = weight.detach().float()
+        if w.dim() == 4:  # Conv2d [Cout,Cin,kh,kw] -> 3-D with kd=1
+            w = w.unsqueeze(2)
+        if w.dim() == 2:  # Linear [out,in] -> 1x1x1
+            w = w[:, :, None, None, None]
+        cout, cin, kd, kh, kw = w.shape
+        b = bias.detach().float() if bias is not None else torch.zeros(cout, device=w.device)
+        if bn is not None:
+            gamma, beta, mean, var, eps = bn
+            scale = gamma.detach().float() / torch.sqrt(var.detach().float() + eps)
+            w = w * scale.view(-1, 1, 1, 1, 1)
+            b = (b - mean.detach().float()) * scale + beta.detach().float()
+        self.cin = cin
+        self.cin_pad = int(cin_pad) if cin_pad is not None else (cin + 7) // 8 * 8
+        assert self.cin_pad >= cin and self.cin_pad % 8 == 0
+        self.cout = cout
+        self.n_tile, self.cout_pad = n_tiling(cout)
+        self.k = (kd, kh, kw)
+        self.stride = tuple(int(s) for s in stride)
+        self.pad_front = tuple(int(p) for p in pad_front)
+        k_real = kd * kh * kw * self.cin_pad
+        self.k_pad = (k_real + 63) // 64 * 64
+        wp = torch.zeros(self.cout_pad, kd, kh, kw, self.cin_pad, dtype=torch.float32, device=w.device)
+        wp[:cout, :, :, :, :cin] = w.permute(0, 2, 3, 4, 1)
+        wk = torch.zeros(self.cout_pad, self.k_pad, dtype=torch.float32, device=w.device)
+        wk[:, :k_real] = wp.reshape(self.cout_pad, k_real)
+        self.w = wk.to(BF16).to(device).contiguous()
+        bp = torch.zeros(self.cout_pad, dtype=torch.float32, device=w.device)
+        bp[:cout] = b
+        self.bias = bp.to(device).contiguous()
+
+    def out_extent(self, in_extent, pad_back=None):
+        """Output (D,H,W) for an input (D,H,W); pad_back defaults to pad_front (symmetric)."""
+        pb = self.pad_front if pad_back is None else pad_back
+        return tuple((i + pf + b - k) // s + 1
+                     for i, k, s, pf, b in zip(in_extent, self.k, self.stride, self.pad_front, pb))
+
+
+def conv_forward(x, pc, y, res=None, act=L.ACT_RELU, feed=L.FEED_AUTO, y_fp32=False, max_ctas=0, n_tile=0):
+    """y = act(conv(x, pc) + bias (+ res)).  x, y, res are CLTensor views."""
+    assert x.C == pc.cin_pad, f"input view has {x.C} channels, weights were packed for {pc.cin_pad}"
+    d = L.ConvDesc()
+    d.x, d.y = x.desc(), y.desc()
+    d.w, d.bias = pc.w.data_ptr(), pc.bias.data_ptr()
+    if res is not None:
+        assert (res.N, res.D, res.H, res.W, res.halo) == (y.N, y.D, y.H, y.W, y.halo) and res.C == y.C
+        d.res, d.res_ld, d.res_coff = res.buf.data_ptr(), res.ld, res.coff
+    d.Cout, d.Cout_pad, d.K_pad = pc.cout, pc.cout_pad, pc.k_pad
+    d.kd, d.kh, d.kw = pc.k
+    d.sd, d.sh, d.sw = pc.stride
+    d.pd, d.ph, d.pw = pc.pad_front
+    d.act, d.y_fp32, d.feed, d.n_tile, d.max_ctas = act, int(y_fp32), feed, n_tile, max_ctas
+    L.check(L.lib().tedspad_conv_forward(C.byref(d), _stream()), "tedspad_conv_forward")
+    return y
+
+
+def maxpool(x, y, k, s, pad_front=(0, 0, 0), zero_pad=False):
+    xd, yd = x.desc(), y.desc()
+    L.check(L.lib().tedspad_maxpool(C.byref(xd), C.byref(yd), *k, *s, *pad_front, int(zero_pad), _stream()),
+            "tedspad_maxpool")
+    return y
+
+
+def upsample2x(x, y):
+    xd, yd = x.desc(), y.desc()
+    L.check(L.lib().tedspad_upsample2x(C.byref(xd), C.byref(yd), _stream()), "tedspad_upsample2x")
+    return y
+
+
+def outconv_sigmoid(x, w, b, y, T, frames_out=None):
+    """w: fp32 [3, C] cuda, b: fp32 [3] cuda; y: encoder-input CLTensor [B,T,H,W,>=3]."""
+    xd, yd = x.desc(), y.desc()
+    fo = frames_out.data_ptr() if frames_out is not None else None
+    L.check(L.lib().tedspad_outconv_sigmoid(C.byref(xd), w.data_ptr(), b.data_ptr(), C.byref(yd), int(T), fo,
+                                            _stream()), "tedspad_outconv_sigmoid")
+    return y
+
+
+def avgpool_features(x, kd=0):
+    od = x.D - (kd if kd > 0 else x.D) + 1
+    out = torch.empty((x.N, od, x.C), device=x.buf.device, dtype=torch.float32)
+    xd = x.desc()
+    L.check(L.lib().tedspad_avgpool_features(C.byref(xd), int(kd), out.data_ptr(), _stream()),
+            "tedspad_avgpool_features")
+    return out
+
+
+def preprocess(frames_u8, desc_i32, crop_hw, y, resample=L.RESAMPLE_AA_FLOAT, frames_f32=None):
+    """frames_u8: cuda uint8 [F,Hs,Ws,3]; desc_i32: cuda int32 [n_out,4] = (src_frame, top, left, hflip)."""
+    _require_cuda(frames_u8, "preprocess")
+    F_, Hs, Ws, ch = frames_u8.shape
+    assert ch == 3 and frames_u8.dtype == torch.uint8 and frames_u8.is_contiguous()
+    assert desc_i32.dtype == torch.int32 and desc_i32.is_contiguous() and desc_i32.shape[1] == 4
+    yd = y.desc()
+    fo = frames_f32.data_ptr() if frames_f32 is not None else None
+    L.check(L.lib().tedspad_preprocess(frames_u8.data_ptr(), F_, Hs, Ws, desc_i32.data_ptr(), desc_i32.shape[0],
+                                       int(crop_hw[0]), int(crop_hw[1]), C.byref(yd), int(resample), fo, _stream()),
+            "tedspad_preprocess")
+    return y
+
+
+def nchw_to_cl(x_f32, y):
+    """fp32 [N,C,H,W] / [N,C,D,H,W] cuda tensor -> channels-last bf16 view y (extra channels zeroed)."""
+    _require_cuda(x_f32, "nchw_to_cl")
+    x_f32 = x_f32.contiguous().float()
+    yd = y.desc()
+    L.check(L.lib().tedspad_nchw_to_cl(x_f32.data_ptr(), int(x_f32.shape[1]), C.byref(yd), _stream()),
+            "tedspad_nchw_to_cl")
+    return y

@@ -1,0 +1,161 @@
+"""CPU emulation of the C-ABI operators' *addressing* (test infrastructure only).
+
+Used by the CPU test-suite to validate the test harness, the weight packing and the padded-flat
+layout arithmetic without a GPU: each function restates what the CUDA kernel does index-for-index
+(flat tap offsets on the haloed buffer, im2col gather with front pads, halo zeroing), in fp32 torch
+on bf16-rounded data.  Never imported by the product package.
+"""
+import torch
+
+from tedspad_b200 import _lib as L
+
+
+def _act(v, act):
+    if act == L.ACT_RELU:
+        return torch.relu(v)
+    if act == L.ACT_SIGMOID:
+        return torch.sigmoid(v)
+    return v
+
+
+def conv_forward(x, pc, y, res=None, act=L.ACT_RELU, feed=L.FEED_AUTO, y_fp32=False, max_ctas=0, n_tile=0):
+    kd, kh, kw = pc.k
+    ntaps = kd * kh * kw
+    W2 = pc.w.float()[:pc.cout]  # [Cout, K_pad]
+    bias = pc.bias[:pc.cout]
+    flat_legal = (pc.stride == (1, 1, 1) and all(k % 2 == 1 for k in pc.k) and pc.pad_front == tuple(k // 2 for k in pc.k)
+                  and x.C % 64 == 0 and (x.D, x.H, x.W) == (y.D, y.H, y.W) and x.halo == y.halo
+                  and all(h >= p for h, p in zip(x.halo, pc.pad_front)) and pc.k_pad == ntaps * x.C)
+    if feed == L.FEED_AUTO:
+        feed = L.FEED_FLAT_TMA if flat_legal else L.FEED_GATHER
+    if feed == L.FEED_FLAT_TMA:
+        assert flat_legal
+        Dp, Hp, Wp = x.D + 2 * x.pd, x.H + 2 * x.ph, x.W + 2 * x.pw
+        M = x.N * Dp * Hp * Wp
+        xf = x.buf.reshape(M, x.ld)[:, x.coff:x.coff + x.C].float()
+        acc = torch.zeros(M, pc.cout)
+        t = 0
+        for a in range(kd):
+            for b in range(kh):
+                for c in range(kw):
+                    off = ((a - pc.pad_front[0]) * Hp + (b - pc.pad_front[1])) * Wp + (c - pc.pad_front[2])
+                    rows = torch.arange(M) + off
+                    ok = (rows >= 0) & (rows < M)
+                    A = torch.zeros(M, x.C)
+                    A[ok] = xf[rows[ok]]
+                    acc += A @ W2[:, t * x.C:(t + 1) * x.C].T
+                    t += 1
+        acc = acc + bias
+        if res is not None:
+            acc = acc + res.buf.reshape(M, res.ld)[:, res.coff:res.coff + res.C].float()
+        acc = _act(acc, act)
+        m = torch.arange(M)
+        wq, hq, dq = m % Wp, (m // Wp) % Hp, (m // (Wp * Hp)) % Dp
+        interior = (wq >= y.pw) & (wq < y.pw + y.W) & (hq >= y.ph) & (hq < y.ph + y.H) & (dq >= y.pd) & (dq < y.pd + y.D)
+        acc[~interior] = 0
+        y.buf.reshape(M, y.ld)[:, y.coff:y.coff + y.C] = acc.to(y.buf.dtype)
+        return y
+    # gather
+    N, OD, OH, OW = y.N, y.D, y.H, y.W
+    xi = x.interior().float()  # [N,D,H,W,C]
+    cols = torch.zeros(N, OD, OH, OW, pc.k_pad)
+    t = 0
+    od = torch.arange(OD) * pc.stride[0] - pc.pad_front[0]
+    oh = torch.arange(OH) * pc.stride[1] - pc.pad_front[1]
+    ow = torch.arange(OW) * pc.stride[2] - pc.pad_front[2]
+    for a in range(kd):
+        for b in range(kh):
+            for c in range(kw):
+                idd, ihh, iww = od + a, oh + b, ow + c
+                vd, vh, vw = (idd >= 0) & (idd < x.D), (ihh >= 0) & (ihh < x.H), (iww >= 0) & (iww < x.W)
+                patch = torch.zeros(N, OD, OH, OW, x.C)
+                sub = xi[:, idd[vd]][:, :, ihh[vh]][:, :, :, iww[vw]]
+                tmp = torch.zeros(N, int(vd.sum()), int(vh.sum()), OW, x.C)
+                tmp[:, :, :, vw] = sub
+                tmp2 = torch.zeros(N, int(vd.sum()), OH, OW, x.C)
+                tmp2[:, :, vh] = tmp
+                patch[:, vd] = tmp2
+                cols[..., t * x.C:(t + 1) * x.C] = patch
+                t += 1
+    acc = cols.reshape(-1, pc.k_pad) @ W2.T + bias
+    acc = acc.reshape(N, OD, OH, OW, pc.cout)
+    if res is not None:
+        acc = acc + res.interior().float()
+    acc = _act(acc, act)
+    y.interior()[...] = acc.to(y.buf.dtype)
+    return y
+
+
+def maxpool(x, y, k, s, pad_front=(0, 0, 0), zero_pad=False):
+    import torch.nn.functional as F
+    xi = x.interior().float().permute(0, 4, 1, 2, 3)
+    need = [(o - 1) * st + kk - pf - i for o, st, kk, pf, i in zip((y.D, y.H, y.W), s, k, pad_front, (x.D, x.H, x.W))]
+    pb = [max(n, 0) for n in need]
+    xp = F.pad(xi, (pad_front[2], pb[2], pad_front[1], pb[1], pad_front[0], pb[0]),
+               value=0.0 if zero_pad else float("-inf"))
+    out = F.max_pool3d(xp, k, s)[:, :, :y.D, :y.H, :y.W]
+    y.interior()[...] = out.permute(0, 2, 3, 4, 1).to(y.buf.dtype)
+    return y
+
+
+def upsample2x(x, y):
+    import torch.nn.functional as F
+    xi = x.interior().float()[:, 0].permute(0, 3, 1, 2)
+    up = F.interpolate(xi, scale_factor=2, mode="bilinear", align_corners=True)
+    dy, dx = y.H - up.shape[2], y.W - up.shape[3]
+    up = F.pad(up, [dx // 2, dx - dx // 2, dy // 2, dy - dy // 2])
+    y.interior()[:, 0] = up.permute(0, 2, 3, 1).to(y.buf.dtype)
+    return y
+
+
+def outconv_sigmoid(x, w, b, y, T, frames_out=None):
+    xi = x.interior().float()[:, 0]  # [F,H,W,C]
+    v = torch.sigmoid(xi @ w.T + b)  # [F,H,W,3]
+    Fr, H, W, _ = v.shape
+    B = Fr // T
+    fr = v.permute(0, 3, 1, 2).contiguous()  # [F,3,H,W]
+    if frames_out is not None:
+        frames_out.copy_(fr)
+    enc = fr.reshape(B, T, 3, H, W).reshape(B, 3, T, H, W)
+    y.interior()[..., :3] = enc.permute(0, 2, 3, 4, 1).to(y.buf.dtype)
+    return y
+
+
+def avgpool_features(x, kd=0):
+    xi = x.interior().float()
+    kd = kd if kd > 0 else x.D
+    outs = [xi[:, d:d + kd].mean(dim=(1, 2, 3)) for d in range(x.D - kd + 1)]
+    return torch.stack(outs, 1)
+
+
+def nchw_to_cl(x_f32, y):
+    if x_f32.dim() == 4:
+        x_f32 = x_f32.unsqueeze(2)
+    y.interior()[...] = 0
+    y.interior()[..., :x_f32.shape[1]] = x_f32.permute(0, 2, 3, 4, 1).to(y.buf.dtype)
+    return y
+
+
+def preprocess(frames_u8, desc_i32, crop_hw, y, resample=L.RESAMPLE_AA_FLOAT, frames_f32=None):
+    import numpy as np
+    from oracle import preprocess as P
+    fr = frames_u8.cpu().numpy()
+    ch, cw = crop_hw
+    outs = []
+    for s, t, l, fl in desc_i32.cpu().tolist():
+        if s < 0:
+            outs.append(np.zeros((3, y.H, y.W), np.float32))
+            continue
+        img = fr[s][:, ::-1] if fl else fr[s]
+        crop = img[t:t + ch, l:l + cw]
+        if resample == L.RESAMPLE_PIL_U8:
+            o = P.resize_pil_u8(crop, y.H, y.W).astype(np.float32).transpose(2, 0, 1) / np.float32(255)
+        else:
+            o = P.resize_aa(crop.astype(np.float32).transpose(2, 0, 1) / np.float32(255), y.H, y.W)
+        outs.append(o)
+    o = torch.from_numpy(np.stack(outs))
+    if frames_f32 is not None:
+        frames_f32.copy_(o)
+    y.interior()[...] = 0
+    y.interior()[:, 0, :, :, :3] = o.permute(0, 2, 3, 1).to(y.buf.dtype)
+    return y

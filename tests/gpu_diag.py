@@ -1,0 +1,388 @@
+"""GPU diagnostic battery (not a pytest file): runs every C-ABI operator against the matching
+torch fp32 op on bf16-rounded operands and prints detailed error statistics, continuing past
+failures.  Usage on the GPU box:
+
+    python tests/gpu_diag.py <group> [...]      groups: flat gather ops prep perf
+
+Each group should be run in its own process (a trapped kernel poisons the CUDA context).
+"""
+import os
+import sys
+import time
+import traceback
+
+import torch
+import torch.nn.functional as F
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from tedspad_b200 import ops, _lib as L  # noqa: E402
+
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+DEV = "cuda"
+RESULTS = []
+
+
+def bf(t):
+    return t.to(torch.bfloat16).float()
+
+
+def report(name, got, ref, tol_rel=2e-2, extra=""):
+    got, ref = got.float(), ref.float()
+    err = (got - ref).abs()
+    scale = ref.abs().max().item() + 1e-12
+    mx = err.max().item()
+    ok = bool(torch.isfinite(got).all()) and mx <= tol_rel * scale
+    RESULTS.append((name, ok))
+    print(f"[{'PASS' if ok else 'FAIL'}] {name}: max_abs_err={mx:.4e} ref_max={scale:.4e} rel={mx / scale:.3e} "
+          f"mean_err={err.mean().item():.3e} {extra}", flush=True)
+    if not ok:
+        bad = err > tol_rel * scale
+        print(f"       bad elements: {int(bad.sum())}/{bad.numel()}  nan={int(torch.isnan(got).sum())}")
+        idx = bad.nonzero()[:8]
+        for i in idx:
+            i = tuple(int(v) for v in i)
+            print(f"       at {i}: got={got[i].item():.5f} ref={ref[i].item():.5f}")
+        if got.dim() == 5:  # N C D H W: error by channel mod 16, by w mod 8
+            e = err.amax(dim=(0, 2, 3))  # C, W
+            print("       max err by channel%16:", [f"{e[c::16].max().item():.2e}" for c in range(min(16, e.shape[0]))])
+            ew = err.amax(dim=(0, 1, 2, 3))
+            print("       max err by w (first 24):", [f"{v:.1e}" for v in ew[:24].tolist()])
+            eh = err.amax(dim=(0, 1, 2, 4))
+            print("       max err by h (first 24):", [f"{v:.1e}" for v in eh[:24].tolist()])
+    return ok
+
+
+def conv_ref(x, w, b, stride, pad6, res=None, act="relu"):
+    """x [N,C,D,H,W] fp32 (already bf16-rounded), w [Cout,Cin,kd,kh,kw]; pad6 = F.pad order (wl,wr,hl,hr,dl,dr)."""
+    y = F.conv3d(F.pad(x, pad6), w, b, stride=stride)
+    if res is not None:
+        y = y + res
+    if act == "relu":
+        y = torch.relu(y)
+    elif act == "sigmoid":
+        y = torch.sigmoid(y)
+    return y
+
+
+def run_conv_case(name, N, dhw, cin, cout, k, stride=(1, 1, 1), pad_f=None, pad_b=None, halo=(0, 0, 0), feed=L.FEED_AUTO,
+                  use_res=False, act="relu", cin_real=None, in_ld=None, in_coff=0, out_ld=None, out_coff=0,
+                  y_fp32=False, max_ctas=0, seed=0, bn=True):
+    try:
+        g = torch.Generator(device="cpu").manual_seed(seed)
+        D, H, W = dhw
+        cin_real = cin_real or cin
+        pad_f = pad_f if pad_f is not None else tuple(kk // 2 for kk in k)
+        pad_b = pad_b if pad_b is not None else pad_f
+        x = torch.randn(N, cin_real, D, H, W, generator=g).to(DEV)
+        w = (torch.randn(cout, cin_real, *k, generator=g) / (cin_real * k[0] * k[1] * k[2]) ** 0.5).to(DEV)
+        b = (torch.rand(cout, generator=g) - 0.5).to(DEV)
+        bnp = None
+        if bn:
+            bnp = ((torch.rand(cout, generator=g) + 0.5).to(DEV), (torch.rand(cout, generator=g) - 0.5).to(DEV),
+                   (torch.rand(cout, generator=g) - 0.5).to(DEV), (torch.rand(cout, generator=g) + 0.5).to(DEV), 1e-3)
+        pc = ops.PackedConv(w, b, bnp, stride=stride, pad_front=pad_f, cin_pad=cin, device=DEV)
+        od, oh, ow = pc.out_extent((D, H, W), pad_b)
+        # input buffer (possibly a channel slice of a wider buffer, filled with junk elsewhere)
+        ld_in = in_ld or cin
+        xb = ops.CLTensor(N, D, H, W, ld_in, halo, device=DEV)
+        if ld_in != cin:
+            xb.interior()[...] = 7.0  # junk in the channels outside the view must not leak
+        xv = xb.slice(in_coff, cin)
+        xv.interior()[..., :cin_real] = x.permute(0, 2, 3, 4, 1).to(torch.bfloat16)
+        if cin_real < cin:
+            xv.interior()[..., cin_real:] = 0
+        out_halo = halo if (od, oh, ow) == (D, H, W) else (0, 0, 0)
+        ld_out = out_ld or cout
+        yb = ops.CLTensor(N, od, oh, ow, ld_out, out_halo, device=DEV, dtype=torch.float32 if y_fp32 else torch.bfloat16)
+        yb.buf.fill_(3.0)  # poison: halo must come back as zeros in FLAT feed, untouched in GATHER feed
+        yv = yb.slice(out_coff, cout)
+        resv, res_t = None, None
+        if use_res:
+            res_t = torch.randn(N, cout, od, oh, ow, generator=g).to(DEV)
+            rb = ops.CLTensor(N, od, oh, ow, cout, out_halo, device=DEV)
+            rb.interior()[...] = res_t.permute(0, 2, 3, 4, 1).to(torch.bfloat16)
+            resv = rb
+        acts = {"relu": L.ACT_RELU, "none": L.ACT_NONE, "sigmoid": L.ACT_SIGMOID}
+        ops.conv_forward(xv, pc, yv, res=resv, act=acts[act], feed=feed, y_fp32=y_fp32, max_ctas=max_ctas,
+                         n_tile=pc.n_tile)
+        torch.cuda.synchronize()
+        # reference from the packed (bf16, BN-folded) weights, fp32 math
+        kd, kh, kw = k
+        wq = pc.w[:cout, :kd * kh * kw * cin].float().reshape(cout, kd, kh, kw, cin)[..., :cin_real].permute(0, 4, 1, 2, 3)
+        pad6 = (pad_f[2], pad_b[2], pad_f[1], pad_b[1], pad_f[0], pad_b[0])
+        ref = conv_ref(bf(x), wq.contiguous(), pc.bias[:cout], stride, pad6, bf(res_t) if use_res else None, act)
+        got = yv.to_ncdhw() if not y_fp32 else yv.interior().permute(0, 4, 1, 2, 3)
+        ok = report(name, got, ref, extra=f"feed={'flat' if (feed == L.FEED_FLAT_TMA) else ('gather' if feed == L.FEED_GATHER else 'auto')} n_tile={pc.n_tile} M={N * od * oh * ow}")
+        # halo check
+        if sum(out_halo) > 0 and (feed != L.FEED_GATHER):
+            full = yb.buf[..., out_coff:out_coff + cout].float().clone()
+            full[:, out_halo[0]:out_halo[0] + od, out_halo[1]:out_halo[1] + oh, out_halo[2]:out_halo[2] + ow] = 0
+            hz = full.abs().max().item()
+            okh = hz == 0.0
+            RESULTS.append((name + ":halo", okh))
+            print(f"[{'PASS' if okh else 'FAIL'}] {name}: halo max |v| = {hz}")
+        if ld_out != cout:
+            other = torch.ones(ld_out, dtype=torch.bool)
+            other[out_coff:out_coff + cout] = False
+            leak = (yb.interior()[..., other.to(DEV)].float() - 3.0).abs().max().item()
+            okl = leak == 0.0
+            RESULTS.append((name + ":slice", okl))
+            print(f"[{'PASS' if okl else 'FAIL'}] {name}: writes outside the channel slice: {leak}")
+        return ok
+    except Exception:
+        RESULTS.append((name, False))
+        print(f"[FAIL] {name}: EXCEPTION\n{traceback.format_exc()}", flush=True)
+        return False
+
+
+def group_flat():
+    FL = L.FEED_FLAT_TMA
+    run_conv_case("F1 2d 64->64 3x3", 2, (1, 12, 20), 64, 64, (1, 3, 3), halo=(0, 1, 1), feed=FL)
+    run_conv_case("F1b 2d 64->64 3x3 1 cta", 2, (1, 12, 20), 64, 64, (1, 3, 3), halo=(0, 1, 1), feed=FL, max_ctas=1)
+    run_conv_case("F2 2d 128->128 3x3", 3, (1, 16, 16), 128, 128, (1, 3, 3), halo=(0, 1, 1), feed=FL)
+    run_conv_case("F3 2d 64->512 3x3 (2 n-tiles)", 2, (1, 12, 20), 64, 512, (1, 3, 3), halo=(0, 1, 1), feed=FL)
+    run_conv_case("F4 2d 64->32 1x1", 2, (1, 12, 20), 64, 32, (1, 1, 1), halo=(0, 1, 1), feed=FL)
+    run_conv_case("F5 2d slices+res", 2, (1, 14, 14), 64, 128, (1, 3, 3), halo=(0, 1, 1), feed=FL, use_res=True,
+                  in_ld=192, in_coff=64, out_ld=256, out_coff=128)
+    run_conv_case("F6 2d 256->256 56x56 8 ctas", 4, (1, 56, 56), 256, 256, (1, 3, 3), halo=(0, 1, 1), feed=FL, max_ctas=8)
+    run_conv_case("F7 3d 64->64 3x3x3", 1, (4, 6, 6), 64, 64, (3, 3, 3), halo=(1, 1, 1), feed=FL)
+    run_conv_case("F8 2d 512->512 14x14", 16, (1, 14, 14), 512, 512, (1, 3, 3), halo=(0, 1, 1), feed=FL)
+    run_conv_case("F9 2d 1024->512 28x28 no-bn sigmoid", 2, (1, 28, 28), 1024, 512, (1, 3, 3), halo=(0, 1, 1), feed=FL,
+                  act="sigmoid", bn=False)
+    run_conv_case("F10 2d 64->16 3x3 (n_tile 16)", 2, (1, 12, 20), 64, 16, (1, 3, 3), halo=(0, 1, 1), feed=FL)
+
+
+def group_gather():
+    G = L.FEED_GATHER
+    run_conv_case("G1 2d 3(8)->64 3x3", 2, (1, 20, 20), 8, 64, (1, 3, 3), feed=G, cin_real=3)
+    run_conv_case("G1b same conv as F1 via gather", 2, (1, 12, 20), 64, 64, (1, 3, 3), feed=G)
+    run_conv_case("G1c gather into haloed out", 2, (1, 12, 20), 64, 64, (1, 3, 3), halo=(0, 1, 1), feed=G)
+    run_conv_case("G2 3d stem 7x7x7 s2 TF-SAME", 1, (8, 20, 20), 8, 64, (7, 7, 7), stride=(2, 2, 2), pad_f=(2, 2, 2),
+                  pad_b=(3, 3, 3), feed=G, cin_real=3)
+    run_conv_case("G3 (1,3,3) s(1,2,2) odd", 2, (2, 11, 11), 128, 128, (1, 3, 3), stride=(1, 2, 2), pad_f=(0, 1, 1), feed=G)
+    run_conv_case("G4 1x1x1 s(1,2,2) 256->512", 2, (2, 11, 11), 256, 512, (1, 1, 1), stride=(1, 2, 2), pad_f=(0, 0, 0), feed=G)
+    run_conv_case("G5 3x3x3 16->32", 2, (4, 7, 7), 16, 32, (3, 3, 3), feed=G)
+    run_conv_case("G5b 3x3x3 24->48 (Cout 48 -> n_tile 48)", 2, (4, 7, 7), 24, 48, (3, 3, 3), feed=G)
+    run_conv_case("G5c 1x1x1 192->24 (n_tile 32)", 2, (4, 7, 7), 192, 24, (1, 1, 1), feed=G)
+    run_conv_case("G6 linear 512->102 fp32", 3, (1, 1, 1), 512, 102, (1, 1, 1), feed=G, y_fp32=True, act="none", bn=False)
+    run_conv_case("G7 (3,1,1) res relu", 2, (4, 7, 7), 64, 256, (3, 1, 1), pad_f=(1, 0, 0), feed=G, use_res=True)
+    run_conv_case("G8 r3d 3x3x3 s2 64->128", 2, (8, 14, 14), 64, 128, (3, 3, 3), stride=(2, 2, 2), pad_f=(1, 1, 1), feed=G)
+    run_conv_case("G9 many tiles 4 ctas", 4, (4, 28, 28), 64, 192, (3, 3, 3), feed=G, max_ctas=4)
+    run_conv_case("G10 slice out + 832 in", 2, (2, 7, 7), 832, 384, (1, 1, 1), feed=G, out_ld=1024, out_coff=0)
+    run_conv_case("G11 auto feed picks flat", 2, (1, 12, 20), 64, 64, (1, 3, 3), halo=(0, 1, 1), feed=L.FEED_AUTO)
+
+
+def group_ops():
+    g = torch.Generator(device="cpu").manual_seed(1)
+    # max pools
+    cases = [
+        ("maxpool2d 2x2", (4, 64, 1, 12, 20), (1, 2, 2), (1, 2, 2), (0, 0, 0), (0, 0, 0), False),
+        ("maxpool (1,3,3)s(1,2,2) SAME", (2, 64, 4, 14, 14), (1, 3, 3), (1, 2, 2), (0, 0, 0), (0, 1, 1), True),
+        ("maxpool 3s2 SAME", (2, 32, 8, 14, 14), (3, 3, 3), (2, 2, 2), (0, 0, 0), (1, 1, 1), True),
+        ("maxpool 3s1 SAME", (2, 32, 4, 7, 7), (3, 3, 3), (1, 1, 1), (1, 1, 1), (1, 1, 1), True),
+        ("maxpool 2s2", (2, 32, 4, 14, 14), (2, 2, 2), (2, 2, 2), (0, 0, 0), (0, 0, 0), True),
+        ("maxpool (2,3,3)s2 p0 floor", (2, 64, 8, 23, 23), (2, 3, 3), (2, 2, 2), (0, 0, 0), (0, 0, 0), False),
+        ("maxpool (2,1,1)", (2, 256, 4, 9, 9), (2, 1, 1), (2, 1, 1), (0, 0, 0), (0, 0, 0), False),
+    ]
+    for name, shp, k, s, pf, pb, zp in cases:
+        try:
+            x = torch.randn(*shp, generator=g).to(DEV)
+            if zp:
+                x = x - 1.0  # mostly negative so zero padding matters
+            xc = ops.CLTensor.from_ncdhw(x, halo=(0, 1, 1))
+            xpad = F.pad(bf(x), (pf[2], pb[2], pf[1], pb[1], pf[0], pb[0]), value=0.0 if zp else float("-inf"))
+            ref = F.max_pool3d(xpad, k, s)
+            yc = ops.CLTensor(shp[0], ref.shape[2], ref.shape[3], ref.shape[4], shp[1], device=DEV)
+            ops.maxpool(xc, yc, k, s, pf, zero_pad=zp)
+            report(name, yc.to_ncdhw(), ref, tol_rel=0)
+        except Exception:
+            RESULTS.append((name, False))
+            print(f"[FAIL] {name}: EXCEPTION\n{traceback.format_exc()}", flush=True)
+    # upsample x2 align_corners into a concat slice
+    for name, (n, c, h, w), (th, tw) in [("upsample 7->14", (3, 64, 7, 7), (14, 14)),
+                                          ("upsample 6x10 -> 13x21 (F.pad)", (2, 128, 6, 10), (13, 21))]:
+        try:
+            x = torch.randn(n, c, h, w, generator=g).to(DEV)
+            xc = ops.CLTensor.from_ncdhw(x, halo=(0, 1, 1))
+            cat = ops.CLTensor(n, 1, th, tw, 2 * c, (0, 1, 1), device=DEV)
+            cat.buf.fill_(5.0)
+            ops.upsample2x(xc, cat.slice(c, c))
+            up = F.interpolate(bf(x), scale_factor=2, mode="bilinear", align_corners=True)
+            dy, dx = th - up.shape[2], tw - up.shape[3]
+            ref = F.pad(up, [dx // 2, dx - dx // 2, dy // 2, dy - dy // 2]).unsqueeze(2)
+            report(name, cat.slice(c, c).to_ncdhw(), ref, tol_rel=1e-2)
+            okk = bool((cat.slice(0, c).interior().float() == 5.0).all())
+            RESULTS.append((name + ":slice", okk))
+            print(f"[{'PASS' if okk else 'FAIL'}] {name}: other slice untouched")
+        except Exception:
+            RESULTS.append((name, False))
+            print(f"[FAIL] {name}: EXCEPTION\n{traceback.format_exc()}", flush=True)
+    # outconv + sigmoid + scatter
+    try:
+        B, T, H, W, Cc = 2, 16, 10, 12, 64
+        x = torch.randn(B * T, Cc, H, W, generator=g).to(DEV)
+        w = (torch.randn(3, Cc, generator=g) / 8).to(DEV)
+        b = torch.randn(3, generator=g).to(DEV)
+        xc = ops.CLTensor.from_ncdhw(x, halo=(0, 1, 1))
+        enc = ops.CLTensor(B, T, H, W, 8, device=DEV)
+        enc.buf.zero_()
+        fr = torch.empty(B * T, 3, H, W, device=DEV)
+        ops.outconv_sigmoid(xc, w, b, enc, T, fr)
+        ref_fr = torch.sigmoid(F.conv2d(bf(x), w[:, :, None, None], b))
+        report("outconv frames fp32", fr, ref_fr, tol_rel=1e-5)
+        ref_enc = ref_fr.reshape(B, T, 3, H, W).reshape(B, 3, T, H, W)  # dali_extraction.py:171-173 raw reshape
+        report("outconv scatter (raw reshape glue)", enc.to_ncdhw()[:, :3], ref_enc, tol_rel=5e-3)
+        okz = bool((enc.interior()[..., 3:] == 0).all())
+        RESULTS.append(("outconv pad channels zero", okz))
+        print(f"[{'PASS' if okz else 'FAIL'}] outconv pad channels stay zero")
+    except Exception:
+        RESULTS.append(("outconv", False))
+        print(f"[FAIL] outconv: EXCEPTION\n{traceback.format_exc()}", flush=True)
+    # avgpool features
+    try:
+        x = torch.randn(3, 1024, 2, 7, 7, generator=g).to(DEV)
+        xc = ops.CLTensor.from_ncdhw(x)
+        out = ops.avgpool_features(xc, 2)
+        ref = F.avg_pool3d(bf(x), (2, 7, 7), 1).reshape(3, 1024, 1).permute(0, 2, 1)
+        report("avgpool (2,7,7)", out, ref, tol_rel=1e-5)
+        x = torch.randn(2, 64, 4, 7, 7, generator=g).to(DEV)
+        out = ops.avgpool_features(ops.CLTensor.from_ncdhw(x), 2)
+        ref = F.avg_pool3d(bf(x), (2, 7, 7), 1).reshape(2, 64, 3).permute(0, 2, 1)
+        report("avgpool sliding D=4", out, ref, tol_rel=1e-5)
+        out = ops.avgpool_features(ops.CLTensor.from_ncdhw(x), 0)
+        report("avgpool global", out, bf(x).mean(dim=(2, 3, 4)).unsqueeze(1), tol_rel=1e-5)
+    except Exception:
+        RESULTS.append(("avgpool", False))
+        print(f"[FAIL] avgpool: EXCEPTION\n{traceback.format_exc()}", flush=True)
+    # nchw -> channels-last
+    try:
+        x = torch.rand(4, 3, 20, 24, generator=g).to(DEV)
+        y = ops.CLTensor(4, 1, 20, 24, 8, device=DEV)
+        y.buf.fill_(9.0)
+        ops.nchw_to_cl(x, y)
+        report("nchw_to_cl C=3->8", y.to_ncdhw()[:, :3, 0], bf(x), tol_rel=0)
+        x5 = torch.rand(2, 3, 4, 6, 10, generator=g).to(DEV)
+        y5 = ops.CLTensor(2, 4, 6, 10, 8, device=DEV)
+        ops.nchw_to_cl(x5, y5)
+        report("nchw_to_cl 5-D", y5.to_ncdhw()[:, :3], bf(x5), tol_rel=0)
+        okz = bool((y.interior()[..., 3:] == 0).all())
+        RESULTS.append(("nchw_to_cl zero pad", okz))
+    except Exception:
+        RESULTS.append(("nchw_to_cl", False))
+        print(f"[FAIL] nchw_to_cl: EXCEPTION\n{traceback.format_exc()}", flush=True)
+
+
+def group_prep():
+    import numpy as np
+    import torchvision.transforms.functional as TF
+    from PIL import Image
+    g = torch.Generator(device="cpu").manual_seed(2)
+    # DALI path: 240x320 -> crop 192x256 -> 224x224, antialias float
+    try:
+        Fr, Hs, Ws = 5, 240, 320
+        frames = torch.randint(0, 256, (Fr, Hs, Ws, 3), generator=g, dtype=torch.uint8)
+        ch, cw = int(Hs * 0.8), int(Ws * 0.8)
+        top, left = int(round((Hs - ch) / 2.0)), int(round((Ws - cw) / 2.0))
+        desc = torch.tensor([[0, top, left, 0], [3, top, left, 0], [-1, top, left, 0], [4, 0, 0, 0], [4, 0, 0, 1]],
+                            dtype=torch.int32)
+        y = ops.CLTensor(5, 1, 224, 224, 8, device=DEV)
+        f32 = torch.empty(5, 3, 224, 224, device=DEV)
+        ops.preprocess(frames.to(DEV), desc.to(DEV), (ch, cw), y, L.RESAMPLE_AA_FLOAT, f32)
+        v = frames.permute(0, 3, 1, 2).float() / 255.0
+        refs = []
+        for s, t, l, fl in desc.tolist():
+            if s < 0:
+                refs.append(torch.zeros(3, 224, 224))
+                continue
+            img = v[s]
+            if fl:
+                img = img.flip(-1)
+            img = img[:, t:t + ch, l:l + cw]
+            refs.append(TF.resize(img, (224, 224), antialias=True))
+        ref = torch.stack(refs).to(DEV)
+        report("preprocess AA float fp32", f32, ref, tol_rel=3e-5)
+        report("preprocess AA bf16 layout", y.to_ncdhw()[:, :3, 0], bf(ref), tol_rel=8e-3)
+        cc = TF.center_crop(v[0:1], (ch, cw))
+        ok = torch.equal(cc, v[0:1, :, top:top + ch, left:left + cw])
+        RESULTS.append(("center_crop offsets", ok))
+        print(f"[{'PASS' if ok else 'FAIL'}] center_crop offset formula")
+    except Exception:
+        RESULTS.append(("preprocess AA", False))
+        print(f"[FAIL] preprocess AA: EXCEPTION\n{traceback.format_exc()}", flush=True)
+    # ShanghaiTech path: 480x856 -> crop 384x384 -> PIL bilinear uint8
+    try:
+        Fr, Hs, Ws = 2, 480, 856
+        frames = torch.randint(0, 256, (Fr, Hs, Ws, 3), generator=g, dtype=torch.uint8)
+        # add smooth content too
+        yy, xx = torch.meshgrid(torch.arange(Hs), torch.arange(Ws), indexing="ij")
+        frames[1] = torch.stack([(yy * 255 // Hs), (xx * 255 // Ws), ((yy + xx) % 256)], -1).to(torch.uint8)
+        ch = cw = int(Hs * 0.8)
+        top, left = int(round((Hs - ch) / 2.0)), int(round((Ws - cw) / 2.0))
+        desc = torch.tensor([[0, top, left, 0], [1, top, left, 0]], dtype=torch.int32)
+        y = ops.CLTensor(2, 1, 224, 224, 8, device=DEV)
+        f32 = torch.empty(2, 3, 224, 224, device=DEV)
+        ops.preprocess(frames.to(DEV), desc.to(DEV), (ch, cw), y, L.RESAMPLE_PIL_U8, f32)
+        refs = []
+        for i in range(2):
+            im = TF.to_pil_image(frames[i].numpy())
+            im = TF.center_crop(im, (ch, cw))
+            im = TF.resize(im, (224, 224), antialias=True)
+            refs.append(TF.to_tensor(im))
+        ref = torch.stack(refs).to(DEV)
+        d = ((f32 - ref).abs() * 255).round()
+        print(f"       PIL emulation: exact={float((d == 0).float().mean()):.6f} max_lsb={int(d.max())}")
+        report("preprocess PIL u8 (bit-exact)", f32, ref, tol_rel=0)
+    except Exception:
+        RESULTS.append(("preprocess PIL", False))
+        print(f"[FAIL] preprocess PIL: EXCEPTION\n{traceback.format_exc()}", flush=True)
+
+
+def time_conv(name, N, hw, cin, cout, k=(1, 3, 3), iters=10):
+    try:
+        H, W = hw
+        halo = (0, 1, 1)
+        x = ops.CLTensor(N, 1, H, W, cin, halo, device=DEV)
+        x.interior().normal_()
+        wt = torch.randn(cout, cin, *k, device=DEV) / (cin * 9) ** 0.5
+        pc = ops.PackedConv(wt, None, None, pad_front=tuple(kk // 2 for kk in k), cin_pad=cin, device=DEV)
+        y = ops.CLTensor(N, 1, H, W, cout, halo, device=DEV)
+        for _ in range(3):
+            ops.conv_forward(x, pc, y, feed=L.FEED_FLAT_TMA, n_tile=pc.n_tile)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            ops.conv_forward(x, pc, y, feed=L.FEED_FLAT_TMA, n_tile=pc.n_tile)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        flops = 2.0 * N * H * W * cin * cout * k[0] * k[1] * k[2]
+        print(f"[PERF] {name}: {ms:.3f} ms  {flops / ms / 1e9:.1f} TFLOP/s (algorithmic)  n_tile={pc.n_tile}", flush=True)
+    except Exception:
+        print(f"[FAIL] perf {name}: EXCEPTION\n{traceback.format_exc()}", flush=True)
+
+
+def group_perf():
+    time_conv("unet 64->64 @224 x16", 16, (224, 224), 64, 64)
+    time_conv("unet 128->64 @224 x16", 16, (224, 224), 128, 64)
+    time_conv("unet 128->128 @112 x16", 16, (112, 112), 128, 128)
+    time_conv("unet 256->256 @56 x16", 16, (56, 56), 256, 256)
+    time_conv("unet 512->512 @28 x16", 16, (28, 28), 512, 512)
+    time_conv("unet 1024->512 @28 x16", 16, (28, 28), 1024, 512)
+    time_conv("unet 512->512 @14 x16", 16, (14, 14), 512, 512)
+    time_conv("unet 256->256 @56 x64", 64, (56, 56), 256, 256)
+    time_conv("unet 512->512 @28 x64", 64, (28, 28), 512, 512)
+
+
+if __name__ == "__main__":
+    groups = sys.argv[1:] or ["flat", "gather", "ops", "prep"]
+    t0 = time.time()
+    print(f"device: {torch.cuda.get_device_name(0)}  sms={L.lib().tedspad_num_sms()}", flush=True)
+    for gname in groups:
+        print(f"===== group {gname} =====", flush=True)
+        globals()["group_" + gname]()
+    torch.cuda.synchronize()
+    nfail = sum(1 for _, ok in RESULTS if not ok)
+    print(f"===== {len(RESULTS) - nfail} passed, {nfail} failed, {time.time() - t0:.1f}s =====", flush=True)
+    sys.exit(1 if nfail else 0)
