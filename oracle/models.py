@@ -1,0 +1,374 @@
+"""ORACLE (test infrastructure, never imported by the product package).
+
+Functional fp32 restatement of the reference models on the feature-extraction path, operating on a
+plain `state_dict` (name -> tensor) whose keys/shapes are those of the reference modules:
+
+  unet_forward              aux_code/models/unet_model.py:26-37, unet_parts.py:8-77
+  i3d_extract_features      aux_code/models/i3d.py:336-340 (Unit3D :89-120, SAME pool :13-45,
+                            InceptionModule :144-149, avg_pool :293-294)
+  i3res50_extract_features  aux_code/models/large_i3d.py:249-263 (Bottleneck :61-84)
+  r3d18_forward             aux_code/model_loaders.py:200-213 + torchvision video/resnet.py
+                            (BasicStem :173-181, BasicBlock :87-121, VideoResNet.forward :251-263)
+  anonymize_and_reshape     feature_extraction/dali_extraction.py:171-173 (raw reshape glue)
+  snippet indexing          dali_extraction.py:58-76 (DALI reader) / shanghai_dl.py:43-98
+
+Pinned in this container against the UNMODIFIED reference modules imported from /root/reference
+(tests/golden/make_golden.py, which also commits the golden vectors tests/test_oracle.py checks).
+
+`calibrated_state_dict` builds the seeded synthetic weights SURVEY.md 8(c) asks for (stock init
+makes the parity gate vacuous): kaiming-normal convs, random BN affine, BN running statistics set
+from a calibration pass over structured clips.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+# ----------------------------------------------------------------------------------- specs
+I3D_MIXED = [
+    ("Mixed_3b", 192, [64, 96, 128, 16, 32, 32]),
+    ("Mixed_3c", 256, [128, 128, 192, 32, 96, 64]),
+    ("Mixed_4b", 480, [192, 96, 208, 16, 48, 64]),
+    ("Mixed_4c", 512, [160, 112, 224, 24, 64, 64]),
+    ("Mixed_4d", 512, [128, 128, 256, 24, 64, 64]),
+    ("Mixed_4e", 512, [112, 144, 288, 32, 64, 64]),
+    ("Mixed_4f", 528, [256, 160, 320, 32, 128, 128]),
+    ("Mixed_5b", 832, [256, 160, 320, 32, 128, 128]),
+    ("Mixed_5c", 832, [384, 192, 384, 48, 128, 128]),
+]
+I3RES50_LAYERS = [  # (planes, blocks, stride, temp_conv)
+    (64, 3, 1, [1, 1, 1]),
+    (128, 4, 2, [1, 0, 1, 0]),
+    (256, 6, 2, [1, 0, 1, 0, 1, 0]),
+    (512, 3, 2, [0, 1, 0]),
+]
+
+
+def conv_bn_names(arch):
+    """Ordered list of (conv_weight_key, conv_bias_key|None, bn_prefix|None, weight_shape) per arch."""
+    out = []
+    if arch == "unet":
+        def dc(prefix, cin, cout, mid=None):
+            mid = mid or cout
+            out.append((f"{prefix}.0.weight", f"{prefix}.0.bias", f"{prefix}.1", (mid, cin, 3, 3)))
+            out.append((f"{prefix}.3.weight", f"{prefix}.3.bias", f"{prefix}.4", (cout, mid, 3, 3)))
+        dc("inc.double_conv", 3, 64)
+        for i, (ci, co) in enumerate([(64, 128), (128, 256), (256, 512), (512, 512)], 1):
+            dc(f"down{i}.maxpool_conv.1.double_conv", ci, co)
+        for i, (ci, co) in enumerate([(1024, 256), (512, 128), (256, 64), (128, 64)], 1):
+            dc(f"up{i}.conv.double_conv", ci, co, ci // 2)
+        out.append(("outc.conv.weight", "outc.conv.bias", None, (3, 64, 1, 1)))
+    elif arch == "i3d":
+        def u(name, cin, cout, k):
+            out.append((f"{name}.conv3d.weight", None, f"{name}.bn", (cout, cin) + tuple(k)))
+        u("Conv3d_1a_7x7", 3, 64, (7, 7, 7))
+        u("Conv3d_2b_1x1", 64, 64, (1, 1, 1))
+        u("Conv3d_2c_3x3", 64, 192, (3, 3, 3))
+        for name, cin, oc in I3D_MIXED:
+            u(f"{name}.b0", cin, oc[0], (1, 1, 1))
+            u(f"{name}.b1a", cin, oc[1], (1, 1, 1))
+            u(f"{name}.b1b", oc[1], oc[2], (3, 3, 3))
+            u(f"{name}.b2a", cin, oc[3], (1, 1, 1))
+            u(f"{name}.b2b", oc[3], oc[4], (3, 3, 3))
+            u(f"{name}.b3b", cin, oc[5], (1, 1, 1))
+    elif arch == "largei3d":
+        out.append(("i3d.conv1.weight", None, "i3d.bn1", (64, 3, 5, 7, 7)))
+        inpl = 64
+        for li, (planes, blocks, stride, tcs) in enumerate(I3RES50_LAYERS, 1):
+            for b in range(blocks):
+                p = f"i3d.layer{li}.{b}"
+                tc = tcs[b]
+                out.append((f"{p}.conv1.weight", None, f"{p}.bn1", (planes, inpl, 1 + 2 * tc, 1, 1)))
+                out.append((f"{p}.conv2.weight", None, f"{p}.bn2", (planes, planes, 1, 3, 3)))
+                out.append((f"{p}.conv3.weight", None, f"{p}.bn3", (planes * 4, planes, 1, 1, 1)))
+                if b == 0:
+                    out.append((f"{p}.downsample.0.weight", None, f"{p}.downsample.1", (planes * 4, inpl, 1, 1, 1)))
+                inpl = planes * 4
+    elif arch == "r3d_18":
+        out.append(("backbone.stem.0.weight", None, "backbone.stem.1", (64, 3, 3, 7, 7)))
+        inpl = 64
+        for li, planes in enumerate([64, 128, 256, 512], 1):
+            for b in range(2):
+                p = f"backbone.layer{li}.{b}"
+                out.append((f"{p}.conv1.0.weight", None, f"{p}.conv1.1", (planes, inpl, 3, 3, 3)))
+                out.append((f"{p}.conv2.0.weight", None, f"{p}.conv2.1", (planes, planes, 3, 3, 3)))
+                if b == 0 and li > 1:
+                    out.append((f"{p}.downsample.0.weight", None, f"{p}.downsample.1", (planes, inpl, 1, 1, 1)))
+                inpl = planes
+    else:
+        raise ValueError(arch)
+    return out
+
+
+def extra_params(arch, num_classes=102):
+    """Parameters on the reference module that are not conv+BN pairs: (key, shape, kind)."""
+    if arch == "i3d":
+        return [("logits.conv3d.weight", (num_classes, 1024, 1, 1, 1), "w"), ("logits.conv3d.bias", (num_classes,), "b")]
+    if arch == "largei3d":
+        ex = [("i3d.fc.weight", (num_classes, 2048), "w"), ("i3d.fc.bias", (num_classes,), "b"),
+              ("mlp.fc1.weight", (512, 2048), "w"), ("mlp.fc1.bias", (512,), "b"), ("mlp.fc2.weight", (128, 512), "w")]
+        for bn, c in (("mlp.bn1", 512), ("mlp.bn2", 128)):
+            ex += [(f"{bn}.weight", (c,), "g"), (f"{bn}.bias", (c,), "beta"), (f"{bn}.running_mean", (c,), "zero"),
+                   (f"{bn}.running_var", (c,), "one"), (f"{bn}.num_batches_tracked", (), "nbt")]
+        return ex
+    if arch == "r3d_18":
+        return [("fc.weight", (num_classes, 512), "w"), ("fc.bias", (num_classes,), "b")]
+    return []
+
+
+# ----------------------------------------------------------------------------------- forward
+class _Ctx:
+    """Forward context: state dict, optional BN calibration, optional activation taps."""
+
+    def __init__(self, sd, calibrate=False, taps=None, bn_eps=1e-5):
+        self.sd, self.calibrate, self.taps, self.bn_eps = sd, calibrate, taps, bn_eps
+
+    def bn(self, x, prefix, eps=None):
+        eps = self.bn_eps if eps is None else eps
+        sd = self.sd
+        if self.calibrate:
+            dims = [0] + list(range(2, x.dim()))
+            sd[prefix + ".running_mean"] = x.mean(dims).detach().clone()
+            sd[prefix + ".running_var"] = x.var(dims, unbiased=True).detach().clone()
+        shape = [1, -1] + [1] * (x.dim() - 2)
+        mean, var = sd[prefix + ".running_mean"].view(shape), sd[prefix + ".running_var"].view(shape)
+        g, b = sd[prefix + ".weight"].view(shape), sd[prefix + ".bias"].view(shape)
+        return (x - mean) / torch.sqrt(var + eps) * g + b
+
+    def tap(self, name, x):
+        if self.taps is not None:
+            self.taps[name] = x.detach().clone()
+        return x
+
+
+def unet_forward(sd, x, calibrate=False, taps=None):
+    """x: fp32 [N,3,H,W] in [0,1] -> [N,3,H,W] in (0,1).  unet_model.py:26-37."""
+    c = _Ctx(sd, calibrate, taps, 1e-5)
+
+    def dconv(x, p):  # unet_parts.py:15-22
+        for ci, bi in ((0, 1), (3, 4)):
+            x = F.conv2d(x, sd[f"{p}.{ci}.weight"], sd[f"{p}.{ci}.bias"], padding=1)
+            x = torch.relu(c.bn(x, f"{p}.{bi}"))
+            c.tap(f"{p}.{ci}", x)
+        return x
+
+    def up(x1, x2, p):  # unet_parts.py:57-68
+        x1 = F.interpolate(x1, scale_factor=2, mode="bilinear", align_corners=True)
+        dy, dx = x2.shape[2] - x1.shape[2], x2.shape[3] - x1.shape[3]
+        x1 = F.pad(x1, [dx // 2, dx - dx // 2, dy // 2, dy - dy // 2])
+        return dconv(torch.cat([x2, x1], 1), p)
+
+    x1 = dconv(x, "inc.double_conv")
+    x2 = dconv(F.max_pool2d(x1, 2), "down1.maxpool_conv.1.double_conv")
+    x3 = dconv(F.max_pool2d(x2, 2), "down2.maxpool_conv.1.double_conv")
+    x4 = dconv(F.max_pool2d(x3, 2), "down3.maxpool_conv.1.double_conv")
+    x5 = dconv(F.max_pool2d(x4, 2), "down4.maxpool_conv.1.double_conv")
+    y = up(x5, x4, "up1.conv.double_conv")
+    y = up(y, x3, "up2.conv.double_conv")
+    y = up(y, x2, "up3.conv.double_conv")
+    y = up(y, x1, "up4.conv.double_conv")
+    return c.tap("out", torch.sigmoid(F.conv2d(y, sd["outc.conv.weight"], sd["outc.conv.bias"])))
+
+
+def same_pad(size, k, s):
+    """TF-SAME total pad -> (front, back).  i3d.py:82-86,102-109."""
+    p = max(k - s, 0) if size % s == 0 else max(k - size % s, 0)
+    return p // 2, p - p // 2
+
+
+def _same_pad6(x, k, s):
+    pads = [same_pad(x.shape[2 + i], k[i], s[i]) for i in range(3)]
+    return (pads[2][0], pads[2][1], pads[1][0], pads[1][1], pads[0][0], pads[0][1])
+
+
+def i3d_extract_features(sd, x, calibrate=False, taps=None):
+    """x: fp32 [B,3,T,H,W] -> [B,1024,T',1,1].  i3d.py:336-340."""
+    c = _Ctx(sd, calibrate, taps, 1e-3)
+
+    def unit(x, name, k, s=(1, 1, 1)):  # i3d.py:89-120
+        x = F.conv3d(F.pad(x, _same_pad6(x, k, s)), sd[f"{name}.conv3d.weight"], None, stride=s)
+        return c.tap(name, torch.relu(c.bn(x, f"{name}.bn")))
+
+    def pool(x, k, s):  # i3d.py:21-45 (zero padding, then max)
+        return F.max_pool3d(F.pad(x, _same_pad6(x, k, s)), k, s)
+
+    def mixed(x, name):  # i3d.py:144-149
+        b0 = unit(x, f"{name}.b0", (1, 1, 1))
+        b1 = unit(unit(x, f"{name}.b1a", (1, 1, 1)), f"{name}.b1b", (3, 3, 3))
+        b2 = unit(unit(x, f"{name}.b2a", (1, 1, 1)), f"{name}.b2b", (3, 3, 3))
+        b3 = unit(pool(x, (3, 3, 3), (1, 1, 1)), f"{name}.b3b", (1, 1, 1))
+        return c.tap(name, torch.cat([b0, b1, b2, b3], 1))
+
+    x = unit(x, "Conv3d_1a_7x7", (7, 7, 7), (2, 2, 2))
+    x = pool(x, (1, 3, 3), (1, 2, 2))
+    x = unit(x, "Conv3d_2b_1x1", (1, 1, 1))
+    x = unit(x, "Conv3d_2c_3x3", (3, 3, 3))
+    x = pool(x, (1, 3, 3), (1, 2, 2))
+    x = mixed(mixed(x, "Mixed_3b"), "Mixed_3c")
+    x = pool(x, (3, 3, 3), (2, 2, 2))
+    for n in ("Mixed_4b", "Mixed_4c", "Mixed_4d", "Mixed_4e", "Mixed_4f"):
+        x = mixed(x, n)
+    x = pool(x, (2, 2, 2), (2, 2, 2))
+    x = mixed(mixed(x, "Mixed_5b"), "Mixed_5c")
+    return F.avg_pool3d(x, (2, 7, 7), 1)
+
+
+def i3res50_extract_features(sd, x, prefix="i3d.", calibrate=False, taps=None):
+    """x: fp32 [B,3,T,H,W] -> [B,2048,1,1,1].  large_i3d.py:249-263."""
+    c = _Ctx(sd, calibrate, taps, 1e-5)
+    P = prefix
+    x = F.conv3d(x, sd[P + "conv1.weight"], None, stride=(2, 2, 2), padding=(2, 3, 3))
+    x = c.tap("conv1", torch.relu(c.bn(x, P + "bn1")))
+    x = F.max_pool3d(x, (2, 3, 3), (2, 2, 2))
+    for li, (planes, blocks, stride, tcs) in enumerate(I3RES50_LAYERS, 1):
+        for b in range(blocks):
+            p = f"{P}layer{li}.{b}"
+            st = stride if b == 0 else 1
+            tc = tcs[b]
+            out = F.conv3d(x, sd[p + ".conv1.weight"], None, padding=(tc, 0, 0))
+            out = torch.relu(c.bn(out, p + ".bn1"))
+            out = F.conv3d(out, sd[p + ".conv2.weight"], None, stride=(1, st, st), padding=(0, 1, 1))
+            out = torch.relu(c.bn(out, p + ".bn2"))
+            out = c.bn(F.conv3d(out, sd[p + ".conv3.weight"], None), p + ".bn3")
+            res = x
+            if b == 0:
+                res = c.bn(F.conv3d(x, sd[p + ".downsample.0.weight"], None, stride=(1, st, st)), p + ".downsample.1")
+            x = c.tap(p, torch.relu(out + res))
+        if li == 1:
+            x = F.max_pool3d(x, (2, 1, 1), (2, 1, 1))
+    return F.adaptive_avg_pool3d(x, 1)
+
+
+def r3d18_forward(sd, x, calibrate=False, taps=None):
+    """x: fp32 [B,3,T,H,W] -> (pred [B,nc], feature [B,512]).  model_loaders.py:210-213."""
+    c = _Ctx(sd, calibrate, taps, 1e-5)
+    x = F.conv3d(x, sd["backbone.stem.0.weight"], None, stride=(1, 2, 2), padding=(1, 3, 3))
+    x = c.tap("stem", torch.relu(c.bn(x, "backbone.stem.1")))
+    for li in range(1, 5):
+        for b in range(2):
+            p = f"backbone.layer{li}.{b}"
+            st = 2 if (b == 0 and li > 1) else 1
+            out = F.conv3d(x, sd[p + ".conv1.0.weight"], None, stride=st, padding=1)
+            out = torch.relu(c.bn(out, p + ".conv1.1"))
+            out = c.bn(F.conv3d(out, sd[p + ".conv2.0.weight"], None, padding=1), p + ".conv2.1")
+            res = x
+            if b == 0 and li > 1:
+                res = c.bn(F.conv3d(x, sd[p + ".downsample.0.weight"], None, stride=st), p + ".downsample.1")
+            x = c.tap(p, torch.relu(out + res))
+    feat = F.adaptive_avg_pool3d(x, 1).flatten(1)
+    return F.linear(feat, sd["fc.weight"], sd["fc.bias"]), feat
+
+
+def encoder_features(arch, sd, x, **kw):
+    """The per-snippet feature row each arch contributes to the .npy ([B,F])."""
+    if arch == "i3d":
+        return i3d_extract_features(sd, x, **kw).flatten(1)
+    if arch == "largei3d":
+        return i3res50_extract_features(sd, x, **kw).flatten(1)
+    if arch == "r3d_18":
+        return r3d18_forward(sd, x, **kw)[1]
+    raise ValueError(arch)
+
+
+def anonymize_and_reshape(sd_fa, inputs, **kw):
+    """inputs: [1,T,3,H,W] -> anonymized [1,3,T,H,W] by the RAW reshape of dali_extraction.py:171-173."""
+    bs, t, ch, h, w = inputs.shape
+    frames = inputs.reshape(-1, ch, h, w)
+    return unet_forward(sd_fa, frames, **kw).reshape(bs, ch, t, h, w)
+
+
+def plane_map(T=16, C=3):
+    """(encoder channel, encoder time) <- (frame t, colour c): plane p = C*t + c -> (p // T, p % T)."""
+    return {(t, c): ((C * t + c) // T, (C * t + c) % T) for t in range(T) for c in range(C)}
+
+
+# ----------------------------------------------------------------------------------- indexing
+def dali_snippet_frames(n_frames, num_frames=16, stride=2, step=None):
+    """DALI fn.readers.video(sequence_length=16, stride=2, step=32, pad_sequences=True) sample list
+    (dali_extraction.py:58-76): snippet i = frames 32i + 2j; frames past the end are -1 (zero image)."""
+    step = step or num_frames * stride
+    out = []
+    start = 0
+    while start < n_frames:
+        idx = [start + stride * j for j in range(num_frames)]
+        out.append([i if i < n_frames else -1 for i in idx])
+        start += step
+    return out
+
+
+def shanghai_snippet_frames(n_frames, num_frames=16, fix_skip=2):
+    """shanghai_dl.py:43-98: 1-based counter, keep count % skip == 0, emit when count % (16*skip) == 0;
+    videos shorter than 32 frames use skip 1; shorter than 16 repeat the last frame."""
+    skip = 1 if n_frames < fix_skip * num_frames else fix_skip
+    out, cur = [], []
+    for count in range(1, n_frames + 1):
+        if count % skip == 0:
+            cur.append(count - 1)
+            if count % (num_frames * skip) == 0:
+                out.append(cur)
+                cur = []
+    if n_frames < num_frames and n_frames > 0:
+        count = n_frames
+        while count % 16 != 0:
+            count += 1
+            cur.append(n_frames - 1)
+            if count % 16 == 0:
+                out.append(cur)
+    return out
+
+
+# ----------------------------------------------------------------------------------- synthetic data
+def structured_clip_u8(seed, T=16, H=240, W=320, grid=12):
+    """Smooth structured uint8 frames [T,H,W,3]: low-resolution noise, trilinearly up-sampled, plus a
+    little per-pixel noise.  Deterministic (numpy RandomState + torch CPU interpolate)."""
+    rs = np.random.RandomState(seed)
+    low = torch.from_numpy(rs.rand(1, 3, max(T // 4, 2), grid, grid * W // H).astype(np.float32))
+    vid = F.interpolate(low, size=(T, H, W), mode="trilinear", align_corners=True)[0]  # [3,T,H,W]
+    vid = vid + torch.from_numpy(rs.rand(3, T, H, W).astype(np.float32)) * 0.08 - 0.04
+    vid = (vid - vid.min()) / (vid.max() - vid.min())
+    return (vid.permute(1, 2, 3, 0) * 255.0).round().clamp(0, 255).to(torch.uint8).numpy()
+
+
+def calibrated_state_dict(arch, seed, calib_input, num_classes=102):
+    """Seeded synthetic weights with data-calibrated BN statistics.
+    calib_input: the tensor the arch's forward takes ([N,3,H,W] for unet, [B,3,T,H,W] for encoders)."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for wk, bk, bn, shape in conv_bn_names(arch):
+        fan_in = int(np.prod(shape[1:]))
+        sd[wk] = torch.randn(shape, generator=g) * math.sqrt(2.0 / fan_in)
+        if bk is not None:
+            sd[bk] = torch.rand(shape[0], generator=g) * 0.2 - 0.1
+        if bn is not None:
+            co = shape[0]
+            sd[bn + ".weight"] = torch.rand(co, generator=g) + 0.5
+            sd[bn + ".bias"] = torch.rand(co, generator=g) * 0.6 - 0.3
+            sd[bn + ".running_mean"] = torch.zeros(co)
+            sd[bn + ".running_var"] = torch.ones(co)
+            sd[bn + ".num_batches_tracked"] = torch.tensor(1, dtype=torch.long)
+    for k, shape, kind in extra_params(arch, num_classes):
+        if kind == "w":
+            sd[k] = torch.randn(shape, generator=g) * math.sqrt(1.0 / int(np.prod(shape[1:])))
+        elif kind == "b":
+            sd[k] = torch.rand(shape, generator=g) * 0.2 - 0.1
+        elif kind == "g":
+            sd[k] = torch.rand(shape, generator=g) + 0.5
+        elif kind == "beta":
+            sd[k] = torch.rand(shape, generator=g) * 0.6 - 0.3
+        elif kind == "zero":
+            sd[k] = torch.zeros(shape)
+        elif kind == "one":
+            sd[k] = torch.ones(shape)
+        elif kind == "nbt":
+            sd[k] = torch.tensor(1, dtype=torch.long)
+    with torch.no_grad():
+        if arch == "unet":
+            unet_forward(sd, calib_input, calibrate=True)
+        elif arch == "i3d":
+            i3d_extract_features(sd, calib_input, calibrate=True)
+        elif arch == "largei3d":
+            i3res50_extract_features(sd, calib_input, calibrate=True)
+        elif arch == "r3d_18":
+            r3d18_forward(sd, calib_input, calibrate=True)
+    return sd
