@@ -1,0 +1,258 @@
+#!/usr/bin/env python
+"""Benchmark of the TeD-SPAD snippet feature-extraction hot path (BASELINE.json metric):
+16-frame 224x224 snippet-clips/s through anonymizer UNet + I3D on N x B200, and the fraction of the
+measured bf16 tensor-core peak the convolution kernel reaches.
+
+A step = one batch of 32 synthetic clips (BASELINE.json configs[1]): 512 decoded uint8 240x320 frames ->
+crop 192x256 -> antialiased resize 224x224 -> UNet (frame-wise) -> raw-reshape glue -> InceptionI3d
+.extract_features -> [32, 1024] fp32 feature rows.
+
+    python bench.py [--gpus N --steps K --warmup W]         # this framework (one rank per GPU under torchrun)
+    python bench.py --impl reference [...]                   # reference algorithm on the host CPU cores
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the definitions.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "ted-spad_b200"))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+GFLOP_UNET, GFLOP_I3D = 979.72, 55.58       # per 16x224x224 clip, conv 2*MAC, un-padded
+GFLOP_CLIP = GFLOP_UNET + GFLOP_I3D
+BATCH_CLIPS, T, SRC_HW, RESO = 32, 16, (240, 320), (224, 224)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["bf16_tflops_sustained"], d["bf16_tflops"], d["hbm_gbs"], "measured"
+    return 1400.0, 1590.0, 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """SM clock + throttle reasons during the timed region (nvidia-smi query, 200 ms period)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+
+    def run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            names = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+                     0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+                     0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+            while not self.stop_flag:
+                self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(
+                    pynvml, "nvmlDeviceGetCurrentClocksEventReasons") else pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, n in names.items():
+                    if r & bit and n != "gpu_idle":
+                        self.reasons.add(n)
+                time.sleep(0.2)
+        except Exception as e:  # clocks are evidence, not a dependency of the measurement
+            self.reasons.add(f"sampler_error:{type(e).__name__}")
+
+    def result(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def synthetic_frames(seed, n_frames, hw):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randint(0, 256, (n_frames, hw[0], hw[1], 3), generator=g, dtype=torch.uint8)
+
+
+def build_models(device):
+    """Random-init weights of the reference architecture (stock torch init of the boundary modules, seeded)."""
+    import contextlib
+    import io
+    from aux_code.model_loaders import load_fa_model, load_ft_model
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        fa, ft = load_fa_model(arch="unet"), load_ft_model(arch="i3d", num_classes=102)
+    return fa.to(device).eval(), ft.to(device).eval()
+
+
+def cpu_reference_clips_per_s(n_timed=3, threads=None):
+    """The reference algorithm (oracle port of UNet + InceptionI3d.extract_features, fp32) on the host cores,
+    batch 1 clip like the reference (params_feature_ex.py:4), 1 warm-up + n_timed clips.  This is the only
+    place bench.py touches oracle/: as the CPU baseline, never on the measured GPU path."""
+    from oracle import models as M
+    from oracle import preprocess as P
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    fa, ft = build_models("cpu")
+    sd_fa, sd_ft = fa.state_dict(), ft.state_dict()
+    clip = synthetic_frames(0, T, SRC_HW).numpy()
+    times = []
+    with torch.no_grad():
+        for i in range(1 + n_timed):
+            t0 = time.perf_counter()
+            x = torch.from_numpy(P.dali_val_augmentations(clip, RESO))
+            enc_in = M.anonymize_and_reshape(sd_fa, x.unsqueeze(0))
+            M.i3d_extract_features(sd_ft, enc_in)
+            times.append(time.perf_counter() - t0)
+    per_clip = float(np.mean(times[1:]))
+    return 1.0 / per_clip, threads, f"{n_timed} clips of 16x240x320 uint8 frames, batch 1, fp32, after 1 warm-up"
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    cps, threads, sample = cpu_reference_clips_per_s(n_timed=steps)
+    line = {
+        "impl": "reference", "metric": "snippet_clips_per_s", "value": cps, "unit": "clips/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": 1, "ms_per_step": 1000.0 / cps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": "anonymizer UNet + I3D snippet features, 16x224x224 clips (BASELINE configs[1]); "
+                               "each step = 1 clip on the host CPU (bounded sample of the 32-clip batch)"},
+        "cpu_baseline": {"value": cps, "unit": "clips/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": cps, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="tedspad_b200", choices=["tedspad_b200", "reference"])
+    ap.add_argument("--batch-clips", type=int, default=BATCH_CLIPS)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: this framework has no CPU path (use --impl reference)")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+
+    from tedspad_b200 import ops
+    from tedspad_b200.extraction import SnippetExtractor, crop_boxes
+
+    fa, ft = build_models(device)
+    B = args.batch_clips
+    ext = SnippetExtractor(fa, ft, reso=RESO, batch_clips=B)
+    (ch, cw), boxes = crop_boxes(*SRC_HW)
+    n_frames = B * T
+    desc = np.zeros((n_frames, 4), dtype=np.int32)
+    desc[:, 0] = np.arange(n_frames)
+    desc[:, 1], desc[:, 2] = boxes[0][0], boxes[0][1]
+    # inputs larger than L2: 512 frames x 230 KB = 118 MB of uint8 per step, two alternating input sets
+    host_sets = [synthetic_frames(1000 + rank * 10 + i, n_frames, SRC_HW).pin_memory() for i in range(2)]
+    dev_sets = [h.to(device) for h in host_sets]
+    feat_host = torch.empty((B, 1, 1024), dtype=torch.float32).pin_memory()
+
+    def step_resident(i):
+        return ext.features_of_clips(dev_sets[i % 2], desc, (ch, cw))
+
+    def step_e2e(i):
+        frames = host_sets[i % 2].to(device, non_blocking=True)      # H2D of this step's decoded frames
+        f = ext.features_of_clips(frames, desc, (ch, cw))
+        feat_host.copy_(f, non_blocking=True)                         # D2H of the step's feature rows
+        torch.cuda.current_stream().synchronize()
+        return f
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for i in range(max(3, args.warmup)):
+        step_resident(i)
+    ops.LAUNCHES = 0
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms_total = timed(step_resident, args.steps)
+    launches = ops.LAUNCHES
+    for i in range(2):
+        step_e2e(i)
+    ms_e2e = timed(step_e2e, args.steps)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    # conv-kernel-only time: same steps, one CUDA event pair around every tedspad_conv_forward launch
+    ops.CONV_EVENTS = []
+    for i in range(2):
+        step_resident(i)
+    torch.cuda.synchronize()
+    conv_ms = sum(a.elapsed_time(b) for a, b in ops.CONV_EVENTS) / 2.0
+    n_conv = len(ops.CONV_EVENTS) // 2
+    ops.CONV_EVENTS = None
+
+    ms_step = ms_total / args.steps
+    clips_per_s = world * B / (ms_step / 1e3)
+    e2e_cps = world * B / (ms_e2e / args.steps / 1e3)
+    sustained, burst, hbm, how = measured_peaks()
+    conv_tflops = B * GFLOP_CLIP / conv_ms            # GFLOP / ms = TFLOP/s
+    line = {
+        "metric": "snippet_clips_per_s", "value": clips_per_s, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "anonymizer UNet + I3D snippet features, 16x224x224 clips, batch 32 per GPU "
+                               "(BASELINE configs[1]) from 512 decoded uint8 240x320 frames per step",
+                   "batch_clips_per_gpu": B, "l2": "inputs larger than L2 (118 MB uint8 per step, two alternating sets; "
+                   "activations ~26 GB per step)", "weights": "random init (seeded stock init of the reference architecture)"},
+        "tflops_algorithmic": clips_per_s * GFLOP_CLIP / 1e3 / world,
+        "roofline": {"bound": "tensor", "kernel": "conv_igemm_kernel (all %d launches of a step)" % n_conv,
+                     "achieved": conv_tflops, "peak": sustained, "unit": "TFLOP/s", "frac": conv_tflops / sustained,
+                     "peak_burst": burst, "peak_source": how + " bf16_tflops_sustained (kernel timed inside a long step)",
+                     "conv_ms_per_step": conv_ms, "conv_share_of_step": conv_ms / ms_step, "traffic": None},
+        "e2e": {"value": e2e_cps, "unit": "clips/s", "h2d_bytes_per_step": int(host_sets[0].numel()),
+                "d2h_bytes_per_step": int(feat_host.numel() * 4)},
+        "gpu_launches": launches,
+        "clocks": sampler.result(),
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cps, threads, sample = cpu_reference_clips_per_s(n_timed=3)
+        line["cpu_baseline"] = {"value": cps, "unit": "clips/s", "cores": threads, "kind": "port", "sample": sample}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

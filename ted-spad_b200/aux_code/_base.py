@@ -1,0 +1,55 @@
+"""Shared behaviour of the boundary nn.Modules: parameters live in torch (reference state_dict
+names), arithmetic lives in libtedspad.so; the packed-weight executor is rebuilt whenever the
+parameters change (load_state_dict, .cuda(), .to())."""
+import os
+import sys
+
+import torch
+import torch.nn as nn
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+if _ROOT not in sys.path:
+    sys.path.insert(0, _ROOT)
+
+from tedspad_b200 import ops  # noqa: E402
+from tedspad_b200.ops import CLTensor  # noqa: E402
+
+
+class CudaModule(nn.Module):
+    """nn.Module whose forward runs on the B200 kernels only (no CPU / eager fallback)."""
+
+    executor_cls = None
+    executor_kwargs = {}
+
+    def _signature(self):
+        return tuple((k, v.data_ptr(), v._version, str(v.device)) for k, v in self.state_dict(keep_vars=True).items())
+
+    def _exec(self, x):
+        if not (isinstance(x, torch.Tensor) and x.is_cuda):
+            raise RuntimeError(f"{type(self).__name__}: input must be a CUDA tensor - this implementation runs only "
+                               "on the sm_100a kernels in libtedspad.so and has no CPU fallback")
+        if self.training:
+            raise RuntimeError(f"{type(self).__name__}: inference only (BatchNorm uses running statistics); "
+                               "call .eval() first as dali_extraction.py:139-141 does")
+        p = next(self.parameters())
+        if p.device != x.device:
+            raise RuntimeError(f"{type(self).__name__}: parameters on {p.device}, input on {x.device}")
+        sig = self._signature()
+        if getattr(self, "_tsp_sig", None) != sig:
+            with torch.cuda.device(x.device):
+                self.__dict__["_tsp_executor"] = self.executor_cls(self.state_dict(), x.device, **self.executor_kwargs)
+            self.__dict__["_tsp_sig"] = sig
+        return self.__dict__["_tsp_executor"]
+
+    def _to_cl(self, x, name="in"):
+        """fp32 [B,3,T,H,W] / [N,3,H,W] -> channels-last bf16 [.., 8] (channels 3..7 zero)."""
+        ex = self.__dict__["_tsp_executor"]
+        if x.dim() == 4:
+            n, c, h, w = x.shape
+            t = 1
+        else:
+            n, c, t, h, w = x.shape
+        if c != 3:
+            raise RuntimeError(f"{type(self).__name__}: expected 3 input channels, got {c}")
+        buf = ex.bufs.get(name, n, t, h, w, 8)
+        return ops.nchw_to_cl(x, buf)

@@ -1,0 +1,317 @@
+"""Network executors: the anonymizer UNet and the three video encoders expressed as sequences of
+C-ABI operator calls over channels-last bf16 buffers.
+
+Each executor is built from a reference-format `state_dict` (the boundary nn.Modules in
+aux_code/ own the parameters and hand them over), folds BatchNorm into the packed weights once,
+and caches its activation buffers per input shape.  Concatenations (unet_parts.py:67, i3d.py:149)
+are never materialised: producers write straight into channel slices of the consumer's input.
+"""
+import torch
+
+from . import _lib as L
+from . import ops
+from .ops import CLTensor, PackedConv
+
+
+def _bn(sd, prefix, eps):
+    return (sd[prefix + ".weight"], sd[prefix + ".bias"], sd[prefix + ".running_mean"], sd[prefix + ".running_var"], eps)
+
+
+def same_pad(size, k, s):
+    """TF-"SAME" padding of i3d.py:82-86: total pad, split front = total // 2."""
+    total = max(k - s, 0) if size % s == 0 else max(k - size % s, 0)
+    return total // 2, total - total // 2
+
+
+class _Buffers:
+    """Named activation buffers, allocated once per executor instance and shape."""
+
+    def __init__(self, device):
+        self.device = device
+        self.pool = {}
+
+    def get(self, name, N, D, H, W, C, halo=(0, 0, 0), dtype=ops.BF16):
+        key = (name, N, D, H, W, C, tuple(halo), dtype)
+        t = self.pool.get(key)
+        if t is None:
+            t = CLTensor(N, D, H, W, C, halo, device=self.device, dtype=dtype)
+            if sum(halo) == 0 and C % 8 == 0:
+                pass  # fully overwritten by its producer
+            self.pool[key] = t
+        return t
+
+    def drop_other_shapes(self, keep_n):
+        for k in [k for k in self.pool if k[1] != keep_n]:
+            del self.pool[k]
+
+
+# ======================================================================================== UNet
+class UNetExecutor:
+    """aux_code/models/unet_model.py:26-37 as 18 tcgen05 convolutions + 4 pools + 4 up-samples + OutConv.
+    All 3x3 convolutions except the first (Cin=3) use the FLAT TMA feed over zero-haloed buffers."""
+
+    HALO = (0, 1, 1)
+
+    def __init__(self, sd, device):
+        self.device = device
+        self.bufs = _Buffers(device)
+        self.convs = {}
+
+        def dc(prefix, cin_pad0):
+            a = PackedConv(sd[f"{prefix}.0.weight"], sd[f"{prefix}.0.bias"], _bn(sd, f"{prefix}.1", 1e-5),
+                           pad_front=(0, 1, 1), cin_pad=cin_pad0, device=device)
+            b = PackedConv(sd[f"{prefix}.3.weight"], sd[f"{prefix}.3.bias"], _bn(sd, f"{prefix}.4", 1e-5),
+                           pad_front=(0, 1, 1), device=device)
+            self.convs[prefix] = (a, b)
+
+        dc("inc.double_conv", 8)
+        for i in range(1, 5):
+            dc(f"down{i}.maxpool_conv.1.double_conv", None)
+        for i in range(1, 5):
+            dc(f"up{i}.conv.double_conv", None)
+        self.out_w = sd["outc.conv.weight"].detach().float().reshape(3, -1).contiguous().to(device)
+        self.out_b = sd["outc.conv.bias"].detach().float().contiguous().to(device)
+
+    def input_buffer(self, n_frames, H, W):
+        """The [n_frames,1,H,W,8] bf16 buffer preprocessing / nchw_to_cl writes the frames into."""
+        return self.bufs.get("x0", n_frames, 1, H, W, 8)
+
+    def run(self, x0, enc_in, T=16, frames_out=None):
+        """x0: input_buffer() filled with frames; enc_in: encoder input [B,T,H,W,>=3] (scatter target)."""
+        N, H, W = x0.N, x0.H, x0.W
+        g, hl = self.bufs.get, self.HALO
+        sizes = [(H, W)]
+        for _ in range(4):
+            sizes.append((sizes[-1][0] // 2, sizes[-1][1] // 2))
+        ch = [64, 128, 256, 512, 512]
+        # encoder path; skip tensors x1..x4 live in the first half of the concat buffers
+        cats = [g(f"cat{i}", N, 1, sizes[i][0], sizes[i][1], 2 * ch[i], hl) for i in range(4)]
+        a, b = self.convs["inc.double_conv"]
+        t = g("t0", N, 1, H, W, 64, hl)
+        ops.conv_forward(x0, a, t, feed=L.FEED_GATHER)
+        skip = cats[0].slice(0, 64)
+        ops.conv_forward(t, b, skip)
+        cur = skip
+        for i in range(1, 5):
+            h, w = sizes[i]
+            p = g(f"p{i}", N, 1, h, w, ch[i - 1], hl)
+            ops.maxpool(cur, p, (1, 2, 2), (1, 2, 2))
+            a, b = self.convs[f"down{i}.maxpool_conv.1.double_conv"]
+            t = g(f"t{i}", N, 1, h, w, ch[i], hl)
+            ops.conv_forward(p, a, t)
+            cur = cats[i].slice(0, ch[i]) if i < 4 else g("x5", N, 1, h, w, ch[4], hl)
+            ops.conv_forward(t, b, cur)
+        # decoder path
+        out_ch = [256, 128, 64, 64]
+        for j in range(4):
+            lvl = 3 - j
+            cat = cats[lvl]
+            ops.upsample2x(cur, cat.slice(ch[lvl], cur.C))
+            a, b = self.convs[f"up{j + 1}.conv.double_conv"]
+            h, w = sizes[lvl]
+            t = g(f"u{j}a", N, 1, h, w, a.cout, hl)
+            ops.conv_forward(cat, a, t)
+            cur = g(f"u{j}", N, 1, h, w, out_ch[j], hl)
+            ops.conv_forward(t, b, cur)
+        ops.outconv_sigmoid(cur, self.out_w, self.out_b, enc_in, T, frames_out)
+        return enc_in
+
+
+# ======================================================================================== I3D
+I3D_MIXED = [
+    ("Mixed_3b", 192, [64, 96, 128, 16, 32, 32]),
+    ("Mixed_3c", 256, [128, 128, 192, 32, 96, 64]),
+    ("Mixed_4b", 480, [192, 96, 208, 16, 48, 64]),
+    ("Mixed_4c", 512, [160, 112, 224, 24, 64, 64]),
+    ("Mixed_4d", 512, [128, 128, 256, 24, 64, 64]),
+    ("Mixed_4e", 512, [112, 144, 288, 32, 64, 64]),
+    ("Mixed_4f", 528, [256, 160, 320, 32, 128, 128]),
+    ("Mixed_5b", 832, [256, 160, 320, 32, 128, 128]),
+    ("Mixed_5c", 832, [384, 192, 384, 48, 128, 128]),
+]
+
+
+class I3DExecutor:
+    """InceptionI3d.extract_features (aux_code/models/i3d.py:336-340): Unit3D = TF-SAME conv + BN(eps 1e-3)
+    + ReLU in one kernel; the four Inception branches write into slices of the block output."""
+
+    def __init__(self, sd, device):
+        self.device = device
+        self.bufs = _Buffers(device)
+        self.sd_w = {}
+        self.specs = {}
+
+        def unit(name, k, s=(1, 1, 1), cin_pad=None):
+            self.specs[name] = (sd[f"{name}.conv3d.weight"], _bn(sd, f"{name}.bn", 1e-3), k, s, cin_pad)
+
+        unit("Conv3d_1a_7x7", (7, 7, 7), (2, 2, 2), 8)
+        unit("Conv3d_2b_1x1", (1, 1, 1))
+        unit("Conv3d_2c_3x3", (3, 3, 3))
+        for name, _, _ in I3D_MIXED:
+            for br, k in (("b0", 1), ("b1a", 1), ("b1b", 3), ("b2a", 1), ("b2b", 3), ("b3b", 1)):
+                unit(f"{name}.{br}", (k, k, k))
+        self.packed = {}
+
+    def _conv(self, name, x, y):
+        """Unit3D.forward (i3d.py:89-120): SAME front pads depend on the input extent."""
+        w, bn, k, s, cin_pad = self.specs[name]
+        pads = [same_pad(sz, kk, ss) for sz, kk, ss in zip((x.D, x.H, x.W), k, s)]
+        pf = tuple(p[0] for p in pads)
+        key = (name, pf)
+        pc = self.packed.get(key)
+        if pc is None:
+            pc = PackedConv(w, None, bn, stride=s, pad_front=pf, cin_pad=cin_pad, device=self.device)
+            self.packed[key] = pc
+        return ops.conv_forward(x, pc, y)
+
+    @staticmethod
+    def _same_out(x, s):
+        return tuple(-(-sz // ss) for sz, ss in zip((x.D, x.H, x.W), s))
+
+    def _pool(self, name, x, k, s):
+        """MaxPool3dSamePadding.forward (i3d.py:21-45): zero padding, then max."""
+        od, oh, ow = self._same_out(x, s)
+        y = self.bufs.get(name, x.N, od, oh, ow, x.C)
+        pf = tuple(same_pad(sz, kk, ss)[0] for sz, kk, ss in zip((x.D, x.H, x.W), k, s))
+        return ops.maxpool(x, y, k, s, pf, zero_pad=True)
+
+    def _unit(self, name, x, cout=None, out=None):
+        _, _, k, s, _ = self.specs[name]
+        od, oh, ow = self._same_out(x, s)
+        if out is None:
+            out = self.bufs.get(name, x.N, od, oh, ow, cout)
+        return self._conv(name, x, out)
+
+    def _mixed(self, name, x, oc):
+        total = oc[0] + oc[2] + oc[4] + oc[5]
+        y = self.bufs.get(name, x.N, x.D, x.H, x.W, total)
+        self._unit(f"{name}.b0", x, out=y.slice(0, oc[0]))
+        t1 = self._unit(f"{name}.b1a", x, oc[1])
+        self._unit(f"{name}.b1b", t1, out=y.slice(oc[0], oc[2]))
+        t2 = self._unit(f"{name}.b2a", x, oc[3])
+        self._unit(f"{name}.b2b", t2, out=y.slice(oc[0] + oc[2], oc[4]))
+        t3 = self._pool(f"{name}.b3a", x, (3, 3, 3), (1, 1, 1))
+        self._unit(f"{name}.b3b", t3, out=y.slice(oc[0] + oc[2] + oc[4], oc[5]))
+        return y
+
+    def run_trunk(self, enc_in):
+        """enc_in: [B,T,H,W,8] (3 real channels) -> Mixed_5c feature map [B,T/8,H/32,W/32,1024]."""
+        x = self._unit("Conv3d_1a_7x7", enc_in, 64)
+        x = self._pool("MaxPool3d_2a_3x3", x, (1, 3, 3), (1, 2, 2))
+        x = self._unit("Conv3d_2b_1x1", x, 64)
+        x = self._unit("Conv3d_2c_3x3", x, 192)
+        x = self._pool("MaxPool3d_3a_3x3", x, (1, 3, 3), (1, 2, 2))
+        mixed = {n: oc for n, _, oc in I3D_MIXED}
+        for n in ("Mixed_3b", "Mixed_3c"):
+            x = self._mixed(n, x, mixed[n])
+        x = self._pool("MaxPool3d_4a_3x3", x, (3, 3, 3), (2, 2, 2))
+        for n in ("Mixed_4b", "Mixed_4c", "Mixed_4d", "Mixed_4e", "Mixed_4f"):
+            x = self._mixed(n, x, mixed[n])
+        x = self._pool("MaxPool3d_5a_2x2", x, (2, 2, 2), (2, 2, 2))
+        for n in ("Mixed_5b", "Mixed_5c"):
+            x = self._mixed(n, x, mixed[n])
+        return x
+
+    def run(self, enc_in):
+        """enc_in: [B,T,H,W,8] -> fp32 features [B, T', 1024] (AvgPool3d([2,7,7], stride 1), i3d.py:293-294,340)."""
+        x = self.run_trunk(enc_in)
+        if x.H != 7 or x.W != 7 or x.D < 2:
+            raise RuntimeError(f"InceptionI3d.extract_features: AvgPool3d([2,7,7]) needs a (>=2,7,7) map, got "
+                               f"({x.D},{x.H},{x.W}); use 224x224 clips of >=16 frames (i3d.py:293-294)")
+        return ops.avgpool_features(x, 2)
+
+
+# ==================================================================================== I3Res50
+I3RES50_LAYERS = [(64, 3, 1, [1, 1, 1]), (128, 4, 2, [1, 0, 1, 0]), (256, 6, 2, [1, 0, 1, 0, 1, 0]), (512, 3, 2, [0, 1, 0])]
+
+
+class I3Res50Executor:
+    """I3Res50.extract_features (aux_code/models/large_i3d.py:249-263).  bn3 + residual add + ReLU
+    (large_i3d.py:72-79) run in the epilogue of conv3."""
+
+    def __init__(self, sd, device, prefix="i3d."):
+        self.device = device
+        self.bufs = _Buffers(device)
+        P = prefix
+        mk = lambda wk, bnk, stride, pad, cin_pad=None: PackedConv(  # noqa: E731
+            sd[P + wk], None, _bn(sd, P + bnk, 1e-5), stride=stride, pad_front=pad, cin_pad=cin_pad, device=device)
+        self.conv1 = mk("conv1.weight", "bn1", (2, 2, 2), (2, 3, 3), 8)
+        self.blocks = []
+        for li, (planes, nblocks, stride, tcs) in enumerate(I3RES50_LAYERS, 1):
+            for b in range(nblocks):
+                p = f"layer{li}.{b}"
+                st = stride if b == 0 else 1
+                blk = {
+                    "c1": mk(f"{p}.conv1.weight", f"{p}.bn1", (1, 1, 1), (tcs[b], 0, 0)),
+                    "c2": mk(f"{p}.conv2.weight", f"{p}.bn2", (1, st, st), (0, 1, 1)),
+                    "c3": mk(f"{p}.conv3.weight", f"{p}.bn3", (1, 1, 1), (0, 0, 0)),
+                    "ds": mk(f"{p}.downsample.0.weight", f"{p}.downsample.1", (1, st, st), (0, 0, 0)) if b == 0 else None,
+                    "name": p, "pool_after": (li == 1 and b == nblocks - 1),
+                }
+                self.blocks.append(blk)
+
+    def _apply(self, name, pc, x, res=None, act=L.ACT_RELU):
+        od, oh, ow = pc.out_extent((x.D, x.H, x.W))
+        y = self.bufs.get(name, x.N, od, oh, ow, pc.cout)
+        return ops.conv_forward(x, pc, y, res=res, act=act)
+
+    def run(self, enc_in):
+        """enc_in: [B,T,H,W,8] -> fp32 features [B, 1, 2048]."""
+        g = self.bufs.get
+        x = self._apply("conv1", self.conv1, enc_in)
+        y = g("maxpool1", x.N, (x.D - 2) // 2 + 1, (x.H - 3) // 2 + 1, (x.W - 3) // 2 + 1, x.C)
+        x = ops.maxpool(x, y, (2, 3, 3), (2, 2, 2))
+        for blk in self.blocks:
+            n = blk["name"]
+            o = self._apply(n + ".c1", blk["c1"], x)
+            o = self._apply(n + ".c2", blk["c2"], o)
+            res = x if blk["ds"] is None else self._apply(n + ".ds", blk["ds"], x, act=L.ACT_NONE)
+            x = self._apply(n + ".c3", blk["c3"], o, res=res)
+            if blk["pool_after"]:
+                y = g("maxpool2", x.N, (x.D - 2) // 2 + 1, x.H, x.W, x.C)
+                x = ops.maxpool(x, y, (2, 1, 1), (2, 1, 1))
+        return ops.avgpool_features(x, 0)
+
+
+# ===================================================================================== R3D-18
+class R3D18Executor:
+    """wrapper_r3d_18.forward (aux_code/model_loaders.py:210-213) over torchvision's VideoResNet
+    (video/resnet.py:251-263): returns (pred, feature)."""
+
+    def __init__(self, sd, device):
+        self.device = device
+        self.bufs = _Buffers(device)
+        mk = lambda wk, bnk, stride, pad, cin_pad=None: PackedConv(  # noqa: E731
+            sd[wk], None, _bn(sd, bnk, 1e-5), stride=stride, pad_front=pad, cin_pad=cin_pad, device=device)
+        self.stem = mk("backbone.stem.0.weight", "backbone.stem.1", (1, 2, 2), (1, 3, 3), 8)
+        self.blocks = []
+        for li in range(1, 5):
+            for b in range(2):
+                p = f"backbone.layer{li}.{b}"
+                st = 2 if (b == 0 and li > 1) else 1
+                self.blocks.append({
+                    "c1": mk(f"{p}.conv1.0.weight", f"{p}.conv1.1", (st, st, st), (1, 1, 1)),
+                    "c2": mk(f"{p}.conv2.0.weight", f"{p}.conv2.1", (1, 1, 1), (1, 1, 1)),
+                    "ds": mk(f"{p}.downsample.0.weight", f"{p}.downsample.1", (st, st, st), (0, 0, 0))
+                    if (b == 0 and li > 1) else None,
+                    "name": p})
+        self.fc = PackedConv(sd["fc.weight"], sd["fc.bias"], None, device=device)
+
+    def _apply(self, name, pc, x, res=None, act=L.ACT_RELU):
+        od, oh, ow = pc.out_extent((x.D, x.H, x.W))
+        y = self.bufs.get(name, x.N, od, oh, ow, pc.cout)
+        return ops.conv_forward(x, pc, y, res=res, act=act)
+
+    def run(self, enc_in):
+        x = self._apply("stem", self.stem, enc_in)
+        for blk in self.blocks:
+            n = blk["name"]
+            o = self._apply(n + ".c1", blk["c1"], x)
+            res = x if blk["ds"] is None else self._apply(n + ".ds", blk["ds"], x, act=L.ACT_NONE)
+            x = self._apply(n + ".c2", blk["c2"], o, res=res)
+        feat = ops.avgpool_features(x, 0)  # [B,1,512] fp32
+        fin = self.bufs.get("fc_in", x.N, 1, 1, 1, 512)
+        fin.buf.copy_(feat.reshape(x.N, 1, 1, 1, 512))  # fp32 -> bf16 operand of the head GEMM
+        pred = self.bufs.get("fc_out", x.N, 1, 1, 1, self.fc.cout, dtype=torch.float32)
+        ops.conv_forward(fin, self.fc, pred, act=L.ACT_NONE, y_fp32=True)
+        return pred.buf.reshape(x.N, self.fc.cout), feat.reshape(x.N, 512)

@@ -1,0 +1,188 @@
+"""Snippet feature-extraction driver: decoded uint8 frames -> crop/resize (CUDA) -> anonymizer UNet
+-> 3-D encoder -> one feature row per 16-frame snippet (optionally 5/10-crop) -> `<video>.npy`.
+
+Mirrors the two reference scripts, minus video decoding (frames arrive decoded):
+  feature_extraction/dali_extraction.py:103-182   (UCF-Crime / XD-Violence, DALI reader semantics)
+  feature_extraction/st_feature_extraction.py:58-100 + shanghai_dl.py:43-98 (ShanghaiTech)
+Differences by design (same results, B200-first execution): snippets are batched instead of one
+clip per iteration, the per-clip blocking D2H + O(n^2) np.vstack (dali_extraction.py:179) becomes
+one D2H per video, and videos are sharded across GPUs by estimated work with no collective.
+"""
+import os
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import ops
+
+
+# ------------------------------------------------------------------------------- snippet indexing
+def dali_snippet_frames(n_frames, num_frames=16, stride=2):
+    """fn.readers.video(sequence_length=16, stride=2, step=32, pad_sequences=True) (dali_extraction.py:58-76):
+    snippet i holds frames 32*i + 2*j; a tail snippet is kept and its missing frames are zero images (-1)."""
+    step = num_frames * stride
+    out = np.full((max(0, -(-n_frames // step)), num_frames), -1, dtype=np.int64)
+    for i in range(out.shape[0]):
+        idx = i * step + stride * np.arange(num_frames)
+        out[i] = np.where(idx < n_frames, idx, -1)
+    return out
+
+
+def shanghai_snippet_frames(n_frames, num_frames=16, fix_skip=2):
+    """shanghai_dl.py:43-98: 1-based frame counter, keep when count % skip == 0, emit a clip when
+    count % (16*skip) == 0 (tail dropped); < 32 frames -> skip 1; < 16 frames -> last frame repeated."""
+    skip = 1 if n_frames < fix_skip * num_frames else fix_skip
+    per = num_frames * skip
+    full = n_frames // per
+    out = [[i * per + skip * (j + 1) - 1 for j in range(num_frames)] for i in range(full)]
+    if 0 < n_frames < num_frames:
+        out.append(list(range(n_frames)) + [n_frames - 1] * (num_frames - n_frames))
+    return np.asarray(out, dtype=np.int64).reshape(-1, num_frames)
+
+
+# ------------------------------------------------------------------------------------ crop boxes
+def center_offsets(h, w, ch, cw):
+    """torchvision center_crop offsets (functional.py:592-593)."""
+    return int(round((h - ch) / 2.0)), int(round((w - cw) / 2.0))
+
+
+def crop_boxes(h, w, ncrops=1, cropping_factor=0.8, no_ar_distortion=False, square_from_h=False):
+    """((crop_h, crop_w), [(top, left, hflip), ...]).  Crop size as dali_extraction.py:45-48
+    (square_from_h: shanghai_dl.py:35 uses H for both sides); crop order for 5/10 crops is torchvision's
+    five_crop / ten_crop: tl, tr, bl, br, center (+ the same five of the h-flipped frame), so that
+    crop 4 (center) is the reference's single crop."""
+    if no_ar_distortion:
+        ch = cw = int(min(h, w) * cropping_factor)
+    elif square_from_h:
+        ch = cw = int(h * cropping_factor)
+    else:
+        ch, cw = int(h * cropping_factor), int(w * cropping_factor)
+    ct, cl = center_offsets(h, w, ch, cw)
+    if ncrops == 1:
+        return (ch, cw), [(ct, cl, 0)]
+    five = [(0, 0), (0, w - cw), (h - ch, 0), (h - ch, w - cw), (ct, cl)]
+    boxes = [(t, l, 0) for t, l in five]
+    if ncrops == 10:
+        boxes += [(t, l, 1) for t, l in five]
+    elif ncrops != 5:
+        raise ValueError("ncrops must be 1, 5 or 10")
+    return (ch, cw), boxes
+
+
+# -------------------------------------------------------------------------------------- extractor
+class SnippetExtractor:
+    """fa_model / ft_model are the nn.Modules returned by aux_code.model_loaders (already .cuda().eval())."""
+
+    def __init__(self, fa_model, ft_model, reso=(224, 224), num_frames=16, fix_skip=2, cropping_factor=0.8,
+                 no_ar_distortion=False, ncrops=1, source="dali", batch_clips=8, device=None):
+        self.fa = fa_model
+        self.ft = ft_model.i3d if (not hasattr(ft_model, "features_from_cl") and hasattr(ft_model, "i3d")) else ft_model
+        self.reso, self.T, self.skip = tuple(reso), num_frames, fix_skip
+        self.cf, self.no_ar, self.ncrops = cropping_factor, no_ar_distortion, ncrops
+        if source not in ("dali", "shanghai"):
+            raise ValueError("source must be 'dali' or 'shanghai'")
+        self.source = source
+        self.resample = L.RESAMPLE_AA_FLOAT if source == "dali" else L.RESAMPLE_PIL_U8
+        self.batch_clips = int(batch_clips)
+        self.device = torch.device(device) if device is not None else next(fa_model.parameters()).device
+        if self.device.type != "cuda":
+            raise RuntimeError("SnippetExtractor needs CUDA modules: there is no CPU path")
+        self._enc = {}
+
+    def snippet_frames(self, n_frames):
+        if self.source == "dali":
+            return dali_snippet_frames(n_frames, self.T, self.skip)
+        return shanghai_snippet_frames(n_frames, self.T, self.skip)
+
+    def _enc_in(self, B):
+        t = self._enc.get(B)
+        if t is None:
+            t = ops.CLTensor(B, self.T, self.reso[0], self.reso[1], 8, device=self.device)
+            t.buf.zero_()  # channels 3..7 stay zero forever (the scatter only writes 0..2)
+            self._enc[B] = t
+        return t
+
+    def features_of_clips(self, frames_dev, desc_host, crop_hw):
+        """frames_dev: cuda uint8 [F,H,W,3]; desc_host: int32 [B*T,4] numpy -> fp32 cuda [B, n_feat_rows, F]."""
+        B = desc_host.shape[0] // self.T
+        with torch.cuda.device(self.device):
+            desc = torch.from_numpy(desc_host).to(self.device, non_blocking=True)
+            ex_fa = self.fa.executor(self.device)
+            x0 = ex_fa.input_buffer(B * self.T, self.reso[0], self.reso[1])
+            ops.preprocess(frames_dev, desc, crop_hw, x0, self.resample)
+            enc_in = self._enc_in(B)
+            self.fa.anonymize_into(x0, enc_in, self.T)
+            return self.ft.features_from_cl(enc_in)
+
+    def extract_video(self, frames):
+        """frames: uint8 [F,H,W,3] torch tensor (CPU, pinned CPU or CUDA), RGB for the DALI path, BGR
+        as cv2 decodes for the ShanghaiTech path.  Returns float64 numpy [n_snip, feat] (ncrops == 1, the
+        reference layout: dali_extraction.py:163,179) or [n_snip, ncrops, feat] (dataset.py:70-71,89)."""
+        n_frames, H, W, _ = frames.shape
+        snips = self.snippet_frames(n_frames)
+        n_snip = snips.shape[0]
+        crop_hw, boxes = crop_boxes(H, W, self.ncrops, self.cf, self.no_ar, square_from_h=(self.source == "shanghai"))
+        rows = []
+        per_batch = max(1, self.batch_clips // self.ncrops)  # snippets per batch
+        for s0 in range(0, n_snip, per_batch):
+            sn = snips[s0:s0 + per_batch]
+            valid = sn[sn >= 0]
+            f_lo, f_hi = (int(valid.min()), int(valid.max()) + 1) if valid.size else (0, 1)
+            chunk = frames[f_lo:f_hi]
+            if not chunk.is_cuda:
+                chunk = chunk.to(self.device, non_blocking=True)
+            chunk = chunk.contiguous()
+            desc = np.empty((sn.shape[0], len(boxes), self.T, 4), dtype=np.int32)
+            desc[..., 0] = np.where(sn >= 0, sn - f_lo, -1)[:, None, :]
+            for ci, (t, l, fl) in enumerate(boxes):
+                desc[:, ci, :, 1], desc[:, ci, :, 2], desc[:, ci, :, 3] = t, l, fl
+            feats = self.features_of_clips(chunk, desc.reshape(-1, 4), crop_hw)  # [B, R, F]
+            rows.append(feats.reshape(sn.shape[0], len(boxes), -1).clone())
+        if not rows:
+            width = 0
+            return np.zeros((0, width), dtype=np.float64)
+        allf = torch.cat(rows, 0).cpu().numpy().astype(np.float64)  # one D2H per video
+        return allf[:, 0, :] if self.ncrops == 1 else allf
+
+
+def feature_path(save_folder, vid_path):
+    """<folder>/<basename minus .mp4/.avi>.npy (dali_extraction.py:159, st_feature_extraction.py:88)."""
+    base = os.path.basename(vid_path).replace('.mp4', '').replace('.avi', '')
+    return os.path.join(save_folder, base + '.npy')
+
+
+# ------------------------------------------------------------------------------------- sharding
+def shard_videos(lengths, world_size):
+    """Longest-processing-time greedy partition of videos over ranks by frame count.
+    Returns a list (per rank) of video indices; every video is owned by exactly one rank."""
+    order = sorted(range(len(lengths)), key=lambda i: (-int(lengths[i]), i))
+    loads = [0] * world_size
+    shards = [[] for _ in range(world_size)]
+    for i in order:
+        r = min(range(world_size), key=lambda k: (loads[k], k))
+        shards[r].append(i)
+        loads[r] += int(lengths[i])
+    return [sorted(s) for s in shards]
+
+
+def extract_dataset(extractor, videos, save_folder, rank=0, world_size=1, log=print):
+    """videos: list of (path, n_frames, loader) with loader() -> uint8 [F,H,W,3].  The partition is computed
+    over the FULL list (so every rank derives the same one no matter when it starts); within its shard a
+    rank skips videos whose .npy already exists - the reference's resume rule (dali_extraction.py:121).
+    Each file is written by exactly one rank (atomic rename); there is no collective."""
+    os.makedirs(save_folder, exist_ok=True)
+    mine = shard_videos([v[1] for v in videos], world_size)[rank]
+    written = []
+    for i in mine:
+        path, _, loader = videos[i]
+        out = feature_path(save_folder, path)
+        if os.path.exists(out):
+            continue
+        log(f'Extracting features for {os.path.basename(path)}.')
+        feats = extractor.extract_video(loader())
+        tmp = out + f".tmp{rank}.npy"
+        np.save(tmp, feats)
+        os.replace(tmp, out)
+        written.append(out)
+    return written

@@ -12,6 +12,14 @@ from . import _lib as L
 
 BF16 = torch.bfloat16
 
+LAUNCHES = 0        # kernels launched through this module (bench.py reports it as gpu_launches)
+CONV_EVENTS = None  # when a list: one (start, end) CUDA event pair is appended per conv launch (bench.py roofline)
+
+
+def _count():
+    global LAUNCHES
+    LAUNCHES += 1
+
 
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -136,13 +144,22 @@ def conv_forward(x, pc, y, res=None, act=L.ACT_RELU, feed=L.FEED_AUTO, y_fp32=Fa
     d.kd, d.kh, d.kw = pc.k
     d.sd, d.sh, d.sw = pc.stride
     d.pd, d.ph, d.pw = pc.pad_front
-    d.act, d.y_fp32, d.feed, d.n_tile, d.max_ctas = act, int(y_fp32), feed, n_tile, max_ctas
+    d.act, d.y_fp32, d.feed, d.n_tile, d.max_ctas = act, int(y_fp32), feed, n_tile or pc.n_tile, max_ctas
+    _count()
+    if CONV_EVENTS is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        L.check(L.lib().tedspad_conv_forward(C.byref(d), _stream()), "tedspad_conv_forward")
+        e1.record()
+        CONV_EVENTS.append((e0, e1))
+        return y
     L.check(L.lib().tedspad_conv_forward(C.byref(d), _stream()), "tedspad_conv_forward")
     return y
 
 
 def maxpool(x, y, k, s, pad_front=(0, 0, 0), zero_pad=False):
     xd, yd = x.desc(), y.desc()
+    _count()
     L.check(L.lib().tedspad_maxpool(C.byref(xd), C.byref(yd), *k, *s, *pad_front, int(zero_pad), _stream()),
             "tedspad_maxpool")
     return y
@@ -150,6 +167,7 @@ def maxpool(x, y, k, s, pad_front=(0, 0, 0), zero_pad=False):
 
 def upsample2x(x, y):
     xd, yd = x.desc(), y.desc()
+    _count()
     L.check(L.lib().tedspad_upsample2x(C.byref(xd), C.byref(yd), _stream()), "tedspad_upsample2x")
     return y
 
@@ -158,6 +176,7 @@ def outconv_sigmoid(x, w, b, y, T, frames_out=None):
     """w: fp32 [3, C] cuda, b: fp32 [3] cuda; y: encoder-input CLTensor [B,T,H,W,>=3]."""
     xd, yd = x.desc(), y.desc()
     fo = frames_out.data_ptr() if frames_out is not None else None
+    _count()
     L.check(L.lib().tedspad_outconv_sigmoid(C.byref(xd), w.data_ptr(), b.data_ptr(), C.byref(yd), int(T), fo,
                                             _stream()), "tedspad_outconv_sigmoid")
     return y
@@ -167,6 +186,7 @@ def avgpool_features(x, kd=0):
     od = x.D - (kd if kd > 0 else x.D) + 1
     out = torch.empty((x.N, od, x.C), device=x.buf.device, dtype=torch.float32)
     xd = x.desc()
+    _count()
     L.check(L.lib().tedspad_avgpool_features(C.byref(xd), int(kd), out.data_ptr(), _stream()),
             "tedspad_avgpool_features")
     return out
@@ -180,6 +200,7 @@ def preprocess(frames_u8, desc_i32, crop_hw, y, resample=L.RESAMPLE_AA_FLOAT, fr
     assert desc_i32.dtype == torch.int32 and desc_i32.is_contiguous() and desc_i32.shape[1] == 4
     yd = y.desc()
     fo = frames_f32.data_ptr() if frames_f32 is not None else None
+    _count()
     L.check(L.lib().tedspad_preprocess(frames_u8.data_ptr(), F_, Hs, Ws, desc_i32.data_ptr(), desc_i32.shape[0],
                                        int(crop_hw[0]), int(crop_hw[1]), C.byref(yd), int(resample), fo, _stream()),
             "tedspad_preprocess")
@@ -191,6 +212,7 @@ def nchw_to_cl(x_f32, y):
     _require_cuda(x_f32, "nchw_to_cl")
     x_f32 = x_f32.contiguous().float()
     yd = y.desc()
+    _count()
     L.check(L.lib().tedspad_nchw_to_cl(x_f32.data_ptr(), int(x_f32.shape[1]), C.byref(yd), _stream()),
             "tedspad_nchw_to_cl")
     return y

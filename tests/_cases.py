@@ -1,0 +1,62 @@
+"""Shared test fixtures: the golden cases (seeds, sizes) and deterministic weights/inputs for them.
+Everything here is regenerated from seeds on any box; tests/golden/golden_v1.npz (made by
+tests/golden/make_golden.py from the real reference) pins that the regeneration is faithful."""
+import functools
+import os
+
+import numpy as np
+import torch
+
+from oracle import models as M
+from oracle import preprocess as P
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v1.npz")
+
+CASES = {
+    # name: (encoder arch, source (H, W), output reso, weight seeds (fa, ft), clip seeds (calib, test, control))
+    "unet_i3d_224": ("i3d", (240, 320), (224, 224), (1, 2), (100, 101, 102)),
+    "unet_largei3d_224": ("largei3d", (240, 320), (224, 224), (1, 3), (100, 101, 102)),
+    "unet_r3d18_112": ("r3d_18", (120, 160), (112, 112), (4, 5), (110, 111, 112)),
+}
+
+
+def golden():
+    return np.load(GOLDEN)
+
+
+@functools.lru_cache(maxsize=None)
+def case_weights(name):
+    arch, hw, reso, wseeds, cseeds = CASES[name]
+    clip = M.structured_clip_u8(cseeds[0], 16, hw[0], hw[1])
+    x = torch.from_numpy(P.dali_val_augmentations(clip, reso))
+    with torch.no_grad():
+        sd_fa = M.calibrated_state_dict("unet", wseeds[0], x)
+        enc_in = M.anonymize_and_reshape(sd_fa, x.unsqueeze(0))
+        sd_ft = M.calibrated_state_dict(arch, wseeds[1], enc_in)
+    return sd_fa, sd_ft
+
+
+def case_clip(name, which="test"):
+    arch, hw, reso, wseeds, cseeds = CASES[name]
+    seed = {"calib": cseeds[0], "test": cseeds[1], "control": cseeds[2]}[which]
+    return M.structured_clip_u8(seed, 16, hw[0], hw[1])
+
+
+def oracle_features(name, clip_u8):
+    """fp32 oracle: uint8 frames -> (preprocessed [16,3,h,w], anonymized enc_in [1,3,16,h,w], features [F])."""
+    arch, hw, reso, _, _ = CASES[name]
+    sd_fa, sd_ft = case_weights(name)
+    x = torch.from_numpy(P.dali_val_augmentations(clip_u8, reso))
+    with torch.no_grad():
+        enc_in = M.anonymize_and_reshape(sd_fa, x.unsqueeze(0))
+        feat = M.encoder_features(arch, sd_ft, enc_in).squeeze(0)
+    return x, enc_in, feat
+
+
+def parity_metrics(got, ref):
+    got, ref = got.double().flatten(), ref.double().flatten()
+    cos = float(torch.nn.functional.cosine_similarity(got, ref, dim=0))
+    gc, rc = got - got.mean(), ref - ref.mean()
+    ccos = float(torch.nn.functional.cosine_similarity(gc, rc, dim=0))
+    return {"cos": cos, "centered_cos": ccos, "max_abs": float((got - ref).abs().max()),
+            "ref_max": float(ref.abs().max())}

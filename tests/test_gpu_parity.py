@@ -1,0 +1,216 @@
+"""GPU parity tests (run on the B200 box with `-m gpu`): every C-ABI operator against the matching
+torch fp32 op, and the whole hot path (uint8 frames -> preprocessing -> anonymizer -> encoder ->
+feature rows) against the fp32 oracle and the golden vectors of the unmodified reference.
+
+Gate (BASELINE.json north_star): per-snippet feature cosine >= 0.9995 and max abs error <= 2e-2 for
+the bf16 pipeline versus the fp32 reference; snippet (temporal) index and crop ordering bit-exact.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import _cases
+from oracle import models as M
+from oracle import preprocess as P
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "ted-spad_b200"))
+
+pytestmark = pytest.mark.gpu
+
+COS_GATE, ABS_GATE = 0.9995, 2e-2
+
+
+def _modules(name):
+    from aux_code.model_loaders import load_fa_model, load_ft_model
+    arch = _cases.CASES[name][0]
+    sd_fa, sd_ft = _cases.case_weights(name)
+    fa = load_fa_model(arch="unet")
+    ft = load_ft_model(arch=arch, num_classes=102)
+    fa.load_state_dict(sd_fa, strict=True)
+    ft.load_state_dict(sd_ft, strict=True)
+    return fa.cuda().eval(), ft.cuda().eval()
+
+
+@pytest.mark.parametrize("group", ["flat", "gather", "ops", "prep"])
+def test_operator_battery(group):
+    """tests/gpu_diag.py: each operator vs torch fp32 on bf16-rounded operands (conv tolerance 2e-2 of the
+    output range, i.e. bf16 output rounding; pooling / layout / PIL preprocessing bit-exact)."""
+    import gpu_diag
+    gpu_diag.RESULTS.clear()
+    getattr(gpu_diag, "group_" + group)()
+    torch.cuda.synchronize()
+    failed = [n for n, ok in gpu_diag.RESULTS if not ok]
+    assert not failed, failed
+    assert len(gpu_diag.RESULTS) >= 4
+
+
+@pytest.mark.parametrize("name", list(_cases.CASES))
+def test_hot_path_parity(name):
+    from tedspad_b200.extraction import SnippetExtractor, crop_boxes
+    arch, hw, reso, _, _ = _cases.CASES[name]
+    fa, ft = _modules(name)
+    ext = SnippetExtractor(fa, ft, reso=reso, batch_clips=2)
+    G = _cases.golden()
+    feats, refs = {}, {}
+    for which in ("test", "control"):
+        clip = _cases.case_clip(name, which)
+        x_ref, enc_ref, f_ref = _cases.oracle_features(name, clip)
+        (ch, cw), boxes = crop_boxes(hw[0], hw[1])
+        desc = np.zeros((16, 4), dtype=np.int32)
+        desc[:, 0] = np.arange(16)
+        desc[:, 1], desc[:, 2] = boxes[0][0], boxes[0][1]
+        f = ext.features_of_clips(torch.from_numpy(clip).cuda(), desc, (ch, cw))
+        torch.cuda.synchronize()
+        feats[which], refs[which] = f.reshape(-1).float().cpu(), f_ref
+        if which == "test":
+            # anonymized clip as the encoder sees it (bf16, scattered by the raw-reshape glue)
+            enc = ext._enc_in(1).to_ncdhw()[:, :3].cpu()
+            e = (enc - enc_ref).abs()
+            print(f"\n{name}: anonymized clip err rms={e.pow(2).mean().sqrt():.4f} max={e.max():.4f}")
+            assert e.pow(2).mean().sqrt() < 0.012 and e.max() < 0.1
+    m = _cases.parity_metrics(feats["test"], refs["test"])
+    mg = _cases.parity_metrics(feats["test"], torch.from_numpy(G[f"{name}/features"]))
+    ctrl = float(torch.nn.functional.cosine_similarity(refs["test"], refs["control"], dim=0))
+    dcos = float(torch.nn.functional.cosine_similarity(feats["test"] - feats["control"], refs["test"] - refs["control"], dim=0))
+    print(f"{name}: vs oracle cos={m['cos']:.6f} max_abs={m['max_abs']:.4f} (|f|max {m['ref_max']:.3f}); "
+          f"vs golden(reference) cos={mg['cos']:.6f} max_abs={mg['max_abs']:.4f}; "
+          f"control cos(different clips)={ctrl:.4f}; cos of clip-to-clip feature difference={dcos:.4f}")
+    assert m["cos"] >= COS_GATE and m["max_abs"] <= ABS_GATE, m
+    assert mg["cos"] >= COS_GATE and mg["max_abs"] <= ABS_GATE, mg
+    assert ctrl < COS_GATE            # the gate can tell two clips apart ...
+    assert dcos > 0.98                # ... and the response to changing the clip matches the reference's
+
+
+def test_drop_in_module_flow():
+    """The loop body of feature_extraction/dali_extraction.py:168-179 run verbatim on the product modules
+    (fp32 torch tensors at every module boundary, bare try/except attribute dispatch)."""
+    name = "unet_largei3d_224"
+    fa_model, ft_model = _modules(name)
+    clip = _cases.case_clip(name)
+    x_ref, enc_ref, f_ref = _cases.oracle_features(name, clip)
+    inputs = x_ref.unsqueeze(0).cuda()                       # what val_augmentations hands over: [1,16,3,224,224]
+    with torch.no_grad():
+        ori_bs, ori_t, ori_c, ori_h, ori_w = inputs.permute(0, 2, 1, 3, 4).shape
+        inputs = inputs.view(-1, inputs.shape[2], inputs.shape[3], inputs.shape[4])
+        anon = fa_model(inputs)
+        assert anon.shape == (16, 3, 224, 224) and anon.dtype == torch.float32 and anon.is_cuda
+        inputs = anon.reshape(ori_bs, ori_t, ori_c, ori_h, ori_w)
+        try:
+            output = ft_model.extract_features(inputs)
+        except:  # noqa: E722  (the reference's own dispatch idiom, dali_extraction.py:175-178)
+            output = ft_model.i3d.extract_features(inputs)
+        assert output.shape == (1, 2048, 1, 1, 1) and output.dtype == torch.float32
+        row = output.squeeze().cpu().numpy()
+    e = (anon.cpu() - enc_ref.reshape(16, 3, 224, 224)).abs()
+    assert e.max() < 0.1
+    m = _cases.parity_metrics(torch.from_numpy(row), f_ref)
+    print(f"\ndrop-in flow: cos={m['cos']:.6f} max_abs={m['max_abs']:.4f}")
+    assert m["cos"] >= COS_GATE and m["max_abs"] <= ABS_GATE, m
+
+
+def test_r3d18_forward_signature():
+    """BASELINE config 1: pred, feat = ft_model(x) for wrapper_r3d_18 (model_loaders.py:210-213)."""
+    name = "unet_r3d18_112"
+    fa, ft = _modules(name)
+    clip = _cases.case_clip(name)
+    x_ref, enc_ref, f_ref = _cases.oracle_features(name, clip)
+    sd_ft = _cases.case_weights(name)[1]
+    with torch.no_grad():
+        pred_ref, feat_ref = M.r3d18_forward(sd_ft, enc_ref)
+        pred, feat = ft(enc_ref.cuda())
+    assert pred.shape == (1, 102) and feat.shape == (1, 512)
+    m = _cases.parity_metrics(feat.cpu(), feat_ref)
+    mp = _cases.parity_metrics(pred.cpu(), pred_ref)
+    print(f"\nr3d18 forward: feat cos={m['cos']:.6f} max_abs={m['max_abs']:.4f}; pred cos={mp['cos']:.6f}")
+    assert m["cos"] >= COS_GATE and m["max_abs"] <= ABS_GATE and mp["cos"] >= 0.999
+
+
+def _video(n_frames, h, w, seed):
+    base = M.structured_clip_u8(seed, 16, h, w)
+    reps = -(-n_frames // 16)
+    g = torch.Generator().manual_seed(seed)
+    vid = torch.from_numpy(base).repeat(reps, 1, 1, 1)[:n_frames].clone()
+    vid += torch.randint(0, 8, (n_frames, 1, 1, 3), generator=g, dtype=torch.uint8) * 4  # make every frame distinct
+    return vid
+
+
+def test_extract_video_rows_and_order():
+    """Per-video matrix: float64 [ceil(N/32), F]; row i == features of frames 32i + 2j (zero images past the
+    end); batched execution == clip-at-a-time execution bit for bit (temporal ordering gate)."""
+    from tedspad_b200.extraction import SnippetExtractor
+    name = "unet_r3d18_112"
+    fa, ft = _modules(name)
+    vid = _video(150, 120, 160, 5)
+    a = SnippetExtractor(fa, ft, reso=(112, 112), batch_clips=4).extract_video(vid)
+    b = SnippetExtractor(fa, ft, reso=(112, 112), batch_clips=1).extract_video(vid.cuda())
+    assert a.dtype == np.float64 and a.shape == (5, 512)
+    assert np.array_equal(a, b)
+    # oracle for rows 1 and 4 (row 4 is the zero-padded tail: frames 128..148 then zeros)
+    for r in (1, 4):
+        idx = M.dali_snippet_frames(150)[r]
+        clip = np.stack([vid[i].numpy() if i >= 0 else np.zeros((120, 160, 3), np.uint8) for i in idx])
+        _, _, f_ref = _cases.oracle_features(name, clip)
+        m = _cases.parity_metrics(torch.from_numpy(a[r]), f_ref)
+        assert m["cos"] >= COS_GATE and m["max_abs"] <= ABS_GATE, (r, m)
+    # a permutation of the snippets must show up as the same permutation of rows
+    assert not np.array_equal(a[0], a[1])
+
+
+def test_multicrop_layout_and_order():
+    """[n_snip, ncrops, F]; crop 4 (center) is the reference's single crop, bit-exact; crops 5..9 are the
+    crops of the horizontally flipped frames (torchvision ten_crop order)."""
+    from tedspad_b200.extraction import SnippetExtractor
+    name = "unet_r3d18_112"
+    fa, ft = _modules(name)
+    vid = _video(64, 120, 160, 6)
+    one = SnippetExtractor(fa, ft, reso=(112, 112), batch_clips=2).extract_video(vid)
+    ten = SnippetExtractor(fa, ft, reso=(112, 112), ncrops=10, batch_clips=20).extract_video(vid)
+    five = SnippetExtractor(fa, ft, reso=(112, 112), ncrops=5, batch_clips=5).extract_video(vid)
+    assert ten.shape == (2, 10, 512) and five.shape == (2, 5, 512) and one.shape == (2, 512)
+    assert np.array_equal(ten[:, 4], one) and np.array_equal(five, ten[:, :5])
+    flipped = SnippetExtractor(fa, ft, reso=(112, 112), ncrops=10, batch_clips=20).extract_video(vid.flip(2))
+    # crops 5..9 are by definition crops 0..4 of the flipped frames, so flipping the video swaps the halves
+    swap = [5, 6, 7, 8, 9, 0, 1, 2, 3, 4]
+    assert np.array_equal(flipped, ten[:, swap])
+
+
+def test_shanghai_path_preprocessing_and_indexing():
+    """ShanghaiTech path: frames 32i+2j+1, tail dropped, crop (int(.8H), int(.8H)), Pillow 8-bit bilinear
+    (bit-exact), channel order untouched (BGR stays BGR)."""
+    from tedspad_b200 import ops, _lib as L
+    from tedspad_b200.extraction import SnippetExtractor, crop_boxes
+    name = "unet_largei3d_224"
+    fa, ft = _modules(name)
+    vid = _video(70, 240, 428, 7)
+    ext = SnippetExtractor(fa, ft, source="shanghai", batch_clips=2)
+    assert ext.snippet_frames(70).tolist() == np.asarray(M.shanghai_snippet_frames(70)).tolist()
+    (ch, cw), boxes = crop_boxes(240, 428, square_from_h=True)
+    desc = torch.tensor([[i, boxes[0][0], boxes[0][1], 0] for i in (1, 3)], dtype=torch.int32).cuda()
+    y = ops.CLTensor(2, 1, 224, 224, 8, device="cuda")
+    f32 = torch.empty(2, 3, 224, 224, device="cuda")
+    ops.preprocess(vid.cuda(), desc, (ch, cw), y, L.RESAMPLE_PIL_U8, f32)
+    ref = np.stack([P.shanghai_augmentation(vid[i].numpy()) for i in (1, 3)])
+    assert np.array_equal(f32.cpu().numpy(), ref)
+    feats = ext.extract_video(vid)
+    assert feats.shape == (2, 2048) and feats.dtype == np.float64
+
+
+def test_sharded_extraction_equals_single(tmp_path):
+    """Union of 2 shards' files == single-process files, bit for bit (SURVEY 8e acceptance test)."""
+    from tedspad_b200.extraction import SnippetExtractor, extract_dataset
+    name = "unet_r3d18_112"
+    fa, ft = _modules(name)
+    ext = SnippetExtractor(fa, ft, reso=(112, 112), batch_clips=4)
+    vids = [(f"/data/v{i}.mp4", n, (lambda n=n, i=i: _video(n, 120, 160, 20 + i))) for i, n in enumerate([40, 96, 33, 70])]
+    single = tmp_path / "single"
+    extract_dataset(ext, vids, str(single), log=lambda *_: None)
+    sharded = tmp_path / "sharded"
+    w0 = extract_dataset(ext, vids, str(sharded), rank=0, world_size=2, log=lambda *_: None)
+    w1 = extract_dataset(ext, vids, str(sharded), rank=1, world_size=2, log=lambda *_: None)
+    assert len(w0) + len(w1) == 4 and not (set(w0) & set(w1))
+    for i in range(4):
+        assert np.array_equal(np.load(single / f"v{i}.npy"), np.load(sharded / f"v{i}.npy"))

@@ -1,0 +1,248 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every declared symbol, the
+boundary modules mirror the reference's parameter tree, weight packing, driver logic, sharding."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import _cases
+import _emu
+from oracle import models as M
+from oracle import preprocess as P
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "ted-spad_b200"))
+
+from tedspad_b200 import _lib as L, engine, extraction, ops  # noqa: E402
+from aux_code.model_loaders import load_fa_model, load_ft_model  # noqa: E402
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "tedspad.h")).read()
+    declared = set(re.findall(r"\b(tedspad_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(L.SYMBOLS), declared ^ set(L.SYMBOLS)
+    lib = L.lib()  # raises if the .so is missing: there is no fallback
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.tedspad_abi_version() == L.ABI_VERSION
+    assert ctypes.sizeof(L.TensorDesc) == 48 and ctypes.sizeof(L.ConvDesc) == 48 * 2 + 24 + 19 * 4 + 4
+
+
+def test_library_has_blackwell_sass():
+    out = subprocess.run(["cuobjdump", "-sass", L.LIB_PATH], capture_output=True, text=True).stdout
+    if not out:
+        pytest.skip("cuobjdump unavailable")
+    assert "sm_100a" in out and "UTCHMMA" in out and "UTMALDG" in out and "LDTM" in out
+
+
+@pytest.mark.parametrize("arch", ["unet", "i3d", "largei3d", "r3d_18"])
+def test_state_dict_matches_reference_tree(arch):
+    """keys + shapes equal the oracle's spec, which make_golden.py loaded strict=True into the real reference."""
+    mod = load_fa_model(arch="unet") if arch == "unet" else load_ft_model(arch=arch, num_classes=102)
+    sd = mod.state_dict()
+    want = {}
+    for wk, bk, bn, shape in M.conv_bn_names(arch):
+        want[wk] = tuple(shape)
+        if bk:
+            want[bk] = (shape[0],)
+        if bn:
+            for s in ("weight", "bias", "running_mean", "running_var"):
+                want[f"{bn}.{s}"] = (shape[0],)
+            want[f"{bn}.num_batches_tracked"] = ()
+    for k, shape, _ in M.extra_params(arch, 102):
+        want[k] = tuple(shape)
+    assert set(sd) == set(want), sorted(set(sd) ^ set(want))[:6]
+    for k, v in sd.items():
+        assert tuple(v.shape) == want[k], (k, tuple(v.shape), want[k])
+    if arch == "i3d":
+        assert list(sd)[0] == "logits.conv3d.weight"  # registered before the trunk (i3d.py:298-304)
+
+
+def test_checkpoint_formats(tmp_path):
+    """'module.' prefix strip (model_loaders.py:43-46), FrozenBN 'scale' rename (:80), .i3d fallback (:84)."""
+    fa = load_fa_model(arch="unet")
+    p = tmp_path / "fa.pth"
+    torch.save({"fa_model_state_dict": {"module." + k: v for k, v in fa.state_dict().items()}, "epoch": 3}, p)
+    fa2 = load_fa_model(saved_model_file=str(p), arch="unet")
+    assert all(torch.equal(a, b) for a, b in zip(fa.state_dict().values(), fa2.state_dict().values()))
+    ft = load_ft_model(arch="largei3d", num_classes=102)
+    inner = {k[len("i3d."):]: v for k, v in ft.state_dict().items() if k.startswith("i3d.")}
+    p2 = tmp_path / "ft.pth"
+    torch.save({"ft_model_state_dict": inner}, p2)
+    ft2 = load_ft_model(arch="largei3d", saved_model_file=str(p2), num_classes=102)
+    assert torch.equal(ft2.i3d.conv1.weight, ft.i3d.conv1.weight)
+    assert not hasattr(ft2, "extract_features") and hasattr(ft2.i3d, "extract_features")
+
+
+def test_no_cpu_fallback():
+    fa = load_fa_model(arch="unet").eval()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        fa(torch.zeros(1, 3, 16, 16))
+    ft = load_ft_model(arch="i3d", num_classes=102).eval()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ft.extract_features(torch.zeros(1, 3, 16, 224, 224))
+    with pytest.raises(NotImplementedError):
+        load_fa_model(arch="unet++")
+
+
+def test_packed_conv_layout():
+    w = torch.arange(2 * 3 * 1 * 2 * 2, dtype=torch.float32).reshape(2, 3, 1, 2, 2) / 64
+    pc = ops.PackedConv(w, None, None, cin_pad=8, device="cpu")
+    assert pc.w.shape == (16, 64) and pc.k_pad == 64 and pc.n_tile == 16
+    k = 0
+    for a in range(2):
+        for b in range(2):
+            for c in range(8):
+                exp = float(w[1, c, 0, a, b]) if c < 3 else 0.0
+                assert float(pc.w[1, k]) == exp
+                k += 1
+    assert ops.n_tiling(288) == (144, 288) and ops.n_tiling(512) == (256, 512) and ops.n_tiling(102) == (112, 112)
+    g = torch.tensor([2.0, 0.5]); beta = torch.tensor([0.1, -0.2]); mu = torch.tensor([1.0, 2.0]); var = torch.tensor([4.0, 0.25])
+    pcb = ops.PackedConv(w, torch.tensor([0.5, 0.25]), (g, beta, mu, var, 0.0), cin_pad=8, device="cpu")
+    assert torch.allclose(pcb.bias[:2], (torch.tensor([0.5, 0.25]) - mu) * g / var.sqrt() + beta)
+    assert torch.allclose(pcb.w[0, 0].float(), (w[0, 0, 0, 0, 0] * 1.0).to(torch.bfloat16).float())
+
+
+def _emulated(monkeypatch, fp32=False):
+    """Replace the CUDA operators by tests/_emu.py; fp32=True also stores activations/weights in fp32 so
+    that executor wiring can be checked exactly (no rounding) against the oracle."""
+    for n in ("conv_forward", "maxpool", "upsample2x", "outconv_sigmoid", "avgpool_features", "nchw_to_cl", "preprocess"):
+        monkeypatch.setattr(ops, n, getattr(_emu, n))
+    if fp32:
+        orig = ops.CLTensor.__init__
+
+        def init(self, *a, **k):
+            if k.get("dtype", torch.bfloat16) == torch.bfloat16:
+                k["dtype"] = torch.float32
+            orig(self, *a, **k)
+        monkeypatch.setattr(ops.CLTensor, "__init__", init)
+        monkeypatch.setattr(ops, "BF16", torch.float32)
+
+
+def test_executor_wiring_unet_r3d_emulated(monkeypatch):
+    """The executors' graph wiring (slices, halos, pads, residuals) against the oracle, with the CUDA
+    operators replaced by tests/_emu.py (bf16 storage, fp32 math).  Also predicts the bf16 error budget."""
+    _emulated(monkeypatch)
+    name = "unet_r3d18_112"
+    sd_fa, sd_ft = _cases.case_weights(name)
+    x, enc_ref, feat_ref = _cases.oracle_features(name, _cases.case_clip(name))
+    ue = engine.UNetExecutor(sd_fa, "cpu")
+    x0 = ue.input_buffer(16, 112, 112)
+    ops.nchw_to_cl(x, x0)
+    enc = ops.CLTensor(1, 16, 112, 112, 8, device="cpu")
+    enc.buf.zero_()
+    fr = torch.empty(16, 3, 112, 112)
+    ue.run(x0, enc, 16, fr)
+    err = (fr - enc_ref.reshape(16, 3, 112, 112)).abs()
+    assert err.max() < 0.08 and err.pow(2).mean().sqrt() < 0.01
+    pred, feat = engine.R3D18Executor(sd_ft, "cpu").run(enc)
+    m = _cases.parity_metrics(feat[0], feat_ref)
+    assert m["cos"] > 0.9995 and m["max_abs"] < 2e-2, m
+
+
+def _cl_fp32(x):
+    n, c, d, h, w = x.shape
+    t = ops.CLTensor(n, d, h, w, 8, device="cpu")
+    t.buf.zero_()
+    t.interior()[..., :c] = x.permute(0, 2, 3, 4, 1)
+    return t
+
+
+def test_executor_wiring_i3res50_exact(monkeypatch):
+    """fp32-storage emulation: I3Res50Executor's graph == large_i3d.py:249-263 to fp32 round-off
+    (odd 55x55 / 27x27 extents, (2,3,3) pad-0 pool, temporal convs, strided downsample, residuals)."""
+    _emulated(monkeypatch, fp32=True)
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(2, 3, 8, 96, 96, generator=g)
+    sd = M.calibrated_state_dict("largei3d", 9, x)
+    ref = M.i3res50_extract_features(sd, x).flatten()
+    feat = engine.I3Res50Executor(sd, "cpu").run(_cl_fp32(x))
+    m = _cases.parity_metrics(feat.flatten(), ref)
+    assert m["max_abs"] < 1e-4 and m["cos"] > 0.999999, m
+
+
+def test_executor_wiring_unet_exact_odd_size(monkeypatch):
+    """fp32-storage emulation of the UNet at a size not divisible by 16 (F.pad branch of unet_parts.py:57-63)."""
+    _emulated(monkeypatch, fp32=True)
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(2, 3, 40, 52, generator=g)
+    sd = M.calibrated_state_dict("unet", 6, x)
+    ref = M.unet_forward(sd, x)
+    ue = engine.UNetExecutor(sd, "cpu")
+    x0 = ue.input_buffer(2, 40, 52)
+    ops.nchw_to_cl(x, x0)
+    enc = ops.CLTensor(2, 1, 40, 52, 8, device="cpu")
+    out = torch.empty(2, 3, 40, 52)
+    ue.run(x0, enc, 1, out)
+    assert (out - ref).abs().max() < 1e-4
+
+
+def test_executor_wiring_i3d_trunk_exact(monkeypatch):
+    """fp32-storage emulation of the Inception trunk on a small odd-sized clip (TF-SAME asymmetric pads,
+    branch concat by channel slices) against the oracle's Mixed_5c tap."""
+    _emulated(monkeypatch, fp32=True)
+    g = torch.Generator().manual_seed(4)
+    x = torch.rand(1, 3, 16, 72, 88, generator=g)
+    sd = M.calibrated_state_dict("i3d", 8, torch.rand(1, 3, 16, 224, 224, generator=g), feature_mean=None)
+    taps = {}
+    with torch.no_grad():
+        try:
+            M.i3d_extract_features(sd, x, taps=taps)
+        except RuntimeError:
+            pass  # AvgPool3d([2,7,7]) cannot run on the small map; the trunk taps are what we compare
+    ex = engine.I3DExecutor(sd, "cpu")
+    fmap = ex.run_trunk(_cl_fp32(x))
+    m = _cases.parity_metrics(fmap.to_ncdhw(), taps["Mixed_5c"])
+    assert m["max_abs"] < 1e-3 and m["cos"] > 0.999999, m
+    with pytest.raises(RuntimeError, match="AvgPool3d"):
+        ex.run(_cl_fp32(x))
+
+
+def test_snippet_indexing_and_crops_match_oracle():
+    for n in (0, 1, 10, 16, 31, 32, 33, 64, 70, 100, 7001):
+        d = extraction.dali_snippet_frames(n)
+        assert d.tolist() == M.dali_snippet_frames(n) or (n == 0 and d.shape[0] == 0)
+        s = extraction.shanghai_snippet_frames(n)
+        assert s.tolist() == np.asarray(M.shanghai_snippet_frames(n)).reshape(-1, 16).tolist()
+    for (h, w) in ((240, 320), (480, 856), (360, 640)):
+        for nc in (1, 5, 10):
+            (ch, cw), boxes = extraction.crop_boxes(h, w, nc)
+            assert (ch, cw) == P.crop_size(h, w) and boxes == P.multi_crop_boxes(h, w, ch, cw, nc)
+    assert extraction.crop_boxes(480, 856, 1, square_from_h=True)[0] == (384, 384)
+    assert extraction.crop_boxes(480, 856, 1, square_from_h=True)[1] == [(48, 236, 0)]
+
+
+def test_feature_path_and_resume(tmp_path):
+    assert extraction.feature_path("out", "/d/Videos/Abuse/Abuse001_x264.mp4") == os.path.join("out", "Abuse001_x264.npy")
+    assert extraction.feature_path("out", "/d/01_001.avi") == os.path.join("out", "01_001.npy")
+
+    class Fake:
+        calls = []
+
+        def extract_video(self, frames):
+            Fake.calls.append(int(frames.shape[0]))
+            return np.full((extraction.dali_snippet_frames(frames.shape[0]).shape[0], 4), float(frames.shape[0]))
+
+    vids = [(f"/x/v{i}.mp4", 40 + 10 * i, (lambda n=40 + 10 * i: torch.zeros(n, 2, 2, 3, dtype=torch.uint8))) for i in range(5)]
+    np.save(tmp_path / "v2.npy", np.zeros((1, 4)))  # already extracted -> skipped (dali_extraction.py:121)
+    written = extraction.extract_dataset(Fake(), vids, str(tmp_path), log=lambda *_: None)
+    assert sorted(os.path.basename(w) for w in written) == ["v0.npy", "v1.npy", "v3.npy", "v4.npy"]
+    assert 60 not in Fake.calls
+    a = np.load(tmp_path / "v4.npy")
+    assert a.dtype == np.float64 and a.shape == (3, 4)
+
+
+def test_shard_videos_properties():
+    rs = np.random.RandomState(0)
+    lengths = rs.randint(100, 30000, 97).tolist()
+    for ws in (1, 2, 4, 8):
+        shards = extraction.shard_videos(lengths, ws)
+        flat = sorted(i for s in shards for i in s)
+        assert flat == list(range(97))                      # a partition: every video exactly once
+        loads = [sum(lengths[i] for i in s) for s in shards]
+        assert max(loads) - min(loads) <= max(lengths)      # LPT balance bound

@@ -1,0 +1,98 @@
+"""CPU tests that pin the ORACLE (oracle/) against the golden vectors produced by the unmodified
+reference (tests/golden/make_golden.py) and against torchvision / Pillow themselves."""
+import numpy as np
+import pytest
+import torch
+import torchvision.transforms.functional as TF
+
+import _cases
+from oracle import models as M
+from oracle import preprocess as P
+
+G = _cases.golden()
+
+
+@pytest.mark.parametrize("name", list(_cases.CASES))
+def test_oracle_reproduces_reference_features(name):
+    """weights + clip regenerated from seeds, oracle forward == features of the real reference run."""
+    clip = _cases.case_clip(name)
+    assert str(G[f"{name}/clip_sha"]) == __import__("hashlib").sha256(np.ascontiguousarray(clip).tobytes()).hexdigest()[:16]
+    x, enc_in, feat = _cases.oracle_features(name, clip)
+    ref = torch.from_numpy(G[f"{name}/features"])
+    m = _cases.parity_metrics(feat, ref)
+    assert m["max_abs"] < 2e-4 and m["cos"] > 0.999999, m
+    a = enc_in.reshape(-1).numpy()
+    st = G[f"{name}/anon_stats"]
+    assert abs(a.mean() - st[0]) < 1e-5 and abs(a.std() - st[1]) < 1e-5
+    idx = np.random.RandomState(7).randint(0, a.size, 256)
+    # anon_samples were taken from the [16,3,h,w] frames tensor, which is the same memory order as enc_in
+    assert np.abs(a[idx] - G[f"{name}/anon_samples"]).max() < 1e-4
+
+
+@pytest.mark.parametrize("name", list(_cases.CASES))
+def test_oracle_is_discriminative(name):
+    """different clips give measurably different features (stock init would give cos 1.0)."""
+    ctrl = float(G[f"{name}/control_cos"])
+    assert ctrl < 0.9995, ctrl
+    f1, f2 = G[f"{name}/features"], G[f"{name}/control_features"]
+    assert np.linalg.norm(f1 - f2) / np.linalg.norm(f1) > 0.03
+
+
+def test_glue_plane_map():
+    """dali_extraction.py:171-173: encoder (channel c', time t') holds anonymizer plane 16*c' + t' = 3*t + c."""
+    probe = G["glue/probe"]  # [3,16] of 10*t + c from the reference's own view/reshape
+    pm = M.plane_map(16, 3)
+    for (t, c), (ce, te) in pm.items():
+        assert probe[ce, te] == 10 * t + c
+    x = torch.arange(16 * 3 * 2 * 2, dtype=torch.float32).reshape(1, 16, 3, 2, 2)
+    ident = {k: v.clone() for k, v in {}.items()}
+    out = x.reshape(-1, 3, 2, 2).reshape(1, 3, 16, 2, 2)
+    for (t, c), (ce, te) in pm.items():
+        assert torch.equal(out[0, ce, te], x[0, t, c])
+
+
+@pytest.mark.parametrize("n", [10, 16, 20, 31, 32, 33, 64, 70, 100])
+def test_shanghai_indexing_matches_reference_reader(n):
+    got = np.asarray(M.shanghai_snippet_frames(n), dtype=np.int64).reshape(-1, 16)
+    assert np.array_equal(got, G[f"shanghai_idx/{n}"])
+
+
+def test_dali_indexing():
+    s = M.dali_snippet_frames(70)
+    assert len(s) == 3 and s[0] == [2 * j for j in range(16)] and s[1][0] == 32
+    assert s[2] == [64, 66, 68] + [-1] * 13          # pad_sequences=True: tail kept, missing frames zero
+    assert len(M.dali_snippet_frames(64)) == 2 and len(M.dali_snippet_frames(65)) == 3
+    assert M.dali_snippet_frames(0) == []
+
+
+def test_preprocess_aa_matches_torchvision():
+    rs = np.random.RandomState(0)
+    for (h, w) in [(240, 320), (360, 640), (120, 160)]:
+        v = rs.randint(0, 256, (2, h, w, 3)).astype(np.uint8)
+        mine = P.dali_val_augmentations(v)
+        vt = torch.from_numpy(v).float().permute(0, 3, 1, 2) / 255.
+        ch, cw = int(h * 0.8), int(w * 0.8)
+        ref = TF.resize(TF.center_crop(vt, (ch, cw)), (224, 224), antialias=True).numpy()
+        assert np.abs(mine - ref).max() < 2e-6
+
+
+def test_preprocess_pil_bit_exact():
+    rs = np.random.RandomState(1)
+    for (h, w) in [(480, 856), (300, 400), (240, 320)]:
+        f = rs.randint(0, 256, (h, w, 3)).astype(np.uint8)
+        mine = P.shanghai_augmentation(f)
+        im = TF.to_pil_image(f)
+        c = int(h * 0.8)
+        im = TF.resize(TF.center_crop(im, (c, c)), (224, 224), antialias=True)
+        assert np.array_equal(mine, TF.to_tensor(im).numpy())
+
+
+def test_multi_crop_order_matches_torchvision():
+    h, w, ch, cw = 24, 32, 19, 25
+    img = torch.arange(h * w, dtype=torch.float32).reshape(1, h, w)
+    for n, crops in ((5, TF.five_crop(img, (ch, cw))), (10, TF.ten_crop(img, (ch, cw)))):
+        boxes = P.multi_crop_boxes(h, w, ch, cw, n)
+        for (t, l, fl), ref in zip(boxes, crops):
+            src = img.flip(-1) if fl else img
+            assert torch.equal(src[:, t:t + ch, l:l + cw], ref)
+    assert P.multi_crop_boxes(h, w, ch, cw, 1)[0] == P.multi_crop_boxes(h, w, ch, cw, 5)[4]
