@@ -218,7 +218,7 @@ def main():
     for i in range(2):
         step_resident(i)
     torch.cuda.synchronize()
-    conv_ms = sum(a.elapsed_time(b) for a, b in ops.CONV_EVENTS) / 2.0
+    conv_ms = sum(a.elapsed_time(b) for a, b, _ in ops.CONV_EVENTS) / 2.0
     n_conv = len(ops.CONV_EVENTS) // 2
     ops.CONV_EVENTS = None
 

@@ -151,7 +151,7 @@ def conv_forward(x, pc, y, res=None, act=L.ACT_RELU, feed=L.FEED_AUTO, y_fp32=Fa
         e0.record()
         L.check(L.lib().tedspad_conv_forward(C.byref(d), _stream()), "tedspad_conv_forward")
         e1.record()
-        CONV_EVENTS.append((e0, e1))
+        CONV_EVENTS.append((e0, e1, (x.N, x.D, x.H, x.W, x.C, pc.cout, pc.k, pc.stride, y.D, y.H, y.W, pc.cin)))
         return y
     L.check(L.lib().tedspad_conv_forward(C.byref(d), _stream()), "tedspad_conv_forward")
     return y
@@ -195,8 +195,9 @@ def avgpool_features(x, kd=0):
 def preprocess(frames_u8, desc_i32, crop_hw, y, resample=L.RESAMPLE_AA_FLOAT, frames_f32=None):
     """frames_u8: cuda uint8 [F,Hs,Ws,3]; desc_i32: cuda int32 [n_out,4] = (src_frame, top, left, hflip)."""
     _require_cuda(frames_u8, "preprocess")
+    frames_u8 = frames_u8.contiguous()
     F_, Hs, Ws, ch = frames_u8.shape
-    assert ch == 3 and frames_u8.dtype == torch.uint8 and frames_u8.is_contiguous()
+    assert ch == 3 and frames_u8.dtype == torch.uint8
     assert desc_i32.dtype == torch.int32 and desc_i32.is_contiguous() and desc_i32.shape[1] == 4
     yd = y.desc()
     fo = frames_f32.data_ptr() if frames_f32 is not None else None

@@ -63,7 +63,7 @@ def test_hot_path_parity(name):
         desc = np.zeros((16, 4), dtype=np.int32)
         desc[:, 0] = np.arange(16)
         desc[:, 1], desc[:, 2] = boxes[0][0], boxes[0][1]
-        f = ext.features_of_clips(torch.from_numpy(clip).cuda(), desc, (ch, cw))
+        f = ext.features_of_clips(torch.from_numpy(np.ascontiguousarray(clip)).cuda(), desc, (ch, cw))
         torch.cuda.synchronize()
         feats[which], refs[which] = f.reshape(-1).float().cpu(), f_ref
         if which == "test":
