@@ -72,23 +72,14 @@ def sha(t):
     return hashlib.sha256(np.ascontiguousarray(t).tobytes()).hexdigest()[:16]
 
 
-CASES = [
-    # name, encoder arch, source frame size (H, W), output reso, weight seeds (fa, ft), clip seeds (calib, test, control)
-    ("unet_i3d_224", "i3d", (240, 320), (224, 224), (1, 2), (100, 101, 102)),
-    ("unet_largei3d_224", "largei3d", (240, 320), (224, 224), (1, 3), (100, 101, 102)),
-    ("unet_r3d18_112", "r3d_18", (120, 160), (112, 112), (4, 5), (110, 111, 112)),
-]
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import _cases  # noqa: E402  (the case table, seeds and synthetic-init regimes are shared with the tests)
+
+CASES = [(name,) + spec for name, spec in _cases.CASES.items()]
 
 
-def build_case_weights(arch, hw, reso, wseeds, calib_seed):
-    """Shared with the tests (tests/_cases.py calls this too): deterministic weights for a case."""
-    clip = M.structured_clip_u8(calib_seed, 16, hw[0], hw[1])
-    x = torch.from_numpy(P.dali_val_augmentations(clip, reso))  # [16,3,h,w]
-    with torch.no_grad():
-        sd_fa = M.calibrated_state_dict("unet", wseeds[0], x)
-        enc_in = M.anonymize_and_reshape(sd_fa, x.unsqueeze(0))
-        sd_ft = M.calibrated_state_dict(arch, wseeds[1], enc_in)
-    return sd_fa, sd_ft
+def build_case_weights(name):
+    return _cases.case_weights(name)
 
 
 def shanghai_index_golden():
@@ -130,7 +121,7 @@ def main():
     torch.set_num_threads(os.cpu_count())
     out = {}
     for name, arch, hw, reso, wseeds, cseeds in CASES:
-        sd_fa, sd_ft = build_case_weights(arch, hw, reso, wseeds, cseeds[0])
+        sd_fa, sd_ft = build_case_weights(name)
         fa = load_fa_model(arch="unet")
         ft = load_ft_model(arch=arch, num_classes=102, kin_pretrained=False)
         missing = set(fa.state_dict().keys()) ^ set(sd_fa.keys())
