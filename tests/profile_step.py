@@ -27,10 +27,12 @@ for _ in range(2):
 torch.cuda.synchronize()
 ops.CONV_EVENTS = []
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+torch.cuda.profiler.start()          # ncu --profile-from-start off captures exactly this steady-state step
 e0.record()
 ext.features_of_clips(frames, desc, (ch, cw))
 e1.record()
 torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 tot = e0.elapsed_time(e1)
 rows = []
 for a, b, (n, d, h, w, c, co, k, s, od, oh, ow, cin) in ops.CONV_EVENTS:
