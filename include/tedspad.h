@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define TEDSPAD_ABI_VERSION 1
+#define TEDSPAD_ABI_VERSION 2
 
 enum { TEDSPAD_ACT_NONE = 0, TEDSPAD_ACT_RELU = 1, TEDSPAD_ACT_SIGMOID = 2 };
 /* A-operand feed of the implicit GEMM: AUTO picks FLAT when legal. */
@@ -79,6 +79,85 @@ typedef struct tedspad_conv {
 } tedspad_conv;
 
 int tedspad_conv_forward(const tedspad_conv* p, void* stream);
+
+/*
+ * SLAB feed of the implicit GEMM: convolutions whose A operand is read in place from ONE spatial
+ * slab of the input held in shared memory, every filter tap being a shifted UMMA descriptor over
+ * that slab (no im2col copies, one TMA box per tile and K stage, weights resident in shared
+ * memory for the whole persistent CTA).  An output tile is 16 rows x (8*tm) columns of one image.
+ *   TEDSPAD_SLAB_3X3     Conv2d 3x3 stride 1 pad 1, Cin % 64 == 0, Cout in {16..256} with
+ *                        9*Cin*Cout*2 bytes <= ~150 KB: the 64/128-channel DoubleConv layers of the
+ *                        anonymizer at 224^2 / 112^2 (aux_code/models/unet_parts.py:15-22).  x must
+ *                        carry a zero halo >= 1 in H and W.  128-byte swizzled slab rows (one pixel
+ *                        x 64 channels); tap (ky,kx) = descriptor start + (ky*slab_w + kx) rows.
+ *   TEDSPAD_SLAB_STEM2D  Conv2d 3x3 stride 1 pad 1 over a Cin<=8 image stored with 8 channels per
+ *                        pixel (16 bytes): the anonymizer's first convolution (unet_parts.py:15).
+ *                        Un-swizzled K-major descriptors with OVERLAPPING K-adjacent core matrices
+ *                        (LBO = 16 B = one pixel): row m of tap kx is pixel m + kx of the slab row.
+ *   TEDSPAD_SLAB_STEM3D  Conv3d (kd,7,7) stride (sd,2,2) over a Cin<=4 clip stored with 4 channels
+ *                        per pixel (8 bytes): Conv3d_1a_7x7 (aux_code/models/i3d.py:238-239),
+ *                        I3Res50.conv1 (large_i3d.py:135), torchvision BasicStem (video/resnet.py:
+ *                        173-181).  Same overlapped descriptors; one UMMA row step (16 B) = the
+ *                        stride of 2 pixels, one K chunk = 2 pixels x 4 channels.
+ * Optional fused epilogues (TEDSPAD_SLAB_3X3 only): MaxPool2d(2) of the output written to `pool`
+ * (unet_parts.py:33), and OutConv 1x1 (Cout->3) + sigmoid written as planar [N][3][H][W] images
+ * (unet_parts.py:71-77, unet_model.py:36-37) in which case y.ptr may be NULL.
+ * `w_image` holds the weights in the exact shared-memory image the kernel reads; build it with
+ * tedspad_conv_slab_pack() from the standard packed layout of tedspad_conv.
+ */
+enum { TEDSPAD_SLAB_3X3 = 0, TEDSPAD_SLAB_STEM2D = 1, TEDSPAD_SLAB_STEM3D = 2 };
+
+typedef struct tedspad_conv_slab {
+  tedspad_tensor x;         /* bf16 input view (see kinds above) */
+  tedspad_tensor y;         /* bf16 output view, interior written only; ptr may be NULL with oc_w */
+  const void* w_image;      /* device: weights, shared-memory image (tedspad_conv_slab_pack) */
+  const float* bias;        /* device: fp32 [Cout_pad] */
+  tedspad_tensor pool;      /* optional fused MaxPool2d(2) output view (ptr NULL = none) */
+  const float* oc_w;        /* optional fused OutConv: device fp32 [3][Cout]; NULL = none */
+  const float* oc_b;        /* device fp32 [3] */
+  void* oc_planes;          /* device bf16 [N][3][H][W] */
+  float* oc_frames;         /* optional device fp32 [N][3][H][W] */
+  int32_t kind;             /* TEDSPAD_SLAB_* */
+  int32_t Cout, Cout_pad;   /* Cout_pad = UMMA N (multiple of 16, <= 256) */
+  int32_t kd, kh, kw;
+  int32_t sd, sh, sw;
+  int32_t pd, ph, pw;       /* front pads */
+  int32_t act;              /* TEDSPAD_ACT_* */
+  int32_t tm;               /* 8-column groups per tile: 1 or 2; 0 = auto */
+  int32_t max_ctas;         /* persistent grid cap; 0 = number of SMs */
+} tedspad_conv_slab;
+
+/* Everything the kernel derives from a tedspad_conv_slab: exposed so that the CPU test-suite can
+ * replay the TMA box / UMMA descriptor arithmetic without a GPU (tests/_slabsim.py). */
+#define TEDSPAD_SLAB_MAX_MMA 112
+typedef struct tedspad_slab_plan {
+  int32_t tm, n_tile, k_stages, n_mma, stages, tmem_cols;
+  int32_t box[5];           /* TMA box, elements: {c, w, h, d, n} */
+  int32_t tdim[5];          /* TMA tensor dims, elements */
+  int64_t tstride[4];       /* TMA global strides, bytes (dims 1..4) */
+  int64_t tbase_off;        /* byte offset of the TMA base from x.ptr */
+  int32_t swizzle128;       /* slab written with the 128-byte swizzle */
+  int32_t slab_bytes, slab_stride, w_bytes, smem_bytes;
+  int32_t a_layout, a_lbo, a_sbo, b_layout, b_lbo, b_sbo;   /* UMMA smem descriptor fields, bytes */
+  int32_t half_a_off;       /* A byte offset of the second 8-column group */
+  int32_t c_step, x_step, x_off, y_step, y_off, z_step, z_off, z_kstep;  /* slab origin per tile / K stage */
+  int32_t tiles_x, tiles_y, tiles_z, total_tiles;
+  uint32_t tab[2 * TEDSPAD_SLAB_MAX_MMA];   /* per (k_stage, mma): {A byte offset in slab, B byte offset in image} */
+} tedspad_slab_plan;
+
+int tedspad_conv_slab_plan(const tedspad_conv_slab* p, tedspad_slab_plan* out);   /* host only, no GPU needed */
+/* Standard packed weights (bf16 [Cout_pad][K_pad], K = (kd,kh,kw,cin_pad), see tedspad_conv) ->
+ * shared-memory image for `kind` (device to device).  Returns the image size through *image_bytes
+ * when image == NULL (no GPU needed for that query). */
+int tedspad_conv_slab_pack(int32_t kind, const void* w_std, int32_t Cout_pad, int32_t K_pad, int32_t cin_pad,
+                           int32_t kd, int32_t kh, int32_t kw, int32_t pw_front, void* image, int64_t* image_bytes,
+                           void* stream);
+int tedspad_conv_slab_forward(const tedspad_conv_slab* p, void* stream);
+
+/* Planar bf16 images [B*T][3][H][W] (the anonymizer's output) -> encoder input view [B][T][H][W][>=3]
+ * through the raw-reshape glue of feature_extraction/dali_extraction.py:171-173: plane p = 3*t + c
+ * of clip b becomes encoder channel p / T at time p % T.  Channels >= 3 of y are written as zero. */
+int tedspad_planes_to_clip(const void* planes, const tedspad_tensor* y, int32_t T, void* stream);
 
 /*
  * Max pooling over (D,H,W) windows, channels-last.  Out-of-range taps contribute `0` when

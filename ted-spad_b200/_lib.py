@@ -13,7 +13,9 @@ LIB_PATH = os.path.join(_HERE, "libtedspad.so")
 ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
 FEED_AUTO, FEED_FLAT_TMA, FEED_GATHER = 0, 1, 2
 RESAMPLE_AA_FLOAT, RESAMPLE_PIL_U8 = 0, 1
-ABI_VERSION = 1
+SLAB_3X3, SLAB_STEM2D, SLAB_STEM3D = 0, 1, 2
+SLAB_MAX_MMA = 112
+ABI_VERSION = 2
 
 
 class TensorDesc(C.Structure):
@@ -30,12 +32,36 @@ class ConvDesc(C.Structure):
                     "pd", "ph", "pw", "act", "y_fp32", "feed", "n_tile", "max_ctas")]
 
 
+class ConvSlabDesc(C.Structure):
+    """struct tedspad_conv_slab"""
+    _fields_ = [("x", TensorDesc), ("y", TensorDesc), ("w_image", C.c_void_p), ("bias", C.c_void_p),
+                ("pool", TensorDesc), ("oc_w", C.c_void_p), ("oc_b", C.c_void_p), ("oc_planes", C.c_void_p),
+                ("oc_frames", C.c_void_p)] + [(n, C.c_int32) for n in (
+                    "kind", "Cout", "Cout_pad", "kd", "kh", "kw", "sd", "sh", "sw", "pd", "ph", "pw", "act", "tm",
+                    "max_ctas")]
+
+
+class SlabPlan(C.Structure):
+    """struct tedspad_slab_plan"""
+    _fields_ = ([(n, C.c_int32) for n in ("tm", "n_tile", "k_stages", "n_mma", "stages", "tmem_cols")] +
+                [("box", C.c_int32 * 5), ("tdim", C.c_int32 * 5), ("tstride", C.c_int64 * 4), ("tbase_off", C.c_int64)] +
+                [(n, C.c_int32) for n in (
+                    "swizzle128", "slab_bytes", "slab_stride", "w_bytes", "smem_bytes", "a_layout", "a_lbo", "a_sbo",
+                    "b_layout", "b_lbo", "b_sbo", "half_a_off", "c_step", "x_step", "x_off", "y_step", "y_off",
+                    "z_step", "z_off", "z_kstep", "tiles_x", "tiles_y", "tiles_z", "total_tiles")] +
+                [("tab", C.c_uint32 * (2 * SLAB_MAX_MMA))])
+
+
 # every symbol include/tedspad.h declares: (name, restype, argtypes)
 _TP = C.POINTER(TensorDesc)
 _I = C.c_int32
 _V = C.c_void_p
 SYMBOLS = {
     "tedspad_conv_forward": (C.c_int, [C.POINTER(ConvDesc), _V]),
+    "tedspad_conv_slab_plan": (C.c_int, [C.POINTER(ConvSlabDesc), C.POINTER(SlabPlan)]),
+    "tedspad_conv_slab_pack": (C.c_int, [_I, _V, _I, _I, _I, _I, _I, _I, _I, _V, C.POINTER(C.c_int64), _V]),
+    "tedspad_conv_slab_forward": (C.c_int, [C.POINTER(ConvSlabDesc), _V]),
+    "tedspad_planes_to_clip": (C.c_int, [_V, _TP, _I, _V]),
     "tedspad_maxpool": (C.c_int, [_TP, _TP, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _V]),
     "tedspad_upsample2x": (C.c_int, [_TP, _TP, _V]),
     "tedspad_outconv_sigmoid": (C.c_int, [_TP, _V, _V, _TP, _I, _V, _V]),

@@ -42,7 +42,7 @@ class CudaModule(nn.Module):
         return self.__dict__["_tsp_executor"]
 
     def _to_cl(self, x, name="in"):
-        """fp32 [B,3,T,H,W] / [N,3,H,W] -> channels-last bf16 [.., 8] (channels 3..7 zero)."""
+        """fp32 [B,3,T,H,W] / [N,3,H,W] -> channels-last bf16 [.., 4|8] (pad channels zero)."""
         ex = self.__dict__["_tsp_executor"]
         if x.dim() == 4:
             n, c, h, w = x.shape
@@ -51,5 +51,7 @@ class CudaModule(nn.Module):
             n, c, t, h, w = x.shape
         if c != 3:
             raise RuntimeError(f"{type(self).__name__}: expected 3 input channels, got {c}")
-        buf = ex.bufs.get(name, n, t, h, w, 8)
+        from tedspad_b200 import engine
+        # clips feed an encoder stem (4-channel pixels for the SLAB stem); frames feed the UNet (8-channel pixels)
+        buf = ex.bufs.get(name, n, t, h, w, engine.ENC_IN_CHANNELS if x.dim() == 5 else 8)
         return ops.nchw_to_cl(x, buf)

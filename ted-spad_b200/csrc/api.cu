@@ -77,6 +77,32 @@ int encode_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint
   return 0;
 }
 
+int encode_tmap_5d_bf16(CUtensorMap* out, const void* base, const uint64_t dims[5], const uint64_t strides_bytes[4],
+                        const uint32_t box[5], bool swizzle128) {
+  EncodeTiledFn fn = get_encode_fn();
+  TSP_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+  TSP_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "tensor map: base %p must be 16-byte aligned", base);
+  cuuint64_t d[5], st[4];
+  cuuint32_t b[5], es[5] = {1, 1, 1, 1, 1};
+  for (int i = 0; i < 5; ++i) {
+    d[i] = dims[i];
+    b[i] = box[i];
+    TSP_CHECK(dims[i] >= 1 && box[i] >= 1 && box[i] <= 256, "tensor map: bad dim/box %d: %llu / %u", i,
+              (unsigned long long)dims[i], box[i]);
+  }
+  for (int i = 0; i < 4; ++i) {
+    st[i] = strides_bytes[i];
+    TSP_CHECK(st[i] % 16 == 0, "tensor map: stride %d = %llu bytes is not a multiple of 16", i,
+              (unsigned long long)st[i]);
+  }
+  TSP_CHECK((box[0] * 2) % 16 == 0 && (!swizzle128 || box[0] * 2 == 128), "tensor map: bad inner box %u", box[0]);
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), d, st, b, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  TSP_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(5d) failed with CUresult %d", (int)r);
+  return 0;
+}
+
 }  // namespace tsp
 
 extern "C" int tedspad_abi_version(void) { return TEDSPAD_ABI_VERSION; }

@@ -34,6 +34,11 @@ void set_error(const char* fmt, ...);
 int encode_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
                         uint32_t box_inner, uint32_t box_outer);
 
+// 5-D bf16 tensor map (dims/box innermost first, strides of dims 1..4 in bytes), zero fill out of
+// bounds, optional 128-byte swizzle (box[0] * 2 must then be 128 bytes).
+int encode_tmap_5d_bf16(CUtensorMap* out, const void* base, const uint64_t dims[5], const uint64_t strides_bytes[4],
+                        const uint32_t box[5], bool swizzle128);
+
 int num_sms();
 
 inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }

@@ -1,0 +1,605 @@
+// SLAB feed of the implicit-GEMM convolution (tcgen05.mma, fp32 accumulators in TMEM).
+//
+// An output tile is 16 rows x (8*tm) columns of one image (tm = 1 or 2 "halves" of 128 GEMM rows
+// each: row m = 8*g + r  <->  output pixel (y0 + g, x0 + 8*half + r)).  For every K stage the
+// producer issues ONE 5-D TMA box that drops the input slab the tile needs (tile + filter reach)
+// into shared memory; every filter tap is then just a UMMA shared-memory descriptor whose start
+// address is shifted inside that slab:
+//
+//   TEDSPAD_SLAB_3X3     slab rows = pixels x 64 channels (128 B, SWIZZLE_128B); an 8-row core group
+//                        = 8 consecutive x of one image row; SBO = slab row pitch; tap (ky,kx) =
+//                        start + (ky*slab_w + kx) * 128 B.  Input bytes cross L2->SM once per tile
+//                        instead of once per tap (9x less operand traffic than the FLAT feed).
+//   TEDSPAD_SLAB_STEM*   un-swizzled K-major descriptors whose K-adjacent core matrices OVERLAP
+//                        (LBO = 16 B): GEMM row m, K chunk j reads the 16 bytes at (m + j) * 16 B of
+//                        a slab row, i.e. the im2col window of a small-Cin convolution in place.
+//
+// The weights live in shared memory for the whole life of the persistent CTA, already in the layout
+// the B descriptors read (tedspad_conv_slab_pack); the MMA issuer walks a host-built table of
+// (A offset, B offset) pairs, so the kernel itself knows nothing about filter geometry.
+//
+//   warp 0      TMA producer   weights once (cp.async.bulk), then one slab box per (tile, K stage)
+//   warp 1      MMA issuer     one thread, n_mma x tm tcgen05.mma per K stage
+//   warp 2      TMEM allocator
+//   warps 4-7   epilogue       tcgen05.ld -> +bias -> ReLU -> bf16 stores; optional fused
+//                              MaxPool2d(2) (warp shuffles) and OutConv 1x1 + sigmoid
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace tsp {
+
+constexpr int SLAB_SMEM_BUDGET = 227 * 1024;
+constexpr int SLAB_TAIL_BYTES = 1024 /*bias*/ + 1024 /*outconv w,b*/ + 256 /*barriers*/;
+constexpr int SLAB_MAX_STAGES = 6;
+
+struct SlabKParams {
+  CUtensorMap tmA;
+  const uint8_t* w_image;
+  const float* bias;
+  int tm, n_tile, k_stages, n_mma, stages, tmem_cols;
+  int slab_bytes, slab_stride, w_bytes, w_stride, zero_slabs;
+  int half_a_off;
+  int c_step, x_step, x_off, y_step, y_off, z_step, z_off, z_kstep;
+  int tiles_x, tiles_y, tiles_z, total_tiles;
+  uint64_t a_desc, b_desc;
+  // epilogue
+  __nv_bfloat16* y;
+  int OH, OW, yDp, yHp, yWp, ypd, yph, ypw, y_ld, y_coff, Cout, act;
+  __nv_bfloat16* pool;
+  int PH, PW, pHp, pWp, pph, ppw, p_ld, p_coff;
+  const float* oc_w;
+  const float* oc_b;
+  __nv_bfloat16* oc_planes;
+  float* oc_frames;
+  uint2 tab[TEDSPAD_SLAB_MAX_MMA];
+};
+
+__device__ __forceinline__ uint32_t pack_bf162(float a, float b) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t max_bf162(uint32_t a, uint32_t b) {
+  const __nv_bfloat162 m = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+  return *reinterpret_cast<const uint32_t*>(&m);
+}
+
+__global__ void __launch_bounds__(256, 1) conv_slab_kernel(const __grid_constant__ SlabKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  const int S = p.stages;
+  uint8_t* smW = smem;
+  uint8_t* smS = smem + p.w_stride;
+  float* sm_bias = reinterpret_cast<float*>(smS + S * p.slab_stride);
+  float* sm_ocw = sm_bias + 256;        // [3][Cout] then [3] bias
+  uint64_t* full = reinterpret_cast<uint64_t*>(sm_ocw + 256);
+  uint64_t* empty = full + SLAB_MAX_STAGES;
+  uint64_t* tfull = empty + SLAB_MAX_STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint64_t* wbar = tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) tma_prefetch_desc(&p.tmA);
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull + a, 1);
+      mbar_init(tempty + a, 4);
+    }
+    mbar_init(wbar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, p.tmem_cols);
+    tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < p.n_tile; i += blockDim.x) sm_bias[i] = p.bias[i];
+  if (p.oc_w != nullptr) {
+    for (int i = threadIdx.x; i < 3 * p.Cout; i += blockDim.x) sm_ocw[i] = p.oc_w[i];
+    if (threadIdx.x < 3) sm_ocw[3 * p.Cout + threadIdx.x] = p.oc_b[threadIdx.x];
+  }
+  if (p.zero_slabs) {
+    // un-swizzled stems read a few bytes past the TMA box (zero-weight K padding): keep them finite
+    uint4* z = reinterpret_cast<uint4*>(smS);
+    const int n16 = S * p.slab_stride / 16;
+    for (int i = threadIdx.x; i < n16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_smem();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      mbar_arrive_expect_tx(wbar, static_cast<uint32_t>(p.w_bytes));
+      for (int off = 0; off < p.w_bytes; off += 16384)
+        bulk_copy_g2s(smW + off, p.w_image + off, static_cast<uint32_t>(min(16384, p.w_bytes - off)), wbar);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int t = tile;
+        const int tx = t % p.tiles_x; t /= p.tiles_x;
+        const int ty = t % p.tiles_y; t /= p.tiles_y;
+        const int tz = t % p.tiles_z;
+        const int n = t / p.tiles_z;
+        const int cx = tx * p.x_step + p.x_off, cy = ty * p.y_step + p.y_off, cz = tz * p.z_step + p.z_off;
+        for (int ks = 0; ks < p.k_stages; ++ks) {
+          mbar_wait(empty + s, ph ^ 1);
+          mbar_arrive_expect_tx(full + s, static_cast<uint32_t>(p.slab_bytes));
+          tma_load_5d(smS + s * p.slab_stride, &p.tmA, full + s, ks * p.c_step, cx, cy, cz + ks * p.z_kstep, n);
+          if (++s == S) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // -------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, p.n_tile);
+      const uint32_t w_addr = smem_u32(smW);
+      const uint64_t half_step = static_cast<uint64_t>(p.half_a_off >> 4);
+      mbar_wait(wbar, 0);
+      int s = 0, as = 0;
+      uint32_t ph = 0, aph = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        mbar_wait(tempty + as, aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * p.tm * p.n_tile);
+        for (int ks = 0; ks < p.k_stages; ++ks) {
+          mbar_wait(full + s, ph);
+          tc_fence_after();
+          const uint32_t slab_addr = smem_u32(smS + s * p.slab_stride);
+          const uint2* tab = p.tab + ks * p.n_mma;
+          for (int i = 0; i < p.n_mma; ++i) {
+            const uint2 e = tab[i];
+            const uint64_t ad = p.a_desc | static_cast<uint64_t>(((slab_addr + e.x) & 0x3FFFFu) >> 4);
+            const uint64_t bd = p.b_desc | static_cast<uint64_t>(((w_addr + e.y) & 0x3FFFFu) >> 4);
+            const uint32_t acc = (ks | i) != 0 ? 1u : 0u;
+            umma_bf16(d_tmem, ad, bd, idesc, acc);
+            if (p.tm == 2) umma_bf16(d_tmem + p.n_tile, ad + half_step, bd, idesc, acc);
+          }
+          umma_commit(empty + s);
+          if (++s == S) { s = 0; ph ^= 1; }
+        }
+        umma_commit(tfull + as);
+        as ^= 1;
+        if (as == 0) aph ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ---------------------------------------------------------------- epilogue
+    const int ew = warp - 4;          // TMEM lane quarter
+    const int g = ew * 4 + (lane >> 3);
+    const int r = lane & 7;
+    int as = 0;
+    uint32_t aph = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      int t = tile;
+      const int tx = t % p.tiles_x; t /= p.tiles_x;
+      const int ty = t % p.tiles_y; t /= p.tiles_y;
+      const int tz = t % p.tiles_z;
+      const int n = t / p.tiles_z;
+      const int oy = ty * 16 + g;
+      mbar_wait(tfull + as, aph);
+      tc_fence_after();
+      for (int h = 0; h < p.tm; ++h) {
+        const int ox = (tx * p.tm + h) * 8 + r;
+        const bool valid = oy < p.OH && ox < p.OW;
+        const long long pix = ((static_cast<long long>(n) * p.yDp + tz + p.ypd) * p.yHp + oy + p.yph) * p.yWp + ox + p.ypw;
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) +
+                               static_cast<uint32_t>((as * p.tm + h) * p.n_tile);
+        float oc[3] = {0.f, 0.f, 0.f};
+        for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(t_row + c0, v);
+          tmem_ld_wait();
+          float f[32];
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(sm_bias + c0 + i);
+            f[i] = __uint_as_float(v[i]) + b4.x;
+            f[i + 1] = __uint_as_float(v[i + 1]) + b4.y;
+            f[i + 2] = __uint_as_float(v[i + 2]) + b4.z;
+            f[i + 3] = __uint_as_float(v[i + 3]) + b4.w;
+          }
+          if (p.act == TEDSPAD_ACT_RELU) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+          }
+          if (p.oc_w != nullptr && c0 < p.Cout) {
+#pragma unroll
+            for (int o = 0; o < 3; ++o) {
+              const float* wr = sm_ocw + o * p.Cout + c0;
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                const float4 w4 = *reinterpret_cast<const float4*>(wr + i);
+                oc[o] = fmaf(f[i], w4.x, oc[o]);
+                oc[o] = fmaf(f[i + 1], w4.y, oc[o]);
+                oc[o] = fmaf(f[i + 2], w4.z, oc[o]);
+                oc[o] = fmaf(f[i + 3], w4.w, oc[o]);
+              }
+            }
+          }
+          uint32_t q[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) q[i] = pack_bf162(f[2 * i], f[2 * i + 1]);
+          if (p.y != nullptr && valid) {
+            __nv_bfloat16* yp = p.y + pix * p.y_ld + p.y_coff + c0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (c0 + 8 * j < p.Cout)
+                *reinterpret_cast<uint4*>(yp + 8 * j) = make_uint4(q[4 * j], q[4 * j + 1], q[4 * j + 2], q[4 * j + 3]);
+          }
+          if (p.pool != nullptr) {
+            // MaxPool2d(2): x partner = lane ^ 1 (r ^ 1), y partner = lane ^ 8 (g ^ 1)
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              q[i] = max_bf162(q[i], __shfl_xor_sync(0xffffffffu, q[i], 1));
+              q[i] = max_bf162(q[i], __shfl_xor_sync(0xffffffffu, q[i], 8));
+            }
+            const int py = oy >> 1, px = ox >> 1;
+            if (((lane & 9) == 0) && py < p.PH && px < p.PW) {
+              const long long ppix = (static_cast<long long>(n) * p.pHp + py + p.pph) * p.pWp + px + p.ppw;
+              __nv_bfloat16* pp = p.pool + ppix * p.p_ld + p.p_coff + c0;
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (c0 + 8 * j < p.Cout)
+                  *reinterpret_cast<uint4*>(pp + 8 * j) = make_uint4(q[4 * j], q[4 * j + 1], q[4 * j + 2], q[4 * j + 3]);
+            }
+          }
+        }
+        if (p.oc_w != nullptr && valid) {
+          const long long plane = static_cast<long long>(p.OH) * p.OW;
+          const long long o0 = static_cast<long long>(n) * 3 * plane + static_cast<long long>(oy) * p.OW + ox;
+#pragma unroll
+          for (int o = 0; o < 3; ++o) {
+            const float sgm = 1.f / (1.f + __expf(-(oc[o] + sm_ocw[3 * p.Cout + o])));
+            p.oc_planes[o0 + o * plane] = __float2bfloat16_rn(sgm);
+            if (p.oc_frames != nullptr) p.oc_frames[o0 + o * plane] = sgm;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty + as);
+      as ^= 1;
+      if (as == 0) aph ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 2) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------ weight image
+struct PackP {
+  const __nv_bfloat16* w_std;
+  __nv_bfloat16* image;
+  int kind, n_tile, K_pad, cin_pad, kd, kh, kw, shift;
+  long long total;  // image elements
+};
+
+// One thread per image element: where does it come from in the standard [Cout_pad][K_pad] layout?
+__global__ void __launch_bounds__(256) slab_pack_kernel(const PackP p) {
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < p.total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    long long src = -1;
+    int n = 0;
+    if (p.kind == TEDSPAD_SLAB_3X3) {
+      // image: [tap*CB + cb] blocks of n_tile rows x 128 B, SWIZZLE_128B, 8-row groups 1024 B apart
+      const long long byte = idx * 2;
+      const int blk_bytes = p.n_tile * 128;
+      const int blk = static_cast<int>(byte / blk_bytes);
+      const int o = static_cast<int>(byte - static_cast<long long>(blk) * blk_bytes);
+      const int grp = o >> 10, row = (o >> 7) & 7, chunk_sw = (o >> 4) & 7, within = (o & 15) >> 1;
+      n = grp * 8 + row;
+      const int k = ((chunk_sw ^ row) << 3) + within;
+      const int cin = p.cin_pad, cb_n = cin / 64;
+      const int tap = blk / cb_n, cb = blk - tap * cb_n;
+      src = static_cast<long long>(tap) * cin + cb * 64 + k;
+    } else {
+      // image: [mma][chunk j (2)][n][8 elements], un-swizzled
+      long long t = idx;
+      const int e = static_cast<int>(t & 7); t >>= 3;
+      n = static_cast<int>(t % p.n_tile); t /= p.n_tile;
+      const int j = static_cast<int>(t & 1); t >>= 1;
+      const int mma = static_cast<int>(t);
+      if (p.kind == TEDSPAD_SLAB_STEM2D) {
+        // mma = ky*2 + q; chunk = tap kx = 2q + j (kx == 3: zero), 8 channels of one pixel
+        const int ky = mma >> 1, q = mma & 1, kx = 2 * q + j;
+        if (kx < 3 && e < p.cin_pad) src = static_cast<long long>(ky * 3 + kx) * p.cin_pad + e;
+      } else {
+        // mma = (kt*kh + ky)*2 + q; chunk = pixel pair pp = 2q + j -> pixels 2pp, 2pp+1 (4 channels each);
+        // filter tap kx = pixel - shift (shift = 1 when the front pad is odd)
+        const int q = mma & 1;
+        const int kyt = mma >> 1;
+        const int ky = kyt % p.kh, kt = kyt / p.kh;
+        const int px = 2 * (2 * q + j) + (e >> 2), ch = e & 3;
+        const int kx = px - p.shift;
+        if (kx >= 0 && kx < p.kw && ch < p.cin_pad)
+          src = (static_cast<long long>(kt * p.kh + ky) * p.kw + kx) * p.cin_pad + ch;
+      }
+    }
+    p.image[idx] = src >= 0 ? p.w_std[static_cast<long long>(n) * p.K_pad + src] : __float2bfloat16_rn(0.f);
+  }
+}
+
+static long long slab_image_bytes(int kind, int n_tile, int cin_pad, int kd, int kh, int kw) {
+  if (kind == TEDSPAD_SLAB_3X3) return 9LL * (cin_pad / 64) * n_tile * 128;
+  if (kind == TEDSPAD_SLAB_STEM2D) return 6LL * 2 * n_tile * 16;
+  return static_cast<long long>(kd) * kh * 2 * 2 * n_tile * 16;
+}
+
+// ------------------------------------------------------------------------------------------- plan
+static int make_plan(const tedspad_conv_slab& c, tedspad_slab_plan& P) {
+  memset(&P, 0, sizeof(P));
+  const tedspad_tensor& x = c.x;
+  const tedspad_tensor& y = c.y;
+  TSP_CHECK(c.Cout_pad % 16 == 0 && c.Cout_pad >= 16 && c.Cout_pad <= 256 && c.Cout <= c.Cout_pad && c.Cout >= 1,
+            "slab: Cout=%d Cout_pad=%d invalid (single N tile <= 256)", c.Cout, c.Cout_pad);
+  TSP_CHECK(c.Cout % 8 == 0, "slab: Cout=%d must be a multiple of 8", c.Cout);
+  TSP_CHECK(x.N == y.N && x.N >= 1, "slab: batch mismatch");
+  P.n_tile = c.Cout_pad;
+  const int Wp = x.W + 2 * x.pw, Hp = x.H + 2 * x.ph, Dp = x.D + 2 * x.pd;
+  int slab_w = 0, slab_h = 0, pad_bytes = 0;
+  if (c.kind == TEDSPAD_SLAB_3X3 || c.kind == TEDSPAD_SLAB_STEM2D) {
+    TSP_CHECK(c.kd == 1 && c.kh == 3 && c.kw == 3 && c.sd == 1 && c.sh == 1 && c.sw == 1 && c.pd == 0 && c.ph == 1 &&
+                  c.pw == 1,
+              "slab: kind %d needs a (1,3,3) stride-1 pad-1 convolution", c.kind);
+    TSP_CHECK(x.D == y.D && x.H == y.H && x.W == y.W, "slab: output extents must equal input extents");
+    const bool sw = c.kind == TEDSPAD_SLAB_3X3;
+    if (sw) {
+      TSP_CHECK(x.C % 64 == 0 && x.C >= 64, "slab 3x3: x.C=%d must be a multiple of 64", x.C);
+      TSP_CHECK(x.ph >= 1 && x.pw >= 1, "slab 3x3: input needs a zero halo >= 1 in H and W");
+    } else {
+      TSP_CHECK(x.C == 8, "slab stem2d: x.C=%d must be 8 (channels padded to one 16-byte pixel)", x.C);
+    }
+    P.w_bytes = static_cast<int>(slab_image_bytes(c.kind, P.n_tile, x.C, 1, 3, 3));
+    P.swizzle128 = sw ? 1 : 0;
+    P.k_stages = sw ? x.C / 64 : 1;
+    P.n_mma = sw ? 36 : 6;
+    const int px_bytes = sw ? 128 : 16;
+    // tile width: two 8-column halves when the image is wide enough and three slab stages still fit
+    int tm = c.tm;
+    if (tm == 0) {
+      tm = x.W > 8 ? 2 : 1;
+      if (tm == 2) {
+        const int stride2 = static_cast<int>(round_up(px_bytes * 18 * 18 + (sw ? 0 : 64), 1024));
+        if (P.w_bytes + 3 * stride2 + SLAB_TAIL_BYTES + 1024 > SLAB_SMEM_BUDGET) tm = 1;
+      }
+    }
+    TSP_CHECK(tm == 1 || tm == 2, "slab: tm=%d", tm);
+    P.tm = tm;
+    slab_w = 8 * tm + 2;
+    slab_h = 18;
+    pad_bytes = sw ? 0 : 64;  // stem: the zero-weight tap kx=3 of the last row reads past the box
+    P.box[0] = sw ? 64 : 8; P.box[1] = slab_w; P.box[2] = slab_h; P.box[3] = 1; P.box[4] = 1;
+    P.tdim[0] = x.C; P.tdim[1] = Wp; P.tdim[2] = Hp; P.tdim[3] = Dp; P.tdim[4] = x.N;
+    P.tstride[0] = static_cast<int64_t>(x.ld) * 2;
+    P.tstride[1] = P.tstride[0] * Wp;
+    P.tstride[2] = P.tstride[1] * Hp;
+    P.tstride[3] = P.tstride[2] * Dp;
+    P.tbase_off = static_cast<int64_t>(x.coff) * 2;
+    P.c_step = sw ? 64 : 0;
+    P.x_step = 8 * tm; P.x_off = x.pw - 1;
+    P.y_step = 16; P.y_off = x.ph - 1;
+    P.z_step = 1; P.z_off = x.pd; P.z_kstep = 0;
+    P.tiles_x = (x.W + 8 * tm - 1) / (8 * tm);
+    P.tiles_y = (x.H + 15) / 16;
+    P.tiles_z = x.D;
+    P.half_a_off = 8 * px_bytes;
+    if (sw) {
+      P.a_layout = 2; P.a_lbo = 16; P.a_sbo = slab_w * 128;
+      P.b_layout = 2; P.b_lbo = 16; P.b_sbo = 1024;
+      const int cb_n = x.C / 64;
+      for (int cb = 0; cb < cb_n; ++cb)
+        for (int tap = 0; tap < 9; ++tap)
+          for (int k = 0; k < 4; ++k) {
+            const int i = (cb * 9 + tap) * 4 + k;
+            TSP_CHECK(i < TEDSPAD_SLAB_MAX_MMA, "slab 3x3: %d MMAs exceed the table (Cin too large)", i + 1);
+            P.tab[2 * i] = static_cast<uint32_t>(((tap / 3) * slab_w + (tap % 3)) * 128 + k * 32);
+            P.tab[2 * i + 1] = static_cast<uint32_t>((tap * cb_n + cb) * P.n_tile * 128 + k * 32);
+          }
+    } else {
+      P.a_layout = 0; P.a_lbo = 16; P.a_sbo = slab_w * 16;
+      P.b_layout = 0; P.b_lbo = P.n_tile * 16; P.b_sbo = 128;
+      for (int i = 0; i < 6; ++i) {
+        P.tab[2 * i] = static_cast<uint32_t>(((i >> 1) * slab_w + 2 * (i & 1)) * 16);
+        P.tab[2 * i + 1] = static_cast<uint32_t>(i * 2 * P.n_tile * 16);
+      }
+    }
+  } else if (c.kind == TEDSPAD_SLAB_STEM3D) {
+    TSP_CHECK(c.kh == 7 && c.kw == 7 && c.sh == 2 && c.sw == 2 && c.kd >= 1 && c.kd <= 7 && c.sd >= 1,
+              "slab stem3d: needs a (kd,7,7) stride (sd,2,2) convolution");
+    TSP_CHECK(x.C == 4 && x.ld == 4 && x.coff == 0 && x.pd == 0 && x.ph == 0 && x.pw == 0 && x.W % 2 == 0,
+              "slab stem3d: input must be an un-haloed [N][D][H][W][4] clip with even W");
+    TSP_CHECK(c.pw >= 0 && c.pw <= 6 && c.ph >= 0 && c.ph <= 6 && c.pd >= 0 && c.pd < c.kd, "slab stem3d: bad front pads");
+    const int shift = c.pw & 1;          // odd front pad: one extra (zero-weight) leading tap
+    const int pwe = c.pw + shift;        // even front pad in pixels
+    TSP_CHECK(7 + shift <= 8, "slab stem3d: window exceeds 8 pixels");
+    P.w_bytes = static_cast<int>(slab_image_bytes(c.kind, P.n_tile, 4, c.kd, 7, 7));
+    int tm = c.tm;
+    if (tm == 0) tm = 1;
+    TSP_CHECK(tm == 1 || tm == 2, "slab: tm=%d", tm);
+    P.tm = tm;
+    const int pairs = 8 * tm + 3;        // 16*tm + 6 pixels
+    slab_w = pairs;
+    slab_h = 37;
+    pad_bytes = 64;
+    P.k_stages = c.kd;
+    P.n_mma = 14;
+    P.box[0] = 8; P.box[1] = pairs; P.box[2] = slab_h; P.box[3] = 1; P.box[4] = 1;
+    P.tdim[0] = 8; P.tdim[1] = x.W / 2; P.tdim[2] = x.H; P.tdim[3] = x.D; P.tdim[4] = x.N;
+    P.tstride[0] = 16;
+    P.tstride[1] = static_cast<int64_t>(x.W) * 8;
+    P.tstride[2] = P.tstride[1] * x.H;
+    P.tstride[3] = P.tstride[2] * x.D;
+    P.tbase_off = 0;
+    P.c_step = 0;
+    P.x_step = 8 * tm; P.x_off = -(pwe / 2);
+    P.y_step = 32; P.y_off = -c.ph;
+    P.z_step = c.sd; P.z_off = -c.pd; P.z_kstep = 1;
+    P.tiles_x = (y.W + 8 * tm - 1) / (8 * tm);
+    P.tiles_y = (y.H + 15) / 16;
+    P.tiles_z = y.D;
+    P.half_a_off = 8 * 16;
+    P.a_layout = 0; P.a_lbo = 16; P.a_sbo = 2 * pairs * 16;
+    P.b_layout = 0; P.b_lbo = P.n_tile * 16; P.b_sbo = 128;
+    for (int kt = 0; kt < c.kd; ++kt)
+      for (int i = 0; i < 14; ++i) {
+        const int e = kt * 14 + i;
+        TSP_CHECK(e < TEDSPAD_SLAB_MAX_MMA, "slab stem3d: table overflow");
+        P.tab[2 * e] = static_cast<uint32_t>((i >> 1) * pairs * 16 + (i & 1) * 32);
+        P.tab[2 * e + 1] = static_cast<uint32_t>(e * 2 * P.n_tile * 16);
+      }
+    // the last output row/column must read inside the zero-filled box: guaranteed by TMA OOB fill
+  } else {
+    TSP_CHECK(false, "slab: unknown kind %d", c.kind);
+  }
+  P.slab_bytes = P.box[0] * 2 * slab_w * slab_h;
+  P.slab_stride = static_cast<int>(round_up(P.slab_bytes + pad_bytes, 1024));
+  const int w_stride = static_cast<int>(round_up(P.w_bytes, 1024));
+  const int avail = SLAB_SMEM_BUDGET - 1024 - SLAB_TAIL_BYTES - w_stride;
+  P.stages = std::min(SLAB_MAX_STAGES, avail / P.slab_stride);
+  TSP_CHECK(P.stages >= 2, "slab: weights (%d B) + two slab stages (%d B each) do not fit in shared memory", P.w_bytes,
+            P.slab_stride);
+  P.smem_bytes = 1024 + w_stride + P.stages * P.slab_stride + SLAB_TAIL_BYTES;
+  int tc = 32;
+  while (tc < 2 * P.tm * P.n_tile) tc <<= 1;
+  TSP_CHECK(tc <= 512, "slab: %d TMEM columns needed", tc);
+  P.tmem_cols = tc;
+  const int64_t total = static_cast<int64_t>(x.N) * P.tiles_z * P.tiles_y * P.tiles_x;
+  TSP_CHECK(total > 0 && total < (int64_t(1) << 31), "slab: tile count out of range");
+  P.total_tiles = static_cast<int>(total);
+  return 0;
+}
+
+static std::once_flag g_slab_attr_once;
+
+}  // namespace tsp
+
+using namespace tsp;
+
+extern "C" int tedspad_conv_slab_plan(const tedspad_conv_slab* c, tedspad_slab_plan* out) {
+  TSP_CHECK(c != nullptr && out != nullptr, "slab plan: null argument");
+  return make_plan(*c, *out);
+}
+
+extern "C" int tedspad_conv_slab_pack(int32_t kind, const void* w_std, int32_t Cout_pad, int32_t K_pad, int32_t cin_pad,
+                                      int32_t kd, int32_t kh, int32_t kw, int32_t pw_front, void* image,
+                                      int64_t* image_bytes, void* stream) {
+  TSP_CHECK(kind >= TEDSPAD_SLAB_3X3 && kind <= TEDSPAD_SLAB_STEM3D, "slab pack: unknown kind %d", kind);
+  TSP_CHECK(Cout_pad % 16 == 0 && Cout_pad >= 16 && Cout_pad <= 256, "slab pack: Cout_pad=%d", Cout_pad);
+  if (kind == TEDSPAD_SLAB_3X3) TSP_CHECK(cin_pad % 64 == 0 && kd == 1 && kh == 3 && kw == 3, "slab pack 3x3: bad geometry");
+  if (kind == TEDSPAD_SLAB_STEM2D) TSP_CHECK(cin_pad <= 8 && kd == 1 && kh == 3 && kw == 3, "slab pack stem2d: bad geometry");
+  if (kind == TEDSPAD_SLAB_STEM3D) TSP_CHECK(cin_pad >= 1 && kh == 7 && kw == 7 && kd >= 1, "slab pack stem3d: bad geometry");
+  TSP_CHECK(K_pad >= kd * kh * kw * cin_pad, "slab pack: K_pad=%d too small", K_pad);
+  const long long bytes = slab_image_bytes(kind, Cout_pad, kind == TEDSPAD_SLAB_STEM3D ? 4 : cin_pad, kd, kh, kw);
+  if (image_bytes) *image_bytes = bytes;
+  if (image == nullptr) return 0;
+  TSP_CHECK(w_std != nullptr, "slab pack: null weights");
+  PackP p;
+  p.w_std = reinterpret_cast<const __nv_bfloat16*>(w_std);
+  p.image = reinterpret_cast<__nv_bfloat16*>(image);
+  p.kind = kind; p.n_tile = Cout_pad; p.K_pad = K_pad; p.cin_pad = cin_pad; p.kd = kd; p.kh = kh; p.kw = kw;
+  p.shift = pw_front & 1;
+  p.total = bytes / 2;
+  const int blocks = static_cast<int>(std::min<long long>((p.total + 255) / 256, 4096));
+  slab_pack_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  TSP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tedspad_conv_slab_forward(const tedspad_conv_slab* c, void* stream_v) {
+  TSP_CHECK(c != nullptr, "slab: null descriptor");
+  const tedspad_tensor& x = c->x;
+  const tedspad_tensor& y = c->y;
+  if (check_tensor(x, "slab.x", c->kind == TEDSPAD_SLAB_STEM3D ? 4 : 8)) return 1;
+  const bool fused_oc = c->oc_w != nullptr;
+  tedspad_tensor ychk = y;
+  if (y.ptr == nullptr) {
+    TSP_CHECK(fused_oc, "slab: y.ptr is NULL without a fused OutConv");
+    ychk.ptr = const_cast<void*>(c->w_image);  // extents are still validated
+  }
+  if (check_tensor(ychk, "slab.y", 8)) return 1;
+  TSP_CHECK(c->w_image && c->bias, "slab: null weights/bias");
+  TSP_CHECK(y.C == c->Cout, "slab: y.C %d != Cout %d", y.C, c->Cout);
+  TSP_CHECK(c->act == TEDSPAD_ACT_RELU || c->act == TEDSPAD_ACT_NONE, "slab: activation %d not supported", c->act);
+  tedspad_slab_plan P;
+  if (int rc = make_plan(*c, P)) return rc;
+
+  SlabKParams p;
+  memset(&p, 0, sizeof(p));
+  uint64_t dims[5], strides[4];
+  uint32_t box[5];
+  for (int i = 0; i < 5; ++i) { dims[i] = (uint64_t)P.tdim[i]; box[i] = (uint32_t)P.box[i]; }
+  for (int i = 0; i < 4; ++i) strides[i] = (uint64_t)P.tstride[i];
+  const uint8_t* base = reinterpret_cast<const uint8_t*>(x.ptr) + P.tbase_off;
+  if (encode_tmap_5d_bf16(&p.tmA, base, dims, strides, box, P.swizzle128 != 0)) return 3;
+  p.w_image = reinterpret_cast<const uint8_t*>(c->w_image);
+  p.bias = c->bias;
+  p.tm = P.tm; p.n_tile = P.n_tile; p.k_stages = P.k_stages; p.n_mma = P.n_mma; p.stages = P.stages;
+  p.tmem_cols = P.tmem_cols;
+  p.slab_bytes = P.slab_bytes; p.slab_stride = P.slab_stride; p.w_bytes = P.w_bytes;
+  p.w_stride = (int)round_up(P.w_bytes, 1024);
+  p.zero_slabs = P.swizzle128 ? 0 : 1;
+  p.half_a_off = P.half_a_off;
+  p.c_step = P.c_step; p.x_step = P.x_step; p.x_off = P.x_off; p.y_step = P.y_step; p.y_off = P.y_off;
+  p.z_step = P.z_step; p.z_off = P.z_off; p.z_kstep = P.z_kstep;
+  p.tiles_x = P.tiles_x; p.tiles_y = P.tiles_y; p.tiles_z = P.tiles_z; p.total_tiles = P.total_tiles;
+  p.a_desc = umma_desc_template(P.a_layout, P.a_lbo, P.a_sbo);
+  p.b_desc = umma_desc_template(P.b_layout, P.b_lbo, P.b_sbo);
+  for (int i = 0; i < P.k_stages * P.n_mma; ++i) p.tab[i] = make_uint2(P.tab[2 * i], P.tab[2 * i + 1]);
+
+  p.y = reinterpret_cast<__nv_bfloat16*>(y.ptr);
+  p.OH = y.H; p.OW = y.W;
+  p.yDp = y.D + 2 * y.pd; p.yHp = y.H + 2 * y.ph; p.yWp = y.W + 2 * y.pw;
+  p.ypd = y.pd; p.yph = y.ph; p.ypw = y.pw; p.y_ld = y.ld; p.y_coff = y.coff;
+  p.Cout = c->Cout; p.act = c->act;
+  if (c->pool.ptr != nullptr) {
+    const tedspad_tensor& q = c->pool;
+    if (check_tensor(q, "slab.pool", 8)) return 1;
+    TSP_CHECK(c->kind == TEDSPAD_SLAB_3X3 && y.D == 1 && q.D == 1 && q.pd == 0 && q.N == y.N && q.C == c->Cout &&
+                  q.H == y.H / 2 && q.W == y.W / 2,
+              "slab: fused MaxPool2d(2) output [%d,%d,%d,%d] does not match", q.N, q.H, q.W, q.C);
+    p.pool = reinterpret_cast<__nv_bfloat16*>(q.ptr);
+    p.PH = q.H; p.PW = q.W; p.pHp = q.H + 2 * q.ph; p.pWp = q.W + 2 * q.pw; p.pph = q.ph; p.ppw = q.pw;
+    p.p_ld = q.ld; p.p_coff = q.coff;
+  }
+  if (fused_oc) {
+    TSP_CHECK(c->oc_b && c->oc_planes, "slab: fused OutConv needs oc_b and oc_planes");
+    TSP_CHECK(c->Cout <= 64 && c->Cout % 4 == 0 && y.D == 1, "slab: fused OutConv needs a 2-D layer with Cout <= 64");
+    p.oc_w = c->oc_w; p.oc_b = c->oc_b;
+    p.oc_planes = reinterpret_cast<__nv_bfloat16*>(c->oc_planes);
+    p.oc_frames = c->oc_frames;
+  }
+
+  int rc = 0;
+  std::call_once(g_slab_attr_once, [&] {
+    cudaError_t e = cudaFuncSetAttribute(conv_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SLAB_SMEM_BUDGET);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(slab smem) failed: %s", cudaGetErrorString(e));
+      rc = 2;
+    }
+  });
+  if (rc) return rc;
+  int ctas = c->max_ctas > 0 ? c->max_ctas : num_sms();
+  ctas = std::max(1, std::min(ctas, p.total_tiles));
+  conv_slab_kernel<<<ctas, 256, P.smem_bytes, reinterpret_cast<cudaStream_t>(stream_v)>>>(p);
+  TSP_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -391,13 +391,13 @@ struct CvtP {
 };
 
 __global__ void __launch_bounds__(256) nchw_to_cl_kernel(const CvtP p) {
-  const int c8n = p.y.C >> 3;
   const long long plane = static_cast<long long>(p.y.D) * p.y.H * p.y.W;
+  const int cw = p.y.C == 4 ? 4 : 8;  // channels per thread: one 8- or 16-byte store
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < p.total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
     // pixel fastest so that the fp32 plane reads are coalesced
     const long long pixl = idx % (plane * p.y.N);
-    const int c8 = static_cast<int>(idx / (plane * p.y.N));
+    const int cg = static_cast<int>(idx / (plane * p.y.N));
     const int n = static_cast<int>(pixl / plane);
     long long r = pixl - n * plane;
     const int w = static_cast<int>(r % p.y.W); r /= p.y.W;
@@ -406,12 +406,65 @@ __global__ void __launch_bounds__(256) nchw_to_cl_kernel(const CvtP p) {
     float f[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int c = c8 * 8 + i;
-      f[i] = c < p.Cx ? __ldg(p.x + (static_cast<long long>(n) * p.Cx + c) * plane + (pixl - n * plane)) : 0.f;
+      const int c = cg * cw + i;
+      f[i] = (i < cw && c < p.Cx) ? __ldg(p.x + (static_cast<long long>(n) * p.Cx + c) * plane + (pixl - n * plane)) : 0.f;
     }
-    *reinterpret_cast<uint4*>(elem_ptr_w(p.y, pix_index(p.y, n, d, h, w), c8 * 8)) = pack8(f);
+    __nv_bfloat16* yp = elem_ptr_w(p.y, pix_index(p.y, n, d, h, w), cg * cw);
+    const uint4 q = pack8(f);
+    if (cw == 4) *reinterpret_cast<uint2*>(yp) = make_uint2(q.x, q.y);
+    else *reinterpret_cast<uint4*>(yp) = q;
   }
-  (void)c8n;
+}
+
+// ------------------------------------- planar anonymizer output -> encoder clip (raw-reshape glue)
+struct P2CP {
+  const __nv_bfloat16* planes;  // [B*T][3][H][W]
+  TView y;                      // [B][T][H][W][C>=3], C in {4, 8}
+  int T;
+  long long total;              // B*T*H*(W/8)
+};
+
+// thread -> 8 consecutive pixels of one encoder row: three 16-byte plane reads, 8 pixel stores
+__global__ void __launch_bounds__(256) planes_to_clip_kernel(const P2CP p) {
+  const int w8n = p.y.W >> 3;
+  const long long plane = static_cast<long long>(p.y.H) * p.y.W;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < p.total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    long long t = idx;
+    const int w8 = static_cast<int>(t % w8n); t /= w8n;
+    const int h = static_cast<int>(t % p.y.H); t /= p.y.H;
+    const int te = static_cast<int>(t % p.T);
+    const int b = static_cast<int>(t / p.T);
+    uint4 src[3];
+#pragma unroll
+    for (int ce = 0; ce < 3; ++ce) {
+      // encoder channel ce, time te  <-  plane ce*T + te of the clip's 3T planes (dali_extraction.py:173)
+      const long long pl = static_cast<long long>(b) * 3 * p.T + ce * p.T + te;
+      src[ce] = __ldg(reinterpret_cast<const uint4*>(p.planes + pl * plane + static_cast<long long>(h) * p.y.W + w8 * 8));
+    }
+    const uint16_t* s0 = reinterpret_cast<const uint16_t*>(&src[0]);
+    const uint16_t* s1 = reinterpret_cast<const uint16_t*>(&src[1]);
+    const uint16_t* s2 = reinterpret_cast<const uint16_t*>(&src[2]);
+    __nv_bfloat16* yp = elem_ptr_w(p.y, pix_index(p.y, b, te, h, w8 * 8), 0);
+    if (p.y.C == 4) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        uint2 o;
+        o.x = static_cast<uint32_t>(s0[i]) | (static_cast<uint32_t>(s1[i]) << 16);
+        o.y = static_cast<uint32_t>(s2[i]);
+        *reinterpret_cast<uint2*>(yp + static_cast<long long>(i) * p.y.ld) = o;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        uint4 o;
+        o.x = static_cast<uint32_t>(s0[i]) | (static_cast<uint32_t>(s1[i]) << 16);
+        o.y = static_cast<uint32_t>(s2[i]);
+        o.z = 0u; o.w = 0u;
+        *reinterpret_cast<uint4*>(yp + static_cast<long long>(i) * p.y.ld) = o;
+      }
+    }
+  }
 }
 
 static int grid_for(long long total, int threads) {
@@ -522,12 +575,29 @@ extern "C" int tedspad_preprocess(const uint8_t* frames, int32_t F, int32_t Hs, 
 
 extern "C" int tedspad_nchw_to_cl(const float* x, int32_t Cx, const tedspad_tensor* y, void* stream) {
   TSP_CHECK(x && y, "nchw_to_cl: null argument");
-  if (check_tensor(*y, "nchw_to_cl.y", 8)) return 1;
-  TSP_CHECK(y->C % 8 == 0 && Cx >= 1 && Cx <= y->C, "nchw_to_cl: Cx=%d vs y.C=%d", Cx, y->C);
+  if (check_tensor(*y, "nchw_to_cl.y", y->C == 4 ? 4 : 8)) return 1;
+  TSP_CHECK((y->C % 8 == 0 || y->C == 4) && Cx >= 1 && Cx <= y->C, "nchw_to_cl: Cx=%d vs y.C=%d", Cx, y->C);
   CvtP p;
   p.x = x; p.Cx = Cx; p.y = make_view(*y);
-  p.total = static_cast<long long>(y->N) * y->D * y->H * y->W * (y->C / 8);
+  p.total = static_cast<long long>(y->N) * y->D * y->H * y->W * (y->C == 4 ? 1 : y->C / 8);
   nchw_to_cl_kernel<<<grid_for(p.total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  TSP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tedspad_planes_to_clip(const void* planes, const tedspad_tensor* y, int32_t T, void* stream) {
+  TSP_CHECK(planes && y, "planes_to_clip: null argument");
+  if (check_tensor(*y, "planes_to_clip.y", 4)) return 1;
+  TSP_CHECK((y->C == 4 || y->C == 8) && y->ld % y->C == 0 && y->coff % y->C == 0 && y->W % 8 == 0 && y->D == T && T >= 1,
+            "planes_to_clip: y must be [B,T,H,W,4|8] with W %% 8 == 0 (got [%d,%d,%d,%d,%d], T=%d)", y->N, y->D, y->H,
+            y->W, y->C, T);
+  TSP_CHECK((reinterpret_cast<uintptr_t>(planes) & 15) == 0, "planes_to_clip: planes must be 16-byte aligned");
+  P2CP p;
+  p.planes = reinterpret_cast<const __nv_bfloat16*>(planes);
+  p.y = make_view(*y);
+  p.T = T;
+  p.total = static_cast<long long>(y->N) * T * y->H * (y->W / 8);
+  planes_to_clip_kernel<<<grid_for(p.total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   TSP_CUDA(cudaGetLastError());
   return 0;
 }

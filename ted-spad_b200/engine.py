@@ -6,11 +6,46 @@ aux_code/ own the parameters and hand them over), folds BatchNorm into the packe
 and caches its activation buffers per input shape.  Concatenations (unet_parts.py:67, i3d.py:149)
 are never materialised: producers write straight into channel slices of the consumer's input.
 """
+import os
+
 import torch
 
 from . import _lib as L
 from . import ops
 from .ops import CLTensor, PackedConv
+
+# SLAB feed switches (csrc/conv_slab.cu): on by default; "0" routes the layer classes back through the FLAT /
+# GATHER feeds of csrc/conv_igemm.cu (kept for A/B measurements and as the general-shape path).
+USE_SLAB = os.environ.get("TEDSPAD_SLAB", "1") != "0"
+USE_SLAB_STEM3D = USE_SLAB and os.environ.get("TEDSPAD_SLAB_STEM3D", "1") != "0"
+SLAB_WEIGHT_LIMIT = 150 * 1024   # bytes of resident weights that still leave room for three slab stages
+ENC_IN_CHANNELS = 4 if USE_SLAB_STEM3D else 8   # channel padding of the encoder input clip
+
+
+def slab3x3(pc):
+    """PackedSlabConv for a (1,3,3) stride-1 pad-1 convolution whose weights can stay resident in shared
+    memory (the 64/128-channel DoubleConv layers), else None."""
+    if not USE_SLAB or pc.k != (1, 3, 3) or pc.stride != (1, 1, 1) or pc.pad_front != (0, 1, 1):
+        return None
+    if pc.cin_pad % 64 or pc.cout_pad > 256 or pc.cout % 8 or 9 * pc.cin_pad * pc.cout_pad * 2 > SLAB_WEIGHT_LIMIT:
+        return None
+    return ops.PackedSlabConv(pc, L.SLAB_3X3)
+
+
+def stem3d(pc):
+    """PackedSlabConv for a (kd,7,7) stride-(sd,2,2) Cin=3 stem fed from a 4-channel clip, else None."""
+    if not USE_SLAB_STEM3D or pc.k[1:] != (7, 7) or pc.stride[1:] != (2, 2) or pc.cin > 4 or pc.cout_pad > 256:
+        return None
+    return ops.PackedSlabConv(pc, L.SLAB_STEM3D)
+
+
+def stem_conv(x, pc, ps, y, act=L.ACT_RELU):
+    """First convolution of an encoder: SLAB stem when the clip is stored with 4 channels, GATHER feed for 8."""
+    if x.C == 4:
+        if ps is None:
+            raise RuntimeError("a 4-channel encoder clip needs the SLAB stem (TEDSPAD_SLAB_STEM3D=1)")
+        return ops.conv_slab_forward(x, ps, y, act=act)
+    return ops.conv_forward(x, pc, y, act=act)
 
 
 def _bn(sd, prefix, eps):
@@ -40,6 +75,15 @@ class _Buffers:
             self.pool[key] = t
         return t
 
+    def raw(self, name, shape, dtype):
+        """Plain (non channels-last) scratch tensor, e.g. the planar anonymizer output."""
+        key = ("raw", name, tuple(shape), dtype)
+        t = self.pool.get(key)
+        if t is None:
+            t = torch.empty(tuple(shape), device=self.device, dtype=dtype)
+            self.pool[key] = t
+        return t
+
     def drop_other_shapes(self, keep_n):
         for k in [k for k in self.pool if k[1] != keep_n]:
             del self.pool[k]
@@ -47,15 +91,19 @@ class _Buffers:
 
 # ======================================================================================== UNet
 class UNetExecutor:
-    """aux_code/models/unet_model.py:26-37 as 18 tcgen05 convolutions + 4 pools + 4 up-samples + OutConv.
-    All 3x3 convolutions except the first (Cin=3) use the FLAT TMA feed over zero-haloed buffers."""
+    """aux_code/models/unet_model.py:26-37 as 18 tcgen05 convolutions + up-samples (+ pools / OutConv when they
+    are not fused).  Feeds: the first convolution (Cin=3) and the 64/128-channel layers whose weights fit in
+    shared memory use the SLAB feed (MaxPool2d and OutConv+sigmoid fused into their epilogues); the wider layers
+    use the FLAT TMA feed over zero-haloed buffers."""
 
     HALO = (0, 1, 1)
+    LEVELS = ["inc.double_conv"] + [f"down{i}.maxpool_conv.1.double_conv" for i in range(1, 5)]
 
     def __init__(self, sd, device):
         self.device = device
         self.bufs = _Buffers(device)
         self.convs = {}
+        self.slabs = {}
 
         def dc(prefix, cin_pad0):
             a = PackedConv(sd[f"{prefix}.0.weight"], sd[f"{prefix}.0.bias"], _bn(sd, f"{prefix}.1", 1e-5),
@@ -63,6 +111,8 @@ class UNetExecutor:
             b = PackedConv(sd[f"{prefix}.3.weight"], sd[f"{prefix}.3.bias"], _bn(sd, f"{prefix}.4", 1e-5),
                            pad_front=(0, 1, 1), device=device)
             self.convs[prefix] = (a, b)
+            sa = ops.PackedSlabConv(a, L.SLAB_STEM2D) if (USE_SLAB and cin_pad0 == 8) else slab3x3(a)
+            self.slabs[prefix] = (sa, slab3x3(b))
 
         dc("inc.double_conv", 8)
         for i in range(1, 5):
@@ -76,8 +126,19 @@ class UNetExecutor:
         """The [n_frames,1,H,W,8] bf16 buffer preprocessing / nchw_to_cl writes the frames into."""
         return self.bufs.get("x0", n_frames, 1, H, W, 8)
 
+    @staticmethod
+    def _conv(x, pc, ps, y, pool=None):
+        """DoubleConv half: conv+BN+ReLU (unet_parts.py:15-22) and, when `pool` is given, the MaxPool2d(2) of the
+        next Down block (unet_parts.py:33) - fused into the SLAB epilogue, a separate kernel otherwise."""
+        if ps is not None:
+            return ops.conv_slab_forward(x, ps, y, pool=pool)
+        ops.conv_forward(x, pc, y, feed=L.FEED_GATHER if pc.cin_pad == 8 else L.FEED_AUTO)
+        if pool is not None:
+            ops.maxpool(y, pool, (1, 2, 2), (1, 2, 2))
+        return y
+
     def run(self, x0, enc_in, T=16, frames_out=None):
-        """x0: input_buffer() filled with frames; enc_in: encoder input [B,T,H,W,>=3] (scatter target)."""
+        """x0: input_buffer() filled with frames; enc_in: encoder input [B,T,H,W,4|8] (glue target)."""
         N, H, W = x0.N, x0.H, x0.W
         g, hl = self.bufs.get, self.HALO
         sizes = [(H, W)]
@@ -86,33 +147,35 @@ class UNetExecutor:
         ch = [64, 128, 256, 512, 512]
         # encoder path; skip tensors x1..x4 live in the first half of the concat buffers
         cats = [g(f"cat{i}", N, 1, sizes[i][0], sizes[i][1], 2 * ch[i], hl) for i in range(4)]
-        a, b = self.convs["inc.double_conv"]
-        t = g("t0", N, 1, H, W, 64, hl)
-        ops.conv_forward(x0, a, t, feed=L.FEED_GATHER)
-        skip = cats[0].slice(0, 64)
-        ops.conv_forward(t, b, skip)
-        cur = skip
-        for i in range(1, 5):
+        cur_in = x0
+        for i, prefix in enumerate(self.LEVELS):
+            (a, b), (sa, sb) = self.convs[prefix], self.slabs[prefix]
             h, w = sizes[i]
-            p = g(f"p{i}", N, 1, h, w, ch[i - 1], hl)
-            ops.maxpool(cur, p, (1, 2, 2), (1, 2, 2))
-            a, b = self.convs[f"down{i}.maxpool_conv.1.double_conv"]
             t = g(f"t{i}", N, 1, h, w, ch[i], hl)
-            ops.conv_forward(p, a, t)
+            self._conv(cur_in, a, sa, t)
             cur = cats[i].slice(0, ch[i]) if i < 4 else g("x5", N, 1, h, w, ch[4], hl)
-            ops.conv_forward(t, b, cur)
+            nxt = g(f"p{i + 1}", N, 1, sizes[i + 1][0], sizes[i + 1][1], ch[i], hl) if i < 4 else None
+            self._conv(t, b, sb, cur, pool=nxt)
+            cur_in = nxt
         # decoder path
         out_ch = [256, 128, 64, 64]
         for j in range(4):
             lvl = 3 - j
             cat = cats[lvl]
             ops.upsample2x(cur, cat.slice(ch[lvl], cur.C))
-            a, b = self.convs[f"up{j + 1}.conv.double_conv"]
+            prefix = f"up{j + 1}.conv.double_conv"
+            (a, b), (sa, sb) = self.convs[prefix], self.slabs[prefix]
             h, w = sizes[lvl]
             t = g(f"u{j}a", N, 1, h, w, a.cout, hl)
-            ops.conv_forward(cat, a, t)
+            self._conv(cat, a, sa, t)
+            if j == 3 and sb is not None and enc_in.W % 8 == 0 and enc_in.C in (4, 8):
+                # OutConv 1x1 + sigmoid (unet_parts.py:71-77, unet_model.py:36-37) in the last epilogue: the 64-channel
+                # tensor is never written; planar images then go through the raw-reshape glue (dali_extraction.py:173)
+                planes = self.bufs.raw("planes", (N, 3, H, W), ops.BF16)
+                ops.conv_slab_forward(t, sb, None, outconv=(self.out_w, self.out_b, planes, frames_out))
+                return ops.planes_to_clip(planes, enc_in, T)
             cur = g(f"u{j}", N, 1, h, w, out_ch[j], hl)
-            ops.conv_forward(t, b, cur)
+            self._conv(t, b, sb, cur)
         ops.outconv_sigmoid(cur, self.out_w, self.out_b, enc_in, T, frames_out)
         return enc_in
 
@@ -162,6 +225,10 @@ class I3DExecutor:
         if pc is None:
             pc = PackedConv(w, None, bn, stride=s, pad_front=pf, cin_pad=cin_pad, device=self.device)
             self.packed[key] = pc
+            if cin_pad == 8:
+                self.packed[key + ("slab",)] = stem3d(pc)
+        if cin_pad == 8:
+            return stem_conv(x, pc, self.packed[key + ("slab",)], y)
         return ops.conv_forward(x, pc, y)
 
     @staticmethod
@@ -195,7 +262,7 @@ class I3DExecutor:
         return y
 
     def run_trunk(self, enc_in):
-        """enc_in: [B,T,H,W,8] (3 real channels) -> Mixed_5c feature map [B,T/8,H/32,W/32,1024]."""
+        """enc_in: [B,T,H,W,4|8] (3 real channels) -> Mixed_5c feature map [B,T/8,H/32,W/32,1024]."""
         x = self._unit("Conv3d_1a_7x7", enc_in, 64)
         x = self._pool("MaxPool3d_2a_3x3", x, (1, 3, 3), (1, 2, 2))
         x = self._unit("Conv3d_2b_1x1", x, 64)
@@ -236,6 +303,7 @@ class I3Res50Executor:
         mk = lambda wk, bnk, stride, pad, cin_pad=None: PackedConv(  # noqa: E731
             sd[P + wk], None, _bn(sd, P + bnk, 1e-5), stride=stride, pad_front=pad, cin_pad=cin_pad, device=device)
         self.conv1 = mk("conv1.weight", "bn1", (2, 2, 2), (2, 3, 3), 8)
+        self.conv1_slab = stem3d(self.conv1)
         self.blocks = []
         for li, (planes, nblocks, stride, tcs) in enumerate(I3RES50_LAYERS, 1):
             for b in range(nblocks):
@@ -258,7 +326,8 @@ class I3Res50Executor:
     def run(self, enc_in):
         """enc_in: [B,T,H,W,8] -> fp32 features [B, 1, 2048]."""
         g = self.bufs.get
-        x = self._apply("conv1", self.conv1, enc_in)
+        od, oh, ow = self.conv1.out_extent((enc_in.D, enc_in.H, enc_in.W))
+        x = stem_conv(enc_in, self.conv1, self.conv1_slab, g("conv1", enc_in.N, od, oh, ow, self.conv1.cout))
         y = g("maxpool1", x.N, (x.D - 2) // 2 + 1, (x.H - 3) // 2 + 1, (x.W - 3) // 2 + 1, x.C)
         x = ops.maxpool(x, y, (2, 3, 3), (2, 2, 2))
         for blk in self.blocks:
@@ -284,6 +353,7 @@ class R3D18Executor:
         mk = lambda wk, bnk, stride, pad, cin_pad=None: PackedConv(  # noqa: E731
             sd[wk], None, _bn(sd, bnk, 1e-5), stride=stride, pad_front=pad, cin_pad=cin_pad, device=device)
         self.stem = mk("backbone.stem.0.weight", "backbone.stem.1", (1, 2, 2), (1, 3, 3), 8)
+        self.stem_slab = stem3d(self.stem)
         self.blocks = []
         for li in range(1, 5):
             for b in range(2):
@@ -303,7 +373,8 @@ class R3D18Executor:
         return ops.conv_forward(x, pc, y, res=res, act=act)
 
     def run(self, enc_in):
-        x = self._apply("stem", self.stem, enc_in)
+        od, oh, ow = self.stem.out_extent((enc_in.D, enc_in.H, enc_in.W))
+        x = stem_conv(enc_in, self.stem, self.stem_slab, self.bufs.get("stem", enc_in.N, od, oh, ow, self.stem.cout))
         for blk in self.blocks:
             n = blk["name"]
             o = self._apply(n + ".c1", blk["c1"], x)

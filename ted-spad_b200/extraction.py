@@ -98,8 +98,9 @@ class SnippetExtractor:
     def _enc_in(self, B):
         t = self._enc.get(B)
         if t is None:
-            t = ops.CLTensor(B, self.T, self.reso[0], self.reso[1], 8, device=self.device)
-            t.buf.zero_()  # channels 3..7 stay zero forever (the scatter only writes 0..2)
+            from . import engine
+            t = ops.CLTensor(B, self.T, self.reso[0], self.reso[1], engine.ENC_IN_CHANNELS, device=self.device)
+            t.buf.zero_()  # pad channels stay zero (the glue writes zeros there, the old scatter only 0..2)
             self._enc[B] = t
         return t
 

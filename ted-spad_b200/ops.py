@@ -157,6 +157,89 @@ def conv_forward(x, pc, y, res=None, act=L.ACT_RELU, feed=L.FEED_AUTO, y_fp32=Fa
     return y
 
 
+class PackedSlabConv:
+    """Weights of a SLAB-feed convolution (include/tedspad.h: tedspad_conv_slab): the standard PackedConv
+    layout re-packed on the device into the shared-memory image the kernel keeps resident."""
+
+    def __init__(self, pc, kind):
+        self.pc, self.kind = pc, int(kind)
+        self.cout, self.cout_pad = pc.cout, pc.cout_pad
+        if pc.cout_pad > 256 or pc.cout % 8:
+            raise ValueError(f"slab feed needs a single N tile (Cout_pad={pc.cout_pad}) with Cout % 8 == 0")
+        self.cin_pad = 4 if kind == L.SLAB_STEM3D else pc.cin_pad
+        nbytes = C.c_int64(0)
+        args = (self.kind, None, pc.cout_pad, pc.k_pad, pc.cin_pad, *pc.k, pc.pad_front[2])
+        L.check(L.lib().tedspad_conv_slab_pack(*args, None, C.byref(nbytes), None), "tedspad_conv_slab_pack(size)")
+        self.image_bytes = int(nbytes.value)
+        self.image = None
+        if pc.w.is_cuda:
+            self.image = torch.empty(self.image_bytes // 2, dtype=BF16, device=pc.w.device)
+            args = (self.kind, pc.w.data_ptr(), pc.cout_pad, pc.k_pad, pc.cin_pad, *pc.k, pc.pad_front[2])
+            _count()
+            L.check(L.lib().tedspad_conv_slab_pack(*args, self.image.data_ptr(), C.byref(nbytes), _stream()),
+                    "tedspad_conv_slab_pack")
+        self.bias = pc.bias
+
+    def desc(self, x, y, act=L.ACT_RELU, pool=None, outconv=None, tm=0, max_ctas=0):
+        """outconv = (w fp32 [3,Cout], b fp32 [3], planes bf16 [N,3,H,W], frames fp32 [N,3,H,W] | None)"""
+        pc = self.pc
+        d = L.ConvSlabDesc()
+        d.x = x.desc()
+        if y is not None:
+            d.y = y.desc()
+        else:  # fused OutConv only: extents of the (never written) convolution output
+            d.y = L.TensorDesc(None, x.N, x.D, x.H, x.W, pc.cout, 0, 0, 0, pc.cout, 0)
+        d.w_image = self.image.data_ptr() if self.image is not None else None
+        d.bias = self.bias.data_ptr()
+        if pool is not None:
+            d.pool = pool.desc()
+        if outconv is not None:
+            w, b, planes, frames = outconv
+            d.oc_w, d.oc_b, d.oc_planes = w.data_ptr(), b.data_ptr(), planes.data_ptr()
+            d.oc_frames = frames.data_ptr() if frames is not None else None
+        d.kind, d.Cout, d.Cout_pad = self.kind, pc.cout, pc.cout_pad
+        d.kd, d.kh, d.kw = pc.k
+        d.sd, d.sh, d.sw = pc.stride
+        d.pd, d.ph, d.pw = pc.pad_front
+        d.act, d.tm, d.max_ctas = act, tm, max_ctas
+        return d
+
+    def plan(self, x, y, **kw):
+        """The kernel's tiling / descriptor plan (host-only call; used by the CPU simulator tests)."""
+        plan = L.SlabPlan()
+        d = self.desc(x, y, **kw)
+        L.check(L.lib().tedspad_conv_slab_plan(C.byref(d), C.byref(plan)), "tedspad_conv_slab_plan")
+        return plan
+
+
+def conv_slab_forward(x, psc, y, act=L.ACT_RELU, pool=None, outconv=None, tm=0, max_ctas=0):
+    """y = act(conv(x) + bias) through the SLAB feed; optional fused MaxPool2d(2) -> pool and
+    OutConv 1x1 + sigmoid -> planar images (y may then be None)."""
+    d = psc.desc(x, y, act=act, pool=pool, outconv=outconv, tm=tm, max_ctas=max_ctas)
+    _count()
+    if CONV_EVENTS is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        L.check(L.lib().tedspad_conv_slab_forward(C.byref(d), _stream()), "tedspad_conv_slab_forward")
+        e1.record()
+        pc = psc.pc
+        od, oh, ow = (y.D, y.H, y.W) if y is not None else (x.D, x.H, x.W)
+        CONV_EVENTS.append((e0, e1, (x.N, x.D, x.H, x.W, x.C, pc.cout, pc.k, pc.stride, od, oh, ow, pc.cin)))
+        return y
+    L.check(L.lib().tedspad_conv_slab_forward(C.byref(d), _stream()), "tedspad_conv_slab_forward")
+    return y
+
+
+def planes_to_clip(planes, y, T):
+    """planar bf16 [B*T,3,H,W] anonymizer output -> encoder input view [B,T,H,W,4|8] (raw-reshape glue)."""
+    _require_cuda(planes, "planes_to_clip")
+    assert planes.dtype == BF16 and planes.is_contiguous()
+    yd = y.desc()
+    _count()
+    L.check(L.lib().tedspad_planes_to_clip(planes.data_ptr(), C.byref(yd), int(T), _stream()), "tedspad_planes_to_clip")
+    return y
+
+
 def maxpool(x, y, k, s, pad_front=(0, 0, 0), zero_pad=False):
     xd, yd = x.desc(), y.desc()
     _count()

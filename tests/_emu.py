@@ -56,8 +56,25 @@ def conv_forward(x, pc, y, res=None, act=L.ACT_RELU, feed=L.FEED_AUTO, y_fp32=Fa
         y.buf.reshape(M, y.ld)[:, y.coff:y.coff + y.C] = acc.to(y.buf.dtype)
         return y
     # gather
-    N, OD, OH, OW = y.N, y.D, y.H, y.W
+    acc = _gather_acc(x, pc, (y.N, y.D, y.H, y.W))
+    if res is not None:
+        acc = acc + res.interior().float()
+    acc = _act(acc, act)
+    y.interior()[...] = acc.to(y.buf.dtype)
+    return y
+
+
+def _gather_acc(x, pc, out_shape):
+    """fp32 conv + bias by explicit im2col with front pads: [N,OD,OH,OW,Cout] (x may carry fewer channels than
+    the weights were packed for, e.g. the 4-channel clip of the SLAB stem: missing channels are zero)."""
+    kd, kh, kw = pc.k
+    W2 = pc.w.float()[:pc.cout]
+    bias = pc.bias[:pc.cout]
+    N, OD, OH, OW = out_shape
     xi = x.interior().float()  # [N,D,H,W,C]
+    Cw = pc.cin_pad
+    if x.C < Cw:
+        xi = torch.cat([xi, torch.zeros(*xi.shape[:-1], Cw - x.C)], -1)
     cols = torch.zeros(N, OD, OH, OW, pc.k_pad)
     t = 0
     od = torch.arange(OD) * pc.stride[0] - pc.pad_front[0]
@@ -68,21 +85,47 @@ def conv_forward(x, pc, y, res=None, act=L.ACT_RELU, feed=L.FEED_AUTO, y_fp32=Fa
             for c in range(kw):
                 idd, ihh, iww = od + a, oh + b, ow + c
                 vd, vh, vw = (idd >= 0) & (idd < x.D), (ihh >= 0) & (ihh < x.H), (iww >= 0) & (iww < x.W)
-                patch = torch.zeros(N, OD, OH, OW, x.C)
+                patch = torch.zeros(N, OD, OH, OW, Cw)
                 sub = xi[:, idd[vd]][:, :, ihh[vh]][:, :, :, iww[vw]]
-                tmp = torch.zeros(N, int(vd.sum()), int(vh.sum()), OW, x.C)
+                tmp = torch.zeros(N, int(vd.sum()), int(vh.sum()), OW, Cw)
                 tmp[:, :, :, vw] = sub
-                tmp2 = torch.zeros(N, int(vd.sum()), OH, OW, x.C)
+                tmp2 = torch.zeros(N, int(vd.sum()), OH, OW, Cw)
                 tmp2[:, :, vh] = tmp
                 patch[:, vd] = tmp2
-                cols[..., t * x.C:(t + 1) * x.C] = patch
+                cols[..., t * Cw:(t + 1) * Cw] = patch
                 t += 1
     acc = cols.reshape(-1, pc.k_pad) @ W2.T + bias
-    acc = acc.reshape(N, OD, OH, OW, pc.cout)
-    if res is not None:
-        acc = acc + res.interior().float()
-    acc = _act(acc, act)
-    y.interior()[...] = acc.to(y.buf.dtype)
+    return acc.reshape(N, OD, OH, OW, pc.cout)
+
+
+def conv_slab_forward(x, psc, y, act=L.ACT_RELU, pool=None, outconv=None, tm=0, max_ctas=0):
+    """SLAB feed (csrc/conv_slab.cu): same arithmetic as the gather restatement; the fused MaxPool2d(2) pools the
+    ROUNDED output (as the kernel does), the fused OutConv consumes the un-rounded fp32 activations."""
+    pc = psc.pc
+    shape = (y.N, y.D, y.H, y.W) if y is not None else (x.N, x.D, x.H, x.W)
+    acc = _act(_gather_acc(x, pc, shape), act)
+    store_dtype = y.buf.dtype if y is not None else (pool.buf.dtype if pool is not None else torch.float32)
+    if y is not None:
+        y.interior()[...] = acc.to(y.buf.dtype)
+    if pool is not None:
+        import torch.nn.functional as F
+        r = acc.to(store_dtype).float()[:, 0].permute(0, 3, 1, 2)
+        pool.interior()[:, 0] = F.max_pool2d(r, 2).permute(0, 2, 3, 1).to(pool.buf.dtype)
+    if outconv is not None:
+        w, b, planes, frames = outconv
+        v = torch.sigmoid(acc[:, 0] @ w.T + b).permute(0, 3, 1, 2).contiguous()  # [N,3,H,W]
+        planes.copy_(v.to(planes.dtype))
+        if frames is not None:
+            frames.copy_(v)
+    return y
+
+
+def planes_to_clip(planes, y, T):
+    Fr, _, H, W = planes.shape
+    B = Fr // T
+    enc = planes.float().reshape(B, T, 3, H, W).reshape(B, 3, T, H, W)  # dali_extraction.py:171-173
+    y.interior()[...] = 0
+    y.interior()[..., :3] = enc.permute(0, 2, 3, 4, 1).to(y.buf.dtype)
     return y
 
 
@@ -131,6 +174,7 @@ def avgpool_features(x, kd=0):
 def nchw_to_cl(x_f32, y):
     if x_f32.dim() == 4:
         x_f32 = x_f32.unsqueeze(2)
+    assert y.C % 8 == 0 or y.C == 4
     y.interior()[...] = 0
     y.interior()[..., :x_f32.shape[1]] = x_f32.permute(0, 2, 3, 4, 1).to(y.buf.dtype)
     return y

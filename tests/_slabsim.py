@@ -1,0 +1,142 @@
+"""CPU replay of the SLAB feed's address arithmetic (test infrastructure only; never imported by the product).
+
+The slab kernel (ted-spad_b200/csrc/conv_slab.cu) is driven entirely by a host-built plan: a 5-D TMA box per
+(tile, K stage), UMMA shared-memory descriptor fields, and a table of (A offset, B offset) pairs.  This module
+replays exactly that plan on the CPU with the hardware semantics pinned on the B200 by tests/probes/umma_probe.cu
+(profiles/r1_umma_probe.txt):
+
+  * TMA tiled load: box elements land row-major (innermost first) in shared memory, out-of-bounds elements are
+    zero, and with SWIZZLE_128B the 16-byte chunk index (byte bits 4-6) is XORed with byte bits 7-9;
+  * UMMA K-major operand, SWIZZLE_128B: element (row, k) at start + (row>>3)*SBO + (row&7)*128 + 2k, the same
+    XOR applied to the final address (descriptor base_offset = 0);
+  * UMMA K-major operand, no swizzle: element (row, k) at start + (row>>3)*SBO + (k>>3)*LBO + (row&7)*16 + 2(k&7),
+    where LBO may be 16 bytes (overlapping K-adjacent core matrices).
+
+so that tiling, descriptor tables and the weight image are verified against F.conv3d without a GPU.  It also holds
+the reference (numpy) packer of the weight image, against which the CUDA pack kernel is compared bit for bit.
+"""
+import numpy as np
+import torch
+
+from tedspad_b200 import _lib as L
+
+
+def bf16_bits(t):
+    """torch bf16 tensor -> numpy uint16 bit patterns (flat)."""
+    return t.contiguous().view(torch.int16).cpu().numpy().view(np.uint16).reshape(-1)
+
+
+def bits_to_f32(u16):
+    return (u16.astype(np.uint32) << 16).view(np.float32)
+
+
+# ---------------------------------------------------------------------------------- weight image
+def pack_image(kind, w_std, n_tile, k_pad, cin_pad, k, pw_front):
+    """numpy restatement of slab_pack_kernel: w_std uint16 [Cout_pad*K_pad] -> image uint16."""
+    kd, kh, kw = k
+    w = w_std.reshape(n_tile, k_pad)
+    if kind == L.SLAB_3X3:
+        total = 9 * (cin_pad // 64) * n_tile * 128 // 2
+        idx = np.arange(total, dtype=np.int64)
+        byte = idx * 2
+        blk_bytes = n_tile * 128
+        blk, o = byte // blk_bytes, byte % blk_bytes
+        grp, row, chunk_sw, within = o >> 10, (o >> 7) & 7, (o >> 4) & 7, (o & 15) >> 1
+        n = grp * 8 + row
+        kk = ((chunk_sw ^ row) << 3) + within
+        cb_n = cin_pad // 64
+        tap, cb = blk // cb_n, blk % cb_n
+        src = tap * cin_pad + cb * 64 + kk
+        return w[n, src]
+    n_mma = 6 if kind == L.SLAB_STEM2D else kd * kh * 2
+    total = n_mma * 2 * n_tile * 8
+    idx = np.arange(total, dtype=np.int64)
+    e = idx & 7
+    t = idx >> 3
+    n = t % n_tile
+    t //= n_tile
+    j = t & 1
+    mma = t >> 1
+    if kind == L.SLAB_STEM2D:
+        ky, q = mma >> 1, mma & 1
+        kx = 2 * q + j
+        ok = (kx < 3) & (e < cin_pad)
+        src = (ky * 3 + kx) * cin_pad + e
+    else:
+        shift = pw_front & 1
+        q = mma & 1
+        kyt = mma >> 1
+        ky, kt = kyt % kh, kyt // kh
+        px = 2 * (2 * q + j) + (e >> 2)
+        ch = e & 3
+        kx = px - shift
+        ok = (kx >= 0) & (kx < kw) & (ch < cin_pad)
+        src = ((kt * kh + ky) * kw + kx) * cin_pad + ch
+    src = np.where(ok, src, 0)
+    return np.where(ok, w[n, src], np.uint16(0))
+
+
+# ------------------------------------------------------------------------------------- hardware
+def tma_box(xbits, plan, coords):
+    """Emulate one 5-D tiled TMA load: returns the shared-memory image (uint16, slab_stride bytes, zero padded)."""
+    box = list(plan.box)
+    dims = list(plan.tdim)
+    strides = [2] + list(plan.tstride)  # bytes
+    ii = np.meshgrid(*[np.arange(b) for b in reversed(box)], indexing="ij")  # order: i4,i3,i2,i1,i0
+    ii = [a.reshape(-1) for a in reversed(ii)]                                # back to i0..i4
+    ok = np.ones(ii[0].shape, dtype=bool)
+    off = np.full(ii[0].shape, plan.tbase_off, dtype=np.int64)
+    for d in range(5):
+        g = ii[d] + coords[d]
+        ok &= (g >= 0) & (g < dims[d])
+        off += g.astype(np.int64) * strides[d]
+    vals = np.where(ok, xbits[np.where(ok, off // 2, 0)], np.uint16(0))
+    lin = ((((ii[4] * box[3] + ii[3]) * box[2] + ii[2]) * box[1] + ii[1]) * box[0] + ii[0]).astype(np.int64) * 2
+    if plan.swizzle128:
+        lin ^= ((lin >> 7) & 7) << 4
+    smem = np.zeros(plan.slab_stride // 2, dtype=np.uint16)
+    smem[lin // 2] = vals
+    return smem
+
+
+def umma_operand(smem_bits, start, rows, layout, lbo, sbo):
+    """[rows, 16] fp32 operand a K=16 tcgen05.mma reads through a K-major shared-memory descriptor."""
+    r = np.arange(rows)[:, None]
+    k = np.arange(16)[None, :]
+    if layout == 2:
+        byte = start + (r >> 3) * sbo + (r & 7) * 128 + k * 2
+        byte = byte ^ (((byte >> 7) & 7) << 4)
+    else:
+        byte = start + (r >> 3) * sbo + (k >> 3) * lbo + (r & 7) * 16 + (k & 7) * 2
+    return bits_to_f32(smem_bits[byte // 2])
+
+
+def simulate_tiles(plan, xbits, image_bits, bias, tiles):
+    """Run the plan for the given tile indices; returns {tile: (n, tz, oy[128*tm], ox[128*tm], acc[128*tm, n_tile])}."""
+    out = {}
+    nt = plan.n_tile
+    img = np.concatenate([image_bits, np.zeros(64, np.uint16)])
+    for tile in tiles:
+        t = tile
+        tx = t % plan.tiles_x; t //= plan.tiles_x
+        ty = t % plan.tiles_y; t //= plan.tiles_y
+        tz = t % plan.tiles_z
+        n = t // plan.tiles_z
+        acc = np.zeros((plan.tm, 128, nt), dtype=np.float64)
+        for ks in range(plan.k_stages):
+            coords = (ks * plan.c_step, tx * plan.x_step + plan.x_off, ty * plan.y_step + plan.y_off,
+                      tz * plan.z_step + plan.z_off + ks * plan.z_kstep, n)
+            slab = tma_box(xbits, plan, coords)
+            for i in range(plan.n_mma):
+                a_off = plan.tab[2 * (ks * plan.n_mma + i)]
+                b_off = plan.tab[2 * (ks * plan.n_mma + i) + 1]
+                B = umma_operand(img, b_off, nt, plan.b_layout, plan.b_lbo, plan.b_sbo).astype(np.float64)
+                for h in range(plan.tm):
+                    A = umma_operand(slab, a_off + h * plan.half_a_off, 128, plan.a_layout, plan.a_lbo, plan.a_sbo)
+                    acc[h] += A.astype(np.float64) @ B.T
+        m = np.arange(128)
+        g, r = m >> 3, m & 7
+        oy = np.concatenate([ty * 16 + g for _ in range(plan.tm)])
+        ox = np.concatenate([(tx * plan.tm + h) * 8 + r for h in range(plan.tm)])
+        out[tile] = (n, tz, oy, ox, acc.reshape(plan.tm * 128, nt) + bias[None, :nt].astype(np.float64))
+    return out

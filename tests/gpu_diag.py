@@ -375,6 +375,187 @@ def group_perf():
     time_conv("unet 512->512 @28 x64", 64, (28, 28), 512, 512)
 
 
+# ------------------------------------------------------------------------------------------ SLAB feed
+def run_slab_case(name, kind, N, dhw, cin_real, cin_buf, cout, k, stride=(1, 1, 1), pad_f=(0, 1, 1), pad_b=None, halo=(0, 0, 0),
+                  tm=0, in_ld=None, in_coff=0, out_ld=None, out_coff=0, out_halo=None, pool=False, outconv=False,
+                  max_ctas=0, seed=0):
+    import numpy as np
+    import _slabsim as S
+    try:
+        g = torch.Generator(device="cpu").manual_seed(seed)
+        D, H, W = dhw
+        pad_b = pad_b if pad_b is not None else pad_f
+        x = torch.randn(N, cin_real, D, H, W, generator=g).to(DEV)
+        w = (torch.randn(cout, cin_real, *k, generator=g) / (cin_real * k[0] * k[1] * k[2]) ** 0.5).to(DEV)
+        b = (torch.rand(cout, generator=g) - 0.5).to(DEV)
+        bnp = ((torch.rand(cout, generator=g) + 0.5).to(DEV), (torch.rand(cout, generator=g) - 0.5).to(DEV),
+               (torch.rand(cout, generator=g) - 0.5).to(DEV), (torch.rand(cout, generator=g) + 0.5).to(DEV), 1e-3)
+        std_cin = 8 if kind != L.SLAB_3X3 else cin_buf
+        pc = ops.PackedConv(w, b, bnp, stride=stride, pad_front=pad_f, cin_pad=std_cin, device=DEV)
+        psc = ops.PackedSlabConv(pc, kind)
+        # the CUDA pack kernel against the numpy restatement, bit for bit
+        img_ref = S.pack_image(kind, S.bf16_bits(pc.w), pc.cout_pad, pc.k_pad, pc.cin_pad, pc.k, pad_f[2])
+        okp = bool(np.array_equal(S.bf16_bits(psc.image), img_ref))
+        RESULTS.append((name + ":pack", okp))
+        print(f"[{'PASS' if okp else 'FAIL'}] {name}: weight image == numpy packer ({img_ref.size * 2} B)")
+        od, oh, ow = pc.out_extent((D, H, W), pad_b)
+        ld_in = in_ld or cin_buf
+        xb = ops.CLTensor(N, D, H, W, ld_in, halo, device=DEV)
+        if ld_in != cin_buf:
+            xb.interior()[...] = 7.0
+        xv = xb.slice(in_coff, cin_buf)
+        xv.interior()[..., :cin_real] = x.permute(0, 2, 3, 4, 1).to(torch.bfloat16)
+        if cin_real < cin_buf:
+            xv.interior()[..., cin_real:] = 0
+        out_halo = out_halo if out_halo is not None else (halo if (od, oh, ow) == (D, H, W) else (0, 0, 0))
+        ld_out = out_ld or cout
+        yb = ops.CLTensor(N, od, oh, ow, ld_out, out_halo, device=DEV)
+        yb.buf.fill_(3.0)
+        yv = yb.slice(out_coff, cout)
+        pv = None
+        if pool:
+            pb = ops.CLTensor(N, 1, oh // 2, ow // 2, cout, (0, 1, 1), device=DEV)
+            pb.buf.fill_(3.0)
+            pv = pb
+        oc = None
+        if outconv:
+            ocw = (torch.randn(3, cout, generator=g) / 8).to(DEV)
+            ocb = torch.randn(3, generator=g).to(DEV)
+            planes = torch.full((N, 3, oh, ow), 9.0, device=DEV, dtype=torch.bfloat16)
+            frames = torch.full((N, 3, oh, ow), 9.0, device=DEV)
+            oc = (ocw, ocb, planes, frames)
+        ops.conv_slab_forward(xv, psc, yv, pool=pv, outconv=oc, tm=tm, max_ctas=max_ctas)
+        torch.cuda.synchronize()
+        kd, kh, kw = k
+        wq = pc.w[:cout, :kd * kh * kw * pc.cin_pad].float().reshape(cout, kd, kh, kw, pc.cin_pad)[..., :cin_real].permute(0, 4, 1, 2, 3)
+        pad6 = (pad_f[2], pad_b[2], pad_f[1], pad_b[1], pad_f[0], pad_b[0])
+        ref = conv_ref(bf(x), wq.contiguous(), pc.bias[:cout], stride, pad6, None, "relu")
+        plan = psc.plan(xv, yv, tm=tm)
+        ok = report(name, yv.to_ncdhw(), ref, extra=f"tm={plan.tm} stages={plan.stages} k_stages={plan.k_stages} tiles={plan.total_tiles} smem={plan.smem_bytes}")
+        if sum(out_halo) > 0:
+            full = yb.buf[..., out_coff:out_coff + cout].float().clone()
+            full[:, out_halo[0]:out_halo[0] + od, out_halo[1]:out_halo[1] + oh, out_halo[2]:out_halo[2] + ow] = 3.0
+            okh = bool((full == 3.0).all())
+            RESULTS.append((name + ":halo", okh))
+            print(f"[{'PASS' if okh else 'FAIL'}] {name}: halo untouched")
+        if ld_out != cout:
+            other = torch.ones(ld_out, dtype=torch.bool)
+            other[out_coff:out_coff + cout] = False
+            leak = (yb.interior()[..., other.to(DEV)].float() - 3.0).abs().max().item()
+            RESULTS.append((name + ":slice", leak == 0.0))
+            print(f"[{'PASS' if leak == 0.0 else 'FAIL'}] {name}: writes outside the channel slice: {leak}")
+        if pool:
+            pref = F.max_pool2d(yv.to_ncdhw()[:, :, 0], 2).unsqueeze(2)   # pooled from the kernel's own bf16 output
+            report(name + ":pool", pv.to_ncdhw(), pref, tol_rel=0)
+            fullp = pb.buf.float().clone()
+            fullp[:, :, 1:1 + oh // 2, 1:1 + ow // 2] = 3.0
+            okh = bool((fullp == 3.0).all())
+            RESULTS.append((name + ":pool halo", okh))
+            print(f"[{'PASS' if okh else 'FAIL'}] {name}: pool halo untouched")
+        if outconv:
+            fr_ref = torch.sigmoid(F.conv2d(ref[:, :, 0], ocw[:, :, None, None], ocb))
+            report(name + ":outconv frames", frames, fr_ref, tol_rel=2e-3)
+            report(name + ":outconv planes", planes.float(), fr_ref, tol_rel=6e-3)
+        return ok
+    except Exception:
+        RESULTS.append((name, False))
+        print(f"[FAIL] {name}: EXCEPTION\n{traceback.format_exc()}", flush=True)
+        return False
+
+
+def group_slab3():
+    K = L.SLAB_3X3
+    run_slab_case("S1 64->64 20x24 tm2", K, 2, (1, 20, 24), 64, 64, 64, (1, 3, 3), halo=(0, 1, 1), tm=2)
+    run_slab_case("S2 64->64 20x24 tm1 1cta", K, 2, (1, 20, 24), 64, 64, 64, (1, 3, 3), halo=(0, 1, 1), tm=1, max_ctas=1)
+    run_slab_case("S3 128->64 slices auto", K, 3, (1, 32, 32), 128, 128, 64, (1, 3, 3), halo=(0, 1, 1), in_ld=192, in_coff=64,
+                  out_ld=128, out_coff=64)
+    run_slab_case("S4 64->128 28x28", K, 2, (1, 28, 28), 64, 64, 128, (1, 3, 3), halo=(0, 1, 1))
+    run_slab_case("S5 64->64 pool fused 32x48", K, 3, (1, 32, 48), 64, 64, 64, (1, 3, 3), halo=(0, 1, 1), pool=True,
+                  out_ld=128, out_coff=0)
+    run_slab_case("S6 64->64 outconv fused", K, 4, (1, 32, 32), 64, 64, 64, (1, 3, 3), halo=(0, 1, 1), outconv=True)
+    run_slab_case("S7 64->64 112x112 x8 many tiles", K, 8, (1, 112, 112), 64, 64, 64, (1, 3, 3), halo=(0, 1, 1))
+    run_slab_case("S8 64->32 odd 19x21", K, 2, (1, 19, 21), 64, 64, 32, (1, 3, 3), halo=(0, 1, 1))
+    run_slab_case("S9 (1,3,3) D=3 64->64", K, 2, (3, 16, 16), 64, 64, 64, (1, 3, 3), halo=(0, 1, 1))
+
+
+def group_slabstem():
+    run_slab_case("T1 stem2d 3(8)->64 20x20 tm2", L.SLAB_STEM2D, 2, (1, 20, 20), 3, 8, 64, (1, 3, 3), tm=2, out_halo=(0, 1, 1))
+    run_slab_case("T2 stem2d tm1 40x24", L.SLAB_STEM2D, 3, (1, 40, 24), 3, 8, 64, (1, 3, 3), tm=1, out_halo=(0, 1, 1))
+    run_slab_case("T3 stem2d 112x112 x4", L.SLAB_STEM2D, 4, (1, 112, 112), 3, 8, 64, (1, 3, 3), out_halo=(0, 1, 1))
+    run_slab_case("T4 stem3d i3d 7x7x7 s2 SAME", L.SLAB_STEM3D, 1, (8, 20, 24), 3, 4, 64, (7, 7, 7), stride=(2, 2, 2),
+                  pad_f=(2, 2, 2), pad_b=(3, 3, 3))
+    run_slab_case("T5 stem3d i3res50 5x7x7 s2 p(2,3,3)", L.SLAB_STEM3D, 2, (8, 32, 32), 3, 4, 64, (5, 7, 7), stride=(2, 2, 2),
+                  pad_f=(2, 3, 3), tm=2)
+    run_slab_case("T6 stem3d r3d (3,7,7) s(1,2,2)", L.SLAB_STEM3D, 2, (4, 28, 28), 3, 4, 64, (3, 7, 7), stride=(1, 2, 2),
+                  pad_f=(1, 3, 3))
+    run_slab_case("T7 stem3d i3d 16x64x64 x2", L.SLAB_STEM3D, 2, (16, 64, 64), 3, 4, 64, (7, 7, 7), stride=(2, 2, 2),
+                  pad_f=(2, 2, 2), pad_b=(3, 3, 3))
+    # planar anonymizer output -> encoder clip (raw-reshape glue)
+    try:
+        g = torch.Generator(device="cpu").manual_seed(5)
+        B, T, H, W = 2, 16, 12, 16
+        fr = torch.rand(B * T, 3, H, W, generator=g).to(DEV).to(torch.bfloat16)
+        ref = fr.float().reshape(B, T, 3, H, W).reshape(B, 3, T, H, W)
+        for cpad in (4, 8):
+            enc = ops.CLTensor(B, T, H, W, cpad, device=DEV)
+            enc.buf.fill_(5.0)
+            ops.planes_to_clip(fr, enc, T)
+            report(f"planes_to_clip C={cpad}", enc.to_ncdhw()[:, :3], ref, tol_rel=0)
+            okz = bool((enc.interior()[..., 3:] == 0).all())
+            RESULTS.append((f"planes_to_clip C={cpad} pad", okz))
+            print(f"[{'PASS' if okz else 'FAIL'}] planes_to_clip C={cpad}: pad channels zero")
+    except Exception:
+        RESULTS.append(("planes_to_clip", False))
+        print(f"[FAIL] planes_to_clip: EXCEPTION\n{traceback.format_exc()}", flush=True)
+
+
+def time_slab(name, kind, N, dhw, cin_buf, cout, k, stride=(1, 1, 1), pad_f=(0, 1, 1), pad_b=None, tm=0, iters=10, pool=False,
+              cin_real=None):
+    try:
+        D, H, W = dhw
+        cin_real = cin_real or cin_buf
+        halo = (0, 1, 1) if kind == L.SLAB_3X3 else (0, 0, 0)
+        x = ops.CLTensor(N, D, H, W, cin_buf, halo, device=DEV)
+        x.interior().normal_()
+        wt = torch.randn(cout, cin_real, *k, device=DEV) / (cin_real * k[0] * k[1] * k[2]) ** 0.5
+        pc = ops.PackedConv(wt, None, None, stride=stride, pad_front=pad_f, cin_pad=cin_buf if kind == L.SLAB_3X3 else 8, device=DEV)
+        psc = ops.PackedSlabConv(pc, kind)
+        od, oh, ow = pc.out_extent((D, H, W), pad_b)
+        y = ops.CLTensor(N, od, oh, ow, cout, (0, 1, 1) if od == 1 else (0, 0, 0), device=DEV)
+        pv = ops.CLTensor(N, 1, oh // 2, ow // 2, cout, (0, 1, 1), device=DEV) if pool else None
+        for _ in range(3):
+            ops.conv_slab_forward(x, psc, y, pool=pv, tm=tm)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            ops.conv_slab_forward(x, psc, y, pool=pv, tm=tm)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        flops = 2.0 * N * od * oh * ow * cin_real * cout * k[0] * k[1] * k[2]
+        plan = psc.plan(x, y, tm=tm)
+        print(f"[PERF] slab {name}: {ms:.3f} ms  {flops / ms / 1e9:.1f} TFLOP/s (algorithmic)  tm={plan.tm} stages={plan.stages}",
+              flush=True)
+    except Exception:
+        print(f"[FAIL] perf slab {name}: EXCEPTION\n{traceback.format_exc()}", flush=True)
+
+
+def group_slabperf():
+    K = L.SLAB_3X3
+    for tm in (1, 2):
+        time_slab(f"64->64 @224 x128 tm{tm}", K, 128, (1, 224, 224), 64, 64, (1, 3, 3), tm=tm)
+    time_slab("64->64 @224 x128 +pool", K, 128, (1, 224, 224), 64, 64, (1, 3, 3), pool=True)
+    time_slab("128->64 @224 x128", K, 128, (1, 224, 224), 128, 64, (1, 3, 3))
+    time_slab("64->128 @112 x128", K, 128, (1, 112, 112), 64, 128, (1, 3, 3))
+    time_slab("128->64 @112 x128", K, 128, (1, 112, 112), 128, 64, (1, 3, 3))
+    for tm in (1, 2):
+        time_slab(f"stem2d 3->64 @224 x128 tm{tm}", L.SLAB_STEM2D, 128, (1, 224, 224), 8, 64, (1, 3, 3), tm=tm, cin_real=3)
+        time_slab(f"stem3d i3d 7x7x7 s2 x8 tm{tm}", L.SLAB_STEM3D, 8, (16, 224, 224), 4, 64, (7, 7, 7), stride=(2, 2, 2),
+                  pad_f=(2, 2, 2), pad_b=(3, 3, 3), tm=tm, cin_real=3)
+    time_conv("FLAT 64->64 @224 x128 (old feed)", 128, (224, 224), 64, 64)
+
+
 if __name__ == "__main__":
     groups = sys.argv[1:] or ["flat", "gather", "ops", "prep"]
     t0 = time.time()

@@ -31,6 +31,7 @@ def test_library_exports_every_declared_symbol():
         assert getattr(lib, name) is not None
     assert lib.tedspad_abi_version() == L.ABI_VERSION
     assert ctypes.sizeof(L.TensorDesc) == 48 and ctypes.sizeof(L.ConvDesc) == 48 * 2 + 24 + 19 * 4 + 4
+    assert ctypes.sizeof(L.ConvSlabDesc) == 256 and ctypes.sizeof(L.SlabPlan) == 1096
 
 
 def test_library_has_blackwell_sass():
@@ -111,7 +112,8 @@ def test_packed_conv_layout():
 def _emulated(monkeypatch, fp32=False):
     """Replace the CUDA operators by tests/_emu.py; fp32=True also stores activations/weights in fp32 so
     that executor wiring can be checked exactly (no rounding) against the oracle."""
-    for n in ("conv_forward", "maxpool", "upsample2x", "outconv_sigmoid", "avgpool_features", "nchw_to_cl", "preprocess"):
+    for n in ("conv_forward", "conv_slab_forward", "planes_to_clip", "maxpool", "upsample2x", "outconv_sigmoid",
+              "avgpool_features", "nchw_to_cl", "preprocess"):
         monkeypatch.setattr(ops, n, getattr(_emu, n))
     if fp32:
         orig = ops.CLTensor.__init__
@@ -134,7 +136,7 @@ def test_executor_wiring_unet_r3d_emulated(monkeypatch):
     ue = engine.UNetExecutor(sd_fa, "cpu")
     x0 = ue.input_buffer(16, 112, 112)
     ops.nchw_to_cl(x, x0)
-    enc = ops.CLTensor(1, 16, 112, 112, 8, device="cpu")
+    enc = ops.CLTensor(1, 16, 112, 112, engine.ENC_IN_CHANNELS, device="cpu")
     enc.buf.zero_()
     fr = torch.empty(16, 3, 112, 112)
     ue.run(x0, enc, 16, fr)
@@ -147,7 +149,7 @@ def test_executor_wiring_unet_r3d_emulated(monkeypatch):
 
 def _cl_fp32(x):
     n, c, d, h, w = x.shape
-    t = ops.CLTensor(n, d, h, w, 8, device="cpu")
+    t = ops.CLTensor(n, d, h, w, engine.ENC_IN_CHANNELS, device="cpu")  # 4: the SLAB stem's clip layout
     t.buf.zero_()
     t.interior()[..., :c] = x.permute(0, 2, 3, 4, 1)
     return t

@@ -1,0 +1,114 @@
+"""CPU tests of the SLAB feed: the plan the C-ABI library builds (TMA boxes, UMMA descriptor fields, MMA table)
+and the weight image, replayed with the hardware addressing rules in tests/_slabsim.py, must reproduce
+F.conv3d.  This pins tiling, tap offsets, swizzles, overlapped descriptors and K padding without a GPU."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "ted-spad_b200"))
+
+import _slabsim as S  # noqa: E402
+from tedspad_b200 import _lib as L, ops  # noqa: E402
+
+
+def _bf(t):
+    return t.to(torch.bfloat16).float()
+
+
+def _run(kind, x_cl, x_ref, w, stride, pad_f, pad_b, y_shape, tm, tiles=None, cin_pad=8):
+    """x_cl: CLTensor view (cpu) holding x_ref's data; returns max abs error over the simulated tiles."""
+    cout = w.shape[0]
+    b = torch.linspace(-0.5, 0.5, cout)
+    pc = ops.PackedConv(w, b, None, stride=stride, pad_front=pad_f, cin_pad=cin_pad, device="cpu")
+    psc = ops.PackedSlabConv(pc, kind)
+    y = ops.CLTensor(*y_shape, cout, device="cpu")
+    plan = psc.plan(x_cl, y, tm=tm)
+    image = S.pack_image(kind, S.bf16_bits(pc.w), pc.cout_pad, pc.k_pad, pc.cin_pad, pc.k, pad_f[2])
+    assert image.size * 2 == psc.image_bytes == plan.w_bytes
+    wq = pc.w[:cout, :pc.k[0] * pc.k[1] * pc.k[2] * pc.cin_pad].float().reshape(cout, *pc.k, pc.cin_pad)
+    wq = wq[..., :w.shape[1]].permute(0, 4, 1, 2, 3).contiguous()
+    pad6 = (pad_f[2], pad_b[2], pad_f[1], pad_b[1], pad_f[0], pad_b[0])
+    ref = F.conv3d(F.pad(_bf(x_ref), pad6), wq, pc.bias[:cout], stride=stride)  # [N,Cout,OD,OH,OW]
+    assert tuple(ref.shape[2:]) == tuple(y_shape[1:]), (ref.shape, y_shape)
+    tiles = list(range(plan.total_tiles)) if tiles is None else [t % plan.total_tiles for t in tiles]
+    res = S.simulate_tiles(plan, S.bf16_bits(x_cl.buf), image, pc.bias.numpy(), tiles)
+    worst, seen = 0.0, 0
+    OH, OW = y_shape[2], y_shape[3]
+    for tile, (n, tz, oy, ox, acc) in res.items():
+        ok = (oy < OH) & (ox < OW)
+        want = ref[n, :, tz][:, torch.from_numpy(oy[ok]), torch.from_numpy(ox[ok])].T.numpy()
+        worst = max(worst, float(np.abs(acc[ok][:, :cout] - want).max()))
+        seen += int(ok.sum())
+    return worst, seen, plan
+
+
+@pytest.mark.parametrize("cin,cout,tm,ld,coff", [(64, 64, 2, 64, 0), (128, 64, 0, 192, 64), (64, 128, 1, 64, 0)])
+def test_slab_3x3_plan_reproduces_conv(cin, cout, tm, ld, coff):
+    g = torch.Generator().manual_seed(cin + cout)
+    N, H, W = 2, 20, 24
+    x = torch.randn(N, cin, 1, H, W, generator=g)
+    w = torch.randn(cout, cin, 1, 3, 3, generator=g) / (9 * cin) ** 0.5
+    buf = ops.CLTensor(N, 1, H, W, ld, (0, 1, 1), device="cpu")
+    if ld != cin:
+        buf.interior()[...] = 7.0  # junk outside the view must never be read
+    xv = buf.slice(coff, cin)
+    xv.interior()[...] = x.permute(0, 2, 3, 4, 1).to(torch.bfloat16)
+    err, seen, plan = _run(L.SLAB_3X3, xv, x, w, (1, 1, 1), (0, 1, 1), (0, 1, 1), (N, 1, H, W), tm, cin_pad=cin)
+    assert plan.k_stages == cin // 64 and plan.n_mma == 36 and plan.swizzle128 == 1
+    assert plan.tm == (tm if tm else 1)  # 128->64 weights leave room for three stages only at tm=1
+    assert seen == N * H * W and err < 2e-5, (err, seen)
+
+
+def test_slab_stem2d_plan_reproduces_conv():
+    g = torch.Generator().manual_seed(3)
+    N, H, W = 2, 20, 20
+    x = torch.rand(N, 3, 1, H, W, generator=g)
+    w = torch.randn(64, 3, 1, 3, 3, generator=g) / 27 ** 0.5
+    xc = ops.CLTensor(N, 1, H, W, 8, device="cpu")
+    xc.buf.zero_()
+    xc.interior()[..., :3] = x.permute(0, 2, 3, 4, 1).to(torch.bfloat16)
+    for tm in (1, 2):
+        err, seen, plan = _run(L.SLAB_STEM2D, xc, x, w, (1, 1, 1), (0, 1, 1), (0, 1, 1), (N, 1, H, W), tm)
+        assert plan.a_layout == 0 and plan.a_lbo == 16 and plan.n_mma == 6 and plan.k_stages == 1
+        assert seen == N * H * W and err < 2e-5, (tm, err)
+
+
+@pytest.mark.parametrize("name,kd,sd,pad_f,pad_b,dhw", [
+    ("i3d Conv3d_1a_7x7 TF-SAME", 7, 2, (2, 2, 2), (3, 3, 3), (8, 20, 24)),
+    ("I3Res50 conv1", 5, 2, (2, 3, 3), (2, 3, 3), (8, 20, 24)),
+    ("r3d_18 stem", 3, 1, (1, 3, 3), (1, 3, 3), (4, 20, 24)),
+])
+def test_slab_stem3d_plan_reproduces_conv(name, kd, sd, pad_f, pad_b, dhw):
+    g = torch.Generator().manual_seed(kd)
+    N = 1
+    D, H, W = dhw
+    x = torch.rand(N, 3, D, H, W, generator=g)
+    w = torch.randn(64, 3, kd, 7, 7, generator=g) / (147 * kd) ** 0.5
+    xc = ops.CLTensor(N, D, H, W, 4, device="cpu")
+    xc.buf.zero_()
+    xc.interior()[..., :3] = x.permute(0, 2, 3, 4, 1).to(torch.bfloat16)
+    od = (D + pad_f[0] + pad_b[0] - kd) // sd + 1
+    oh = (H + pad_f[1] + pad_b[1] - 7) // 2 + 1
+    ow = (W + pad_f[2] + pad_b[2] - 7) // 2 + 1
+    for tm in (1, 2):
+        err, seen, plan = _run(L.SLAB_STEM3D, xc, x, w, (sd, 2, 2), pad_f, pad_b, (N, od, oh, ow), tm)
+        assert plan.k_stages == kd and plan.n_mma == 14
+        assert seen == N * od * oh * ow and err < 2e-5, (name, tm, err)
+
+
+def test_slab_plan_rejects_what_it_cannot_run():
+    pc = ops.PackedConv(torch.zeros(64, 64, 1, 3, 3), None, None, pad_front=(0, 1, 1), device="cpu")
+    psc = ops.PackedSlabConv(pc, L.SLAB_3X3)
+    x_nohalo = ops.CLTensor(1, 1, 16, 16, 64, device="cpu")
+    y = ops.CLTensor(1, 1, 16, 16, 64, device="cpu")
+    with pytest.raises(RuntimeError, match="halo"):
+        psc.plan(x_nohalo, y)
+    big = ops.PackedConv(torch.zeros(128, 128, 1, 3, 3), None, None, pad_front=(0, 1, 1), device="cpu")
+    x = ops.CLTensor(1, 1, 16, 16, 128, (0, 1, 1), device="cpu")
+    with pytest.raises(RuntimeError, match="do not fit"):
+        ops.PackedSlabConv(big, L.SLAB_3X3).plan(x, ops.CLTensor(1, 1, 16, 16, 128, device="cpu"))
