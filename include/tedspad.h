@@ -132,17 +132,19 @@ typedef struct tedspad_conv_slab {
 #define TEDSPAD_SLAB_MAX_MMA 112
 typedef struct tedspad_slab_plan {
   int32_t tm, n_tile, k_stages, n_mma, stages, tmem_cols;
+  int32_t n_grp, nk, a_kstep, b_kstep;   /* a K stage = n_grp table groups x nk K=16 steps (byte steps per K step) */
   int32_t box[5];           /* TMA box, elements: {c, w, h, d, n} */
   int32_t tdim[5];          /* TMA tensor dims, elements */
   int64_t tstride[4];       /* TMA global strides, bytes (dims 1..4) */
   int64_t tbase_off;        /* byte offset of the TMA base from x.ptr */
   int32_t swizzle128;       /* slab written with the 128-byte swizzle */
+  int32_t merged_cw;        /* stems: TMA dims are {W*C, H, D, N, 1}; the box x coordinate is scaled by 8 */
   int32_t slab_bytes, slab_stride, w_bytes, smem_bytes;
   int32_t a_layout, a_lbo, a_sbo, b_layout, b_lbo, b_sbo;   /* UMMA smem descriptor fields, bytes */
   int32_t half_a_off;       /* A byte offset of the second 8-column group */
   int32_t c_step, x_step, x_off, y_step, y_off, z_step, z_off, z_kstep;  /* slab origin per tile / K stage */
   int32_t tiles_x, tiles_y, tiles_z, total_tiles;
-  uint32_t tab[2 * TEDSPAD_SLAB_MAX_MMA];   /* per (k_stage, mma): {A byte offset in slab, B byte offset in image} */
+  uint32_t tab[2 * TEDSPAD_SLAB_MAX_MMA];   /* per (k_stage, group): {A byte offset in slab, B byte offset in image} */
 } tedspad_slab_plan;
 
 int tedspad_conv_slab_plan(const tedspad_conv_slab* p, tedspad_slab_plan* out);   /* host only, no GPU needed */

@@ -43,10 +43,11 @@ class ConvSlabDesc(C.Structure):
 
 class SlabPlan(C.Structure):
     """struct tedspad_slab_plan"""
-    _fields_ = ([(n, C.c_int32) for n in ("tm", "n_tile", "k_stages", "n_mma", "stages", "tmem_cols")] +
+    _fields_ = ([(n, C.c_int32) for n in ("tm", "n_tile", "k_stages", "n_mma", "stages", "tmem_cols", "n_grp", "nk",
+                                                  "a_kstep", "b_kstep")] +
                 [("box", C.c_int32 * 5), ("tdim", C.c_int32 * 5), ("tstride", C.c_int64 * 4), ("tbase_off", C.c_int64)] +
                 [(n, C.c_int32) for n in (
-                    "swizzle128", "slab_bytes", "slab_stride", "w_bytes", "smem_bytes", "a_layout", "a_lbo", "a_sbo",
+                    "swizzle128", "merged_cw", "slab_bytes", "slab_stride", "w_bytes", "smem_bytes", "a_layout", "a_lbo", "a_sbo",
                     "b_layout", "b_lbo", "b_sbo", "half_a_off", "c_step", "x_step", "x_off", "y_step", "y_off",
                     "z_step", "z_off", "z_kstep", "tiles_x", "tiles_y", "tiles_z", "total_tiles")] +
                 [("tab", C.c_uint32 * (2 * SLAB_MAX_MMA))])

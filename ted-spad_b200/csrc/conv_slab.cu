@@ -18,11 +18,12 @@
 // the B descriptors read (tedspad_conv_slab_pack); the MMA issuer walks a host-built table of
 // (A offset, B offset) pairs, so the kernel itself knows nothing about filter geometry.
 //
-//   warp 0      TMA producer   weights once (cp.async.bulk), then one slab box per (tile, K stage)
-//   warp 1      MMA issuer     one thread, n_mma x tm tcgen05.mma per K stage
-//   warp 2      TMEM allocator
-//   warps 4-7   epilogue       tcgen05.ld -> +bias -> ReLU -> bf16 stores; optional fused
-//                              MaxPool2d(2) (warp shuffles) and OutConv 1x1 + sigmoid
+//   warps 0-7   epilogue       two warps per TMEM lane quarter; tcgen05.ld (software-pipelined 32-column
+//                              chunks) -> +bias -> ReLU -> bf16 stores; optional fused MaxPool2d(2)
+//                              (warp shuffles) and OutConv 1x1 + sigmoid
+//   warp 8      TMA producer   weights once (cp.async.bulk), then one slab box per (tile, K stage)
+//   warp 9      MMA issuer     warp-uniform loop, one elected lane issues n_mma x tm tcgen05.mma per K stage
+//   warp 10     TMEM allocator
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
@@ -41,10 +42,10 @@ struct SlabKParams {
   CUtensorMap tmA;
   const uint8_t* w_image;
   const float* bias;
-  int tm, n_tile, k_stages, n_mma, stages, tmem_cols;
+  int tm, n_tile, k_stages, n_grp, nk, a_kstep, b_kstep, stages, tmem_cols;
   int slab_bytes, slab_stride, w_bytes, w_stride, zero_slabs;
   int half_a_off;
-  int c_step, x_step, x_off, y_step, y_off, z_step, z_off, z_kstep;
+  int c_step, x_step, x_off, y_step, y_off, z_step, z_off, z_kstep, merged_cw;
   int tiles_x, tiles_y, tiles_z, total_tiles;
   uint64_t a_desc, b_desc;
   // epilogue
@@ -68,9 +69,178 @@ __device__ __forceinline__ uint32_t max_bf162(uint32_t a, uint32_t b) {
   return *reinterpret_cast<const uint32_t*>(&m);
 }
 
-__global__ void __launch_bounds__(256, 1) conv_slab_kernel(const __grid_constant__ SlabKParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// MMA issue, executed by ALL lanes of the issuing warp with warp-uniform values (so the compiler keeps the
+// descriptors in uniform registers); one elected lane issues the tcgen05 instructions.  A K stage is n_grp
+// table groups (one filter tap / filter row each) of NK K=16 steps; the next group's table entry is fetched
+// while the current group's MMAs are issued.  TM and NK are compile-time so that the inner loop is straight
+// line code of ~3 uniform instructions per tcgen05.mma: at N = 64 the tensor pipe wants a new instruction
+// every ~48 clocks and a single warp retires a dependent uniform instruction only every ~7.
+template <int TM, int NK>
+__device__ __forceinline__ void slab_issue(const SlabKParams& p, uint8_t* smS, uint32_t w_addr, uint32_t tmem_base,
+                                           uint64_t* full, uint64_t* empty, uint64_t* tfull, uint64_t* tempty,
+                                           uint64_t* wbar) {
+  const uint32_t idesc = umma_idesc_bf16(128, p.n_tile);
+  const uint32_t a_hi = static_cast<uint32_t>(p.a_desc >> 32), a_lo0 = static_cast<uint32_t>(p.a_desc);
+  const uint32_t b_hi = static_cast<uint32_t>(p.b_desc >> 32);
+  const uint32_t b_lo0 = static_cast<uint32_t>(p.b_desc) + (w_addr >> 4);
+  const uint32_t half_step = static_cast<uint32_t>(p.half_a_off >> 4);
+  const uint32_t a_ks = static_cast<uint32_t>(p.a_kstep >> 4), b_ks = static_cast<uint32_t>(p.b_kstep >> 4);
+  const int S = p.stages, NG = p.n_grp, KS = p.k_stages, total = p.total_tiles;
+  const uint32_t n_tile = static_cast<uint32_t>(p.n_tile);
+  const uint32_t slab_step = static_cast<uint32_t>(p.slab_stride >> 4);
+  const uint32_t a_lo_base = a_lo0 + (smem_u32(smS) >> 4);
+  mbar_wait(wbar, 0);
+  int s = 0, as = 0;
+  uint32_t ph = 0, aph = 0;
+  for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    mbar_wait(tempty + as, aph ^ 1);
+    tc_fence_after();
+    const uint32_t d0 = tmem_base + static_cast<uint32_t>(as * TM) * n_tile;
+    const uint32_t d1 = d0 + n_tile;
+    for (int ks = 0; ks < KS; ++ks) {
+      const uint2* tab = p.tab + ks * NG;
+      uint2 cur = tab[0];
+      mbar_wait(full + s, ph);
+      tc_fence_after();
+      const uint32_t a_lo_s = a_lo_base + static_cast<uint32_t>(s) * slab_step;
+      for (int g = 0; g < NG; ++g) {
+        const uint2 nxt = tab[g + 1 < NG ? g + 1 : g];
+        const uint32_t a_lo = a_lo_s + cur.x, b_lo = b_lo0 + cur.y;
+        const uint32_t acc0 = (g | ks) != 0 ? 1u : 0u;
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < NK; ++k) {
+            const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) | (a_lo + k * a_ks);
+            const uint64_t bd = (static_cast<uint64_t>(b_hi) << 32) | (b_lo + k * b_ks);
+            umma_bf16_nc(d0, ad, bd, idesc, k == 0 ? acc0 : 1u);
+            if (TM == 2) {
+              const uint64_t ad1 = (static_cast<uint64_t>(a_hi) << 32) | (a_lo + k * a_ks + half_step);
+              umma_bf16_nc(d1, ad1, bd, idesc, k == 0 ? acc0 : 1u);
+            }
+          }
+        }
+        cur = nxt;
+      }
+      if (elect_one()) umma_commit(empty + s);
+      __syncwarp();
+      if (++s == S) { s = 0; ph ^= 1; }
+    }
+    if (elect_one()) umma_commit(tfull + as);
+    __syncwarp();
+    as ^= 1;
+    if (as == 0) aph ^= 1;
+  }
+}
+
+// One 32-column chunk of one half of the tile, for this thread's pixel: +bias, activation, bf16 stores and the
+// optional fused epilogues.  v = raw fp32 accumulators from TMEM.
+struct EpiCtx {
+  const float* bias;   // shared
+  const float* ocw;    // shared: [3][Cout] then [3]
+  __nv_bfloat16* y;
+  __nv_bfloat16* pool;
+  int Cout, act, y_ld, y_coff, p_ld, p_coff;
+  bool fuse_oc;
+};
+
+__device__ __forceinline__ void slab_epi_chunk(const EpiCtx& c, const uint32_t (&v)[32], int c0, bool row_ok, int x0,
+                                               int ow_lim, long long pix, bool pool_writer, long long ppix,
+                                               float (&oc)[3]) {
+  float f[32];
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    const float4 b4 = *reinterpret_cast<const float4*>(c.bias + c0 + i);
+    f[i] = __uint_as_float(v[i]) + b4.x;
+    f[i + 1] = __uint_as_float(v[i + 1]) + b4.y;
+    f[i + 2] = __uint_as_float(v[i + 2]) + b4.z;
+    f[i + 3] = __uint_as_float(v[i + 3]) + b4.w;
+  }
+  if (c.act == TEDSPAD_ACT_RELU) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+  }
+  if (c.fuse_oc && c0 < c.Cout) {
+#pragma unroll
+    for (int o = 0; o < 3; ++o) {
+      const float* wr = c.ocw + o * c.Cout + c0;
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const float4 w4 = *reinterpret_cast<const float4*>(wr + i);
+        oc[o] = fmaf(f[i], w4.x, oc[o]);
+        oc[o] = fmaf(f[i + 1], w4.y, oc[o]);
+        oc[o] = fmaf(f[i + 2], w4.z, oc[o]);
+        oc[o] = fmaf(f[i + 3], w4.w, oc[o]);
+      }
+    }
+  }
+  uint32_t q[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) q[i] = pack_bf162(f[2 * i], f[2 * i + 1]);
+  if (c.y != nullptr) {
+    // 4x4 transpose of 16-byte pieces inside each lane quad (two shuffle butterflies), so that one store
+    // instruction writes whole 64-byte runs (4 lanes = the 32 channels of ONE pixel, 8 pixels per instruction)
+    // instead of 32 lanes x 16 bytes in 32 different cache lines: 4x fewer L1 wavefronts per byte stored.
+    uint32_t t[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) t[i] = q[i];
+    const int qp = threadIdx.x & 3;
+    const bool odd = qp & 1, hi = qp & 2;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {  // stage 1 (lane ^ 1): even lanes trade pieces 1,3 for the partner's 0,2
+      const uint32_t x = odd ? t[0 + w] : t[4 + w], yv = odd ? t[8 + w] : t[12 + w];
+      const uint32_t xr = __shfl_xor_sync(0xffffffffu, x, 1), yr = __shfl_xor_sync(0xffffffffu, yv, 1);
+      if (odd) { t[0 + w] = xr; t[8 + w] = yr; } else { t[4 + w] = xr; t[12 + w] = yr; }
+    }
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {  // stage 2 (lane ^ 2): lanes 0,1 trade pieces 2,3 for the partners' 0,1
+      const uint32_t x = hi ? t[0 + w] : t[8 + w], yv = hi ? t[4 + w] : t[12 + w];
+      const uint32_t xr = __shfl_xor_sync(0xffffffffu, x, 2), yr = __shfl_xor_sync(0xffffffffu, yv, 2);
+      if (hi) { t[0 + w] = xr; t[4 + w] = yr; } else { t[8 + w] = xr; t[12 + w] = yr; }
+    }
+    // piece i now holds channels [c0 + 8*qp, +8) of the pixel of quad lane i: x0 - qp + i, same image row
+    if (c0 + 8 * qp < c.Cout) {
+      __nv_bfloat16* yp = c.y + (pix - qp) * c.y_ld + c.y_coff + c0 + 8 * qp;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (row_ok && x0 - qp + i < ow_lim)
+          *reinterpret_cast<uint4*>(yp + static_cast<long long>(i) * c.y_ld) =
+              make_uint4(t[4 * i], t[4 * i + 1], t[4 * i + 2], t[4 * i + 3]);
+    }
+  }
+  if (c.pool != nullptr) {
+    // MaxPool2d(2): x partner = lane ^ 1 (r ^ 1), y partner = lane ^ 8 (g ^ 1)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      q[i] = max_bf162(q[i], __shfl_xor_sync(0xffffffffu, q[i], 1));
+      q[i] = max_bf162(q[i], __shfl_xor_sync(0xffffffffu, q[i], 8));
+    }
+    if (pool_writer) {
+      __nv_bfloat16* pp = c.pool + ppix * c.p_ld + c.p_coff + c0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (c0 + 8 * j < c.Cout)
+          *reinterpret_cast<uint4*>(pp + 8 * j) = make_uint4(q[4 * j], q[4 * j + 1], q[4 * j + 2], q[4 * j + 3]);
+    }
+  }
+}
+
+constexpr int SLAB_THREADS = 352;   // warps 0-7 epilogue (two per TMEM lane quarter), 8 producer, 9 MMA, 10 TMEM alloc
+
+__global__ void __launch_bounds__(SLAB_THREADS, 1) conv_slab_kernel(const __grid_constant__ SlabKParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // round up inside the shared window (pointer arithmetic on the symbol keeps the shared address space,
+  // so bias / OutConv weights are read with LDS instead of generic loads)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
   const int S = p.stages;
   uint8_t* smW = smem;
@@ -84,23 +254,23 @@ __global__ void __launch_bounds__(256, 1) conv_slab_kernel(const __grid_constant
   uint64_t* wbar = tempty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);  // provably warp-uniform
   const int lane = threadIdx.x & 31;
 
-  if (warp == 0 && lane == 0) tma_prefetch_desc(&p.tmA);
-  if (warp == 1 && lane == 0) {
+  if (warp == 8 && lane == 0) tma_prefetch_desc(&p.tmA);
+  if (warp == 9 && lane == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(full + s, 1);
       mbar_init(empty + s, 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull + a, 1);
-      mbar_init(tempty + a, 4);
+      mbar_init(tempty + a, 8);
     }
     mbar_init(wbar, 1);
     fence_barrier_init();
   }
-  if (warp == 2) {
+  if (warp == 10) {
     tmem_alloc(tmem_slot, p.tmem_cols);
     tmem_relinquish();
   }
@@ -121,7 +291,7 @@ __global__ void __launch_bounds__(256, 1) conv_slab_kernel(const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == 8) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
       mbar_arrive_expect_tx(wbar, static_cast<uint32_t>(p.w_bytes));
@@ -139,50 +309,40 @@ __global__ void __launch_bounds__(256, 1) conv_slab_kernel(const __grid_constant
         for (int ks = 0; ks < p.k_stages; ++ks) {
           mbar_wait(empty + s, ph ^ 1);
           mbar_arrive_expect_tx(full + s, static_cast<uint32_t>(p.slab_bytes));
-          tma_load_5d(smS + s * p.slab_stride, &p.tmA, full + s, ks * p.c_step, cx, cy, cz + ks * p.z_kstep, n);
+          if (p.merged_cw)  // stems: (pixel, channel) merged into one contiguous inner dimension of 8-element pixels
+            tma_load_5d(smS + s * p.slab_stride, &p.tmA, full + s, cx * 8, cy, cz + ks * p.z_kstep, n, 0);
+          else
+            tma_load_5d(smS + s * p.slab_stride, &p.tmA, full + s, ks * p.c_step, cx, cy, cz + ks * p.z_kstep, n);
           if (++s == S) { s = 0; ph ^= 1; }
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 9) {
     // -------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(128, p.n_tile);
-      const uint32_t w_addr = smem_u32(smW);
-      const uint64_t half_step = static_cast<uint64_t>(p.half_a_off >> 4);
-      mbar_wait(wbar, 0);
-      int s = 0, as = 0;
-      uint32_t ph = 0, aph = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        mbar_wait(tempty + as, aph ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * p.tm * p.n_tile);
-        for (int ks = 0; ks < p.k_stages; ++ks) {
-          mbar_wait(full + s, ph);
-          tc_fence_after();
-          const uint32_t slab_addr = smem_u32(smS + s * p.slab_stride);
-          const uint2* tab = p.tab + ks * p.n_mma;
-          for (int i = 0; i < p.n_mma; ++i) {
-            const uint2 e = tab[i];
-            const uint64_t ad = p.a_desc | static_cast<uint64_t>(((slab_addr + e.x) & 0x3FFFFu) >> 4);
-            const uint64_t bd = p.b_desc | static_cast<uint64_t>(((w_addr + e.y) & 0x3FFFFu) >> 4);
-            const uint32_t acc = (ks | i) != 0 ? 1u : 0u;
-            umma_bf16(d_tmem, ad, bd, idesc, acc);
-            if (p.tm == 2) umma_bf16(d_tmem + p.n_tile, ad + half_step, bd, idesc, acc);
-          }
-          umma_commit(empty + s);
-          if (++s == S) { s = 0; ph ^= 1; }
-        }
-        umma_commit(tfull + as);
-        as ^= 1;
-        if (as == 0) aph ^= 1;
-      }
+    const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+    if (p.tm == 2) {
+      if (p.nk == 4) slab_issue<2, 4>(p, smS, smem_u32(smW), tb, full, empty, tfull, tempty, wbar);
+      else slab_issue<2, 2>(p, smS, smem_u32(smW), tb, full, empty, tfull, tempty, wbar);
+    } else {
+      if (p.nk == 4) slab_issue<1, 4>(p, smS, smem_u32(smW), tb, full, empty, tfull, tempty, wbar);
+      else slab_issue<1, 2>(p, smS, smem_u32(smW), tb, full, empty, tfull, tempty, wbar);
     }
-  } else if (warp >= 4) {
+  } else if (warp < 8) {
     // ---------------------------------------------------------------- epilogue
-    const int ew = warp - 4;          // TMEM lane quarter
+    // Two warps per TMEM lane quarter.  tm == 2: warp group eg owns half eg of the tile (all its columns, so the
+    // fused OutConv dot product stays inside one thread); tm == 1: the groups split the 32-column chunks.
+    const int ew = warp & 3, eg = warp >> 2;
     const int g = ew * 4 + (lane >> 3);
     const int r = lane & 7;
+    const int tm = p.tm, n_tile = p.n_tile, OH = p.OH, OW = p.OW;
+    const int nchunk_all = n_tile >> 5;
+    EpiCtx c;
+    c.bias = sm_bias; c.ocw = sm_ocw; c.y = p.y; c.pool = p.pool; c.Cout = p.Cout; c.act = p.act;
+    c.y_ld = p.y_ld; c.y_coff = p.y_coff; c.p_ld = p.p_ld; c.p_coff = p.p_coff; c.fuse_oc = p.oc_w != nullptr;
+    int h, c_first, c_step, nch;
+    if (tm == 2) { h = eg; c_first = 0; c_step = 32; nch = nchunk_all; }
+    else if (c.fuse_oc) { h = 0; c_first = 0; c_step = 32; nch = eg == 0 ? nchunk_all : 0; }
+    else { h = 0; c_first = 32 * eg; c_step = 64; nch = (nchunk_all + 1 - eg) >> 1; }
     int as = 0;
     uint32_t aph = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -192,88 +352,44 @@ __global__ void __launch_bounds__(256, 1) conv_slab_kernel(const __grid_constant
       const int tz = t % p.tiles_z;
       const int n = t / p.tiles_z;
       const int oy = ty * 16 + g;
+      const int ox = (tx * tm + h) * 8 + r;
+      const bool valid = oy < OH && ox < OW;
+      const long long pix = ((static_cast<long long>(n) * p.yDp + tz + p.ypd) * p.yHp + oy + p.yph) * p.yWp + ox + p.ypw;
+      const int py = oy >> 1, px = ox >> 1;
+      const bool pool_writer = ((lane & 9) == 0) && py < p.PH && px < p.PW;
+      const long long ppix = (static_cast<long long>(n) * p.pHp + py + p.pph) * p.pWp + px + p.ppw;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) +
+                             static_cast<uint32_t>((as * tm + h) * n_tile + c_first);
+      float oc[3] = {0.f, 0.f, 0.f};
       mbar_wait(tfull + as, aph);
       tc_fence_after();
-      for (int h = 0; h < p.tm; ++h) {
-        const int ox = (tx * p.tm + h) * 8 + r;
-        const bool valid = oy < p.OH && ox < p.OW;
-        const long long pix = ((static_cast<long long>(n) * p.yDp + tz + p.ypd) * p.yHp + oy + p.yph) * p.yWp + ox + p.ypw;
-        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) +
-                               static_cast<uint32_t>((as * p.tm + h) * p.n_tile);
-        float oc[3] = {0.f, 0.f, 0.f};
-        for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld32(t_row + c0, v);
+      // software pipeline over this warp's chunks: the next chunk's TMEM load is in flight while one is processed
+      uint32_t va[32], vb[32];
+      if (nch > 0) tmem_ld32(t_row, va);
+      for (int i = 0; i < nch; i += 2) {
+        tmem_ld_wait();
+        if (i + 1 < nch) tmem_ld32(t_row + (i + 1) * c_step, vb);
+        slab_epi_chunk(c, va, c_first + i * c_step, oy < OH, ox, OW, pix, pool_writer, ppix, oc);
+        if (i + 1 < nch) {
           tmem_ld_wait();
-          float f[32];
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 b4 = *reinterpret_cast<const float4*>(sm_bias + c0 + i);
-            f[i] = __uint_as_float(v[i]) + b4.x;
-            f[i + 1] = __uint_as_float(v[i + 1]) + b4.y;
-            f[i + 2] = __uint_as_float(v[i + 2]) + b4.z;
-            f[i + 3] = __uint_as_float(v[i + 3]) + b4.w;
-          }
-          if (p.act == TEDSPAD_ACT_RELU) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
-          }
-          if (p.oc_w != nullptr && c0 < p.Cout) {
-#pragma unroll
-            for (int o = 0; o < 3; ++o) {
-              const float* wr = sm_ocw + o * p.Cout + c0;
-#pragma unroll
-              for (int i = 0; i < 32; i += 4) {
-                const float4 w4 = *reinterpret_cast<const float4*>(wr + i);
-                oc[o] = fmaf(f[i], w4.x, oc[o]);
-                oc[o] = fmaf(f[i + 1], w4.y, oc[o]);
-                oc[o] = fmaf(f[i + 2], w4.z, oc[o]);
-                oc[o] = fmaf(f[i + 3], w4.w, oc[o]);
-              }
-            }
-          }
-          uint32_t q[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) q[i] = pack_bf162(f[2 * i], f[2 * i + 1]);
-          if (p.y != nullptr && valid) {
-            __nv_bfloat16* yp = p.y + pix * p.y_ld + p.y_coff + c0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (c0 + 8 * j < p.Cout)
-                *reinterpret_cast<uint4*>(yp + 8 * j) = make_uint4(q[4 * j], q[4 * j + 1], q[4 * j + 2], q[4 * j + 3]);
-          }
-          if (p.pool != nullptr) {
-            // MaxPool2d(2): x partner = lane ^ 1 (r ^ 1), y partner = lane ^ 8 (g ^ 1)
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              q[i] = max_bf162(q[i], __shfl_xor_sync(0xffffffffu, q[i], 1));
-              q[i] = max_bf162(q[i], __shfl_xor_sync(0xffffffffu, q[i], 8));
-            }
-            const int py = oy >> 1, px = ox >> 1;
-            if (((lane & 9) == 0) && py < p.PH && px < p.PW) {
-              const long long ppix = (static_cast<long long>(n) * p.pHp + py + p.pph) * p.pWp + px + p.ppw;
-              __nv_bfloat16* pp = p.pool + ppix * p.p_ld + p.p_coff + c0;
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                if (c0 + 8 * j < p.Cout)
-                  *reinterpret_cast<uint4*>(pp + 8 * j) = make_uint4(q[4 * j], q[4 * j + 1], q[4 * j + 2], q[4 * j + 3]);
-            }
-          }
-        }
-        if (p.oc_w != nullptr && valid) {
-          const long long plane = static_cast<long long>(p.OH) * p.OW;
-          const long long o0 = static_cast<long long>(n) * 3 * plane + static_cast<long long>(oy) * p.OW + ox;
-#pragma unroll
-          for (int o = 0; o < 3; ++o) {
-            const float sgm = 1.f / (1.f + __expf(-(oc[o] + sm_ocw[3 * p.Cout + o])));
-            p.oc_planes[o0 + o * plane] = __float2bfloat16_rn(sgm);
-            if (p.oc_frames != nullptr) p.oc_frames[o0 + o * plane] = sgm;
-          }
+          if (i + 2 < nch) tmem_ld32(t_row + (i + 2) * c_step, va);
+          slab_epi_chunk(c, vb, c_first + (i + 1) * c_step, oy < OH, ox, OW, pix, pool_writer, ppix, oc);
         }
       }
+      // all TMEM reads of this accumulator are complete (wait::ld above): hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty + as);
+      if (c.fuse_oc && valid && nch > 0) {
+        const long long plane = static_cast<long long>(OH) * OW;
+        const long long o0 = static_cast<long long>(n) * 3 * plane + static_cast<long long>(oy) * OW + ox;
+#pragma unroll
+        for (int o = 0; o < 3; ++o) {
+          const float sgm = 1.f / (1.f + __expf(-(oc[o] + sm_ocw[3 * p.Cout + o])));
+          p.oc_planes[o0 + o * plane] = __float2bfloat16_rn(sgm);
+          if (p.oc_frames != nullptr) p.oc_frames[o0 + o * plane] = sgm;
+        }
+      }
       as ^= 1;
       if (as == 0) aph ^= 1;
     }
@@ -282,7 +398,7 @@ __global__ void __launch_bounds__(256, 1) conv_slab_kernel(const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == 2) tmem_dealloc(tmem_base, p.tmem_cols);
+  if (warp == 10) tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
 // ------------------------------------------------------------------------------------ weight image
@@ -351,7 +467,8 @@ static int make_plan(const tedspad_conv_slab& c, tedspad_slab_plan& P) {
   const tedspad_tensor& y = c.y;
   TSP_CHECK(c.Cout_pad % 16 == 0 && c.Cout_pad >= 16 && c.Cout_pad <= 256 && c.Cout <= c.Cout_pad && c.Cout >= 1,
             "slab: Cout=%d Cout_pad=%d invalid (single N tile <= 256)", c.Cout, c.Cout_pad);
-  TSP_CHECK(c.Cout % 8 == 0, "slab: Cout=%d must be a multiple of 8", c.Cout);
+  TSP_CHECK(c.Cout % 8 == 0 && c.Cout_pad % 32 == 0, "slab: Cout=%d must be a multiple of 8 and Cout_pad=%d of 32", c.Cout,
+            c.Cout_pad);
   TSP_CHECK(x.N == y.N && x.N >= 1, "slab: batch mismatch");
   P.n_tile = c.Cout_pad;
   const int Wp = x.W + 2 * x.pw, Hp = x.H + 2 * x.ph, Dp = x.D + 2 * x.pd;
@@ -371,7 +488,9 @@ static int make_plan(const tedspad_conv_slab& c, tedspad_slab_plan& P) {
     P.w_bytes = static_cast<int>(slab_image_bytes(c.kind, P.n_tile, x.C, 1, 3, 3));
     P.swizzle128 = sw ? 1 : 0;
     P.k_stages = sw ? x.C / 64 : 1;
-    P.n_mma = sw ? 36 : 6;
+    P.n_grp = sw ? 9 : 3;     // filter taps (3x3) / filter rows (stem)
+    P.nk = sw ? 4 : 2;        // K=16 steps per group
+    P.n_mma = P.n_grp * P.nk;
     const int px_bytes = sw ? 128 : 16;
     // tile width: two 8-column halves when the image is wide enough and three slab stages still fit
     int tm = c.tm;
@@ -387,12 +506,25 @@ static int make_plan(const tedspad_conv_slab& c, tedspad_slab_plan& P) {
     slab_w = 8 * tm + 2;
     slab_h = 18;
     pad_bytes = sw ? 0 : 64;  // stem: the zero-weight tap kx=3 of the last row reads past the box
-    P.box[0] = sw ? 64 : 8; P.box[1] = slab_w; P.box[2] = slab_h; P.box[3] = 1; P.box[4] = 1;
-    P.tdim[0] = x.C; P.tdim[1] = Wp; P.tdim[2] = Hp; P.tdim[3] = Dp; P.tdim[4] = x.N;
-    P.tstride[0] = static_cast<int64_t>(x.ld) * 2;
-    P.tstride[1] = P.tstride[0] * Wp;
-    P.tstride[2] = P.tstride[1] * Hp;
-    P.tstride[3] = P.tstride[2] * Dp;
+    if (sw) {
+      P.box[0] = 64; P.box[1] = slab_w; P.box[2] = slab_h; P.box[3] = 1; P.box[4] = 1;
+      P.tdim[0] = x.C; P.tdim[1] = Wp; P.tdim[2] = Hp; P.tdim[3] = Dp; P.tdim[4] = x.N;
+      P.tstride[0] = static_cast<int64_t>(x.ld) * 2;
+      P.tstride[1] = P.tstride[0] * Wp;
+      P.tstride[2] = P.tstride[1] * Hp;
+      P.tstride[3] = P.tstride[2] * Dp;
+    } else {
+      // pixels are 16 contiguous bytes: merge (pixel, channel) into one inner dimension so that a slab row
+      // is ONE contiguous TMA row of slab_w*16 bytes instead of slab_w 16-byte rows
+      TSP_CHECK(x.ld == 8 && x.coff == 0, "slab stem2d: input must be a dense 8-channel image (ld=%d coff=%d)", x.ld, x.coff);
+      P.merged_cw = 1;
+      P.box[0] = slab_w * 8; P.box[1] = slab_h; P.box[2] = 1; P.box[3] = 1; P.box[4] = 1;
+      P.tdim[0] = Wp * 8; P.tdim[1] = Hp; P.tdim[2] = Dp; P.tdim[3] = x.N; P.tdim[4] = 1;
+      P.tstride[0] = static_cast<int64_t>(Wp) * 16;
+      P.tstride[1] = P.tstride[0] * Hp;
+      P.tstride[2] = P.tstride[1] * Dp;
+      P.tstride[3] = P.tstride[2] * x.N;
+    }
     P.tbase_off = static_cast<int64_t>(x.coff) * 2;
     P.c_step = sw ? 64 : 0;
     P.x_step = 8 * tm; P.x_off = x.pw - 1;
@@ -405,21 +537,22 @@ static int make_plan(const tedspad_conv_slab& c, tedspad_slab_plan& P) {
     if (sw) {
       P.a_layout = 2; P.a_lbo = 16; P.a_sbo = slab_w * 128;
       P.b_layout = 2; P.b_lbo = 16; P.b_sbo = 1024;
+      P.a_kstep = 32; P.b_kstep = 32;
       const int cb_n = x.C / 64;
       for (int cb = 0; cb < cb_n; ++cb)
-        for (int tap = 0; tap < 9; ++tap)
-          for (int k = 0; k < 4; ++k) {
-            const int i = (cb * 9 + tap) * 4 + k;
-            TSP_CHECK(i < TEDSPAD_SLAB_MAX_MMA, "slab 3x3: %d MMAs exceed the table (Cin too large)", i + 1);
-            P.tab[2 * i] = static_cast<uint32_t>(((tap / 3) * slab_w + (tap % 3)) * 128 + k * 32);
-            P.tab[2 * i + 1] = static_cast<uint32_t>((tap * cb_n + cb) * P.n_tile * 128 + k * 32);
-          }
+        for (int tap = 0; tap < 9; ++tap) {
+          const int i = cb * 9 + tap;
+          TSP_CHECK(i < TEDSPAD_SLAB_MAX_MMA, "slab 3x3: %d table groups exceed the table (Cin too large)", i + 1);
+          P.tab[2 * i] = static_cast<uint32_t>(((tap / 3) * slab_w + (tap % 3)) * 128);
+          P.tab[2 * i + 1] = static_cast<uint32_t>((tap * cb_n + cb) * P.n_tile * 128);
+        }
     } else {
       P.a_layout = 0; P.a_lbo = 16; P.a_sbo = slab_w * 16;
       P.b_layout = 0; P.b_lbo = P.n_tile * 16; P.b_sbo = 128;
-      for (int i = 0; i < 6; ++i) {
-        P.tab[2 * i] = static_cast<uint32_t>(((i >> 1) * slab_w + 2 * (i & 1)) * 16);
-        P.tab[2 * i + 1] = static_cast<uint32_t>(i * 2 * P.n_tile * 16);
+      P.a_kstep = 32; P.b_kstep = 2 * P.n_tile * 16;   // next K=16 step: two pixels further, next weight block
+      for (int ky = 0; ky < 3; ++ky) {
+        P.tab[2 * ky] = static_cast<uint32_t>(ky * slab_w * 16);
+        P.tab[2 * ky + 1] = static_cast<uint32_t>(ky * 2 * P.b_kstep);
       }
     }
   } else if (c.kind == TEDSPAD_SLAB_STEM3D) {
@@ -441,13 +574,17 @@ static int make_plan(const tedspad_conv_slab& c, tedspad_slab_plan& P) {
     slab_h = 37;
     pad_bytes = 64;
     P.k_stages = c.kd;
+    P.n_grp = 7;   // filter rows
+    P.nk = 2;      // two K=16 steps = 4 pixel pairs = the 8-pixel window of one filter row
     P.n_mma = 14;
-    P.box[0] = 8; P.box[1] = pairs; P.box[2] = slab_h; P.box[3] = 1; P.box[4] = 1;
-    P.tdim[0] = 8; P.tdim[1] = x.W / 2; P.tdim[2] = x.H; P.tdim[3] = x.D; P.tdim[4] = x.N;
-    P.tstride[0] = 16;
-    P.tstride[1] = static_cast<int64_t>(x.W) * 8;
-    P.tstride[2] = P.tstride[1] * x.H;
-    P.tstride[3] = P.tstride[2] * x.D;
+    // (pixel pair, channel) merged into one contiguous inner dimension: a slab row is one TMA row
+    P.merged_cw = 1;
+    P.box[0] = pairs * 8; P.box[1] = slab_h; P.box[2] = 1; P.box[3] = 1; P.box[4] = 1;
+    P.tdim[0] = x.W * 4; P.tdim[1] = x.H; P.tdim[2] = x.D; P.tdim[3] = x.N; P.tdim[4] = 1;
+    P.tstride[0] = static_cast<int64_t>(x.W) * 8;
+    P.tstride[1] = P.tstride[0] * x.H;
+    P.tstride[2] = P.tstride[1] * x.D;
+    P.tstride[3] = P.tstride[2] * x.N;
     P.tbase_off = 0;
     P.c_step = 0;
     P.x_step = 8 * tm; P.x_off = -(pwe / 2);
@@ -459,18 +596,19 @@ static int make_plan(const tedspad_conv_slab& c, tedspad_slab_plan& P) {
     P.half_a_off = 8 * 16;
     P.a_layout = 0; P.a_lbo = 16; P.a_sbo = 2 * pairs * 16;
     P.b_layout = 0; P.b_lbo = P.n_tile * 16; P.b_sbo = 128;
+    P.a_kstep = 32; P.b_kstep = 2 * P.n_tile * 16;
     for (int kt = 0; kt < c.kd; ++kt)
-      for (int i = 0; i < 14; ++i) {
-        const int e = kt * 14 + i;
+      for (int ky = 0; ky < 7; ++ky) {
+        const int e = kt * 7 + ky;
         TSP_CHECK(e < TEDSPAD_SLAB_MAX_MMA, "slab stem3d: table overflow");
-        P.tab[2 * e] = static_cast<uint32_t>((i >> 1) * pairs * 16 + (i & 1) * 32);
-        P.tab[2 * e + 1] = static_cast<uint32_t>(e * 2 * P.n_tile * 16);
+        P.tab[2 * e] = static_cast<uint32_t>(ky * pairs * 16);
+        P.tab[2 * e + 1] = static_cast<uint32_t>(e * 2 * P.b_kstep);
       }
     // the last output row/column must read inside the zero-filled box: guaranteed by TMA OOB fill
   } else {
     TSP_CHECK(false, "slab: unknown kind %d", c.kind);
   }
-  P.slab_bytes = P.box[0] * 2 * slab_w * slab_h;
+  P.slab_bytes = 2 * P.box[0] * P.box[1] * P.box[2] * P.box[3] * P.box[4];
   P.slab_stride = static_cast<int>(round_up(P.slab_bytes + pad_bytes, 1024));
   const int w_stride = static_cast<int>(round_up(P.w_bytes, 1024));
   const int avail = SLAB_SMEM_BUDGET - 1024 - SLAB_TAIL_BYTES - w_stride;
@@ -552,18 +690,19 @@ extern "C" int tedspad_conv_slab_forward(const tedspad_conv_slab* c, void* strea
   if (encode_tmap_5d_bf16(&p.tmA, base, dims, strides, box, P.swizzle128 != 0)) return 3;
   p.w_image = reinterpret_cast<const uint8_t*>(c->w_image);
   p.bias = c->bias;
-  p.tm = P.tm; p.n_tile = P.n_tile; p.k_stages = P.k_stages; p.n_mma = P.n_mma; p.stages = P.stages;
+  p.tm = P.tm; p.n_tile = P.n_tile; p.k_stages = P.k_stages; p.n_grp = P.n_grp; p.nk = P.nk; p.stages = P.stages;
+  p.a_kstep = P.a_kstep; p.b_kstep = P.b_kstep;
   p.tmem_cols = P.tmem_cols;
   p.slab_bytes = P.slab_bytes; p.slab_stride = P.slab_stride; p.w_bytes = P.w_bytes;
   p.w_stride = (int)round_up(P.w_bytes, 1024);
   p.zero_slabs = P.swizzle128 ? 0 : 1;
   p.half_a_off = P.half_a_off;
   p.c_step = P.c_step; p.x_step = P.x_step; p.x_off = P.x_off; p.y_step = P.y_step; p.y_off = P.y_off;
-  p.z_step = P.z_step; p.z_off = P.z_off; p.z_kstep = P.z_kstep;
+  p.z_step = P.z_step; p.z_off = P.z_off; p.z_kstep = P.z_kstep; p.merged_cw = P.merged_cw;
   p.tiles_x = P.tiles_x; p.tiles_y = P.tiles_y; p.tiles_z = P.tiles_z; p.total_tiles = P.total_tiles;
   p.a_desc = umma_desc_template(P.a_layout, P.a_lbo, P.a_sbo);
   p.b_desc = umma_desc_template(P.b_layout, P.b_lbo, P.b_sbo);
-  for (int i = 0; i < P.k_stages * P.n_mma; ++i) p.tab[i] = make_uint2(P.tab[2 * i], P.tab[2 * i + 1]);
+  for (int i = 0; i < P.k_stages * P.n_grp; ++i) p.tab[i] = make_uint2(P.tab[2 * i] >> 4, P.tab[2 * i + 1] >> 4);  // 16-byte units
 
   p.y = reinterpret_cast<__nv_bfloat16*>(y.ptr);
   p.OH = y.H; p.OW = y.W;
@@ -599,7 +738,7 @@ extern "C" int tedspad_conv_slab_forward(const tedspad_conv_slab* c, void* strea
   if (rc) return rc;
   int ctas = c->max_ctas > 0 ? c->max_ctas : num_sms();
   ctas = std::max(1, std::min(ctas, p.total_tiles));
-  conv_slab_kernel<<<ctas, 256, P.smem_bytes, reinterpret_cast<cudaStream_t>(stream_v)>>>(p);
+  conv_slab_kernel<<<ctas, SLAB_THREADS, P.smem_bytes, reinterpret_cast<cudaStream_t>(stream_v)>>>(p);
   TSP_CUDA(cudaGetLastError());
   return 0;
 }

@@ -124,12 +124,14 @@ def simulate_tiles(plan, xbits, image_bits, bias, tiles):
         n = t // plan.tiles_z
         acc = np.zeros((plan.tm, 128, nt), dtype=np.float64)
         for ks in range(plan.k_stages):
-            coords = (ks * plan.c_step, tx * plan.x_step + plan.x_off, ty * plan.y_step + plan.y_off,
-                      tz * plan.z_step + plan.z_off + ks * plan.z_kstep, n)
+            cx, cy = tx * plan.x_step + plan.x_off, ty * plan.y_step + plan.y_off
+            cz = tz * plan.z_step + plan.z_off + ks * plan.z_kstep
+            coords = (cx * 8, cy, cz, n, 0) if plan.merged_cw else (ks * plan.c_step, cx, cy, cz, n)
             slab = tma_box(xbits, plan, coords)
-            for i in range(plan.n_mma):
-                a_off = plan.tab[2 * (ks * plan.n_mma + i)]
-                b_off = plan.tab[2 * (ks * plan.n_mma + i) + 1]
+            for i in range(plan.n_grp * plan.nk):
+                grp, kk = divmod(i, plan.nk)
+                a_off = plan.tab[2 * (ks * plan.n_grp + grp)] + kk * plan.a_kstep
+                b_off = plan.tab[2 * (ks * plan.n_grp + grp) + 1] + kk * plan.b_kstep
                 B = umma_operand(img, b_off, nt, plan.b_layout, plan.b_lbo, plan.b_sbo).astype(np.float64)
                 for h in range(plan.tm):
                     A = umma_operand(slab, a_off + h * plan.half_a_off, 128, plan.a_layout, plan.a_lbo, plan.a_sbo)
