@@ -35,15 +35,18 @@
 namespace tsp {
 
 constexpr int SLAB_SMEM_BUDGET = 227 * 1024;
-constexpr int SLAB_TAIL_BYTES = 1024 /*bias*/ + 1024 /*outconv w,b*/ + 256 /*barriers*/;
+constexpr int SLAB_TAIL_BYTES = 2048 /*bias*/ + 1024 /*outconv w,b*/ + 512 /*barriers*/;
+constexpr int SLAB_MAX_BSTAGES = 8;
 constexpr int SLAB_MAX_STAGES = 6;
 
 struct SlabKParams {
   CUtensorMap tmA;
+  CUtensorMap tmB;           // streamed weights: standard packed [Cout_pad][K_pad], box {64, n_tile}
   const uint8_t* w_image;
   const float* bias;
   int tm, n_tile, k_stages, n_grp, nk, a_kstep, b_kstep, stages, tmem_cols;
   int slab_bytes, slab_stride, w_bytes, w_stride, zero_slabs;
+  int b_stream, b_stages, b_stride, cb_n, cin, num_n_tiles, tab_per_stage;
   int half_a_off;
   int c_step, x_step, x_off, y_step, y_off, z_step, z_off, z_kstep, merged_cw;
   int tiles_x, tiles_y, tiles_z, total_tiles;
@@ -85,10 +88,10 @@ __device__ __forceinline__ bool elect_one() {
 // while the current group's MMAs are issued.  TM and NK are compile-time so that the inner loop is straight
 // line code of ~3 uniform instructions per tcgen05.mma: at N = 64 the tensor pipe wants a new instruction
 // every ~48 clocks and a single warp retires a dependent uniform instruction only every ~7.
-template <int TM, int NK>
+template <int TM, int NK, bool STREAM>
 __device__ __forceinline__ void slab_issue(const SlabKParams& p, uint8_t* smS, uint32_t w_addr, uint32_t tmem_base,
                                            uint64_t* full, uint64_t* empty, uint64_t* tfull, uint64_t* tempty,
-                                           uint64_t* wbar) {
+                                           uint64_t* wbar, uint64_t* bfull, uint64_t* bempty) {
   const uint32_t idesc = umma_idesc_bf16(128, p.n_tile);
   const uint32_t a_hi = static_cast<uint32_t>(p.a_desc >> 32), a_lo0 = static_cast<uint32_t>(p.a_desc);
   const uint32_t b_hi = static_cast<uint32_t>(p.b_desc >> 32);
@@ -99,23 +102,33 @@ __device__ __forceinline__ void slab_issue(const SlabKParams& p, uint8_t* smS, u
   const uint32_t n_tile = static_cast<uint32_t>(p.n_tile);
   const uint32_t slab_step = static_cast<uint32_t>(p.slab_stride >> 4);
   const uint32_t a_lo_base = a_lo0 + (smem_u32(smS) >> 4);
-  mbar_wait(wbar, 0);
-  int s = 0, as = 0;
-  uint32_t ph = 0, aph = 0;
+  const uint32_t b_step = static_cast<uint32_t>(p.b_stride >> 4);
+  const int BS = p.b_stages, tab_ps = p.tab_per_stage;
+  if (!STREAM) mbar_wait(wbar, 0);
+  int s = 0, as = 0, bs = 0;
+  uint32_t ph = 0, aph = 0, bph = 0;
   for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
     mbar_wait(tempty + as, aph ^ 1);
     tc_fence_after();
     const uint32_t d0 = tmem_base + static_cast<uint32_t>(as * TM) * n_tile;
     const uint32_t d1 = d0 + n_tile;
     for (int ks = 0; ks < KS; ++ks) {
-      const uint2* tab = p.tab + ks * NG;
+      const uint2* tab = p.tab + (tab_ps ? ks * NG : 0);
       uint2 cur = tab[0];
       mbar_wait(full + s, ph);
       tc_fence_after();
       const uint32_t a_lo_s = a_lo_base + static_cast<uint32_t>(s) * slab_step;
       for (int g = 0; g < NG; ++g) {
         const uint2 nxt = tab[g + 1 < NG ? g + 1 : g];
-        const uint32_t a_lo = a_lo_s + cur.x, b_lo = b_lo0 + cur.y;
+        const uint32_t a_lo = a_lo_s + cur.x;
+        uint32_t b_lo;
+        if (STREAM) {  // this tap's weight block arrives through its own ring
+          mbar_wait(bfull + bs, bph);
+          tc_fence_after();
+          b_lo = b_lo0 + static_cast<uint32_t>(bs) * b_step;
+        } else {
+          b_lo = b_lo0 + cur.y;
+        }
         const uint32_t acc0 = (g | ks) != 0 ? 1u : 0u;
         if (elect_one()) {
 #pragma unroll
@@ -128,6 +141,11 @@ __device__ __forceinline__ void slab_issue(const SlabKParams& p, uint8_t* smS, u
               umma_bf16_nc(d1, ad1, bd, idesc, k == 0 ? acc0 : 1u);
             }
           }
+          if (STREAM) umma_commit(bempty + bs);
+        }
+        if (STREAM) {
+          __syncwarp();
+          if (++bs == BS) { bs = 0; bph ^= 1; }
         }
         cur = nxt;
       }
@@ -150,71 +168,69 @@ struct EpiCtx {
   __nv_bfloat16* y;
   __nv_bfloat16* pool;
   int Cout, act, y_ld, y_coff, p_ld, p_coff;
-  bool fuse_oc;
+  bool fuse_oc, wide_ok, pool_wide_ok;
 };
 
-__device__ __forceinline__ void slab_epi_chunk(const EpiCtx& c, const uint32_t (&v)[32], int c0, bool row_ok, int x0,
-                                               int ow_lim, long long pix, bool pool_writer, long long ppix,
-                                               float (&oc)[3]) {
-  float f[32];
+__device__ __forceinline__ void slab_epi_chunk(const EpiCtx& c, const uint32_t (&v)[32], int c0, bool valid,
+                                               long long pix, bool pool_writer, long long ppix, float (&oc)[3]) {
+  uint32_t q[16];
+  if (!c.fuse_oc) {
+    // fast path: 16 packed fp32x2 bias adds + 16 converts with the ReLU fused into the rounding instruction
+    const bool relu = c.act == TEDSPAD_ACT_RELU;
 #pragma unroll
-  for (int i = 0; i < 32; i += 4) {
-    const float4 b4 = *reinterpret_cast<const float4*>(c.bias + c0 + i);
-    f[i] = __uint_as_float(v[i]) + b4.x;
-    f[i + 1] = __uint_as_float(v[i + 1]) + b4.y;
-    f[i + 2] = __uint_as_float(v[i + 2]) + b4.z;
-    f[i + 3] = __uint_as_float(v[i + 3]) + b4.w;
-  }
-  if (c.act == TEDSPAD_ACT_RELU) {
+    for (int i = 0; i < 32; i += 4) {
+      const float4 b4 = *reinterpret_cast<const float4*>(c.bias + c0 + i);
+      float f0 = __uint_as_float(v[i]), f1 = __uint_as_float(v[i + 1]);
+      float f2 = __uint_as_float(v[i + 2]), f3 = __uint_as_float(v[i + 3]);
+      add_f32x2(f0, f1, b4.x, b4.y);
+      add_f32x2(f2, f3, b4.z, b4.w);
+      q[i >> 1] = cvt_bf16x2(f0, f1, relu);
+      q[(i >> 1) + 1] = cvt_bf16x2(f2, f3, relu);
+    }
+  } else {
+    // fused OutConv 1x1: the dot products consume the un-rounded fp32 activations
+    float f[32];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
-  }
-  if (c.fuse_oc && c0 < c.Cout) {
+    for (int i = 0; i < 32; i += 4) {
+      const float4 b4 = *reinterpret_cast<const float4*>(c.bias + c0 + i);
+      f[i] = __uint_as_float(v[i]) + b4.x;
+      f[i + 1] = __uint_as_float(v[i + 1]) + b4.y;
+      f[i + 2] = __uint_as_float(v[i + 2]) + b4.z;
+      f[i + 3] = __uint_as_float(v[i + 3]) + b4.w;
+    }
+    if (c.act == TEDSPAD_ACT_RELU) {
 #pragma unroll
-    for (int o = 0; o < 3; ++o) {
-      const float* wr = c.ocw + o * c.Cout + c0;
+      for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+    }
+    if (c0 < c.Cout) {
 #pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        const float4 w4 = *reinterpret_cast<const float4*>(wr + i);
-        oc[o] = fmaf(f[i], w4.x, oc[o]);
-        oc[o] = fmaf(f[i + 1], w4.y, oc[o]);
-        oc[o] = fmaf(f[i + 2], w4.z, oc[o]);
-        oc[o] = fmaf(f[i + 3], w4.w, oc[o]);
+      for (int o = 0; o < 3; ++o) {
+        const float* wr = c.ocw + o * c.Cout + c0;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const float4 w4 = *reinterpret_cast<const float4*>(wr + i);
+          oc[o] = fmaf(f[i], w4.x, oc[o]);
+          oc[o] = fmaf(f[i + 1], w4.y, oc[o]);
+          oc[o] = fmaf(f[i + 2], w4.z, oc[o]);
+          oc[o] = fmaf(f[i + 3], w4.w, oc[o]);
+        }
       }
     }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) q[i] = pack_bf162(f[2 * i], f[2 * i + 1]);
   }
-  uint32_t q[16];
+  if (c.y != nullptr && valid) {
+    // each lane owns 64 contiguous bytes of its pixel: two 32-byte stores (a warp store instruction touches 32
+    // cache lines whatever its width, so wider stores halve the L1 wavefronts per byte)
+    __nv_bfloat16* yp = c.y + pix * c.y_ld + c.y_coff + c0;
+    if (c.wide_ok && c0 + 32 <= c.Cout) {
+      st_global_256(yp, q);
+      st_global_256(yp + 16, q + 8);
+    } else {
 #pragma unroll
-  for (int i = 0; i < 16; ++i) q[i] = pack_bf162(f[2 * i], f[2 * i + 1]);
-  if (c.y != nullptr) {
-    // 4x4 transpose of 16-byte pieces inside each lane quad (two shuffle butterflies), so that one store
-    // instruction writes whole 64-byte runs (4 lanes = the 32 channels of ONE pixel, 8 pixels per instruction)
-    // instead of 32 lanes x 16 bytes in 32 different cache lines: 4x fewer L1 wavefronts per byte stored.
-    uint32_t t[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) t[i] = q[i];
-    const int qp = threadIdx.x & 3;
-    const bool odd = qp & 1, hi = qp & 2;
-#pragma unroll
-    for (int w = 0; w < 4; ++w) {  // stage 1 (lane ^ 1): even lanes trade pieces 1,3 for the partner's 0,2
-      const uint32_t x = odd ? t[0 + w] : t[4 + w], yv = odd ? t[8 + w] : t[12 + w];
-      const uint32_t xr = __shfl_xor_sync(0xffffffffu, x, 1), yr = __shfl_xor_sync(0xffffffffu, yv, 1);
-      if (odd) { t[0 + w] = xr; t[8 + w] = yr; } else { t[4 + w] = xr; t[12 + w] = yr; }
-    }
-#pragma unroll
-    for (int w = 0; w < 4; ++w) {  // stage 2 (lane ^ 2): lanes 0,1 trade pieces 2,3 for the partners' 0,1
-      const uint32_t x = hi ? t[0 + w] : t[8 + w], yv = hi ? t[4 + w] : t[12 + w];
-      const uint32_t xr = __shfl_xor_sync(0xffffffffu, x, 2), yr = __shfl_xor_sync(0xffffffffu, yv, 2);
-      if (hi) { t[0 + w] = xr; t[4 + w] = yr; } else { t[8 + w] = xr; t[12 + w] = yr; }
-    }
-    // piece i now holds channels [c0 + 8*qp, +8) of the pixel of quad lane i: x0 - qp + i, same image row
-    if (c0 + 8 * qp < c.Cout) {
-      __nv_bfloat16* yp = c.y + (pix - qp) * c.y_ld + c.y_coff + c0 + 8 * qp;
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        if (row_ok && x0 - qp + i < ow_lim)
-          *reinterpret_cast<uint4*>(yp + static_cast<long long>(i) * c.y_ld) =
-              make_uint4(t[4 * i], t[4 * i + 1], t[4 * i + 2], t[4 * i + 3]);
+      for (int j = 0; j < 4; ++j)
+        if (c0 + 8 * j < c.Cout)
+          *reinterpret_cast<uint4*>(yp + 8 * j) = make_uint4(q[4 * j], q[4 * j + 1], q[4 * j + 2], q[4 * j + 3]);
     }
   }
   if (c.pool != nullptr) {
@@ -226,10 +242,15 @@ __device__ __forceinline__ void slab_epi_chunk(const EpiCtx& c, const uint32_t (
     }
     if (pool_writer) {
       __nv_bfloat16* pp = c.pool + ppix * c.p_ld + c.p_coff + c0;
+      if (c.pool_wide_ok && c0 + 32 <= c.Cout) {
+        st_global_256(pp, q);
+        st_global_256(pp + 16, q + 8);
+      } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (c0 + 8 * j < c.Cout)
-          *reinterpret_cast<uint4*>(pp + 8 * j) = make_uint4(q[4 * j], q[4 * j + 1], q[4 * j + 2], q[4 * j + 3]);
+        for (int j = 0; j < 4; ++j)
+          if (c0 + 8 * j < c.Cout)
+            *reinterpret_cast<uint4*>(pp + 8 * j) = make_uint4(q[4 * j], q[4 * j + 1], q[4 * j + 2], q[4 * j + 3]);
+      }
     }
   }
 }
@@ -246,18 +267,23 @@ __global__ void __launch_bounds__(SLAB_THREADS, 1) conv_slab_kernel(const __grid
   uint8_t* smW = smem;
   uint8_t* smS = smem + p.w_stride;
   float* sm_bias = reinterpret_cast<float*>(smS + S * p.slab_stride);
-  float* sm_ocw = sm_bias + 256;        // [3][Cout] then [3] bias
+  float* sm_ocw = sm_bias + 512;        // [3][Cout] then [3] bias
   uint64_t* full = reinterpret_cast<uint64_t*>(sm_ocw + 256);
   uint64_t* empty = full + SLAB_MAX_STAGES;
   uint64_t* tfull = empty + SLAB_MAX_STAGES;
   uint64_t* tempty = tfull + 2;
   uint64_t* wbar = tempty + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
+  uint64_t* bfull = wbar + 1;
+  uint64_t* bempty = bfull + SLAB_MAX_BSTAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bempty + SLAB_MAX_BSTAGES);
 
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);  // provably warp-uniform
   const int lane = threadIdx.x & 31;
 
-  if (warp == 8 && lane == 0) tma_prefetch_desc(&p.tmA);
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&p.tmA);
+    if (p.b_stream) tma_prefetch_desc(&p.tmB);
+  }
   if (warp == 9 && lane == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(full + s, 1);
@@ -268,13 +294,17 @@ __global__ void __launch_bounds__(SLAB_THREADS, 1) conv_slab_kernel(const __grid
       mbar_init(tempty + a, 8);
     }
     mbar_init(wbar, 1);
+    for (int b = 0; b < p.b_stages; ++b) {
+      mbar_init(bfull + b, 1);
+      mbar_init(bempty + b, 1);
+    }
     fence_barrier_init();
   }
   if (warp == 10) {
     tmem_alloc(tmem_slot, p.tmem_cols);
     tmem_relinquish();
   }
-  for (int i = threadIdx.x; i < p.n_tile; i += blockDim.x) sm_bias[i] = p.bias[i];
+  for (int i = threadIdx.x; i < p.n_tile * p.num_n_tiles; i += blockDim.x) sm_bias[i] = p.bias[i];
   if (p.oc_w != nullptr) {
     for (int i = threadIdx.x; i < 3 * p.Cout; i += blockDim.x) sm_ocw[i] = p.oc_w[i];
     if (threadIdx.x < 3) sm_ocw[3 * p.Cout + threadIdx.x] = p.oc_b[threadIdx.x];
@@ -294,39 +324,55 @@ __global__ void __launch_bounds__(SLAB_THREADS, 1) conv_slab_kernel(const __grid
   if (warp == 8) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      mbar_arrive_expect_tx(wbar, static_cast<uint32_t>(p.w_bytes));
-      for (int off = 0; off < p.w_bytes; off += 16384)
-        bulk_copy_g2s(smW + off, p.w_image + off, static_cast<uint32_t>(min(16384, p.w_bytes - off)), wbar);
-      int s = 0;
-      uint32_t ph = 0;
+      if (!p.b_stream) {
+        mbar_arrive_expect_tx(wbar, static_cast<uint32_t>(p.w_bytes));
+        for (int off = 0; off < p.w_bytes; off += 16384)
+          bulk_copy_g2s(smW + off, p.w_image + off, static_cast<uint32_t>(min(16384, p.w_bytes - off)), wbar);
+      }
+      int s = 0, bs = 0;
+      uint32_t ph = 0, bph = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         int t = tile;
+        const int nt = t % p.num_n_tiles; t /= p.num_n_tiles;
         const int tx = t % p.tiles_x; t /= p.tiles_x;
         const int ty = t % p.tiles_y; t /= p.tiles_y;
         const int tz = t % p.tiles_z;
         const int n = t / p.tiles_z;
         const int cx = tx * p.x_step + p.x_off, cy = ty * p.y_step + p.y_off, cz = tz * p.z_step + p.z_off;
         for (int ks = 0; ks < p.k_stages; ++ks) {
+          const int kt = ks / p.cb_n, cb = ks - kt * p.cb_n;   // K stage = (temporal tap, 64-channel block)
           mbar_wait(empty + s, ph ^ 1);
           mbar_arrive_expect_tx(full + s, static_cast<uint32_t>(p.slab_bytes));
           if (p.merged_cw)  // stems: (pixel, channel) merged into one contiguous inner dimension of 8-element pixels
-            tma_load_5d(smS + s * p.slab_stride, &p.tmA, full + s, cx * 8, cy, cz + ks * p.z_kstep, n, 0);
+            tma_load_5d(smS + s * p.slab_stride, &p.tmA, full + s, cx * 8, cy, cz + kt * p.z_kstep, n, 0);
           else
-            tma_load_5d(smS + s * p.slab_stride, &p.tmA, full + s, ks * p.c_step, cx, cy, cz + ks * p.z_kstep, n);
+            tma_load_5d(smS + s * p.slab_stride, &p.tmA, full + s, cb * p.c_step, cx, cy, cz + kt * p.z_kstep, n);
           if (++s == S) { s = 0; ph ^= 1; }
+          if (p.b_stream) {
+            // one [n_tile x 64] weight block per filter tap, K ordered (kd,kh,kw,cin): tap kt*n_grp+g, block cb
+            for (int g = 0; g < p.n_grp; ++g) {
+              mbar_wait(bempty + bs, bph ^ 1);
+              mbar_arrive_expect_tx(bfull + bs, static_cast<uint32_t>(p.b_stride));
+              tma_load_2d(smW + bs * p.b_stride, &p.tmB, bfull + bs, (kt * p.n_grp + g) * p.cin + cb * 64, nt * p.n_tile);
+              if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
+            }
+          }
         }
       }
     }
   } else if (warp == 9) {
     // -------------------------------------------------------------- MMA issuer
     const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
-    if (p.tm == 2) {
-      if (p.nk == 4) slab_issue<2, 4>(p, smS, smem_u32(smW), tb, full, empty, tfull, tempty, wbar);
-      else slab_issue<2, 2>(p, smS, smem_u32(smW), tb, full, empty, tfull, tempty, wbar);
+    const uint32_t wa = smem_u32(smW);
+#define TSP_ISSUE(TM_, NK_, ST_) slab_issue<TM_, NK_, ST_>(p, smS, wa, tb, full, empty, tfull, tempty, wbar, bfull, bempty)
+    if (p.b_stream) {
+      if (p.tm == 2) TSP_ISSUE(2, 4, true); else TSP_ISSUE(1, 4, true);
+    } else if (p.tm == 2) {
+      if (p.nk == 4) TSP_ISSUE(2, 4, false); else TSP_ISSUE(2, 2, false);
     } else {
-      if (p.nk == 4) slab_issue<1, 4>(p, smS, smem_u32(smW), tb, full, empty, tfull, tempty, wbar);
-      else slab_issue<1, 2>(p, smS, smem_u32(smW), tb, full, empty, tfull, tempty, wbar);
+      if (p.nk == 4) TSP_ISSUE(1, 4, false); else TSP_ISSUE(1, 2, false);
     }
+#undef TSP_ISSUE
   } else if (warp < 8) {
     // ---------------------------------------------------------------- epilogue
     // Two warps per TMEM lane quarter.  tm == 2: warp group eg owns half eg of the tile (all its columns, so the
@@ -339,6 +385,9 @@ __global__ void __launch_bounds__(SLAB_THREADS, 1) conv_slab_kernel(const __grid
     EpiCtx c;
     c.bias = sm_bias; c.ocw = sm_ocw; c.y = p.y; c.pool = p.pool; c.Cout = p.Cout; c.act = p.act;
     c.y_ld = p.y_ld; c.y_coff = p.y_coff; c.p_ld = p.p_ld; c.p_coff = p.p_coff; c.fuse_oc = p.oc_w != nullptr;
+    // 32-byte stores need 32-byte aligned pixel chunks
+    c.wide_ok = ((p.y_ld | p.y_coff) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.y) & 31) == 0;
+    c.pool_wide_ok = ((p.p_ld | p.p_coff) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.pool) & 31) == 0;
     int h, c_first, c_step, nch;
     if (tm == 2) { h = eg; c_first = 0; c_step = 32; nch = nchunk_all; }
     else if (c.fuse_oc) { h = 0; c_first = 0; c_step = 32; nch = eg == 0 ? nchunk_all : 0; }
@@ -347,6 +396,7 @@ __global__ void __launch_bounds__(SLAB_THREADS, 1) conv_slab_kernel(const __grid
     uint32_t aph = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       int t = tile;
+      const int n0 = (t % p.num_n_tiles) * n_tile; t /= p.num_n_tiles;   // first output channel of this N tile
       const int tx = t % p.tiles_x; t /= p.tiles_x;
       const int ty = t % p.tiles_y; t /= p.tiles_y;
       const int tz = t % p.tiles_z;
@@ -369,11 +419,11 @@ __global__ void __launch_bounds__(SLAB_THREADS, 1) conv_slab_kernel(const __grid
       for (int i = 0; i < nch; i += 2) {
         tmem_ld_wait();
         if (i + 1 < nch) tmem_ld32(t_row + (i + 1) * c_step, vb);
-        slab_epi_chunk(c, va, c_first + i * c_step, oy < OH, ox, OW, pix, pool_writer, ppix, oc);
+        slab_epi_chunk(c, va, n0 + c_first + i * c_step, valid, pix, pool_writer, ppix, oc);
         if (i + 1 < nch) {
           tmem_ld_wait();
           if (i + 2 < nch) tmem_ld32(t_row + (i + 2) * c_step, va);
-          slab_epi_chunk(c, vb, c_first + (i + 1) * c_step, oy < OH, ox, OW, pix, pool_writer, ppix, oc);
+          slab_epi_chunk(c, vb, n0 + c_first + (i + 1) * c_step, valid, pix, pool_writer, ppix, oc);
         }
       }
       // all TMEM reads of this accumulator are complete (wait::ld above): hand it back to the MMA warp

@@ -49,52 +49,65 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return q;
 }
 
+constexpr long long ROWS_PER_BLOCK = 1;  // >1 was measured: no L1-reuse gain, less parallelism on small maps
+
 // ------------------------------------------------------------------ max pool
 struct PoolP {
   TView x, y;
   int kd, kh, kw, sd, sh, sw, pd, ph, pw, zero_pad;
-  long long total;  // N*OD*OH*OW*(C/8)
+  long long total;  // output rows N*OD*OH
 };
 
+// One block per output row (n, od, oh): the row decode is done once per block, the threads walk the
+// (ow, 8-channel group) items of the row with 32-bit arithmetic only (the previous one-item-per-thread
+// version spent most of its time in 64-bit div/mod).
 __global__ void __launch_bounds__(256) maxpool_kernel(const PoolP p) {
   const int c8n = p.y.C >> 3;
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < p.total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    long long t = idx;
-    const int c8 = static_cast<int>(t % c8n); t /= c8n;
-    const int ow = static_cast<int>(t % p.y.W); t /= p.y.W;
-    const int oh = static_cast<int>(t % p.y.H); t /= p.y.H;
-    const int od = static_cast<int>(t % p.y.D);
-    const int n = static_cast<int>(t / p.y.D);
-    float m[8];
+  const int items = p.y.W * c8n;
+  // ROWS_PER_BLOCK consecutive output rows per block: the window rows they share are re-read from L1, not L2
+  for (long long rowi = blockIdx.x; rowi * ROWS_PER_BLOCK < p.total; rowi += gridDim.x)
+  for (long long row = rowi * ROWS_PER_BLOCK; row < min(p.total, (rowi + 1) * ROWS_PER_BLOCK); ++row) {
+    int t = static_cast<int>(row);
+    const int oh = t % p.y.H; t /= p.y.H;
+    const int od = t % p.y.D;
+    const int n = t / p.y.D;
+    const int id0 = od * p.sd - p.pd, ih0 = oh * p.sh - p.ph;
+    const __nv_bfloat16* xn = reinterpret_cast<const __nv_bfloat16*>(p.x.ptr) + p.x.coff;
+    __nv_bfloat16* yrow = elem_ptr_w(p.y, pix_index(p.y, n, od, oh, 0), 0);
+    for (int it = threadIdx.x; it < items; it += blockDim.x) {
+      const int ow = it / c8n, c8 = it - ow * c8n;
+      const int iw0 = ow * p.sw - p.pw;
+      float m[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) m[i] = -INFINITY;
-    bool any_oob = false;
-    for (int a = 0; a < p.kd; ++a) {
-      const int id = od * p.sd - p.pd + a;
-      for (int b = 0; b < p.kh; ++b) {
-        const int ih = oh * p.sh - p.ph + b;
-        for (int c = 0; c < p.kw; ++c) {
-          const int iw = ow * p.sw - p.pw + c;
-          if (static_cast<unsigned>(id) < static_cast<unsigned>(p.x.D) &&
-              static_cast<unsigned>(ih) < static_cast<unsigned>(p.x.H) &&
-              static_cast<unsigned>(iw) < static_cast<unsigned>(p.x.W)) {
-            const uint4 q = __ldg(reinterpret_cast<const uint4*>(elem_ptr(p.x, pix_index(p.x, n, id, ih, iw), c8 * 8)));
-            float f[8];
-            unpack8(q, f);
+      for (int i = 0; i < 8; ++i) m[i] = -INFINITY;
+      bool any_oob = false;
+      for (int a = 0; a < p.kd; ++a) {
+        const int id = id0 + a;
+        const bool okd = static_cast<unsigned>(id) < static_cast<unsigned>(p.x.D);
+        for (int b = 0; b < p.kh; ++b) {
+          const int ih = ih0 + b;
+          const bool okh = okd && static_cast<unsigned>(ih) < static_cast<unsigned>(p.x.H);
+          const long long rowpix = okh ? pix_index(p.x, n, id, ih, 0) : 0;
+          for (int c = 0; c < p.kw; ++c) {
+            const int iw = iw0 + c;
+            if (okh && static_cast<unsigned>(iw) < static_cast<unsigned>(p.x.W)) {
+              const uint4 q = __ldg(reinterpret_cast<const uint4*>(xn + (rowpix + iw) * p.x.ld + c8 * 8));
+              float f[8];
+              unpack8(q, f);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], f[i]);
-          } else {
-            any_oob = true;
+              for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], f[i]);
+            } else {
+              any_oob = true;
+            }
           }
         }
       }
-    }
-    if (any_oob && p.zero_pad) {
+      if (any_oob && p.zero_pad) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], 0.f);
+        for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], 0.f);
+      }
+      *reinterpret_cast<uint4*>(yrow + static_cast<long long>(ow) * p.y.ld + c8 * 8) = pack8(m);
     }
-    *reinterpret_cast<uint4*>(elem_ptr_w(p.y, pix_index(p.y, n, od, oh, ow), c8 * 8)) = pack8(m);
   }
 }
 
@@ -103,37 +116,48 @@ struct UpP {
   TView x, y;
   int UH, UW, offy, offx;  // up-sampled size and F.pad offsets inside y
   float sy, sx;
-  long long total;  // N*H*W*(C/8) over y's interior
+  long long total;  // output rows N*H of y's interior
 };
 
+// One block per output row (n, oh): vertical taps / weights once per block, threads walk (ow, 8-channel group).
 __global__ void __launch_bounds__(256) upsample2x_kernel(const UpP p) {
   const int c8n = p.y.C >> 3;
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < p.total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    long long t = idx;
-    const int c8 = static_cast<int>(t % c8n); t /= c8n;
-    const int ow = static_cast<int>(t % p.y.W); t /= p.y.W;
-    const int oh = static_cast<int>(t % p.y.H);
-    const int n = static_cast<int>(t / p.y.H);
-    float o[8];
+  const int items = p.y.W * c8n;
+  // ROWS_PER_BLOCK consecutive output rows per block: they interpolate between the same 2-3 input rows (L1 hits)
+  for (long long rowi = blockIdx.x; rowi * ROWS_PER_BLOCK < p.total; rowi += gridDim.x)
+  for (long long row = rowi * ROWS_PER_BLOCK; row < min(p.total, (rowi + 1) * ROWS_PER_BLOCK); ++row) {
+    const int n = static_cast<int>(row / p.y.H);
+    const int oh = static_cast<int>(row - static_cast<long long>(n) * p.y.H);
+    const int uy = oh - p.offy;
+    const bool row_in = uy >= 0 && uy < p.UH;
+    const float fy = p.sy * uy;
+    const int y0 = row_in ? static_cast<int>(fy) : 0;
+    const int y1 = y0 + (y0 < p.x.H - 1 ? 1 : 0);
+    const float ly1 = fy - y0, ly0 = 1.f - ly1;
+    const __nv_bfloat16* r0 = elem_ptr(p.x, pix_index(p.x, n, 0, y0, 0), 0);
+    const __nv_bfloat16* r1 = elem_ptr(p.x, pix_index(p.x, n, 0, y1, 0), 0);
+    __nv_bfloat16* yrow = elem_ptr_w(p.y, pix_index(p.y, n, 0, oh, 0), 0);
+    for (int it = threadIdx.x; it < items; it += blockDim.x) {
+      const int ow = it / c8n, c8 = it - ow * c8n;
+      float o[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = 0.f;
-    const int uy = oh - p.offy, ux = ow - p.offx;
-    if (uy >= 0 && uy < p.UH && ux >= 0 && ux < p.UW) {
-      const float fy = p.sy * uy, fx = p.sx * ux;
-      const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
-      const int y1 = y0 + (y0 < p.x.H - 1 ? 1 : 0), x1 = x0 + (x0 < p.x.W - 1 ? 1 : 0);
-      const float ly1 = fy - y0, lx1 = fx - x0;
-      const float ly0 = 1.f - ly1, lx0 = 1.f - lx1;
-      float a[8], b[8], c[8], d[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(elem_ptr(p.x, pix_index(p.x, n, 0, y0, x0), c8 * 8))), a);
-      unpack8(__ldg(reinterpret_cast<const uint4*>(elem_ptr(p.x, pix_index(p.x, n, 0, y0, x1), c8 * 8))), b);
-      unpack8(__ldg(reinterpret_cast<const uint4*>(elem_ptr(p.x, pix_index(p.x, n, 0, y1, x0), c8 * 8))), c);
-      unpack8(__ldg(reinterpret_cast<const uint4*>(elem_ptr(p.x, pix_index(p.x, n, 0, y1, x1), c8 * 8))), d);
+      for (int i = 0; i < 8; ++i) o[i] = 0.f;
+      const int ux = ow - p.offx;
+      if (row_in && ux >= 0 && ux < p.UW) {
+        const float fx = p.sx * ux;
+        const int x0 = static_cast<int>(fx);
+        const int x1 = x0 + (x0 < p.x.W - 1 ? 1 : 0);
+        const float lx1 = fx - x0, lx0 = 1.f - lx1;
+        float a[8], b[8], c[8], d[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(r0 + static_cast<long long>(x0) * p.x.ld + c8 * 8)), a);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(r0 + static_cast<long long>(x1) * p.x.ld + c8 * 8)), b);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(r1 + static_cast<long long>(x0) * p.x.ld + c8 * 8)), c);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(r1 + static_cast<long long>(x1) * p.x.ld + c8 * 8)), d);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = ly0 * (lx0 * a[i] + lx1 * b[i]) + ly1 * (lx0 * c[i] + lx1 * d[i]);
+        for (int i = 0; i < 8; ++i) o[i] = ly0 * (lx0 * a[i] + lx1 * b[i]) + ly1 * (lx0 * c[i] + lx1 * d[i]);
+      }
+      *reinterpret_cast<uint4*>(yrow + static_cast<long long>(ow) * p.y.ld + c8 * 8) = pack8(o);
     }
-    *reinterpret_cast<uint4*>(elem_ptr_w(p.y, pix_index(p.y, n, 0, oh, ow), c8 * 8)) = pack8(o);
   }
 }
 
@@ -473,6 +497,16 @@ static int grid_for(long long total, int threads) {
   return static_cast<int>(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
 }
 
+// grid for the row-per-block kernels: every row when rows are long enough to fill a block, else fewer
+// blocks that loop over rows (so that tiny rows do not launch mostly idle blocks)
+static int rows_grid(long long rows, int items_per_row) {
+  const long long cap = static_cast<long long>(num_sms()) * 64;
+  long long blocks = (rows + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK;
+  if (items_per_row < 128) blocks = (rows * items_per_row + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks > cap ? cap : (blocks > rows ? rows : blocks));
+}
+
 }  // namespace tsp
 
 using namespace tsp;
@@ -490,8 +524,9 @@ extern "C" int tedspad_maxpool(const tedspad_tensor* x, const tedspad_tensor* y,
   p.x = make_view(*x); p.y = make_view(*y);
   p.kd = kd; p.kh = kh; p.kw = kw; p.sd = sd; p.sh = sh; p.sw = sw; p.pd = pd; p.ph = ph; p.pw = pw;
   p.zero_pad = zero_pad;
-  p.total = static_cast<long long>(y->N) * y->D * y->H * y->W * (y->C / 8);
-  maxpool_kernel<<<grid_for(p.total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  p.total = static_cast<long long>(y->N) * y->D * y->H;   // output rows
+  TSP_CHECK(p.total < (1LL << 31), "maxpool: too many rows");
+  maxpool_kernel<<<rows_grid(p.total, y->W * (y->C / 8)), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   TSP_CUDA(cudaGetLastError());
   return 0;
 }
@@ -507,8 +542,8 @@ extern "C" int tedspad_upsample2x(const tedspad_tensor* x, const tedspad_tensor*
   p.offy = (y->H - p.UH) / 2; p.offx = (y->W - p.UW) / 2;  // F.pad(diff//2, diff - diff//2)
   p.sy = p.UH > 1 ? static_cast<float>(x->H - 1) / static_cast<float>(p.UH - 1) : 0.f;
   p.sx = p.UW > 1 ? static_cast<float>(x->W - 1) / static_cast<float>(p.UW - 1) : 0.f;
-  p.total = static_cast<long long>(y->N) * y->H * y->W * (y->C / 8);
-  upsample2x_kernel<<<grid_for(p.total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  p.total = static_cast<long long>(y->N) * y->H;   // output rows
+  upsample2x_kernel<<<rows_grid(p.total, y->W * (y->C / 8)), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   TSP_CUDA(cudaGetLastError());
   return 0;
 }

@@ -181,6 +181,31 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t
   return d;
 }
 
+// ------------------------------------------------------------- epilogue math / stores (sm_100)
+// (a0, a1) += (b0, b1) as one packed fp32x2 add (FADD2)
+__device__ __forceinline__ void add_f32x2(float& a0, float& a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 x, y;\n\t"
+      "mov.b64 x, {%0, %1};\n\t"
+      "mov.b64 y, {%2, %3};\n\t"
+      "add.rn.f32x2 x, x, y;\n\t"
+      "mov.b64 {%0, %1}, x;\n\t}"
+      : "+f"(a0), "+f"(a1)
+      : "f"(b0), "f"(b1));
+}
+// two fp32 -> packed bf16x2 (lo in the low half), round to nearest even, optional fused ReLU (one F2FP)
+__device__ __forceinline__ uint32_t cvt_bf16x2(float lo, float hi, bool relu) {
+  uint32_t d;
+  if (relu) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+// 32-byte store (address 32-byte aligned): half as many store instructions / L1 wavefronts per byte as v4
+__device__ __forceinline__ void st_global_256(void* p, const uint32_t* q) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"l"(p), "r"(q[0]), "r"(q[1]), "r"(q[2]), "r"(q[3]), "r"(q[4]), "r"(q[5]), "r"(q[6]), "r"(q[7])
+               : "memory");
+}
+
 // Generic UMMA shared-memory descriptor WITHOUT the start address (add (addr >> 4) & 0x3FFF):
 // layout 0 = no swizzle (LBO = byte step between K-adjacent 8x16-byte core matrices, SBO = between
 // M/N-adjacent ones), layout 2 = SWIZZLE_128B (LBO unused, SBO = byte step between 8-row groups).
