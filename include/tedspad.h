@@ -87,8 +87,8 @@ int tedspad_conv_forward(const tedspad_conv* p, void* stream);
  * memory for the whole persistent CTA).  An output tile is 16 rows x (8*tm) columns of one image.
  *   TEDSPAD_SLAB_3X3     Conv2d 3x3 stride 1 pad 1, Cin % 64 == 0, Cout in {16..256} with
  *                        9*Cin*Cout*2 bytes <= ~150 KB: the 64/128-channel DoubleConv layers of the
- *                        anonymizer at 224^2 / 112^2 (aux_code/models/unet_parts.py:15-22).  x must
- *                        carry a zero halo >= 1 in H and W.  128-byte swizzled slab rows (one pixel
+ *                        anonymizer at 224^2 / 112^2 (aux_code/models/unet_parts.py:15-22).  Taps outside
+ *                        the tensor are zero-filled by TMA.  128-byte swizzled slab rows (one pixel
  *                        x 64 channels); tap (ky,kx) = descriptor start + (ky*slab_w + kx) rows.
  *   TEDSPAD_SLAB_STEM2D  Conv2d 3x3 stride 1 pad 1 over a Cin<=8 image stored with 8 channels per
  *                        pixel (16 bytes): the anonymizer's first convolution (unet_parts.py:15).
@@ -99,13 +99,21 @@ int tedspad_conv_forward(const tedspad_conv* p, void* stream);
  *                        I3Res50.conv1 (large_i3d.py:135), torchvision BasicStem (video/resnet.py:
  *                        173-181).  Same overlapped descriptors; one UMMA row step (16 B) = the
  *                        stride of 2 pixels, one K chunk = 2 pixels x 4 channels.
+ *   TEDSPAD_SLAB_3X3_STREAM  Conv2d 3x3 / Conv3d 3x3x3 (or (1,3,3)), stride 1, same padding, Cin % 64
+ *                        == 0, any Cout_pad <= 512 (multiple of 32): same slab for the activations, but
+ *                        the weights are too large to stay resident and stream through their own ring
+ *                        of [n_tile x 64] blocks, one per filter tap (2-D TMA on the STANDARD packed
+ *                        layout: pass it as `w_image`, with K_pad).  A K stage = (temporal tap, 64-channel
+ *                        block).  The 128-channel DoubleConv layers (unet_parts.py:15-22), Conv3d_2c_3x3
+ *                        and the Inception 3x3x3 branches (aux_code/models/i3d.py:244,132-136).  Taps
+ *                        outside the tensor are zero-filled by TMA: no halo required.
  * Optional fused epilogues (TEDSPAD_SLAB_3X3 only): MaxPool2d(2) of the output written to `pool`
  * (unet_parts.py:33), and OutConv 1x1 (Cout->3) + sigmoid written as planar [N][3][H][W] images
  * (unet_parts.py:71-77, unet_model.py:36-37) in which case y.ptr may be NULL.
  * `w_image` holds the weights in the exact shared-memory image the kernel reads; build it with
  * tedspad_conv_slab_pack() from the standard packed layout of tedspad_conv.
  */
-enum { TEDSPAD_SLAB_3X3 = 0, TEDSPAD_SLAB_STEM2D = 1, TEDSPAD_SLAB_STEM3D = 2 };
+enum { TEDSPAD_SLAB_3X3 = 0, TEDSPAD_SLAB_STEM2D = 1, TEDSPAD_SLAB_STEM3D = 2, TEDSPAD_SLAB_3X3_STREAM = 3 };
 
 typedef struct tedspad_conv_slab {
   tedspad_tensor x;         /* bf16 input view (see kinds above) */
@@ -125,6 +133,8 @@ typedef struct tedspad_conv_slab {
   int32_t act;              /* TEDSPAD_ACT_* */
   int32_t tm;               /* 8-column groups per tile: 1 or 2; 0 = auto */
   int32_t max_ctas;         /* persistent grid cap; 0 = number of SMs */
+  int32_t n_tile;           /* STREAM kind: UMMA N per tile (multiple of 32 dividing Cout_pad); 0 = auto */
+  int32_t K_pad;            /* STREAM kind: row length of the standard packed weights */
 } tedspad_conv_slab;
 
 /* Everything the kernel derives from a tedspad_conv_slab: exposed so that the CPU test-suite can
@@ -144,6 +154,7 @@ typedef struct tedspad_slab_plan {
   int32_t half_a_off;       /* A byte offset of the second 8-column group */
   int32_t c_step, x_step, x_off, y_step, y_off, z_step, z_off, z_kstep;  /* slab origin per tile / K stage */
   int32_t tiles_x, tiles_y, tiles_z, total_tiles;
+  int32_t b_stream, b_stages, b_stride, cb_n, cin, num_n_tiles, tab_per_stage, reserved0;
   uint32_t tab[2 * TEDSPAD_SLAB_MAX_MMA];   /* per (k_stage, group): {A byte offset in slab, B byte offset in image} */
 } tedspad_slab_plan;
 

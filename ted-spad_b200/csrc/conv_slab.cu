@@ -515,12 +515,22 @@ static int make_plan(const tedspad_conv_slab& c, tedspad_slab_plan& P) {
   memset(&P, 0, sizeof(P));
   const tedspad_tensor& x = c.x;
   const tedspad_tensor& y = c.y;
-  TSP_CHECK(c.Cout_pad % 16 == 0 && c.Cout_pad >= 16 && c.Cout_pad <= 256 && c.Cout <= c.Cout_pad && c.Cout >= 1,
-            "slab: Cout=%d Cout_pad=%d invalid (single N tile <= 256)", c.Cout, c.Cout_pad);
-  TSP_CHECK(c.Cout % 8 == 0 && c.Cout_pad % 32 == 0, "slab: Cout=%d must be a multiple of 8 and Cout_pad=%d of 32", c.Cout,
-            c.Cout_pad);
+  const bool stream = c.kind == TEDSPAD_SLAB_3X3_STREAM;
+  TSP_CHECK(c.Cout_pad % 32 == 0 && c.Cout_pad >= 32 && c.Cout_pad <= (stream ? 512 : 256) && c.Cout <= c.Cout_pad &&
+                c.Cout >= 1 && c.Cout % 8 == 0,
+            "slab: Cout=%d (multiple of 8) / Cout_pad=%d (multiple of 32, <= %d) invalid", c.Cout, c.Cout_pad,
+            stream ? 512 : 256);
   TSP_CHECK(x.N == y.N && x.N >= 1, "slab: batch mismatch");
   P.n_tile = c.Cout_pad;
+  P.num_n_tiles = 1;
+  P.cb_n = 1;
+  P.tab_per_stage = 1;
+  if (stream) {
+    P.n_tile = c.n_tile > 0 ? c.n_tile : c.Cout_pad / ((c.Cout_pad + 255) / 256);
+    TSP_CHECK(P.n_tile % 32 == 0 && P.n_tile <= 256 && c.Cout_pad % P.n_tile == 0, "slab stream: n_tile=%d does not tile Cout_pad=%d",
+              P.n_tile, c.Cout_pad);
+    P.num_n_tiles = c.Cout_pad / P.n_tile;
+  }
   const int Wp = x.W + 2 * x.pw, Hp = x.H + 2 * x.ph, Dp = x.D + 2 * x.pd;
   int slab_w = 0, slab_h = 0, pad_bytes = 0;
   if (c.kind == TEDSPAD_SLAB_3X3 || c.kind == TEDSPAD_SLAB_STEM2D) {
@@ -531,13 +541,14 @@ static int make_plan(const tedspad_conv_slab& c, tedspad_slab_plan& P) {
     const bool sw = c.kind == TEDSPAD_SLAB_3X3;
     if (sw) {
       TSP_CHECK(x.C % 64 == 0 && x.C >= 64, "slab 3x3: x.C=%d must be a multiple of 64", x.C);
-      TSP_CHECK(x.ph >= 1 && x.pw >= 1, "slab 3x3: input needs a zero halo >= 1 in H and W");
+      // no halo needed: taps outside the tensor are zero-filled by TMA (a zero halo works just as well)
     } else {
       TSP_CHECK(x.C == 8, "slab stem2d: x.C=%d must be 8 (channels padded to one 16-byte pixel)", x.C);
     }
     P.w_bytes = static_cast<int>(slab_image_bytes(c.kind, P.n_tile, x.C, 1, 3, 3));
     P.swizzle128 = sw ? 1 : 0;
     P.k_stages = sw ? x.C / 64 : 1;
+    P.cb_n = P.k_stages;
     P.n_grp = sw ? 9 : 3;     // filter taps (3x3) / filter rows (stem)
     P.nk = sw ? 4 : 2;        // K=16 steps per group
     P.n_mma = P.n_grp * P.nk;
@@ -605,6 +616,51 @@ static int make_plan(const tedspad_conv_slab& c, tedspad_slab_plan& P) {
         P.tab[2 * ky + 1] = static_cast<uint32_t>(ky * 2 * P.b_kstep);
       }
     }
+  } else if (c.kind == TEDSPAD_SLAB_3X3_STREAM) {
+    TSP_CHECK((c.kd == 1 || c.kd == 3) && c.kh == 3 && c.kw == 3 && c.sd == 1 && c.sh == 1 && c.sw == 1 &&
+                  c.pd == c.kd / 2 && c.ph == 1 && c.pw == 1,
+              "slab stream: needs a (1|3,3,3) stride-1 same-padded convolution");
+    TSP_CHECK(x.D == y.D && x.H == y.H && x.W == y.W, "slab: output extents must equal input extents");
+    TSP_CHECK(x.C % 64 == 0 && x.C >= 64, "slab stream: x.C=%d must be a multiple of 64", x.C);
+    TSP_CHECK(c.K_pad == c.kd * 9 * x.C, "slab stream: K_pad=%d != %d taps x %d channels", c.K_pad, c.kd * 9, x.C);
+    TSP_CHECK(c.oc_w == nullptr, "slab stream: fused OutConv needs the resident-weight kind");
+    P.swizzle128 = 1;
+    P.cb_n = x.C / 64;
+    P.cin = x.C;
+    P.k_stages = c.kd * P.cb_n;
+    P.n_grp = 9; P.nk = 4; P.n_mma = 36;
+    P.tab_per_stage = 0;      // the 9 tap offsets are the same for every K stage
+    P.b_stream = 1;
+    P.b_stride = P.n_tile * 128;
+    int tm = c.tm;
+    if (tm == 0) tm = (x.W > 8 && 4 * P.n_tile <= 512) ? 2 : 1;
+    TSP_CHECK((tm == 1 || tm == 2) && 2 * tm * P.n_tile <= 512, "slab stream: tm=%d with n_tile=%d exceeds TMEM", tm, P.n_tile);
+    P.tm = tm;
+    slab_w = 8 * tm + 2;
+    slab_h = 18;
+    P.box[0] = 64; P.box[1] = slab_w; P.box[2] = slab_h; P.box[3] = 1; P.box[4] = 1;
+    P.tdim[0] = x.C; P.tdim[1] = Wp; P.tdim[2] = Hp; P.tdim[3] = Dp; P.tdim[4] = x.N;
+    P.tstride[0] = static_cast<int64_t>(x.ld) * 2;
+    P.tstride[1] = P.tstride[0] * Wp;
+    P.tstride[2] = P.tstride[1] * Hp;
+    P.tstride[3] = P.tstride[2] * Dp;
+    P.tbase_off = static_cast<int64_t>(x.coff) * 2;
+    // no halo needed: taps outside the tensor are zero-filled by TMA (a zero halo works just as well)
+    P.c_step = 64;
+    P.x_step = 8 * tm; P.x_off = x.pw - 1;
+    P.y_step = 16; P.y_off = x.ph - 1;
+    P.z_step = 1; P.z_off = x.pd - c.kd / 2; P.z_kstep = 1;
+    P.tiles_x = (x.W + 8 * tm - 1) / (8 * tm);
+    P.tiles_y = (x.H + 15) / 16;
+    P.tiles_z = x.D;
+    P.half_a_off = 8 * 128;
+    P.a_layout = 2; P.a_lbo = 16; P.a_sbo = slab_w * 128;
+    P.b_layout = 2; P.b_lbo = 16; P.b_sbo = 1024;
+    P.a_kstep = 32; P.b_kstep = 32;
+    for (int tap = 0; tap < 9; ++tap) {
+      P.tab[2 * tap] = static_cast<uint32_t>(((tap / 3) * slab_w + (tap % 3)) * 128);
+      P.tab[2 * tap + 1] = 0;
+    }
   } else if (c.kind == TEDSPAD_SLAB_STEM3D) {
     TSP_CHECK(c.kh == 7 && c.kw == 7 && c.sh == 2 && c.sw == 2 && c.kd >= 1 && c.kd <= 7 && c.sd >= 1,
               "slab stem3d: needs a (kd,7,7) stride (sd,2,2) convolution");
@@ -660,17 +716,26 @@ static int make_plan(const tedspad_conv_slab& c, tedspad_slab_plan& P) {
   }
   P.slab_bytes = 2 * P.box[0] * P.box[1] * P.box[2] * P.box[3] * P.box[4];
   P.slab_stride = static_cast<int>(round_up(P.slab_bytes + pad_bytes, 1024));
-  const int w_stride = static_cast<int>(round_up(P.w_bytes, 1024));
-  const int avail = SLAB_SMEM_BUDGET - 1024 - SLAB_TAIL_BYTES - w_stride;
-  P.stages = std::min(SLAB_MAX_STAGES, avail / P.slab_stride);
-  TSP_CHECK(P.stages >= 2, "slab: weights (%d B) + two slab stages (%d B each) do not fit in shared memory", P.w_bytes,
-            P.slab_stride);
+  int w_stride = static_cast<int>(round_up(P.w_bytes, 1024));
+  if (P.b_stream) {
+    // two (tm=2) or three slab stages; the rest of shared memory is the weight-block ring
+    P.stages = P.tm == 2 ? 2 : 3;
+    const int avail_b = SLAB_SMEM_BUDGET - 1024 - SLAB_TAIL_BYTES - P.stages * P.slab_stride;
+    P.b_stages = std::min(SLAB_MAX_BSTAGES, avail_b / P.b_stride);
+    TSP_CHECK(P.b_stages >= 3, "slab stream: only %d weight-block stages fit", P.b_stages);
+    w_stride = P.b_stages * P.b_stride;
+  } else {
+    const int avail = SLAB_SMEM_BUDGET - 1024 - SLAB_TAIL_BYTES - w_stride;
+    P.stages = std::min(SLAB_MAX_STAGES, avail / P.slab_stride);
+    TSP_CHECK(P.stages >= 2, "slab: weights (%d B) + two slab stages (%d B each) do not fit in shared memory", P.w_bytes,
+              P.slab_stride);
+  }
   P.smem_bytes = 1024 + w_stride + P.stages * P.slab_stride + SLAB_TAIL_BYTES;
   int tc = 32;
   while (tc < 2 * P.tm * P.n_tile) tc <<= 1;
   TSP_CHECK(tc <= 512, "slab: %d TMEM columns needed", tc);
   P.tmem_cols = tc;
-  const int64_t total = static_cast<int64_t>(x.N) * P.tiles_z * P.tiles_y * P.tiles_x;
+  const int64_t total = static_cast<int64_t>(x.N) * P.tiles_z * P.tiles_y * P.tiles_x * P.num_n_tiles;
   TSP_CHECK(total > 0 && total < (int64_t(1) << 31), "slab: tile count out of range");
   P.total_tiles = static_cast<int>(total);
   return 0;
@@ -740,11 +805,19 @@ extern "C" int tedspad_conv_slab_forward(const tedspad_conv_slab* c, void* strea
   if (encode_tmap_5d_bf16(&p.tmA, base, dims, strides, box, P.swizzle128 != 0)) return 3;
   p.w_image = reinterpret_cast<const uint8_t*>(c->w_image);
   p.bias = c->bias;
+  p.b_stream = P.b_stream; p.b_stages = P.b_stages; p.b_stride = P.b_stride; p.cb_n = P.cb_n; p.cin = P.cin;
+  p.num_n_tiles = P.num_n_tiles; p.tab_per_stage = P.tab_per_stage;
+  if (P.b_stream) {
+    // w_image holds the STANDARD packed weights [Cout_pad][K_pad] for the streaming kind
+    if (encode_tmap_2d_bf16(&p.tmB, c->w_image, (uint64_t)c->K_pad, (uint64_t)c->Cout_pad, (uint64_t)c->K_pad * 2, 64,
+                            (uint32_t)P.n_tile))
+      return 3;
+  }
   p.tm = P.tm; p.n_tile = P.n_tile; p.k_stages = P.k_stages; p.n_grp = P.n_grp; p.nk = P.nk; p.stages = P.stages;
   p.a_kstep = P.a_kstep; p.b_kstep = P.b_kstep;
   p.tmem_cols = P.tmem_cols;
   p.slab_bytes = P.slab_bytes; p.slab_stride = P.slab_stride; p.w_bytes = P.w_bytes;
-  p.w_stride = (int)round_up(P.w_bytes, 1024);
+  p.w_stride = P.b_stream ? P.b_stages * P.b_stride : (int)round_up(P.w_bytes, 1024);
   p.zero_slabs = P.swizzle128 ? 0 : 1;
   p.half_a_off = P.half_a_off;
   p.c_step = P.c_step; p.x_step = P.x_step; p.x_off = P.x_off; p.y_step = P.y_step; p.y_off = P.y_off;
@@ -752,7 +825,8 @@ extern "C" int tedspad_conv_slab_forward(const tedspad_conv_slab* c, void* strea
   p.tiles_x = P.tiles_x; p.tiles_y = P.tiles_y; p.tiles_z = P.tiles_z; p.total_tiles = P.total_tiles;
   p.a_desc = umma_desc_template(P.a_layout, P.a_lbo, P.a_sbo);
   p.b_desc = umma_desc_template(P.b_layout, P.b_lbo, P.b_sbo);
-  for (int i = 0; i < P.k_stages * P.n_grp; ++i) p.tab[i] = make_uint2(P.tab[2 * i] >> 4, P.tab[2 * i + 1] >> 4);  // 16-byte units
+  const int n_tab = P.tab_per_stage ? P.k_stages * P.n_grp : P.n_grp;
+  for (int i = 0; i < n_tab; ++i) p.tab[i] = make_uint2(P.tab[2 * i] >> 4, P.tab[2 * i + 1] >> 4);  // 16-byte units
 
   p.y = reinterpret_cast<__nv_bfloat16*>(y.ptr);
   p.OH = y.H; p.OW = y.W;

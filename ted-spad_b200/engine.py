@@ -22,14 +22,28 @@ SLAB_WEIGHT_LIMIT = 150 * 1024   # bytes of resident weights that still leave ro
 ENC_IN_CHANNELS = 4 if USE_SLAB_STEM3D else 8   # channel padding of the encoder input clip
 
 
-def slab3x3(pc):
-    """PackedSlabConv for a (1,3,3) stride-1 pad-1 convolution whose weights can stay resident in shared
-    memory (the 64/128-channel DoubleConv layers), else None."""
-    if not USE_SLAB or pc.k != (1, 3, 3) or pc.stride != (1, 1, 1) or pc.pad_front != (0, 1, 1):
+def slab3x3(pc, max_stream_cout=512):
+    """Best SLAB variant for a stride-1 same-padded (1|3,3,3) convolution with Cin % 64 == 0, or None:
+    resident weights when they fit in shared memory (the 64-channel DoubleConv layers), streamed weight blocks
+    otherwise (128-channel DoubleConv layers, Conv3d_2c_3x3, Inception 3x3x3 branches, ResNet (1,3,3)/3x3x3)."""
+    kd = pc.k[0]
+    if not USE_SLAB or kd not in (1, 3) or pc.k[1:] != (3, 3) or pc.stride != (1, 1, 1) or pc.pad_front != (kd // 2, 1, 1):
         return None
-    if pc.cin_pad % 64 or pc.cout_pad > 256 or pc.cout % 8 or 9 * pc.cin_pad * pc.cout_pad * 2 > SLAB_WEIGHT_LIMIT:
+    if pc.cin_pad % 64 or pc.cout % 8 or pc.cout_pad % 32 or pc.k_pad != kd * 9 * pc.cin_pad:
         return None
-    return ops.PackedSlabConv(pc, L.SLAB_3X3)
+    if kd == 1 and pc.cout_pad <= 256 and 9 * pc.cin_pad * pc.cout_pad * 2 <= SLAB_WEIGHT_LIMIT:
+        return ops.PackedSlabConv(pc, L.SLAB_3X3)
+    if pc.cout_pad <= max_stream_cout and pc.n_tile % 32 == 0:
+        return ops.PackedSlabConv(pc, L.SLAB_3X3_STREAM)
+    return None
+
+
+def conv_auto(x, pc, y, res=None, act=L.ACT_RELU):
+    """Convolution through the SLAB feed when the layer has one (pc.slab) and needs no residual, else FLAT/GATHER."""
+    ps = getattr(pc, "slab", None)
+    if ps is not None and res is None and act in (L.ACT_RELU, L.ACT_NONE):
+        return ops.conv_slab_forward(x, ps, y, act=act)
+    return ops.conv_forward(x, pc, y, res=res, act=act)
 
 
 def stem3d(pc):
@@ -65,13 +79,14 @@ class _Buffers:
         self.device = device
         self.pool = {}
 
-    def get(self, name, N, D, H, W, C, halo=(0, 0, 0), dtype=ops.BF16):
+    def get(self, name, N, D, H, W, C, halo=(0, 0, 0), dtype=ops.BF16, zero=False):
+        """zero=True: cleared once at allocation (channel-padded buffers whose pad channels are never written)."""
         key = (name, N, D, H, W, C, tuple(halo), dtype)
         t = self.pool.get(key)
         if t is None:
             t = CLTensor(N, D, H, W, C, halo, device=self.device, dtype=dtype)
-            if sum(halo) == 0 and C % 8 == 0:
-                pass  # fully overwritten by its producer
+            if zero:
+                t.buf.zero_()
             self.pool[key] = t
         return t
 
@@ -111,8 +126,9 @@ class UNetExecutor:
             b = PackedConv(sd[f"{prefix}.3.weight"], sd[f"{prefix}.3.bias"], _bn(sd, f"{prefix}.4", 1e-5),
                            pad_front=(0, 1, 1), device=device)
             self.convs[prefix] = (a, b)
-            sa = ops.PackedSlabConv(a, L.SLAB_STEM2D) if (USE_SLAB and cin_pad0 == 8) else slab3x3(a)
-            self.slabs[prefix] = (sa, slab3x3(b))
+            # 256/512-channel layers run the tensor pipe at ~80 % through the FLAT feed already: SLAB up to 128 outputs
+            sa = ops.PackedSlabConv(a, L.SLAB_STEM2D) if (USE_SLAB and cin_pad0 == 8) else slab3x3(a, 128)
+            self.slabs[prefix] = (sa, slab3x3(b, 128))
 
         dc("inc.double_conv", 8)
         for i in range(1, 5):
@@ -131,7 +147,11 @@ class UNetExecutor:
         """DoubleConv half: conv+BN+ReLU (unet_parts.py:15-22) and, when `pool` is given, the MaxPool2d(2) of the
         next Down block (unet_parts.py:33) - fused into the SLAB epilogue, a separate kernel otherwise."""
         if ps is not None:
-            return ops.conv_slab_forward(x, ps, y, pool=pool)
+            fuse = pool is not None and ps.kind == L.SLAB_3X3
+            ops.conv_slab_forward(x, ps, y, pool=pool if fuse else None)
+            if pool is not None and not fuse:
+                ops.maxpool(y, pool, (1, 2, 2), (1, 2, 2))
+            return y
         ops.conv_forward(x, pc, y, feed=L.FEED_GATHER if pc.cin_pad == 8 else L.FEED_AUTO)
         if pool is not None:
             ops.maxpool(y, pool, (1, 2, 2), (1, 2, 2))
@@ -205,7 +225,10 @@ class I3DExecutor:
         self.specs = {}
 
         def unit(name, k, s=(1, 1, 1), cin_pad=None):
-            self.specs[name] = (sd[f"{name}.conv3d.weight"], _bn(sd, f"{name}.bn", 1e-3), k, s, cin_pad)
+            w = sd[f"{name}.conv3d.weight"]
+            if USE_SLAB and k == (3, 3, 3) and w.shape[1] >= 64:
+                cin_pad = -(-w.shape[1] // 64) * 64   # SLAB feed: 64-channel K blocks (pad channels are zero)
+            self.specs[name] = (w, _bn(sd, f"{name}.bn", 1e-3), k, s, cin_pad)
 
         unit("Conv3d_1a_7x7", (7, 7, 7), (2, 2, 2), 8)
         unit("Conv3d_2b_1x1", (1, 1, 1))
@@ -223,13 +246,16 @@ class I3DExecutor:
         key = (name, pf)
         pc = self.packed.get(key)
         if pc is None:
-            pc = PackedConv(w, None, bn, stride=s, pad_front=pf, cin_pad=cin_pad, device=self.device)
+            pc = PackedConv(w, None, bn, stride=s, pad_front=pf, cin_pad=cin_pad, device=self.device,
+                            n_align=32 if k == (3, 3, 3) else 16)
             self.packed[key] = pc
             if cin_pad == 8:
                 self.packed[key + ("slab",)] = stem3d(pc)
+            else:
+                pc.slab = slab3x3(pc)
         if cin_pad == 8:
             return stem_conv(x, pc, self.packed[key + ("slab",)], y)
-        return ops.conv_forward(x, pc, y)
+        return conv_auto(x, pc, y)
 
     @staticmethod
     def _same_out(x, s):
@@ -253,7 +279,10 @@ class I3DExecutor:
         total = oc[0] + oc[2] + oc[4] + oc[5]
         y = self.bufs.get(name, x.N, x.D, x.H, x.W, total)
         self._unit(f"{name}.b0", x, out=y.slice(0, oc[0]))
-        t1 = self._unit(f"{name}.b1a", x, oc[1])
+        # b1a's output is stored with the channel padding b1b's feed wants (pad channels zero, never written)
+        c1 = self.specs[f"{name}.b1b"][4] or oc[1]
+        t1 = self.bufs.get(f"{name}.b1a", x.N, x.D, x.H, x.W, c1, zero=True)
+        self._unit(f"{name}.b1a", x, out=t1.slice(0, oc[1]))
         self._unit(f"{name}.b1b", t1, out=y.slice(oc[0], oc[2]))
         t2 = self._unit(f"{name}.b2a", x, oc[3])
         self._unit(f"{name}.b2b", t2, out=y.slice(oc[0] + oc[2], oc[4]))
@@ -300,8 +329,11 @@ class I3Res50Executor:
         self.device = device
         self.bufs = _Buffers(device)
         P = prefix
-        mk = lambda wk, bnk, stride, pad, cin_pad=None: PackedConv(  # noqa: E731
-            sd[P + wk], None, _bn(sd, P + bnk, 1e-5), stride=stride, pad_front=pad, cin_pad=cin_pad, device=device)
+        def mk(wk, bnk, stride, pad, cin_pad=None):
+            pc = PackedConv(sd[P + wk], None, _bn(sd, P + bnk, 1e-5), stride=stride, pad_front=pad, cin_pad=cin_pad,
+                            device=device, n_align=32)
+            pc.slab = slab3x3(pc)     # the stride-1 (1,3,3) conv2 of most Bottlenecks
+            return pc
         self.conv1 = mk("conv1.weight", "bn1", (2, 2, 2), (2, 3, 3), 8)
         self.conv1_slab = stem3d(self.conv1)
         self.blocks = []
@@ -321,10 +353,10 @@ class I3Res50Executor:
     def _apply(self, name, pc, x, res=None, act=L.ACT_RELU):
         od, oh, ow = pc.out_extent((x.D, x.H, x.W))
         y = self.bufs.get(name, x.N, od, oh, ow, pc.cout)
-        return ops.conv_forward(x, pc, y, res=res, act=act)
+        return conv_auto(x, pc, y, res=res, act=act)
 
     def run(self, enc_in):
-        """enc_in: [B,T,H,W,8] -> fp32 features [B, 1, 2048]."""
+        """enc_in: [B,T,H,W,4|8] -> fp32 features [B, 1, 2048]."""
         g = self.bufs.get
         od, oh, ow = self.conv1.out_extent((enc_in.D, enc_in.H, enc_in.W))
         x = stem_conv(enc_in, self.conv1, self.conv1_slab, g("conv1", enc_in.N, od, oh, ow, self.conv1.cout))
@@ -350,8 +382,11 @@ class R3D18Executor:
     def __init__(self, sd, device):
         self.device = device
         self.bufs = _Buffers(device)
-        mk = lambda wk, bnk, stride, pad, cin_pad=None: PackedConv(  # noqa: E731
-            sd[wk], None, _bn(sd, bnk, 1e-5), stride=stride, pad_front=pad, cin_pad=cin_pad, device=device)
+        def mk(wk, bnk, stride, pad, cin_pad=None):
+            pc = PackedConv(sd[wk], None, _bn(sd, bnk, 1e-5), stride=stride, pad_front=pad, cin_pad=cin_pad, device=device,
+                            n_align=32)
+            pc.slab = slab3x3(pc)     # stride-1 3x3x3 convolutions (used when no residual is added in the epilogue)
+            return pc
         self.stem = mk("backbone.stem.0.weight", "backbone.stem.1", (1, 2, 2), (1, 3, 3), 8)
         self.stem_slab = stem3d(self.stem)
         self.blocks = []
@@ -370,7 +405,7 @@ class R3D18Executor:
     def _apply(self, name, pc, x, res=None, act=L.ACT_RELU):
         od, oh, ow = pc.out_extent((x.D, x.H, x.W))
         y = self.bufs.get(name, x.N, od, oh, ow, pc.cout)
-        return ops.conv_forward(x, pc, y, res=res, act=act)
+        return conv_auto(x, pc, y, res=res, act=act)
 
     def run(self, enc_in):
         od, oh, ow = self.stem.out_extent((enc_in.D, enc_in.H, enc_in.W))

@@ -79,11 +79,11 @@ class CLTensor:
         return out
 
 
-def n_tiling(cout):
-    """(n_tile, Cout_pad) the conv kernel uses for `cout` output channels."""
-    c16 = (cout + 15) // 16 * 16
+def n_tiling(cout, align=16):
+    """(n_tile, Cout_pad) the conv kernels use for `cout` output channels (the SLAB feed wants align=32)."""
+    c16 = (cout + align - 1) // align * align
     nt = (c16 + 255) // 256
-    n_tile = ((c16 + nt - 1) // nt + 15) // 16 * 16
+    n_tile = ((c16 + nt - 1) // nt + align - 1) // align * align
     return n_tile, n_tile * nt
 
 
@@ -92,7 +92,7 @@ class PackedConv:
     (kd,kh,kw,cin_pad); BatchNorm (eval) folded in fp32 before rounding; fp32 bias [Cout_pad]."""
 
     def __init__(self, weight, bias=None, bn=None, stride=(1, 1, 1), pad_front=(0, 0, 0), cin_pad=None,
-                 device="cuda"):
+                 device="cuda", n_align=16):
         w = weight.detach().float()
         if w.dim() == 4:  # Conv2d [Cout,Cin,kh,kw] -> 3-D with kd=1
             w = w.unsqueeze(2)
@@ -109,7 +109,7 @@ class PackedConv:
         self.cin_pad = int(cin_pad) if cin_pad is not None else (cin + 7) // 8 * 8
         assert self.cin_pad >= cin and self.cin_pad % 8 == 0
         self.cout = cout
-        self.n_tile, self.cout_pad = n_tiling(cout)
+        self.n_tile, self.cout_pad = n_tiling(cout, n_align)
         self.k = (kd, kh, kw)
         self.stride = tuple(int(s) for s in stride)
         self.pad_front = tuple(int(p) for p in pad_front)
@@ -164,9 +164,16 @@ class PackedSlabConv:
     def __init__(self, pc, kind):
         self.pc, self.kind = pc, int(kind)
         self.cout, self.cout_pad = pc.cout, pc.cout_pad
+        self.bias = pc.bias
+        self.cin_pad = 4 if kind == L.SLAB_STEM3D else pc.cin_pad
+        if kind == L.SLAB_3X3_STREAM:
+            # weights stream from the standard packed layout: nothing to re-pack
+            if pc.cout_pad % 32 or pc.cout_pad > 512 or pc.cout % 8 or pc.n_tile % 32:
+                raise ValueError(f"slab stream feed needs Cout_pad % 32 == 0 (<= 512), got {pc.cout_pad} / n_tile {pc.n_tile}")
+            self.image, self.image_bytes = pc.w, pc.w.numel() * 2
+            return
         if pc.cout_pad > 256 or pc.cout % 8:
             raise ValueError(f"slab feed needs a single N tile (Cout_pad={pc.cout_pad}) with Cout % 8 == 0")
-        self.cin_pad = 4 if kind == L.SLAB_STEM3D else pc.cin_pad
         nbytes = C.c_int64(0)
         args = (self.kind, None, pc.cout_pad, pc.k_pad, pc.cin_pad, *pc.k, pc.pad_front[2])
         L.check(L.lib().tedspad_conv_slab_pack(*args, None, C.byref(nbytes), None), "tedspad_conv_slab_pack(size)")
@@ -178,7 +185,6 @@ class PackedSlabConv:
             _count()
             L.check(L.lib().tedspad_conv_slab_pack(*args, self.image.data_ptr(), C.byref(nbytes), _stream()),
                     "tedspad_conv_slab_pack")
-        self.bias = pc.bias
 
     def desc(self, x, y, act=L.ACT_RELU, pool=None, outconv=None, tm=0, max_ctas=0):
         """outconv = (w fp32 [3,Cout], b fp32 [3], planes bf16 [N,3,H,W], frames fp32 [N,3,H,W] | None)"""
@@ -202,6 +208,7 @@ class PackedSlabConv:
         d.sd, d.sh, d.sw = pc.stride
         d.pd, d.ph, d.pw = pc.pad_front
         d.act, d.tm, d.max_ctas = act, tm, max_ctas
+        d.n_tile, d.K_pad = (pc.n_tile if self.kind == L.SLAB_3X3_STREAM else 0), pc.k_pad
         return d
 
     def plan(self, x, y, **kw):

@@ -111,28 +111,48 @@ def umma_operand(smem_bits, start, rows, layout, lbo, sbo):
     return bits_to_f32(smem_bits[byte // 2])
 
 
-def simulate_tiles(plan, xbits, image_bits, bias, tiles):
-    """Run the plan for the given tile indices; returns {tile: (n, tz, oy[128*tm], ox[128*tm], acc[128*tm, n_tile])}."""
+def stream_block(w_std, k_pad, n0, n_tile, k0):
+    """Shared-memory image of one streamed weight block: rows n0..n0+n_tile, K columns k0..k0+64 of the standard
+    packed weights, as the 2-D SWIZZLE_128B TMA box {64, n_tile} lays it out."""
+    w = w_std.reshape(-1, k_pad)[n0:n0 + n_tile, k0:k0 + 64]
+    byte = (np.arange(n_tile)[:, None] * 128 + np.arange(64)[None, :] * 2).astype(np.int64)
+    byte ^= ((byte >> 7) & 7) << 4
+    slot = np.zeros(n_tile * 64 + 64, dtype=np.uint16)
+    slot[byte // 2] = w
+    return slot
+
+
+def simulate_tiles(plan, xbits, image_bits, bias, tiles, k_pad=0):
+    """Run the plan for the given tile indices; returns {tile: (n, tz, oy[128*tm], ox[128*tm], acc[128*tm, n_tile], n0)}.
+    image_bits: the weight image (resident kinds) or the standard packed weights (streaming kind, with k_pad)."""
     out = {}
     nt = plan.n_tile
     img = np.concatenate([image_bits, np.zeros(64, np.uint16)])
     for tile in tiles:
         t = tile
+        ntile = t % plan.num_n_tiles; t //= plan.num_n_tiles
+        n0 = ntile * nt
         tx = t % plan.tiles_x; t //= plan.tiles_x
         ty = t % plan.tiles_y; t //= plan.tiles_y
         tz = t % plan.tiles_z
         n = t // plan.tiles_z
         acc = np.zeros((plan.tm, 128, nt), dtype=np.float64)
         for ks in range(plan.k_stages):
+            kt, cb = divmod(ks, plan.cb_n)
             cx, cy = tx * plan.x_step + plan.x_off, ty * plan.y_step + plan.y_off
-            cz = tz * plan.z_step + plan.z_off + ks * plan.z_kstep
-            coords = (cx * 8, cy, cz, n, 0) if plan.merged_cw else (ks * plan.c_step, cx, cy, cz, n)
+            cz = tz * plan.z_step + plan.z_off + kt * plan.z_kstep
+            coords = (cx * 8, cy, cz, n, 0) if plan.merged_cw else (cb * plan.c_step, cx, cy, cz, n)
             slab = tma_box(xbits, plan, coords)
+            tbase = ks * plan.n_grp if plan.tab_per_stage else 0
             for i in range(plan.n_grp * plan.nk):
                 grp, kk = divmod(i, plan.nk)
-                a_off = plan.tab[2 * (ks * plan.n_grp + grp)] + kk * plan.a_kstep
-                b_off = plan.tab[2 * (ks * plan.n_grp + grp) + 1] + kk * plan.b_kstep
-                B = umma_operand(img, b_off, nt, plan.b_layout, plan.b_lbo, plan.b_sbo).astype(np.float64)
+                a_off = plan.tab[2 * (tbase + grp)] + kk * plan.a_kstep
+                if plan.b_stream:
+                    slot = stream_block(image_bits, k_pad, n0, nt, (kt * plan.n_grp + grp) * plan.cin + cb * 64)
+                    B = umma_operand(slot, kk * plan.b_kstep, nt, plan.b_layout, plan.b_lbo, plan.b_sbo).astype(np.float64)
+                else:
+                    b_off = plan.tab[2 * (tbase + grp) + 1] + kk * plan.b_kstep
+                    B = umma_operand(img, b_off, nt, plan.b_layout, plan.b_lbo, plan.b_sbo).astype(np.float64)
                 for h in range(plan.tm):
                     A = umma_operand(slab, a_off + h * plan.half_a_off, 128, plan.a_layout, plan.a_lbo, plan.a_sbo)
                     acc[h] += A.astype(np.float64) @ B.T
@@ -140,5 +160,5 @@ def simulate_tiles(plan, xbits, image_bits, bias, tiles):
         g, r = m >> 3, m & 7
         oy = np.concatenate([ty * 16 + g for _ in range(plan.tm)])
         ox = np.concatenate([(tx * plan.tm + h) * 8 + r for h in range(plan.tm)])
-        out[tile] = (n, tz, oy, ox, acc.reshape(plan.tm * 128, nt) + bias[None, :nt].astype(np.float64))
+        out[tile] = (n, tz, oy, ox, acc.reshape(plan.tm * 128, nt) + bias[None, n0:n0 + nt].astype(np.float64), n0)
     return out

@@ -390,14 +390,15 @@ def run_slab_case(name, kind, N, dhw, cin_real, cin_buf, cout, k, stride=(1, 1, 
         b = (torch.rand(cout, generator=g) - 0.5).to(DEV)
         bnp = ((torch.rand(cout, generator=g) + 0.5).to(DEV), (torch.rand(cout, generator=g) - 0.5).to(DEV),
                (torch.rand(cout, generator=g) - 0.5).to(DEV), (torch.rand(cout, generator=g) + 0.5).to(DEV), 1e-3)
-        std_cin = 8 if kind != L.SLAB_3X3 else cin_buf
-        pc = ops.PackedConv(w, b, bnp, stride=stride, pad_front=pad_f, cin_pad=std_cin, device=DEV)
+        std_cin = cin_buf if kind in (L.SLAB_3X3, L.SLAB_3X3_STREAM) else 8
+        pc = ops.PackedConv(w, b, bnp, stride=stride, pad_front=pad_f, cin_pad=std_cin, device=DEV, n_align=32)
         psc = ops.PackedSlabConv(pc, kind)
-        # the CUDA pack kernel against the numpy restatement, bit for bit
-        img_ref = S.pack_image(kind, S.bf16_bits(pc.w), pc.cout_pad, pc.k_pad, pc.cin_pad, pc.k, pad_f[2])
-        okp = bool(np.array_equal(S.bf16_bits(psc.image), img_ref))
-        RESULTS.append((name + ":pack", okp))
-        print(f"[{'PASS' if okp else 'FAIL'}] {name}: weight image == numpy packer ({img_ref.size * 2} B)")
+        if kind != L.SLAB_3X3_STREAM:
+            # the CUDA pack kernel against the numpy restatement, bit for bit
+            img_ref = S.pack_image(kind, S.bf16_bits(pc.w), pc.cout_pad, pc.k_pad, pc.cin_pad, pc.k, pad_f[2])
+            okp = bool(np.array_equal(S.bf16_bits(psc.image), img_ref))
+            RESULTS.append((name + ":pack", okp))
+            print(f"[{'PASS' if okp else 'FAIL'}] {name}: weight image == numpy packer ({img_ref.size * 2} B)")
         od, oh, ow = pc.out_extent((D, H, W), pad_b)
         ld_in = in_ld or cin_buf
         xb = ops.CLTensor(N, D, H, W, ld_in, halo, device=DEV)
@@ -431,7 +432,8 @@ def run_slab_case(name, kind, N, dhw, cin_real, cin_buf, cout, k, stride=(1, 1, 
         pad6 = (pad_f[2], pad_b[2], pad_f[1], pad_b[1], pad_f[0], pad_b[0])
         ref = conv_ref(bf(x), wq.contiguous(), pc.bias[:cout], stride, pad6, None, "relu")
         plan = psc.plan(xv, yv, tm=tm)
-        ok = report(name, yv.to_ncdhw(), ref, extra=f"tm={plan.tm} stages={plan.stages} k_stages={plan.k_stages} tiles={plan.total_tiles} smem={plan.smem_bytes}")
+        ok = report(name, yv.to_ncdhw(), ref, extra=f"tm={plan.tm} stages={plan.stages} b_stages={plan.b_stages} k_stages={plan.k_stages} "
+                    f"n_tile={plan.n_tile}x{plan.num_n_tiles} tiles={plan.total_tiles} smem={plan.smem_bytes}")
         if sum(out_halo) > 0:
             full = yb.buf[..., out_coff:out_coff + cout].float().clone()
             full[:, out_halo[0]:out_halo[0] + od, out_halo[1]:out_halo[1] + oh, out_halo[2]:out_halo[2] + ow] = 3.0
@@ -478,6 +480,21 @@ def group_slab3():
     run_slab_case("S9 (1,3,3) D=3 64->64", K, 2, (3, 16, 16), 64, 64, 64, (1, 3, 3), halo=(0, 1, 1))
 
 
+def group_slabstream():
+    K = L.SLAB_3X3_STREAM
+    run_slab_case("R1 128->128 20x24 haloed", K, 2, (1, 20, 24), 128, 128, 128, (1, 3, 3), halo=(0, 1, 1))
+    run_slab_case("R2 256->128 28x28 tm1 1cta", K, 2, (1, 28, 28), 256, 256, 128, (1, 3, 3), halo=(0, 1, 1), tm=1, max_ctas=1)
+    run_slab_case("R3 256->128 slices", K, 3, (1, 32, 32), 256, 256, 128, (1, 3, 3), halo=(0, 1, 1), in_ld=320, in_coff=64,
+                  out_ld=256, out_coff=128)
+    run_slab_case("R4 3x3x3 64->192 no halo", K, 2, (4, 28, 20), 64, 64, 192, (3, 3, 3), pad_f=(1, 1, 1))
+    run_slab_case("R5 3x3x3 96(128)->208 padded K, slice out", K, 2, (4, 14, 14), 96, 128, 208, (3, 3, 3), pad_f=(1, 1, 1),
+                  out_ld=480, out_coff=192)
+    run_slab_case("R6 3x3x3 192->384 two N tiles 7x7", K, 4, (2, 7, 7), 192, 192, 384, (3, 3, 3), pad_f=(1, 1, 1))
+    run_slab_case("R7 (1,3,3) D=2 512->512 no halo", K, 2, (2, 14, 14), 512, 512, 512, (1, 3, 3))
+    run_slab_case("R8 128->128 112x112 x8 many tiles", K, 8, (1, 112, 112), 128, 128, 128, (1, 3, 3), halo=(0, 1, 1))
+    run_slab_case("R9 3x3x3 64->64 r3d 8x28x28", K, 2, (8, 28, 28), 64, 64, 64, (3, 3, 3), pad_f=(1, 1, 1))
+
+
 def group_slabstem():
     run_slab_case("T1 stem2d 3(8)->64 20x20 tm2", L.SLAB_STEM2D, 2, (1, 20, 20), 3, 8, 64, (1, 3, 3), tm=2, out_halo=(0, 1, 1))
     run_slab_case("T2 stem2d tm1 40x24", L.SLAB_STEM2D, 3, (1, 40, 24), 3, 8, 64, (1, 3, 3), tm=1, out_halo=(0, 1, 1))
@@ -514,11 +531,12 @@ def time_slab(name, kind, N, dhw, cin_buf, cout, k, stride=(1, 1, 1), pad_f=(0, 
     try:
         D, H, W = dhw
         cin_real = cin_real or cin_buf
-        halo = (0, 1, 1) if kind == L.SLAB_3X3 else (0, 0, 0)
+        halo = (0, 1, 1) if (kind in (L.SLAB_3X3, L.SLAB_3X3_STREAM) and D == 1) else (0, 0, 0)
         x = ops.CLTensor(N, D, H, W, cin_buf, halo, device=DEV)
         x.interior().normal_()
         wt = torch.randn(cout, cin_real, *k, device=DEV) / (cin_real * k[0] * k[1] * k[2]) ** 0.5
-        pc = ops.PackedConv(wt, None, None, stride=stride, pad_front=pad_f, cin_pad=cin_buf if kind == L.SLAB_3X3 else 8, device=DEV)
+        pc = ops.PackedConv(wt, None, None, stride=stride, pad_front=pad_f,
+                            cin_pad=cin_buf if kind in (L.SLAB_3X3, L.SLAB_3X3_STREAM) else 8, device=DEV, n_align=32)
         psc = ops.PackedSlabConv(pc, kind)
         od, oh, ow = pc.out_extent((D, H, W), pad_b)
         y = ops.CLTensor(N, od, oh, ow, cout, (0, 1, 1) if od == 1 else (0, 0, 0), device=DEV)
@@ -535,10 +553,24 @@ def time_slab(name, kind, N, dhw, cin_buf, cout, k, stride=(1, 1, 1), pad_f=(0, 
         ms = e0.elapsed_time(e1) / iters
         flops = 2.0 * N * od * oh * ow * cin_real * cout * k[0] * k[1] * k[2]
         plan = psc.plan(x, y, tm=tm)
-        print(f"[PERF] slab {name}: {ms:.3f} ms  {flops / ms / 1e9:.1f} TFLOP/s (algorithmic)  tm={plan.tm} stages={plan.stages}",
-              flush=True)
+        print(f"[PERF] slab {name}: {ms:.3f} ms  {flops / ms / 1e9:.1f} TFLOP/s (algorithmic)  tm={plan.tm} stages={plan.stages} "
+              f"b_stages={plan.b_stages}", flush=True)
     except Exception:
         print(f"[FAIL] perf slab {name}: EXCEPTION\n{traceback.format_exc()}", flush=True)
+
+
+def group_streamperf():
+    K = L.SLAB_3X3_STREAM
+    for tm in (1, 2):
+        time_slab(f"128->128 @112 x128 tm{tm}", K, 128, (1, 112, 112), 128, 128, (1, 3, 3), tm=tm)
+    time_slab("256->128 @112 x128", K, 128, (1, 112, 112), 256, 128, (1, 3, 3))
+    time_slab("256->128 @56 x128", K, 128, (1, 56, 56), 256, 128, (1, 3, 3))
+    time_slab("128->256 @56 x128", K, 128, (1, 56, 56), 128, 256, (1, 3, 3))
+    time_slab("i3d 2c 64->192 3x3x3 @8x56x56 x8", K, 8, (8, 56, 56), 64, 192, (3, 3, 3), pad_f=(1, 1, 1))
+    time_slab("i3d 3c.b1b 128->192 @8x28x28 x8", K, 8, (8, 28, 28), 128, 192, (3, 3, 3), pad_f=(1, 1, 1))
+    time_slab("i3d 4f.b1b 192(160)->320 @4x14x14 x8", K, 8, (4, 14, 14), 192, 320, (3, 3, 3), pad_f=(1, 1, 1))
+    time_conv("FLAT 128->128 @112 x128 (old feed)", 128, (112, 112), 128, 128)
+    time_conv("FLAT 256->128 @112 x128 (old feed)", 128, (112, 112), 256, 128)
 
 
 def group_slabperf():

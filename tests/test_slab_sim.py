@@ -24,26 +24,30 @@ def _run(kind, x_cl, x_ref, w, stride, pad_f, pad_b, y_shape, tm, tiles=None, ci
     """x_cl: CLTensor view (cpu) holding x_ref's data; returns max abs error over the simulated tiles."""
     cout = w.shape[0]
     b = torch.linspace(-0.5, 0.5, cout)
-    pc = ops.PackedConv(w, b, None, stride=stride, pad_front=pad_f, cin_pad=cin_pad, device="cpu")
+    pc = ops.PackedConv(w, b, None, stride=stride, pad_front=pad_f, cin_pad=cin_pad, device="cpu", n_align=32)
     psc = ops.PackedSlabConv(pc, kind)
     y = ops.CLTensor(*y_shape, cout, device="cpu")
     plan = psc.plan(x_cl, y, tm=tm)
-    image = S.pack_image(kind, S.bf16_bits(pc.w), pc.cout_pad, pc.k_pad, pc.cin_pad, pc.k, pad_f[2])
-    assert image.size * 2 == psc.image_bytes == plan.w_bytes
+    if kind == L.SLAB_3X3_STREAM:
+        image = S.bf16_bits(pc.w)
+    else:
+        image = S.pack_image(kind, S.bf16_bits(pc.w), pc.cout_pad, pc.k_pad, pc.cin_pad, pc.k, pad_f[2])
+        assert image.size * 2 == psc.image_bytes == plan.w_bytes
     wq = pc.w[:cout, :pc.k[0] * pc.k[1] * pc.k[2] * pc.cin_pad].float().reshape(cout, *pc.k, pc.cin_pad)
     wq = wq[..., :w.shape[1]].permute(0, 4, 1, 2, 3).contiguous()
     pad6 = (pad_f[2], pad_b[2], pad_f[1], pad_b[1], pad_f[0], pad_b[0])
     ref = F.conv3d(F.pad(_bf(x_ref), pad6), wq, pc.bias[:cout], stride=stride)  # [N,Cout,OD,OH,OW]
     assert tuple(ref.shape[2:]) == tuple(y_shape[1:]), (ref.shape, y_shape)
     tiles = list(range(plan.total_tiles)) if tiles is None else [t % plan.total_tiles for t in tiles]
-    res = S.simulate_tiles(plan, S.bf16_bits(x_cl.buf), image, pc.bias.numpy(), tiles)
+    res = S.simulate_tiles(plan, S.bf16_bits(x_cl.buf), image, pc.bias.numpy(), tiles, k_pad=pc.k_pad)
     worst, seen = 0.0, 0
     OH, OW = y_shape[2], y_shape[3]
-    for tile, (n, tz, oy, ox, acc) in res.items():
+    for tile, (n, tz, oy, ox, acc, n0) in res.items():
         ok = (oy < OH) & (ox < OW)
-        want = ref[n, :, tz][:, torch.from_numpy(oy[ok]), torch.from_numpy(ox[ok])].T.numpy()
-        worst = max(worst, float(np.abs(acc[ok][:, :cout] - want).max()))
-        seen += int(ok.sum())
+        nc = min(plan.n_tile, cout - n0)   # real channels of this N tile
+        want = ref[n, n0:n0 + nc, tz][:, torch.from_numpy(oy[ok]), torch.from_numpy(ox[ok])].T.numpy()
+        worst = max(worst, float(np.abs(acc[ok][:, :nc] - want).max()))
+        seen += int(ok.sum()) if n0 == 0 else 0
     return worst, seen, plan
 
 
@@ -62,6 +66,32 @@ def test_slab_3x3_plan_reproduces_conv(cin, cout, tm, ld, coff):
     assert plan.k_stages == cin // 64 and plan.n_mma == 36 and plan.swizzle128 == 1
     assert plan.tm == (tm if tm else 1)  # 128->64 weights leave room for three stages only at tm=1
     assert seen == N * H * W and err < 2e-5, (err, seen)
+
+
+@pytest.mark.parametrize("name,dhw,cin,cout,kd,halo,tm", [
+    ("unet 128->128 haloed", (1, 20, 24), 128, 128, 1, (0, 1, 1), 0),
+    ("unet 256->128 tm1", (1, 18, 16), 256, 128, 1, (0, 1, 1), 1),
+    ("i3d Conv3d_2c 64->192 3x3x3 no halo", (4, 20, 12), 64, 192, 3, (0, 0, 0), 0),
+    ("i3d 5c.b1b 192->384 (two N tiles)", (2, 7, 7), 192, 384, 3, (0, 0, 0), 0),
+    ("i3d 4b.b1b 128(96)->208 padded", (3, 14, 14), 128, 208, 3, (0, 0, 0), 0),
+])
+def test_slab_stream_plan_reproduces_conv(name, dhw, cin, cout, kd, halo, tm):
+    g = torch.Generator().manual_seed(cin + cout + kd)
+    N = 2
+    D, H, W = dhw
+    x = torch.randn(N, cin, D, H, W, generator=g)
+    w = torch.randn(cout, cin, kd, 3, 3, generator=g) / (9 * kd * cin) ** 0.5
+    xc = ops.CLTensor(N, D, H, W, cin, halo, device="cpu")
+    xc.buf.zero_()
+    xc.interior()[...] = x.permute(0, 2, 3, 4, 1).to(torch.bfloat16)
+    pad = (kd // 2, 1, 1)
+    tiles = None if D * H * W < 2000 else list(range(0, 10 ** 6, 7))[:24]
+    err, seen, plan = _run(L.SLAB_3X3_STREAM, xc, x, w, (1, 1, 1), pad, pad, (N, D, H, W), tm, tiles=tiles, cin_pad=cin)
+    assert plan.b_stream == 1 and plan.k_stages == kd * (cin // 64) and plan.b_stages >= 3
+    assert plan.num_n_tiles == (2 if cout > 256 else 1)
+    if tiles is None:
+        assert seen == N * D * H * W
+    assert err < 3e-5, (name, err)
 
 
 def test_slab_stem2d_plan_reproduces_conv():
@@ -104,10 +134,10 @@ def test_slab_stem3d_plan_reproduces_conv(name, kd, sd, pad_f, pad_b, dhw):
 def test_slab_plan_rejects_what_it_cannot_run():
     pc = ops.PackedConv(torch.zeros(64, 64, 1, 3, 3), None, None, pad_front=(0, 1, 1), device="cpu")
     psc = ops.PackedSlabConv(pc, L.SLAB_3X3)
-    x_nohalo = ops.CLTensor(1, 1, 16, 16, 64, device="cpu")
+    x_c32 = ops.CLTensor(1, 1, 16, 16, 32, device="cpu")
     y = ops.CLTensor(1, 1, 16, 16, 64, device="cpu")
-    with pytest.raises(RuntimeError, match="halo"):
-        psc.plan(x_nohalo, y)
+    with pytest.raises(RuntimeError, match="multiple of 64"):
+        psc.plan(x_c32, y)
     big = ops.PackedConv(torch.zeros(128, 128, 1, 3, 3), None, None, pad_front=(0, 1, 1), device="cpu")
     x = ops.CLTensor(1, 1, 16, 16, 128, (0, 1, 1), device="cpu")
     with pytest.raises(RuntimeError, match="do not fit"):
