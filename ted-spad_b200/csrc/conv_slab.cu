@@ -836,7 +836,8 @@ extern "C" int tedspad_conv_slab_forward(const tedspad_conv_slab* c, void* strea
   if (c->pool.ptr != nullptr) {
     const tedspad_tensor& q = c->pool;
     if (check_tensor(q, "slab.pool", 8)) return 1;
-    TSP_CHECK(c->kind == TEDSPAD_SLAB_3X3 && y.D == 1 && q.D == 1 && q.pd == 0 && q.N == y.N && q.C == c->Cout &&
+    TSP_CHECK((c->kind == TEDSPAD_SLAB_3X3 || c->kind == TEDSPAD_SLAB_3X3_STREAM) && y.D == 1 && q.D == 1 && q.pd == 0 &&
+                  q.N == y.N && q.C == c->Cout &&
                   q.H == y.H / 2 && q.W == y.W / 2,
               "slab: fused MaxPool2d(2) output [%d,%d,%d,%d] does not match", q.N, q.H, q.W, q.C);
     p.pool = reinterpret_cast<__nv_bfloat16*>(q.ptr);

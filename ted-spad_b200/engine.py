@@ -107,9 +107,9 @@ class _Buffers:
 # ======================================================================================== UNet
 class UNetExecutor:
     """aux_code/models/unet_model.py:26-37 as 18 tcgen05 convolutions + up-samples (+ pools / OutConv when they
-    are not fused).  Feeds: the first convolution (Cin=3) and the 64/128-channel layers whose weights fit in
-    shared memory use the SLAB feed (MaxPool2d and OutConv+sigmoid fused into their epilogues); the wider layers
-    use the FLAT TMA feed over zero-haloed buffers."""
+    are not fused).  Every convolution runs through the SLAB feed: the Cin=3 stem, resident weights for the
+    64-channel layers (MaxPool2d and OutConv+sigmoid fused into their epilogues), streamed weights for the rest;
+    TEDSPAD_SLAB=0 switches back to the FLAT TMA / GATHER feeds over the same zero-haloed buffers."""
 
     HALO = (0, 1, 1)
     LEVELS = ["inc.double_conv"] + [f"down{i}.maxpool_conv.1.double_conv" for i in range(1, 5)]
@@ -126,9 +126,8 @@ class UNetExecutor:
             b = PackedConv(sd[f"{prefix}.3.weight"], sd[f"{prefix}.3.bias"], _bn(sd, f"{prefix}.4", 1e-5),
                            pad_front=(0, 1, 1), device=device)
             self.convs[prefix] = (a, b)
-            # 256/512-channel layers run the tensor pipe at ~80 % through the FLAT feed already: SLAB up to 128 outputs
-            sa = ops.PackedSlabConv(a, L.SLAB_STEM2D) if (USE_SLAB and cin_pad0 == 8) else slab3x3(a, 128)
-            self.slabs[prefix] = (sa, slab3x3(b, 128))
+            sa = ops.PackedSlabConv(a, L.SLAB_STEM2D) if (USE_SLAB and cin_pad0 == 8) else slab3x3(a)
+            self.slabs[prefix] = (sa, slab3x3(b))
 
         dc("inc.double_conv", 8)
         for i in range(1, 5):
@@ -147,11 +146,7 @@ class UNetExecutor:
         """DoubleConv half: conv+BN+ReLU (unet_parts.py:15-22) and, when `pool` is given, the MaxPool2d(2) of the
         next Down block (unet_parts.py:33) - fused into the SLAB epilogue, a separate kernel otherwise."""
         if ps is not None:
-            fuse = pool is not None and ps.kind == L.SLAB_3X3
-            ops.conv_slab_forward(x, ps, y, pool=pool if fuse else None)
-            if pool is not None and not fuse:
-                ops.maxpool(y, pool, (1, 2, 2), (1, 2, 2))
-            return y
+            return ops.conv_slab_forward(x, ps, y, pool=pool)
         ops.conv_forward(x, pc, y, feed=L.FEED_GATHER if pc.cin_pad == 8 else L.FEED_AUTO)
         if pool is not None:
             ops.maxpool(y, pool, (1, 2, 2), (1, 2, 2))

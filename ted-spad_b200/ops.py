@@ -161,14 +161,17 @@ class PackedSlabConv:
     """Weights of a SLAB-feed convolution (include/tedspad.h: tedspad_conv_slab): the standard PackedConv
     layout re-packed on the device into the shared-memory image the kernel keeps resident."""
 
-    def __init__(self, pc, kind):
+    def __init__(self, pc, kind, n_tile=0):
         self.pc, self.kind = pc, int(kind)
+        # STREAM kind: UMMA N per tile (<= 256).  Measured on B200 (tests/gpu_diag.py wideperf): for 256/512 outputs
+        # one 256-wide tile beats two 128-wide ones; 128 outputs get two 8-column halves per weight block.
+        self.n_tile = int(n_tile) or pc.n_tile
         self.cout, self.cout_pad = pc.cout, pc.cout_pad
         self.bias = pc.bias
         self.cin_pad = 4 if kind == L.SLAB_STEM3D else pc.cin_pad
         if kind == L.SLAB_3X3_STREAM:
             # weights stream from the standard packed layout: nothing to re-pack
-            if pc.cout_pad % 32 or pc.cout_pad > 512 or pc.cout % 8 or pc.n_tile % 32:
+            if pc.cout_pad % 32 or pc.cout_pad > 512 or pc.cout % 8 or self.n_tile % 32 or pc.cout_pad % self.n_tile:
                 raise ValueError(f"slab stream feed needs Cout_pad % 32 == 0 (<= 512), got {pc.cout_pad} / n_tile {pc.n_tile}")
             self.image, self.image_bytes = pc.w, pc.w.numel() * 2
             return
@@ -208,7 +211,7 @@ class PackedSlabConv:
         d.sd, d.sh, d.sw = pc.stride
         d.pd, d.ph, d.pw = pc.pad_front
         d.act, d.tm, d.max_ctas = act, tm, max_ctas
-        d.n_tile, d.K_pad = (pc.n_tile if self.kind == L.SLAB_3X3_STREAM else 0), pc.k_pad
+        d.n_tile, d.K_pad = (self.n_tile if self.kind == L.SLAB_3X3_STREAM else 0), pc.k_pad
         return d
 
     def plan(self, x, y, **kw):

@@ -493,6 +493,9 @@ def group_slabstream():
     run_slab_case("R7 (1,3,3) D=2 512->512 no halo", K, 2, (2, 14, 14), 512, 512, 512, (1, 3, 3))
     run_slab_case("R8 128->128 112x112 x8 many tiles", K, 8, (1, 112, 112), 128, 128, 128, (1, 3, 3), halo=(0, 1, 1))
     run_slab_case("R9 3x3x3 64->64 r3d 8x28x28", K, 2, (8, 28, 28), 64, 64, 64, (3, 3, 3), pad_f=(1, 1, 1))
+    run_slab_case("R10 128->128 pool fused", K, 3, (1, 32, 48), 128, 128, 128, (1, 3, 3), halo=(0, 1, 1), pool=True)
+    run_slab_case("R11 256->256 pool fused (N=256, tm=1)", K, 2, (1, 28, 28), 256, 256, 256, (1, 3, 3), halo=(0, 1, 1), pool=True)
+    run_slab_case("R12 512->512 two N tiles pool fused", K, 2, (1, 28, 28), 512, 512, 512, (1, 3, 3), halo=(0, 1, 1), pool=True)
 
 
 def group_slabstem():
@@ -527,7 +530,7 @@ def group_slabstem():
 
 
 def time_slab(name, kind, N, dhw, cin_buf, cout, k, stride=(1, 1, 1), pad_f=(0, 1, 1), pad_b=None, tm=0, iters=10, pool=False,
-              cin_real=None):
+              cin_real=None, n_tile=0):
     try:
         D, H, W = dhw
         cin_real = cin_real or cin_buf
@@ -537,7 +540,7 @@ def time_slab(name, kind, N, dhw, cin_buf, cout, k, stride=(1, 1, 1), pad_f=(0, 
         wt = torch.randn(cout, cin_real, *k, device=DEV) / (cin_real * k[0] * k[1] * k[2]) ** 0.5
         pc = ops.PackedConv(wt, None, None, stride=stride, pad_front=pad_f,
                             cin_pad=cin_buf if kind in (L.SLAB_3X3, L.SLAB_3X3_STREAM) else 8, device=DEV, n_align=32)
-        psc = ops.PackedSlabConv(pc, kind)
+        psc = ops.PackedSlabConv(pc, kind, n_tile=n_tile)
         od, oh, ow = pc.out_extent((D, H, W), pad_b)
         y = ops.CLTensor(N, od, oh, ow, cout, (0, 1, 1) if od == 1 else (0, 0, 0), device=DEV)
         pv = ops.CLTensor(N, 1, oh // 2, ow // 2, cout, (0, 1, 1), device=DEV) if pool else None
@@ -554,7 +557,7 @@ def time_slab(name, kind, N, dhw, cin_buf, cout, k, stride=(1, 1, 1), pad_f=(0, 
         flops = 2.0 * N * od * oh * ow * cin_real * cout * k[0] * k[1] * k[2]
         plan = psc.plan(x, y, tm=tm)
         print(f"[PERF] slab {name}: {ms:.3f} ms  {flops / ms / 1e9:.1f} TFLOP/s (algorithmic)  tm={plan.tm} stages={plan.stages} "
-              f"b_stages={plan.b_stages}", flush=True)
+              f"b_stages={plan.b_stages} n_tile={plan.n_tile}x{plan.num_n_tiles}", flush=True)
     except Exception:
         print(f"[FAIL] perf slab {name}: EXCEPTION\n{traceback.format_exc()}", flush=True)
 
@@ -571,6 +574,16 @@ def group_streamperf():
     time_slab("i3d 4f.b1b 192(160)->320 @4x14x14 x8", K, 8, (4, 14, 14), 192, 320, (3, 3, 3), pad_f=(1, 1, 1))
     time_conv("FLAT 128->128 @112 x128 (old feed)", 128, (112, 112), 128, 128)
     time_conv("FLAT 256->128 @112 x128 (old feed)", 128, (112, 112), 256, 128)
+
+
+def group_wideperf():
+    """256/512-channel UNet layers: streaming SLAB (128- and 256-wide N tiles) against the FLAT feed."""
+    K = L.SLAB_3X3_STREAM
+    for (cin, cout, hw) in ((128, 256, 56), (256, 256, 56), (512, 256, 56), (256, 512, 28), (512, 512, 28), (1024, 512, 28),
+                            (512, 512, 14)):
+        for nt in (128, 256):
+            time_slab(f"{cin}->{cout} @{hw} x128 n_tile={nt}", K, 128, (1, hw, hw), cin, cout, (1, 3, 3), n_tile=nt)
+        time_conv(f"FLAT {cin}->{cout} @{hw} x128", 128, (hw, hw), cin, cout)
 
 
 def group_slabperf():
