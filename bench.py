@@ -39,6 +39,16 @@ def measured_peaks():
     return 1400.0, 1590.0, 6650.0, "fallback"
 
 
+def ncu_traffic(batch_clips):
+    """dram__bytes_read.sum + dram__bytes_write.sum of all convolution launches of one step, from the committed ncu
+    capture of `tests/profile_step.py 32` (profiles/r1_conv_dram_bytes.json); None for any other batch size."""
+    p = os.path.join(ROOT, "profiles", "r1_conv_dram_bytes.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    return d["dram_bytes_per_step"] if d.get("batch_clips") == batch_clips else None
+
+
 class ClockSampler(threading.Thread):
     """SM clock + throttle reasons during the timed region (nvidia-smi query, 200 ms period)."""
 
@@ -236,10 +246,10 @@ def main():
                    "batch_clips_per_gpu": B, "l2": "inputs larger than L2 (118 MB uint8 per step, two alternating sets; "
                    "activations ~26 GB per step)", "weights": "random init (seeded stock init of the reference architecture)"},
         "tflops_algorithmic": clips_per_s * GFLOP_CLIP / 1e3 / world,
-        "roofline": {"bound": "tensor", "kernel": "conv_igemm_kernel (all %d launches of a step)" % n_conv,
+        "roofline": {"bound": "tensor", "kernel": "conv_slab_kernel + conv_igemm_kernel (all %d convolution launches of a step)" % n_conv,
                      "achieved": conv_tflops, "peak": sustained, "unit": "TFLOP/s", "frac": conv_tflops / sustained,
                      "peak_burst": burst, "peak_source": how + " bf16_tflops_sustained (kernel timed inside a long step)",
-                     "conv_ms_per_step": conv_ms, "conv_share_of_step": conv_ms / ms_step, "traffic": None},
+                     "conv_ms_per_step": conv_ms, "conv_share_of_step": conv_ms / ms_step, "traffic": ncu_traffic(B)},
         "e2e": {"value": e2e_cps, "unit": "clips/s", "h2d_bytes_per_step": int(host_sets[0].numel()),
                 "d2h_bytes_per_step": int(feat_host.numel() * 4)},
         "gpu_launches": launches,

@@ -51,10 +51,23 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 
 constexpr long long ROWS_PER_BLOCK = 1;  // >1 was measured: no L1-reuse gain, less parallelism on small maps
 
+// bf16 pair -> two fp32 (a bf16 is the upper half of an fp32: one shift / one mask)
+__device__ __forceinline__ void bf2_to_f32(uint32_t v, float& lo, float& hi) {
+  lo = __uint_as_float(v << 16);
+  hi = __uint_as_float(v & 0xffff0000u);
+}
+__device__ __forceinline__ uint32_t hmax2_bf16(uint32_t a, uint32_t b) {
+  const __nv_bfloat162 m = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+  return *reinterpret_cast<const uint32_t*>(&m);
+}
+// it / d for it < 2^16 with magic = ceil(2^32 / d) (exact in that range for d <= 2^16)
+__device__ __forceinline__ int fast_div(int it, uint32_t magic) { return static_cast<int>(__umulhi(static_cast<uint32_t>(it), magic)); }
+
 // ------------------------------------------------------------------ max pool
 struct PoolP {
   TView x, y;
   int kd, kh, kw, sd, sh, sw, pd, ph, pw, zero_pad;
+  uint32_t c8_magic;
   long long total;  // output rows N*OD*OH
 };
 
@@ -75,11 +88,10 @@ __global__ void __launch_bounds__(256) maxpool_kernel(const PoolP p) {
     const __nv_bfloat16* xn = reinterpret_cast<const __nv_bfloat16*>(p.x.ptr) + p.x.coff;
     __nv_bfloat16* yrow = elem_ptr_w(p.y, pix_index(p.y, n, od, oh, 0), 0);
     for (int it = threadIdx.x; it < items; it += blockDim.x) {
-      const int ow = it / c8n, c8 = it - ow * c8n;
+      const int ow = fast_div(it, p.c8_magic), c8 = it - ow * c8n;
       const int iw0 = ow * p.sw - p.pw;
-      float m[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) m[i] = -INFINITY;
+      // max on packed bf16 pairs (exact: max commutes with rounding); -inf = 0xff80
+      uint4 m = make_uint4(0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u);
       bool any_oob = false;
       for (int a = 0; a < p.kd; ++a) {
         const int id = id0 + a;
@@ -92,10 +104,8 @@ __global__ void __launch_bounds__(256) maxpool_kernel(const PoolP p) {
             const int iw = iw0 + c;
             if (okh && static_cast<unsigned>(iw) < static_cast<unsigned>(p.x.W)) {
               const uint4 q = __ldg(reinterpret_cast<const uint4*>(xn + (rowpix + iw) * p.x.ld + c8 * 8));
-              float f[8];
-              unpack8(q, f);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], f[i]);
+              m.x = hmax2_bf16(m.x, q.x); m.y = hmax2_bf16(m.y, q.y);
+              m.z = hmax2_bf16(m.z, q.z); m.w = hmax2_bf16(m.w, q.w);
             } else {
               any_oob = true;
             }
@@ -103,10 +113,9 @@ __global__ void __launch_bounds__(256) maxpool_kernel(const PoolP p) {
         }
       }
       if (any_oob && p.zero_pad) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], 0.f);
+        m.x = hmax2_bf16(m.x, 0u); m.y = hmax2_bf16(m.y, 0u); m.z = hmax2_bf16(m.z, 0u); m.w = hmax2_bf16(m.w, 0u);
       }
-      *reinterpret_cast<uint4*>(yrow + static_cast<long long>(ow) * p.y.ld + c8 * 8) = pack8(m);
+      *reinterpret_cast<uint4*>(yrow + static_cast<long long>(ow) * p.y.ld + c8 * 8) = m;
     }
   }
 }
@@ -116,6 +125,7 @@ struct UpP {
   TView x, y;
   int UH, UW, offy, offx;  // up-sampled size and F.pad offsets inside y
   float sy, sx;
+  uint32_t c8_magic;
   long long total;  // output rows N*H of y's interior
 };
 
@@ -138,25 +148,34 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const UpP p) {
     const __nv_bfloat16* r1 = elem_ptr(p.x, pix_index(p.x, n, 0, y1, 0), 0);
     __nv_bfloat16* yrow = elem_ptr_w(p.y, pix_index(p.y, n, 0, oh, 0), 0);
     for (int it = threadIdx.x; it < items; it += blockDim.x) {
-      const int ow = it / c8n, c8 = it - ow * c8n;
-      float o[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = 0.f;
+      const int ow = fast_div(it, p.c8_magic), c8 = it - ow * c8n;
+      uint4 out = make_uint4(0u, 0u, 0u, 0u);
       const int ux = ow - p.offx;
       if (row_in && ux >= 0 && ux < p.UW) {
         const float fx = p.sx * ux;
         const int x0 = static_cast<int>(fx);
         const int x1 = x0 + (x0 < p.x.W - 1 ? 1 : 0);
         const float lx1 = fx - x0, lx0 = 1.f - lx1;
-        float a[8], b[8], c[8], d[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(r0 + static_cast<long long>(x0) * p.x.ld + c8 * 8)), a);
-        unpack8(__ldg(reinterpret_cast<const uint4*>(r0 + static_cast<long long>(x1) * p.x.ld + c8 * 8)), b);
-        unpack8(__ldg(reinterpret_cast<const uint4*>(r1 + static_cast<long long>(x0) * p.x.ld + c8 * 8)), c);
-        unpack8(__ldg(reinterpret_cast<const uint4*>(r1 + static_cast<long long>(x1) * p.x.ld + c8 * 8)), d);
+        const float w00 = ly0 * lx0, w01 = ly0 * lx1, w10 = ly1 * lx0, w11 = ly1 * lx1;
+        const uint4 qa = __ldg(reinterpret_cast<const uint4*>(r0 + static_cast<long long>(x0) * p.x.ld + c8 * 8));
+        const uint4 qb = __ldg(reinterpret_cast<const uint4*>(r0 + static_cast<long long>(x1) * p.x.ld + c8 * 8));
+        const uint4 qc = __ldg(reinterpret_cast<const uint4*>(r1 + static_cast<long long>(x0) * p.x.ld + c8 * 8));
+        const uint4 qd = __ldg(reinterpret_cast<const uint4*>(r1 + static_cast<long long>(x1) * p.x.ld + c8 * 8));
+        const uint32_t* pa = reinterpret_cast<const uint32_t*>(&qa);
+        const uint32_t* pb = reinterpret_cast<const uint32_t*>(&qb);
+        const uint32_t* pc = reinterpret_cast<const uint32_t*>(&qc);
+        const uint32_t* pd = reinterpret_cast<const uint32_t*>(&qd);
+        uint32_t* po = reinterpret_cast<uint32_t*>(&out);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = ly0 * (lx0 * a[i] + lx1 * b[i]) + ly1 * (lx0 * c[i] + lx1 * d[i]);
+        for (int i = 0; i < 4; ++i) {
+          float a0, a1, b0, b1, c0, c1, d0, d1;
+          bf2_to_f32(pa[i], a0, a1); bf2_to_f32(pb[i], b0, b1); bf2_to_f32(pc[i], c0, c1); bf2_to_f32(pd[i], d0, d1);
+          const float o0 = fmaf(w11, d0, fmaf(w10, c0, fmaf(w01, b0, w00 * a0)));
+          const float o1 = fmaf(w11, d1, fmaf(w10, c1, fmaf(w01, b1, w00 * a1)));
+          po[i] = cvt_bf16x2(o0, o1, false);
+        }
       }
-      *reinterpret_cast<uint4*>(yrow + static_cast<long long>(ow) * p.y.ld + c8 * 8) = pack8(o);
+      *reinterpret_cast<uint4*>(yrow + static_cast<long long>(ow) * p.y.ld + c8 * 8) = out;
     }
   }
 }
@@ -524,6 +543,8 @@ extern "C" int tedspad_maxpool(const tedspad_tensor* x, const tedspad_tensor* y,
   p.x = make_view(*x); p.y = make_view(*y);
   p.kd = kd; p.kh = kh; p.kw = kw; p.sd = sd; p.sh = sh; p.sw = sw; p.pd = pd; p.ph = ph; p.pw = pw;
   p.zero_pad = zero_pad;
+  p.c8_magic = static_cast<uint32_t>((0x100000000ULL + (y->C / 8) - 1) / (y->C / 8));
+  TSP_CHECK(static_cast<long long>(y->W) * (y->C / 8) < 65536, "maxpool: row of %d x %d channels too long", y->W, y->C);
   p.total = static_cast<long long>(y->N) * y->D * y->H;   // output rows
   TSP_CHECK(p.total < (1LL << 31), "maxpool: too many rows");
   maxpool_kernel<<<rows_grid(p.total, y->W * (y->C / 8)), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
@@ -543,6 +564,8 @@ extern "C" int tedspad_upsample2x(const tedspad_tensor* x, const tedspad_tensor*
   p.sy = p.UH > 1 ? static_cast<float>(x->H - 1) / static_cast<float>(p.UH - 1) : 0.f;
   p.sx = p.UW > 1 ? static_cast<float>(x->W - 1) / static_cast<float>(p.UW - 1) : 0.f;
   p.total = static_cast<long long>(y->N) * y->H;   // output rows
+  p.c8_magic = static_cast<uint32_t>((0x100000000ULL + (y->C / 8) - 1) / (y->C / 8));
+  TSP_CHECK(static_cast<long long>(y->W) * (y->C / 8) < 65536, "upsample2x: row of %d x %d channels too long", y->W, y->C);
   upsample2x_kernel<<<rows_grid(p.total, y->W * (y->C / 8)), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   TSP_CUDA(cudaGetLastError());
   return 0;
