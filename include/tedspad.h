@@ -107,6 +107,9 @@ int tedspad_conv_forward(const tedspad_conv* p, void* stream);
  *                        block).  The 128-channel DoubleConv layers (unet_parts.py:15-22), Conv3d_2c_3x3
  *                        and the Inception 3x3x3 branches (aux_code/models/i3d.py:244,132-136).  Taps
  *                        outside the tensor are zero-filled by TMA: no halo required.
+ * Optional fused producer (3X3 kinds, 2-D): `up` = the low-resolution tensor of Up.forward; its x2 bilinear
+ * (align_corners=True) up-sampling is computed by four producer warps straight into the shared-memory slab,
+ * so the up-sampled half of torch.cat([x2, x1]) (unet_parts.py:67) is never written to or read from HBM.
  * Optional fused epilogues (TEDSPAD_SLAB_3X3 only): MaxPool2d(2) of the output written to `pool`
  * (unet_parts.py:33), and OutConv 1x1 (Cout->3) + sigmoid written as planar [N][3][H][W] images
  * (unet_parts.py:71-77, unet_model.py:36-37) in which case y.ptr may be NULL.
@@ -121,6 +124,8 @@ typedef struct tedspad_conv_slab {
   const void* w_image;      /* device: weights, shared-memory image (tedspad_conv_slab_pack) */
   const float* bias;        /* device: fp32 [Cout_pad] */
   tedspad_tensor pool;      /* optional fused MaxPool2d(2) output view (ptr NULL = none) */
+  tedspad_tensor up;        /* optional fused Up.forward input (unet_parts.py:50,57-67): the convolution sees
+                               [x | upsample2x(up)] along the channels; ptr NULL = none */
   const float* oc_w;        /* optional fused OutConv: device fp32 [3][Cout]; NULL = none */
   const float* oc_b;        /* device fp32 [3] */
   void* oc_planes;          /* device bf16 [N][3][H][W] */
@@ -154,7 +159,8 @@ typedef struct tedspad_slab_plan {
   int32_t half_a_off;       /* A byte offset of the second 8-column group */
   int32_t c_step, x_step, x_off, y_step, y_off, z_step, z_off, z_kstep;  /* slab origin per tile / K stage */
   int32_t tiles_x, tiles_y, tiles_z, total_tiles;
-  int32_t b_stream, b_stages, b_stride, cb_n, cin, num_n_tiles, tab_per_stage, reserved0;
+  int32_t b_stream, b_stages, b_stride, cb_n, cin, num_n_tiles, tab_per_stage;
+  int32_t up_cb_first;      /* channel blocks >= this one are interpolated from `up` instead of loaded by TMA */
   uint32_t tab[2 * TEDSPAD_SLAB_MAX_MMA];   /* per (k_stage, group): {A byte offset in slab, B byte offset in image} */
 } tedspad_slab_plan;
 

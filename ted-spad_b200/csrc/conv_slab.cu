@@ -47,6 +47,11 @@ struct SlabKParams {
   int tm, n_tile, k_stages, n_grp, nk, a_kstep, b_kstep, stages, tmem_cols;
   int slab_bytes, slab_stride, w_bytes, w_stride, zero_slabs;
   int b_stream, b_stages, b_stride, cb_n, cin, num_n_tiles, tab_per_stage;
+  // fused x2 bilinear up-sampling source (channel blocks >= up_cb_first are interpolated into the slab)
+  const __nv_bfloat16* up;
+  int up_cb_first, up_H, up_W, up_Hp, up_Wp, up_ph, up_pw, up_ld, up_coff, up_UH, up_UW, up_offy, up_offx, slab_w, slab_px;
+  float up_sy, up_sx;
+  uint32_t slab_w_magic;
   int half_a_off;
   int c_step, x_step, x_off, y_step, y_off, z_step, z_off, z_kstep, merged_cw;
   int tiles_x, tiles_y, tiles_z, total_tiles;
@@ -71,6 +76,9 @@ __device__ __forceinline__ uint32_t max_bf162(uint32_t a, uint32_t b) {
   const __nv_bfloat162 m = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
   return *reinterpret_cast<const uint32_t*>(&m);
 }
+
+// r / d for r < 2^16 with magic = ceil(2^32 / d)
+__device__ __forceinline__ int fast_div16(int r, uint32_t magic) { return static_cast<int>(__umulhi(static_cast<uint32_t>(r), magic)); }
 
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
@@ -255,9 +263,46 @@ __device__ __forceinline__ void slab_epi_chunk(const EpiCtx& c, const uint32_t (
   }
 }
 
-constexpr int SLAB_THREADS = 352;   // warps 0-7 epilogue (two per TMEM lane quarter), 8 producer, 9 MMA, 10 TMEM alloc
+// The four bilinear taps (16 bytes = 8 channels each) and weights of slab pixel r of the up-sampled half.
+struct UpTaps {
+  uint4 qa, qb, qc, qd;
+  float w00, w01, w10, w11;
+  bool in;
+};
 
-__global__ void __launch_bounds__(SLAB_THREADS, 1) conv_slab_kernel(const __grid_constant__ SlabKParams p) {
+__device__ __forceinline__ UpTaps up_fetch(const SlabKParams& p, int r, int iy0, int ix0, int n, int ch) {
+  UpTaps t;
+  const int sy = fast_div16(r, p.slab_w_magic), sx = r - sy * p.slab_w;
+  const int iy = iy0 + sy, ix = ix0 + sx;
+  const int uy = iy - p.up_offy, ux = ix - p.up_offx;
+  t.in = static_cast<unsigned>(iy) < static_cast<unsigned>(p.OH) && static_cast<unsigned>(ix) < static_cast<unsigned>(p.OW) &&
+         static_cast<unsigned>(uy) < static_cast<unsigned>(p.up_UH) && static_cast<unsigned>(ux) < static_cast<unsigned>(p.up_UW);
+  if (t.in) {
+    const float fy = p.up_sy * uy, fx = p.up_sx * ux;
+    const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+    const int y1 = y0 + (y0 < p.up_H - 1 ? 1 : 0), x1 = x0 + (x0 < p.up_W - 1 ? 1 : 0);
+    const float ly1 = fy - y0, ly0 = 1.f - ly1, lx1 = fx - x0, lx0 = 1.f - lx1;
+    t.w00 = ly0 * lx0; t.w01 = ly0 * lx1; t.w10 = ly1 * lx0; t.w11 = ly1 * lx1;
+    const long long rb0 = (static_cast<long long>(n) * p.up_Hp + y0 + p.up_ph) * p.up_Wp + p.up_pw;
+    const long long rb1 = (static_cast<long long>(n) * p.up_Hp + y1 + p.up_ph) * p.up_Wp + p.up_pw;
+    t.qa = __ldg(reinterpret_cast<const uint4*>(p.up + (rb0 + x0) * p.up_ld + ch));
+    t.qb = __ldg(reinterpret_cast<const uint4*>(p.up + (rb0 + x1) * p.up_ld + ch));
+    t.qc = __ldg(reinterpret_cast<const uint4*>(p.up + (rb1 + x0) * p.up_ld + ch));
+    t.qd = __ldg(reinterpret_cast<const uint4*>(p.up + (rb1 + x1) * p.up_ld + ch));
+  }
+  return t;
+}
+
+constexpr int SLAB_THREADS = 352;      // warps 0-7 epilogue (two per TMEM lane quarter), 8 producer, 9 MMA, 10 TMEM alloc
+constexpr int SLAB_THREADS_UP = 480;   // + warps 11-14: up-sampling slab producers
+
+// HAS_UP: the input is the concatenation [skip | upsample2x(low-res)] of Up.forward (unet_parts.py:57-67) and the
+// up-sampled half is never materialised: for its channel blocks four producer warps interpolate the low-res
+// tensor (bilinear, align_corners=True, F.pad offsets) straight into the swizzled slab the TMA would have
+// filled.  Same arithmetic as upsample2x_kernel (ops.cu), so fused == unfused bit for bit.
+template <bool HAS_UP>
+__global__ void __launch_bounds__(HAS_UP ? SLAB_THREADS_UP : SLAB_THREADS, 1)
+conv_slab_kernel(const __grid_constant__ SlabKParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // round up inside the shared window (pointer arithmetic on the symbol keeps the shared address space,
   // so bias / OutConv weights are read with LDS instead of generic loads)
@@ -286,7 +331,7 @@ __global__ void __launch_bounds__(SLAB_THREADS, 1) conv_slab_kernel(const __grid
   }
   if (warp == 9 && lane == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(full + s, 1);
+      mbar_init(full + s, HAS_UP ? 1 + 4 : 1);
       mbar_init(empty + s, 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -342,11 +387,15 @@ __global__ void __launch_bounds__(SLAB_THREADS, 1) conv_slab_kernel(const __grid
         for (int ks = 0; ks < p.k_stages; ++ks) {
           const int kt = ks / p.cb_n, cb = ks - kt * p.cb_n;   // K stage = (temporal tap, 64-channel block)
           mbar_wait(empty + s, ph ^ 1);
-          mbar_arrive_expect_tx(full + s, static_cast<uint32_t>(p.slab_bytes));
-          if (p.merged_cw)  // stems: (pixel, channel) merged into one contiguous inner dimension of 8-element pixels
-            tma_load_5d(smS + s * p.slab_stride, &p.tmA, full + s, cx * 8, cy, cz + kt * p.z_kstep, n, 0);
-          else
-            tma_load_5d(smS + s * p.slab_stride, &p.tmA, full + s, cb * p.c_step, cx, cy, cz + kt * p.z_kstep, n);
+          if (HAS_UP && cb >= p.up_cb_first) {
+            mbar_arrive(full + s);   // this slab is written by the up-sampling warps
+          } else {
+            mbar_arrive_expect_tx(full + s, static_cast<uint32_t>(p.slab_bytes));
+            if (p.merged_cw)  // stems: (pixel, channel) merged into one contiguous inner dimension of 8-element pixels
+              tma_load_5d(smS + s * p.slab_stride, &p.tmA, full + s, cx * 8, cy, cz + kt * p.z_kstep, n, 0);
+            else
+              tma_load_5d(smS + s * p.slab_stride, &p.tmA, full + s, cb * p.c_step, cx, cy, cz + kt * p.z_kstep, n);
+          }
           if (++s == S) { s = 0; ph ^= 1; }
           if (p.b_stream) {
             // one [n_tile x 64] weight block per filter tap, K ordered (kd,kh,kw,cin): tap kt*n_grp+g, block cb
@@ -414,16 +463,25 @@ __global__ void __launch_bounds__(SLAB_THREADS, 1) conv_slab_kernel(const __grid
       mbar_wait(tfull + as, aph);
       tc_fence_after();
       // software pipeline over this warp's chunks: the next chunk's TMEM load is in flight while one is processed
-      uint32_t va[32], vb[32];
-      if (nch > 0) tmem_ld32(t_row, va);
-      for (int i = 0; i < nch; i += 2) {
-        tmem_ld_wait();
-        if (i + 1 < nch) tmem_ld32(t_row + (i + 1) * c_step, vb);
-        slab_epi_chunk(c, va, n0 + c_first + i * c_step, valid, pix, pool_writer, ppix, oc);
-        if (i + 1 < nch) {
+      if (HAS_UP) {   // 480-thread variant: 136 registers per thread, one chunk in flight
+        uint32_t va[32];
+        for (int i = 0; i < nch; ++i) {
+          tmem_ld32(t_row + i * c_step, va);
           tmem_ld_wait();
-          if (i + 2 < nch) tmem_ld32(t_row + (i + 2) * c_step, va);
-          slab_epi_chunk(c, vb, n0 + c_first + (i + 1) * c_step, valid, pix, pool_writer, ppix, oc);
+          slab_epi_chunk(c, va, n0 + c_first + i * c_step, valid, pix, pool_writer, ppix, oc);
+        }
+      } else {
+        uint32_t va[32], vb[32];
+        if (nch > 0) tmem_ld32(t_row, va);
+        for (int i = 0; i < nch; i += 2) {
+          tmem_ld_wait();
+          if (i + 1 < nch) tmem_ld32(t_row + (i + 1) * c_step, vb);
+          slab_epi_chunk(c, va, n0 + c_first + i * c_step, valid, pix, pool_writer, ppix, oc);
+          if (i + 1 < nch) {
+            tmem_ld_wait();
+            if (i + 2 < nch) tmem_ld32(t_row + (i + 2) * c_step, va);
+            slab_epi_chunk(c, vb, n0 + c_first + (i + 1) * c_step, valid, pix, pool_writer, ppix, oc);
+          }
         }
       }
       // all TMEM reads of this accumulator are complete (wait::ld above): hand it back to the MMA warp
@@ -442,6 +500,61 @@ __global__ void __launch_bounds__(SLAB_THREADS, 1) conv_slab_kernel(const __grid
       }
       as ^= 1;
       if (as == 0) aph ^= 1;
+    }
+  }
+
+  if (HAS_UP && warp >= 11) {
+    // -------------------------------------------------- up-sampling slab producers (warps 11-14)
+    // thread -> one 16-byte channel chunk (8 channels) of 16 slab pixels per pass; the slab row of pixel r is
+    // r*128 bytes with the SWIZZLE_128B chunk permutation the TMA would have applied.
+    const int it = static_cast<int>(threadIdx.x) - 11 * 32;
+    const int c8 = it & 7, p0 = it >> 3;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      int t = tile;
+      t /= p.num_n_tiles;
+      const int tx = t % p.tiles_x; t /= p.tiles_x;
+      const int ty = t % p.tiles_y; t /= p.tiles_y;
+      const int n = t / p.tiles_z;
+      const int iy0 = ty * p.y_step - 1, ix0 = tx * p.x_step - 1;   // image coordinates of slab pixel (0,0)
+      for (int ks = 0; ks < p.k_stages; ++ks) {
+        const int cb = ks % p.cb_n;
+        mbar_wait(empty + s, ph ^ 1);
+        if (cb >= p.up_cb_first) {
+          uint8_t* slab = smS + s * p.slab_stride;
+          const int ch = (cb - p.up_cb_first) * 64 + c8 * 8 + p.up_coff;
+          // software pipeline: the four taps of pixel r+16 are in flight while pixel r is interpolated
+          UpTaps cur = up_fetch(p, p0, iy0, ix0, n, ch);
+          for (int r = p0; r < p.slab_px; r += 16) {
+            const UpTaps nxt = (r + 16 < p.slab_px) ? up_fetch(p, r + 16, iy0, ix0, n, ch) : cur;
+            uint4 out = make_uint4(0u, 0u, 0u, 0u);
+            if (cur.in) {
+              const uint32_t* pa = reinterpret_cast<const uint32_t*>(&cur.qa);
+              const uint32_t* pb = reinterpret_cast<const uint32_t*>(&cur.qb);
+              const uint32_t* pc = reinterpret_cast<const uint32_t*>(&cur.qc);
+              const uint32_t* pd = reinterpret_cast<const uint32_t*>(&cur.qd);
+              uint32_t* po = reinterpret_cast<uint32_t*>(&out);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float a0 = __uint_as_float(pa[i] << 16), a1 = __uint_as_float(pa[i] & 0xffff0000u);
+                const float b0 = __uint_as_float(pb[i] << 16), b1 = __uint_as_float(pb[i] & 0xffff0000u);
+                const float c0 = __uint_as_float(pc[i] << 16), c1 = __uint_as_float(pc[i] & 0xffff0000u);
+                const float d0 = __uint_as_float(pd[i] << 16), d1 = __uint_as_float(pd[i] & 0xffff0000u);
+                const float o0 = fmaf(cur.w11, d0, fmaf(cur.w10, c0, fmaf(cur.w01, b0, cur.w00 * a0)));
+                const float o1 = fmaf(cur.w11, d1, fmaf(cur.w10, c1, fmaf(cur.w01, b1, cur.w00 * a1)));
+                po[i] = cvt_bf16x2(o0, o1, false);
+              }
+            }
+            *reinterpret_cast<uint4*>(slab + r * 128 + ((c8 ^ (r & 7)) << 4)) = out;
+            cur = nxt;
+          }
+          fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full + s);
+        if (++s == S) { s = 0; ph ^= 1; }
+      }
     }
   }
 
@@ -533,6 +646,17 @@ static int make_plan(const tedspad_conv_slab& c, tedspad_slab_plan& P) {
   }
   const int Wp = x.W + 2 * x.pw, Hp = x.H + 2 * x.ph, Dp = x.D + 2 * x.pd;
   int slab_w = 0, slab_h = 0, pad_bytes = 0;
+  // fused up-sampling: the convolution sees [x | upsample2x(up)] along the channels
+  const bool has_up = c.up.ptr != nullptr;
+  if (has_up) {
+    TSP_CHECK(c.kind == TEDSPAD_SLAB_3X3 || c.kind == TEDSPAD_SLAB_3X3_STREAM, "slab: fused up-sampling needs a 3x3 kind");
+    TSP_CHECK(c.up.C % 64 == 0 && c.up.C >= 64 && c.up.N == x.N && c.up.D == 1 && x.D == 1 && c.kd == 1 &&
+                  2 * c.up.H <= x.H && 2 * c.up.W <= x.W,
+              "slab: up-sampling source [%d,%d,%d,%d] does not fit the [%d,%d,%d] input", c.up.N, c.up.H, c.up.W, c.up.C,
+              x.N, x.H, x.W);
+  }
+  const int cin_total = x.C + (has_up ? c.up.C : 0);
+  P.up_cb_first = has_up ? x.C / 64 : 1 << 20;
   if (c.kind == TEDSPAD_SLAB_3X3 || c.kind == TEDSPAD_SLAB_STEM2D) {
     TSP_CHECK(c.kd == 1 && c.kh == 3 && c.kw == 3 && c.sd == 1 && c.sh == 1 && c.sw == 1 && c.pd == 0 && c.ph == 1 &&
                   c.pw == 1,
@@ -545,9 +669,9 @@ static int make_plan(const tedspad_conv_slab& c, tedspad_slab_plan& P) {
     } else {
       TSP_CHECK(x.C == 8, "slab stem2d: x.C=%d must be 8 (channels padded to one 16-byte pixel)", x.C);
     }
-    P.w_bytes = static_cast<int>(slab_image_bytes(c.kind, P.n_tile, x.C, 1, 3, 3));
+    P.w_bytes = static_cast<int>(slab_image_bytes(c.kind, P.n_tile, sw ? cin_total : x.C, 1, 3, 3));
     P.swizzle128 = sw ? 1 : 0;
-    P.k_stages = sw ? x.C / 64 : 1;
+    P.k_stages = sw ? cin_total / 64 : 1;
     P.cb_n = P.k_stages;
     P.n_grp = sw ? 9 : 3;     // filter taps (3x3) / filter rows (stem)
     P.nk = sw ? 4 : 2;        // K=16 steps per group
@@ -599,7 +723,7 @@ static int make_plan(const tedspad_conv_slab& c, tedspad_slab_plan& P) {
       P.a_layout = 2; P.a_lbo = 16; P.a_sbo = slab_w * 128;
       P.b_layout = 2; P.b_lbo = 16; P.b_sbo = 1024;
       P.a_kstep = 32; P.b_kstep = 32;
-      const int cb_n = x.C / 64;
+      const int cb_n = cin_total / 64;
       for (int cb = 0; cb < cb_n; ++cb)
         for (int tap = 0; tap < 9; ++tap) {
           const int i = cb * 9 + tap;
@@ -622,11 +746,11 @@ static int make_plan(const tedspad_conv_slab& c, tedspad_slab_plan& P) {
               "slab stream: needs a (1|3,3,3) stride-1 same-padded convolution");
     TSP_CHECK(x.D == y.D && x.H == y.H && x.W == y.W, "slab: output extents must equal input extents");
     TSP_CHECK(x.C % 64 == 0 && x.C >= 64, "slab stream: x.C=%d must be a multiple of 64", x.C);
-    TSP_CHECK(c.K_pad == c.kd * 9 * x.C, "slab stream: K_pad=%d != %d taps x %d channels", c.K_pad, c.kd * 9, x.C);
+    TSP_CHECK(c.K_pad == c.kd * 9 * cin_total, "slab stream: K_pad=%d != %d taps x %d channels", c.K_pad, c.kd * 9, cin_total);
     TSP_CHECK(c.oc_w == nullptr, "slab stream: fused OutConv needs the resident-weight kind");
     P.swizzle128 = 1;
-    P.cb_n = x.C / 64;
-    P.cin = x.C;
+    P.cb_n = cin_total / 64;
+    P.cin = cin_total;
     P.k_stages = c.kd * P.cb_n;
     P.n_grp = 9; P.nk = 4; P.n_mma = 36;
     P.tab_per_stage = 0;      // the 9 tap offsets are the same for every K stage
@@ -852,9 +976,30 @@ extern "C" int tedspad_conv_slab_forward(const tedspad_conv_slab* c, void* strea
     p.oc_frames = c->oc_frames;
   }
 
+  const bool has_up = c->up.ptr != nullptr;
+  if (has_up) {
+    const tedspad_tensor& u = c->up;
+    if (check_tensor(u, "slab.up", 8)) return 1;
+    p.up = reinterpret_cast<const __nv_bfloat16*>(u.ptr);
+    p.up_cb_first = P.up_cb_first;
+    p.up_H = u.H; p.up_W = u.W; p.up_Hp = u.H + 2 * u.ph; p.up_Wp = u.W + 2 * u.pw; p.up_ph = u.ph; p.up_pw = u.pw;
+    p.up_ld = u.ld; p.up_coff = u.coff;
+    // same geometry as tedspad_upsample2x: x2 bilinear, align_corners=True, centred with F.pad (unet_parts.py:50,57-63)
+    p.up_UH = 2 * u.H; p.up_UW = 2 * u.W;
+    p.up_offy = (x.H - p.up_UH) / 2; p.up_offx = (x.W - p.up_UW) / 2;
+    p.up_sy = p.up_UH > 1 ? static_cast<float>(u.H - 1) / static_cast<float>(p.up_UH - 1) : 0.f;
+    p.up_sx = p.up_UW > 1 ? static_cast<float>(u.W - 1) / static_cast<float>(p.up_UW - 1) : 0.f;
+    p.slab_w = P.box[1]; p.slab_px = P.box[1] * P.box[2];
+    p.slab_w_magic = static_cast<uint32_t>((0x100000000ULL + p.slab_w - 1) / p.slab_w);
+  } else {
+    p.up_cb_first = 1 << 20;
+  }
+
   int rc = 0;
   std::call_once(g_slab_attr_once, [&] {
-    cudaError_t e = cudaFuncSetAttribute(conv_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SLAB_SMEM_BUDGET);
+    cudaError_t e = cudaFuncSetAttribute(conv_slab_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SLAB_SMEM_BUDGET);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_slab_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SLAB_SMEM_BUDGET);
     if (e != cudaSuccess) {
       set_error("cudaFuncSetAttribute(slab smem) failed: %s", cudaGetErrorString(e));
       rc = 2;
@@ -863,7 +1008,10 @@ extern "C" int tedspad_conv_slab_forward(const tedspad_conv_slab* c, void* strea
   if (rc) return rc;
   int ctas = c->max_ctas > 0 ? c->max_ctas : num_sms();
   ctas = std::max(1, std::min(ctas, p.total_tiles));
-  conv_slab_kernel<<<ctas, SLAB_THREADS, P.smem_bytes, reinterpret_cast<cudaStream_t>(stream_v)>>>(p);
+  if (has_up)
+    conv_slab_kernel<true><<<ctas, SLAB_THREADS_UP, P.smem_bytes, reinterpret_cast<cudaStream_t>(stream_v)>>>(p);
+  else
+    conv_slab_kernel<false><<<ctas, SLAB_THREADS, P.smem_bytes, reinterpret_cast<cudaStream_t>(stream_v)>>>(p);
   TSP_CUDA(cudaGetLastError());
   return 0;
 }

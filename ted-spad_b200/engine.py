@@ -20,6 +20,12 @@ USE_SLAB = os.environ.get("TEDSPAD_SLAB", "1") != "0"
 USE_SLAB_STEM3D = USE_SLAB and os.environ.get("TEDSPAD_SLAB_STEM3D", "1") != "0"
 SLAB_WEIGHT_LIMIT = 150 * 1024   # bytes of resident weights that still leave room for three slab stages
 ENC_IN_CHANNELS = 4 if USE_SLAB_STEM3D else 8   # channel padding of the encoder input clip
+# Up.forward inside the convolution: decoder levels (1 = deepest, up1) whose up-sampled input is interpolated by the
+# conv's slab producers instead of being materialised by tedspad_upsample2x.  Bit-identical to the two-kernel path
+# (tests/gpu_diag.py slabup) but MEASURED SLOWER on B200 at every level (905 clips/s unfused; 890 / 881 / 845 / 751
+# with levels 1 / 1-2 / 1-3 / 1-4 fused): the interpolation competes with the epilogue warps for issue slots while the
+# stand-alone kernel already runs at the HBM write ceiling.  Off by default; kept as an option for narrower batches.
+FUSE_UPSAMPLE_LEVELS = tuple(int(v) for v in os.environ.get("TEDSPAD_FUSE_UPSAMPLE", "").split(",") if v) if USE_SLAB else ()
 
 
 def slab3x3(pc, max_stream_cout=512):
@@ -177,12 +183,17 @@ class UNetExecutor:
         for j in range(4):
             lvl = 3 - j
             cat = cats[lvl]
-            ops.upsample2x(cur, cat.slice(ch[lvl], cur.C))
             prefix = f"up{j + 1}.conv.double_conv"
             (a, b), (sa, sb) = self.convs[prefix], self.slabs[prefix]
             h, w = sizes[lvl]
             t = g(f"u{j}a", N, 1, h, w, a.cout, hl)
-            self._conv(cat, a, sa, t)
+            if sa is not None and (j + 1) in FUSE_UPSAMPLE_LEVELS and cur.C % 64 == 0:
+                # Up.forward (unet_parts.py:57-67): the up-sampled half of the concatenation is interpolated inside
+                # the convolution's slab producers and never materialised
+                ops.conv_slab_forward(cat.slice(0, ch[lvl]), sa, t, up=cur)
+            else:
+                ops.upsample2x(cur, cat.slice(ch[lvl], cur.C))
+                self._conv(cat, a, sa, t)
             if j == 3 and sb is not None and enc_in.W % 8 == 0 and enc_in.C in (4, 8):
                 # OutConv 1x1 + sigmoid (unet_parts.py:71-77, unet_model.py:36-37) in the last epilogue: the 64-channel
                 # tensor is never written; planar images then go through the raw-reshape glue (dali_extraction.py:173)
@@ -273,16 +284,25 @@ class I3DExecutor:
     def _mixed(self, name, x, oc):
         total = oc[0] + oc[2] + oc[4] + oc[5]
         y = self.bufs.get(name, x.N, x.D, x.H, x.W, total)
-        self._unit(f"{name}.b0", x, out=y.slice(0, oc[0]))
         # b1a's output is stored with the channel padding b1b's feed wants (pad channels zero, never written)
         c1 = self.specs[f"{name}.b1b"][4] or oc[1]
         t1 = self.bufs.get(f"{name}.b1a", x.N, x.D, x.H, x.W, c1, zero=True)
-        self._unit(f"{name}.b1a", x, out=t1.slice(0, oc[1]))
-        self._unit(f"{name}.b1b", t1, out=y.slice(oc[0], oc[2]))
-        t2 = self._unit(f"{name}.b2a", x, oc[3])
-        self._unit(f"{name}.b2b", t2, out=y.slice(oc[0] + oc[2], oc[4]))
-        t3 = self._pool(f"{name}.b3a", x, (3, 3, 3), (1, 1, 1))
-        self._unit(f"{name}.b3b", t3, out=y.slice(oc[0] + oc[2] + oc[4], oc[5]))
+
+        def b1():
+            self._unit(f"{name}.b1a", x, out=t1.slice(0, oc[1]))
+            self._unit(f"{name}.b1b", t1, out=y.slice(oc[0], oc[2]))
+
+        def b2():
+            t2 = self._unit(f"{name}.b2a", x, oc[3])
+            self._unit(f"{name}.b2b", t2, out=y.slice(oc[0] + oc[2], oc[4]))
+
+        def b3():
+            t3 = self._pool(f"{name}.b3a", x, (3, 3, 3), (1, 1, 1))
+            self._unit(f"{name}.b3b", t3, out=y.slice(oc[0] + oc[2] + oc[4], oc[5]))
+
+        # (running the four branches on side streams was measured on B200: no gain, the step is not latency-bound)
+        self._unit(f"{name}.b0", x, out=y.slice(0, oc[0]))
+        b1(); b2(); b3()
         return y
 
     def run_trunk(self, enc_in):

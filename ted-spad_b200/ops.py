@@ -14,11 +14,31 @@ BF16 = torch.bfloat16
 
 LAUNCHES = 0        # kernels launched through this module (bench.py reports it as gpu_launches)
 CONV_EVENTS = None  # when a list: one (start, end) CUDA event pair is appended per conv launch (bench.py roofline)
+OP_EVENTS = None    # when a list: (start, end, name) per non-convolution launch (tests/profile_step.py)
 
 
 def _count():
     global LAUNCHES
     LAUNCHES += 1
+
+
+class _timed:
+    """with _timed("maxpool"): ...  records a CUDA event pair on the current stream when OP_EVENTS is a list."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if OP_EVENTS is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if OP_EVENTS is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            OP_EVENTS.append((self.e0, e1, self.name))
+        return False
 
 
 def _stream():
@@ -189,7 +209,7 @@ class PackedSlabConv:
             L.check(L.lib().tedspad_conv_slab_pack(*args, self.image.data_ptr(), C.byref(nbytes), _stream()),
                     "tedspad_conv_slab_pack")
 
-    def desc(self, x, y, act=L.ACT_RELU, pool=None, outconv=None, tm=0, max_ctas=0):
+    def desc(self, x, y, act=L.ACT_RELU, pool=None, outconv=None, tm=0, max_ctas=0, up=None):
         """outconv = (w fp32 [3,Cout], b fp32 [3], planes bf16 [N,3,H,W], frames fp32 [N,3,H,W] | None)"""
         pc = self.pc
         d = L.ConvSlabDesc()
@@ -202,6 +222,8 @@ class PackedSlabConv:
         d.bias = self.bias.data_ptr()
         if pool is not None:
             d.pool = pool.desc()
+        if up is not None:
+            d.up = up.desc()
         if outconv is not None:
             w, b, planes, frames = outconv
             d.oc_w, d.oc_b, d.oc_planes = w.data_ptr(), b.data_ptr(), planes.data_ptr()
@@ -222,10 +244,10 @@ class PackedSlabConv:
         return plan
 
 
-def conv_slab_forward(x, psc, y, act=L.ACT_RELU, pool=None, outconv=None, tm=0, max_ctas=0):
-    """y = act(conv(x) + bias) through the SLAB feed; optional fused MaxPool2d(2) -> pool and
-    OutConv 1x1 + sigmoid -> planar images (y may then be None)."""
-    d = psc.desc(x, y, act=act, pool=pool, outconv=outconv, tm=tm, max_ctas=max_ctas)
+def conv_slab_forward(x, psc, y, act=L.ACT_RELU, pool=None, outconv=None, tm=0, max_ctas=0, up=None):
+    """y = act(conv(x) + bias) through the SLAB feed; optional fused MaxPool2d(2) -> pool, OutConv 1x1 + sigmoid
+    -> planar images (y may then be None), and fused Up.forward input: conv([x | upsample2x(up)])."""
+    d = psc.desc(x, y, act=act, pool=pool, outconv=outconv, tm=tm, max_ctas=max_ctas, up=up)
     _count()
     if CONV_EVENTS is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -246,22 +268,25 @@ def planes_to_clip(planes, y, T):
     assert planes.dtype == BF16 and planes.is_contiguous()
     yd = y.desc()
     _count()
-    L.check(L.lib().tedspad_planes_to_clip(planes.data_ptr(), C.byref(yd), int(T), _stream()), "tedspad_planes_to_clip")
+    with _timed("planes_to_clip"):
+        L.check(L.lib().tedspad_planes_to_clip(planes.data_ptr(), C.byref(yd), int(T), _stream()), "tedspad_planes_to_clip")
     return y
 
 
 def maxpool(x, y, k, s, pad_front=(0, 0, 0), zero_pad=False):
     xd, yd = x.desc(), y.desc()
     _count()
-    L.check(L.lib().tedspad_maxpool(C.byref(xd), C.byref(yd), *k, *s, *pad_front, int(zero_pad), _stream()),
-            "tedspad_maxpool")
+    with _timed("maxpool"):
+        L.check(L.lib().tedspad_maxpool(C.byref(xd), C.byref(yd), *k, *s, *pad_front, int(zero_pad), _stream()),
+                "tedspad_maxpool")
     return y
 
 
 def upsample2x(x, y):
     xd, yd = x.desc(), y.desc()
     _count()
-    L.check(L.lib().tedspad_upsample2x(C.byref(xd), C.byref(yd), _stream()), "tedspad_upsample2x")
+    with _timed("upsample2x"):
+        L.check(L.lib().tedspad_upsample2x(C.byref(xd), C.byref(yd), _stream()), "tedspad_upsample2x")
     return y
 
 
@@ -270,8 +295,9 @@ def outconv_sigmoid(x, w, b, y, T, frames_out=None):
     xd, yd = x.desc(), y.desc()
     fo = frames_out.data_ptr() if frames_out is not None else None
     _count()
-    L.check(L.lib().tedspad_outconv_sigmoid(C.byref(xd), w.data_ptr(), b.data_ptr(), C.byref(yd), int(T), fo,
-                                            _stream()), "tedspad_outconv_sigmoid")
+    with _timed("outconv"):
+        L.check(L.lib().tedspad_outconv_sigmoid(C.byref(xd), w.data_ptr(), b.data_ptr(), C.byref(yd), int(T), fo,
+                                                _stream()), "tedspad_outconv_sigmoid")
     return y
 
 
@@ -280,8 +306,9 @@ def avgpool_features(x, kd=0):
     out = torch.empty((x.N, od, x.C), device=x.buf.device, dtype=torch.float32)
     xd = x.desc()
     _count()
-    L.check(L.lib().tedspad_avgpool_features(C.byref(xd), int(kd), out.data_ptr(), _stream()),
-            "tedspad_avgpool_features")
+    with _timed("avgpool"):
+        L.check(L.lib().tedspad_avgpool_features(C.byref(xd), int(kd), out.data_ptr(), _stream()),
+                "tedspad_avgpool_features")
     return out
 
 
@@ -295,9 +322,10 @@ def preprocess(frames_u8, desc_i32, crop_hw, y, resample=L.RESAMPLE_AA_FLOAT, fr
     yd = y.desc()
     fo = frames_f32.data_ptr() if frames_f32 is not None else None
     _count()
-    L.check(L.lib().tedspad_preprocess(frames_u8.data_ptr(), F_, Hs, Ws, desc_i32.data_ptr(), desc_i32.shape[0],
-                                       int(crop_hw[0]), int(crop_hw[1]), C.byref(yd), int(resample), fo, _stream()),
-            "tedspad_preprocess")
+    with _timed("preprocess"):
+        L.check(L.lib().tedspad_preprocess(frames_u8.data_ptr(), F_, Hs, Ws, desc_i32.data_ptr(), desc_i32.shape[0],
+                                           int(crop_hw[0]), int(crop_hw[1]), C.byref(yd), int(resample), fo, _stream()),
+                "tedspad_preprocess")
     return y
 
 

@@ -98,10 +98,17 @@ def _gather_acc(x, pc, out_shape):
     return acc.reshape(N, OD, OH, OW, pc.cout)
 
 
-def conv_slab_forward(x, psc, y, act=L.ACT_RELU, pool=None, outconv=None, tm=0, max_ctas=0):
+def conv_slab_forward(x, psc, y, act=L.ACT_RELU, pool=None, outconv=None, tm=0, max_ctas=0, up=None):
     """SLAB feed (csrc/conv_slab.cu): same arithmetic as the gather restatement; the fused MaxPool2d(2) pools the
-    ROUNDED output (as the kernel does), the fused OutConv consumes the un-rounded fp32 activations."""
+    ROUNDED output (as the kernel does), the fused OutConv consumes the un-rounded fp32 activations; with `up` the
+    convolution input is [x | upsample2x(up)] (the up-sampled half rounded to the storage dtype, as the kernel does)."""
     pc = psc.pc
+    if up is not None:
+        from tedspad_b200.ops import CLTensor
+        cat = CLTensor(x.N, x.D, x.H, x.W, x.C + up.C, device="cpu", dtype=x.buf.dtype)
+        cat.interior()[..., :x.C] = x.interior()
+        upsample2x(up, cat.slice(x.C, up.C))
+        x = cat
     shape = (y.N, y.D, y.H, y.W) if y is not None else (x.N, x.D, x.H, x.W)
     acc = _act(_gather_acc(x, pc, shape), act)
     store_dtype = y.buf.dtype if y is not None else (pool.buf.dtype if pool is not None else torch.float32)

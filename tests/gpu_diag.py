@@ -498,6 +498,54 @@ def group_slabstream():
     run_slab_case("R12 512->512 two N tiles pool fused", K, 2, (1, 28, 28), 512, 512, 512, (1, 3, 3), halo=(0, 1, 1), pool=True)
 
 
+def run_up_case(name, kind, N, hw, c_skip, c_up, cout, up_hw=None, tm=0):
+    """conv([skip | upsample2x(low)]) fused (slab producers interpolate) vs the unfused pair of kernels (bit-exact)
+    and vs torch (F.interpolate align_corners=True + F.pad + cat + conv2d)."""
+    try:
+        g = torch.Generator(device="cpu").manual_seed(len(name))
+        H, W = hw
+        uh, uw = up_hw or (H // 2, W // 2)
+        skip = torch.randn(N, c_skip, H, W, generator=g).to(DEV)
+        low = torch.randn(N, c_up, uh, uw, generator=g).to(DEV)
+        cin = c_skip + c_up
+        w = (torch.randn(cout, cin, 1, 3, 3, generator=g) / (9 * cin) ** 0.5).to(DEV)
+        b = (torch.rand(cout, generator=g) - 0.5).to(DEV)
+        pc = ops.PackedConv(w, b, None, pad_front=(0, 1, 1), cin_pad=cin, device=DEV, n_align=32)
+        psc = ops.PackedSlabConv(pc, kind)
+        cat = ops.CLTensor(N, 1, H, W, cin, (0, 1, 1), device=DEV)
+        cat.slice(0, c_skip).interior()[...] = skip.unsqueeze(2).permute(0, 2, 3, 4, 1).to(torch.bfloat16)
+        cat.slice(c_skip, c_up).interior()[...] = 9.0   # must never be read by the fused path
+        lowc = ops.CLTensor.from_ncdhw(low, halo=(0, 1, 1))
+        y1 = ops.CLTensor(N, 1, H, W, cout, (0, 1, 1), device=DEV)
+        ops.conv_slab_forward(cat.slice(0, c_skip), psc, y1, up=lowc, tm=tm)
+        # unfused: materialise the up-sampled half, then the same convolution over the full concat buffer
+        ops.upsample2x(lowc, cat.slice(c_skip, c_up))
+        y2 = ops.CLTensor(N, 1, H, W, cout, (0, 1, 1), device=DEV)
+        ops.conv_slab_forward(cat, psc, y2, tm=tm)
+        torch.cuda.synchronize()
+        same = bool(torch.equal(y1.buf, y2.buf))
+        RESULTS.append((name + ":fused==unfused", same))
+        print(f"[{'PASS' if same else 'FAIL'}] {name}: fused == unfused bit for bit")
+        up = F.interpolate(bf(low), scale_factor=2, mode="bilinear", align_corners=True).to(torch.bfloat16).float()
+        dy, dx = H - up.shape[2], W - up.shape[3]
+        up = F.pad(up, [dx // 2, dx - dx // 2, dy // 2, dy - dy // 2])
+        wq = pc.w[:cout, :9 * cin].float().reshape(cout, 3, 3, cin).permute(0, 3, 1, 2)
+        ref = torch.relu(F.conv2d(torch.cat([bf(skip), up], 1), wq.contiguous(), pc.bias[:cout], padding=1)).unsqueeze(2)
+        report(name, y1.to_ncdhw(), ref)
+    except Exception:
+        RESULTS.append((name, False))
+        print(f"[FAIL] {name}: EXCEPTION\n{traceback.format_exc()}", flush=True)
+
+
+def group_slabup():
+    run_up_case("U1 up4.0 shape 64|64->64 resident 32x48", L.SLAB_3X3, 2, (32, 48), 64, 64, 64)
+    run_up_case("U2 resident tm1 odd 21x27 (F.pad)", L.SLAB_3X3, 2, (21, 27), 64, 64, 64, up_hw=(10, 13), tm=1)
+    run_up_case("U3 up3.0 shape 128|128->128 stream 28x28", L.SLAB_3X3_STREAM, 3, (28, 28), 128, 128, 128)
+    run_up_case("U4 up1.0 shape 512|512->512 stream 28x28 (2 N tiles)", L.SLAB_3X3_STREAM, 2, (28, 28), 512, 512, 512)
+    run_up_case("U5 stream 256|256->256 56x56 x4", L.SLAB_3X3_STREAM, 4, (56, 56), 256, 256, 256)
+    run_up_case("U6 resident 64|64->64 112x112 x8 many tiles", L.SLAB_3X3, 8, (112, 112), 64, 64, 64)
+
+
 def group_slabstem():
     run_slab_case("T1 stem2d 3(8)->64 20x20 tm2", L.SLAB_STEM2D, 2, (1, 20, 20), 3, 8, 64, (1, 3, 3), tm=2, out_halo=(0, 1, 1))
     run_slab_case("T2 stem2d tm1 40x24", L.SLAB_STEM2D, 3, (1, 40, 24), 3, 8, 64, (1, 3, 3), tm=1, out_halo=(0, 1, 1))

@@ -26,6 +26,7 @@ for _ in range(2):
     ext.features_of_clips(frames, desc, (ch, cw))
 torch.cuda.synchronize()
 ops.CONV_EVENTS = []
+ops.OP_EVENTS = []
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 torch.cuda.profiler.start()          # ncu --profile-from-start off captures exactly this steady-state step
 e0.record()
@@ -43,3 +44,14 @@ conv = sum(r[0] for r in rows)
 print(f"step {tot:.2f} ms, conv {conv:.2f} ms over {len(rows)} launches, B={B}")
 for ms, gf, name in rows:
     print(f"{ms:8.3f} ms {gf / ms:8.1f} TFLOP/s  {gf:9.1f} GF  {name}")
+from collections import defaultdict
+agg = defaultdict(lambda: [0, 0.0])
+for a, b, name in ops.OP_EVENTS:
+    agg[name][0] += 1
+    agg[name][1] += a.elapsed_time(b)
+print("non-convolution launches (CUDA events, in-step):")
+for name, (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+    print(f"{ms:8.3f} ms  n={n:3d}  {name}")
+for a, b, name in ops.OP_EVENTS:
+    if name in ("upsample2x", "maxpool"):
+        print(f"   {a.elapsed_time(b):7.3f} ms {name}")
