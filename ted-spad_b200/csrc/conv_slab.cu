@@ -266,7 +266,7 @@ __device__ __forceinline__ void slab_epi_chunk(const EpiCtx& c, const uint32_t (
 // The four bilinear taps (16 bytes = 8 channels each) and weights of slab pixel r of the up-sampled half.
 struct UpTaps {
   uint4 qa, qb, qc, qd;
-  float w00, w01, w10, w11;
+  float lx0, lx1, ly0, ly1;
   bool in;
 };
 
@@ -281,8 +281,7 @@ __device__ __forceinline__ UpTaps up_fetch(const SlabKParams& p, int r, int iy0,
     const float fy = p.up_sy * uy, fx = p.up_sx * ux;
     const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
     const int y1 = y0 + (y0 < p.up_H - 1 ? 1 : 0), x1 = x0 + (x0 < p.up_W - 1 ? 1 : 0);
-    const float ly1 = fy - y0, ly0 = 1.f - ly1, lx1 = fx - x0, lx0 = 1.f - lx1;
-    t.w00 = ly0 * lx0; t.w01 = ly0 * lx1; t.w10 = ly1 * lx0; t.w11 = ly1 * lx1;
+    t.ly1 = fy - y0; t.ly0 = 1.f - t.ly1; t.lx1 = fx - x0; t.lx0 = 1.f - t.lx1;
     const long long rb0 = (static_cast<long long>(n) * p.up_Hp + y0 + p.up_ph) * p.up_Wp + p.up_pw;
     const long long rb1 = (static_cast<long long>(n) * p.up_Hp + y1 + p.up_ph) * p.up_Wp + p.up_pw;
     t.qa = __ldg(reinterpret_cast<const uint4*>(p.up + (rb0 + x0) * p.up_ld + ch));
@@ -541,8 +540,9 @@ conv_slab_kernel(const __grid_constant__ SlabKParams p) {
                 const float b0 = __uint_as_float(pb[i] << 16), b1 = __uint_as_float(pb[i] & 0xffff0000u);
                 const float c0 = __uint_as_float(pc[i] << 16), c1 = __uint_as_float(pc[i] & 0xffff0000u);
                 const float d0 = __uint_as_float(pd[i] << 16), d1 = __uint_as_float(pd[i] & 0xffff0000u);
-                const float o0 = fmaf(cur.w11, d0, fmaf(cur.w10, c0, fmaf(cur.w01, b0, cur.w00 * a0)));
-                const float o1 = fmaf(cur.w11, d1, fmaf(cur.w10, c1, fmaf(cur.w01, b1, cur.w00 * a1)));
+                // separable form, the same operation order as upsample2x_kernel (ops.cu)
+                const float o0 = fmaf(cur.ly1, fmaf(cur.lx1, d0, cur.lx0 * c0), cur.ly0 * fmaf(cur.lx1, b0, cur.lx0 * a0));
+                const float o1 = fmaf(cur.ly1, fmaf(cur.lx1, d1, cur.lx0 * c1), cur.ly0 * fmaf(cur.lx1, b1, cur.lx0 * a1));
                 po[i] = cvt_bf16x2(o0, o1, false);
               }
             }

@@ -72,14 +72,21 @@ struct PoolP {
 };
 
 // One block per output row (n, od, oh): the row decode is done once per block, the threads walk the
-// (ow, 8-channel group) items of the row with 32-bit arithmetic only (the previous one-item-per-thread
-// version spent most of its time in 64-bit div/mod).
+// (ow, 8-channel group) items of the row with 32-bit arithmetic only.  KD/KH/KW > 0: compile-time window, so
+// the whole window's loads are issued before the first max (the runtime-window loop serialises on load latency:
+// 0.26 ms for the 27-tap Inception pool of Mixed_3b vs a 0.03 ms DRAM floor); 0 = runtime window (p.kd/kh/kw).
+__device__ __forceinline__ void max8(uint4& m, const uint4& q) {
+  m.x = hmax2_bf16(m.x, q.x); m.y = hmax2_bf16(m.y, q.y);
+  m.z = hmax2_bf16(m.z, q.z); m.w = hmax2_bf16(m.w, q.w);
+}
+
+template <int KD, int KH, int KW>
 __global__ void __launch_bounds__(256) maxpool_kernel(const PoolP p) {
+  const int kd = KD > 0 ? KD : p.kd, kh = KH > 0 ? KH : p.kh, kw = KW > 0 ? KW : p.kw;
   const int c8n = p.y.C >> 3;
   const int items = p.y.W * c8n;
-  // ROWS_PER_BLOCK consecutive output rows per block: the window rows they share are re-read from L1, not L2
-  for (long long rowi = blockIdx.x; rowi * ROWS_PER_BLOCK < p.total; rowi += gridDim.x)
-  for (long long row = rowi * ROWS_PER_BLOCK; row < min(p.total, (rowi + 1) * ROWS_PER_BLOCK); ++row) {
+  const uint4 neg = make_uint4(0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u);   // -inf pairs
+  for (long long row = blockIdx.x; row < p.total; row += gridDim.x) {
     int t = static_cast<int>(row);
     const int oh = t % p.y.H; t /= p.y.H;
     const int od = t % p.y.D;
@@ -90,32 +97,87 @@ __global__ void __launch_bounds__(256) maxpool_kernel(const PoolP p) {
     for (int it = threadIdx.x; it < items; it += blockDim.x) {
       const int ow = fast_div(it, p.c8_magic), c8 = it - ow * c8n;
       const int iw0 = ow * p.sw - p.pw;
-      // max on packed bf16 pairs (exact: max commutes with rounding); -inf = 0xff80
-      uint4 m = make_uint4(0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u);
+      // max on packed bf16 pairs (exact: max commutes with rounding)
+      uint4 m = neg;
       bool any_oob = false;
-      for (int a = 0; a < p.kd; ++a) {
+#pragma unroll
+      for (int a = 0; a < kd; ++a) {
         const int id = id0 + a;
         const bool okd = static_cast<unsigned>(id) < static_cast<unsigned>(p.x.D);
-        for (int b = 0; b < p.kh; ++b) {
+#pragma unroll
+        for (int b = 0; b < kh; ++b) {
           const int ih = ih0 + b;
           const bool okh = okd && static_cast<unsigned>(ih) < static_cast<unsigned>(p.x.H);
           const long long rowpix = okh ? pix_index(p.x, n, id, ih, 0) : 0;
-          for (int c = 0; c < p.kw; ++c) {
+#pragma unroll
+          for (int c = 0; c < kw; ++c) {
             const int iw = iw0 + c;
-            if (okh && static_cast<unsigned>(iw) < static_cast<unsigned>(p.x.W)) {
-              const uint4 q = __ldg(reinterpret_cast<const uint4*>(xn + (rowpix + iw) * p.x.ld + c8 * 8));
-              m.x = hmax2_bf16(m.x, q.x); m.y = hmax2_bf16(m.y, q.y);
-              m.z = hmax2_bf16(m.z, q.z); m.w = hmax2_bf16(m.w, q.w);
-            } else {
-              any_oob = true;
-            }
+            const bool ok = okh && static_cast<unsigned>(iw) < static_cast<unsigned>(p.x.W);
+            uint4 q = neg;
+            if (ok) q = __ldg(reinterpret_cast<const uint4*>(xn + (rowpix + iw) * p.x.ld + c8 * 8));
+            max8(m, q);
+            any_oob |= !ok;
           }
         }
       }
-      if (any_oob && p.zero_pad) {
-        m.x = hmax2_bf16(m.x, 0u); m.y = hmax2_bf16(m.y, 0u); m.z = hmax2_bf16(m.z, 0u); m.w = hmax2_bf16(m.w, 0u);
-      }
+      if (any_oob && p.zero_pad) max8(m, make_uint4(0u, 0u, 0u, 0u));
       *reinterpret_cast<uint4*>(yrow + static_cast<long long>(ow) * p.y.ld + c8 * 8) = m;
+    }
+  }
+}
+
+// (3,3,3) stride-1 pad-1 pooling (the Inception pool branch, i3d.py:138-139 through MaxPool3dSamePadding): one
+// thread per (n, od, oh, 8-channel group) walks its output row with a sliding window of three column maxima
+// (column = the 3x3 (d,h) taps at one w), i.e. 9 loads per output instead of 27.  The (d,h) bounds are per-thread
+// constants; consecutive threads own consecutive channel groups, so every load instruction is coalesced.
+__global__ void __launch_bounds__(256) maxpool333_s1_kernel(const PoolP p) {
+  const int c8n = p.y.C >> 3;
+  const long long total = p.total * c8n;
+  const uint4 neg = make_uint4(0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u);
+  const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+  const uint4 oob_col = p.zero_pad ? zero : neg;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c8 = static_cast<int>(idx % c8n);
+    int t = static_cast<int>(idx / c8n);
+    const int oh = t % p.y.H; t /= p.y.H;
+    const int od = t % p.y.D;
+    const int n = t / p.y.D;
+    const __nv_bfloat16* xn = reinterpret_cast<const __nv_bfloat16*>(p.x.ptr) + p.x.coff + c8 * 8;
+    const __nv_bfloat16* rp[9];
+    bool dh_oob = false;
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+        const int id = od - 1 + a, ih = oh - 1 + b;
+        const bool ok = static_cast<unsigned>(id) < static_cast<unsigned>(p.x.D) &&
+                        static_cast<unsigned>(ih) < static_cast<unsigned>(p.x.H);
+        rp[a * 3 + b] = ok ? xn + pix_index(p.x, n, id, ih, 0) * p.x.ld : nullptr;
+        dh_oob |= !ok;
+      }
+    const uint4 col_floor = (dh_oob && p.zero_pad) ? zero : neg;
+    auto column = [&](int iw) {
+      uint4 m = col_floor;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) {
+        uint4 q = neg;
+        if (rp[i] != nullptr) q = __ldg(reinterpret_cast<const uint4*>(rp[i] + static_cast<long long>(iw) * p.x.ld));
+        max8(m, q);
+      }
+      return m;
+    };
+    __nv_bfloat16* yrow = elem_ptr_w(p.y, pix_index(p.y, n, od, oh, 0), c8 * 8);
+    uint4 c0 = oob_col, c1 = column(0);
+#pragma unroll 2
+    for (int ow = 0; ow < p.y.W; ++ow) {
+      const uint4 c2 = ow + 1 < p.x.W ? column(ow + 1) : oob_col;
+      uint4 m = c0;
+      max8(m, c1);
+      max8(m, c2);
+      *reinterpret_cast<uint4*>(yrow + static_cast<long long>(ow) * p.y.ld) = m;
+      c0 = c1;
+      c1 = c2;
     }
   }
 }
@@ -126,56 +188,84 @@ struct UpP {
   int UH, UW, offy, offx;  // up-sampled size and F.pad offsets inside y
   float sy, sx;
   uint32_t c8_magic;
-  long long total;  // output rows N*H of y's interior
+  long long total;  // N * bands of UP_ROWS output rows
 };
 
-// One block per output row (n, oh): vertical taps / weights once per block, threads walk (ow, 8-channel group).
+// One block per UP_ROWS consecutive output rows of one image; a thread owns one (ow, 8-channel group) column of
+// that band and walks down it.  The interpolation is separable - out = ly0*(lx0*a + lx1*b) + ly1*(lx0*c + lx1*d),
+// the form aten's upsample_bilinear2d uses - so the horizontally interpolated source rows are kept in registers
+// and re-used by the 2-3 output rows between them: ~1.25 16-byte loads per output instead of 4 and half the ALU
+// work of the four-tap form (the kernel was instruction-bound at 2/3 of the HBM write ceiling).
+constexpr int UP_ROWS = 8;
+
+__device__ __forceinline__ void up_hrow(const __nv_bfloat16* r, long long o0, long long o1, float lx0, float lx1, float (&h)[8]) {
+  const uint4 qa = __ldg(reinterpret_cast<const uint4*>(r + o0));
+  const uint4 qb = __ldg(reinterpret_cast<const uint4*>(r + o1));
+  const uint32_t* pa = reinterpret_cast<const uint32_t*>(&qa);
+  const uint32_t* pb = reinterpret_cast<const uint32_t*>(&qb);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float a0, a1, b0, b1;
+    bf2_to_f32(pa[i], a0, a1); bf2_to_f32(pb[i], b0, b1);
+    h[2 * i] = fmaf(lx1, b0, lx0 * a0);
+    h[2 * i + 1] = fmaf(lx1, b1, lx0 * a1);
+  }
+}
+
 __global__ void __launch_bounds__(256) upsample2x_kernel(const UpP p) {
   const int c8n = p.y.C >> 3;
   const int items = p.y.W * c8n;
-  // ROWS_PER_BLOCK consecutive output rows per block: they interpolate between the same 2-3 input rows (L1 hits)
-  for (long long rowi = blockIdx.x; rowi * ROWS_PER_BLOCK < p.total; rowi += gridDim.x)
-  for (long long row = rowi * ROWS_PER_BLOCK; row < min(p.total, (rowi + 1) * ROWS_PER_BLOCK); ++row) {
-    const int n = static_cast<int>(row / p.y.H);
-    const int oh = static_cast<int>(row - static_cast<long long>(n) * p.y.H);
-    const int uy = oh - p.offy;
-    const bool row_in = uy >= 0 && uy < p.UH;
-    const float fy = p.sy * uy;
-    const int y0 = row_in ? static_cast<int>(fy) : 0;
-    const int y1 = y0 + (y0 < p.x.H - 1 ? 1 : 0);
-    const float ly1 = fy - y0, ly0 = 1.f - ly1;
-    const __nv_bfloat16* r0 = elem_ptr(p.x, pix_index(p.x, n, 0, y0, 0), 0);
-    const __nv_bfloat16* r1 = elem_ptr(p.x, pix_index(p.x, n, 0, y1, 0), 0);
-    __nv_bfloat16* yrow = elem_ptr_w(p.y, pix_index(p.y, n, 0, oh, 0), 0);
+  const int bands = (p.y.H + UP_ROWS - 1) / UP_ROWS;
+  for (long long bi = blockIdx.x; bi < p.total; bi += gridDim.x) {
+    const int n = static_cast<int>(bi / bands);
+    const int oh0 = static_cast<int>(bi - static_cast<long long>(n) * bands) * UP_ROWS;
+    const int oh1 = min(oh0 + UP_ROWS, p.y.H);
+    const __nv_bfloat16* xn = elem_ptr(p.x, pix_index(p.x, n, 0, 0, 0), 0);
+    const long long x_row = static_cast<long long>(p.x.Wp) * p.x.ld;
+    __nv_bfloat16* yn = elem_ptr_w(p.y, pix_index(p.y, n, 0, oh0, 0), 0);
+    const long long y_row = static_cast<long long>(p.y.Wp) * p.y.ld;
     for (int it = threadIdx.x; it < items; it += blockDim.x) {
       const int ow = fast_div(it, p.c8_magic), c8 = it - ow * c8n;
-      uint4 out = make_uint4(0u, 0u, 0u, 0u);
       const int ux = ow - p.offx;
-      if (row_in && ux >= 0 && ux < p.UW) {
-        const float fx = p.sx * ux;
-        const int x0 = static_cast<int>(fx);
-        const int x1 = x0 + (x0 < p.x.W - 1 ? 1 : 0);
-        const float lx1 = fx - x0, lx0 = 1.f - lx1;
-        const float w00 = ly0 * lx0, w01 = ly0 * lx1, w10 = ly1 * lx0, w11 = ly1 * lx1;
-        const uint4 qa = __ldg(reinterpret_cast<const uint4*>(r0 + static_cast<long long>(x0) * p.x.ld + c8 * 8));
-        const uint4 qb = __ldg(reinterpret_cast<const uint4*>(r0 + static_cast<long long>(x1) * p.x.ld + c8 * 8));
-        const uint4 qc = __ldg(reinterpret_cast<const uint4*>(r1 + static_cast<long long>(x0) * p.x.ld + c8 * 8));
-        const uint4 qd = __ldg(reinterpret_cast<const uint4*>(r1 + static_cast<long long>(x1) * p.x.ld + c8 * 8));
-        const uint32_t* pa = reinterpret_cast<const uint32_t*>(&qa);
-        const uint32_t* pb = reinterpret_cast<const uint32_t*>(&qb);
-        const uint32_t* pc = reinterpret_cast<const uint32_t*>(&qc);
-        const uint32_t* pd = reinterpret_cast<const uint32_t*>(&qd);
-        uint32_t* po = reinterpret_cast<uint32_t*>(&out);
+      const bool col_in = ux >= 0 && ux < p.UW;
+      const float fx = p.sx * ux;
+      const int x0 = col_in ? static_cast<int>(fx) : 0;
+      const int x1 = x0 + (x0 < p.x.W - 1 ? 1 : 0);
+      const float lx1 = fx - x0, lx0 = 1.f - lx1;
+      const long long o0 = static_cast<long long>(x0) * p.x.ld + c8 * 8, o1 = static_cast<long long>(x1) * p.x.ld + c8 * 8;
+      __nv_bfloat16* yp = yn + static_cast<long long>(ow) * p.y.ld + c8 * 8;
+      float h0[8], h1[8];
+      int cur = -2;   // source row held in h0 (h1 holds row min(cur + 1, H - 1))
+      for (int oh = oh0; oh < oh1; ++oh, yp += y_row) {
+        const int uy = oh - p.offy;
+        uint4 out = make_uint4(0u, 0u, 0u, 0u);
+        if (col_in && uy >= 0 && uy < p.UH) {
+          const float fy = p.sy * uy;
+          const int y0 = static_cast<int>(fy);
+          const int y1 = y0 + (y0 < p.x.H - 1 ? 1 : 0);
+          const float ly1 = fy - y0, ly0 = 1.f - ly1;
+          if (y0 != cur) {
+            if (y0 == cur + 1) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float a0, a1, b0, b1, c0, c1, d0, d1;
-          bf2_to_f32(pa[i], a0, a1); bf2_to_f32(pb[i], b0, b1); bf2_to_f32(pc[i], c0, c1); bf2_to_f32(pd[i], d0, d1);
-          const float o0 = fmaf(w11, d0, fmaf(w10, c0, fmaf(w01, b0, w00 * a0)));
-          const float o1 = fmaf(w11, d1, fmaf(w10, c1, fmaf(w01, b1, w00 * a1)));
-          po[i] = cvt_bf16x2(o0, o1, false);
+              for (int i = 0; i < 8; ++i) h0[i] = h1[i];
+            } else {
+              up_hrow(xn + y0 * x_row, o0, o1, lx0, lx1, h0);
+            }
+            if (y1 != y0) {
+              up_hrow(xn + y1 * x_row, o0, o1, lx0, lx1, h1);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) h1[i] = h0[i];
+            }
+            cur = y0;
+          }
+          uint32_t* po = reinterpret_cast<uint32_t*>(&out);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            po[i] = cvt_bf16x2(fmaf(ly1, h1[2 * i], ly0 * h0[2 * i]), fmaf(ly1, h1[2 * i + 1], ly0 * h0[2 * i + 1]), false);
         }
+        *reinterpret_cast<uint4*>(yp) = out;
       }
-      *reinterpret_cast<uint4*>(yrow + static_cast<long long>(ow) * p.y.ld + c8 * 8) = out;
     }
   }
 }
@@ -369,12 +459,12 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PrepP p) {
   const int n = blockIdx.y;
   const int32_t* d = p.desc + n * 4;
   const int src = d[0], top = d[1], left = d[2], flip = d[3];
-  const long long band = (static_cast<long long>(Ho) * Wo + gridDim.x - 1) / gridDim.x;
-  const long long p0 = blockIdx.x * band;
-  const long long p1 = min(p0 + band, static_cast<long long>(Ho) * Wo);
+  const int band = (Ho * Wo + gridDim.x - 1) / gridDim.x;   // Ho, Wo <= PP_MAXOUT: 32-bit pixel arithmetic
+  const int p0 = blockIdx.x * band;
+  const int p1 = min(p0 + band, Ho * Wo);
   const uint8_t* img = p.frames + static_cast<long long>(src < 0 ? 0 : src) * p.Hs * p.Ws * 3;
-  for (long long q = p0 + threadIdx.x; q < p1; q += blockDim.x) {
-    const int oy = static_cast<int>(q / Wo), ox = static_cast<int>(q - static_cast<long long>(oy) * Wo);
+  for (int q = p0 + threadIdx.x; q < p1; q += blockDim.x) {
+    const int oy = q / Wo, ox = q - oy * Wo;
     float o[3] = {0.f, 0.f, 0.f};
     if (src >= 0) {
       const int yl = ylo[oy], yn = ycnt[oy], xl = xlo[ox], xn = xcnt[ox];
@@ -547,7 +637,27 @@ extern "C" int tedspad_maxpool(const tedspad_tensor* x, const tedspad_tensor* y,
   TSP_CHECK(static_cast<long long>(y->W) * (y->C / 8) < 65536, "maxpool: row of %d x %d channels too long", y->W, y->C);
   p.total = static_cast<long long>(y->N) * y->D * y->H;   // output rows
   TSP_CHECK(p.total < (1LL << 31), "maxpool: too many rows");
-  maxpool_kernel<<<rows_grid(p.total, y->W * (y->C / 8)), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int grid = rows_grid(p.total, y->W * (y->C / 8));
+  const bool same333 = kd == 3 && kh == 3 && kw == 3 && sd == 1 && sh == 1 && sw == 1 && pd == 1 && ph == 1 && pw == 1 &&
+                       x->D == y->D && x->H == y->H && x->W == y->W;
+  if (same333) {
+    maxpool333_s1_kernel<<<grid_for(p.total * (y->C / 8), 256), 256, 0, st>>>(p);
+  } else if (kd == 1 && kh == 3 && kw == 3) {
+    maxpool_kernel<1, 3, 3><<<grid, 256, 0, st>>>(p);
+  } else if (kd == 3 && kh == 3 && kw == 3) {
+    maxpool_kernel<3, 3, 3><<<grid, 256, 0, st>>>(p);
+  } else if (kd == 2 && kh == 2 && kw == 2) {
+    maxpool_kernel<2, 2, 2><<<grid, 256, 0, st>>>(p);
+  } else if (kd == 1 && kh == 2 && kw == 2) {
+    maxpool_kernel<1, 2, 2><<<grid, 256, 0, st>>>(p);
+  } else if (kd == 2 && kh == 3 && kw == 3) {
+    maxpool_kernel<2, 3, 3><<<grid, 256, 0, st>>>(p);
+  } else if (kd == 2 && kh == 1 && kw == 1) {
+    maxpool_kernel<2, 1, 1><<<grid, 256, 0, st>>>(p);
+  } else {
+    maxpool_kernel<0, 0, 0><<<grid, 256, 0, st>>>(p);
+  }
   TSP_CUDA(cudaGetLastError());
   return 0;
 }
@@ -563,7 +673,7 @@ extern "C" int tedspad_upsample2x(const tedspad_tensor* x, const tedspad_tensor*
   p.offy = (y->H - p.UH) / 2; p.offx = (y->W - p.UW) / 2;  // F.pad(diff//2, diff - diff//2)
   p.sy = p.UH > 1 ? static_cast<float>(x->H - 1) / static_cast<float>(p.UH - 1) : 0.f;
   p.sx = p.UW > 1 ? static_cast<float>(x->W - 1) / static_cast<float>(p.UW - 1) : 0.f;
-  p.total = static_cast<long long>(y->N) * y->H;   // output rows
+  p.total = static_cast<long long>(y->N) * ((y->H + UP_ROWS - 1) / UP_ROWS);   // bands of UP_ROWS output rows
   p.c8_magic = static_cast<uint32_t>((0x100000000ULL + (y->C / 8) - 1) / (y->C / 8));
   TSP_CHECK(static_cast<long long>(y->W) * (y->C / 8) < 65536, "upsample2x: row of %d x %d channels too long", y->W, y->C);
   upsample2x_kernel<<<rows_grid(p.total, y->W * (y->C / 8)), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
@@ -624,7 +734,10 @@ extern "C" int tedspad_preprocess(const uint8_t* frames, int32_t F, int32_t Hs, 
   p.y = make_view(*y);
   p.frames_f32 = frames_f32;
   const size_t smem = (2 * y->W + 2 * y->H) * sizeof(int) + (y->W + y->H) * PP_KMAX * sizeof(float) + 256 * sizeof(float);
-  const int bands = std::max(1, std::min(64, (y->H * y->W + 2047) / 2048));
+  // every block rebuilds the two resampling tables (~(H+W) entries): give it enough pixels to amortise that, but
+  // keep ~16 blocks per SM in the grid (a 512-frame batch gets 5 bands of ~10k pixels, a single clip 64 of 784)
+  const int want = (num_sms() * 16 + n_out - 1) / n_out;
+  const int bands = std::max(1, std::min(std::min(64, want), (y->H * y->W + 511) / 512));
   dim3 grid(bands, n_out);
   preprocess_kernel<<<grid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   TSP_CUDA(cudaGetLastError());

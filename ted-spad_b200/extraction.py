@@ -89,6 +89,7 @@ class SnippetExtractor:
         if self.device.type != "cuda":
             raise RuntimeError("SnippetExtractor needs CUDA modules: there is no CPU path")
         self._enc = {}
+        self._copy_stream = None
 
     def snippet_frames(self, n_frames):
         if self.source == "dali":
@@ -116,6 +117,39 @@ class SnippetExtractor:
             self.fa.anonymize_into(x0, enc_in, self.T)
             return self.ft.features_from_cl(enc_in)
 
+    def _stage(self, frames):
+        """Host frames -> device on the copy stream (returns the device tensor and the event that marks its arrival)."""
+        if frames.is_cuda:
+            return frames.contiguous(), None
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        with torch.cuda.stream(self._copy_stream):
+            dev = frames.contiguous().to(self.device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        return dev, ev
+
+    def features_stream(self, batches):
+        """batches: iterable of (frames uint8 [F,H,W,3] on the host (pinned for a truly asynchronous copy) or on the
+        device, desc int32 [B*T,4] numpy, crop_hw).  Yields fp32 cuda features [B, n_feat_rows, F] per batch.  The
+        host->device copy of batch i+1 runs on a copy stream while batch i is computed (the reference hands DALI's
+        GPU tensors over one clip at a time, dali_extraction.py:147-150)."""
+        it = iter(batches)
+        nxt = next(it, None)
+        staged = self._stage(nxt[0]) if nxt is not None else None
+        while nxt is not None:
+            cur, (dev, ev) = nxt, staged
+            nxt = next(it, None)
+            if nxt is not None:
+                staged = self._stage(nxt[0])          # in flight while `cur` is computed
+            compute = torch.cuda.current_stream(self.device)
+            if ev is not None:
+                compute.wait_event(ev)
+            feats = self.features_of_clips(dev, cur[1], cur[2])
+            if ev is not None:
+                dev.record_stream(compute)            # allocated on the copy stream, consumed on the compute stream
+            yield feats
+
     def extract_video(self, frames):
         """frames: uint8 [F,H,W,3] torch tensor (CPU, pinned CPU or CUDA), RGB for the DALI path, BGR
         as cv2 decodes for the ShanghaiTech path.  Returns float64 numpy [n_snip, feat] (ncrops == 1, the
@@ -124,22 +158,20 @@ class SnippetExtractor:
         snips = self.snippet_frames(n_frames)
         n_snip = snips.shape[0]
         crop_hw, boxes = crop_boxes(H, W, self.ncrops, self.cf, self.no_ar, square_from_h=(self.source == "shanghai"))
-        rows = []
         per_batch = max(1, self.batch_clips // self.ncrops)  # snippets per batch
-        for s0 in range(0, n_snip, per_batch):
-            sn = snips[s0:s0 + per_batch]
-            valid = sn[sn >= 0]
-            f_lo, f_hi = (int(valid.min()), int(valid.max()) + 1) if valid.size else (0, 1)
-            chunk = frames[f_lo:f_hi]
-            if not chunk.is_cuda:
-                chunk = chunk.to(self.device, non_blocking=True)
-            chunk = chunk.contiguous()
-            desc = np.empty((sn.shape[0], len(boxes), self.T, 4), dtype=np.int32)
-            desc[..., 0] = np.where(sn >= 0, sn - f_lo, -1)[:, None, :]
-            for ci, (t, l, fl) in enumerate(boxes):
-                desc[:, ci, :, 1], desc[:, ci, :, 2], desc[:, ci, :, 3] = t, l, fl
-            feats = self.features_of_clips(chunk, desc.reshape(-1, 4), crop_hw)  # [B, R, F]
-            rows.append(feats.reshape(sn.shape[0], len(boxes), -1).clone())
+
+        def batches():
+            for s0 in range(0, n_snip, per_batch):
+                sn = snips[s0:s0 + per_batch]
+                valid = sn[sn >= 0]
+                f_lo, f_hi = (int(valid.min()), int(valid.max()) + 1) if valid.size else (0, 1)
+                desc = np.empty((sn.shape[0], len(boxes), self.T, 4), dtype=np.int32)
+                desc[..., 0] = np.where(sn >= 0, sn - f_lo, -1)[:, None, :]
+                for ci, (t, l, fl) in enumerate(boxes):
+                    desc[:, ci, :, 1], desc[:, ci, :, 2], desc[:, ci, :, 3] = t, l, fl
+                yield frames[f_lo:f_hi], desc.reshape(-1, 4), crop_hw
+
+        rows = [f.reshape(-1, len(boxes), f.shape[-1] * f.shape[-2]).clone() for f in self.features_stream(batches())]
         if not rows:
             width = 0
             return np.zeros((0, width), dtype=np.float64)
