@@ -107,7 +107,13 @@ int tedspad_conv_forward(const tedspad_conv* p, void* stream);
  *                        block).  The 128-channel DoubleConv layers (unet_parts.py:15-22), Conv3d_2c_3x3
  *                        and the Inception 3x3x3 branches (aux_code/models/i3d.py:244,132-136).  Taps
  *                        outside the tensor are zero-filled by TMA: no halo required.
- * Optional fused producer (3X3 kinds, 2-D): `up` = the low-resolution tensor of Up.forward; its x2 bilinear
+ *   TEDSPAD_SLAB_3X3_PAIR  TEDSPAD_SLAB_3X3 executed by CTA PAIRS (clusters of two CTAs on the SMs of one TPC,
+ *                        tcgen05.mma.cta_group::2, M = 256): each CTA owns one tile and HALF of the weight rows, so
+ *                        the shared-memory operand reads that bound the N = 64 tensor-core rate at 67 % drop to
+ *                        (128 + 32) rows per step = 80 %.  The 64-output-channel DoubleConv layers.  Needs
+ *                        Cout_pad % 32 == 0, W > 8 and an even tile count; same fused epilogues as 3X3; the image
+ *                        from tedspad_conv_slab_pack(kind = PAIR) holds the two halves back to back.
+ * Optional fused producer (single-CTA 3X3 kinds, 2-D): `up` = the low-resolution tensor of Up.forward; its x2 bilinear
  * (align_corners=True) up-sampling is computed by four producer warps straight into the shared-memory slab,
  * so the up-sampled half of torch.cat([x2, x1]) (unet_parts.py:67) is never written to or read from HBM.
  * Optional fused epilogues (TEDSPAD_SLAB_3X3 only): MaxPool2d(2) of the output written to `pool`
@@ -116,7 +122,8 @@ int tedspad_conv_forward(const tedspad_conv* p, void* stream);
  * `w_image` holds the weights in the exact shared-memory image the kernel reads; build it with
  * tedspad_conv_slab_pack() from the standard packed layout of tedspad_conv.
  */
-enum { TEDSPAD_SLAB_3X3 = 0, TEDSPAD_SLAB_STEM2D = 1, TEDSPAD_SLAB_STEM3D = 2, TEDSPAD_SLAB_3X3_STREAM = 3 };
+enum { TEDSPAD_SLAB_3X3 = 0, TEDSPAD_SLAB_STEM2D = 1, TEDSPAD_SLAB_STEM3D = 2, TEDSPAD_SLAB_3X3_STREAM = 3,
+       TEDSPAD_SLAB_3X3_PAIR = 4 };
 
 typedef struct tedspad_conv_slab {
   tedspad_tensor x;         /* bf16 input view (see kinds above) */
@@ -161,6 +168,7 @@ typedef struct tedspad_slab_plan {
   int32_t tiles_x, tiles_y, tiles_z, total_tiles;
   int32_t b_stream, b_stages, b_stride, cb_n, cin, num_n_tiles, tab_per_stage;
   int32_t up_cb_first;      /* channel blocks >= this one are interpolated from `up` instead of loaded by TMA */
+  int32_t pair;             /* 1: CTA pairs (cluster of 2, cta_group::2); w_bytes / tab B offsets are per CTA (N/2 rows) */
   uint32_t tab[2 * TEDSPAD_SLAB_MAX_MMA];   /* per (k_stage, group): {A byte offset in slab, B byte offset in image} */
 } tedspad_slab_plan;
 

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libtedspad.so")
 ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
 FEED_AUTO, FEED_FLAT_TMA, FEED_GATHER = 0, 1, 2
 RESAMPLE_AA_FLOAT, RESAMPLE_PIL_U8 = 0, 1
-SLAB_3X3, SLAB_STEM2D, SLAB_STEM3D, SLAB_3X3_STREAM = 0, 1, 2, 3
+SLAB_3X3, SLAB_STEM2D, SLAB_STEM3D, SLAB_3X3_STREAM, SLAB_3X3_PAIR = 0, 1, 2, 3, 4
 SLAB_MAX_MMA = 112
 ABI_VERSION = 2
 
@@ -50,7 +50,7 @@ class SlabPlan(C.Structure):
                     "swizzle128", "merged_cw", "slab_bytes", "slab_stride", "w_bytes", "smem_bytes", "a_layout", "a_lbo", "a_sbo",
                     "b_layout", "b_lbo", "b_sbo", "half_a_off", "c_step", "x_step", "x_off", "y_step", "y_off",
                     "z_step", "z_off", "z_kstep", "tiles_x", "tiles_y", "tiles_z", "total_tiles", "b_stream", "b_stages",
-                    "b_stride", "cb_n", "cin", "num_n_tiles", "tab_per_stage", "up_cb_first")] +
+                    "b_stride", "cb_n", "cin", "num_n_tiles", "tab_per_stage", "up_cb_first", "pair")] +
                 [("tab", C.c_uint32 * (2 * SLAB_MAX_MMA))])
 
 

@@ -96,11 +96,11 @@ __device__ __forceinline__ bool elect_one() {
 // while the current group's MMAs are issued.  TM and NK are compile-time so that the inner loop is straight
 // line code of ~3 uniform instructions per tcgen05.mma: at N = 64 the tensor pipe wants a new instruction
 // every ~48 clocks and a single warp retires a dependent uniform instruction only every ~7.
-template <int TM, int NK, bool STREAM>
+template <int TM, int NK, bool STREAM, bool PAIR>
 __device__ __forceinline__ void slab_issue(const SlabKParams& p, uint8_t* smS, uint32_t w_addr, uint32_t tmem_base,
                                            uint64_t* full, uint64_t* empty, uint64_t* tfull, uint64_t* tempty,
                                            uint64_t* wbar, uint64_t* bfull, uint64_t* bempty) {
-  const uint32_t idesc = umma_idesc_bf16(128, p.n_tile);
+  const uint32_t idesc = umma_idesc_bf16(PAIR ? 256 : 128, p.n_tile);   // PAIR: M = 256 over the two CTAs
   const uint32_t a_hi = static_cast<uint32_t>(p.a_desc >> 32), a_lo0 = static_cast<uint32_t>(p.a_desc);
   const uint32_t b_hi = static_cast<uint32_t>(p.b_desc >> 32);
   const uint32_t b_lo0 = static_cast<uint32_t>(p.b_desc) + (w_addr >> 4);
@@ -113,10 +113,11 @@ __device__ __forceinline__ void slab_issue(const SlabKParams& p, uint8_t* smS, u
   const uint32_t b_step = static_cast<uint32_t>(p.b_stride >> 4);
   const int BS = p.b_stages, tab_ps = p.tab_per_stage;
   if (!STREAM) mbar_wait(wbar, 0);
+  if (PAIR) mbar_wait_cluster(bfull, 0);   // the peer's half of the weights has landed in ITS shared memory
   int s = 0, as = 0, bs = 0;
   uint32_t ph = 0, aph = 0, bph = 0;
   for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-    mbar_wait(tempty + as, aph ^ 1);
+    mbar_wait(tempty + as, aph ^ 1);   // PAIR: 16 arrivals, the peer's come through mbar_arrive_cluster
     tc_fence_after();
     const uint32_t d0 = tmem_base + static_cast<uint32_t>(as * TM) * n_tile;
     const uint32_t d1 = d0 + n_tile;
@@ -143,10 +144,12 @@ __device__ __forceinline__ void slab_issue(const SlabKParams& p, uint8_t* smS, u
           for (int k = 0; k < NK; ++k) {
             const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) | (a_lo + k * a_ks);
             const uint64_t bd = (static_cast<uint64_t>(b_hi) << 32) | (b_lo + k * b_ks);
-            umma_bf16_nc(d0, ad, bd, idesc, k == 0 ? acc0 : 1u);
+            if (PAIR) umma_bf16_nc_pair(d0, ad, bd, idesc, k == 0 ? acc0 : 1u);
+            else umma_bf16_nc(d0, ad, bd, idesc, k == 0 ? acc0 : 1u);
             if (TM == 2) {
               const uint64_t ad1 = (static_cast<uint64_t>(a_hi) << 32) | (a_lo + k * a_ks + half_step);
-              umma_bf16_nc(d1, ad1, bd, idesc, k == 0 ? acc0 : 1u);
+              if (PAIR) umma_bf16_nc_pair(d1, ad1, bd, idesc, k == 0 ? acc0 : 1u);
+              else umma_bf16_nc(d1, ad1, bd, idesc, k == 0 ? acc0 : 1u);
             }
           }
           if (STREAM) umma_commit(bempty + bs);
@@ -157,11 +160,11 @@ __device__ __forceinline__ void slab_issue(const SlabKParams& p, uint8_t* smS, u
         }
         cur = nxt;
       }
-      if (elect_one()) umma_commit(empty + s);
+      if (elect_one()) { if (PAIR) umma_commit_pair(empty + s); else umma_commit(empty + s); }
       __syncwarp();
       if (++s == S) { s = 0; ph ^= 1; }
     }
-    if (elect_one()) umma_commit(tfull + as);
+    if (elect_one()) { if (PAIR) umma_commit_pair(tfull + as); else umma_commit(tfull + as); }
     __syncwarp();
     as ^= 1;
     if (as == 0) aph ^= 1;
@@ -299,7 +302,15 @@ constexpr int SLAB_THREADS_UP = 480;   // + warps 11-14: up-sampling slab produc
 // up-sampled half is never materialised: for its channel blocks four producer warps interpolate the low-res
 // tensor (bilinear, align_corners=True, F.pad offsets) straight into the swizzled slab the TMA would have
 // filled.  Same arithmetic as upsample2x_kernel (ops.cu), so fused == unfused bit for bit.
-template <bool HAS_UP>
+//
+// PAIR: the grid is made of clusters of two CTAs (the two SMs of a TPC) that run one tcgen05.mma.cta_group::2 of
+// M = 256 per step: CTA r of the pair owns tile blockIdx.x (its own slab, its own accumulator, its own epilogue)
+// and HALF of the output-channel rows of the weights.  At N = 64 a single-CTA MMA is bound by shared-memory
+// reads ((128 + 64) rows x 32 B per 32 tensor clocks = 67 % of the tensor peak, profiles/r1_umma_probe.txt);
+// with the B rows split over two SMs it is (128 + 32) rows = 80 %.  Only the leader issues MMAs; its `full`
+// barriers collect the TMA bytes of both CTAs, commits are multicast to both, the peer's epilogue warps
+// arrive remotely on the leader's `tempty`.
+template <bool HAS_UP, bool PAIR>
 __global__ void __launch_bounds__(HAS_UP ? SLAB_THREADS_UP : SLAB_THREADS, 1)
 conv_slab_kernel(const __grid_constant__ SlabKParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -323,6 +334,7 @@ conv_slab_kernel(const __grid_constant__ SlabKParams p) {
 
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);  // provably warp-uniform
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;   // == blockIdx.x & 1: the tile loops below need no change
 
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
@@ -335,9 +347,10 @@ conv_slab_kernel(const __grid_constant__ SlabKParams p) {
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull + a, 1);
-      mbar_init(tempty + a, 8);
+      mbar_init(tempty + a, PAIR ? 16 : 8);   // PAIR (leader): the epilogue warps of both CTAs
     }
     mbar_init(wbar, 1);
+    if (PAIR) mbar_init(bfull, 1);           // leader: "the peer's weights are resident"
     for (int b = 0; b < p.b_stages; ++b) {
       mbar_init(bfull + b, 1);
       mbar_init(bempty + b, 1);
@@ -345,8 +358,13 @@ conv_slab_kernel(const __grid_constant__ SlabKParams p) {
     fence_barrier_init();
   }
   if (warp == 10) {
-    tmem_alloc(tmem_slot, p.tmem_cols);
-    tmem_relinquish();
+    if (PAIR) {
+      tmem_alloc_pair(tmem_slot, p.tmem_cols);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, p.tmem_cols);
+      tmem_relinquish();
+    }
   }
   for (int i = threadIdx.x; i < p.n_tile * p.num_n_tiles; i += blockDim.x) sm_bias[i] = p.bias[i];
   if (p.oc_w != nullptr) {
@@ -361,7 +379,7 @@ conv_slab_kernel(const __grid_constant__ SlabKParams p) {
     fence_proxy_async_smem();
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();   // PAIR: the peer's barriers are initialised before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -369,9 +387,10 @@ conv_slab_kernel(const __grid_constant__ SlabKParams p) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
       if (!p.b_stream) {
+        const uint8_t* w_src = p.w_image + (PAIR ? static_cast<size_t>(rank) * p.w_bytes : 0);   // this CTA's half
         mbar_arrive_expect_tx(wbar, static_cast<uint32_t>(p.w_bytes));
         for (int off = 0; off < p.w_bytes; off += 16384)
-          bulk_copy_g2s(smW + off, p.w_image + off, static_cast<uint32_t>(min(16384, p.w_bytes - off)), wbar);
+          bulk_copy_g2s(smW + off, w_src + off, static_cast<uint32_t>(min(16384, p.w_bytes - off)), wbar);
       }
       int s = 0, bs = 0;
       uint32_t ph = 0, bph = 0;
@@ -388,6 +407,11 @@ conv_slab_kernel(const __grid_constant__ SlabKParams p) {
           mbar_wait(empty + s, ph ^ 1);
           if (HAS_UP && cb >= p.up_cb_first) {
             mbar_arrive(full + s);   // this slab is written by the up-sampling warps
+          } else if (PAIR) {
+            // both slabs complete on the LEADER's barrier (its issuer reads both shared memories)
+            if (rank == 0) mbar_arrive_expect_tx(full + s, 2u * static_cast<uint32_t>(p.slab_bytes));
+            tma_load_5d_pair(smS + s * p.slab_stride, &p.tmA, mapa_u32(smem_u32(full + s), 0), cb * p.c_step, cx, cy,
+                             cz + kt * p.z_kstep, n);
           } else {
             mbar_arrive_expect_tx(full + s, static_cast<uint32_t>(p.slab_bytes));
             if (p.merged_cw)  // stems: (pixel, channel) merged into one contiguous inner dimension of 8-element pixels
@@ -412,8 +436,16 @@ conv_slab_kernel(const __grid_constant__ SlabKParams p) {
     // -------------------------------------------------------------- MMA issuer
     const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t wa = smem_u32(smW);
-#define TSP_ISSUE(TM_, NK_, ST_) slab_issue<TM_, NK_, ST_>(p, smS, wa, tb, full, empty, tfull, tempty, wbar, bfull, bempty)
-    if (p.b_stream) {
+#define TSP_ISSUE(TM_, NK_, ST_) slab_issue<TM_, NK_, ST_, false>(p, smS, wa, tb, full, empty, tfull, tempty, wbar, bfull, bempty)
+    if (PAIR) {
+      if (rank == 0) {
+        slab_issue<2, 4, false, true>(p, smS, wa, tb, full, empty, tfull, tempty, wbar, bfull, bempty);
+      } else {
+        // peer: report its half of the weights resident, then leave the issuing to the leader
+        mbar_wait(wbar, 0);
+        if (lane == 0) mbar_arrive_cluster_release(mapa_u32(smem_u32(bfull), 0));
+      }
+    } else if (p.b_stream) {
       if (p.tm == 2) TSP_ISSUE(2, 4, true); else TSP_ISSUE(1, 4, true);
     } else if (p.tm == 2) {
       if (p.nk == 4) TSP_ISSUE(2, 4, false); else TSP_ISSUE(2, 2, false);
@@ -486,7 +518,10 @@ conv_slab_kernel(const __grid_constant__ SlabKParams p) {
       // all TMEM reads of this accumulator are complete (wait::ld above): hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty + as);
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(tempty + as), 0));
+        else mbar_arrive(tempty + as);
+      }
       if (c.fuse_oc && valid && nch > 0) {
         const long long plane = static_cast<long long>(OH) * OW;
         const long long o0 = static_cast<long long>(n) * 3 * plane + static_cast<long long>(oy) * OW + ox;
@@ -559,9 +594,12 @@ conv_slab_kernel(const __grid_constant__ SlabKParams p) {
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();   // PAIR: the leader's MMAs read the peer's shared memory to the end
   tc_fence_after();
-  if (warp == 10) tmem_dealloc(tmem_base, p.tmem_cols);
+  if (warp == 10) {
+    if (PAIR) tmem_dealloc_pair(tmem_base, p.tmem_cols);
+    else tmem_dealloc(tmem_base, p.tmem_cols);
+  }
 }
 
 // ------------------------------------------------------------------------------------ weight image
@@ -629,6 +667,8 @@ static int make_plan(const tedspad_conv_slab& c, tedspad_slab_plan& P) {
   const tedspad_tensor& x = c.x;
   const tedspad_tensor& y = c.y;
   const bool stream = c.kind == TEDSPAD_SLAB_3X3_STREAM;
+  const bool pair = c.kind == TEDSPAD_SLAB_3X3_PAIR;
+  P.pair = pair ? 1 : 0;
   TSP_CHECK(c.Cout_pad % 32 == 0 && c.Cout_pad >= 32 && c.Cout_pad <= (stream ? 512 : 256) && c.Cout <= c.Cout_pad &&
                 c.Cout >= 1 && c.Cout % 8 == 0,
             "slab: Cout=%d (multiple of 8) / Cout_pad=%d (multiple of 32, <= %d) invalid", c.Cout, c.Cout_pad,
@@ -649,7 +689,7 @@ static int make_plan(const tedspad_conv_slab& c, tedspad_slab_plan& P) {
   // fused up-sampling: the convolution sees [x | upsample2x(up)] along the channels
   const bool has_up = c.up.ptr != nullptr;
   if (has_up) {
-    TSP_CHECK(c.kind == TEDSPAD_SLAB_3X3 || c.kind == TEDSPAD_SLAB_3X3_STREAM, "slab: fused up-sampling needs a 3x3 kind");
+    TSP_CHECK(c.kind == TEDSPAD_SLAB_3X3 || c.kind == TEDSPAD_SLAB_3X3_STREAM, "slab: fused up-sampling needs a single-CTA 3x3 kind");
     TSP_CHECK(c.up.C % 64 == 0 && c.up.C >= 64 && c.up.N == x.N && c.up.D == 1 && x.D == 1 && c.kd == 1 &&
                   2 * c.up.H <= x.H && 2 * c.up.W <= x.W,
               "slab: up-sampling source [%d,%d,%d,%d] does not fit the [%d,%d,%d] input", c.up.N, c.up.H, c.up.W, c.up.C,
@@ -657,19 +697,21 @@ static int make_plan(const tedspad_conv_slab& c, tedspad_slab_plan& P) {
   }
   const int cin_total = x.C + (has_up ? c.up.C : 0);
   P.up_cb_first = has_up ? x.C / 64 : 1 << 20;
-  if (c.kind == TEDSPAD_SLAB_3X3 || c.kind == TEDSPAD_SLAB_STEM2D) {
+  if (c.kind == TEDSPAD_SLAB_3X3 || c.kind == TEDSPAD_SLAB_STEM2D || pair) {
     TSP_CHECK(c.kd == 1 && c.kh == 3 && c.kw == 3 && c.sd == 1 && c.sh == 1 && c.sw == 1 && c.pd == 0 && c.ph == 1 &&
                   c.pw == 1,
               "slab: kind %d needs a (1,3,3) stride-1 pad-1 convolution", c.kind);
     TSP_CHECK(x.D == y.D && x.H == y.H && x.W == y.W, "slab: output extents must equal input extents");
-    const bool sw = c.kind == TEDSPAD_SLAB_3X3;
+    const bool sw = c.kind == TEDSPAD_SLAB_3X3 || pair;
+    const int b_rows = pair ? P.n_tile / 2 : P.n_tile;   // weight rows (output channels) held by one CTA
+    if (pair) TSP_CHECK(P.n_tile % 32 == 0 && x.W > 8, "slab pair: needs Cout_pad %% 32 == 0 and W > 8 (got %d, %d)", P.n_tile, x.W);
     if (sw) {
       TSP_CHECK(x.C % 64 == 0 && x.C >= 64, "slab 3x3: x.C=%d must be a multiple of 64", x.C);
       // no halo needed: taps outside the tensor are zero-filled by TMA (a zero halo works just as well)
     } else {
       TSP_CHECK(x.C == 8, "slab stem2d: x.C=%d must be 8 (channels padded to one 16-byte pixel)", x.C);
     }
-    P.w_bytes = static_cast<int>(slab_image_bytes(c.kind, P.n_tile, sw ? cin_total : x.C, 1, 3, 3));
+    P.w_bytes = static_cast<int>(slab_image_bytes(sw ? TEDSPAD_SLAB_3X3 : c.kind, b_rows, sw ? cin_total : x.C, 1, 3, 3));
     P.swizzle128 = sw ? 1 : 0;
     P.k_stages = sw ? cin_total / 64 : 1;
     P.cb_n = P.k_stages;
@@ -687,6 +729,7 @@ static int make_plan(const tedspad_conv_slab& c, tedspad_slab_plan& P) {
       }
     }
     TSP_CHECK(tm == 1 || tm == 2, "slab: tm=%d", tm);
+    TSP_CHECK(!pair || tm == 2, "slab pair: the tile must be two 8-column halves (weights too large for three slab stages?)");
     P.tm = tm;
     slab_w = 8 * tm + 2;
     slab_h = 18;
@@ -729,7 +772,7 @@ static int make_plan(const tedspad_conv_slab& c, tedspad_slab_plan& P) {
           const int i = cb * 9 + tap;
           TSP_CHECK(i < TEDSPAD_SLAB_MAX_MMA, "slab 3x3: %d table groups exceed the table (Cin too large)", i + 1);
           P.tab[2 * i] = static_cast<uint32_t>(((tap / 3) * slab_w + (tap % 3)) * 128);
-          P.tab[2 * i + 1] = static_cast<uint32_t>((tap * cb_n + cb) * P.n_tile * 128);
+          P.tab[2 * i + 1] = static_cast<uint32_t>((tap * cb_n + cb) * b_rows * 128);
         }
     } else {
       P.a_layout = 0; P.a_lbo = 16; P.a_sbo = slab_w * 16;
@@ -862,6 +905,7 @@ static int make_plan(const tedspad_conv_slab& c, tedspad_slab_plan& P) {
   const int64_t total = static_cast<int64_t>(x.N) * P.tiles_z * P.tiles_y * P.tiles_x * P.num_n_tiles;
   TSP_CHECK(total > 0 && total < (int64_t(1) << 31), "slab: tile count out of range");
   P.total_tiles = static_cast<int>(total);
+  TSP_CHECK(!pair || total % 2 == 0, "slab pair: %lld tiles cannot be split over CTA pairs", (long long)total);
   return 0;
 }
 
@@ -879,25 +923,33 @@ extern "C" int tedspad_conv_slab_plan(const tedspad_conv_slab* c, tedspad_slab_p
 extern "C" int tedspad_conv_slab_pack(int32_t kind, const void* w_std, int32_t Cout_pad, int32_t K_pad, int32_t cin_pad,
                                       int32_t kd, int32_t kh, int32_t kw, int32_t pw_front, void* image,
                                       int64_t* image_bytes, void* stream) {
-  TSP_CHECK(kind >= TEDSPAD_SLAB_3X3 && kind <= TEDSPAD_SLAB_STEM3D, "slab pack: unknown kind %d", kind);
+  TSP_CHECK((kind >= TEDSPAD_SLAB_3X3 && kind <= TEDSPAD_SLAB_STEM3D) || kind == TEDSPAD_SLAB_3X3_PAIR, "slab pack: unknown kind %d", kind);
+  const bool pair = kind == TEDSPAD_SLAB_3X3_PAIR;
+  if (pair) {
+    kind = TEDSPAD_SLAB_3X3;   // two 3X3 images of Cout_pad / 2 rows each, the leader's first
+    TSP_CHECK(Cout_pad % 32 == 0, "slab pack pair: Cout_pad=%d must be a multiple of 32", Cout_pad);
+  }
+  const int halves = pair ? 2 : 1, rows = Cout_pad / halves;
   TSP_CHECK(Cout_pad % 16 == 0 && Cout_pad >= 16 && Cout_pad <= 256, "slab pack: Cout_pad=%d", Cout_pad);
   if (kind == TEDSPAD_SLAB_3X3) TSP_CHECK(cin_pad % 64 == 0 && kd == 1 && kh == 3 && kw == 3, "slab pack 3x3: bad geometry");
   if (kind == TEDSPAD_SLAB_STEM2D) TSP_CHECK(cin_pad <= 8 && kd == 1 && kh == 3 && kw == 3, "slab pack stem2d: bad geometry");
   if (kind == TEDSPAD_SLAB_STEM3D) TSP_CHECK(cin_pad >= 1 && kh == 7 && kw == 7 && kd >= 1, "slab pack stem3d: bad geometry");
   TSP_CHECK(K_pad >= kd * kh * kw * cin_pad, "slab pack: K_pad=%d too small", K_pad);
-  const long long bytes = slab_image_bytes(kind, Cout_pad, kind == TEDSPAD_SLAB_STEM3D ? 4 : cin_pad, kd, kh, kw);
-  if (image_bytes) *image_bytes = bytes;
+  const long long bytes = slab_image_bytes(kind, rows, kind == TEDSPAD_SLAB_STEM3D ? 4 : cin_pad, kd, kh, kw);
+  if (image_bytes) *image_bytes = bytes * halves;
   if (image == nullptr) return 0;
   TSP_CHECK(w_std != nullptr, "slab pack: null weights");
-  PackP p;
-  p.w_std = reinterpret_cast<const __nv_bfloat16*>(w_std);
-  p.image = reinterpret_cast<__nv_bfloat16*>(image);
-  p.kind = kind; p.n_tile = Cout_pad; p.K_pad = K_pad; p.cin_pad = cin_pad; p.kd = kd; p.kh = kh; p.kw = kw;
-  p.shift = pw_front & 1;
-  p.total = bytes / 2;
-  const int blocks = static_cast<int>(std::min<long long>((p.total + 255) / 256, 4096));
-  slab_pack_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
-  TSP_CUDA(cudaGetLastError());
+  for (int h = 0; h < halves; ++h) {
+    PackP p;
+    p.w_std = reinterpret_cast<const __nv_bfloat16*>(w_std) + static_cast<long long>(h) * rows * K_pad;
+    p.image = reinterpret_cast<__nv_bfloat16*>(image) + h * (bytes / 2);
+    p.kind = kind; p.n_tile = rows; p.K_pad = K_pad; p.cin_pad = cin_pad; p.kd = kd; p.kh = kh; p.kw = kw;
+    p.shift = pw_front & 1;
+    p.total = bytes / 2;
+    const int blocks = static_cast<int>(std::min<long long>((p.total + 255) / 256, 4096));
+    slab_pack_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    TSP_CUDA(cudaGetLastError());
+  }
   return 0;
 }
 
@@ -960,7 +1012,8 @@ extern "C" int tedspad_conv_slab_forward(const tedspad_conv_slab* c, void* strea
   if (c->pool.ptr != nullptr) {
     const tedspad_tensor& q = c->pool;
     if (check_tensor(q, "slab.pool", 8)) return 1;
-    TSP_CHECK((c->kind == TEDSPAD_SLAB_3X3 || c->kind == TEDSPAD_SLAB_3X3_STREAM) && y.D == 1 && q.D == 1 && q.pd == 0 &&
+    TSP_CHECK((c->kind == TEDSPAD_SLAB_3X3 || c->kind == TEDSPAD_SLAB_3X3_STREAM || c->kind == TEDSPAD_SLAB_3X3_PAIR) &&
+                  y.D == 1 && q.D == 1 && q.pd == 0 &&
                   q.N == y.N && q.C == c->Cout &&
                   q.H == y.H / 2 && q.W == y.W / 2,
               "slab: fused MaxPool2d(2) output [%d,%d,%d,%d] does not match", q.N, q.H, q.W, q.C);
@@ -997,9 +1050,11 @@ extern "C" int tedspad_conv_slab_forward(const tedspad_conv_slab* c, void* strea
 
   int rc = 0;
   std::call_once(g_slab_attr_once, [&] {
-    cudaError_t e = cudaFuncSetAttribute(conv_slab_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SLAB_SMEM_BUDGET);
+    cudaError_t e = cudaFuncSetAttribute(conv_slab_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SLAB_SMEM_BUDGET);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(conv_slab_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SLAB_SMEM_BUDGET);
+      e = cudaFuncSetAttribute(conv_slab_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SLAB_SMEM_BUDGET);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_slab_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SLAB_SMEM_BUDGET);
     if (e != cudaSuccess) {
       set_error("cudaFuncSetAttribute(slab smem) failed: %s", cudaGetErrorString(e));
       rc = 2;
@@ -1008,10 +1063,28 @@ extern "C" int tedspad_conv_slab_forward(const tedspad_conv_slab* c, void* strea
   if (rc) return rc;
   int ctas = c->max_ctas > 0 ? c->max_ctas : num_sms();
   ctas = std::max(1, std::min(ctas, p.total_tiles));
-  if (has_up)
-    conv_slab_kernel<true><<<ctas, SLAB_THREADS_UP, P.smem_bytes, reinterpret_cast<cudaStream_t>(stream_v)>>>(p);
-  else
-    conv_slab_kernel<false><<<ctas, SLAB_THREADS, P.smem_bytes, reinterpret_cast<cudaStream_t>(stream_v)>>>(p);
+  if (P.pair) {
+    // clusters of two CTAs (one TPC); an even grid keeps the two tile loops of a pair in lock step
+    ctas &= ~1;
+    TSP_CHECK(ctas >= 2 && !has_up, "slab pair: needs at least two CTAs and no fused up-sampling");
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ctas);
+    cfg.blockDim = dim3(SLAB_THREADS);
+    cfg.dynamicSmemBytes = P.smem_bytes;
+    cfg.stream = reinterpret_cast<cudaStream_t>(stream_v);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    TSP_CUDA(cudaLaunchKernelEx(&cfg, conv_slab_kernel<false, true>, p));
+  } else if (has_up) {
+    conv_slab_kernel<true, false><<<ctas, SLAB_THREADS_UP, P.smem_bytes, reinterpret_cast<cudaStream_t>(stream_v)>>>(p);
+  } else {
+    conv_slab_kernel<false, false><<<ctas, SLAB_THREADS, P.smem_bytes, reinterpret_cast<cudaStream_t>(stream_v)>>>(p);
+  }
   TSP_CUDA(cudaGetLastError());
   return 0;
 }

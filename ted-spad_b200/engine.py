@@ -17,6 +17,7 @@ from .ops import CLTensor, PackedConv
 # SLAB feed switches (csrc/conv_slab.cu): on by default; "0" routes the layer classes back through the FLAT /
 # GATHER feeds of csrc/conv_igemm.cu (kept for A/B measurements and as the general-shape path).
 USE_SLAB = os.environ.get("TEDSPAD_SLAB", "1") != "0"
+USE_PAIR = os.environ.get("TEDSPAD_PAIR", "1") != "0"     # cta_group::2 for the 64-output-channel 3x3 layers
 USE_SLAB_STEM3D = USE_SLAB and os.environ.get("TEDSPAD_SLAB_STEM3D", "1") != "0"
 SLAB_WEIGHT_LIMIT = 150 * 1024   # bytes of resident weights that still leave room for three slab stages
 ENC_IN_CHANNELS = 4 if USE_SLAB_STEM3D else 8   # channel padding of the encoder input clip
@@ -38,7 +39,9 @@ def slab3x3(pc, max_stream_cout=512):
     if pc.cin_pad % 64 or pc.cout % 8 or pc.cout_pad % 32 or pc.k_pad != kd * 9 * pc.cin_pad:
         return None
     if kd == 1 and pc.cout_pad <= 256 and 9 * pc.cin_pad * pc.cout_pad * 2 <= SLAB_WEIGHT_LIMIT:
-        return ops.PackedSlabConv(pc, L.SLAB_3X3)
+        # N = 64 is shared-memory-read bound on one SM (67 % of the tensor peak): CTA pairs split the weight rows.
+        # At N = 128 the halved weight image makes room for 16x16 tiles (measured +7 %).
+        return ops.PackedSlabConv(pc, L.SLAB_3X3_PAIR if (USE_PAIR and pc.cout_pad in (64, 128)) else L.SLAB_3X3)
     if pc.cout_pad <= max_stream_cout and pc.n_tile % 32 == 0:
         return ops.PackedSlabConv(pc, L.SLAB_3X3_STREAM)
     return None

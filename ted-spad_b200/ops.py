@@ -197,6 +197,8 @@ class PackedSlabConv:
             return
         if pc.cout_pad > 256 or pc.cout % 8:
             raise ValueError(f"slab feed needs a single N tile (Cout_pad={pc.cout_pad}) with Cout % 8 == 0")
+        # CTA-pair kind: layers it cannot tile (W <= 8, odd tile count) run through the single-CTA kind
+        self.fallback = PackedSlabConv(pc, L.SLAB_3X3) if kind == L.SLAB_3X3_PAIR else None
         nbytes = C.c_int64(0)
         args = (self.kind, None, pc.cout_pad, pc.k_pad, pc.cin_pad, *pc.k, pc.pad_front[2])
         L.check(L.lib().tedspad_conv_slab_pack(*args, None, C.byref(nbytes), None), "tedspad_conv_slab_pack(size)")
@@ -236,10 +238,17 @@ class PackedSlabConv:
         d.n_tile, d.K_pad = (self.n_tile if self.kind == L.SLAB_3X3_STREAM else 0), pc.k_pad
         return d
 
+    def resolve(self, x, tm=0, up=None):
+        """The PackedSlabConv that runs this input: the CTA-pair kind needs 16x16 tiles (W > 8) in an even number."""
+        if self.kind == L.SLAB_3X3_PAIR and (up is not None or tm == 1 or x.W <= 8 or
+                                             (x.N * x.D * (-(-x.H // 16)) * (-(-x.W // 16))) % 2):
+            return self.fallback
+        return self
+
     def plan(self, x, y, **kw):
         """The kernel's tiling / descriptor plan (host-only call; used by the CPU simulator tests)."""
         plan = L.SlabPlan()
-        d = self.desc(x, y, **kw)
+        d = self.resolve(x, kw.get("tm", 0), kw.get("up")).desc(x, y, **kw)
         L.check(L.lib().tedspad_conv_slab_plan(C.byref(d), C.byref(plan)), "tedspad_conv_slab_plan")
         return plan
 
@@ -247,6 +256,7 @@ class PackedSlabConv:
 def conv_slab_forward(x, psc, y, act=L.ACT_RELU, pool=None, outconv=None, tm=0, max_ctas=0, up=None):
     """y = act(conv(x) + bias) through the SLAB feed; optional fused MaxPool2d(2) -> pool, OutConv 1x1 + sigmoid
     -> planar images (y may then be None), and fused Up.forward input: conv([x | upsample2x(up)])."""
+    psc = psc.resolve(x, tm, up)
     d = psc.desc(x, y, act=act, pool=pool, outconv=outconv, tm=tm, max_ctas=max_ctas, up=up)
     _count()
     if CONV_EVENTS is not None:

@@ -390,7 +390,7 @@ def run_slab_case(name, kind, N, dhw, cin_real, cin_buf, cout, k, stride=(1, 1, 
         b = (torch.rand(cout, generator=g) - 0.5).to(DEV)
         bnp = ((torch.rand(cout, generator=g) + 0.5).to(DEV), (torch.rand(cout, generator=g) - 0.5).to(DEV),
                (torch.rand(cout, generator=g) - 0.5).to(DEV), (torch.rand(cout, generator=g) + 0.5).to(DEV), 1e-3)
-        std_cin = cin_buf if kind in (L.SLAB_3X3, L.SLAB_3X3_STREAM) else 8
+        std_cin = cin_buf if kind in (L.SLAB_3X3, L.SLAB_3X3_STREAM, L.SLAB_3X3_PAIR) else 8
         pc = ops.PackedConv(w, b, bnp, stride=stride, pad_front=pad_f, cin_pad=std_cin, device=DEV, n_align=32)
         psc = ops.PackedSlabConv(pc, kind)
         if kind != L.SLAB_3X3_STREAM:
@@ -478,6 +478,31 @@ def group_slab3():
     run_slab_case("S7 64->64 112x112 x8 many tiles", K, 8, (1, 112, 112), 64, 64, 64, (1, 3, 3), halo=(0, 1, 1))
     run_slab_case("S8 64->32 odd 19x21", K, 2, (1, 19, 21), 64, 64, 32, (1, 3, 3), halo=(0, 1, 1))
     run_slab_case("S9 (1,3,3) D=3 64->64", K, 2, (3, 16, 16), 64, 64, 64, (1, 3, 3), halo=(0, 1, 1))
+
+
+def group_slabpair():
+    """CTA-pair kind (cta_group::2): same cases as the single-CTA 3X3 kind wherever the tile count is even."""
+    K = L.SLAB_3X3_PAIR
+    run_slab_case("P1 64->64 20x24 pair", K, 2, (1, 20, 24), 64, 64, 64, (1, 3, 3), halo=(0, 1, 1))
+    run_slab_case("P2 64->64 20x24 pair 2 ctas", K, 2, (1, 20, 24), 64, 64, 64, (1, 3, 3), halo=(0, 1, 1), max_ctas=2)
+    run_slab_case("P3 128->64 slices pair", K, 4, (1, 32, 32), 128, 128, 64, (1, 3, 3), halo=(0, 1, 1), in_ld=192, in_coff=64,
+                  out_ld=128, out_coff=64)
+    run_slab_case("P4 64->64 pool fused 32x48 pair", K, 3, (1, 32, 48), 64, 64, 64, (1, 3, 3), halo=(0, 1, 1), pool=True,
+                  out_ld=128, out_coff=0)
+    run_slab_case("P5 64->64 outconv fused pair", K, 4, (1, 32, 32), 64, 64, 64, (1, 3, 3), halo=(0, 1, 1), outconv=True)
+    run_slab_case("P6 64->64 112x112 x8 many tiles pair", K, 8, (1, 112, 112), 64, 64, 64, (1, 3, 3), halo=(0, 1, 1))
+    run_slab_case("P7 64->64 odd 19x21 x2 pair", K, 2, (1, 19, 21), 64, 64, 64, (1, 3, 3), halo=(0, 1, 1))
+    run_slab_case("P8 64->64 odd tile count -> single-CTA fallback", K, 1, (1, 16, 48), 64, 64, 64, (1, 3, 3), halo=(0, 1, 1))
+    run_slab_case("P9 64->128 28x28 pair (N=128)", K, 2, (1, 28, 28), 64, 64, 128, (1, 3, 3), halo=(0, 1, 1))
+
+
+def group_pairperf():
+    for K, nm in ((L.SLAB_3X3, "single"), (L.SLAB_3X3_PAIR, "pair")):
+        time_slab(f"64->64 @224 x128 {nm}", K, 128, (1, 224, 224), 64, 64, (1, 3, 3))
+        time_slab(f"64->64 @224 x128 +pool {nm}", K, 128, (1, 224, 224), 64, 64, (1, 3, 3), pool=True)
+        time_slab(f"128->64 @224 x128 {nm}", K, 128, (1, 224, 224), 128, 64, (1, 3, 3))
+        time_slab(f"128->64 @112 x128 {nm}", K, 128, (1, 112, 112), 128, 64, (1, 3, 3))
+        time_slab(f"64->128 @112 x128 {nm}", K, 128, (1, 112, 112), 64, 128, (1, 3, 3))
 
 
 def group_slabstream():
@@ -582,12 +607,12 @@ def time_slab(name, kind, N, dhw, cin_buf, cout, k, stride=(1, 1, 1), pad_f=(0, 
     try:
         D, H, W = dhw
         cin_real = cin_real or cin_buf
-        halo = (0, 1, 1) if (kind in (L.SLAB_3X3, L.SLAB_3X3_STREAM) and D == 1) else (0, 0, 0)
+        halo = (0, 1, 1) if (kind in (L.SLAB_3X3, L.SLAB_3X3_STREAM, L.SLAB_3X3_PAIR) and D == 1) else (0, 0, 0)
         x = ops.CLTensor(N, D, H, W, cin_buf, halo, device=DEV)
         x.interior().normal_()
         wt = torch.randn(cout, cin_real, *k, device=DEV) / (cin_real * k[0] * k[1] * k[2]) ** 0.5
         pc = ops.PackedConv(wt, None, None, stride=stride, pad_front=pad_f,
-                            cin_pad=cin_buf if kind in (L.SLAB_3X3, L.SLAB_3X3_STREAM) else 8, device=DEV, n_align=32)
+                            cin_pad=cin_buf if kind in (L.SLAB_3X3, L.SLAB_3X3_STREAM, L.SLAB_3X3_PAIR) else 8, device=DEV, n_align=32)
         psc = ops.PackedSlabConv(pc, kind, n_tile=n_tile)
         od, oh, ow = pc.out_extent((D, H, W), pad_b)
         y = ops.CLTensor(N, od, oh, ow, cout, (0, 1, 1) if od == 1 else (0, 0, 0), device=DEV)
