@@ -147,6 +147,9 @@ typedef struct tedspad_conv_slab {
   int32_t max_ctas;         /* persistent grid cap; 0 = number of SMs */
   int32_t n_tile;           /* STREAM kind: UMMA N per tile (multiple of 32 dividing Cout_pad); 0 = auto */
   int32_t K_pad;            /* STREAM kind: row length of the standard packed weights */
+  int32_t stack_rows;       /* 2-D 3X3 kinds over buffers with zero halo rows (x.ph >= 1): tile the rows of all N images
+                               as one column of N*(H+2ph) rows (no per-image remainder).  0 = when it saves tensor
+                               time, 1 = always (when legal), -1 = never */
 } tedspad_conv_slab;
 
 /* Everything the kernel derives from a tedspad_conv_slab: exposed so that the CPU test-suite can
@@ -168,6 +171,8 @@ typedef struct tedspad_slab_plan {
   int32_t tiles_x, tiles_y, tiles_z, total_tiles;
   int32_t b_stream, b_stages, b_stride, cb_n, cin, num_n_tiles, tab_per_stage;
   int32_t up_cb_first;      /* channel blocks >= this one are interpolated from `up` instead of loaded by TMA */
+  int32_t stack_hp, stack_ph, stack_n;   /* stacked rows: padded image height, halo rows, batch (stack_hp 0 = off):
+                               tile row g of row-tile ty is stacked row R = ph + 16*ty + g = image R / hp, row R % hp - ph */
   int32_t pair;             /* 1: CTA pairs (cluster of 2, cta_group::2); w_bytes / tab B offsets are per CTA (N/2 rows) */
   uint32_t tab[2 * TEDSPAD_SLAB_MAX_MMA];   /* per (k_stage, group): {A byte offset in slab, B byte offset in image} */
 } tedspad_slab_plan;

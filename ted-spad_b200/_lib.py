@@ -38,7 +38,7 @@ class ConvSlabDesc(C.Structure):
                 ("pool", TensorDesc), ("up", TensorDesc), ("oc_w", C.c_void_p), ("oc_b", C.c_void_p), ("oc_planes", C.c_void_p),
                 ("oc_frames", C.c_void_p)] + [(n, C.c_int32) for n in (
                     "kind", "Cout", "Cout_pad", "kd", "kh", "kw", "sd", "sh", "sw", "pd", "ph", "pw", "act", "tm",
-                    "max_ctas", "n_tile", "K_pad")]
+                    "max_ctas", "n_tile", "K_pad", "stack_rows")]
 
 
 class SlabPlan(C.Structure):
@@ -50,7 +50,7 @@ class SlabPlan(C.Structure):
                     "swizzle128", "merged_cw", "slab_bytes", "slab_stride", "w_bytes", "smem_bytes", "a_layout", "a_lbo", "a_sbo",
                     "b_layout", "b_lbo", "b_sbo", "half_a_off", "c_step", "x_step", "x_off", "y_step", "y_off",
                     "z_step", "z_off", "z_kstep", "tiles_x", "tiles_y", "tiles_z", "total_tiles", "b_stream", "b_stages",
-                    "b_stride", "cb_n", "cin", "num_n_tiles", "tab_per_stage", "up_cb_first", "pair")] +
+                    "b_stride", "cb_n", "cin", "num_n_tiles", "tab_per_stage", "up_cb_first", "stack_hp", "stack_ph", "stack_n", "pair")] +
                 [("tab", C.c_uint32 * (2 * SLAB_MAX_MMA))])
 
 

@@ -55,6 +55,7 @@ struct SlabKParams {
   int half_a_off;
   int c_step, x_step, x_off, y_step, y_off, z_step, z_off, z_kstep, merged_cw;
   int tiles_x, tiles_y, tiles_z, total_tiles;
+  int stack_hp, stack_ph, stack_n;   // stacked rows (see make_plan): padded image height, halo rows, batch; 0 = off
   uint64_t a_desc, b_desc;
   // epilogue
   __nv_bfloat16* y;
@@ -121,6 +122,10 @@ __device__ __forceinline__ void slab_issue(const SlabKParams& p, uint8_t* smS, u
     tc_fence_after();
     const uint32_t d0 = tmem_base + static_cast<uint32_t>(as * TM) * n_tile;
     const uint32_t d1 = d0 + n_tile;
+    // the second 8-column half of the last tile of a row may lie entirely outside the image (W = 56: 7 groups):
+    // its MMAs are skipped (its epilogue warps find nothing valid to store)
+    bool h1 = TM == 2;
+    if (TM == 2 && !PAIR) h1 = ((tile / p.num_n_tiles) % p.tiles_x) * 16 + 8 < p.OW;
     for (int ks = 0; ks < KS; ++ks) {
       const uint2* tab = p.tab + (tab_ps ? ks * NG : 0);
       uint2 cur = tab[0];
@@ -146,7 +151,7 @@ __device__ __forceinline__ void slab_issue(const SlabKParams& p, uint8_t* smS, u
             const uint64_t bd = (static_cast<uint64_t>(b_hi) << 32) | (b_lo + k * b_ks);
             if (PAIR) umma_bf16_nc_pair(d0, ad, bd, idesc, k == 0 ? acc0 : 1u);
             else umma_bf16_nc(d0, ad, bd, idesc, k == 0 ? acc0 : 1u);
-            if (TM == 2) {
+            if (TM == 2 && h1) {
               const uint64_t ad1 = (static_cast<uint64_t>(a_hi) << 32) | (a_lo + k * a_ks + half_step);
               if (PAIR) umma_bf16_nc_pair(d1, ad1, bd, idesc, k == 0 ? acc0 : 1u);
               else umma_bf16_nc(d1, ad1, bd, idesc, k == 0 ? acc0 : 1u);
@@ -480,13 +485,21 @@ conv_slab_kernel(const __grid_constant__ SlabKParams p) {
       const int tx = t % p.tiles_x; t /= p.tiles_x;
       const int ty = t % p.tiles_y; t /= p.tiles_y;
       const int tz = t % p.tiles_z;
-      const int n = t / p.tiles_z;
-      const int oy = ty * 16 + g;
+      int n = t / p.tiles_z;
+      int oy = ty * 16 + g;
       const int ox = (tx * tm + h) * 8 + r;
-      const bool valid = oy < OH && ox < OW;
+      bool valid = ox < OW;
+      if (p.stack_hp) {
+        // stacked rows: the tile's 16 rows are consecutive rows of the zero-haloed images of the whole batch
+        const int R = oy + p.stack_ph;
+        n = R / p.stack_hp;
+        oy = R - n * p.stack_hp - p.stack_ph;
+        valid = valid && n < p.stack_n;
+      }
+      valid = valid && static_cast<unsigned>(oy) < static_cast<unsigned>(OH);
       const long long pix = ((static_cast<long long>(n) * p.yDp + tz + p.ypd) * p.yHp + oy + p.yph) * p.yWp + ox + p.ypw;
       const int py = oy >> 1, px = ox >> 1;
-      const bool pool_writer = ((lane & 9) == 0) && py < p.PH && px < p.PW;
+      const bool pool_writer = ((lane & 9) == 0) && valid && py < p.PH && px < p.PW;
       const long long ppix = (static_cast<long long>(n) * p.pHp + py + p.pph) * p.pWp + px + p.ppw;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) +
                              static_cast<uint32_t>((as * tm + h) * n_tile + c_first);
@@ -881,6 +894,23 @@ static int make_plan(const tedspad_conv_slab& c, tedspad_slab_plan& P) {
   } else {
     TSP_CHECK(false, "slab: unknown kind %d", c.kind);
   }
+  // Stacked rows.  A 16-row tile grid wastes ceil(H/16)*16/H of the tensor-core time per image (56, 28: +14 %).
+  // When the input buffer carries zero halo ROWS (x.ph >= 1, the contract of the anonymizer's buffers), the rows of
+  // all images are tiled as ONE column of N*(H+2ph) rows instead: a tile's slab then simply runs across the halo
+  // rows between two images (which are the zero padding both need), the per-image remainder disappears and only
+  // the halo rows themselves are computed in vain (58/56, 30/28).  Tile row 0 = stacked row ph, so that with an
+  // even padded height the 2x2 pooling pairs of the fused MaxPool2d never straddle tiles or images.
+  int64_t batch = x.N;
+  const bool kind3x3 = c.kind == TEDSPAD_SLAB_3X3 || c.kind == TEDSPAD_SLAB_3X3_STREAM || pair;
+  if (kind3x3 && c.stack_rows >= 0 && x.D == 1 && x.pd == 0 && c.kd == 1 && x.ph >= 1 && !has_up && x.N > 1 &&
+      (c.stack_rows > 0 || Hp < round_up(x.H, 16)) && (c.pool.ptr == nullptr || Hp % 2 == 0)) {
+    P.stack_hp = Hp; P.stack_ph = x.ph; P.stack_n = x.N;
+    P.tdim[2] = Hp * x.N; P.tdim[3] = 1; P.tdim[4] = 1;
+    P.tstride[2] = P.tstride[1] * Hp * x.N;
+    P.tstride[3] = P.tstride[2];
+    P.tiles_y = (Hp * x.N - 2 * x.ph + 15) / 16;
+    batch = 1;
+  }
   P.slab_bytes = 2 * P.box[0] * P.box[1] * P.box[2] * P.box[3] * P.box[4];
   P.slab_stride = static_cast<int>(round_up(P.slab_bytes + pad_bytes, 1024));
   int w_stride = static_cast<int>(round_up(P.w_bytes, 1024));
@@ -902,7 +932,7 @@ static int make_plan(const tedspad_conv_slab& c, tedspad_slab_plan& P) {
   while (tc < 2 * P.tm * P.n_tile) tc <<= 1;
   TSP_CHECK(tc <= 512, "slab: %d TMEM columns needed", tc);
   P.tmem_cols = tc;
-  const int64_t total = static_cast<int64_t>(x.N) * P.tiles_z * P.tiles_y * P.tiles_x * P.num_n_tiles;
+  const int64_t total = batch * P.tiles_z * P.tiles_y * P.tiles_x * P.num_n_tiles;
   TSP_CHECK(total > 0 && total < (int64_t(1) << 31), "slab: tile count out of range");
   P.total_tiles = static_cast<int>(total);
   TSP_CHECK(!pair || total % 2 == 0, "slab pair: %lld tiles cannot be split over CTA pairs", (long long)total);
@@ -999,6 +1029,7 @@ extern "C" int tedspad_conv_slab_forward(const tedspad_conv_slab* c, void* strea
   p.c_step = P.c_step; p.x_step = P.x_step; p.x_off = P.x_off; p.y_step = P.y_step; p.y_off = P.y_off;
   p.z_step = P.z_step; p.z_off = P.z_off; p.z_kstep = P.z_kstep; p.merged_cw = P.merged_cw;
   p.tiles_x = P.tiles_x; p.tiles_y = P.tiles_y; p.tiles_z = P.tiles_z; p.total_tiles = P.total_tiles;
+  p.stack_hp = P.stack_hp; p.stack_ph = P.stack_ph; p.stack_n = P.stack_n;
   p.a_desc = umma_desc_template(P.a_layout, P.a_lbo, P.a_sbo);
   p.b_desc = umma_desc_template(P.b_layout, P.b_lbo, P.b_sbo);
   const int n_tab = P.tab_per_stage ? P.k_stages * P.n_grp : P.n_grp;

@@ -211,7 +211,7 @@ class PackedSlabConv:
             L.check(L.lib().tedspad_conv_slab_pack(*args, self.image.data_ptr(), C.byref(nbytes), _stream()),
                     "tedspad_conv_slab_pack")
 
-    def desc(self, x, y, act=L.ACT_RELU, pool=None, outconv=None, tm=0, max_ctas=0, up=None):
+    def desc(self, x, y, act=L.ACT_RELU, pool=None, outconv=None, tm=0, max_ctas=0, up=None, stack_rows=0):
         """outconv = (w fp32 [3,Cout], b fp32 [3], planes bf16 [N,3,H,W], frames fp32 [N,3,H,W] | None)"""
         pc = self.pc
         d = L.ConvSlabDesc()
@@ -234,30 +234,31 @@ class PackedSlabConv:
         d.kd, d.kh, d.kw = pc.k
         d.sd, d.sh, d.sw = pc.stride
         d.pd, d.ph, d.pw = pc.pad_front
-        d.act, d.tm, d.max_ctas = act, tm, max_ctas
+        d.act, d.tm, d.max_ctas, d.stack_rows = act, tm, max_ctas, stack_rows
         d.n_tile, d.K_pad = (self.n_tile if self.kind == L.SLAB_3X3_STREAM else 0), pc.k_pad
         return d
 
-    def resolve(self, x, tm=0, up=None):
-        """The PackedSlabConv that runs this input: the CTA-pair kind needs 16x16 tiles (W > 8) in an even number."""
-        if self.kind == L.SLAB_3X3_PAIR and (up is not None or tm == 1 or x.W <= 8 or
-                                             (x.N * x.D * (-(-x.H // 16)) * (-(-x.W // 16))) % 2):
+    def resolve(self, x, tm=0, up=None, stack_rows=0):
+        """The PackedSlabConv that runs this input: the CTA-pair kind needs 16x16 tiles (W > 8) in an even number
+        (per-image row tiles: the pair layers run at 224 / 112 where those are exact)."""
+        if self.kind == L.SLAB_3X3_PAIR and (up is not None or tm == 1 or x.W <= 8 or stack_rows > 0 or x.H % 16 or
+                                             (x.N * x.D * (x.H // 16) * (-(-x.W // 16))) % 2):
             return self.fallback
         return self
 
     def plan(self, x, y, **kw):
         """The kernel's tiling / descriptor plan (host-only call; used by the CPU simulator tests)."""
         plan = L.SlabPlan()
-        d = self.resolve(x, kw.get("tm", 0), kw.get("up")).desc(x, y, **kw)
+        d = self.resolve(x, kw.get("tm", 0), kw.get("up"), kw.get("stack_rows", 0)).desc(x, y, **kw)
         L.check(L.lib().tedspad_conv_slab_plan(C.byref(d), C.byref(plan)), "tedspad_conv_slab_plan")
         return plan
 
 
-def conv_slab_forward(x, psc, y, act=L.ACT_RELU, pool=None, outconv=None, tm=0, max_ctas=0, up=None):
+def conv_slab_forward(x, psc, y, act=L.ACT_RELU, pool=None, outconv=None, tm=0, max_ctas=0, up=None, stack_rows=0):
     """y = act(conv(x) + bias) through the SLAB feed; optional fused MaxPool2d(2) -> pool, OutConv 1x1 + sigmoid
     -> planar images (y may then be None), and fused Up.forward input: conv([x | upsample2x(up)])."""
-    psc = psc.resolve(x, tm, up)
-    d = psc.desc(x, y, act=act, pool=pool, outconv=outconv, tm=tm, max_ctas=max_ctas, up=up)
+    psc = psc.resolve(x, tm, up, stack_rows)
+    d = psc.desc(x, y, act=act, pool=pool, outconv=outconv, tm=tm, max_ctas=max_ctas, up=up, stack_rows=stack_rows)
     _count()
     if CONV_EVENTS is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

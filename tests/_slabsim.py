@@ -127,7 +127,8 @@ def stream_block(w_std, k_pad, n0, n_tile, k0):
 
 
 def simulate_tiles(plan, xbits, image_bits, bias, tiles, k_pad=0):
-    """Run the plan for the given tile indices; returns {tile: (n, tz, oy[128*tm], ox[128*tm], acc[128*tm, n_tile], n0)}.
+    """Run the plan for the given tile indices; returns {tile: (n[128*tm], tz, oy[128*tm], ox[128*tm], acc[128*tm, n_tile], n0)}
+    (oy < 0 or >= OH marks rows the epilogue does not store).
     image_bits: the weight image (resident kinds) or the standard packed weights (streaming kind, with k_pad)."""
     out = {}
     nt = plan.n_tile
@@ -164,5 +165,12 @@ def simulate_tiles(plan, xbits, image_bits, bias, tiles, k_pad=0):
         g, r = m >> 3, m & 7
         oy = np.concatenate([ty * 16 + g for _ in range(plan.tm)])
         ox = np.concatenate([(tx * plan.tm + h) * 8 + r for h in range(plan.tm)])
-        out[tile] = (n, tz, oy, ox, acc.reshape(plan.tm * 128, nt) + bias[None, n0:n0 + nt].astype(np.float64), n0)
+        nn = np.full(oy.shape, n, dtype=np.int64)
+        if plan.stack_hp:   # stacked rows: the epilogue's (image, row) decode of conv_slab_kernel
+            R = oy + plan.stack_ph
+            nn = R // plan.stack_hp
+            oy = R - nn * plan.stack_hp - plan.stack_ph
+            oy = np.where(nn < plan.stack_n, oy, -1)   # rows past the last image are never stored
+            nn = np.minimum(nn, plan.stack_n - 1)
+        out[tile] = (nn, tz, oy, ox, acc.reshape(plan.tm * 128, nt) + bias[None, n0:n0 + nt].astype(np.float64), n0)
     return out

@@ -43,9 +43,9 @@ def _run(kind, x_cl, x_ref, w, stride, pad_f, pad_b, y_shape, tm, tiles=None, ci
     worst, seen = 0.0, 0
     OH, OW = y_shape[2], y_shape[3]
     for tile, (n, tz, oy, ox, acc, n0) in res.items():
-        ok = (oy < OH) & (ox < OW)
+        ok = (oy >= 0) & (oy < OH) & (ox < OW)
         nc = min(plan.n_tile, cout - n0)   # real channels of this N tile
-        want = ref[n, n0:n0 + nc, tz][:, torch.from_numpy(oy[ok]), torch.from_numpy(ox[ok])].T.numpy()
+        want = ref[torch.from_numpy(n[ok]), n0:n0 + nc, tz, torch.from_numpy(oy[ok]), torch.from_numpy(ox[ok])].numpy()
         worst = max(worst, float(np.abs(acc[ok][:, :nc] - want).max()))
         seen += int(ok.sum()) if n0 == 0 else 0
     return worst, seen, plan
