@@ -15,7 +15,7 @@ FEED_AUTO, FEED_FLAT_TMA, FEED_GATHER = 0, 1, 2
 RESAMPLE_AA_FLOAT, RESAMPLE_PIL_U8 = 0, 1
 SLAB_3X3, SLAB_STEM2D, SLAB_STEM3D, SLAB_3X3_STREAM, SLAB_3X3_PAIR = 0, 1, 2, 3, 4
 SLAB_MAX_MMA = 112
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class TensorDesc(C.Structure):
