@@ -76,6 +76,13 @@ typedef struct tedspad_conv {
   int32_t feed;             /* TEDSPAD_FEED_* */
   int32_t n_tile;           /* UMMA N per tile; 0 = auto */
   int32_t max_ctas;         /* persistent grid cap; 0 = number of SMs */
+  /* Optional extra destinations: convolutions that read the SAME input (the 1x1 branches b0 / b1a / b2a of an
+   * InceptionModule, aux_code/models/i3d.py:144-149) run as ONE GEMM over their concatenated weight rows; output
+   * columns [0, y.C) go to y, [y2_begin, y2_begin + y2.C) to y2 and [y3_begin, y3_begin + y3.C) to y3.  Begins are
+   * multiples of 16 in increasing order; y2/y3 share y's (N,D,H,W) and halo; Cout = end of the last segment; no
+   * residual, bf16 outputs.  ptr NULL = none (y3 needs y2). */
+  tedspad_tensor y2, y3;
+  int32_t y2_begin, y3_begin;
 } tedspad_conv;
 
 int tedspad_conv_forward(const tedspad_conv* p, void* stream);

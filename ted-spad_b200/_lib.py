@@ -29,7 +29,8 @@ class ConvDesc(C.Structure):
     _fields_ = [("x", TensorDesc), ("y", TensorDesc), ("w", C.c_void_p), ("bias", C.c_void_p),
                 ("res", C.c_void_p)] + [(n, C.c_int32) for n in (
                     "res_ld", "res_coff", "Cout", "Cout_pad", "K_pad", "kd", "kh", "kw", "sd", "sh", "sw",
-                    "pd", "ph", "pw", "act", "y_fp32", "feed", "n_tile", "max_ctas")]
+                    "pd", "ph", "pw", "act", "y_fp32", "feed", "n_tile", "max_ctas")] + [
+                    ("y2", TensorDesc), ("y3", TensorDesc), ("y2_begin", C.c_int32), ("y3_begin", C.c_int32)]
 
 
 class ConvSlabDesc(C.Structure):

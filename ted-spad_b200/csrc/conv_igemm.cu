@@ -58,6 +58,11 @@ struct ConvKParams {
   const float* bias;
   const __nv_bfloat16* res;
   int res_ld, res_coff, act;
+  // output column segments (same pixel geometry, different buffers / channel slices): segment s holds columns
+  // [seg_begin[s], seg_begin[s] + seg_cout[s]); a single-destination convolution is one segment starting at 0
+  int nseg;
+  int seg_begin[3], seg_cout[3], seg_ld[3], seg_coff[3];
+  void* seg_y[3];
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -163,7 +168,9 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constan
     // ---------------------------------------------------------------- epilogue
     const int ew = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may read
     const int row = ew * 32 + lane;
-    const bool vec_ok = ((p.y_ld | p.y_coff) & 7) == 0;
+    bool seg_vec[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) seg_vec[i] = ((p.seg_ld[i] | p.seg_coff[i]) & 7) == 0;
     const bool rvec_ok = p.res != nullptr && ((p.res_ld | p.res_coff) & 7) == 0;
     int as = 0;
     uint32_t aph = 0;
@@ -189,7 +196,6 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constan
         const int n = t / p.OD;
         pix = ((static_cast<long long>(n) * p.yDp + od + p.ypd) * p.yHp + oh + p.yph) * p.yWp + ow + p.ypw;
       }
-      const long long yoff = pix * p.y_ld + p.y_coff;
       const long long roff = pix * p.res_ld + p.res_coff;
 
       mbar_wait(tfull + as, aph);
@@ -200,12 +206,19 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constan
         tmem_ld16(t_row + c, v);
         tmem_ld_wait();
         const int cg = n0 + c;
-        if (row_ok && cg < p.Cout) {
+        // destination of this 16-column chunk (segments start at multiples of 16)
+        int sg = 0;
+        if (p.nseg > 1 && cg >= p.seg_begin[1]) sg = (p.nseg > 2 && cg >= p.seg_begin[2]) ? 2 : 1;
+        const int cl = cg - p.seg_begin[sg];          // column inside the segment
+        const int s_cout = p.seg_cout[sg];
+        const bool vec_ok = seg_vec[sg];
+        const long long yoff = pix * p.seg_ld[sg] + p.seg_coff[sg];
+        if (row_ok && cl < s_cout) {
           float f[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) + __ldg(p.bias + cg + i);
           if (p.res != nullptr) {
-            if (rvec_ok && cg + 16 <= p.Cout) {
+            if (rvec_ok && cl + 16 <= s_cout) {
               const uint4* rp = reinterpret_cast<const uint4*>(p.res + roff + cg);
 #pragma unroll
               for (int h = 0; h < 2; ++h) {
@@ -220,20 +233,20 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constan
               }
             } else {
               for (int i = 0; i < 16; ++i)
-                if (cg + i < p.Cout) f[i] += __bfloat162float(p.res[roff + cg + i]);
+                if (cl + i < s_cout) f[i] += __bfloat162float(p.res[roff + cg + i]);
             }
           }
 #pragma unroll
           for (int i = 0; i < 16; ++i) f[i] = interior ? apply_act(f[i], p.act) : 0.f;
           if (p.y_fp32) {
-            float* yp = reinterpret_cast<float*>(p.y) + yoff + cg;
+            float* yp = reinterpret_cast<float*>(p.seg_y[sg]) + yoff + cl;
             for (int i = 0; i < 16; ++i)
-              if (cg + i < p.Cout) yp[i] = f[i];
+              if (cl + i < s_cout) yp[i] = f[i];
           } else {
-            __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.y) + yoff + cg;
+            __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(p.seg_y[sg]) + yoff + cl;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-              if (vec_ok && cg + h * 8 + 8 <= p.Cout) {
+              if (vec_ok && cl + h * 8 + 8 <= s_cout) {
                 uint4 o;
                 __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
@@ -241,7 +254,7 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constan
                 *reinterpret_cast<uint4*>(yp + h * 8) = o;
               } else {
                 for (int i = 0; i < 8; ++i)
-                  if (cg + h * 8 + i < p.Cout) yp[h * 8 + i] = __float2bfloat16_rn(f[h * 8 + i]);
+                  if (cl + h * 8 + i < s_cout) yp[h * 8 + i] = __float2bfloat16_rn(f[h * 8 + i]);
               }
             }
           }
@@ -350,7 +363,22 @@ extern "C" int tedspad_conv_forward(const tedspad_conv* c, void* stream_v) {
   TSP_CHECK(c->w && c->bias, "conv: null weights/bias");
   TSP_CHECK(c->kd >= 1 && c->kh >= 1 && c->kw >= 1 && c->sd >= 1 && c->sh >= 1 && c->sw >= 1, "conv: bad kernel/stride");
   TSP_CHECK(x.N == y.N, "conv: batch mismatch %d vs %d", x.N, y.N);
-  TSP_CHECK(y.C == c->Cout, "conv: y.C %d != Cout %d", y.C, c->Cout);
+  const tedspad_tensor* extra[2] = {&c->y2, &c->y3};
+  const int extra_begin[2] = {c->y2_begin, c->y3_begin};
+  int nseg = 1;
+  for (int i = 0; i < 2; ++i) {
+    if (extra[i]->ptr == nullptr) break;
+    const tedspad_tensor& e = *extra[i];
+    if (check_tensor(e, "conv.y2/y3", 1)) return 1;
+    const int prev_end = i == 0 ? y.C : extra_begin[0] + extra[0]->C;
+    TSP_CHECK(nseg == i + 1 && extra_begin[i] % 16 == 0 && extra_begin[i] >= prev_end && c->res == nullptr && !c->y_fp32 &&
+                  e.N == y.N && e.D == y.D && e.H == y.H && e.W == y.W && e.pd == y.pd && e.ph == y.ph && e.pw == y.pw &&
+                  extra_begin[i] + e.C <= c->Cout,
+              "conv: extra destination %d (columns %d..%d of %d) must follow the previous one at a multiple of 16 and "
+              "share y's pixel geometry", i + 2, extra_begin[i], extra_begin[i] + e.C, c->Cout);
+    ++nseg;
+  }
+  TSP_CHECK(nseg > 1 ? y.C <= c->Cout : y.C == c->Cout, "conv: y.C %d != Cout %d", y.C, c->Cout);
   TSP_CHECK(x.C % 8 == 0, "conv: x.C=%d must be a multiple of 8 (pad input channels)", x.C);
   const int ntaps = c->kd * c->kh * c->kw;
   TSP_CHECK(c->K_pad % BLOCK_K == 0 && c->K_pad >= ntaps * x.C, "conv: K_pad=%d invalid for %d taps x %d ch", c->K_pad,
@@ -408,6 +436,14 @@ extern "C" int tedspad_conv_forward(const tedspad_conv* c, void* stream_v) {
   p.yDp = y.D + 2 * y.pd; p.yHp = y.H + 2 * y.ph; p.yWp = y.W + 2 * y.pw;
   p.ypd = y.pd; p.yph = y.ph; p.ypw = y.pw;
   p.y_ld = y.ld; p.y_coff = y.coff; p.y_fp32 = c->y_fp32;
+  p.nseg = nseg;
+  p.seg_begin[0] = 0; p.seg_cout[0] = y.C; p.seg_ld[0] = y.ld; p.seg_coff[0] = y.coff; p.seg_y[0] = y.ptr;
+  for (int i = 1; i < 3; ++i) {
+    const bool on = i < nseg;
+    const tedspad_tensor& e = on ? *extra[i - 1] : y;
+    p.seg_begin[i] = on ? extra_begin[i - 1] : (1 << 30);
+    p.seg_cout[i] = on ? e.C : 0; p.seg_ld[i] = e.ld; p.seg_coff[i] = e.coff; p.seg_y[i] = e.ptr;
+  }
   p.bias = c->bias;
   p.res = reinterpret_cast<const __nv_bfloat16*>(c->res);
   p.res_ld = c->res_ld; p.res_coff = c->res_coff;

@@ -209,27 +209,29 @@ __device__ __forceinline__ void slab_epi_chunk(const EpiCtx& c, const uint32_t (
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
       const float4 b4 = *reinterpret_cast<const float4*>(c.bias + c0 + i);
-      f[i] = __uint_as_float(v[i]) + b4.x;
-      f[i + 1] = __uint_as_float(v[i + 1]) + b4.y;
-      f[i + 2] = __uint_as_float(v[i + 2]) + b4.z;
-      f[i + 3] = __uint_as_float(v[i + 3]) + b4.w;
+      f[i] = __uint_as_float(v[i]); f[i + 1] = __uint_as_float(v[i + 1]);
+      f[i + 2] = __uint_as_float(v[i + 2]); f[i + 3] = __uint_as_float(v[i + 3]);
+      add_f32x2(f[i], f[i + 1], b4.x, b4.y);
+      add_f32x2(f[i + 2], f[i + 3], b4.z, b4.w);
     }
     if (c.act == TEDSPAD_ACT_RELU) {
 #pragma unroll
       for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
     }
     if (c0 < c.Cout) {
+      // packed fp32x2 FMAs into two independent accumulator pairs per output (the scalar version was one serial
+      // 32-deep FFMA chain per output: the epilogue, not the tensor pipe, set the pace of the last UNet layer)
 #pragma unroll
       for (int o = 0; o < 3; ++o) {
         const float* wr = c.ocw + o * c.Cout + c0;
+        float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
           const float4 w4 = *reinterpret_cast<const float4*>(wr + i);
-          oc[o] = fmaf(f[i], w4.x, oc[o]);
-          oc[o] = fmaf(f[i + 1], w4.y, oc[o]);
-          oc[o] = fmaf(f[i + 2], w4.z, oc[o]);
-          oc[o] = fmaf(f[i + 3], w4.w, oc[o]);
+          fma_f32x2(a0, a1, f[i], f[i + 1], w4.x, w4.y);
+          fma_f32x2(b0, b1, f[i + 2], f[i + 3], w4.z, w4.w);
         }
+        oc[o] += (a0 + a1) + (b0 + b1);
       }
     }
 #pragma unroll
@@ -250,24 +252,25 @@ __device__ __forceinline__ void slab_epi_chunk(const EpiCtx& c, const uint32_t (
     }
   }
   if (c.pool != nullptr) {
-    // MaxPool2d(2): x partner = lane ^ 1 (r ^ 1), y partner = lane ^ 8 (g ^ 1)
+    // MaxPool2d(2): x partner = lane ^ 1 (r ^ 1), y partner = lane ^ 8 (g ^ 1).  Each exchange also halves the
+    // channels a lane carries on (the partner keeps the other half), so the 2x2 window costs 8 + 4 shuffles per
+    // 32 channels instead of 32, and all four lanes of the window store 16 bytes (8 channels) of the pooled pixel.
+    const uint32_t lane = threadIdx.x & 31u;
+    const bool odd_x = (lane & 1u) != 0, odd_y = (lane & 8u) != 0;
+    uint32_t a[8], b[4];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      q[i] = max_bf162(q[i], __shfl_xor_sync(0xffffffffu, q[i], 1));
-      q[i] = max_bf162(q[i], __shfl_xor_sync(0xffffffffu, q[i], 8));
+    for (int i = 0; i < 8; ++i) {
+      const uint32_t give = odd_x ? q[i] : q[i + 8], keep = odd_x ? q[i + 8] : q[i];
+      a[i] = max_bf162(keep, __shfl_xor_sync(0xffffffffu, give, 1));
     }
-    if (pool_writer) {
-      __nv_bfloat16* pp = c.pool + ppix * c.p_ld + c.p_coff + c0;
-      if (c.pool_wide_ok && c0 + 32 <= c.Cout) {
-        st_global_256(pp, q);
-        st_global_256(pp + 16, q + 8);
-      } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (c0 + 8 * j < c.Cout)
-            *reinterpret_cast<uint4*>(pp + 8 * j) = make_uint4(q[4 * j], q[4 * j + 1], q[4 * j + 2], q[4 * j + 3]);
-      }
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t give = odd_y ? a[i] : a[i + 4], keep = odd_y ? a[i + 4] : a[i];
+      b[i] = max_bf162(keep, __shfl_xor_sync(0xffffffffu, give, 8));
     }
+    const int cq = c0 + (odd_x ? 16 : 0) + (odd_y ? 8 : 0);   // first of this lane's 8 pooled channels
+    if (pool_writer && cq < c.Cout)
+      *reinterpret_cast<uint4*>(c.pool + ppix * c.p_ld + c.p_coff + cq) = make_uint4(b[0], b[1], b[2], b[3]);
   }
 }
 
@@ -499,7 +502,8 @@ conv_slab_kernel(const __grid_constant__ SlabKParams p) {
       valid = valid && static_cast<unsigned>(oy) < static_cast<unsigned>(OH);
       const long long pix = ((static_cast<long long>(n) * p.yDp + tz + p.ypd) * p.yHp + oy + p.yph) * p.yWp + ox + p.ypw;
       const int py = oy >> 1, px = ox >> 1;
-      const bool pool_writer = ((lane & 9) == 0) && valid && py < p.PH && px < p.PW;
+      // all four lanes of a 2x2 window write (8 channels each); the window is in the image iff its pooled pixel is
+      const bool pool_writer = oy >= 0 && ox < OW && py < p.PH && px < p.PW && (p.stack_hp == 0 || n < p.stack_n);
       const long long ppix = (static_cast<long long>(n) * p.pHp + py + p.pph) * p.pWp + px + p.ppw;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) +
                              static_cast<uint32_t>((as * tm + h) * n_tile + c_first);

@@ -276,6 +276,17 @@ __device__ __forceinline__ void add_f32x2(float& a0, float& a1, float b0, float 
       : "+f"(a0), "+f"(a1)
       : "f"(b0), "f"(b1));
 }
+// (a0, a1) = (x0, x1) * (y0, y1) + (a0, a1) as one packed fp32x2 FMA (FFMA2)
+__device__ __forceinline__ void fma_f32x2(float& a0, float& a1, float x0, float x1, float y0, float y1) {
+  asm("{\n\t.reg .b64 a, x, y;\n\t"
+      "mov.b64 a, {%0, %1};\n\t"
+      "mov.b64 x, {%2, %3};\n\t"
+      "mov.b64 y, {%4, %5};\n\t"
+      "fma.rn.f32x2 a, x, y, a;\n\t"
+      "mov.b64 {%0, %1}, a;\n\t}"
+      : "+f"(a0), "+f"(a1)
+      : "f"(x0), "f"(x1), "f"(y0), "f"(y1));
+}
 // two fp32 -> packed bf16x2 (lo in the low half), round to nearest even, optional fused ReLU (one F2FP)
 __device__ __forceinline__ uint32_t cvt_bf16x2(float lo, float hi, bool relu) {
   uint32_t d;

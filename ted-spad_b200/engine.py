@@ -18,6 +18,8 @@ from .ops import CLTensor, PackedConv
 # GATHER feeds of csrc/conv_igemm.cu (kept for A/B measurements and as the general-shape path).
 USE_SLAB = os.environ.get("TEDSPAD_SLAB", "1") != "0"
 USE_PAIR = os.environ.get("TEDSPAD_PAIR", "1") != "0"     # cta_group::2 for the 64-output-channel 3x3 layers
+PAD_SMALL_3X3 = USE_SLAB and os.environ.get("TEDSPAD_PAD_SMALL_3X3", "1") != "0"
+MERGE_1X1 = os.environ.get("TEDSPAD_MERGE_1X1", "1") != "0"  # Inception b0/b1a/b2a (same input) as one GEMM
 USE_SLAB_STEM3D = USE_SLAB and os.environ.get("TEDSPAD_SLAB_STEM3D", "1") != "0"
 SLAB_WEIGHT_LIMIT = 150 * 1024   # bytes of resident weights that still leave room for three slab stages
 ENC_IN_CHANNELS = 4 if USE_SLAB_STEM3D else 8   # channel padding of the encoder input clip
@@ -235,8 +237,10 @@ class I3DExecutor:
 
         def unit(name, k, s=(1, 1, 1), cin_pad=None):
             w = sd[f"{name}.conv3d.weight"]
-            if USE_SLAB and k == (3, 3, 3) and w.shape[1] >= 64:
-                cin_pad = -(-w.shape[1] // 64) * 64   # SLAB feed: 64-channel K blocks (pad channels are zero)
+            if USE_SLAB and k == (3, 3, 3) and w.shape[1] >= (16 if PAD_SMALL_3X3 else 64):
+                # SLAB feed: 64-channel K blocks (pad channels are zero).  Also for the 16..48-channel b2b branches:
+                # up to 4x the MMA work, but through the slab feed instead of the instruction-bound GATHER feed
+                cin_pad = -(-w.shape[1] // 64) * 64
             self.specs[name] = (w, _bn(sd, f"{name}.bn", 1e-3), k, s, cin_pad)
 
         unit("Conv3d_1a_7x7", (7, 7, 7), (2, 2, 2), 8)
@@ -246,6 +250,18 @@ class I3DExecutor:
             for br, k in (("b0", 1), ("b1a", 1), ("b1b", 3), ("b2a", 1), ("b2b", 3), ("b3b", 1)):
                 unit(f"{name}.{br}", (k, k, k))
         self.packed = {}
+
+    def _packed_unit(self, name, x):
+        """PackedConv of a Unit3D for this input extent (1x1x1 units: no padding involved)."""
+        w, bn, k, s, cin_pad = self.specs[name]
+        key = (name, (0, 0, 0))
+        pc = self.packed.get(key)
+        if pc is None:
+            assert k == (1, 1, 1)
+            pc = PackedConv(w, None, bn, stride=s, pad_front=(0, 0, 0), cin_pad=cin_pad, device=self.device, n_align=16)
+            pc.slab = None
+            self.packed[key] = pc
+        return pc
 
     def _conv(self, name, x, y):
         """Unit3D.forward (i3d.py:89-120): SAME front pads depend on the input extent."""
@@ -290,13 +306,13 @@ class I3DExecutor:
         # b1a's output is stored with the channel padding b1b's feed wants (pad channels zero, never written)
         c1 = self.specs[f"{name}.b1b"][4] or oc[1]
         t1 = self.bufs.get(f"{name}.b1a", x.N, x.D, x.H, x.W, c1, zero=True)
+        c2 = self.specs[f"{name}.b2b"][4] or oc[3]
+        t2 = self.bufs.get(f"{name}.b2a", x.N, x.D, x.H, x.W, c2, zero=True)
 
         def b1():
-            self._unit(f"{name}.b1a", x, out=t1.slice(0, oc[1]))
             self._unit(f"{name}.b1b", t1, out=y.slice(oc[0], oc[2]))
 
         def b2():
-            t2 = self._unit(f"{name}.b2a", x, oc[3])
             self._unit(f"{name}.b2b", t2, out=y.slice(oc[0] + oc[2], oc[4]))
 
         def b3():
@@ -304,7 +320,19 @@ class I3DExecutor:
             self._unit(f"{name}.b3b", t3, out=y.slice(oc[0] + oc[2] + oc[4], oc[5]))
 
         # (running the four branches on side streams was measured on B200: no gain, the step is not latency-bound)
-        self._unit(f"{name}.b0", x, out=y.slice(0, oc[0]))
+        heads = [y.slice(0, oc[0]), t1.slice(0, oc[1]), t2.slice(0, oc[3])]
+        if MERGE_1X1:
+            # the three 1x1x1 convolutions that read x (i3d.py:144-148) as ONE GEMM over stacked weight rows: x crosses
+            # L2->SM once instead of three times and two launches disappear per block
+            key = (name, "heads")
+            pcm = self.packed.get(key)
+            if pcm is None:
+                pcm = ops.PackedConv.concat([self._packed_unit(f"{name}.{br}", x) for br in ("b0", "b1a", "b2a")])
+                self.packed[key] = pcm
+            ops.conv_forward(x, pcm, heads)
+        else:
+            for br, out in zip(("b0", "b1a", "b2a"), heads):
+                self._unit(f"{name}.{br}", x, out=out)
         b1(); b2(); b3()
         return y
 

@@ -144,6 +144,29 @@ class PackedConv:
         bp[:cout] = b
         self.bias = bp.to(device).contiguous()
 
+    @staticmethod
+    def concat(pcs):
+        """One GEMM for convolutions that read the same input (same kernel / stride / pads / cin_pad): their weight
+        rows are stacked, each block padded to a multiple of 16 rows.  Returns the merged PackedConv; .seg_begin[i]
+        is the first output column of pcs[i] (tedspad_conv y / y2 / y3)."""
+        a = pcs[0]
+        assert all((p.k, p.stride, p.pad_front, p.cin_pad, p.k_pad) == (a.k, a.stride, a.pad_front, a.cin_pad, a.k_pad)
+                   for p in pcs) and 1 <= len(pcs) <= 3
+        m = PackedConv.__new__(PackedConv)
+        m.cin, m.cin_pad, m.k, m.stride, m.pad_front, m.k_pad = a.cin, a.cin_pad, a.k, a.stride, a.pad_front, a.k_pad
+        rows = [(p.cout + 15) // 16 * 16 for p in pcs]
+        m.seg_begin = [sum(rows[:i]) for i in range(len(pcs))]
+        m.seg_cout = [p.cout for p in pcs]
+        m.cout = m.seg_begin[-1] + pcs[-1].cout
+        m.n_tile, m.cout_pad = n_tiling(sum(rows), 16)
+        w = torch.zeros(m.cout_pad, m.k_pad, dtype=BF16, device=a.w.device)
+        b = torch.zeros(m.cout_pad, dtype=torch.float32, device=a.bias.device)
+        for p, r0 in zip(pcs, m.seg_begin):
+            w[r0:r0 + p.cout] = p.w[:p.cout]
+            b[r0:r0 + p.cout] = p.bias[:p.cout]
+        m.w, m.bias = w.contiguous(), b.contiguous()
+        return m
+
     def out_extent(self, in_extent, pad_back=None):
         """Output (D,H,W) for an input (D,H,W); pad_back defaults to pad_front (symmetric)."""
         pb = self.pad_front if pad_back is None else pad_back
@@ -152,9 +175,18 @@ class PackedConv:
 
 
 def conv_forward(x, pc, y, res=None, act=L.ACT_RELU, feed=L.FEED_AUTO, y_fp32=False, max_ctas=0, n_tile=0):
-    """y = act(conv(x, pc) + bias (+ res)).  x, y, res are CLTensor views."""
+    """y = act(conv(x, pc) + bias (+ res)).  x, y, res are CLTensor views.  With a PackedConv.concat() merge, y is the
+    list of destination views (one per merged convolution)."""
     assert x.C == pc.cin_pad, f"input view has {x.C} channels, weights were packed for {pc.cin_pad}"
     d = L.ConvDesc()
+    if isinstance(y, (list, tuple)):
+        ys = list(y)
+        y = ys[0]
+        assert len(ys) == len(pc.seg_begin) and res is None and all(t.C == c for t, c in zip(ys, pc.seg_cout))
+        if len(ys) > 1:
+            d.y2, d.y2_begin = ys[1].desc(), pc.seg_begin[1]
+        if len(ys) > 2:
+            d.y3, d.y3_begin = ys[2].desc(), pc.seg_begin[2]
     d.x, d.y = x.desc(), y.desc()
     d.w, d.bias = pc.w.data_ptr(), pc.bias.data_ptr()
     if res is not None:

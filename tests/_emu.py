@@ -19,6 +19,13 @@ def _act(v, act):
 
 
 def conv_forward(x, pc, y, res=None, act=L.ACT_RELU, feed=L.FEED_AUTO, y_fp32=False, max_ctas=0, n_tile=0):
+    if isinstance(y, (list, tuple)):   # PackedConv.concat merge: one destination per stacked weight block
+        import copy
+        for yi, r0, co in zip(y, pc.seg_begin, pc.seg_cout):
+            sub = copy.copy(pc)
+            sub.w, sub.bias, sub.cout = pc.w[r0:r0 + co], pc.bias[r0:r0 + co], co
+            conv_forward(x, sub, yi, None, act, feed, y_fp32, max_ctas, n_tile)
+        return y[0]
     kd, kh, kw = pc.k
     ntaps = kd * kh * kw
     W2 = pc.w.float()[:pc.cout]  # [Cout, K_pad]

@@ -153,6 +153,50 @@ def group_flat():
     run_conv_case("F10 2d 64->16 3x3 (n_tile 16)", 2, (1, 12, 20), 64, 16, (1, 3, 3), halo=(0, 1, 1), feed=FL)
 
 
+def run_multi_case(name, N, dhw, cin, couts):
+    """b0 / b1a / b2a of an InceptionModule as ONE GEMM with three destinations (tedspad_conv y / y2 / y3)."""
+    try:
+        g = torch.Generator(device="cpu").manual_seed(cin + sum(couts))
+        D, H, W = dhw
+        x = torch.randn(N, cin, D, H, W, generator=g).to(DEV)
+        xc = ops.CLTensor.from_ncdhw(x)
+        pcs, refs = [], []
+        for co in couts:
+            w = (torch.randn(co, cin, 1, 1, 1, generator=g) / cin ** 0.5).to(DEV)
+            bnp = ((torch.rand(co, generator=g) + 0.5).to(DEV), (torch.rand(co, generator=g) - 0.5).to(DEV),
+                   (torch.rand(co, generator=g) - 0.5).to(DEV), (torch.rand(co, generator=g) + 0.5).to(DEV), 1e-3)
+            pc = ops.PackedConv(w, None, bnp, device=DEV)
+            pcs.append(pc)
+            wq = pc.w[:co, :cin].float().reshape(co, cin, 1, 1, 1)
+            refs.append(conv_ref(bf(x), wq, pc.bias[:co], (1, 1, 1), (0, 0, 0, 0, 0, 0), None, "relu"))
+        pcm = ops.PackedConv.concat(pcs)
+        # destinations: a slice of a wide buffer, a 64-channel padded scratch and a plain tensor
+        big = ops.CLTensor(N, D, H, W, couts[0] + 40, device=DEV)
+        big.buf.fill_(3.0)
+        t1 = ops.CLTensor(N, D, H, W, max(128, couts[1] + 16), device=DEV)
+        t1.buf.fill_(3.0)
+        t2 = ops.CLTensor(N, D, H, W, couts[2], device=DEV)
+        ys = [big.slice(8, couts[0]), t1.slice(0, couts[1]), t2]
+        ops.conv_forward(xc, pcm, ys)
+        torch.cuda.synchronize()
+        for i, (yv, ref) in enumerate(zip(ys, refs)):
+            report(f"{name}: destination {i} ({couts[i]} ch)", yv.to_ncdhw(), ref)
+        untouched = bool((big.buf[..., :8] == 3.0).all() and (big.buf[..., 8 + couts[0]:] == 3.0).all() and
+                         (t1.buf[..., couts[1]:] == 3.0).all())
+        RESULTS.append((name + ":slices", untouched))
+        print(f"[{'PASS' if untouched else 'FAIL'}] {name}: nothing written outside the destination slices")
+    except Exception:
+        RESULTS.append((name, False))
+        print(f"[FAIL] {name}: EXCEPTION\n{traceback.format_exc()}", flush=True)
+
+
+def group_multi():
+    run_multi_case("M1 Mixed_3b heads 192 -> 64|96|16 (FLAT)", 2, (4, 14, 14), 192, (64, 96, 16))
+    run_multi_case("M2 Mixed_4b heads 480 -> 192|96|16 (GATHER)", 2, (4, 14, 14), 480, (192, 96, 16))
+    run_multi_case("M3 Mixed_4c heads 512 -> 160|112|24", 2, (2, 7, 7), 512, (160, 112, 24))
+    run_multi_case("M4 Mixed_5c heads 832 -> 384|192|48 (3 N tiles)", 3, (2, 7, 7), 832, (384, 192, 48))
+
+
 def group_gather():
     G = L.FEED_GATHER
     run_conv_case("G1 2d 3(8)->64 3x3", 2, (1, 20, 20), 8, 64, (1, 3, 3), feed=G, cin_real=3)
