@@ -180,6 +180,7 @@ typedef struct tedspad_slab_plan {
   int32_t up_cb_first;      /* channel blocks >= this one are interpolated from `up` instead of loaded by TMA */
   int32_t stack_hp, stack_ph, stack_n;   /* stacked rows: padded image height, halo rows, batch (stack_hp 0 = off):
                                tile row g of row-tile ty is stacked row R = ph + 16*ty + g = image R / hp, row R % hp - ph */
+  int32_t acc_stages;       /* depth of the TMEM accumulator ring (2..4) */
   int32_t pair;             /* 1: CTA pairs (cluster of 2, cta_group::2); w_bytes / tab B offsets are per CTA (N/2 rows) */
   uint32_t tab[2 * TEDSPAD_SLAB_MAX_MMA];   /* per (k_stage, group): {A byte offset in slab, B byte offset in image} */
 } tedspad_slab_plan;

@@ -51,7 +51,7 @@ class SlabPlan(C.Structure):
                     "swizzle128", "merged_cw", "slab_bytes", "slab_stride", "w_bytes", "smem_bytes", "a_layout", "a_lbo", "a_sbo",
                     "b_layout", "b_lbo", "b_sbo", "half_a_off", "c_step", "x_step", "x_off", "y_step", "y_off",
                     "z_step", "z_off", "z_kstep", "tiles_x", "tiles_y", "tiles_z", "total_tiles", "b_stream", "b_stages",
-                    "b_stride", "cb_n", "cin", "num_n_tiles", "tab_per_stage", "up_cb_first", "stack_hp", "stack_ph", "stack_n", "pair")] +
+                    "b_stride", "cb_n", "cin", "num_n_tiles", "tab_per_stage", "up_cb_first", "stack_hp", "stack_ph", "stack_n", "acc_stages", "pair")] +
                 [("tab", C.c_uint32 * (2 * SLAB_MAX_MMA))])
 
 

@@ -38,13 +38,31 @@ constexpr int SLAB_SMEM_BUDGET = 227 * 1024;
 constexpr int SLAB_TAIL_BYTES = 2048 /*bias*/ + 1024 /*outconv w,b*/ + 512 /*barriers*/;
 constexpr int SLAB_MAX_BSTAGES = 8;
 constexpr int SLAB_MAX_STAGES = 6;
+constexpr int SLAB_MAX_ACC = 4;      // TMEM accumulator ring depth (2..4: as many as fit in the 512 columns)
+
+// n / d for any 32-bit n >= 0 with magic = ceil(2^64 / d) (0 encodes d == 1): exact because n * d < 2^64.  A hardware
+// integer division is ~25 instructions; the epilogue warps decode (n_tile, tx, ty, tz, image, row) for every tile,
+// and those warps run at one instruction per ~5 clocks (ncu: 20 % issue-selected).
+struct DivMagic {
+  uint64_t m;
+  int d;
+};
+__device__ __forceinline__ int fdiv(int n, const DivMagic& k) {
+  return k.m ? static_cast<int>(__umul64hi(static_cast<uint64_t>(static_cast<uint32_t>(n)), k.m)) : n;
+}
+static DivMagic make_div(int d) {
+  DivMagic k;
+  k.d = d;
+  k.m = d <= 1 ? 0 : (~0ULL / static_cast<uint64_t>(d)) + 1;   // = ceil(2^64 / d) for every d >= 2
+  return k;
+}
 
 struct SlabKParams {
   CUtensorMap tmA;
   CUtensorMap tmB;           // streamed weights: standard packed [Cout_pad][K_pad], box {64, n_tile}
   const uint8_t* w_image;
   const float* bias;
-  int tm, n_tile, k_stages, n_grp, nk, a_kstep, b_kstep, stages, tmem_cols;
+  int tm, n_tile, k_stages, n_grp, nk, a_kstep, b_kstep, stages, tmem_cols, acc_stages;
   int slab_bytes, slab_stride, w_bytes, w_stride, zero_slabs;
   int b_stream, b_stages, b_stride, cb_n, cin, num_n_tiles, tab_per_stage;
   // fused x2 bilinear up-sampling source (channel blocks >= up_cb_first are interpolated into the slab)
@@ -55,6 +73,7 @@ struct SlabKParams {
   int half_a_off;
   int c_step, x_step, x_off, y_step, y_off, z_step, z_off, z_kstep, merged_cw;
   int tiles_x, tiles_y, tiles_z, total_tiles;
+  DivMagic dv_nt, dv_tx, dv_ty, dv_tz, dv_hp;   // divisors: num_n_tiles, tiles_x, tiles_y, tiles_z, stack_hp
   int stack_hp, stack_ph, stack_n;   // stacked rows (see make_plan): padded image height, halo rows, batch; 0 = off
   uint64_t a_desc, b_desc;
   // epilogue
@@ -171,8 +190,7 @@ __device__ __forceinline__ void slab_issue(const SlabKParams& p, uint8_t* smS, u
     }
     if (elect_one()) { if (PAIR) umma_commit_pair(tfull + as); else umma_commit(tfull + as); }
     __syncwarp();
-    as ^= 1;
-    if (as == 0) aph ^= 1;
+    if (++as == p.acc_stages) { as = 0; aph ^= 1; }
   }
 }
 
@@ -234,8 +252,10 @@ __device__ __forceinline__ void slab_epi_chunk(const EpiCtx& c, const uint32_t (
         oc[o] += (a0 + a1) + (b0 + b1);
       }
     }
+    if (c.y != nullptr || c.pool != nullptr) {   // (OutConv-only launches never write the 64-channel tensor)
 #pragma unroll
-    for (int i = 0; i < 16; ++i) q[i] = pack_bf162(f[2 * i], f[2 * i + 1]);
+      for (int i = 0; i < 16; ++i) q[i] = pack_bf162(f[2 * i], f[2 * i + 1]);
+    }
   }
   if (c.y != nullptr && valid) {
     // each lane owns 64 contiguous bytes of its pixel: two 32-byte stores (a warp store instruction touches 32
@@ -334,8 +354,8 @@ conv_slab_kernel(const __grid_constant__ SlabKParams p) {
   uint64_t* full = reinterpret_cast<uint64_t*>(sm_ocw + 256);
   uint64_t* empty = full + SLAB_MAX_STAGES;
   uint64_t* tfull = empty + SLAB_MAX_STAGES;
-  uint64_t* tempty = tfull + 2;
-  uint64_t* wbar = tempty + 2;
+  uint64_t* tempty = tfull + SLAB_MAX_ACC;
+  uint64_t* wbar = tempty + SLAB_MAX_ACC;
   uint64_t* bfull = wbar + 1;
   uint64_t* bempty = bfull + SLAB_MAX_BSTAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bempty + SLAB_MAX_BSTAGES);
@@ -353,7 +373,7 @@ conv_slab_kernel(const __grid_constant__ SlabKParams p) {
       mbar_init(full + s, HAS_UP ? 1 + 4 : 1);
       mbar_init(empty + s, 1);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < p.acc_stages; ++a) {
       mbar_init(tfull + a, 1);
       mbar_init(tempty + a, PAIR ? 16 : 8);   // PAIR (leader): the epilogue warps of both CTAs
     }
@@ -483,19 +503,23 @@ conv_slab_kernel(const __grid_constant__ SlabKParams p) {
     int as = 0;
     uint32_t aph = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      int t = tile;
-      const int n0 = (t % p.num_n_tiles) * n_tile; t /= p.num_n_tiles;   // first output channel of this N tile
-      const int tx = t % p.tiles_x; t /= p.tiles_x;
-      const int ty = t % p.tiles_y; t /= p.tiles_y;
-      const int tz = t % p.tiles_z;
-      int n = t / p.tiles_z;
+      int t = tile, q;
+      q = fdiv(t, p.dv_nt);
+      const int n0 = (t - q * p.dv_nt.d) * n_tile; t = q;   // first output channel of this N tile
+      q = fdiv(t, p.dv_tx);
+      const int tx = t - q * p.dv_tx.d; t = q;
+      q = fdiv(t, p.dv_ty);
+      const int ty = t - q * p.dv_ty.d; t = q;
+      q = fdiv(t, p.dv_tz);
+      const int tz = t - q * p.dv_tz.d;
+      int n = q;
       int oy = ty * 16 + g;
       const int ox = (tx * tm + h) * 8 + r;
       bool valid = ox < OW;
       if (p.stack_hp) {
         // stacked rows: the tile's 16 rows are consecutive rows of the zero-haloed images of the whole batch
         const int R = oy + p.stack_ph;
-        n = R / p.stack_hp;
+        n = fdiv(R, p.dv_hp);
         oy = R - n * p.stack_hp - p.stack_ph;
         valid = valid && n < p.stack_n;
       }
@@ -549,8 +573,7 @@ conv_slab_kernel(const __grid_constant__ SlabKParams p) {
           if (p.oc_frames != nullptr) p.oc_frames[o0 + o * plane] = sgm;
         }
       }
-      as ^= 1;
-      if (as == 0) aph ^= 1;
+      if (++as == p.acc_stages) { as = 0; aph ^= 1; }
     }
   }
 
@@ -933,7 +956,12 @@ static int make_plan(const tedspad_conv_slab& c, tedspad_slab_plan& P) {
   }
   P.smem_bytes = 1024 + w_stride + P.stages * P.slab_stride + SLAB_TAIL_BYTES;
   int tc = 32;
-  while (tc < 2 * P.tm * P.n_tile) tc <<= 1;
+  // accumulator ring: the epilogue of tile i overlaps the MMAs of tiles i+1 .. i+acc-1.  Two stages are enough when
+  // a tile holds several K stages; with ONE K stage per tile (64 -> 64) the hand-back round trip (commit -> epilogue
+  // -> arrive, across the CTA pair) is longer than a tile's MMAs and the issuer stalled on `tempty` (28 polls per
+  // tile in profiles/r1d): use every TMEM column that is there.
+  P.acc_stages = std::max(2, std::min(SLAB_MAX_ACC, 512 / (P.tm * P.n_tile)));
+  while (tc < P.acc_stages * P.tm * P.n_tile) tc <<= 1;
   TSP_CHECK(tc <= 512, "slab: %d TMEM columns needed", tc);
   P.tmem_cols = tc;
   const int64_t total = batch * P.tiles_z * P.tiles_y * P.tiles_x * P.num_n_tiles;
@@ -1025,7 +1053,7 @@ extern "C" int tedspad_conv_slab_forward(const tedspad_conv_slab* c, void* strea
   }
   p.tm = P.tm; p.n_tile = P.n_tile; p.k_stages = P.k_stages; p.n_grp = P.n_grp; p.nk = P.nk; p.stages = P.stages;
   p.a_kstep = P.a_kstep; p.b_kstep = P.b_kstep;
-  p.tmem_cols = P.tmem_cols;
+  p.tmem_cols = P.tmem_cols; p.acc_stages = P.acc_stages;
   p.slab_bytes = P.slab_bytes; p.slab_stride = P.slab_stride; p.w_bytes = P.w_bytes;
   p.w_stride = P.b_stream ? P.b_stages * P.b_stride : (int)round_up(P.w_bytes, 1024);
   p.zero_slabs = P.swizzle128 ? 0 : 1;
@@ -1034,6 +1062,8 @@ extern "C" int tedspad_conv_slab_forward(const tedspad_conv_slab* c, void* strea
   p.z_step = P.z_step; p.z_off = P.z_off; p.z_kstep = P.z_kstep; p.merged_cw = P.merged_cw;
   p.tiles_x = P.tiles_x; p.tiles_y = P.tiles_y; p.tiles_z = P.tiles_z; p.total_tiles = P.total_tiles;
   p.stack_hp = P.stack_hp; p.stack_ph = P.stack_ph; p.stack_n = P.stack_n;
+  p.dv_nt = make_div(P.num_n_tiles); p.dv_tx = make_div(P.tiles_x); p.dv_ty = make_div(P.tiles_y);
+  p.dv_tz = make_div(P.tiles_z); p.dv_hp = make_div(P.stack_hp > 0 ? P.stack_hp : 1);
   p.a_desc = umma_desc_template(P.a_layout, P.a_lbo, P.a_sbo);
   p.b_desc = umma_desc_template(P.b_layout, P.b_lbo, P.b_sbo);
   const int n_tab = P.tab_per_stage ? P.k_stages * P.n_grp : P.n_grp;
