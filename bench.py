@@ -40,12 +40,13 @@ def measured_peaks():
 
 
 def ncu_traffic(batch_clips):
-    """dram__bytes_read.sum + dram__bytes_write.sum of all convolution launches of one step, from the committed ncu
-    capture of `tests/profile_step.py 32` (profiles/r1_conv_dram_bytes.json); None for any other batch size."""
-    p = os.path.join(ROOT, "profiles", "r1_conv_dram_bytes.json")
-    if not os.path.exists(p):
+    """dram__bytes_read.sum + dram__bytes_write.sum of all convolution launches of one step, from the newest committed
+    ncu capture of `tests/profile_step.py 32` (profiles/r1*_conv_dram_bytes.json); None for any other batch size."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_conv_dram_bytes.json")))
+    if not files:
         return None
-    d = json.load(open(p))
+    d = json.load(open(files[-1]))
     return d["dram_bytes_per_step"] if d.get("batch_clips") == batch_clips else None
 
 

@@ -219,3 +219,24 @@ def extract_dataset(extractor, videos, save_folder, rank=0, world_size=1, log=pr
         os.replace(tmp, out)
         written.append(out)
     return written
+
+
+def extract_dataset_distributed(extractor, videos, save_folder, log=print):
+    """extract_dataset under torch.distributed (one process per GPU, `torchrun`): rank / world size come from the
+    process group, every rank extracts its own shard with NO collective on the data path, and the run manifest
+    (which rank wrote which file) is gathered on the host afterwards - the "host-side gather of feature files" of
+    the north star.  Returns {path: rank} on every rank.  Works with the gloo and nccl backends."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return {w: 0 for w in extract_dataset(extractor, videos, save_folder, 0, 1, log)}
+    rank, world = dist.get_rank(), dist.get_world_size()
+    written = extract_dataset(extractor, videos, save_folder, rank, world, log)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, written)          # control plane only: file names, after the work is done
+    manifest = {}
+    for r, files in enumerate(gathered):
+        for f in files:
+            if f in manifest:
+                raise RuntimeError(f"{f} was written by ranks {manifest[f]} and {r}: the shards overlap")
+            manifest[f] = r
+    return manifest

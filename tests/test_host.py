@@ -248,3 +248,66 @@ def test_shard_videos_properties():
         assert flat == list(range(97))                      # a partition: every video exactly once
         loads = [sum(lengths[i] for i in s) for s in shards]
         assert max(loads) - min(loads) <= max(lengths)      # LPT balance bound
+
+
+# ------------------------------------------------------------------------- N > 1 host logic (gloo, CPU)
+class _StubExtractor:
+    """Deterministic stand-in for SnippetExtractor.extract_video (the CUDA path cannot run here): features are a
+    function of the frames only, so sharded and single-process runs must produce identical files."""
+
+    def extract_video(self, frames):
+        n = extraction.dali_snippet_frames(frames.shape[0]).shape[0]
+        base = frames.reshape(frames.shape[0], -1).double().mean(1)
+        return np.stack([np.full(8, float(base[min(32 * i, frames.shape[0] - 1)]) + i) for i in range(n)]) if n else np.zeros((0, 8))
+
+
+def _stub_videos():
+    rs = np.random.RandomState(3)
+    vids = []
+    for i, n in enumerate(rs.randint(20, 400, 13).tolist()):
+        def loader(i=i, n=n):
+            g = torch.Generator().manual_seed(100 + i)
+            return torch.randint(0, 256, (n, 4, 4, 3), generator=g, dtype=torch.uint8)
+        vids.append((f"/data/vid_{i:02d}.mp4", n, loader))
+    return vids
+
+
+def _gloo_worker(rank, world, port, folder, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        manifest = extraction.extract_dataset_distributed(_StubExtractor(), _stub_videos(), folder, log=lambda *_: None)
+        q.put((rank, manifest))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world_size_2_gloo_sharded_extraction_equals_single(tmp_path):
+    """Two processes over gloo: disjoint shards, every file written exactly once, no data-path collective, the
+    gathered manifest identical on both ranks, and the files bit-identical to a single-process run."""
+    import socket
+    import torch.multiprocessing as mp
+    single = tmp_path / "single"
+    extraction.extract_dataset(_StubExtractor(), _stub_videos(), str(single), log=lambda *_: None)
+    with socket.socket() as s_:
+        s_.bind(("127.0.0.1", 0))
+        port = s_.getsockname()[1]
+    sharded = tmp_path / "sharded"
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, str(sharded), q)) for r in range(2)]
+    for p_ in procs:
+        p_.start()
+    results = dict(q.get(timeout=120) for _ in range(2))
+    for p_ in procs:
+        p_.join(timeout=60)
+        assert p_.exitcode == 0
+    assert results[0] == results[1] and len(results[0]) == 13
+    expect = extraction.shard_videos([v[1] for v in _stub_videos()], 2)
+    for r in (0, 1):
+        mine = sorted(os.path.basename(f) for f, owner in results[0].items() if owner == r)
+        assert mine == sorted(f"vid_{i:02d}.npy" for i in expect[r])
+    for f in sorted(os.listdir(single)):
+        assert np.array_equal(np.load(single / f), np.load(sharded / f)), f
+    assert sorted(os.listdir(single)) == sorted(os.listdir(sharded))
