@@ -121,19 +121,29 @@ def cpu_reference_clips_per_s(n_timed=3, threads=None):
     return 1.0 / per_clip, threads, f"{n_timed} clips of 16x240x320 uint8 frames, batch 1, fp32, after 1 warm-up"
 
 
+def workload_config(batch_clips):
+    """The workload both arms are quoted on (BASELINE.json configs[1])."""
+    return {"workload": "anonymizer UNet + I3D snippet features, 16x224x224 clips, batch %d per GPU (BASELINE configs[1]) "
+                        "from %d decoded uint8 240x320 frames per step" % (batch_clips, batch_clips * T),
+            "batch_clips_per_gpu": batch_clips,
+            "l2": "inputs larger than L2 (%d MB uint8 per step, two alternating sets; activations ~%d GB per step)"
+                  % (batch_clips * T * SRC_HW[0] * SRC_HW[1] * 3 // 1000000, round(26 * batch_clips / 32)),
+            "weights": "random init (seeded stock init of the reference architecture)"}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 3))
+    steps = max(1, min(args.steps, 10))   # 1 clip per step, ~1 s each on the box's host cores
     t0 = time.perf_counter()
     cps, threads, sample = cpu_reference_clips_per_s(n_timed=steps)
     line = {
         "impl": "reference", "metric": "snippet_clips_per_s", "value": cps, "unit": "clips/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": 1, "ms_per_step": 1000.0 / cps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-        "config": {"workload": "anonymizer UNet + I3D snippet features, 16x224x224 clips (BASELINE configs[1]); "
-                               "each step = 1 clip on the host CPU (bounded sample of the 32-clip batch)"},
+        "config": dict(workload_config(BATCH_CLIPS), reference_sample="each step = 1 clip of that workload on the host CPU "
+                       "(batch 1 like params_feature_ex.py:4), all host threads"),
         "cpu_baseline": {"value": cps, "unit": "clips/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": cps, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": time.perf_counter() - t0,
@@ -179,18 +189,27 @@ def main():
     # inputs larger than L2: 512 frames x 230 KB = 118 MB of uint8 per step, two alternating input sets
     host_sets = [synthetic_frames(1000 + rank * 10 + i, n_frames, SRC_HW).pin_memory() for i in range(2)]
     dev_sets = [h.to(device) for h in host_sets]
-    feat_host = torch.empty((B, 1, 1024), dtype=torch.float32).pin_memory()
 
     def step_resident(i):
         return ext.features_of_clips(dev_sets[i % 2], desc, (ch, cw))
 
+    feat_ring = [torch.empty((B, 1, 1024), dtype=torch.float32).pin_memory() for _ in range(2)]
+
     def run_e2e(steps):
         """The public streaming API on HOST frames: every step's H2D copy (pinned memory, copy stream; overlaps the
-        previous step's kernels) and the D2H read of its feature rows are inside the timed region."""
+        previous step's kernels) and the D2H read of its feature rows are inside the timed region.  The host waits
+        for step i-1's rows to have landed before it enqueues step i+1 (one step of slack keeps the GPU fed)."""
         batches = ((host_sets[i % 2], desc, (ch, cw)) for i in range(steps))
-        for f in ext.features_stream(batches):
-            feat_host.copy_(f, non_blocking=True)                     # D2H of the step's feature rows
-            torch.cuda.current_stream().synchronize()
+        done = []
+        for i, f in enumerate(ext.features_stream(batches)):
+            feat_ring[i % 2].copy_(f, non_blocking=True)              # D2H of this step's feature rows
+            ev = torch.cuda.Event()
+            ev.record()
+            done.append(ev)
+            if i >= 1:
+                done[i - 1].synchronize()                             # step i-1's rows are in host memory
+        if done:
+            done[-1].synchronize()
 
     def barrier():
         if dist is not None:
@@ -245,22 +264,19 @@ def main():
         "metric": "snippet_clips_per_s", "value": clips_per_s, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "anonymizer UNet + I3D snippet features, 16x224x224 clips, batch 32 per GPU "
-                               "(BASELINE configs[1]) from 512 decoded uint8 240x320 frames per step",
-                   "batch_clips_per_gpu": B, "l2": "inputs larger than L2 (118 MB uint8 per step, two alternating sets; "
-                   "activations ~26 GB per step)", "weights": "random init (seeded stock init of the reference architecture)"},
+        "config": workload_config(B),
         "tflops_algorithmic": clips_per_s * GFLOP_CLIP / 1e3 / world,
         "roofline": {"bound": "tensor", "kernel": "conv_slab_kernel + conv_igemm_kernel (all %d convolution launches of a step)" % n_conv,
                      "achieved": conv_tflops, "peak": sustained, "unit": "TFLOP/s", "frac": conv_tflops / sustained,
                      "peak_burst": burst, "peak_source": how + " bf16_tflops_sustained (kernel timed inside a long step)",
                      "conv_ms_per_step": conv_ms, "conv_share_of_step": conv_ms / ms_step, "traffic": ncu_traffic(B)},
         "e2e": {"value": e2e_cps, "unit": "clips/s", "h2d_bytes_per_step": int(host_sets[0].numel()),
-                "d2h_bytes_per_step": int(feat_host.numel() * 4)},
+                "d2h_bytes_per_step": int(feat_ring[0].numel() * 4)},
         "gpu_launches": launches,
         "clocks": sampler.result(),
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cps, threads, sample = cpu_reference_clips_per_s(n_timed=3)
+        cps, threads, sample = cpu_reference_clips_per_s(n_timed=8)
         line["cpu_baseline"] = {"value": cps, "unit": "clips/s", "cores": threads, "kind": "port", "sample": sample}
     if rank == 0:
         print(json.dumps(line), flush=True)
