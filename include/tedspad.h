@@ -120,6 +120,9 @@ int tedspad_conv_forward(const tedspad_conv* p, void* stream);
  *                        (128 + 32) rows per step = 80 %.  The 64-output-channel DoubleConv layers.  Needs
  *                        Cout_pad % 32 == 0, W > 8 and an even tile count; same fused epilogues as 3X3; the image
  *                        from tedspad_conv_slab_pack(kind = PAIR) holds the two halves back to back.
+ *   TEDSPAD_SLAB_3X3_STREAM_PAIR  TEDSPAD_SLAB_3X3_STREAM executed by CTA pairs: every CTA streams HALF of each weight
+ *                        block's rows.  One N tile (Cout_pad <= 256, multiple of 32), even tile count.  The N = 128
+ *                        layers, whose single-CTA MMA reads shared memory at exactly its 128 B/clk limit.
  * Optional fused producer (single-CTA 3X3 kinds, 2-D): `up` = the low-resolution tensor of Up.forward; its x2 bilinear
  * (align_corners=True) up-sampling is computed by four producer warps straight into the shared-memory slab,
  * so the up-sampled half of torch.cat([x2, x1]) (unet_parts.py:67) is never written to or read from HBM.
@@ -130,7 +133,7 @@ int tedspad_conv_forward(const tedspad_conv* p, void* stream);
  * tedspad_conv_slab_pack() from the standard packed layout of tedspad_conv.
  */
 enum { TEDSPAD_SLAB_3X3 = 0, TEDSPAD_SLAB_STEM2D = 1, TEDSPAD_SLAB_STEM3D = 2, TEDSPAD_SLAB_3X3_STREAM = 3,
-       TEDSPAD_SLAB_3X3_PAIR = 4 };
+       TEDSPAD_SLAB_3X3_PAIR = 4, TEDSPAD_SLAB_3X3_STREAM_PAIR = 5 };
 
 typedef struct tedspad_conv_slab {
   tedspad_tensor x;         /* bf16 input view (see kinds above) */

@@ -133,7 +133,7 @@ __device__ __forceinline__ void slab_issue(const SlabKParams& p, uint8_t* smS, u
   const uint32_t b_step = static_cast<uint32_t>(p.b_stride >> 4);
   const int BS = p.b_stages, tab_ps = p.tab_per_stage;
   if (!STREAM) mbar_wait(wbar, 0);
-  if (PAIR) mbar_wait_cluster(bfull, 0);   // the peer's half of the weights has landed in ITS shared memory
+  if (PAIR && !STREAM) mbar_wait_cluster(bfull, 0);   // the peer's half of the weights has landed in ITS shared memory
   int s = 0, as = 0, bs = 0;
   uint32_t ph = 0, aph = 0, bph = 0;
   for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
@@ -176,7 +176,7 @@ __device__ __forceinline__ void slab_issue(const SlabKParams& p, uint8_t* smS, u
               else umma_bf16_nc(d1, ad1, bd, idesc, k == 0 ? acc0 : 1u);
             }
           }
-          if (STREAM) umma_commit(bempty + bs);
+          if (STREAM) { if (PAIR) umma_commit_pair(bempty + bs); else umma_commit(bempty + bs); }
         }
         if (STREAM) {
           __syncwarp();
@@ -378,7 +378,7 @@ conv_slab_kernel(const __grid_constant__ SlabKParams p) {
       mbar_init(tempty + a, PAIR ? 16 : 8);   // PAIR (leader): the epilogue warps of both CTAs
     }
     mbar_init(wbar, 1);
-    if (PAIR) mbar_init(bfull, 1);           // leader: "the peer's weights are resident"
+    if (PAIR && !p.b_stream) mbar_init(bfull, 1);   // leader: "the peer's weights are resident"
     for (int b = 0; b < p.b_stages; ++b) {
       mbar_init(bfull + b, 1);
       mbar_init(bempty + b, 1);
@@ -452,8 +452,15 @@ conv_slab_kernel(const __grid_constant__ SlabKParams p) {
             // one [n_tile x 64] weight block per filter tap, K ordered (kd,kh,kw,cin): tap kt*n_grp+g, block cb
             for (int g = 0; g < p.n_grp; ++g) {
               mbar_wait(bempty + bs, bph ^ 1);
-              mbar_arrive_expect_tx(bfull + bs, static_cast<uint32_t>(p.b_stride));
-              tma_load_2d(smW + bs * p.b_stride, &p.tmB, bfull + bs, (kt * p.n_grp + g) * p.cin + cb * 64, nt * p.n_tile);
+              if (PAIR) {
+                // each CTA streams HALF of the block's rows; both halves complete on the leader's barrier
+                if (rank == 0) mbar_arrive_expect_tx(bfull + bs, 2u * static_cast<uint32_t>(p.b_stride));
+                tma_load_2d_pair(smW + bs * p.b_stride, &p.tmB, mapa_u32(smem_u32(bfull + bs), 0),
+                                 (kt * p.n_grp + g) * p.cin + cb * 64, nt * p.n_tile + static_cast<int>(rank) * (p.n_tile >> 1));
+              } else {
+                mbar_arrive_expect_tx(bfull + bs, static_cast<uint32_t>(p.b_stride));
+                tma_load_2d(smW + bs * p.b_stride, &p.tmB, bfull + bs, (kt * p.n_grp + g) * p.cin + cb * 64, nt * p.n_tile);
+              }
               if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
             }
           }
@@ -467,8 +474,14 @@ conv_slab_kernel(const __grid_constant__ SlabKParams p) {
 #define TSP_ISSUE(TM_, NK_, ST_) slab_issue<TM_, NK_, ST_, false>(p, smS, wa, tb, full, empty, tfull, tempty, wbar, bfull, bempty)
     if (PAIR) {
       if (rank == 0) {
-        slab_issue<2, 4, false, true>(p, smS, wa, tb, full, empty, tfull, tempty, wbar, bfull, bempty);
-      } else {
+#define TSP_ISSUE_PAIR(TM_, ST_) slab_issue<TM_, 4, ST_, true>(p, smS, wa, tb, full, empty, tfull, tempty, wbar, bfull, bempty)
+        if (p.b_stream) {
+          if (p.tm == 2) TSP_ISSUE_PAIR(2, true); else TSP_ISSUE_PAIR(1, true);
+        } else {
+          TSP_ISSUE_PAIR(2, false);
+        }
+#undef TSP_ISSUE_PAIR
+      } else if (!p.b_stream) {
         // peer: report its half of the weights resident, then leave the issuing to the leader
         mbar_wait(wbar, 0);
         if (lane == 0) mbar_arrive_cluster_release(mapa_u32(smem_u32(bfull), 0));
@@ -706,8 +719,8 @@ static int make_plan(const tedspad_conv_slab& c, tedspad_slab_plan& P) {
   memset(&P, 0, sizeof(P));
   const tedspad_tensor& x = c.x;
   const tedspad_tensor& y = c.y;
-  const bool stream = c.kind == TEDSPAD_SLAB_3X3_STREAM;
-  const bool pair = c.kind == TEDSPAD_SLAB_3X3_PAIR;
+  const bool stream = c.kind == TEDSPAD_SLAB_3X3_STREAM || c.kind == TEDSPAD_SLAB_3X3_STREAM_PAIR;
+  const bool pair = c.kind == TEDSPAD_SLAB_3X3_PAIR || c.kind == TEDSPAD_SLAB_3X3_STREAM_PAIR;
   P.pair = pair ? 1 : 0;
   TSP_CHECK(c.Cout_pad % 32 == 0 && c.Cout_pad >= 32 && c.Cout_pad <= (stream ? 512 : 256) && c.Cout <= c.Cout_pad &&
                 c.Cout >= 1 && c.Cout % 8 == 0,
@@ -737,7 +750,7 @@ static int make_plan(const tedspad_conv_slab& c, tedspad_slab_plan& P) {
   }
   const int cin_total = x.C + (has_up ? c.up.C : 0);
   P.up_cb_first = has_up ? x.C / 64 : 1 << 20;
-  if (c.kind == TEDSPAD_SLAB_3X3 || c.kind == TEDSPAD_SLAB_STEM2D || pair) {
+  if (c.kind == TEDSPAD_SLAB_3X3 || c.kind == TEDSPAD_SLAB_STEM2D || c.kind == TEDSPAD_SLAB_3X3_PAIR) {
     TSP_CHECK(c.kd == 1 && c.kh == 3 && c.kw == 3 && c.sd == 1 && c.sh == 1 && c.sw == 1 && c.pd == 0 && c.ph == 1 &&
                   c.pw == 1,
               "slab: kind %d needs a (1,3,3) stride-1 pad-1 convolution", c.kind);
@@ -823,7 +836,7 @@ static int make_plan(const tedspad_conv_slab& c, tedspad_slab_plan& P) {
         P.tab[2 * ky + 1] = static_cast<uint32_t>(ky * 2 * P.b_kstep);
       }
     }
-  } else if (c.kind == TEDSPAD_SLAB_3X3_STREAM) {
+  } else if (stream) {
     TSP_CHECK((c.kd == 1 || c.kd == 3) && c.kh == 3 && c.kw == 3 && c.sd == 1 && c.sh == 1 && c.sw == 1 &&
                   c.pd == c.kd / 2 && c.ph == 1 && c.pw == 1,
               "slab stream: needs a (1|3,3,3) stride-1 same-padded convolution");
@@ -838,7 +851,12 @@ static int make_plan(const tedspad_conv_slab& c, tedspad_slab_plan& P) {
     P.n_grp = 9; P.nk = 4; P.n_mma = 36;
     P.tab_per_stage = 0;      // the 9 tap offsets are the same for every K stage
     P.b_stream = 1;
-    P.b_stride = P.n_tile * 128;
+    // CTA pairs: every CTA streams half of each weight block's rows (the MMA reads N/2 rows from either SM), which
+    // takes the N = 128 layers off the shared-memory read limit ((128 + 128) rows per K step = exactly 128 B/clk,
+    // 70-80 % tensor-active once the TMA fills compete; (128 + 64) rows leave room) and halves the weight traffic
+    TSP_CHECK(!pair || (P.num_n_tiles == 1 && P.n_tile % 32 == 0),
+              "slab stream pair: one N tile (Cout_pad <= 256, multiple of 32) needed, got %d x %d", P.n_tile, P.num_n_tiles);
+    P.b_stride = (pair ? P.n_tile / 2 : P.n_tile) * 128;
     int tm = c.tm;
     if (tm == 0) tm = (x.W > 8 && 4 * P.n_tile <= 512) ? 2 : 1;
     TSP_CHECK((tm == 1 || tm == 2) && 2 * tm * P.n_tile <= 512, "slab stream: tm=%d with n_tile=%d exceeds TMEM", tm, P.n_tile);
@@ -928,7 +946,7 @@ static int make_plan(const tedspad_conv_slab& c, tedspad_slab_plan& P) {
   // the halo rows themselves are computed in vain (58/56, 30/28).  Tile row 0 = stacked row ph, so that with an
   // even padded height the 2x2 pooling pairs of the fused MaxPool2d never straddle tiles or images.
   int64_t batch = x.N;
-  const bool kind3x3 = c.kind == TEDSPAD_SLAB_3X3 || c.kind == TEDSPAD_SLAB_3X3_STREAM || pair;
+  const bool kind3x3 = c.kind == TEDSPAD_SLAB_3X3 || stream || pair;
   if (kind3x3 && c.stack_rows >= 0 && x.D == 1 && x.pd == 0 && c.kd == 1 && x.ph >= 1 && !has_up && x.N > 1 &&
       (c.stack_rows > 0 || Hp < round_up(x.H, 16)) && (c.pool.ptr == nullptr || Hp % 2 == 0)) {
     P.stack_hp = Hp; P.stack_ph = x.ph; P.stack_n = x.N;
@@ -943,7 +961,7 @@ static int make_plan(const tedspad_conv_slab& c, tedspad_slab_plan& P) {
   int w_stride = static_cast<int>(round_up(P.w_bytes, 1024));
   if (P.b_stream) {
     // two (tm=2) or three slab stages; the rest of shared memory is the weight-block ring
-    P.stages = P.tm == 2 ? 2 : 3;
+    P.stages = (P.tm == 2 && !pair) ? 2 : 3;   // (a pair's half-size weight blocks leave room for a third 16x16 slab)
     const int avail_b = SLAB_SMEM_BUDGET - 1024 - SLAB_TAIL_BYTES - P.stages * P.slab_stride;
     P.b_stages = std::min(SLAB_MAX_BSTAGES, avail_b / P.b_stride);
     TSP_CHECK(P.b_stages >= 3, "slab stream: only %d weight-block stages fit", P.b_stages);
@@ -1048,7 +1066,7 @@ extern "C" int tedspad_conv_slab_forward(const tedspad_conv_slab* c, void* strea
   if (P.b_stream) {
     // w_image holds the STANDARD packed weights [Cout_pad][K_pad] for the streaming kind
     if (encode_tmap_2d_bf16(&p.tmB, c->w_image, (uint64_t)c->K_pad, (uint64_t)c->Cout_pad, (uint64_t)c->K_pad * 2, 64,
-                            (uint32_t)P.n_tile))
+                            (uint32_t)(P.pair ? P.n_tile / 2 : P.n_tile)))
       return 3;
   }
   p.tm = P.tm; p.n_tile = P.n_tile; p.k_stages = P.k_stages; p.n_grp = P.n_grp; p.nk = P.nk; p.stages = P.stages;
@@ -1077,7 +1095,8 @@ extern "C" int tedspad_conv_slab_forward(const tedspad_conv_slab* c, void* strea
   if (c->pool.ptr != nullptr) {
     const tedspad_tensor& q = c->pool;
     if (check_tensor(q, "slab.pool", 8)) return 1;
-    TSP_CHECK((c->kind == TEDSPAD_SLAB_3X3 || c->kind == TEDSPAD_SLAB_3X3_STREAM || c->kind == TEDSPAD_SLAB_3X3_PAIR) &&
+    TSP_CHECK((c->kind == TEDSPAD_SLAB_3X3 || c->kind == TEDSPAD_SLAB_3X3_STREAM || c->kind == TEDSPAD_SLAB_3X3_PAIR ||
+               c->kind == TEDSPAD_SLAB_3X3_STREAM_PAIR) &&
                   y.D == 1 && q.D == 1 && q.pd == 0 &&
                   q.N == y.N && q.C == c->Cout &&
                   q.H == y.H / 2 && q.W == y.W / 2,

@@ -45,6 +45,10 @@ def slab3x3(pc, max_stream_cout=512):
         # At N = 128 the halved weight image makes room for 16x16 tiles (measured +7 %).
         return ops.PackedSlabConv(pc, L.SLAB_3X3_PAIR if (USE_PAIR and pc.cout_pad in (64, 128)) else L.SLAB_3X3)
     if pc.cout_pad <= max_stream_cout and pc.n_tile % 32 == 0:
+        # 2-D layers with one N tile: CTA pairs stream half a weight block each (measured +11..17 % at N = 128 / 256 on
+        # 112^2 / 56^2 maps, neutral at 28^2; the 3-D Inception branches with their few tiles per launch lose 0-5 %)
+        if USE_PAIR and kd == 1 and pc.cout_pad <= 256 and pc.n_tile == pc.cout_pad:
+            return ops.PackedSlabConv(pc, L.SLAB_3X3_STREAM_PAIR)
         return ops.PackedSlabConv(pc, L.SLAB_3X3_STREAM)
     return None
 

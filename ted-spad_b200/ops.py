@@ -221,16 +221,20 @@ class PackedSlabConv:
         self.cout, self.cout_pad = pc.cout, pc.cout_pad
         self.bias = pc.bias
         self.cin_pad = 4 if kind == L.SLAB_STEM3D else pc.cin_pad
-        if kind == L.SLAB_3X3_STREAM:
+        self.fallback = None
+        if kind in (L.SLAB_3X3_STREAM, L.SLAB_3X3_STREAM_PAIR):
             # weights stream from the standard packed layout: nothing to re-pack
             if pc.cout_pad % 32 or pc.cout_pad > 512 or pc.cout % 8 or self.n_tile % 32 or pc.cout_pad % self.n_tile:
                 raise ValueError(f"slab stream feed needs Cout_pad % 32 == 0 (<= 512), got {pc.cout_pad} / n_tile {pc.n_tile}")
             self.image, self.image_bytes = pc.w, pc.w.numel() * 2
+            if kind == L.SLAB_3X3_STREAM_PAIR:
+                self.fallback = PackedSlabConv(pc, L.SLAB_3X3_STREAM, n_tile)
             return
         if pc.cout_pad > 256 or pc.cout % 8:
             raise ValueError(f"slab feed needs a single N tile (Cout_pad={pc.cout_pad}) with Cout % 8 == 0")
         # CTA-pair kind: layers it cannot tile (W <= 8, odd tile count) run through the single-CTA kind
-        self.fallback = PackedSlabConv(pc, L.SLAB_3X3) if kind == L.SLAB_3X3_PAIR else None
+        if kind == L.SLAB_3X3_PAIR:
+            self.fallback = PackedSlabConv(pc, L.SLAB_3X3)
         nbytes = C.c_int64(0)
         args = (self.kind, None, pc.cout_pad, pc.k_pad, pc.cin_pad, *pc.k, pc.pad_front[2])
         L.check(L.lib().tedspad_conv_slab_pack(*args, None, C.byref(nbytes), None), "tedspad_conv_slab_pack(size)")
@@ -267,7 +271,7 @@ class PackedSlabConv:
         d.sd, d.sh, d.sw = pc.stride
         d.pd, d.ph, d.pw = pc.pad_front
         d.act, d.tm, d.max_ctas, d.stack_rows = act, tm, max_ctas, stack_rows
-        d.n_tile, d.K_pad = (self.n_tile if self.kind == L.SLAB_3X3_STREAM else 0), pc.k_pad
+        d.n_tile, d.K_pad = (self.n_tile if self.kind in (L.SLAB_3X3_STREAM, L.SLAB_3X3_STREAM_PAIR) else 0), pc.k_pad
         return d
 
     def resolve(self, x, tm=0, up=None, stack_rows=0):
@@ -276,6 +280,16 @@ class PackedSlabConv:
         if self.kind == L.SLAB_3X3_PAIR and (up is not None or tm == 1 or x.W <= 8 or stack_rows > 0 or x.H % 16 or
                                              (x.N * x.D * (x.H // 16) * (-(-x.W // 16))) % 2):
             return self.fallback
+        if self.kind == L.SLAB_3X3_STREAM_PAIR:
+            # the plan knows (stacked rows, tile shape): an odd tile count cannot be split over CTA pairs
+            if up is not None:
+                return self.fallback
+            y = CLTensor.__new__(CLTensor)
+            y.__dict__.update(x.__dict__)
+            y.C, y.ld, y.coff, y.buf = self.pc.cout, self.pc.cout, 0, x.buf
+            d = self.desc(x, y, tm=tm, stack_rows=stack_rows)
+            if L.lib().tedspad_conv_slab_plan(C.byref(d), C.byref(L.SlabPlan())) != 0:
+                return self.fallback
         return self
 
     def plan(self, x, y, **kw):

@@ -434,10 +434,10 @@ def run_slab_case(name, kind, N, dhw, cin_real, cin_buf, cout, k, stride=(1, 1, 
         b = (torch.rand(cout, generator=g) - 0.5).to(DEV)
         bnp = ((torch.rand(cout, generator=g) + 0.5).to(DEV), (torch.rand(cout, generator=g) - 0.5).to(DEV),
                (torch.rand(cout, generator=g) - 0.5).to(DEV), (torch.rand(cout, generator=g) + 0.5).to(DEV), 1e-3)
-        std_cin = cin_buf if kind in (L.SLAB_3X3, L.SLAB_3X3_STREAM, L.SLAB_3X3_PAIR) else 8
+        std_cin = cin_buf if kind in (L.SLAB_3X3, L.SLAB_3X3_STREAM, L.SLAB_3X3_PAIR, L.SLAB_3X3_STREAM_PAIR) else 8
         pc = ops.PackedConv(w, b, bnp, stride=stride, pad_front=pad_f, cin_pad=std_cin, device=DEV, n_align=32)
         psc = ops.PackedSlabConv(pc, kind)
-        if kind != L.SLAB_3X3_STREAM:
+        if kind not in (L.SLAB_3X3_STREAM, L.SLAB_3X3_STREAM_PAIR):
             # the CUDA pack kernel against the numpy restatement, bit for bit
             img_ref = S.pack_image(kind, S.bf16_bits(pc.w), pc.cout_pad, pc.k_pad, pc.cin_pad, pc.k, pad_f[2])
             okp = bool(np.array_equal(S.bf16_bits(psc.image), img_ref))
@@ -538,6 +538,35 @@ def group_slabpair():
     run_slab_case("P7 64->64 odd 19x21 x2 pair", K, 2, (1, 19, 21), 64, 64, 64, (1, 3, 3), halo=(0, 1, 1))
     run_slab_case("P8 64->64 odd tile count -> single-CTA fallback", K, 1, (1, 16, 48), 64, 64, 64, (1, 3, 3), halo=(0, 1, 1))
     run_slab_case("P9 64->128 28x28 pair (N=128)", K, 2, (1, 28, 28), 64, 64, 128, (1, 3, 3), halo=(0, 1, 1))
+
+
+def group_streampair():
+    """Streaming kind on CTA pairs: every CTA streams half of each weight block's rows."""
+    K = L.SLAB_3X3_STREAM_PAIR
+    run_slab_case("Q1 128->128 20x24 haloed pair", K, 2, (1, 20, 24), 128, 128, 128, (1, 3, 3), halo=(0, 1, 1))
+    run_slab_case("Q2 256->128 28x28 tm1 pair", K, 2, (1, 28, 28), 256, 256, 128, (1, 3, 3), halo=(0, 1, 1), tm=1)
+    run_slab_case("Q3 256->128 slices pair", K, 4, (1, 32, 32), 256, 256, 128, (1, 3, 3), halo=(0, 1, 1), in_ld=320, in_coff=64,
+                  out_ld=256, out_coff=128)
+    run_slab_case("Q4 3x3x3 64->192 no halo pair", K, 2, (4, 28, 20), 64, 64, 192, (3, 3, 3), pad_f=(1, 1, 1))
+    run_slab_case("Q5 3x3x3 96(128)->208 -> n_tile 224 pair", K, 2, (4, 14, 14), 96, 128, 224, (3, 3, 3), pad_f=(1, 1, 1),
+                  out_ld=480, out_coff=192)
+    run_slab_case("Q6 (1,3,3) 256->256 28x28 pair (N=256)", K, 2, (1, 28, 28), 256, 256, 256, (1, 3, 3), halo=(0, 1, 1))
+    run_slab_case("Q7 128->128 112x112 x8 many tiles pair", K, 8, (1, 112, 112), 128, 128, 128, (1, 3, 3), halo=(0, 1, 1))
+    run_slab_case("Q8 128->128 pool fused pair", K, 4, (1, 32, 48), 128, 128, 128, (1, 3, 3), halo=(0, 1, 1), pool=True)
+    run_slab_case("Q9 384-out two N tiles -> single-CTA fallback", K, 4, (2, 7, 7), 192, 192, 384, (3, 3, 3), pad_f=(1, 1, 1))
+
+
+def group_streampairperf():
+    for K, nm in ((L.SLAB_3X3_STREAM, "single"), (L.SLAB_3X3_STREAM_PAIR, "pair")):
+        time_slab(f"128->128 @112 x128 {nm}", K, 128, (1, 112, 112), 128, 128, (1, 3, 3))
+        time_slab(f"128->128 @112 x128 +pool {nm}", K, 128, (1, 112, 112), 128, 128, (1, 3, 3), pool=True)
+        time_slab(f"256->128 @112 x128 {nm}", K, 128, (1, 112, 112), 256, 128, (1, 3, 3))
+        time_slab(f"256->128 @56 x128 {nm}", K, 128, (1, 56, 56), 256, 128, (1, 3, 3))
+        time_slab(f"128->256 @56 x128 {nm}", K, 128, (1, 56, 56), 128, 256, (1, 3, 3))
+        time_slab(f"512->256 @56 x128 {nm}", K, 128, (1, 56, 56), 512, 256, (1, 3, 3))
+        time_slab(f"512->256 @28 x128 {nm}", K, 128, (1, 28, 28), 512, 256, (1, 3, 3))
+        time_slab(f"i3d 2c 64->192 3x3x3 @8x56x56 x8 {nm}", K, 8, (8, 56, 56), 64, 192, (3, 3, 3), pad_f=(1, 1, 1))
+        time_slab(f"i3d 3c.b1b 128->192 @8x28x28 x8 {nm}", K, 8, (8, 28, 28), 128, 192, (3, 3, 3), pad_f=(1, 1, 1))
 
 
 def group_pairperf():
@@ -651,12 +680,12 @@ def time_slab(name, kind, N, dhw, cin_buf, cout, k, stride=(1, 1, 1), pad_f=(0, 
     try:
         D, H, W = dhw
         cin_real = cin_real or cin_buf
-        halo = (0, 1, 1) if (kind in (L.SLAB_3X3, L.SLAB_3X3_STREAM, L.SLAB_3X3_PAIR) and D == 1) else (0, 0, 0)
+        halo = (0, 1, 1) if (kind in (L.SLAB_3X3, L.SLAB_3X3_STREAM, L.SLAB_3X3_PAIR, L.SLAB_3X3_STREAM_PAIR) and D == 1) else (0, 0, 0)
         x = ops.CLTensor(N, D, H, W, cin_buf, halo, device=DEV)
         x.interior().normal_()
         wt = torch.randn(cout, cin_real, *k, device=DEV) / (cin_real * k[0] * k[1] * k[2]) ** 0.5
         pc = ops.PackedConv(wt, None, None, stride=stride, pad_front=pad_f,
-                            cin_pad=cin_buf if kind in (L.SLAB_3X3, L.SLAB_3X3_STREAM, L.SLAB_3X3_PAIR) else 8, device=DEV, n_align=32)
+                            cin_pad=cin_buf if kind in (L.SLAB_3X3, L.SLAB_3X3_STREAM, L.SLAB_3X3_PAIR, L.SLAB_3X3_STREAM_PAIR) else 8, device=DEV, n_align=32)
         psc = ops.PackedSlabConv(pc, kind, n_tile=n_tile)
         od, oh, ow = pc.out_extent((D, H, W), pad_b)
         y = ops.CLTensor(N, od, oh, ow, cout, (0, 1, 1) if od == 1 else (0, 0, 0), device=DEV)
