@@ -90,6 +90,7 @@ class SnippetExtractor:
             raise RuntimeError("SnippetExtractor needs CUDA modules: there is no CPU path")
         self._enc = {}
         self._copy_stream = None
+        self._stage_bufs, self._stage_free = [None, None], [None, None]
 
     def snippet_frames(self, n_frames):
         if self.source == "dali":
@@ -117,14 +118,25 @@ class SnippetExtractor:
             self.fa.anonymize_into(x0, enc_in, self.T)
             return self.ft.features_from_cl(enc_in)
 
-    def _stage(self, frames):
-        """Host frames -> device on the copy stream (returns the device tensor and the event that marks its arrival)."""
+    def _stage(self, frames, slot):
+        """Host frames -> one of two persistent device staging buffers, on the copy stream.  Returns the device view
+        and the event that marks its arrival.  (Fresh allocations per batch made the caching allocator cudaMalloc -
+        a device-wide synchronisation - whenever the previous batch's block was still in use.)"""
         if frames.is_cuda:
             return frames.contiguous(), None
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
+        frames = frames.contiguous()
+        n = frames.numel()
+        buf = self._stage_bufs[slot]
+        if buf is None or buf.numel() < n:
+            buf = torch.empty(max(n, 1), dtype=torch.uint8, device=self.device)
+            self._stage_bufs[slot] = buf
+        dev = buf[:n].view(frames.shape)
         with torch.cuda.stream(self._copy_stream):
-            dev = frames.contiguous().to(self.device, non_blocking=True)
+            if self._stage_free[slot] is not None:
+                self._copy_stream.wait_event(self._stage_free[slot])   # the batch that used this buffer has been consumed
+            dev.copy_(frames, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self._copy_stream)
         return dev, ev
@@ -136,18 +148,22 @@ class SnippetExtractor:
         GPU tensors over one clip at a time, dali_extraction.py:147-150)."""
         it = iter(batches)
         nxt = next(it, None)
-        staged = self._stage(nxt[0]) if nxt is not None else None
+        i = 0
+        staged = self._stage(nxt[0], 0) if nxt is not None else None
         while nxt is not None:
             cur, (dev, ev) = nxt, staged
             nxt = next(it, None)
             if nxt is not None:
-                staged = self._stage(nxt[0])          # in flight while `cur` is computed
+                staged = self._stage(nxt[0], (i + 1) % 2)          # in flight while `cur` is computed
             compute = torch.cuda.current_stream(self.device)
             if ev is not None:
                 compute.wait_event(ev)
             feats = self.features_of_clips(dev, cur[1], cur[2])
             if ev is not None:
-                dev.record_stream(compute)            # allocated on the copy stream, consumed on the compute stream
+                done = torch.cuda.Event()
+                done.record(compute)
+                self._stage_free[i % 2] = done                      # buffer i % 2 may be overwritten after this point
+            i += 1
             yield feats
 
     def extract_video(self, frames):
