@@ -207,6 +207,41 @@ def test_extract_video_rows_and_order():
     assert not np.array_equal(a[0], a[1])
 
 
+def test_full_size_config_properties():
+    """BASELINE.json configs[1] at full size: 32 clips of 16x224x224 from 512 decoded 240x320 frames, UNet + I3D, one
+    batch.  Size-independent properties (the fp32 oracle needs > 1 s per clip): the batched run equals the
+    clip-at-a-time run bit for bit (tiles of the stacked-row / CTA-pair kernels straddle frames and clips, results
+    must not), reversing the clips reverses the rows bit for bit, rows of different clips differ, and two rows are
+    checked against the oracle with the north-star gate."""
+    from tedspad_b200.extraction import SnippetExtractor, crop_boxes
+    name = "unet_i3d_224"
+    fa, ft = _modules(name)
+    B, T = 32, 16
+    clips = [M.structured_clip_u8(500 + i, T, 240, 320) for i in range(B)]
+    frames = torch.from_numpy(np.concatenate(clips)).cuda()                       # [512, 240, 320, 3]
+    (ch, cw), boxes = crop_boxes(240, 320)
+    desc = np.zeros((B * T, 4), dtype=np.int32)
+    desc[:, 0] = np.arange(B * T)
+    desc[:, 1], desc[:, 2] = boxes[0][0], boxes[0][1]
+    big = SnippetExtractor(fa, ft, batch_clips=B)
+    f32 = big.features_of_clips(frames, desc, (ch, cw)).reshape(B, -1).float().cpu()
+    assert f32.shape == (B, 1024) and bool(torch.isfinite(f32).all())
+    one = SnippetExtractor(fa, ft, batch_clips=1)
+    d1 = desc[:T].copy()
+    for b in range(B):
+        fb = one.features_of_clips(frames[b * T:(b + 1) * T], d1, (ch, cw)).reshape(-1).float().cpu()
+        assert torch.equal(fb, f32[b]), f"clip {b}: batched != clip-at-a-time"
+    rev = desc.reshape(B, T, 4)[::-1].reshape(B * T, 4).copy()
+    f_rev = big.features_of_clips(frames, rev, (ch, cw)).reshape(B, -1).float().cpu()
+    assert torch.equal(f_rev, f32.flip(0))
+    cos = torch.nn.functional.cosine_similarity(f32[:-1], f32[1:], dim=1)
+    assert float(cos.max()) < 0.99999, "different clips must give different rows"
+    for b in (0, 21):
+        _, _, f_ref = _cases.oracle_features(name, clips[b])
+        m = _cases.parity_metrics(f32[b], f_ref)
+        assert m["cos"] >= COS_GATE and m["max_abs"] <= ABS_GATE, (b, m)
+
+
 def test_multicrop_layout_and_order():
     """[n_snip, ncrops, F]; crop 4 (center) is the reference's single crop, bit-exact; crops 5..9 are the
     crops of the horizontally flipped frames (torchvision ten_crop order)."""
