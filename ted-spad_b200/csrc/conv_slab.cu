@@ -205,12 +205,18 @@ struct EpiCtx {
   bool fuse_oc, wide_ok, pool_wide_ok;
 };
 
-__device__ __forceinline__ void slab_epi_chunk(const EpiCtx& c, const uint32_t (&v)[32], int c0, bool valid,
-                                               long long pix, bool pool_writer, long long ppix, float (&oc)[3]) {
-  uint32_t q[16];
-  if (!c.fuse_oc) {
-    // fast path: 16 packed fp32x2 bias adds + 16 converts with the ReLU fused into the rounding instruction
-    const bool relu = c.act == TEDSPAD_ACT_RELU;
+// MODE: 0 = bf16 stores only, 1 = + fused MaxPool2d(2), 2 = fused OutConv (stores / pool optional at run time),
+// 3 = fused OutConv alone (the last UNet layer: its 64-channel tensor is never written).
+// Compile-time modes keep run-time branches out of the per-chunk code: the epilogue warps are latency-bound (ncu:
+// issue-selected 12-16 % of their samples, the rest short-scoreboard / fixed-latency waits).  (Processing both
+// chunks of a 64-output tile as one instruction stream - no TMEM-load / math overlap, twice the live registers -
+// was measured slower: 64->64 + OutConv 1.70 -> 2.20 ms.)
+enum { EPI_PLAIN = 0, EPI_POOL = 1, EPI_OC = 2, EPI_OC_ONLY = 3 };   // OC_ONLY: OutConv with no 64-channel store, no pool
+
+template <int MODE, bool RELU>
+__device__ __forceinline__ void epi_math(const EpiCtx& c, const uint32_t (&v)[32], int c0, uint32_t (&q)[16], float (&oc)[3]) {
+  if (MODE != EPI_OC && MODE != EPI_OC_ONLY) {
+    // 16 packed fp32x2 bias adds + 16 converts with the ReLU fused into the rounding instruction
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
       const float4 b4 = *reinterpret_cast<const float4*>(c.bias + c0 + i);
@@ -218,8 +224,8 @@ __device__ __forceinline__ void slab_epi_chunk(const EpiCtx& c, const uint32_t (
       float f2 = __uint_as_float(v[i + 2]), f3 = __uint_as_float(v[i + 3]);
       add_f32x2(f0, f1, b4.x, b4.y);
       add_f32x2(f2, f3, b4.z, b4.w);
-      q[i >> 1] = cvt_bf16x2(f0, f1, relu);
-      q[(i >> 1) + 1] = cvt_bf16x2(f2, f3, relu);
+      q[i >> 1] = cvt_bf16x2(f0, f1, RELU);
+      q[(i >> 1) + 1] = cvt_bf16x2(f2, f3, RELU);
     }
   } else {
     // fused OutConv 1x1: the dot products consume the un-rounded fp32 activations
@@ -232,13 +238,12 @@ __device__ __forceinline__ void slab_epi_chunk(const EpiCtx& c, const uint32_t (
       add_f32x2(f[i], f[i + 1], b4.x, b4.y);
       add_f32x2(f[i + 2], f[i + 3], b4.z, b4.w);
     }
-    if (c.act == TEDSPAD_ACT_RELU) {
+    if (RELU) {
 #pragma unroll
       for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
     }
     if (c0 < c.Cout) {
-      // packed fp32x2 FMAs into two independent accumulator pairs per output (the scalar version was one serial
-      // 32-deep FFMA chain per output: the epilogue, not the tensor pipe, set the pace of the last UNet layer)
+      // packed fp32x2 FMAs into two independent accumulator pairs per output
 #pragma unroll
       for (int o = 0; o < 3; ++o) {
         const float* wr = c.ocw + o * c.Cout + c0;
@@ -252,12 +257,18 @@ __device__ __forceinline__ void slab_epi_chunk(const EpiCtx& c, const uint32_t (
         oc[o] += (a0 + a1) + (b0 + b1);
       }
     }
-    if (c.y != nullptr || c.pool != nullptr) {   // (OutConv-only launches never write the 64-channel tensor)
+    if (MODE == EPI_OC && (c.y != nullptr || c.pool != nullptr)) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) q[i] = pack_bf162(f[2 * i], f[2 * i + 1]);
     }
   }
-  if (c.y != nullptr && valid) {
+}
+
+template <int MODE>
+__device__ __forceinline__ void epi_out(const EpiCtx& c, const uint32_t (&q)[16], int c0, bool valid, long long pix,
+                                        bool pool_writer, long long ppix) {
+  if (MODE == EPI_OC_ONLY) return;
+  if ((MODE != EPI_OC || c.y != nullptr) && valid) {
     // each lane owns 64 contiguous bytes of its pixel: two 32-byte stores (a warp store instruction touches 32
     // cache lines whatever its width, so wider stores halve the L1 wavefronts per byte)
     __nv_bfloat16* yp = c.y + pix * c.y_ld + c.y_coff + c0;
@@ -271,7 +282,7 @@ __device__ __forceinline__ void slab_epi_chunk(const EpiCtx& c, const uint32_t (
           *reinterpret_cast<uint4*>(yp + 8 * j) = make_uint4(q[4 * j], q[4 * j + 1], q[4 * j + 2], q[4 * j + 3]);
     }
   }
-  if (c.pool != nullptr) {
+  if (MODE == EPI_POOL || (MODE == EPI_OC && c.pool != nullptr)) {
     // MaxPool2d(2): x partner = lane ^ 1 (r ^ 1), y partner = lane ^ 8 (g ^ 1).  Each exchange also halves the
     // channels a lane carries on (the partner keeps the other half), so the 2x2 window costs 8 + 4 shuffles per
     // 32 channels instead of 32, and all four lanes of the window store 16 bytes (8 channels) of the pooled pixel.
@@ -291,6 +302,109 @@ __device__ __forceinline__ void slab_epi_chunk(const EpiCtx& c, const uint32_t (
     const int cq = c0 + (odd_x ? 16 : 0) + (odd_y ? 8 : 0);   // first of this lane's 8 pooled channels
     if (pool_writer && cq < c.Cout)
       *reinterpret_cast<uint4*>(c.pool + ppix * c.p_ld + c.p_coff + cq) = make_uint4(b[0], b[1], b[2], b[3]);
+  }
+}
+
+// The epilogue role (warps 0-7).  Two warps per TMEM lane quarter.  tm == 2: warp group eg owns half eg of the tile
+// (all its columns, so the fused OutConv dot product stays inside one thread); tm == 1: the groups split the
+// 32-column chunks.
+template <bool HAS_UP, bool PAIR, int MODE, bool RELU>
+__device__ __forceinline__ void slab_epilogue(const SlabKParams& p, int warp, int lane, uint32_t tmem_base, const float* sm_bias,
+                                              const float* sm_ocw, uint64_t* tfull, uint64_t* tempty) {
+  const int ew = warp & 3, eg = warp >> 2;
+  const int g = ew * 4 + (lane >> 3);
+  const int r = lane & 7;
+  const int tm = p.tm, n_tile = p.n_tile, OH = p.OH, OW = p.OW;
+  const int nchunk_all = n_tile >> 5;
+  EpiCtx c;
+  c.bias = sm_bias; c.ocw = sm_ocw; c.y = p.y; c.pool = p.pool; c.Cout = p.Cout; c.act = p.act;
+  c.y_ld = p.y_ld; c.y_coff = p.y_coff; c.p_ld = p.p_ld; c.p_coff = p.p_coff; c.fuse_oc = MODE >= EPI_OC;
+  // 32-byte stores need 32-byte aligned pixel chunks
+  c.wide_ok = ((p.y_ld | p.y_coff) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.y) & 31) == 0;
+  c.pool_wide_ok = false;
+  int h, c_first, c_step, nch;
+  if (tm == 2) { h = eg; c_first = 0; c_step = 32; nch = nchunk_all; }
+  else if (MODE >= EPI_OC) { h = 0; c_first = 0; c_step = 32; nch = eg == 0 ? nchunk_all : 0; }
+  else { h = 0; c_first = 32 * eg; c_step = 64; nch = (nchunk_all + 1 - eg) >> 1; }
+  int as = 0;
+  uint32_t aph = 0;
+  for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    int t = tile, q;
+    q = fdiv(t, p.dv_nt);
+    const int n0 = (t - q * p.dv_nt.d) * n_tile; t = q;   // first output channel of this N tile
+    q = fdiv(t, p.dv_tx);
+    const int tx = t - q * p.dv_tx.d; t = q;
+    q = fdiv(t, p.dv_ty);
+    const int ty = t - q * p.dv_ty.d; t = q;
+    q = fdiv(t, p.dv_tz);
+    const int tz = t - q * p.dv_tz.d;
+    int n = q;
+    int oy = ty * 16 + g;
+    const int ox = (tx * tm + h) * 8 + r;
+    bool valid = ox < OW;
+    if (p.stack_hp) {
+      // stacked rows: the tile's 16 rows are consecutive rows of the zero-haloed images of the whole batch
+      const int R = oy + p.stack_ph;
+      n = fdiv(R, p.dv_hp);
+      oy = R - n * p.stack_hp - p.stack_ph;
+      valid = valid && n < p.stack_n;
+    }
+    valid = valid && static_cast<unsigned>(oy) < static_cast<unsigned>(OH);
+    const long long pix = ((static_cast<long long>(n) * p.yDp + tz + p.ypd) * p.yHp + oy + p.yph) * p.yWp + ox + p.ypw;
+    const int py = oy >> 1, px = ox >> 1;
+    // all four lanes of a 2x2 window write (8 channels each); the window is in the image iff its pooled pixel is
+    const bool pool_writer = oy >= 0 && ox < OW && py < p.PH && px < p.PW && (p.stack_hp == 0 || n < p.stack_n);
+    const long long ppix = (static_cast<long long>(n) * p.pHp + py + p.pph) * p.pWp + px + p.ppw;
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) +
+                           static_cast<uint32_t>((as * tm + h) * n_tile + c_first);
+    float oc[3] = {0.f, 0.f, 0.f};
+    mbar_wait(tfull + as, aph);
+    tc_fence_after();
+    if (HAS_UP) {   // 480-thread variant: 136 registers per thread, one chunk in flight
+      uint32_t va[32], qa[16];
+      for (int i = 0; i < nch; ++i) {
+        tmem_ld32(t_row + i * c_step, va);
+        tmem_ld_wait();
+        const int c0 = n0 + c_first + i * c_step;
+        epi_math<MODE, RELU>(c, va, c0, qa, oc);
+        epi_out<MODE>(c, qa, c0, valid, pix, pool_writer, ppix);
+      }
+    } else {
+      // software pipeline over this warp's chunks: the next chunk's TMEM load is in flight while one is processed
+      uint32_t va[32], vb[32], qa[16];
+      if (nch > 0) tmem_ld32(t_row, va);
+      for (int i = 0; i < nch; i += 2) {
+        tmem_ld_wait();
+        if (i + 1 < nch) tmem_ld32(t_row + (i + 1) * c_step, vb);
+        const int c0 = n0 + c_first + i * c_step;
+        epi_math<MODE, RELU>(c, va, c0, qa, oc);
+        epi_out<MODE>(c, qa, c0, valid, pix, pool_writer, ppix);
+        if (i + 1 < nch) {
+          tmem_ld_wait();
+          if (i + 2 < nch) tmem_ld32(t_row + (i + 2) * c_step, va);
+          epi_math<MODE, RELU>(c, vb, c0 + c_step, qa, oc);
+          epi_out<MODE>(c, qa, c0 + c_step, valid, pix, pool_writer, ppix);
+        }
+      }
+    }
+    // all TMEM reads of this accumulator are complete (wait::ld above): hand it back to the MMA warp
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) {
+      if (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(tempty + as), 0));
+      else mbar_arrive(tempty + as);
+    }
+    if (MODE >= EPI_OC && valid && nch > 0) {
+      const long long plane = static_cast<long long>(OH) * OW;
+      const long long o0 = static_cast<long long>(n) * 3 * plane + static_cast<long long>(oy) * OW + ox;
+#pragma unroll
+      for (int o = 0; o < 3; ++o) {
+        const float sgm = 1.f / (1.f + __expf(-(oc[o] + sm_ocw[3 * p.Cout + o])));
+        p.oc_planes[o0 + o * plane] = __float2bfloat16_rn(sgm);
+        if (p.oc_frames != nullptr) p.oc_frames[o0 + o * plane] = sgm;
+      }
+    }
+    if (++as == p.acc_stages) { as = 0; aph ^= 1; }
   }
 }
 
@@ -495,99 +609,18 @@ conv_slab_kernel(const __grid_constant__ SlabKParams p) {
     }
 #undef TSP_ISSUE
   } else if (warp < 8) {
-    // ---------------------------------------------------------------- epilogue
-    // Two warps per TMEM lane quarter.  tm == 2: warp group eg owns half eg of the tile (all its columns, so the
-    // fused OutConv dot product stays inside one thread); tm == 1: the groups split the 32-column chunks.
-    const int ew = warp & 3, eg = warp >> 2;
-    const int g = ew * 4 + (lane >> 3);
-    const int r = lane & 7;
-    const int tm = p.tm, n_tile = p.n_tile, OH = p.OH, OW = p.OW;
-    const int nchunk_all = n_tile >> 5;
-    EpiCtx c;
-    c.bias = sm_bias; c.ocw = sm_ocw; c.y = p.y; c.pool = p.pool; c.Cout = p.Cout; c.act = p.act;
-    c.y_ld = p.y_ld; c.y_coff = p.y_coff; c.p_ld = p.p_ld; c.p_coff = p.p_coff; c.fuse_oc = p.oc_w != nullptr;
-    // 32-byte stores need 32-byte aligned pixel chunks
-    c.wide_ok = ((p.y_ld | p.y_coff) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.y) & 31) == 0;
-    c.pool_wide_ok = ((p.p_ld | p.p_coff) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.pool) & 31) == 0;
-    int h, c_first, c_step, nch;
-    if (tm == 2) { h = eg; c_first = 0; c_step = 32; nch = nchunk_all; }
-    else if (c.fuse_oc) { h = 0; c_first = 0; c_step = 32; nch = eg == 0 ? nchunk_all : 0; }
-    else { h = 0; c_first = 32 * eg; c_step = 64; nch = (nchunk_all + 1 - eg) >> 1; }
-    int as = 0;
-    uint32_t aph = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      int t = tile, q;
-      q = fdiv(t, p.dv_nt);
-      const int n0 = (t - q * p.dv_nt.d) * n_tile; t = q;   // first output channel of this N tile
-      q = fdiv(t, p.dv_tx);
-      const int tx = t - q * p.dv_tx.d; t = q;
-      q = fdiv(t, p.dv_ty);
-      const int ty = t - q * p.dv_ty.d; t = q;
-      q = fdiv(t, p.dv_tz);
-      const int tz = t - q * p.dv_tz.d;
-      int n = q;
-      int oy = ty * 16 + g;
-      const int ox = (tx * tm + h) * 8 + r;
-      bool valid = ox < OW;
-      if (p.stack_hp) {
-        // stacked rows: the tile's 16 rows are consecutive rows of the zero-haloed images of the whole batch
-        const int R = oy + p.stack_ph;
-        n = fdiv(R, p.dv_hp);
-        oy = R - n * p.stack_hp - p.stack_ph;
-        valid = valid && n < p.stack_n;
-      }
-      valid = valid && static_cast<unsigned>(oy) < static_cast<unsigned>(OH);
-      const long long pix = ((static_cast<long long>(n) * p.yDp + tz + p.ypd) * p.yHp + oy + p.yph) * p.yWp + ox + p.ypw;
-      const int py = oy >> 1, px = ox >> 1;
-      // all four lanes of a 2x2 window write (8 channels each); the window is in the image iff its pooled pixel is
-      const bool pool_writer = oy >= 0 && ox < OW && py < p.PH && px < p.PW && (p.stack_hp == 0 || n < p.stack_n);
-      const long long ppix = (static_cast<long long>(n) * p.pHp + py + p.pph) * p.pWp + px + p.ppw;
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) +
-                             static_cast<uint32_t>((as * tm + h) * n_tile + c_first);
-      float oc[3] = {0.f, 0.f, 0.f};
-      mbar_wait(tfull + as, aph);
-      tc_fence_after();
-      // software pipeline over this warp's chunks: the next chunk's TMEM load is in flight while one is processed
-      if (HAS_UP) {   // 480-thread variant: 136 registers per thread, one chunk in flight
-        uint32_t va[32];
-        for (int i = 0; i < nch; ++i) {
-          tmem_ld32(t_row + i * c_step, va);
-          tmem_ld_wait();
-          slab_epi_chunk(c, va, n0 + c_first + i * c_step, valid, pix, pool_writer, ppix, oc);
-        }
-      } else {
-        uint32_t va[32], vb[32];
-        if (nch > 0) tmem_ld32(t_row, va);
-        for (int i = 0; i < nch; i += 2) {
-          tmem_ld_wait();
-          if (i + 1 < nch) tmem_ld32(t_row + (i + 1) * c_step, vb);
-          slab_epi_chunk(c, va, n0 + c_first + i * c_step, valid, pix, pool_writer, ppix, oc);
-          if (i + 1 < nch) {
-            tmem_ld_wait();
-            if (i + 2 < nch) tmem_ld32(t_row + (i + 2) * c_step, va);
-            slab_epi_chunk(c, vb, n0 + c_first + (i + 1) * c_step, valid, pix, pool_writer, ppix, oc);
-          }
-        }
-      }
-      // all TMEM reads of this accumulator are complete (wait::ld above): hand it back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(tempty + as), 0));
-        else mbar_arrive(tempty + as);
-      }
-      if (c.fuse_oc && valid && nch > 0) {
-        const long long plane = static_cast<long long>(OH) * OW;
-        const long long o0 = static_cast<long long>(n) * 3 * plane + static_cast<long long>(oy) * OW + ox;
-#pragma unroll
-        for (int o = 0; o < 3; ++o) {
-          const float sgm = 1.f / (1.f + __expf(-(oc[o] + sm_ocw[3 * p.Cout + o])));
-          p.oc_planes[o0 + o * plane] = __float2bfloat16_rn(sgm);
-          if (p.oc_frames != nullptr) p.oc_frames[o0 + o * plane] = sgm;
-        }
-      }
-      if (++as == p.acc_stages) { as = 0; aph ^= 1; }
-    }
+    // ---------------------------------------------------------------- epilogue (slab_epilogue above)
+    const bool relu = p.act == TEDSPAD_ACT_RELU;
+#define TSP_EPI(MODE_) \
+    do { \
+      if (relu) slab_epilogue<HAS_UP, PAIR, MODE_, true>(p, warp, lane, tmem_base, sm_bias, sm_ocw, tfull, tempty); \
+      else slab_epilogue<HAS_UP, PAIR, MODE_, false>(p, warp, lane, tmem_base, sm_bias, sm_ocw, tfull, tempty); \
+    } while (0)
+    if (p.oc_w != nullptr && p.y == nullptr && p.pool == nullptr) TSP_EPI(EPI_OC_ONLY);
+    else if (p.oc_w != nullptr) TSP_EPI(EPI_OC);
+    else if (p.pool != nullptr) TSP_EPI(EPI_POOL);
+    else TSP_EPI(EPI_PLAIN);
+#undef TSP_EPI
   }
 
   if (HAS_UP && warp >= 11) {
