@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define TEDSPAD_ABI_VERSION 3
+#define TEDSPAD_ABI_VERSION 4
 
 enum { TEDSPAD_ACT_NONE = 0, TEDSPAD_ACT_RELU = 1, TEDSPAD_ACT_SIGMOID = 2 };
 /* A-operand feed of the implicit GEMM: AUTO picks FLAT when legal. */
@@ -145,7 +145,7 @@ typedef struct tedspad_conv_slab {
                                [x | upsample2x(up)] along the channels; ptr NULL = none */
   const float* oc_w;        /* optional fused OutConv: device fp32 [3][Cout]; NULL = none */
   const float* oc_b;        /* device fp32 [3] */
-  void* oc_planes;          /* device bf16 [N][3][H][W] */
+  void* oc_planes;          /* device bf16 [N][3][H][W] (may be NULL when oc_clip is given) */
   float* oc_frames;         /* optional device fp32 [N][3][H][W] */
   int32_t kind;             /* TEDSPAD_SLAB_* */
   int32_t Cout, Cout_pad;   /* Cout_pad = UMMA N (multiple of 16, <= 256) */
@@ -157,6 +157,11 @@ typedef struct tedspad_conv_slab {
   int32_t max_ctas;         /* persistent grid cap; 0 = number of SMs */
   int32_t n_tile;           /* STREAM kind: UMMA N per tile (multiple of 32 dividing Cout_pad); 0 = auto */
   int32_t K_pad;            /* STREAM kind: row length of the standard packed weights */
+  tedspad_tensor oc_clip;   /* optional fused OutConv destination: the ENCODER clip [B][T][H][W][>=3] (bf16), written
+                               through the raw-reshape glue of dali_extraction.py:171-173 (plane 3t+c of clip b ->
+                               channel (3t+c)/T, time (3t+c)%T); channels >= 3 are not touched.  With it oc_planes may be
+                               NULL.  ptr NULL = none */
+  int32_t oc_T;             /* frames per clip for oc_clip (x.N % oc_T == 0) */
   int32_t stack_rows;       /* 2-D 3X3 kinds over buffers with zero halo rows (x.ph >= 1): tile the rows of all N images
                                as one column of N*(H+2ph) rows (no per-image remainder).  0 = when it saves tensor
                                time, 1 = always (when legal), -1 = never */

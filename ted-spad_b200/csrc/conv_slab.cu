@@ -85,6 +85,9 @@ struct SlabKParams {
   const float* oc_b;
   __nv_bfloat16* oc_planes;
   float* oc_frames;
+  __nv_bfloat16* oc_clip;      // encoder clip written through the raw-reshape glue (NULL = planes only)
+  int oc_T, cDp, cHp, cWp, cpd, cph, cpw, c_ld, c_coff;
+  DivMagic dv_T;
   uint2 tab[TEDSPAD_SLAB_MAX_MMA];
 };
 
@@ -397,11 +400,19 @@ __device__ __forceinline__ void slab_epilogue(const SlabKParams& p, int warp, in
     if (MODE >= EPI_OC && valid && nch > 0) {
       const long long plane = static_cast<long long>(OH) * OW;
       const long long o0 = static_cast<long long>(n) * 3 * plane + static_cast<long long>(oy) * OW + ox;
+      const int bclip = fdiv(n, p.dv_T), tf = n - bclip * p.oc_T;   // frame n = clip bclip, time tf
 #pragma unroll
       for (int o = 0; o < 3; ++o) {
         const float sgm = 1.f / (1.f + __expf(-(oc[o] + sm_ocw[3 * p.Cout + o])));
-        p.oc_planes[o0 + o * plane] = __float2bfloat16_rn(sgm);
+        const __nv_bfloat16 sb = __float2bfloat16_rn(sgm);
+        if (p.oc_planes != nullptr) p.oc_planes[o0 + o * plane] = sb;
         if (p.oc_frames != nullptr) p.oc_frames[o0 + o * plane] = sgm;
+        if (p.oc_clip != nullptr) {
+          // dali_extraction.py:171-173: plane 3*tf + o of the clip's 3T planes is encoder channel ce at time te
+          const int pl = 3 * tf + o, ce = fdiv(pl, p.dv_T), te = pl - ce * p.oc_T;
+          const long long cp = ((static_cast<long long>(bclip) * p.cDp + te + p.cpd) * p.cHp + oy + p.cph) * p.cWp + ox + p.cpw;
+          p.oc_clip[cp * p.c_ld + p.c_coff + ce] = sb;
+        }
       }
     }
     if (++as == p.acc_stages) { as = 0; aph ^= 1; }
@@ -1139,11 +1150,25 @@ extern "C" int tedspad_conv_slab_forward(const tedspad_conv_slab* c, void* strea
     p.p_ld = q.ld; p.p_coff = q.coff;
   }
   if (fused_oc) {
-    TSP_CHECK(c->oc_b && c->oc_planes, "slab: fused OutConv needs oc_b and oc_planes");
+    TSP_CHECK(c->oc_b && (c->oc_planes || c->oc_clip.ptr), "slab: fused OutConv needs oc_b and oc_planes or oc_clip");
     TSP_CHECK(c->Cout <= 64 && c->Cout % 4 == 0 && y.D == 1, "slab: fused OutConv needs a 2-D layer with Cout <= 64");
     p.oc_w = c->oc_w; p.oc_b = c->oc_b;
     p.oc_planes = reinterpret_cast<__nv_bfloat16*>(c->oc_planes);
     p.oc_frames = c->oc_frames;
+    p.dv_T = make_div(1);
+    p.oc_T = 1;
+    if (c->oc_clip.ptr != nullptr) {
+      const tedspad_tensor& e = c->oc_clip;
+      if (check_tensor(e, "slab.oc_clip", 1)) return 1;
+      TSP_CHECK(c->oc_T >= 1 && x.N % c->oc_T == 0 && e.N == x.N / c->oc_T && e.D == c->oc_T && e.H == y.H && e.W == y.W &&
+                    e.C >= 3,
+                "slab: oc_clip [%d,%d,%d,%d,%d] does not match %d frames of T=%d", e.N, e.D, e.H, e.W, e.C, x.N, c->oc_T);
+      p.oc_clip = reinterpret_cast<__nv_bfloat16*>(e.ptr);
+      p.oc_T = c->oc_T;
+      p.dv_T = make_div(c->oc_T);
+      p.cDp = e.D + 2 * e.pd; p.cHp = e.H + 2 * e.ph; p.cWp = e.W + 2 * e.pw;
+      p.cpd = e.pd; p.cph = e.ph; p.cpw = e.pw; p.c_ld = e.ld; p.c_coff = e.coff;
+    }
   }
 
   const bool has_up = c->up.ptr != nullptr;

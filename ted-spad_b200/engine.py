@@ -206,9 +206,10 @@ class UNetExecutor:
             if j == 3 and sb is not None and enc_in.W % 8 == 0 and enc_in.C in (4, 8):
                 # OutConv 1x1 + sigmoid (unet_parts.py:71-77, unet_model.py:36-37) in the last epilogue: the 64-channel
                 # tensor is never written; planar images then go through the raw-reshape glue (dali_extraction.py:173)
-                planes = self.bufs.raw("planes", (N, 3, H, W), ops.BF16)
-                ops.conv_slab_forward(t, sb, None, outconv=(self.out_w, self.out_b, planes, frames_out))
-                return ops.planes_to_clip(planes, enc_in, T)
+                # ... and the sigmoid images go straight into the encoder clip through the raw-reshape glue
+                # (dali_extraction.py:173): no planar intermediate, no separate glue kernel
+                ops.conv_slab_forward(t, sb, None, outconv=(self.out_w, self.out_b, None, frames_out, enc_in, T))
+                return enc_in
             cur = g(f"u{j}", N, 1, h, w, out_ch[j], hl)
             self._conv(t, b, sb, cur)
         ops.outconv_sigmoid(cur, self.out_w, self.out_b, enc_in, T, frames_out)

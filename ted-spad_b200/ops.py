@@ -248,7 +248,9 @@ class PackedSlabConv:
                     "tedspad_conv_slab_pack")
 
     def desc(self, x, y, act=L.ACT_RELU, pool=None, outconv=None, tm=0, max_ctas=0, up=None, stack_rows=0):
-        """outconv = (w fp32 [3,Cout], b fp32 [3], planes bf16 [N,3,H,W], frames fp32 [N,3,H,W] | None)"""
+        """outconv = (w fp32 [3,Cout], b fp32 [3], planes bf16 [N,3,H,W] | None, frames fp32 [N,3,H,W] | None
+        [, clip CLTensor [B,T,H,W,>=3], T]): with `clip` the sigmoid images go straight into the encoder input
+        through the raw-reshape glue"""
         pc = self.pc
         d = L.ConvSlabDesc()
         d.x = x.desc()
@@ -263,9 +265,12 @@ class PackedSlabConv:
         if up is not None:
             d.up = up.desc()
         if outconv is not None:
-            w, b, planes, frames = outconv
-            d.oc_w, d.oc_b, d.oc_planes = w.data_ptr(), b.data_ptr(), planes.data_ptr()
+            w, b, planes, frames = outconv[:4]
+            d.oc_w, d.oc_b = w.data_ptr(), b.data_ptr()
+            d.oc_planes = planes.data_ptr() if planes is not None else None
             d.oc_frames = frames.data_ptr() if frames is not None else None
+            if len(outconv) > 4:
+                d.oc_clip, d.oc_T = outconv[4].desc(), int(outconv[5])
         d.kind, d.Cout, d.Cout_pad = self.kind, pc.cout, pc.cout_pad
         d.kd, d.kh, d.kw = pc.k
         d.sd, d.sh, d.sw = pc.stride

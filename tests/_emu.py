@@ -126,11 +126,24 @@ def conv_slab_forward(x, psc, y, act=L.ACT_RELU, pool=None, outconv=None, tm=0, 
         r = acc.to(store_dtype).float()[:, 0].permute(0, 3, 1, 2)
         pool.interior()[:, 0] = F.max_pool2d(r, 2).permute(0, 2, 3, 1).to(pool.buf.dtype)
     if outconv is not None:
-        w, b, planes, frames = outconv
+        w, b, planes, frames = outconv[:4]
         v = torch.sigmoid(acc[:, 0] @ w.T + b).permute(0, 3, 1, 2).contiguous()  # [N,3,H,W]
-        planes.copy_(v.to(planes.dtype))
+        if planes is not None:
+            planes.copy_(v.to(planes.dtype))
         if frames is not None:
             frames.copy_(v)
+        if len(outconv) > 4:   # straight into the encoder clip through the raw-reshape glue
+            clip, T = outconv[4], outconv[5]
+            planes_to_clip_into(v, clip, T)
+    return y
+
+
+def planes_to_clip_into(v, y, T):
+    """fp32 [F,3,H,W] images -> channels 0..2 of the encoder clip (other channels untouched)."""
+    Fr, _, H, W = v.shape
+    B = Fr // T
+    enc = v.float().reshape(B, T, 3, H, W).reshape(B, 3, T, H, W)  # dali_extraction.py:171-173
+    y.interior()[..., :3] = enc.permute(0, 2, 3, 4, 1).to(y.buf.dtype)
     return y
 
 

@@ -468,7 +468,10 @@ def run_slab_case(name, kind, N, dhw, cin_real, cin_buf, cout, k, stride=(1, 1, 
             ocb = torch.randn(3, generator=g).to(DEV)
             planes = torch.full((N, 3, oh, ow), 9.0, device=DEV, dtype=torch.bfloat16)
             frames = torch.full((N, 3, oh, ow), 9.0, device=DEV)
-            oc = (ocw, ocb, planes, frames)
+            Tc = 2 if N % 2 == 0 else 1
+            clip = ops.CLTensor(N // Tc, Tc, oh, ow, 4, device=DEV)
+            clip.buf.fill_(9.0)
+            oc = (ocw, ocb, planes, frames, clip, Tc)
         ops.conv_slab_forward(xv, psc, yv, pool=pv, outconv=oc, tm=tm, max_ctas=max_ctas)
         torch.cuda.synchronize()
         kd, kh, kw = k
@@ -502,6 +505,13 @@ def run_slab_case(name, kind, N, dhw, cin_real, cin_buf, cout, k, stride=(1, 1, 
             fr_ref = torch.sigmoid(F.conv2d(ref[:, :, 0], ocw[:, :, None, None], ocb))
             report(name + ":outconv frames", frames, fr_ref, tol_rel=2e-3)
             report(name + ":outconv planes", planes.float(), fr_ref, tol_rel=6e-3)
+            # the same images through the raw-reshape glue (dali_extraction.py:171-173), straight into the encoder clip
+            enc_ref = fr_ref.reshape(N // Tc, Tc, 3, oh, ow).reshape(N // Tc, 3, Tc, oh, ow)
+            report(name + ":outconv clip (glue)", clip.to_ncdhw()[:, :3], enc_ref, tol_rel=6e-3)
+            okc = bool(torch.equal(clip.to_ncdhw()[:, :3].to(torch.bfloat16).reshape(N // Tc, 3 * Tc, oh, ow),
+                                   planes.reshape(N // Tc, 3 * Tc, oh, ow))) and bool((clip.interior()[..., 3] == 9.0).all())
+            RESULTS.append((name + ":clip==planes", okc))
+            print(f"[{'PASS' if okc else 'FAIL'}] {name}: clip channels == planes bit for bit, pad channel untouched")
         return ok
     except Exception:
         RESULTS.append((name, False))
