@@ -1,4 +1,5 @@
 // C-ABI plumbing: error text, tensor checks, SM count, TMA tensor-map encoding.
+#include <cstdlib>
 #include <cstdarg>
 #include <cstdio>
 #include <mutex>
@@ -103,6 +104,16 @@ int encode_tmap_5d_bf16(CUtensorMap* out, const void* base, const uint64_t dims[
   return 0;
 }
 
+}  // namespace tsp
+
+namespace tsp {
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("TEDSPAD_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
 }  // namespace tsp
 
 extern "C" int tedspad_abi_version(void) { return TEDSPAD_ABI_VERSION; }

@@ -41,6 +41,40 @@ int encode_tmap_5d_bf16(CUtensorMap* out, const void* base, const uint64_t dims[
 
 int num_sms();
 
+// Programmatic dependent launch (TEDSPAD_PDL=0 switches it off): every hot-path kernel is launched with
+// programmaticStreamSerialization, calls griddepcontrol.launch_dependents when it starts and griddepcontrol.wait
+// before its first access to memory a previous kernel may still be using.  The next kernel's CTAs are then placed
+// on SMs as the current kernel's CTAs drain, and its prologue (barrier init, TMEM allocation, tensor-map prefetch,
+// resident-weight load, resampling tables) overlaps the tail of the current one instead of following it.
+bool pdl_enabled();
+
+template <typename P>
+inline cudaError_t launch_kernel(void (*kernel)(P), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, const P& params,
+                                 int cluster = 1) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  unsigned n = 0;
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (cluster > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = static_cast<unsigned>(cluster);
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, params);
+}
+
 inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 
 // byte address of element (n, d, h, w, c=coff) of the LOGICAL view (halo skipped)

@@ -113,6 +113,8 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();   // programmatic dependent launch, see common.h
+  pdl_wait();                // (this kernel's prologue above touched no tensor memory)
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -477,7 +479,7 @@ extern "C" int tedspad_conv_forward(const tedspad_conv* c, void* stream_v) {
   int ctas = c->max_ctas > 0 ? c->max_ctas : num_sms();
   ctas = std::max(1, std::min(ctas, total_tiles));
   const int threads = feed == TEDSPAD_FEED_GATHER ? 384 : 256;
-  conv_igemm_kernel<<<ctas, threads, smem_bytes, reinterpret_cast<cudaStream_t>(stream_v)>>>(p);
+  TSP_CUDA(launch_kernel(conv_igemm_kernel, dim3(ctas), dim3(threads), smem_bytes, reinterpret_cast<cudaStream_t>(stream_v), p));
   TSP_CUDA(cudaGetLastError());
   return 0;
 }

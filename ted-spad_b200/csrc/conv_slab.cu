@@ -314,6 +314,7 @@ __device__ __forceinline__ void epi_out(const EpiCtx& c, const uint32_t (&q)[16]
 template <bool HAS_UP, bool PAIR, int MODE, bool RELU>
 __device__ __forceinline__ void slab_epilogue(const SlabKParams& p, int warp, int lane, uint32_t tmem_base, const float* sm_bias,
                                               const float* sm_ocw, uint64_t* tfull, uint64_t* tempty) {
+  pdl_wait();   // the previous kernel may still be reading the buffers this one writes
   const int ew = warp & 3, eg = warp >> 2;
   const int g = ew * 4 + (lane >> 3);
   const int r = lane & 7;
@@ -535,6 +536,7 @@ conv_slab_kernel(const __grid_constant__ SlabKParams p) {
   if (PAIR) cluster_sync_all(); else __syncthreads();   // PAIR: the peer's barriers are initialised before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();   // the next kernel may start its prologue on SMs this grid has left (common.h)
 
   if (warp == 8) {
     // ------------------------------------------------------------ TMA producer
@@ -545,6 +547,7 @@ conv_slab_kernel(const __grid_constant__ SlabKParams p) {
         for (int off = 0; off < p.w_bytes; off += 16384)
           bulk_copy_g2s(smW + off, w_src + off, static_cast<uint32_t>(min(16384, p.w_bytes - off)), wbar);
       }
+      pdl_wait();   // (weights / bias are constants: loaded above, before the previous kernel has finished)
       int s = 0, bs = 0;
       uint32_t ph = 0, bph = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -638,6 +641,7 @@ conv_slab_kernel(const __grid_constant__ SlabKParams p) {
     // -------------------------------------------------- up-sampling slab producers (warps 11-14)
     // thread -> one 16-byte channel chunk (8 channels) of 16 slab pixels per pass; the slab row of pixel r is
     // r*128 bytes with the SWIZZLE_128B chunk permutation the TMA would have applied.
+    pdl_wait();
     const int it = static_cast<int>(threadIdx.x) - 11 * 32;
     const int c8 = it & 7, p0 = it >> 3;
     int s = 0;
@@ -1205,27 +1209,16 @@ extern "C" int tedspad_conv_slab_forward(const tedspad_conv_slab* c, void* strea
   if (rc) return rc;
   int ctas = c->max_ctas > 0 ? c->max_ctas : num_sms();
   ctas = std::max(1, std::min(ctas, p.total_tiles));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_v);
   if (P.pair) {
     // clusters of two CTAs (one TPC); an even grid keeps the two tile loops of a pair in lock step
     ctas &= ~1;
     TSP_CHECK(ctas >= 2 && !has_up, "slab pair: needs at least two CTAs and no fused up-sampling");
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(ctas);
-    cfg.blockDim = dim3(SLAB_THREADS);
-    cfg.dynamicSmemBytes = P.smem_bytes;
-    cfg.stream = reinterpret_cast<cudaStream_t>(stream_v);
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    TSP_CUDA(cudaLaunchKernelEx(&cfg, conv_slab_kernel<false, true>, p));
+    TSP_CUDA(launch_kernel(conv_slab_kernel<false, true>, dim3(ctas), dim3(SLAB_THREADS), P.smem_bytes, st, p, 2));
   } else if (has_up) {
-    conv_slab_kernel<true, false><<<ctas, SLAB_THREADS_UP, P.smem_bytes, reinterpret_cast<cudaStream_t>(stream_v)>>>(p);
+    TSP_CUDA(launch_kernel(conv_slab_kernel<true, false>, dim3(ctas), dim3(SLAB_THREADS_UP), P.smem_bytes, st, p));
   } else {
-    conv_slab_kernel<false, false><<<ctas, SLAB_THREADS, P.smem_bytes, reinterpret_cast<cudaStream_t>(stream_v)>>>(p);
+    TSP_CUDA(launch_kernel(conv_slab_kernel<false, false>, dim3(ctas), dim3(SLAB_THREADS), P.smem_bytes, st, p));
   }
   TSP_CUDA(cudaGetLastError());
   return 0;

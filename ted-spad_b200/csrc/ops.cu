@@ -82,6 +82,8 @@ __device__ __forceinline__ void max8(uint4& m, const uint4& q) {
 
 template <int KD, int KH, int KW>
 __global__ void __launch_bounds__(256) maxpool_kernel(const PoolP p) {
+  pdl_launch_dependents();   // programmatic dependent launch, see common.h
+  pdl_wait();
   const int kd = KD > 0 ? KD : p.kd, kh = KH > 0 ? KH : p.kh, kw = KW > 0 ? KW : p.kw;
   const int c8n = p.y.C >> 3;
   const int items = p.y.W * c8n;
@@ -131,6 +133,8 @@ __global__ void __launch_bounds__(256) maxpool_kernel(const PoolP p) {
 // (column = the 3x3 (d,h) taps at one w), i.e. 9 loads per output instead of 27.  The (d,h) bounds are per-thread
 // constants; consecutive threads own consecutive channel groups, so every load instruction is coalesced.
 __global__ void __launch_bounds__(256) maxpool333_s1_kernel(const PoolP p) {
+  pdl_launch_dependents();   // programmatic dependent launch, see common.h
+  pdl_wait();
   const int c8n = p.y.C >> 3;
   const long long total = p.total * c8n;
   const uint4 neg = make_uint4(0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u);
@@ -213,6 +217,8 @@ __device__ __forceinline__ void up_hrow(const __nv_bfloat16* r, long long o0, lo
 }
 
 __global__ void __launch_bounds__(256) upsample2x_kernel(const UpP p) {
+  pdl_launch_dependents();   // programmatic dependent launch, see common.h
+  pdl_wait();
   const int c8n = p.y.C >> 3;
   const int items = p.y.W * c8n;
   const int bands = (p.y.H + UP_ROWS - 1) / UP_ROWS;
@@ -284,8 +290,10 @@ struct OutP {
 // are combined with warp shuffles.
 __global__ void __launch_bounds__(256) outconv_sigmoid_kernel(const OutP p) {
   extern __shared__ float sw[];  // [3][C]
-  for (int i = threadIdx.x; i < 3 * p.x.C; i += blockDim.x) sw[i] = p.w[i];
+  pdl_launch_dependents();
+  for (int i = threadIdx.x; i < 3 * p.x.C; i += blockDim.x) sw[i] = p.w[i];   // constants: before the wait
   __syncthreads();
+  pdl_wait();
   const int sub = threadIdx.x & 7;
   const int chunks = p.x.C >> 3;
   const long long gstride = static_cast<long long>(gridDim.x) * (blockDim.x >> 3);
@@ -338,6 +346,8 @@ struct AvgP {
 
 // one block per (n, od); thread -> 8 channels; loops over the kd*H*W window (coalesced 16-byte loads)
 __global__ void __launch_bounds__(256) avgpool_kernel(const AvgP p) {
+  pdl_launch_dependents();   // programmatic dependent launch, see common.h
+  pdl_wait();
   const int n = blockIdx.x / p.OD, od = blockIdx.x - n * p.OD;
   const float inv = 1.f / static_cast<float>(p.kd * p.x.H * p.x.W);
   for (int c8 = threadIdx.x; c8 < (p.x.C >> 3); c8 += blockDim.x) {
@@ -454,7 +464,9 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PrepP p) {
   build_axis_table(p.crop_w, Wo, p.resample, xlo, xcnt, xwf, xwi);
   build_axis_table(p.crop_h, Ho, p.resample, ylo, ycnt, ywf, ywi);
   for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = static_cast<float>(i) / 255.f;
+  pdl_launch_dependents();
   __syncthreads();
+  pdl_wait();   // the tables above depend on the launch parameters only
 
   const int n = blockIdx.y;
   const int32_t* d = p.desc + n * 4;
@@ -524,6 +536,8 @@ struct CvtP {
 };
 
 __global__ void __launch_bounds__(256) nchw_to_cl_kernel(const CvtP p) {
+  pdl_launch_dependents();   // programmatic dependent launch, see common.h
+  pdl_wait();
   const long long plane = static_cast<long long>(p.y.D) * p.y.H * p.y.W;
   const int cw = p.y.C == 4 ? 4 : 8;  // channels per thread: one 8- or 16-byte store
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < p.total;
@@ -559,6 +573,8 @@ struct P2CP {
 
 // thread -> 8 consecutive pixels of one encoder row: three 16-byte plane reads, 8 pixel stores
 __global__ void __launch_bounds__(256) planes_to_clip_kernel(const P2CP p) {
+  pdl_launch_dependents();   // programmatic dependent launch, see common.h
+  pdl_wait();
   const int w8n = p.y.W >> 3;
   const long long plane = static_cast<long long>(p.y.H) * p.y.W;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < p.total;
@@ -642,21 +658,21 @@ extern "C" int tedspad_maxpool(const tedspad_tensor* x, const tedspad_tensor* y,
   const bool same333 = kd == 3 && kh == 3 && kw == 3 && sd == 1 && sh == 1 && sw == 1 && pd == 1 && ph == 1 && pw == 1 &&
                        x->D == y->D && x->H == y->H && x->W == y->W;
   if (same333) {
-    maxpool333_s1_kernel<<<grid_for(p.total * (y->C / 8), 256), 256, 0, st>>>(p);
+    TSP_CUDA(launch_kernel(maxpool333_s1_kernel, dim3(grid_for(p.total * (y->C / 8), 256)), dim3(256), 0, st, p));
   } else if (kd == 1 && kh == 3 && kw == 3) {
-    maxpool_kernel<1, 3, 3><<<grid, 256, 0, st>>>(p);
+    TSP_CUDA(launch_kernel(maxpool_kernel<1, 3, 3>, dim3(grid), dim3(256), 0, st, p));
   } else if (kd == 3 && kh == 3 && kw == 3) {
-    maxpool_kernel<3, 3, 3><<<grid, 256, 0, st>>>(p);
+    TSP_CUDA(launch_kernel(maxpool_kernel<3, 3, 3>, dim3(grid), dim3(256), 0, st, p));
   } else if (kd == 2 && kh == 2 && kw == 2) {
-    maxpool_kernel<2, 2, 2><<<grid, 256, 0, st>>>(p);
+    TSP_CUDA(launch_kernel(maxpool_kernel<2, 2, 2>, dim3(grid), dim3(256), 0, st, p));
   } else if (kd == 1 && kh == 2 && kw == 2) {
-    maxpool_kernel<1, 2, 2><<<grid, 256, 0, st>>>(p);
+    TSP_CUDA(launch_kernel(maxpool_kernel<1, 2, 2>, dim3(grid), dim3(256), 0, st, p));
   } else if (kd == 2 && kh == 3 && kw == 3) {
-    maxpool_kernel<2, 3, 3><<<grid, 256, 0, st>>>(p);
+    TSP_CUDA(launch_kernel(maxpool_kernel<2, 3, 3>, dim3(grid), dim3(256), 0, st, p));
   } else if (kd == 2 && kh == 1 && kw == 1) {
-    maxpool_kernel<2, 1, 1><<<grid, 256, 0, st>>>(p);
+    TSP_CUDA(launch_kernel(maxpool_kernel<2, 1, 1>, dim3(grid), dim3(256), 0, st, p));
   } else {
-    maxpool_kernel<0, 0, 0><<<grid, 256, 0, st>>>(p);
+    TSP_CUDA(launch_kernel(maxpool_kernel<0, 0, 0>, dim3(grid), dim3(256), 0, st, p));
   }
   TSP_CUDA(cudaGetLastError());
   return 0;
@@ -676,7 +692,7 @@ extern "C" int tedspad_upsample2x(const tedspad_tensor* x, const tedspad_tensor*
   p.total = static_cast<long long>(y->N) * ((y->H + UP_ROWS - 1) / UP_ROWS);   // bands of UP_ROWS output rows
   p.c8_magic = static_cast<uint32_t>((0x100000000ULL + (y->C / 8) - 1) / (y->C / 8));
   TSP_CHECK(static_cast<long long>(y->W) * (y->C / 8) < 65536, "upsample2x: row of %d x %d channels too long", y->W, y->C);
-  upsample2x_kernel<<<rows_grid(p.total, y->W * (y->C / 8)), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  TSP_CUDA(launch_kernel(upsample2x_kernel, dim3(rows_grid(p.total, y->W * (y->C / 8))), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), p));
   TSP_CUDA(cudaGetLastError());
   return 0;
 }
@@ -694,7 +710,7 @@ extern "C" int tedspad_outconv_sigmoid(const tedspad_tensor* x, const float* w, 
   p.w = w; p.b = b; p.frames = frames_out; p.T = T;
   p.total = static_cast<long long>(x->N) * x->H * x->W;
   const int blocks = grid_for(p.total * 8, 256);
-  outconv_sigmoid_kernel<<<blocks, 256, 3 * x->C * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  TSP_CUDA(launch_kernel(outconv_sigmoid_kernel, dim3(blocks), dim3(256), 3 * x->C * sizeof(float), reinterpret_cast<cudaStream_t>(stream), p));
   TSP_CUDA(cudaGetLastError());
   return 0;
 }
@@ -709,7 +725,7 @@ extern "C" int tedspad_avgpool_features(const tedspad_tensor* x, int32_t kd, flo
   TSP_CHECK(p.kd <= x->D, "avgpool: window %d larger than D=%d", p.kd, x->D);
   p.OD = x->D - p.kd + 1;
   p.out = out;
-  avgpool_kernel<<<x->N * p.OD, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  TSP_CUDA(launch_kernel(avgpool_kernel, dim3(x->N * p.OD), dim3(128), 0, reinterpret_cast<cudaStream_t>(stream), p));
   TSP_CUDA(cudaGetLastError());
   return 0;
 }
@@ -739,7 +755,7 @@ extern "C" int tedspad_preprocess(const uint8_t* frames, int32_t F, int32_t Hs, 
   const int want = (num_sms() * 16 + n_out - 1) / n_out;
   const int bands = std::max(1, std::min(std::min(64, want), (y->H * y->W + 511) / 512));
   dim3 grid(bands, n_out);
-  preprocess_kernel<<<grid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  TSP_CUDA(launch_kernel(preprocess_kernel, grid, dim3(256), smem, reinterpret_cast<cudaStream_t>(stream), p));
   TSP_CUDA(cudaGetLastError());
   return 0;
 }
@@ -751,7 +767,7 @@ extern "C" int tedspad_nchw_to_cl(const float* x, int32_t Cx, const tedspad_tens
   CvtP p;
   p.x = x; p.Cx = Cx; p.y = make_view(*y);
   p.total = static_cast<long long>(y->N) * y->D * y->H * y->W * (y->C == 4 ? 1 : y->C / 8);
-  nchw_to_cl_kernel<<<grid_for(p.total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  TSP_CUDA(launch_kernel(nchw_to_cl_kernel, dim3(grid_for(p.total, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), p));
   TSP_CUDA(cudaGetLastError());
   return 0;
 }
@@ -768,7 +784,7 @@ extern "C" int tedspad_planes_to_clip(const void* planes, const tedspad_tensor* 
   p.y = make_view(*y);
   p.T = T;
   p.total = static_cast<long long>(y->N) * T * y->H * (y->W / 8);
-  planes_to_clip_kernel<<<grid_for(p.total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  TSP_CUDA(launch_kernel(planes_to_clip_kernel, dim3(grid_for(p.total, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), p));
   TSP_CUDA(cudaGetLastError());
   return 0;
 }
