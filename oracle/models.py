@@ -399,3 +399,38 @@ def calibrated_state_dict(arch, seed, calib_input, num_classes=102, beta_over_ga
             sd[bn + ".bias"] = sd[bn + ".bias"] * s
         _calibrate(arch, sd, calib_input)
     return sd
+
+
+def segment_features_dali(vid_features, num_features):
+    """feature_extraction/dali_extraction.py:85-100, statement for statement (disabled in the script, `segment=False`)."""
+    segmented_features = np.zeros((32, num_features))
+    segment_loc = np.linspace(0, vid_features.shape[0], 33, dtype=int)
+    for idx in range(len(segment_loc) - 1):
+        ss, es = segment_loc[idx], segment_loc[idx + 1] - 1
+        if idx == 31:
+            es += 1
+        if ss <= es or es < ss:
+            temp_vect = vid_features[ss][:]
+        else:
+            temp_vect = np.mean(vid_features[ss:es][:])
+        temp_vect = temp_vect / np.linalg.norm(temp_vect)
+        segmented_features[idx] = temp_vect
+    return segmented_features
+
+
+def segment_features_shanghai(vid_features):
+    """feature_extraction/st_feature_extraction.py:40-55, statement for statement (width taken from the input
+    instead of the hard-coded 1024)."""
+    segmented_features = np.zeros((32, vid_features.shape[1]))
+    segment_loc = np.linspace(0, vid_features.shape[0], 33, dtype=int)
+    for idx in range(len(segment_loc) - 1):
+        ss, es = segment_loc[idx], segment_loc[idx + 1] - 1
+        if idx == 31:
+            es += 1
+        if ss <= es:
+            temp_vect = vid_features[ss][:]
+        else:
+            temp_vect = np.mean(vid_features[ss:es][:])
+        temp_vect = temp_vect / np.linalg.norm(temp_vect)
+        segmented_features[idx] = temp_vect
+    return segmented_features

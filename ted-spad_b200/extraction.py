@@ -195,6 +195,36 @@ class SnippetExtractor:
         return allf[:, 0, :] if self.ncrops == 1 else allf
 
 
+def segment_features(vid_features, num_features=None, rule="dali"):
+    """The optional 32-segment pooling of the reference scripts ("as in Sultani et al."), which both scripts ship
+    DISABLED (`segment=False`: dali_extraction.py:155,181; st_feature_extraction.py:100).  Restated as written:
+    segment boundaries `np.linspace(0, n, 33, dtype=int)`; the DALI script's branch `ss <= es or es < ss` is always
+    true (dali_extraction.py:93), so every segment is the single row at its start, L2-normalised; the ShanghaiTech
+    script (st_feature_extraction.py:49-52) takes that row when `ss <= es` and otherwise the *scalar*
+    `np.mean(vid_features[ss:es])` (NaN for an empty slice, the mean of all rows but the last when es == -1)
+    divided by its own norm and broadcast over the row.  Returns
+    float64 [32, F]."""
+    vid_features = np.asarray(vid_features)
+    n, F = vid_features.shape
+    if num_features is not None and num_features != F:
+        raise ValueError(f"features have {F} columns, expected {num_features}")
+    if rule not in ("dali", "shanghai"):
+        raise ValueError("rule must be 'dali' or 'shanghai'")
+    loc = np.linspace(0, n, 33, dtype=int)
+    out = np.zeros((32, F))
+    with np.errstate(invalid="ignore", divide="ignore"):
+        for idx in range(32):
+            ss, es = loc[idx], loc[idx + 1] - 1
+            if idx == 31:
+                es += 1
+            if rule == "dali" or ss <= es:
+                v = vid_features[ss]                          # raises for an empty video, like the reference
+            else:
+                v = np.mean(vid_features[ss:es])              # scalar; Python slice semantics (es may be -1)
+            out[idx] = v / np.linalg.norm(v)
+    return out
+
+
 def feature_path(save_folder, vid_path):
     """<folder>/<basename minus .mp4/.avi>.npy (dali_extraction.py:159, st_feature_extraction.py:88)."""
     base = os.path.basename(vid_path).replace('.mp4', '').replace('.avi', '')
@@ -215,7 +245,7 @@ def shard_videos(lengths, world_size):
     return [sorted(s) for s in shards]
 
 
-def extract_dataset(extractor, videos, save_folder, rank=0, world_size=1, log=print):
+def extract_dataset(extractor, videos, save_folder, rank=0, world_size=1, log=print, segment=False):
     """videos: list of (path, n_frames, loader) with loader() -> uint8 [F,H,W,3].  The partition is computed
     over the FULL list (so every rank derives the same one no matter when it starts); within its shard a
     rank skips videos whose .npy already exists - the reference's resume rule (dali_extraction.py:121).
@@ -230,6 +260,8 @@ def extract_dataset(extractor, videos, save_folder, rank=0, world_size=1, log=pr
             continue
         log(f'Extracting features for {os.path.basename(path)}.')
         feats = extractor.extract_video(loader())
+        if segment:   # the reference's `segment` flag (False in both scripts: dali_extraction.py:181, st:100)
+            feats = segment_features(feats, rule="shanghai" if getattr(extractor, "source", "dali") == "shanghai" else "dali")
         tmp = out + f".tmp{rank}.npy"
         np.save(tmp, feats)
         os.replace(tmp, out)

@@ -311,3 +311,19 @@ def test_world_size_2_gloo_sharded_extraction_equals_single(tmp_path):
     for f in sorted(os.listdir(single)):
         assert np.array_equal(np.load(single / f), np.load(sharded / f)), f
     assert sorted(os.listdir(single)) == sorted(os.listdir(sharded))
+
+
+def test_segment_features_match_reference_statements():
+    """a-11: the (disabled) 32-segment pooling of both scripts, against their statement-for-statement restatement."""
+    import warnings
+    rs = np.random.RandomState(5)
+    for n in (1, 7, 31, 32, 33, 64, 219, 1000):
+        f = rs.rand(n, 16) + 0.1
+        assert np.array_equal(extraction.segment_features(f, 16), M.segment_features_dali(f, 16))
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            want = M.segment_features_shanghai(f)
+        got = extraction.segment_features(f, rule="shanghai")
+        assert np.array_equal(np.isnan(got), np.isnan(want)) and np.array_equal(np.nan_to_num(got), np.nan_to_num(want)), n
+    with pytest.raises(IndexError):
+        extraction.segment_features(np.zeros((0, 16)))
