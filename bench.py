@@ -246,13 +246,16 @@ def main():
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
-    # conv-kernel-only time: same steps, one CUDA event pair around every tedspad_conv_forward launch
+    # conv-kernel-only time: the same K steps again, back to back with the timed region (same thermal / power state),
+    # with one CUDA event pair around every convolution launch; the first step re-warms and is not counted
+    n_ev = max(2, args.steps)
+    step_resident(0)
     ops.CONV_EVENTS = []
-    for i in range(2):
-        step_resident(i)
+    for i in range(n_ev):
+        step_resident(i + 1)
     torch.cuda.synchronize()
-    conv_ms = sum(a.elapsed_time(b) for a, b, _ in ops.CONV_EVENTS) / 2.0
-    n_conv = len(ops.CONV_EVENTS) // 2
+    conv_ms = sum(a.elapsed_time(b) for a, b, _ in ops.CONV_EVENTS) / n_ev
+    n_conv = len(ops.CONV_EVENTS) // n_ev
     ops.CONV_EVENTS = None
 
     ms_step = ms_total / args.steps

@@ -20,6 +20,7 @@ USE_SLAB = os.environ.get("TEDSPAD_SLAB", "1") != "0"
 USE_PAIR = os.environ.get("TEDSPAD_PAIR", "1") != "0"     # cta_group::2 for the 64-output-channel 3x3 layers
 PAD_SMALL_3X3 = USE_SLAB and os.environ.get("TEDSPAD_PAD_SMALL_3X3", "1") != "0"
 MERGE_1X1 = os.environ.get("TEDSPAD_MERGE_1X1", "1") != "0"  # Inception b0/b1a/b2a (same input) as one GEMM
+USE_STREAM_PAIR = USE_PAIR and os.environ.get("TEDSPAD_STREAM_PAIR", "1") != "0"
 USE_SLAB_STEM3D = USE_SLAB and os.environ.get("TEDSPAD_SLAB_STEM3D", "1") != "0"
 SLAB_WEIGHT_LIMIT = 150 * 1024   # bytes of resident weights that still leave room for three slab stages
 ENC_IN_CHANNELS = 4 if USE_SLAB_STEM3D else 8   # channel padding of the encoder input clip
@@ -47,7 +48,7 @@ def slab3x3(pc, max_stream_cout=512):
     if pc.cout_pad <= max_stream_cout and pc.n_tile % 32 == 0:
         # 2-D layers with one N tile: CTA pairs stream half a weight block each (measured +11..17 % at N = 128 / 256 on
         # 112^2 / 56^2 maps, neutral at 28^2; the 3-D Inception branches with their few tiles per launch lose 0-5 %)
-        if USE_PAIR and kd == 1 and pc.cout_pad <= 256 and pc.n_tile == pc.cout_pad:
+        if USE_STREAM_PAIR and kd == 1 and pc.cout_pad <= 256 and pc.n_tile == pc.cout_pad:
             return ops.PackedSlabConv(pc, L.SLAB_3X3_STREAM_PAIR)
         return ops.PackedSlabConv(pc, L.SLAB_3X3_STREAM)
     return None
