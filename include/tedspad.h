@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define TEDSPAD_ABI_VERSION 4
+#define TEDSPAD_ABI_VERSION 5
 
 enum { TEDSPAD_ACT_NONE = 0, TEDSPAD_ACT_RELU = 1, TEDSPAD_ACT_SIGMOID = 2 };
 /* A-operand feed of the implicit GEMM: AUTO picks FLAT when legal. */
@@ -106,8 +106,10 @@ int tedspad_conv_forward(const tedspad_conv* p, void* stream);
  *                        I3Res50.conv1 (large_i3d.py:135), torchvision BasicStem (video/resnet.py:
  *                        173-181).  Same overlapped descriptors; one UMMA row step (16 B) = the
  *                        stride of 2 pixels, one K chunk = 2 pixels x 4 channels.
- *   TEDSPAD_SLAB_3X3_STREAM  Conv2d 3x3 / Conv3d 3x3x3 (or (1,3,3)), stride 1, same padding, Cin % 64
- *                        == 0, any Cout_pad <= 512 (multiple of 32): same slab for the activations, but
+ *   TEDSPAD_SLAB_3X3_STREAM  Conv2d 3x3 / Conv3d 3x3x3 (or (1,3,3)) and, with ONE spatial tap per K stage, 1x1x1 /
+ *                        (3,1,1) convolutions (Bottleneck conv1 / conv3 of large_i3d.py:47-58, the Inception pool
+ *                        branch and Conv3d_2b of i3d.py), stride 1, same padding, Cin % 64
+ *                        == 0, any Cout_pad <= 2048 (multiple of 32): same slab for the activations, but
  *                        the weights are too large to stay resident and stream through their own ring
  *                        of [n_tile x 64] blocks, one per filter tap (2-D TMA on the STANDARD packed
  *                        layout: pass it as `w_image`, with K_pad).  A K stage = (temporal tap, 64-channel
@@ -157,6 +159,9 @@ typedef struct tedspad_conv_slab {
   int32_t max_ctas;         /* persistent grid cap; 0 = number of SMs */
   int32_t n_tile;           /* STREAM kind: UMMA N per tile (multiple of 32 dividing Cout_pad); 0 = auto */
   int32_t K_pad;            /* STREAM kind: row length of the standard packed weights */
+  const void* res;          /* optional bf16 residual laid out like y (same pixel geometry and halo): y = act(conv + bias +
+                               res), the Bottleneck tail of large_i3d.py:72-79.  Excludes pool / OutConv / up.  NULL = none */
+  int32_t res_ld, res_coff; /* residual row length and first channel, elements */
   tedspad_tensor oc_clip;   /* optional fused OutConv destination: the ENCODER clip [B][T][H][W][>=3] (bf16), written
                                through the raw-reshape glue of dali_extraction.py:171-173 (plane 3t+c of clip b ->
                                channel (3t+c)/T, time (3t+c)%T); channels >= 3 are not touched.  With it oc_planes may be

@@ -15,7 +15,7 @@ FEED_AUTO, FEED_FLAT_TMA, FEED_GATHER = 0, 1, 2
 RESAMPLE_AA_FLOAT, RESAMPLE_PIL_U8 = 0, 1
 SLAB_3X3, SLAB_STEM2D, SLAB_STEM3D, SLAB_3X3_STREAM, SLAB_3X3_PAIR, SLAB_3X3_STREAM_PAIR = 0, 1, 2, 3, 4, 5
 SLAB_MAX_MMA = 112
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class TensorDesc(C.Structure):
@@ -39,7 +39,7 @@ class ConvSlabDesc(C.Structure):
                 ("pool", TensorDesc), ("up", TensorDesc), ("oc_w", C.c_void_p), ("oc_b", C.c_void_p), ("oc_planes", C.c_void_p),
                 ("oc_frames", C.c_void_p)] + [(n, C.c_int32) for n in (
                     "kind", "Cout", "Cout_pad", "kd", "kh", "kw", "sd", "sh", "sw", "pd", "ph", "pw", "act", "tm",
-                    "max_ctas", "n_tile", "K_pad")] + [("oc_clip", TensorDesc), ("oc_T", C.c_int32), ("stack_rows", C.c_int32)]
+                    "max_ctas", "n_tile", "K_pad")] + [("res", C.c_void_p), ("res_ld", C.c_int32), ("res_coff", C.c_int32), ("oc_clip", TensorDesc), ("oc_T", C.c_int32), ("stack_rows", C.c_int32)]
 
 
 class SlabPlan(C.Structure):

@@ -62,7 +62,7 @@ struct SlabKParams {
   CUtensorMap tmB;           // streamed weights: standard packed [Cout_pad][K_pad], box {64, n_tile}
   const uint8_t* w_image;
   const float* bias;
-  int tm, n_tile, k_stages, n_grp, nk, a_kstep, b_kstep, stages, tmem_cols, acc_stages;
+  int tm, n_tile, k_stages, n_grp, nk, a_kstep, b_kstep, stages, tmem_cols, acc_stages, bias_floats;
   int slab_bytes, slab_stride, w_bytes, w_stride, zero_slabs;
   int b_stream, b_stages, b_stride, cb_n, cin, num_n_tiles, tab_per_stage;
   // fused x2 bilinear up-sampling source (channel blocks >= up_cb_first are interpolated into the slab)
@@ -85,6 +85,8 @@ struct SlabKParams {
   const float* oc_b;
   __nv_bfloat16* oc_planes;
   float* oc_frames;
+  const __nv_bfloat16* res;    // optional bf16 residual with y's geometry (added before the activation)
+  int res_ld, res_coff;
   __nv_bfloat16* oc_clip;      // encoder clip written through the raw-reshape glue (NULL = planes only)
   int oc_T, cDp, cHp, cWp, cpd, cph, cpw, c_ld, c_coff;
   DivMagic dv_T;
@@ -206,6 +208,8 @@ struct EpiCtx {
   __nv_bfloat16* pool;
   int Cout, act, y_ld, y_coff, p_ld, p_coff;
   bool fuse_oc, wide_ok, pool_wide_ok;
+  const __nv_bfloat16* res;   // EPI_RES: bf16 residual with y's pixel geometry
+  int res_ld, res_coff;
 };
 
 // MODE: 0 = bf16 stores only, 1 = + fused MaxPool2d(2), 2 = fused OutConv (stores / pool optional at run time),
@@ -214,12 +218,26 @@ struct EpiCtx {
 // issue-selected 12-16 % of their samples, the rest short-scoreboard / fixed-latency waits).  (Processing both
 // chunks of a 64-output tile as one instruction stream - no TMEM-load / math overlap, twice the live registers -
 // was measured slower: 64->64 + OutConv 1.70 -> 2.20 ms.)
-enum { EPI_PLAIN = 0, EPI_POOL = 1, EPI_OC = 2, EPI_OC_ONLY = 3 };   // OC_ONLY: OutConv with no 64-channel store, no pool
+enum { EPI_PLAIN = 0, EPI_POOL = 1, EPI_OC = 2, EPI_OC_ONLY = 3, EPI_RES = 4 };   // OC_ONLY: OutConv with no 64-channel
+                                                                                  // store, no pool; RES: plain + residual
+
+// The 64 bytes (32 bf16) of residual of one chunk of this thread's pixel, fetched with pinned loads when the chunk's
+// accumulator load is issued (so that the DRAM round trip overlaps the previous chunk's arithmetic).
+__device__ __forceinline__ void epi_res_fetch(const EpiCtx& c, long long pix, int c0, bool valid, uint4 (&r)[4]) {
+  const __nv_bfloat16* rp = c.res + pix * c.res_ld + c.res_coff + c0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    r[j] = make_uint4(0u, 0u, 0u, 0u);
+    if (valid && c0 + 8 * j < c.Cout) r[j] = ld_nc_v4_pinned(rp + 8 * j);
+  }
+}
 
 template <int MODE, bool RELU>
-__device__ __forceinline__ void epi_math(const EpiCtx& c, const uint32_t (&v)[32], int c0, uint32_t (&q)[16], float (&oc)[3]) {
+__device__ __forceinline__ void epi_math(const EpiCtx& c, const uint32_t (&v)[32], int c0, uint32_t (&q)[16], float (&oc)[3],
+                                         const uint4 (&r)[4]) {
   if (MODE != EPI_OC && MODE != EPI_OC_ONLY) {
     // 16 packed fp32x2 bias adds + 16 converts with the ReLU fused into the rounding instruction
+    const uint32_t* rw = reinterpret_cast<const uint32_t*>(&r[0]);   // EPI_RES: 16 packed bf16 pairs
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
       const float4 b4 = *reinterpret_cast<const float4*>(c.bias + c0 + i);
@@ -227,6 +245,11 @@ __device__ __forceinline__ void epi_math(const EpiCtx& c, const uint32_t (&v)[32
       float f2 = __uint_as_float(v[i + 2]), f3 = __uint_as_float(v[i + 3]);
       add_f32x2(f0, f1, b4.x, b4.y);
       add_f32x2(f2, f3, b4.z, b4.w);
+      if (MODE == EPI_RES) {   // bn3 + residual, then ReLU (large_i3d.py:72-79); a bf16 is the upper half of an fp32
+        const uint32_t p0 = rw[i >> 1], p1 = rw[(i >> 1) + 1];
+        add_f32x2(f0, f1, __uint_as_float(p0 << 16), __uint_as_float(p0 & 0xffff0000u));
+        add_f32x2(f2, f3, __uint_as_float(p1 << 16), __uint_as_float(p1 & 0xffff0000u));
+      }
       q[i >> 1] = cvt_bf16x2(f0, f1, RELU);
       q[(i >> 1) + 1] = cvt_bf16x2(f2, f3, RELU);
     }
@@ -322,13 +345,14 @@ __device__ __forceinline__ void slab_epilogue(const SlabKParams& p, int warp, in
   const int nchunk_all = n_tile >> 5;
   EpiCtx c;
   c.bias = sm_bias; c.ocw = sm_ocw; c.y = p.y; c.pool = p.pool; c.Cout = p.Cout; c.act = p.act;
-  c.y_ld = p.y_ld; c.y_coff = p.y_coff; c.p_ld = p.p_ld; c.p_coff = p.p_coff; c.fuse_oc = MODE >= EPI_OC;
+  c.y_ld = p.y_ld; c.y_coff = p.y_coff; c.p_ld = p.p_ld; c.p_coff = p.p_coff; c.fuse_oc = (MODE == EPI_OC || MODE == EPI_OC_ONLY);
   // 32-byte stores need 32-byte aligned pixel chunks
   c.wide_ok = ((p.y_ld | p.y_coff) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.y) & 31) == 0;
   c.pool_wide_ok = false;
+  c.res = p.res; c.res_ld = p.res_ld; c.res_coff = p.res_coff;
   int h, c_first, c_step, nch;
   if (tm == 2) { h = eg; c_first = 0; c_step = 32; nch = nchunk_all; }
-  else if (MODE >= EPI_OC) { h = 0; c_first = 0; c_step = 32; nch = eg == 0 ? nchunk_all : 0; }
+  else if ((MODE == EPI_OC || MODE == EPI_OC_ONLY)) { h = 0; c_first = 0; c_step = 32; nch = eg == 0 ? nchunk_all : 0; }
   else { h = 0; c_first = 32 * eg; c_step = 64; nch = (nchunk_all + 1 - eg) >> 1; }
   int as = 0;
   uint32_t aph = 0;
@@ -364,29 +388,42 @@ __device__ __forceinline__ void slab_epilogue(const SlabKParams& p, int warp, in
     float oc[3] = {0.f, 0.f, 0.f};
     mbar_wait(tfull + as, aph);
     tc_fence_after();
+    uint4 ra[4], rb[4];   // EPI_RES only (dead otherwise)
     if (HAS_UP) {   // 480-thread variant: 136 registers per thread, one chunk in flight
       uint32_t va[32], qa[16];
       for (int i = 0; i < nch; ++i) {
-        tmem_ld32(t_row + i * c_step, va);
-        tmem_ld_wait();
         const int c0 = n0 + c_first + i * c_step;
-        epi_math<MODE, RELU>(c, va, c0, qa, oc);
+        tmem_ld32(t_row + i * c_step, va);
+        if (MODE == EPI_RES) epi_res_fetch(c, pix, c0, valid, ra);
+        tmem_ld_wait();
+        epi_math<MODE, RELU>(c, va, c0, qa, oc, ra);
         epi_out<MODE>(c, qa, c0, valid, pix, pool_writer, ppix);
       }
     } else {
-      // software pipeline over this warp's chunks: the next chunk's TMEM load is in flight while one is processed
+      // software pipeline over this warp's chunks: the next chunk's TMEM load (and residual) is in flight while one
+      // is processed
       uint32_t va[32], vb[32], qa[16];
-      if (nch > 0) tmem_ld32(t_row, va);
+      const int cbase = n0 + c_first;
+      if (nch > 0) {
+        tmem_ld32(t_row, va);
+        if (MODE == EPI_RES) epi_res_fetch(c, pix, cbase, valid, ra);
+      }
       for (int i = 0; i < nch; i += 2) {
         tmem_ld_wait();
-        if (i + 1 < nch) tmem_ld32(t_row + (i + 1) * c_step, vb);
-        const int c0 = n0 + c_first + i * c_step;
-        epi_math<MODE, RELU>(c, va, c0, qa, oc);
+        const int c0 = cbase + i * c_step;
+        if (i + 1 < nch) {
+          tmem_ld32(t_row + (i + 1) * c_step, vb);
+          if (MODE == EPI_RES) epi_res_fetch(c, pix, c0 + c_step, valid, rb);
+        }
+        epi_math<MODE, RELU>(c, va, c0, qa, oc, ra);
         epi_out<MODE>(c, qa, c0, valid, pix, pool_writer, ppix);
         if (i + 1 < nch) {
           tmem_ld_wait();
-          if (i + 2 < nch) tmem_ld32(t_row + (i + 2) * c_step, va);
-          epi_math<MODE, RELU>(c, vb, c0 + c_step, qa, oc);
+          if (i + 2 < nch) {
+            tmem_ld32(t_row + (i + 2) * c_step, va);
+            if (MODE == EPI_RES) epi_res_fetch(c, pix, c0 + 2 * c_step, valid, ra);
+          }
+          epi_math<MODE, RELU>(c, vb, c0 + c_step, qa, oc, rb);
           epi_out<MODE>(c, qa, c0 + c_step, valid, pix, pool_writer, ppix);
         }
       }
@@ -398,7 +435,7 @@ __device__ __forceinline__ void slab_epilogue(const SlabKParams& p, int warp, in
       if (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(tempty + as), 0));
       else mbar_arrive(tempty + as);
     }
-    if (MODE >= EPI_OC && valid && nch > 0) {
+    if ((MODE == EPI_OC || MODE == EPI_OC_ONLY) && valid && nch > 0) {
       const long long plane = static_cast<long long>(OH) * OW;
       const long long o0 = static_cast<long long>(n) * 3 * plane + static_cast<long long>(oy) * OW + ox;
       const int bclip = fdiv(n, p.dv_T), tf = n - bclip * p.oc_T;   // frame n = clip bclip, time tf
@@ -476,7 +513,7 @@ conv_slab_kernel(const __grid_constant__ SlabKParams p) {
   uint8_t* smW = smem;
   uint8_t* smS = smem + p.w_stride;
   float* sm_bias = reinterpret_cast<float*>(smS + S * p.slab_stride);
-  float* sm_ocw = sm_bias + 512;        // [3][Cout] then [3] bias
+  float* sm_ocw = sm_bias + p.bias_floats;   // [3][Cout] then [3] bias
   uint64_t* full = reinterpret_cast<uint64_t*>(sm_ocw + 256);
   uint64_t* empty = full + SLAB_MAX_STAGES;
   uint64_t* tfull = empty + SLAB_MAX_STAGES;
@@ -630,7 +667,8 @@ conv_slab_kernel(const __grid_constant__ SlabKParams p) {
       if (relu) slab_epilogue<HAS_UP, PAIR, MODE_, true>(p, warp, lane, tmem_base, sm_bias, sm_ocw, tfull, tempty); \
       else slab_epilogue<HAS_UP, PAIR, MODE_, false>(p, warp, lane, tmem_base, sm_bias, sm_ocw, tfull, tempty); \
     } while (0)
-    if (p.oc_w != nullptr && p.y == nullptr && p.pool == nullptr) TSP_EPI(EPI_OC_ONLY);
+    if (p.res != nullptr) TSP_EPI(EPI_RES);
+    else if (p.oc_w != nullptr && p.y == nullptr && p.pool == nullptr) TSP_EPI(EPI_OC_ONLY);
     else if (p.oc_w != nullptr) TSP_EPI(EPI_OC);
     else if (p.pool != nullptr) TSP_EPI(EPI_POOL);
     else TSP_EPI(EPI_PLAIN);
@@ -770,10 +808,10 @@ static int make_plan(const tedspad_conv_slab& c, tedspad_slab_plan& P) {
   const bool stream = c.kind == TEDSPAD_SLAB_3X3_STREAM || c.kind == TEDSPAD_SLAB_3X3_STREAM_PAIR;
   const bool pair = c.kind == TEDSPAD_SLAB_3X3_PAIR || c.kind == TEDSPAD_SLAB_3X3_STREAM_PAIR;
   P.pair = pair ? 1 : 0;
-  TSP_CHECK(c.Cout_pad % 32 == 0 && c.Cout_pad >= 32 && c.Cout_pad <= (stream ? 512 : 256) && c.Cout <= c.Cout_pad &&
+  TSP_CHECK(c.Cout_pad % 32 == 0 && c.Cout_pad >= 32 && c.Cout_pad <= (stream ? 2048 : 256) && c.Cout <= c.Cout_pad &&
                 c.Cout >= 1 && c.Cout % 8 == 0,
             "slab: Cout=%d (multiple of 8) / Cout_pad=%d (multiple of 32, <= %d) invalid", c.Cout, c.Cout_pad,
-            stream ? 512 : 256);
+            stream ? 2048 : 256);
   TSP_CHECK(x.N == y.N && x.N >= 1, "slab: batch mismatch");
   P.n_tile = c.Cout_pad;
   P.num_n_tiles = 1;
@@ -885,19 +923,21 @@ static int make_plan(const tedspad_conv_slab& c, tedspad_slab_plan& P) {
       }
     }
   } else if (stream) {
-    TSP_CHECK((c.kd == 1 || c.kd == 3) && c.kh == 3 && c.kw == 3 && c.sd == 1 && c.sh == 1 && c.sw == 1 &&
-                  c.pd == c.kd / 2 && c.ph == 1 && c.pw == 1,
-              "slab stream: needs a (1|3,3,3) stride-1 same-padded convolution");
+    const bool k33 = c.kh == 3 && c.kw == 3 && c.ph == 1 && c.pw == 1;
+    const bool k11 = c.kh == 1 && c.kw == 1 && c.ph == 0 && c.pw == 0;   // 1x1x1 and (3,1,1): one tap per K stage
+    TSP_CHECK((c.kd == 1 || c.kd == 3) && (k33 || k11) && c.sd == 1 && c.sh == 1 && c.sw == 1 && c.pd == c.kd / 2,
+              "slab stream: needs a (1|3) x (3x3 | 1x1) stride-1 same-padded convolution");
+    const int ntap = c.kh * c.kw, hw = c.kw / 2;   // spatial taps per K stage, halo of the slab
     TSP_CHECK(x.D == y.D && x.H == y.H && x.W == y.W, "slab: output extents must equal input extents");
     TSP_CHECK(x.C % 64 == 0 && x.C >= 64, "slab stream: x.C=%d must be a multiple of 64", x.C);
-    TSP_CHECK(c.K_pad == c.kd * 9 * cin_total, "slab stream: K_pad=%d != %d taps x %d channels", c.K_pad, c.kd * 9, cin_total);
+    TSP_CHECK(c.K_pad == c.kd * ntap * cin_total, "slab stream: K_pad=%d != %d taps x %d channels", c.K_pad, c.kd * ntap, cin_total);
     TSP_CHECK(c.oc_w == nullptr, "slab stream: fused OutConv needs the resident-weight kind");
     P.swizzle128 = 1;
     P.cb_n = cin_total / 64;
     P.cin = cin_total;
     P.k_stages = c.kd * P.cb_n;
-    P.n_grp = 9; P.nk = 4; P.n_mma = 36;
-    P.tab_per_stage = 0;      // the 9 tap offsets are the same for every K stage
+    P.n_grp = ntap; P.nk = 4; P.n_mma = 4 * ntap;
+    P.tab_per_stage = 0;      // the tap offsets are the same for every K stage
     P.b_stream = 1;
     // CTA pairs: every CTA streams half of each weight block's rows (the MMA reads N/2 rows from either SM), which
     // takes the N = 128 layers off the shared-memory read limit ((128 + 128) rows per K step = exactly 128 B/clk,
@@ -909,8 +949,8 @@ static int make_plan(const tedspad_conv_slab& c, tedspad_slab_plan& P) {
     if (tm == 0) tm = (x.W > 8 && 4 * P.n_tile <= 512) ? 2 : 1;
     TSP_CHECK((tm == 1 || tm == 2) && 2 * tm * P.n_tile <= 512, "slab stream: tm=%d with n_tile=%d exceeds TMEM", tm, P.n_tile);
     P.tm = tm;
-    slab_w = 8 * tm + 2;
-    slab_h = 18;
+    slab_w = 8 * tm + 2 * hw;
+    slab_h = 16 + 2 * hw;
     P.box[0] = 64; P.box[1] = slab_w; P.box[2] = slab_h; P.box[3] = 1; P.box[4] = 1;
     P.tdim[0] = x.C; P.tdim[1] = Wp; P.tdim[2] = Hp; P.tdim[3] = Dp; P.tdim[4] = x.N;
     P.tstride[0] = static_cast<int64_t>(x.ld) * 2;
@@ -920,8 +960,8 @@ static int make_plan(const tedspad_conv_slab& c, tedspad_slab_plan& P) {
     P.tbase_off = static_cast<int64_t>(x.coff) * 2;
     // no halo needed: taps outside the tensor are zero-filled by TMA (a zero halo works just as well)
     P.c_step = 64;
-    P.x_step = 8 * tm; P.x_off = x.pw - 1;
-    P.y_step = 16; P.y_off = x.ph - 1;
+    P.x_step = 8 * tm; P.x_off = x.pw - hw;
+    P.y_step = 16; P.y_off = x.ph - hw;
     P.z_step = 1; P.z_off = x.pd - c.kd / 2; P.z_kstep = 1;
     P.tiles_x = (x.W + 8 * tm - 1) / (8 * tm);
     P.tiles_y = (x.H + 15) / 16;
@@ -930,8 +970,8 @@ static int make_plan(const tedspad_conv_slab& c, tedspad_slab_plan& P) {
     P.a_layout = 2; P.a_lbo = 16; P.a_sbo = slab_w * 128;
     P.b_layout = 2; P.b_lbo = 16; P.b_sbo = 1024;
     P.a_kstep = 32; P.b_kstep = 32;
-    for (int tap = 0; tap < 9; ++tap) {
-      P.tab[2 * tap] = static_cast<uint32_t>(((tap / 3) * slab_w + (tap % 3)) * 128);
+    for (int tap = 0; tap < ntap; ++tap) {
+      P.tab[2 * tap] = static_cast<uint32_t>(((tap / c.kw) * slab_w + (tap % c.kw)) * 128);
       P.tab[2 * tap + 1] = 0;
     }
   } else if (c.kind == TEDSPAD_SLAB_STEM3D) {
@@ -1004,23 +1044,26 @@ static int make_plan(const tedspad_conv_slab& c, tedspad_slab_plan& P) {
     P.tiles_y = (Hp * x.N - 2 * x.ph + 15) / 16;
     batch = 1;
   }
+  // the bias of every N tile lives in shared memory: 512 floats by default, more for the 1024 / 2048-output convolutions
+  const int bias_floats = std::max(512, c.Cout_pad);
+  const int tail_bytes = SLAB_TAIL_BYTES + (bias_floats - 512) * 4;
   P.slab_bytes = 2 * P.box[0] * P.box[1] * P.box[2] * P.box[3] * P.box[4];
   P.slab_stride = static_cast<int>(round_up(P.slab_bytes + pad_bytes, 1024));
   int w_stride = static_cast<int>(round_up(P.w_bytes, 1024));
   if (P.b_stream) {
     // two (tm=2) or three slab stages; the rest of shared memory is the weight-block ring
     P.stages = (P.tm == 2 && !pair) ? 2 : 3;   // (a pair's half-size weight blocks leave room for a third 16x16 slab)
-    const int avail_b = SLAB_SMEM_BUDGET - 1024 - SLAB_TAIL_BYTES - P.stages * P.slab_stride;
+    const int avail_b = SLAB_SMEM_BUDGET - 1024 - tail_bytes - P.stages * P.slab_stride;
     P.b_stages = std::min(SLAB_MAX_BSTAGES, avail_b / P.b_stride);
     TSP_CHECK(P.b_stages >= 3, "slab stream: only %d weight-block stages fit", P.b_stages);
     w_stride = P.b_stages * P.b_stride;
   } else {
-    const int avail = SLAB_SMEM_BUDGET - 1024 - SLAB_TAIL_BYTES - w_stride;
+    const int avail = SLAB_SMEM_BUDGET - 1024 - tail_bytes - w_stride;
     P.stages = std::min(SLAB_MAX_STAGES, avail / P.slab_stride);
     TSP_CHECK(P.stages >= 2, "slab: weights (%d B) + two slab stages (%d B each) do not fit in shared memory", P.w_bytes,
               P.slab_stride);
   }
-  P.smem_bytes = 1024 + w_stride + P.stages * P.slab_stride + SLAB_TAIL_BYTES;
+  P.smem_bytes = 1024 + w_stride + P.stages * P.slab_stride + tail_bytes;
   int tc = 32;
   // accumulator ring: the epilogue of tile i overlaps the MMAs of tiles i+1 .. i+acc-1.  Two stages are enough when
   // a tile holds several K stages; with ONE K stage per tile (64 -> 64) the hand-back round trip (commit -> epilogue
@@ -1120,6 +1163,7 @@ extern "C" int tedspad_conv_slab_forward(const tedspad_conv_slab* c, void* strea
   p.tm = P.tm; p.n_tile = P.n_tile; p.k_stages = P.k_stages; p.n_grp = P.n_grp; p.nk = P.nk; p.stages = P.stages;
   p.a_kstep = P.a_kstep; p.b_kstep = P.b_kstep;
   p.tmem_cols = P.tmem_cols; p.acc_stages = P.acc_stages;
+  p.bias_floats = std::max(512, (int)c->Cout_pad);
   p.slab_bytes = P.slab_bytes; p.slab_stride = P.slab_stride; p.w_bytes = P.w_bytes;
   p.w_stride = P.b_stream ? P.b_stages * P.b_stride : (int)round_up(P.w_bytes, 1024);
   p.zero_slabs = P.swizzle128 ? 0 : 1;
@@ -1140,6 +1184,13 @@ extern "C" int tedspad_conv_slab_forward(const tedspad_conv_slab* c, void* strea
   p.yDp = y.D + 2 * y.pd; p.yHp = y.H + 2 * y.ph; p.yWp = y.W + 2 * y.pw;
   p.ypd = y.pd; p.yph = y.ph; p.ypw = y.pw; p.y_ld = y.ld; p.y_coff = y.coff;
   p.Cout = c->Cout; p.act = c->act;
+  if (c->res != nullptr) {
+    TSP_CHECK(c->pool.ptr == nullptr && !fused_oc && !(c->up.ptr != nullptr) && (c->res_ld | c->res_coff) % 8 == 0 &&
+                  (reinterpret_cast<uintptr_t>(c->res) & 15) == 0,
+              "slab: a residual excludes the fused pool / OutConv / up-sampling and must be 16-byte aligned per pixel chunk");
+    p.res = reinterpret_cast<const __nv_bfloat16*>(c->res);
+    p.res_ld = c->res_ld; p.res_coff = c->res_coff;
+  }
   if (c->pool.ptr != nullptr) {
     const tedspad_tensor& q = c->pool;
     if (check_tensor(q, "slab.pool", 8)) return 1;

@@ -307,6 +307,13 @@ __device__ __forceinline__ uint32_t cvt_bf16x2(float lo, float hi, bool relu) {
   else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
   return d;
 }
+// 16-byte read-only load that stays where it is written (volatile: the compiler may not sink it to its first use,
+// which would turn a prefetch back into a dependent load)
+__device__ __forceinline__ uint4 ld_nc_v4_pinned(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
 // 32-byte store (address 32-byte aligned): half as many store instructions / L1 wavefronts per byte as v4
 __device__ __forceinline__ void st_global_256(void* p, const uint32_t* q) {
   asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"

@@ -18,6 +18,10 @@ from .ops import CLTensor, PackedConv
 # GATHER feeds of csrc/conv_igemm.cu (kept for A/B measurements and as the general-shape path).
 USE_SLAB = os.environ.get("TEDSPAD_SLAB", "1") != "0"
 USE_PAIR = os.environ.get("TEDSPAD_PAIR", "1") != "0"     # cta_group::2 for the 64-output-channel 3x3 layers
+# 1x1x1 / (3,1,1) stride-1 convolutions (ResNet bottleneck conv1 / conv3, Inception pool branch, Conv3d_2b) through the
+# streaming SLAB kind (one tap per K stage) instead of the general kernel, whose 4-warp 16-column epilogue runs a
+# 128 x 256 tile in ~27k clocks (ncu: I3Res50.layer1 conv3 + residual at 37 TFLOP/s)
+SLAB_1X1 = USE_SLAB and os.environ.get("TEDSPAD_SLAB_1X1", "1") != "0"
 PAD_SMALL_3X3 = USE_SLAB and os.environ.get("TEDSPAD_PAD_SMALL_3X3", "1") != "0"
 MERGE_1X1 = os.environ.get("TEDSPAD_MERGE_1X1", "1") != "0"  # Inception b0/b1a/b2a (same input) as one GEMM
 USE_STREAM_PAIR = USE_PAIR and os.environ.get("TEDSPAD_STREAM_PAIR", "1") != "0"
@@ -32,16 +36,19 @@ ENC_IN_CHANNELS = 4 if USE_SLAB_STEM3D else 8   # channel padding of the encoder
 FUSE_UPSAMPLE_LEVELS = tuple(int(v) for v in os.environ.get("TEDSPAD_FUSE_UPSAMPLE", "").split(",") if v) if USE_SLAB else ()
 
 
-def slab3x3(pc, max_stream_cout=512):
-    """Best SLAB variant for a stride-1 same-padded (1|3,3,3) convolution with Cin % 64 == 0, or None:
+def slab3x3(pc, max_stream_cout=2048):
+    """Best SLAB variant for a stride-1 same-padded (1|3) x (3x3 | 1x1) convolution with Cin % 64 == 0, or None:
     resident weights when they fit in shared memory (the 64-channel DoubleConv layers), streamed weight blocks
     otherwise (128-channel DoubleConv layers, Conv3d_2c_3x3, Inception 3x3x3 branches, ResNet (1,3,3)/3x3x3)."""
-    kd = pc.k[0]
-    if not USE_SLAB or kd not in (1, 3) or pc.k[1:] != (3, 3) or pc.stride != (1, 1, 1) or pc.pad_front != (kd // 2, 1, 1):
+    kd, sp = pc.k[0], pc.k[1:]
+    if not USE_SLAB or kd not in (1, 3) or sp not in ((3, 3), (1, 1)) or pc.stride != (1, 1, 1) or \
+            pc.pad_front != (kd // 2, sp[0] // 2, sp[1] // 2):
         return None
-    if pc.cin_pad % 64 or pc.cout % 8 or pc.cout_pad % 32 or pc.k_pad != kd * 9 * pc.cin_pad:
+    if sp == (1, 1) and not SLAB_1X1:
         return None
-    if kd == 1 and pc.cout_pad <= 256 and 9 * pc.cin_pad * pc.cout_pad * 2 <= SLAB_WEIGHT_LIMIT:
+    if pc.cin_pad % 64 or pc.cout % 8 or pc.cout_pad % 32 or pc.k_pad != kd * sp[0] * sp[1] * pc.cin_pad:
+        return None
+    if kd == 1 and sp == (3, 3) and pc.cout_pad <= 256 and 9 * pc.cin_pad * pc.cout_pad * 2 <= SLAB_WEIGHT_LIMIT:
         # N = 64 is shared-memory-read bound on one SM (67 % of the tensor peak): CTA pairs split the weight rows.
         # At N = 128 the halved weight image makes room for 16x16 tiles (measured +7 %).
         return ops.PackedSlabConv(pc, L.SLAB_3X3_PAIR if (USE_PAIR and pc.cout_pad in (64, 128)) else L.SLAB_3X3)
@@ -55,10 +62,11 @@ def slab3x3(pc, max_stream_cout=512):
 
 
 def conv_auto(x, pc, y, res=None, act=L.ACT_RELU):
-    """Convolution through the SLAB feed when the layer has one (pc.slab) and needs no residual, else FLAT/GATHER."""
+    """Convolution through the SLAB feed when the layer has one (pc.slab; bf16 residual added in its epilogue), else
+    FLAT/GATHER."""
     ps = getattr(pc, "slab", None)
-    if ps is not None and res is None and act in (L.ACT_RELU, L.ACT_NONE):
-        return ops.conv_slab_forward(x, ps, y, act=act)
+    if ps is not None and act in (L.ACT_RELU, L.ACT_NONE):
+        return ops.conv_slab_forward(x, ps, y, act=act, res=res)
     return ops.conv_forward(x, pc, y, res=res, act=act)
 
 
@@ -277,8 +285,9 @@ class I3DExecutor:
         key = (name, pf)
         pc = self.packed.get(key)
         if pc is None:
+            heads = name.rsplit(".", 1)[-1] in ("b0", "b1a", "b2a") and MERGE_1X1   # merged: general kernel
             pc = PackedConv(w, None, bn, stride=s, pad_front=pf, cin_pad=cin_pad, device=self.device,
-                            n_align=32 if k == (3, 3, 3) else 16)
+                            n_align=16 if (k == (1, 1, 1) and (heads or w.shape[0] % 8)) else 32)
             self.packed[key] = pc
             if cin_pad == 8:
                 self.packed[key + ("slab",)] = stem3d(pc)

@@ -224,8 +224,8 @@ class PackedSlabConv:
         self.fallback = None
         if kind in (L.SLAB_3X3_STREAM, L.SLAB_3X3_STREAM_PAIR):
             # weights stream from the standard packed layout: nothing to re-pack
-            if pc.cout_pad % 32 or pc.cout_pad > 512 or pc.cout % 8 or self.n_tile % 32 or pc.cout_pad % self.n_tile:
-                raise ValueError(f"slab stream feed needs Cout_pad % 32 == 0 (<= 512), got {pc.cout_pad} / n_tile {pc.n_tile}")
+            if pc.cout_pad % 32 or pc.cout_pad > 2048 or pc.cout % 8 or self.n_tile % 32 or pc.cout_pad % self.n_tile:
+                raise ValueError(f"slab stream feed needs Cout_pad % 32 == 0 (<= 2048), got {pc.cout_pad} / n_tile {pc.n_tile}")
             self.image, self.image_bytes = pc.w, pc.w.numel() * 2
             if kind == L.SLAB_3X3_STREAM_PAIR:
                 self.fallback = PackedSlabConv(pc, L.SLAB_3X3_STREAM, n_tile)
@@ -247,7 +247,7 @@ class PackedSlabConv:
             L.check(L.lib().tedspad_conv_slab_pack(*args, self.image.data_ptr(), C.byref(nbytes), _stream()),
                     "tedspad_conv_slab_pack")
 
-    def desc(self, x, y, act=L.ACT_RELU, pool=None, outconv=None, tm=0, max_ctas=0, up=None, stack_rows=0):
+    def desc(self, x, y, act=L.ACT_RELU, pool=None, outconv=None, tm=0, max_ctas=0, up=None, stack_rows=0, res=None):
         """outconv = (w fp32 [3,Cout], b fp32 [3], planes bf16 [N,3,H,W] | None, frames fp32 [N,3,H,W] | None
         [, clip CLTensor [B,T,H,W,>=3], T]): with `clip` the sigmoid images go straight into the encoder input
         through the raw-reshape glue"""
@@ -264,6 +264,9 @@ class PackedSlabConv:
             d.pool = pool.desc()
         if up is not None:
             d.up = up.desc()
+        if res is not None:
+            assert (res.N, res.D, res.H, res.W, res.halo, res.C) == (y.N, y.D, y.H, y.W, y.halo, y.C)
+            d.res, d.res_ld, d.res_coff = res.buf.data_ptr(), res.ld, res.coff
         if outconv is not None:
             w, b, planes, frames = outconv[:4]
             d.oc_w, d.oc_b = w.data_ptr(), b.data_ptr()
@@ -286,8 +289,9 @@ class PackedSlabConv:
                                              (x.N * x.D * (x.H // 16) * (-(-x.W // 16))) % 2):
             return self.fallback
         if self.kind == L.SLAB_3X3_STREAM_PAIR:
-            # the plan knows (stacked rows, tile shape): an odd tile count cannot be split over CTA pairs
-            if up is not None:
+            # the plan knows (stacked rows, tile shape): an odd tile count cannot be split over CTA pairs; 3-D tensors
+            # (few tiles per launch) were measured 0-5 % slower on pairs
+            if up is not None or x.D > 1:
                 return self.fallback
             y = CLTensor.__new__(CLTensor)
             y.__dict__.update(x.__dict__)
@@ -305,11 +309,11 @@ class PackedSlabConv:
         return plan
 
 
-def conv_slab_forward(x, psc, y, act=L.ACT_RELU, pool=None, outconv=None, tm=0, max_ctas=0, up=None, stack_rows=0):
+def conv_slab_forward(x, psc, y, act=L.ACT_RELU, pool=None, outconv=None, tm=0, max_ctas=0, up=None, stack_rows=0, res=None):
     """y = act(conv(x) + bias) through the SLAB feed; optional fused MaxPool2d(2) -> pool, OutConv 1x1 + sigmoid
     -> planar images (y may then be None), and fused Up.forward input: conv([x | upsample2x(up)])."""
     psc = psc.resolve(x, tm, up, stack_rows)
-    d = psc.desc(x, y, act=act, pool=pool, outconv=outconv, tm=tm, max_ctas=max_ctas, up=up, stack_rows=stack_rows)
+    d = psc.desc(x, y, act=act, pool=pool, outconv=outconv, tm=tm, max_ctas=max_ctas, up=up, stack_rows=stack_rows, res=res)
     _count()
     if CONV_EVENTS is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

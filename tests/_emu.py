@@ -105,7 +105,7 @@ def _gather_acc(x, pc, out_shape):
     return acc.reshape(N, OD, OH, OW, pc.cout)
 
 
-def conv_slab_forward(x, psc, y, act=L.ACT_RELU, pool=None, outconv=None, tm=0, max_ctas=0, up=None):
+def conv_slab_forward(x, psc, y, act=L.ACT_RELU, pool=None, outconv=None, tm=0, max_ctas=0, up=None, stack_rows=0, res=None):
     """SLAB feed (csrc/conv_slab.cu): same arithmetic as the gather restatement; the fused MaxPool2d(2) pools the
     ROUNDED output (as the kernel does), the fused OutConv consumes the un-rounded fp32 activations; with `up` the
     convolution input is [x | upsample2x(up)] (the up-sampled half rounded to the storage dtype, as the kernel does)."""
@@ -117,7 +117,10 @@ def conv_slab_forward(x, psc, y, act=L.ACT_RELU, pool=None, outconv=None, tm=0, 
         upsample2x(up, cat.slice(x.C, up.C))
         x = cat
     shape = (y.N, y.D, y.H, y.W) if y is not None else (x.N, x.D, x.H, x.W)
-    acc = _act(_gather_acc(x, pc, shape), act)
+    acc = _gather_acc(x, pc, shape)
+    if res is not None:
+        acc = acc + res.interior().float()
+    acc = _act(acc, act)
     store_dtype = y.buf.dtype if y is not None else (pool.buf.dtype if pool is not None else torch.float32)
     if y is not None:
         y.interior()[...] = acc.to(y.buf.dtype)

@@ -422,7 +422,7 @@ def group_perf():
 # ------------------------------------------------------------------------------------------ SLAB feed
 def run_slab_case(name, kind, N, dhw, cin_real, cin_buf, cout, k, stride=(1, 1, 1), pad_f=(0, 1, 1), pad_b=None, halo=(0, 0, 0),
                   tm=0, in_ld=None, in_coff=0, out_ld=None, out_coff=0, out_halo=None, pool=False, outconv=False,
-                  max_ctas=0, seed=0):
+                  max_ctas=0, seed=0, res=False):
     import numpy as np
     import _slabsim as S
     try:
@@ -472,12 +472,19 @@ def run_slab_case(name, kind, N, dhw, cin_real, cin_buf, cout, k, stride=(1, 1, 
             clip = ops.CLTensor(N // Tc, Tc, oh, ow, 4, device=DEV)
             clip.buf.fill_(9.0)
             oc = (ocw, ocb, planes, frames, clip, Tc)
-        ops.conv_slab_forward(xv, psc, yv, pool=pv, outconv=oc, tm=tm, max_ctas=max_ctas)
+        rv, rres = None, None
+        if res:   # bf16 residual living in a channel slice of a wider buffer (Bottleneck tail: relu(conv + bias + res))
+            rres = torch.randn(N, cout, od, oh, ow, generator=g).to(DEV)
+            rb = ops.CLTensor(N, od, oh, ow, cout + 16, out_halo, device=DEV)
+            rb.buf.fill_(5.0)
+            rv = rb.slice(8, cout)
+            rv.interior()[...] = rres.permute(0, 2, 3, 4, 1).to(torch.bfloat16)
+        ops.conv_slab_forward(xv, psc, yv, pool=pv, outconv=oc, tm=tm, max_ctas=max_ctas, res=rv)
         torch.cuda.synchronize()
         kd, kh, kw = k
         wq = pc.w[:cout, :kd * kh * kw * pc.cin_pad].float().reshape(cout, kd, kh, kw, pc.cin_pad)[..., :cin_real].permute(0, 4, 1, 2, 3)
         pad6 = (pad_f[2], pad_b[2], pad_f[1], pad_b[1], pad_f[0], pad_b[0])
-        ref = conv_ref(bf(x), wq.contiguous(), pc.bias[:cout], stride, pad6, None, "relu")
+        ref = conv_ref(bf(x), wq.contiguous(), pc.bias[:cout], stride, pad6, bf(rres) if res else None, "relu")
         plan = psc.plan(xv, yv, tm=tm)
         ok = report(name, yv.to_ncdhw(), ref, extra=f"tm={plan.tm} stages={plan.stages} b_stages={plan.b_stages} k_stages={plan.k_stages} "
                     f"n_tile={plan.n_tile}x{plan.num_n_tiles} tiles={plan.total_tiles} smem={plan.smem_bytes}")
@@ -548,6 +555,22 @@ def group_slabpair():
     run_slab_case("P7 64->64 odd 19x21 x2 pair", K, 2, (1, 19, 21), 64, 64, 64, (1, 3, 3), halo=(0, 1, 1))
     run_slab_case("P8 64->64 odd tile count -> single-CTA fallback", K, 1, (1, 16, 48), 64, 64, 64, (1, 3, 3), halo=(0, 1, 1))
     run_slab_case("P9 64->128 28x28 pair (N=128)", K, 2, (1, 28, 28), 64, 64, 128, (1, 3, 3), halo=(0, 1, 1))
+
+
+def group_slab1x1():
+    """One spatial tap per K stage (1x1x1 and (3,1,1)) and the residual epilogue of the streaming kind."""
+    K = L.SLAB_3X3_STREAM
+    run_slab_case("T1 1x1x1 64->64 Conv3d_2b shape", K, 2, (4, 28, 28), 64, 64, 64, (1, 1, 1), pad_f=(0, 0, 0))
+    run_slab_case("T2 1x1x1 256->64 bottleneck conv1 odd 55x55", K, 2, (2, 55, 55), 256, 256, 64, (1, 1, 1), pad_f=(0, 0, 0))
+    run_slab_case("T3 (3,1,1) 256->64 temporal conv1", K, 2, (4, 23, 23), 256, 256, 64, (3, 1, 1), pad_f=(1, 0, 0))
+    run_slab_case("T4 1x1x1 64->256 conv3 + residual", K, 2, (2, 55, 55), 64, 64, 256, (1, 1, 1), pad_f=(0, 0, 0), res=True)
+    run_slab_case("T5 1x1x1 512->2048 conv3 + residual (8 N tiles)", K, 2, (2, 7, 7), 512, 512, 2048, (1, 1, 1), pad_f=(0, 0, 0), res=True)
+    run_slab_case("T6 1x1x1 192->32 pool branch, slice out", K, 2, (4, 14, 14), 192, 192, 32, (1, 1, 1), pad_f=(0, 0, 0),
+                  out_ld=256, out_coff=224)
+    run_slab_case("T7 3x3x3 64->64 + residual (R3D BasicBlock conv2)", K, 2, (4, 28, 28), 64, 64, 64, (3, 3, 3), pad_f=(1, 1, 1), res=True)
+    run_slab_case("T8 2-D 1x1 128->128 haloed (stacked rows)", K, 3, (1, 20, 24), 128, 128, 128, (1, 1, 1), pad_f=(0, 0, 0),
+                  halo=(0, 1, 1))
+    run_slab_case("T9 1x1x1 832->128 7x7", K, 4, (2, 7, 7), 832, 832, 128, (1, 1, 1), pad_f=(0, 0, 0))
 
 
 def group_streampair():

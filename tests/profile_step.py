@@ -14,8 +14,13 @@ from tedspad_b200 import ops  # noqa: E402
 from tedspad_b200.extraction import SnippetExtractor, crop_boxes  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+ARCH = sys.argv[2] if len(sys.argv) > 2 else "i3d"
 dev = torch.device("cuda", 0)
 fa, ft = bench.build_models(dev)
+if ARCH != "i3d":   # e.g. largei3d (the encoder the reference scripts configure) or r3d_18
+    from aux_code.model_loaders import load_ft_model
+    torch.manual_seed(0)
+    ft = load_ft_model(arch=ARCH, num_classes=102).to(dev).eval()
 ext = SnippetExtractor(fa, ft, reso=bench.RESO, batch_clips=B)
 (ch, cw), boxes = crop_boxes(*bench.SRC_HW)
 desc = np.zeros((B * 16, 4), dtype=np.int32)

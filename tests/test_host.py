@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
         assert getattr(lib, name) is not None
     assert lib.tedspad_abi_version() == L.ABI_VERSION
     assert ctypes.sizeof(L.TensorDesc) == 48 and ctypes.sizeof(L.ConvDesc) == 48 * 2 + 24 + 19 * 4 + 4 + 2 * 48 + 8
-    assert ctypes.sizeof(L.ConvSlabDesc) == 368 and ctypes.sizeof(L.SlabPlan) == 1168
+    assert ctypes.sizeof(L.ConvSlabDesc) == 384 and ctypes.sizeof(L.SlabPlan) == 1168
 
 
 def test_library_has_blackwell_sass():

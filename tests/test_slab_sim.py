@@ -74,17 +74,23 @@ def test_slab_3x3_plan_reproduces_conv(cin, cout, tm, ld, coff):
     ("i3d Conv3d_2c 64->192 3x3x3 no halo", (4, 20, 12), 64, 192, 3, (0, 0, 0), 0),
     ("i3d 5c.b1b 192->384 (two N tiles)", (2, 7, 7), 192, 384, 3, (0, 0, 0), 0),
     ("i3d 4b.b1b 128(96)->208 padded", (3, 14, 14), 128, 208, 3, (0, 0, 0), 0),
+    ("1x1x1 bottleneck conv1 256->64 odd", (2, 13, 11), 256, 64, -1, (0, 0, 0), 0),
+    ("(3,1,1) temporal conv1 128->64", (4, 9, 12), 128, 64, -3, (0, 0, 0), 0),
+    ("2-D 1x1 128->128 haloed (stacked rows)", (1, 20, 24), 128, 128, -1, (0, 1, 1), 0),
 ])
 def test_slab_stream_plan_reproduces_conv(name, dhw, cin, cout, kd, halo, tm):
     g = torch.Generator().manual_seed(cin + cout + kd)
     N = 2
     D, H, W = dhw
     x = torch.randn(N, cin, D, H, W, generator=g)
-    w = torch.randn(cout, cin, kd, 3, 3, generator=g) / (9 * kd * cin) ** 0.5
+    ks = 3
+    if kd < 0:   # negative kd: |kd| temporal taps with a 1x1 spatial window (one tap per K stage)
+        kd, ks = -kd, 1
+    w = torch.randn(cout, cin, kd, ks, ks, generator=g) / (ks * ks * kd * cin) ** 0.5
     xc = ops.CLTensor(N, D, H, W, cin, halo, device="cpu")
     xc.buf.zero_()
     xc.interior()[...] = x.permute(0, 2, 3, 4, 1).to(torch.bfloat16)
-    pad = (kd // 2, 1, 1)
+    pad = (kd // 2, ks // 2, ks // 2)
     tiles = None if D * H * W < 2000 else list(range(0, 10 ** 6, 7))[:24]
     err, seen, plan = _run(L.SLAB_3X3_STREAM, xc, x, w, (1, 1, 1), pad, pad, (N, D, H, W), tm, tiles=tiles, cin_pad=cin)
     assert plan.b_stream == 1 and plan.k_stages == kd * (cin // 64) and plan.b_stages >= 3
