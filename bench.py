@@ -173,6 +173,8 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
+        # NCCL prints its version banner on stdout when NCCL_DEBUG is set in the environment: keep stdout = ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=device)
 
     from tedspad_b200 import ops
