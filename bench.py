@@ -171,10 +171,13 @@ def main():
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     dist = None
+    # stdout carries exactly ONE JSON line: whatever libraries print while the job runs (NCCL writes its version banner
+    # to file descriptor 1 when the first communicator is created) goes to stderr; fd 1 is restored for the final print
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         import torch.distributed as dist
-        # NCCL prints its version banner on stdout when NCCL_DEBUG is set in the environment: keep stdout = ONE JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=device)
 
     from tedspad_b200 import ops
@@ -283,6 +286,9 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cps, threads, sample = cpu_reference_clips_per_s(n_timed=8)
         line["cpu_baseline"] = {"value": cps, "unit": "clips/s", "cores": threads, "kind": "port", "sample": sample}
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    os.close(saved_stdout)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if dist is not None:
