@@ -573,6 +573,41 @@ def group_slab1x1():
     run_slab_case("T9 1x1x1 832->128 7x7", K, 4, (2, 7, 7), 832, 832, 128, (1, 1, 1), pad_f=(0, 0, 0))
 
 
+def group_fuzz():
+    """Seeded random shapes through the engine's own kind selection (resident / pair / stream / stream-pair, stacked
+    rows, odd extents, slices, fused pool, residual) against torch."""
+    import random
+    from tedspad_b200 import engine
+    rnd = random.Random(1234)
+    for i in range(48):
+        threeD = rnd.random() < 0.35
+        sp = rnd.choice([(3, 3), (3, 3), (1, 1)])
+        kd = rnd.choice([1, 3]) if threeD else 1
+        k = (kd, sp[0], sp[1])
+        cin = rnd.choice([64, 64, 128, 192, 256])
+        cout = rnd.choice([32, 64, 64, 96, 128, 160, 256, 320, 512])
+        N = rnd.randint(1, 5)
+        D = rnd.randint(2, 5) if threeD else 1
+        H, W = rnd.randint(5, 61), rnd.randint(5, 61)
+        halo = (0, 1, 1) if (not threeD and rnd.random() < 0.6) else (0, 0, 0)
+        res = rnd.random() < 0.25
+        pool = (not res) and (not threeD) and sp == (3, 3) and H % 2 == 0 and W % 2 == 0 and rnd.random() < 0.4
+        pad = (kd // 2, sp[0] // 2, sp[1] // 2)
+        # pick the kind the executors would pick for this layer
+        g = torch.Generator(device="cpu").manual_seed(i)
+        wtmp = torch.zeros(cout, cin, *k)
+        pc = ops.PackedConv(wtmp, None, None, pad_front=pad, cin_pad=cin, device=DEV, n_align=32)
+        ps = engine.slab3x3(pc)
+        if ps is None:
+            print(f"[SKIP] fuzz {i}: no slab kind for k={k} {cin}->{cout}")
+            continue
+        slice_out = rnd.random() < 0.3
+        run_slab_case(f"Z{i} k={k} {cin}->{cout} N={N} D={D} {H}x{W} halo={halo[1]} kind={ps.kind}"
+                      f"{' +pool' if pool else ''}{' +res' if res else ''}{' slice' if slice_out else ''}",
+                      ps.kind, N, (D, H, W), cin, cin, cout, k, pad_f=pad, halo=halo, pool=pool, res=res, seed=100 + i,
+                      out_ld=(cout + 32) if slice_out else None, out_coff=16 if slice_out else 0)
+
+
 def group_streampair():
     """Streaming kind on CTA pairs: every CTA streams half of each weight block's rows."""
     K = L.SLAB_3X3_STREAM_PAIR

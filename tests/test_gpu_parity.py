@@ -35,7 +35,7 @@ def _modules(name, stress=False):
     return fa.cuda().eval(), ft.cuda().eval()
 
 
-@pytest.mark.parametrize("group", ["flat", "gather", "multi", "ops", "prep", "slabpair", "streampair", "slab1x1"])
+@pytest.mark.parametrize("group", ["flat", "gather", "multi", "ops", "prep", "slabpair", "streampair", "slab1x1", "fuzz"])
 def test_operator_battery(group):
     """tests/gpu_diag.py: each operator vs torch fp32 on bf16-rounded operands (conv tolerance 2e-2 of the
     output range, i.e. bf16 output rounding; pooling / layout / PIL preprocessing bit-exact)."""
