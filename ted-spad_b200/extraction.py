@@ -122,21 +122,25 @@ class SnippetExtractor:
         """Host frames -> one of two persistent device staging buffers, on the copy stream.  Returns the device view
         and the event that marks its arrival.  (Fresh allocations per batch made the caching allocator cudaMalloc -
         a device-wide synchronisation - whenever the previous batch's block was still in use.)"""
-        if frames.is_cuda:
-            return frames.contiguous(), None
+        chunks = list(frames) if isinstance(frames, (list, tuple)) else [frames]
+        if all(c.is_cuda for c in chunks):
+            return (chunks[0] if len(chunks) == 1 else torch.cat(chunks, 0)).contiguous(), None
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
-        frames = frames.contiguous()
-        n = frames.numel()
+        chunks = [c.contiguous() for c in chunks]
+        n = sum(c.numel() for c in chunks)
         buf = self._stage_bufs[slot]
         if buf is None or buf.numel() < n:
             buf = torch.empty(max(n, 1), dtype=torch.uint8, device=self.device)
             self._stage_bufs[slot] = buf
-        dev = buf[:n].view(frames.shape)
+        dev = buf[:n].view((sum(c.shape[0] for c in chunks),) + tuple(chunks[0].shape[1:]))
         with torch.cuda.stream(self._copy_stream):
             if self._stage_free[slot] is not None:
                 self._copy_stream.wait_event(self._stage_free[slot])   # the batch that used this buffer has been consumed
-            dev.copy_(frames, non_blocking=True)
+            f0 = 0
+            for c in chunks:   # frame ranges of one or several videos, back to back in the staging buffer
+                dev[f0:f0 + c.shape[0]].copy_(c, non_blocking=True)
+                f0 += c.shape[0]
             ev = torch.cuda.Event()
             ev.record(self._copy_stream)
         return dev, ev
@@ -165,6 +169,77 @@ class SnippetExtractor:
                 self._stage_free[i % 2] = done                      # buffer i % 2 may be overwritten after this point
             i += 1
             yield feats
+
+    def extract_videos(self, videos):
+        """videos: iterable of uint8 [F,H,W,3] tensors or of callables returning them.  Yields (index, features) in
+        input order, features as extract_video returns them.  Snippets are packed into full batches ACROSS videos
+        (frames of equal size share a batch): datasets of short videos - ShanghaiTech averages ~25 snippets per video -
+        would otherwise run one partial batch per video.  Every clip is computed independently of its batch
+        neighbours, so the rows are bit-identical to extract_video's (tests/test_gpu_parity.py)."""
+        import collections
+        per_batch = max(1, self.batch_clips // self.ncrops)   # snippets per batch
+        recs = collections.deque()      # videos in flight, in input order
+        metas = collections.deque()     # per issued batch: [(record, snippets taken), ...]
+
+        def batches():
+            chunks, descs, meta, count, base, hw, crop = [], [], [], 0, 0, None, None
+
+            def flush():
+                nonlocal chunks, descs, meta, count, base
+                out = (chunks, np.concatenate(descs, 0).reshape(-1, 4), crop)
+                metas.append(meta)
+                chunks, descs, meta, count, base = [], [], [], 0, 0
+                return out
+
+            for idx, v in enumerate(videos):
+                frames = v() if callable(v) else v
+                n_frames, H, W, _ = frames.shape
+                snips = self.snippet_frames(n_frames)
+                crop_hw, boxes = crop_boxes(H, W, self.ncrops, self.cf, self.no_ar, square_from_h=(self.source == "shanghai"))
+                rec = {"idx": idx, "left": snips.shape[0], "rows": []}
+                recs.append(rec)
+                if count and (H, W) != hw:
+                    yield flush()
+                hw, crop = (H, W), crop_hw
+                s0 = 0
+                while s0 < snips.shape[0]:
+                    take = min(per_batch - count, snips.shape[0] - s0)
+                    sn = snips[s0:s0 + take]
+                    valid = sn[sn >= 0]
+                    f_lo, f_hi = (int(valid.min()), int(valid.max()) + 1) if valid.size else (0, 1)
+                    desc = np.empty((take, len(boxes), self.T, 4), dtype=np.int32)
+                    desc[..., 0] = np.where(sn >= 0, sn - f_lo + base, -1)[:, None, :]
+                    for ci, (t, l, fl) in enumerate(boxes):
+                        desc[:, ci, :, 1], desc[:, ci, :, 2], desc[:, ci, :, 3] = t, l, fl
+                    chunks.append(frames[f_lo:f_hi])
+                    descs.append(desc.reshape(-1, 4))
+                    meta.append((rec, take))
+                    base += f_hi - f_lo
+                    count += take
+                    s0 += take
+                    if count == per_batch:
+                        yield flush()
+            if count:
+                yield flush()
+
+        def finished():
+            while recs and recs[0]["left"] == 0:
+                rec = recs.popleft()
+                if not rec["rows"]:
+                    yield rec["idx"], np.zeros((0, 0), dtype=np.float64)
+                    continue
+                allf = torch.cat(rec["rows"], 0).cpu().numpy().astype(np.float64)   # one D2H per video
+                yield rec["idx"], (allf[:, 0, :] if self.ncrops == 1 else allf)
+
+        for f in self.features_stream(batches()):
+            f = f.reshape(-1, self.ncrops, f.shape[-1] * f.shape[-2])
+            r0 = 0
+            for rec, take in metas.popleft():
+                rec["rows"].append(f[r0:r0 + take].clone())
+                rec["left"] -= take
+                r0 += take
+            yield from finished()
+        yield from finished()
 
     def extract_video(self, frames):
         """frames: uint8 [F,H,W,3] torch tensor (CPU, pinned CPU or CUDA), RGB for the DALI path, BGR
@@ -252,20 +327,29 @@ def extract_dataset(extractor, videos, save_folder, rank=0, world_size=1, log=pr
     Each file is written by exactly one rank (atomic rename); there is no collective."""
     os.makedirs(save_folder, exist_ok=True)
     mine = shard_videos([v[1] for v in videos], world_size)[rank]
+    todo = [i for i in mine if not os.path.exists(feature_path(save_folder, videos[i][0]))]
     written = []
-    for i in mine:
-        path, _, loader = videos[i]
-        out = feature_path(save_folder, path)
-        if os.path.exists(out):
-            continue
-        log(f'Extracting features for {os.path.basename(path)}.')
-        feats = extractor.extract_video(loader())
+
+    def save(i, feats):
+        out = feature_path(save_folder, videos[i][0])
         if segment:   # the reference's `segment` flag (False in both scripts: dali_extraction.py:181, st:100)
             feats = segment_features(feats, rule="shanghai" if getattr(extractor, "source", "dali") == "shanghai" else "dali")
         tmp = out + f".tmp{rank}.npy"
         np.save(tmp, feats)
         os.replace(tmp, out)
         written.append(out)
+
+    def load(i):
+        log(f'Extracting features for {os.path.basename(videos[i][0])}.')
+        return videos[i][2]()
+
+    if hasattr(extractor, "extract_videos"):
+        # snippets packed into full batches across this rank's videos (same rows, see SnippetExtractor.extract_videos)
+        for k, feats in extractor.extract_videos((lambda i=i: load(i)) for i in todo):
+            save(todo[k], feats)
+    else:
+        for i in todo:
+            save(i, extractor.extract_video(load(i)))
     return written
 
 

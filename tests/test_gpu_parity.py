@@ -296,3 +296,25 @@ def test_sharded_extraction_equals_single(tmp_path):
     assert len(w0) + len(w1) == 4 and not (set(w0) & set(w1))
     for i in range(4):
         assert np.array_equal(np.load(single / f"v{i}.npy"), np.load(sharded / f"v{i}.npy"))
+
+
+def test_packed_videos_equal_per_video():
+    """extract_videos packs snippets of several (short) videos into full batches, also across the copy-stream staging
+    buffers and around a change of frame size: rows must equal the per-video extract_video bit for bit, in order."""
+    from tedspad_b200.extraction import SnippetExtractor
+    name = "unet_r3d18_112"
+    fa, ft = _modules(name)
+    lens = [40, 96, 33, 0, 70, 150, 31]
+    vids = [_video(n, 120, 160, 30 + i) if n else torch.zeros((0, 120, 160, 3), dtype=torch.uint8) for i, n in enumerate(lens)]
+    vids.insert(3, _video(50, 100, 140, 77))            # a different frame size in the middle: forces a flush
+    ext = SnippetExtractor(fa, ft, reso=(112, 112), batch_clips=4)
+    packed = list(ext.extract_videos(v.pin_memory() if v.shape[0] else v for v in vids))
+    assert [i for i, _ in packed] == list(range(len(vids)))
+    for (i, got), v in zip(packed, vids):
+        want = ext.extract_video(v) if v.shape[0] else np.zeros((0, 0))
+        assert got.dtype == np.float64 and got.shape == want.shape, (i, got.shape, want.shape)
+        assert np.array_equal(got, want), i
+    ten = SnippetExtractor(fa, ft, reso=(112, 112), ncrops=10, batch_clips=20)
+    packed10 = dict(ten.extract_videos(vids[:3]))
+    for i in range(3):
+        assert np.array_equal(packed10[i], ten.extract_video(vids[i]))
