@@ -273,6 +273,11 @@ int tedspad_preprocess(const uint8_t* frames, int32_t F, int32_t Hs, int32_t Ws,
 int tedspad_nchw_to_cl(const float* x, int32_t Cx, const tedspad_tensor* y, void* stream);
 
 int tedspad_abi_version(void);
+/* Struct layout as THIS library was compiled: out[0..9] = sizeof(tedspad_tensor), sizeof(tedspad_conv),
+ * sizeof(tedspad_conv_slab), sizeof(tedspad_slab_plan), offsetof(tedspad_conv, y2), offsetof(tedspad_conv_slab, kind),
+ * offsetof(tedspad_conv_slab, res), offsetof(tedspad_conv_slab, oc_clip), offsetof(tedspad_conv_slab, stack_rows),
+ * offsetof(tedspad_slab_plan, tab).  A binding checks its own struct declarations against these (returns the count). */
+int tedspad_abi_layout(int32_t* out, int32_t n);
 int tedspad_num_sms(void);
 const char* tedspad_last_error(void);
 

@@ -72,6 +72,7 @@ SYMBOLS = {
     "tedspad_preprocess": (C.c_int, [_V, _I, _I, _I, _V, _I, _I, _I, _TP, _I, _V, _V]),
     "tedspad_nchw_to_cl": (C.c_int, [_V, _I, _TP, _V]),
     "tedspad_abi_version": (C.c_int, []),
+    "tedspad_abi_layout": (C.c_int, [C.POINTER(C.c_int32), C.c_int32]),
     "tedspad_num_sms": (C.c_int, []),
     "tedspad_last_error": (C.c_char_p, []),
 }

@@ -1,4 +1,5 @@
 // C-ABI plumbing: error text, tensor checks, SM count, TMA tensor-map encoding.
+#include <cstddef>
 #include <cstdlib>
 #include <cstdarg>
 #include <cstdio>
@@ -117,5 +118,15 @@ bool pdl_enabled() {
 }  // namespace tsp
 
 extern "C" int tedspad_abi_version(void) { return TEDSPAD_ABI_VERSION; }
+
+extern "C" int tedspad_abi_layout(int32_t* out, int32_t n) {
+  const int32_t v[10] = {(int32_t)sizeof(tedspad_tensor), (int32_t)sizeof(tedspad_conv), (int32_t)sizeof(tedspad_conv_slab),
+                         (int32_t)sizeof(tedspad_slab_plan), (int32_t)offsetof(tedspad_conv, y2),
+                         (int32_t)offsetof(tedspad_conv_slab, kind), (int32_t)offsetof(tedspad_conv_slab, res),
+                         (int32_t)offsetof(tedspad_conv_slab, oc_clip), (int32_t)offsetof(tedspad_conv_slab, stack_rows),
+                         (int32_t)offsetof(tedspad_slab_plan, tab)};
+  for (int i = 0; i < 10 && i < n; ++i) out[i] = v[i];
+  return 10;
+}
 extern "C" int tedspad_num_sms(void) { return tsp::num_sms(); }
 extern "C" const char* tedspad_last_error(void) { return tsp::g_err; }

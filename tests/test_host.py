@@ -30,6 +30,12 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert getattr(lib, name) is not None
     assert lib.tedspad_abi_version() == L.ABI_VERSION
+    lay = (ctypes.c_int32 * 10)()
+    assert lib.tedspad_abi_layout(lay, 10) == 10
+    assert list(lay) == [ctypes.sizeof(L.TensorDesc), ctypes.sizeof(L.ConvDesc), ctypes.sizeof(L.ConvSlabDesc),
+                         ctypes.sizeof(L.SlabPlan), L.ConvDesc.y2.offset, L.ConvSlabDesc.kind.offset,
+                         L.ConvSlabDesc.res.offset, L.ConvSlabDesc.oc_clip.offset, L.ConvSlabDesc.stack_rows.offset,
+                         L.SlabPlan.tab.offset], "the ctypes structs drifted from include/tedspad.h as compiled"
     assert ctypes.sizeof(L.TensorDesc) == 48 and ctypes.sizeof(L.ConvDesc) == 48 * 2 + 24 + 19 * 4 + 4 + 2 * 48 + 8
     assert ctypes.sizeof(L.ConvSlabDesc) == 384 and ctypes.sizeof(L.SlabPlan) == 1168
 
