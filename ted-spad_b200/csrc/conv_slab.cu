@@ -207,7 +207,7 @@ struct EpiCtx {
   __nv_bfloat16* y;
   __nv_bfloat16* pool;
   int Cout, act, y_ld, y_coff, p_ld, p_coff;
-  bool fuse_oc, wide_ok, pool_wide_ok;
+  bool fuse_oc, wide_ok;
   const __nv_bfloat16* res;   // EPI_RES: bf16 residual with y's pixel geometry
   int res_ld, res_coff;
 };
@@ -348,7 +348,6 @@ __device__ __forceinline__ void slab_epilogue(const SlabKParams& p, int warp, in
   c.y_ld = p.y_ld; c.y_coff = p.y_coff; c.p_ld = p.p_ld; c.p_coff = p.p_coff; c.fuse_oc = (MODE == EPI_OC || MODE == EPI_OC_ONLY);
   // 32-byte stores need 32-byte aligned pixel chunks
   c.wide_ok = ((p.y_ld | p.y_coff) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.y) & 31) == 0;
-  c.pool_wide_ok = false;
   c.res = p.res; c.res_ld = p.res_ld; c.res_coff = p.res_coff;
   int h, c_first, c_step, nch;
   if (tm == 2) { h = eg; c_first = 0; c_step = 32; nch = nchunk_all; }
