@@ -333,3 +333,50 @@ def test_segment_features_match_reference_statements():
         assert np.array_equal(np.isnan(got), np.isnan(want)) and np.array_equal(np.nan_to_num(got), np.nan_to_num(want)), n
     with pytest.raises(IndexError):
         extraction.segment_features(np.zeros((0, 16)))
+
+
+def test_extract_videos_packing_bookkeeping_on_cpu():
+    """The cross-video batch packer of SnippetExtractor.extract_videos (frame-range offsets inside the shared staging
+    buffer, per-batch metadata, completion order, empty videos, flush on a frame-size change) with the CUDA pipeline
+    replaced by a deterministic function of exactly the frames each clip references."""
+    class FakePipe(extraction.SnippetExtractor):
+        def __init__(self, ncrops, batch_clips, source="dali"):   # no modules, no device: only the driver logic
+            self.reso, self.T, self.skip = (8, 8), 16, 2
+            self.cf, self.no_ar, self.ncrops, self.source, self.batch_clips = 0.8, False, ncrops, source, batch_clips
+            self.batches_seen = []
+
+        def features_stream(self, batches):
+            for chunks, desc, crop_hw in batches:
+                frames = torch.cat([c for c in (chunks if isinstance(chunks, (list, tuple)) else [chunks])], 0).double()
+                self.batches_seen.append(desc.shape[0] // self.T)
+                d = desc.reshape(-1, self.T, 4)
+                rows = []
+                for clip in d:
+                    acc = [0.0, 0.0, 0.0]
+                    for t, (fi, top, left, flip) in enumerate(clip.tolist()):
+                        if fi >= 0:
+                            acc[0] += float(frames[fi].mean()) * (t + 1)
+                            acc[1] += float(frames[fi, top % frames.shape[1], left % frames.shape[2], 0]) + flip
+                    acc[2] = float(crop_hw[0] * 1000 + crop_hw[1])
+                    rows.append(acc)
+                yield torch.tensor(rows, dtype=torch.float32).reshape(len(rows), 1, 3)
+
+    rs = np.random.RandomState(0)
+    def vid(n, h, w):
+        return torch.from_numpy(rs.randint(0, 256, (n, h, w, 3)).astype(np.uint8))
+    vids = [vid(40, 20, 24), vid(130, 20, 24), vid(0, 20, 24), vid(33, 20, 24), vid(70, 16, 30), vid(95, 16, 30), vid(31, 20, 24)]
+    for ncrops, bc, source in ((1, 4, "dali"), (10, 20, "dali"), (5, 7, "dali"), (1, 3, "shanghai")):
+        ext = FakePipe(ncrops, bc, source)
+        packed = list(ext.extract_videos(iter(vids)))
+        assert [i for i, _ in packed] == list(range(len(vids)))
+        n_batches_packed = len(ext.batches_seen)
+        per_video = 0
+        for (i, got), v in zip(packed, vids):
+            if ext.snippet_frames(v.shape[0]).shape[0] == 0:
+                assert got.shape[0] == 0
+                continue
+            ext.batches_seen = []
+            want = ext.extract_video(v)
+            per_video += len(ext.batches_seen)
+            assert got.shape == want.shape and np.array_equal(got, want), (ncrops, bc, source, i)
+        assert n_batches_packed <= per_video      # packing never issues more batches than the per-video path
