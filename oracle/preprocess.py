@@ -87,6 +87,18 @@ def dali_val_augmentations(video_fhwc, reso=(224, 224), cropping_factor=0.8, no_
     return resize_aa(v, reso[0], reso[1])
 
 
+def dali_crop_augmentations(video_fhwc, box, crop_hw, reso=(224, 224)):
+    """val_augmentations with an explicit crop instead of the centre one: box = (top, left, hflip) in torchvision
+    five_crop / ten_crop terms (the crop is taken from the horizontally flipped frame when hflip), crop_hw = the
+    reference's crop size (dali_extraction.py:45-48).  box = the centre box reproduces dali_val_augmentations."""
+    v = np.asarray(video_fhwc, dtype=np.float32).transpose(0, 3, 1, 2) / np.float32(255.0)
+    top, left, hflip = box
+    if hflip:
+        v = v[..., ::-1]
+    v = v[..., top:top + crop_hw[0], left:left + crop_hw[1]]
+    return resize_aa(np.ascontiguousarray(v), reso[0], reso[1])
+
+
 # ----------------------------------------------------------------------------- Pillow 8-bit
 def pil_axis_coeffs(in_size, out_size):
     """Pillow precompute_coeffs (bilinear, support 1.0) + normalize_coeffs_8bpc -> [(xmin, int kk[])]."""

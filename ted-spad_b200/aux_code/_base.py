@@ -21,6 +21,14 @@ class CudaModule(nn.Module):
     executor_cls = None
     executor_kwargs = {}
 
+    def _replicate_for_data_parallel(self):
+        # nn.DataParallel (dali_extraction.py:126-141) broadcasts the parameters to per-device replicas whose
+        # parameters() are empty and calls forward from one thread per device.  The reference's own multi-GPU branch
+        # cannot run (its DataParallel-wrapped ft_model has no .extract_features / .i3d); this
+        # implementation scales as one process per GPU over a sharded video list instead.
+        raise RuntimeError(f"{type(self).__name__}: nn.DataParallel is not supported - run one process per GPU "
+                           "(torchrun) and shard the video list with tedspad_b200.extraction.extract_dataset_distributed")
+
     def _signature(self):
         return tuple((k, v.data_ptr(), v._version, str(v.device)) for k, v in self.state_dict(keep_vars=True).items())
 

@@ -30,16 +30,43 @@ int check_tensor(const tedspad_tensor& t, const char* name, int elem_align) {
   return 0;
 }
 
+constexpr int MAX_DEVICES = 64;
+static std::mutex g_dev_mutex;
+static int g_sms[MAX_DEVICES] = {0};
+static bool g_once[MAX_DEVICES][ONCE_SLOTS] = {{false}};
+
+static int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEVICES) return -1;
+  return dev;
+}
+
 int num_sms() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 1;
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 1;
-    sms = prop.multiProcessorCount;
+  const int dev = current_device();
+  if (dev < 0) return 1;
+  std::lock_guard<std::mutex> lock(g_dev_mutex);
+  if (g_sms[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 1;
+    g_sms[dev] = n;
   }
-  return sms;
+  return g_sms[dev];
+}
+
+bool device_once(int slot) {
+  const int dev = current_device();
+  if (dev < 0) return true;   // unknown device: redo the (idempotent) setup every time
+  std::lock_guard<std::mutex> lock(g_dev_mutex);
+  if (g_once[dev][slot]) return false;
+  g_once[dev][slot] = true;
+  return true;
+}
+
+void device_once_reset(int slot) {
+  const int dev = current_device();
+  if (dev < 0) return;
+  std::lock_guard<std::mutex> lock(g_dev_mutex);
+  g_once[dev][slot] = false;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

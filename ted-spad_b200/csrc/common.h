@@ -39,7 +39,14 @@ int encode_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint
 int encode_tmap_5d_bf16(CUtensorMap* out, const void* base, const uint64_t dims[5], const uint64_t strides_bytes[4],
                         const uint32_t box[5], bool swizzle128);
 
-int num_sms();
+int num_sms();   // of the CURRENT device (cached per device)
+
+// Per-device one-time setup (cudaFuncSetAttribute is a per-device property of a kernel: a process that touches a
+// second GPU must opt every kernel in to > 48 KB of dynamic shared memory there as well).  Returns true exactly once
+// per (current device, slot); the caller then performs the setup and, on failure, calls device_once_reset.
+enum { ONCE_IGEMM_ATTR = 0, ONCE_SLAB_ATTR = 1, ONCE_SLOTS = 4 };
+bool device_once(int slot);
+void device_once_reset(int slot);
 
 // Programmatic dependent launch (TEDSPAD_PDL=0 switches it off): every hot-path kernel is launched with
 // programmaticStreamSerialization, calls griddepcontrol.launch_dependents when it starts and griddepcontrol.wait

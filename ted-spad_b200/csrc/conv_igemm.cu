@@ -351,7 +351,6 @@ static int pick_n_tile(int cout_pad) {
   return n;
 }
 
-static std::once_flag g_attr_once;
 
 }  // namespace tsp
 
@@ -465,15 +464,14 @@ extern "C" int tedspad_conv_forward(const tedspad_conv* c, void* stream_v) {
       return 3;
   }
 
-  int rc = 0;
-  std::call_once(g_attr_once, [&] {
+  if (device_once(ONCE_IGEMM_ATTR)) {   // per device: the opt-in to > 48 KB of dynamic shared memory
     cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET);
     if (e != cudaSuccess) {
+      device_once_reset(ONCE_IGEMM_ATTR);
       set_error("cudaFuncSetAttribute(smem) failed: %s", cudaGetErrorString(e));
-      rc = 2;
+      return 2;
     }
-  });
-  if (rc) return rc;
+  }
 
   const int total_tiles = p.num_m_tiles * p.num_n_tiles;
   int ctas = c->max_ctas > 0 ? c->max_ctas : num_sms();

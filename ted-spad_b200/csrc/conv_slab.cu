@@ -549,7 +549,10 @@ conv_slab_kernel(const __grid_constant__ SlabKParams p) {
   }
   if (warp == 10) {
     if (PAIR) {
-      tmem_alloc_pair(tmem_slot, p.tmem_cols);
+      // one warp of EACH CTA of the pair executes the collective cta_group::2 allocation; each passes its own slot
+      // (tmem_slot[rank]) so that the two instructions never name the same shared-memory word (compute-sanitizer
+      // racecheck otherwise reports the pair's two identical-value writes as a hazard)
+      tmem_alloc_pair(tmem_slot + rank, p.tmem_cols);
       tmem_relinquish_pair();
     } else {
       tmem_alloc(tmem_slot, p.tmem_cols);
@@ -571,7 +574,7 @@ conv_slab_kernel(const __grid_constant__ SlabKParams p) {
   tc_fence_before();
   if (PAIR) cluster_sync_all(); else __syncthreads();   // PAIR: the peer's barriers are initialised before any remote arrive
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = tmem_slot[rank];
   pdl_launch_dependents();   // the next kernel may start its prologue on SMs this grid has left (common.h)
 
   if (warp == 8) {
@@ -1079,8 +1082,6 @@ static int make_plan(const tedspad_conv_slab& c, tedspad_slab_plan& P) {
   return 0;
 }
 
-static std::once_flag g_slab_attr_once;
-
 }  // namespace tsp
 
 using namespace tsp;
@@ -1244,19 +1245,18 @@ extern "C" int tedspad_conv_slab_forward(const tedspad_conv_slab* c, void* strea
     p.up_cb_first = 1 << 20;
   }
 
-  int rc = 0;
-  std::call_once(g_slab_attr_once, [&] {
+  if (device_once(ONCE_SLAB_ATTR)) {   // per device: the opt-in to > 48 KB of dynamic shared memory
     cudaError_t e = cudaFuncSetAttribute(conv_slab_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SLAB_SMEM_BUDGET);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(conv_slab_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SLAB_SMEM_BUDGET);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(conv_slab_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SLAB_SMEM_BUDGET);
     if (e != cudaSuccess) {
+      device_once_reset(ONCE_SLAB_ATTR);
       set_error("cudaFuncSetAttribute(slab smem) failed: %s", cudaGetErrorString(e));
-      rc = 2;
+      return 2;
     }
-  });
-  if (rc) return rc;
+  }
   int ctas = c->max_ctas > 0 ? c->max_ctas : num_sms();
   ctas = std::max(1, std::min(ctas, p.total_tiles));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_v);

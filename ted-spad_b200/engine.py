@@ -97,35 +97,62 @@ def same_pad(size, k, s):
 
 
 class _Buffers:
-    """Named activation buffers, allocated once per executor instance and shape."""
+    """Named activation buffers of one executor.  ONE allocation per name, sized for the largest batch seen so far: a
+    smaller batch (the tail of a video, a flush at a resolution change) runs on the N-prefix view of the same memory,
+    a larger batch or a different geometry replaces the allocation.  The footprint is therefore bounded by the largest
+    batch (~0.8 GB per 16x224x224 clip for the UNet, 26 GB at 32 clips) however many distinct batch sizes a dataset's
+    video tails produce."""
 
     def __init__(self, device):
         self.device = device
-        self.pool = {}
+        self.pool = {}      # name -> (spec, N allocated, CLTensor | torch.Tensor)
+        self.views = {}     # (name, N) -> prefix view
 
     def get(self, name, N, D, H, W, C, halo=(0, 0, 0), dtype=ops.BF16, zero=False):
         """zero=True: cleared once at allocation (channel-padded buffers whose pad channels are never written)."""
-        key = (name, N, D, H, W, C, tuple(halo), dtype)
-        t = self.pool.get(key)
-        if t is None:
+        v = self.views.get((name, N))
+        spec = (D, H, W, C, tuple(halo), dtype)
+        if v is not None and v[0] == spec:
+            return v[1]
+        ent = self.pool.get(name)
+        if ent is None or ent[0] != spec or ent[1] < N:
+            for k in [k for k in self.views if k[0] == name]:
+                del self.views[k]
+            self.pool.pop(name, None)   # (freed before the replacement is allocated)
+            ent = None
             t = CLTensor(N, D, H, W, C, halo, device=self.device, dtype=dtype)
             if zero:
                 t.buf.zero_()
-            self.pool[key] = t
+            ent = (spec, N, t)
+            self.pool[name] = ent
+        full = ent[2]
+        t = full if ent[1] == N else CLTensor(N, D, H, W, C, halo, ld=full.ld, buf=full.buf[:N], coff=full.coff)
+        self.views[(name, N)] = (spec, t)
         return t
 
     def raw(self, name, shape, dtype):
         """Plain (non channels-last) scratch tensor, e.g. the planar anonymizer output."""
-        key = ("raw", name, tuple(shape), dtype)
-        t = self.pool.get(key)
-        if t is None:
-            t = torch.empty(tuple(shape), device=self.device, dtype=dtype)
-            self.pool[key] = t
-        return t
+        key = ("raw", name)
+        ent = self.pool.get(key)
+        if ent is None or ent[0] != (tuple(shape), dtype):
+            ent = ((tuple(shape), dtype), 0, torch.empty(tuple(shape), device=self.device, dtype=dtype))
+            self.pool[key] = ent
+        return ent[2]
 
-    def drop_other_shapes(self, keep_n):
-        for k in [k for k in self.pool if k[1] != keep_n]:
-            del self.pool[k]
+    def find(self, name, N=None):
+        """The buffer last handed out under `name` (its N-prefix view when N is given), or None: lets the parity tests
+        read intermediate activations after a run."""
+        ent = self.pool.get(name)
+        if ent is None:
+            return None
+        if N is None or N == ent[1]:
+            return ent[2]
+        v = self.views.get((name, N))
+        return v[1] if v is not None else None
+
+    def nbytes(self):
+        return sum((e[2].buf if isinstance(e[2], CLTensor) else e[2]).numel() *
+                   (e[2].buf if isinstance(e[2], CLTensor) else e[2]).element_size() for e in self.pool.values())
 
 
 # ======================================================================================== UNet

@@ -52,7 +52,11 @@ def crop_boxes(h, w, ncrops=1, cropping_factor=0.8, no_ar_distortion=False, squa
     (square_from_h: shanghai_dl.py:35 uses H for both sides); crop order for 5/10 crops is torchvision's
     five_crop / ten_crop: tl, tr, bl, br, center (+ the same five of the h-flipped frame), so that
     crop 4 (center) is the reference's single crop."""
-    if no_ar_distortion:
+    if no_ar_distortion and square_from_h:
+        # shanghai_dl.py:30 takes min(image.shape) of the (H, W, 3) array, i.e. 3: a 2 x 2 crop with the default
+        # factor.  Reproduced as written (the reference ships no_ar_distortion=False, params_feature_ex.py:8).
+        ch = cw = int(min(h, w, 3) * cropping_factor)
+    elif no_ar_distortion:
         ch = cw = int(min(h, w) * cropping_factor)
     elif square_from_h:
         ch = cw = int(h * cropping_factor)
@@ -91,6 +95,7 @@ class SnippetExtractor:
         self._enc = {}
         self._copy_stream = None
         self._stage_bufs, self._stage_free = [None, None], [None, None]
+        self._desc_ring, self._desc_i = [], 0   # pinned host staging of the per-image descriptors (+ device copy)
 
     def snippet_frames(self, n_frames):
         if self.source == "dali":
@@ -98,25 +103,69 @@ class SnippetExtractor:
         return shanghai_snippet_frames(n_frames, self.T, self.skip)
 
     def _enc_in(self, B):
+        """Encoder input clip [B,T,H,W,4|8]: one allocation for the largest batch seen, smaller batches (video tails)
+        run on its B-prefix view, so the footprint does not grow with the number of distinct tail sizes."""
         t = self._enc.get(B)
         if t is None:
             from . import engine
-            t = ops.CLTensor(B, self.T, self.reso[0], self.reso[1], engine.ENC_IN_CHANNELS, device=self.device)
-            t.buf.zero_()  # pad channels stay zero (the glue writes zeros there, the old scatter only 0..2)
+            full = self._enc.get("full")
+            if full is None or full.N < B:
+                self._enc.clear()
+                full = ops.CLTensor(B, self.T, self.reso[0], self.reso[1], engine.ENC_IN_CHANNELS, device=self.device)
+                full.buf.zero_()  # pad channels stay zero (the glue never writes them)
+                self._enc["full"] = full
+            t = full if full.N == B else ops.CLTensor(B, full.D, full.H, full.W, full.C, ld=full.ld, buf=full.buf[:B])
             self._enc[B] = t
         return t
 
     def features_of_clips(self, frames_dev, desc_host, crop_hw):
         """frames_dev: cuda uint8 [F,H,W,3]; desc_host: int32 [B*T,4] numpy -> fp32 cuda [B, n_feat_rows, F]."""
         B = desc_host.shape[0] // self.T
+        self._check_desc(desc_host, frames_dev.shape, crop_hw)
         with torch.cuda.device(self.device):
-            desc = torch.from_numpy(desc_host).to(self.device, non_blocking=True)
+            desc = self._desc_to_device(desc_host)
             ex_fa = self.fa.executor(self.device)
             x0 = ex_fa.input_buffer(B * self.T, self.reso[0], self.reso[1])
             ops.preprocess(frames_dev, desc, crop_hw, x0, self.resample)
             enc_in = self._enc_in(B)
             self.fa.anonymize_into(x0, enc_in, self.T)
             return self.ft.features_from_cl(enc_in)
+
+    @staticmethod
+    def _check_desc(desc, frames_shape, crop_hw):
+        """Host-side validation of the (src_frame, top, left, hflip) rows: the preprocessing kernel indexes the frame
+        buffer with them unchecked."""
+        F_, Hs, Ws = int(frames_shape[0]), int(frames_shape[1]), int(frames_shape[2])
+        d = np.asarray(desc)
+        if d.ndim != 2 or d.shape[1] != 4 or d.dtype != np.int32:
+            raise ValueError("desc must be int32 [n, 4] = (src_frame, top, left, hflip)")
+        if d.size and (int(d[:, 0].max()) >= F_ or int(d[:, 1].min()) < 0 or int(d[:, 2].min()) < 0 or
+                       int(d[:, 1].max()) + int(crop_hw[0]) > Hs or int(d[:, 2].max()) + int(crop_hw[1]) > Ws):
+            raise ValueError(f"desc addresses pixels outside the [{F_},{Hs},{Ws}] frame buffer "
+                             f"(crop {tuple(crop_hw)}, max frame {int(d[:, 0].max())}, max top {int(d[:, 1].max())}, "
+                             f"max left {int(d[:, 2].max())})")
+
+    def _desc_to_device(self, desc_host):
+        """Per-image descriptors through a small ring of PINNED host buffers (a pageable source makes the copy
+        synchronous with the host) into per-slot device buffers; a slot is reused only after its copy has run."""
+        n = desc_host.shape[0]
+        if not self._desc_ring:
+            self._desc_ring = [[None, None, None] for _ in range(4)]
+        slot = self._desc_ring[self._desc_i % 4]
+        self._desc_i += 1
+        if slot[0] is None or slot[0].shape[0] < n:
+            if slot[2] is not None:
+                slot[2].synchronize()
+            slot[0] = torch.empty((max(n, 512), 4), dtype=torch.int32).pin_memory()
+            slot[1] = torch.empty((max(n, 512), 4), dtype=torch.int32, device=self.device)
+        elif slot[2] is not None:
+            slot[2].synchronize()
+        slot[0][:n].numpy()[...] = desc_host
+        dev = slot[1][:n]
+        dev.copy_(slot[0][:n], non_blocking=True)
+        slot[2] = torch.cuda.Event()
+        slot[2].record()
+        return dev
 
     def _stage(self, frames, slot):
         """Host frames -> one of two persistent device staging buffers, on the copy stream.  Returns the device view
@@ -131,7 +180,13 @@ class SnippetExtractor:
         n = sum(c.numel() for c in chunks)
         buf = self._stage_bufs[slot]
         if buf is None or buf.numel() < n:
-            buf = torch.empty(max(n, 1), dtype=torch.uint8, device=self.device)
+            # allocated ON the copy stream (the stream that writes it); a block the caching allocator hands back from
+            # the compute stream could still be read by kernels in flight there.  The buffer being replaced may still
+            # be read by the compute stream: tell the allocator before dropping it.
+            if buf is not None:
+                buf.record_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(self._copy_stream):
+                buf = torch.empty(max(n, 1), dtype=torch.uint8, device=self.device)
             self._stage_bufs[slot] = buf
         dev = buf[:n].view((sum(c.shape[0] for c in chunks),) + tuple(chunks[0].shape[1:]))
         with torch.cuda.stream(self._copy_stream):

@@ -79,3 +79,17 @@ def parity_metrics(got, ref):
     ccos = float(torch.nn.functional.cosine_similarity(gc, rc, dim=0))
     return {"cos": cos, "centered_cos": ccos, "max_abs": float((got - ref).abs().max()),
             "ref_max": float(ref.abs().max())}
+
+
+# ---- consumer contract (SURVEY a-12): feature matrices as the extraction scripts write them (float64), loaded the way
+# anomaly_detection_mgfn/datasets/dataset.py does.  tests/golden/consumer_v1.npz holds the reference's own outputs.
+CONSUMER_GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "consumer_v1.npz")
+CONSUMER_CASES = {"t7_f8": (7, None, 8), "t40_f8": (40, None, 8), "t75_c10_f6": (75, 10, 6), "t32_c5_f4": (32, 5, 4),
+                  "t33_f3": (33, None, 3)}   # name: (T, ncrops | None, F)
+
+
+def consumer_case_features(name):
+    T, ncrops, F = CONSUMER_CASES[name]
+    rs = np.random.RandomState(sum(map(ord, name)))
+    shape = (T, F) if ncrops is None else (T, ncrops, F)
+    return rs.rand(*shape).astype(np.float64) * 2.0   # the extraction scripts write float64 (dali_extraction.py:163)

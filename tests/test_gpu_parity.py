@@ -22,6 +22,14 @@ sys.path.insert(0, os.path.join(ROOT, "ted-spad_b200"))
 pytestmark = pytest.mark.gpu
 
 COS_GATE, ABS_GATE = 0.9995, 2e-2
+# Scale-free companions of the absolute gate (the absolute gate depends on the synthetic feature
+# scale).  REL_L2 = ||got - ref|| / ||ref|| (cos >= 0.9995 <=> <= 0.0316 for unbiased noise); REL_MAX = worst element
+# over the largest feature; TAP_REL = relative RMS error of every intermediate activation the executors keep, against
+# the oracle's taps of the same layer (a kernel bug shows up at ITS layer at the size of the signal, bf16 storage noise
+# stays at the 1e-2 level and grows slowly with depth).
+REL_L2_GATE = 0.0316
+REL_MAX_GATE = {"i3d": 0.10, "largei3d": 0.03, "r3d_18": 0.03}
+TAP_REL_GATE = 0.03
 
 
 def _modules(name, stress=False):
@@ -35,7 +43,8 @@ def _modules(name, stress=False):
     return fa.cuda().eval(), ft.cuda().eval()
 
 
-@pytest.mark.parametrize("group", ["flat", "gather", "multi", "ops", "prep", "slabpair", "streampair", "slab1x1", "fuzz"])
+@pytest.mark.parametrize("group", ["flat", "gather", "multi", "ops", "prep", "slab3", "slabpair", "slabstream", "streampair",
+                                   "slab1x1", "slabstem", "slabup", "fuzz"])
 def test_operator_battery(group):
     """tests/gpu_diag.py: each operator vs torch fp32 on bf16-rounded operands (conv tolerance 2e-2 of the
     output range, i.e. bf16 output rounding; pooling / layout / PIL preprocessing bit-exact)."""
@@ -58,6 +67,55 @@ def _pipeline_features(ext, name, which, hw):
     f = ext.features_of_clips(torch.from_numpy(np.ascontiguousarray(clip)).cuda(), desc, (ch, cw))
     torch.cuda.synchronize()
     return clip, f.reshape(-1).float().cpu()
+
+
+def _rel_l2(got, ref):
+    got, ref = got.double().flatten(), ref.double().flatten()
+    return float((got - ref).norm() / ref.norm())
+
+
+def _tap_errors(fa, ft, arch, taps_fa, taps_ft, B=1):
+    """{layer: relative RMS error} of the activation buffers the executors keep after a run vs the oracle's taps."""
+    from tedspad_b200.engine import UNetExecutor
+    dev = next(fa.parameters()).device
+    ex_fa = fa.executor(dev)
+    enc_mod = ft.i3d if hasattr(ft, "i3d") else ft
+    ex_ft = enc_mod._exec(torch.empty(1, device=dev))
+    pairs = []   # (label, CLTensor, oracle tensor [N,C,(D,)H,W])
+    lv = UNetExecutor.LEVELS
+    for i, p in enumerate(lv):
+        pairs.append((f"unet:{p}.0", ex_fa.bufs.find(f"t{i}"), taps_fa[f"{p}.0"]))
+        b = ex_fa.bufs.find(f"cat{i}") if i < 4 else ex_fa.bufs.find("x5")
+        pairs.append((f"unet:{p}.3", b.slice(0, taps_fa[f"{p}.3"].shape[1]) if i < 4 else b, taps_fa[f"{p}.3"]))
+    for j in range(4):
+        p = f"up{j + 1}.conv.double_conv"
+        pairs.append((f"unet:{p}.0", ex_fa.bufs.find(f"u{j}a"), taps_fa[f"{p}.0"]))
+        if j < 3:
+            pairs.append((f"unet:{p}.3", ex_fa.bufs.find(f"u{j}"), taps_fa[f"{p}.3"]))
+    if arch == "i3d":
+        for n in ["Conv3d_1a_7x7", "Conv3d_2b_1x1", "Conv3d_2c_3x3"] + [m[0] for m in M.I3D_MIXED]:
+            pairs.append((f"i3d:{n}", ex_ft.bufs.find(n), taps_ft[n]))
+    elif arch == "largei3d":
+        pairs.append(("i3res50:conv1", ex_ft.bufs.find("conv1"), taps_ft["conv1"]))
+        for blk in ex_ft.blocks:
+            # (layer1's last block is followed by the temporal max-pool in the oracle tap: compare the others)
+            if not blk["pool_after"]:
+                pairs.append((f"i3res50:{blk['name']}", ex_ft.bufs.find(blk["name"] + ".c3"), taps_ft["i3d." + blk["name"]]))
+    else:
+        pairs.append(("r3d:stem", ex_ft.bufs.find("stem"), taps_ft["stem"]))
+        for blk in ex_ft.blocks:
+            pairs.append((f"r3d:{blk['name']}", ex_ft.bufs.find(blk["name"] + ".c2"), taps_ft[blk["name"]]))
+    out = {}
+    for label, buf, ref in pairs:
+        assert buf is not None, label
+        got = buf.to_ncdhw().cpu()
+        got = got[:ref.shape[0]]
+        if ref.dim() == 4:
+            got = got[:, :, 0]
+        got = got[:, :ref.shape[1]]
+        assert got.shape == ref.shape, (label, got.shape, ref.shape)
+        out[label] = _rel_l2(got, ref)
+    return out
 
 
 def _torch_autocast_bf16_features(name, x_ref, stress=False):
@@ -102,6 +160,22 @@ def test_hot_path_parity(name):
           f"control cos(different clips)={ctrl:.4f}; cos of clip-to-clip feature difference={dcos:.4f}")
     assert m["cos"] >= COS_GATE and m["max_abs"] <= ABS_GATE, m
     assert mg["cos"] >= COS_GATE and mg["max_abs"] <= ABS_GATE, mg
+    # scale-free: relative L2 and worst element relative to the largest feature
+    rl2, rmax = _rel_l2(feats["test"], refs["test"]), m["max_abs"] / m["ref_max"]
+    print(f"{name}: rel_l2={rl2:.5f} (gate {REL_L2_GATE}) max_abs/|f|max={rmax:.4f} (gate {REL_MAX_GATE[arch]})")
+    assert rl2 <= REL_L2_GATE and rmax <= REL_MAX_GATE[arch]
+    # per-layer: every intermediate activation of the LAST run (the control clip) against the oracle's taps
+    taps_fa, taps_ft = {}, {}
+    sd_fa, sd_ft = _cases.case_weights(name)
+    with torch.no_grad():
+        x_c = torch.from_numpy(P.dali_val_augmentations(_cases.case_clip(name, "control"), reso))
+        enc_c = M.anonymize_and_reshape(sd_fa, x_c.unsqueeze(0), taps=taps_fa)
+        M.encoder_features(arch, sd_ft, enc_c, taps=taps_ft)
+    errs = _tap_errors(fa, ft, arch, taps_fa, taps_ft)
+    worst = max(errs, key=errs.get)
+    print(f"{name}: per-layer relative RMS error: " + ", ".join(f"{k.split(':')[1]}={v:.4f}" for k, v in errs.items()))
+    print(f"{name}: worst layer {worst} {errs[worst]:.4f} (gate {TAP_REL_GATE})")
+    assert errs[worst] <= TAP_REL_GATE, (worst, errs[worst])
     assert ctrl < COS_GATE            # the gate can tell two clips apart ...
     assert dcos > 0.98                # ... and the response to changing the clip matches the reference's
     # no worse than the existing bf16 kernels on the same network
@@ -318,3 +392,98 @@ def test_packed_videos_equal_per_video():
     packed10 = dict(ten.extract_videos(vids[:3]))
     for i in range(3):
         assert np.array_equal(packed10[i], ten.extract_video(vids[i]))
+
+
+def test_shanghai_feature_parity():
+    """ShanghaiTech path end to end at the dataset's frame size (480x856, BGR as cv2 decodes): snippet rows against the
+    oracle (shanghai_dl.augmentation -> anonymizer -> raw-reshape glue -> I3Res50.extract_features) under the
+    north-star gate.  Frames 32i+2j+1, crop 384x384 at (48, 236), Pillow 8-bit resize."""
+    from tedspad_b200.extraction import SnippetExtractor
+    name = "unet_largei3d_224"
+    fa, ft = _modules(name)
+    vid = _video(70, 480, 856, 9)
+    feats = SnippetExtractor(fa, ft, source="shanghai", batch_clips=2).extract_video(vid)
+    assert feats.shape == (2, 2048) and feats.dtype == np.float64
+    sd_fa, sd_ft = _cases.case_weights(name)
+    idx = M.shanghai_snippet_frames(70)
+    for r in (0, 1):
+        x = torch.from_numpy(np.stack([P.shanghai_augmentation(vid[i].numpy()) for i in idx[r]]))
+        with torch.no_grad():
+            f_ref = M.encoder_features("largei3d", sd_ft, M.anonymize_and_reshape(sd_fa, x.unsqueeze(0)))[0]
+        m = _cases.parity_metrics(torch.from_numpy(feats[r]), f_ref)
+        print(f"\nshanghai row {r}: cos={m['cos']:.6f} max_abs={m['max_abs']:.4f} rel_l2={_rel_l2(torch.from_numpy(feats[r]), f_ref):.5f}")
+        assert m["cos"] >= COS_GATE and m["max_abs"] <= ABS_GATE, (r, m)
+    assert not np.array_equal(feats[0], feats[1])
+
+
+def test_multicrop_feature_parity_corner_and_flipped():
+    """10-crop path: a corner crop (1 = top right) and a crop of the flipped frame (7 = bottom left of the h-flipped
+    frame) as FEATURES against the oracle run on that crop (r1 only checked boxes and crop 4)."""
+    from tedspad_b200.extraction import SnippetExtractor, crop_boxes
+    name = "unet_r3d18_112"
+    fa, ft = _modules(name)
+    vid = _video(32, 120, 160, 11)
+    ten = SnippetExtractor(fa, ft, reso=(112, 112), ncrops=10, batch_clips=10).extract_video(vid)
+    assert ten.shape == (1, 10, 512)
+    (ch, cw), boxes = crop_boxes(120, 160, 10)
+    sd_fa, sd_ft = _cases.case_weights(name)
+    clip = vid[M.dali_snippet_frames(32)[0]].numpy()
+    for ci in (1, 7, 4):
+        x = torch.from_numpy(P.dali_crop_augmentations(clip, boxes[ci], (ch, cw), (112, 112)))
+        with torch.no_grad():
+            f_ref = M.encoder_features("r3d_18", sd_ft, M.anonymize_and_reshape(sd_fa, x.unsqueeze(0)))[0]
+        m = _cases.parity_metrics(torch.from_numpy(ten[0, ci]), f_ref)
+        print(f"\ncrop {ci} {boxes[ci]}: cos={m['cos']:.6f} max_abs={m['max_abs']:.4f}")
+        assert m["cos"] >= COS_GATE and m["max_abs"] <= ABS_GATE, (ci, m)
+    assert not np.array_equal(ten[0, 1], ten[0, 7])
+
+
+def test_saved_files_load_like_the_mgfn_consumer(tmp_path):
+    """SURVEY a-12: files written by extract_dataset, loaded exactly as anomaly_detection_mgfn's Dataset.__getitem__
+    does (dataset.py:53-55 np.load -> float32; :70-71 / :87-89 expand_dims(axis=1), transpose to [ncrops,T,F];
+    process_feat to 32 segments; magnitude appended) for the [T,F] and the [T,10,F] layouts."""
+    from oracle import consumer as C
+    from tedspad_b200.extraction import SnippetExtractor, extract_dataset
+    name = "unet_r3d18_112"
+    fa, ft = _modules(name)
+    vids = [(f"/data/Abuse{i:03d}_x264.mp4", n, (lambda n=n, i=i: _video(n, 120, 160, 40 + i))) for i, n in enumerate([100, 33])]
+    for ncrops, folder in ((1, "ucf_features_ours"), (10, "ucf_features_ours_10crop")):
+        ext = SnippetExtractor(fa, ft, reso=(112, 112), ncrops=ncrops, batch_clips=10)
+        out = tmp_path / folder
+        written = extract_dataset(ext, vids, str(out), log=lambda *_: None)
+        assert sorted(os.path.basename(w) for w in written) == ["Abuse000_x264.npy", "Abuse001_x264.npy"]
+        for (path, n, _), T in zip(vids, (4, 2)):
+            f = str(out / (os.path.basename(path).replace(".mp4", "") + ".npy"))
+            raw = np.load(f, allow_pickle=True)
+            assert raw.dtype == np.float64 and raw.shape == ((T, 512) if ncrops == 1 else (T, 10, 512))
+            feats = C.load_features(f)                      # dataset.py:53-55
+            test_item = C.getitem_test(feats)               # dataset.py:68-86
+            train_item = C.getitem_train(feats)             # dataset.py:87-99
+            assert test_item.shape == (T, ncrops, 513) and train_item.shape == (ncrops, 32, 513)
+            assert test_item.dtype == np.float32 and train_item.dtype == np.float32
+            assert np.allclose(test_item[..., 512], np.linalg.norm(feats.reshape(T, ncrops, 512), axis=2), rtol=1e-6)
+            assert np.isfinite(train_item).all() and float(np.abs(train_item[..., :512]).max()) > 0
+            # T < 32: every segment of process_feat is a single snippet row, in order (utils.py:39-42)
+            r = np.linspace(0, T, 33, dtype=int)
+            crop0 = feats.reshape(T, ncrops, 512)[:, 0]
+            for s in (0, 15, 31):
+                want = crop0[r[s]:r[s + 1]].mean(0) if r[s] != r[s + 1] else crop0[min(r[s], T - 1)]
+                assert np.allclose(train_item[0, s, :512], want, rtol=1e-6)
+
+
+def test_second_device_after_first():
+    """the > 48 KB shared-memory opt-in and the SM count are per DEVICE; a process that used cuda:0 must be
+    able to run on cuda:1 (needs a 2-GPU box: `gpurun --gpus 2`)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from tedspad_b200.extraction import SnippetExtractor
+    name = "unet_r3d18_112"
+    arch, hw, reso, _, _ = _cases.CASES[name]
+    rows = []
+    for dev in ("cuda:0", "cuda:1"):
+        fa, ft = _modules(name)
+        ext = SnippetExtractor(fa.to(dev), ft.to(dev), reso=reso, batch_clips=2)
+        with torch.cuda.device(dev):
+            clip = _cases.case_clip(name)
+            rows.append(ext.extract_video(torch.from_numpy(np.ascontiguousarray(clip)).repeat(2, 1, 1, 1)))
+    assert np.array_equal(rows[0], rows[1])

@@ -223,6 +223,12 @@ def test_snippet_indexing_and_crops_match_oracle():
             assert (ch, cw) == P.crop_size(h, w) and boxes == P.multi_crop_boxes(h, w, ch, cw, nc)
     assert extraction.crop_boxes(480, 856, 1, square_from_h=True)[0] == (384, 384)
     assert extraction.crop_boxes(480, 856, 1, square_from_h=True)[1] == [(48, 236, 0)]
+    # no_ar_distortion: DALI path crops the square of the short side (dali_extraction.py:46); the ShanghaiTech path
+    # takes min over the (H, W, 3) array shape = 3 (shanghai_dl.py:30) - reproduced as written, like the oracle
+    assert extraction.crop_boxes(240, 320, 1, no_ar_distortion=True)[0] == P.crop_size(240, 320, no_ar_distortion=True) == (192, 192)
+    assert extraction.crop_boxes(480, 856, 1, no_ar_distortion=True, square_from_h=True)[0] == (2, 2)
+    f = np.random.RandomState(0).randint(0, 256, (480, 856, 3)).astype(np.uint8)
+    assert P.shanghai_augmentation(f, no_ar_distortion=True).shape == (3, 224, 224)
 
 
 def test_feature_path_and_resume(tmp_path):
@@ -380,3 +386,34 @@ def test_extract_videos_packing_bookkeeping_on_cpu():
             per_video += len(ext.batches_seen)
             assert got.shape == want.shape and np.array_equal(got, want), (ncrops, bc, source, i)
         assert n_batches_packed <= per_video      # packing never issues more batches than the per-video path
+
+
+def test_activation_buffers_are_bounded_by_the_largest_batch():
+    """every distinct batch size used to get its own full buffer set (OOM over a dataset's video tails).
+    One allocation per name now; smaller batches are N-prefix views of it, a larger batch replaces it."""
+    from tedspad_b200.engine import _Buffers
+    b = _Buffers("cpu")
+    full = b.get("t0", 8, 1, 6, 6, 64, (0, 1, 1))
+    size0 = b.nbytes()
+    for n in (8, 3, 5, 1, 7, 8, 2):
+        v = b.get("t0", n, 1, 6, 6, 64, (0, 1, 1))
+        assert v.N == n and v.buf.data_ptr() == full.buf.data_ptr() and v.buf.is_contiguous()
+        assert tuple(v.buf.shape) == (n, 1, 8, 8, 64)
+        assert b.get("t0", n, 1, 6, 6, 64, (0, 1, 1)) is v            # views are cached, not rebuilt per step
+        assert b.nbytes() == size0
+    assert b.find("t0") is full and b.find("t0", 3).N == 3
+    big = b.get("t0", 12, 1, 6, 6, 64, (0, 1, 1))                      # larger batch: replaces, does not add
+    assert big.N == 12 and b.nbytes() == size0 * 12 // 8 and len(b.pool) == 1
+    other = b.get("t0", 4, 1, 10, 10, 64, (0, 1, 1))                   # new geometry under the same name: replaces
+    assert (other.H, other.N) == (10, 4) and len(b.pool) == 1
+    z = b.get("pad", 2, 1, 4, 4, 64, zero=True)
+    assert float(z.buf.float().abs().max()) == 0.0
+
+
+def test_data_parallel_is_rejected_explicitly():
+    """dali_extraction.py:126-141 wraps the models in nn.DataParallel when it sees several GPUs; replicas have no
+    parameters and run on threads.  The boundary modules refuse replication with a clear message."""
+    from aux_code.model_loaders import load_fa_model
+    fa = load_fa_model(arch="unet")
+    with pytest.raises(RuntimeError, match="one process per GPU"):
+        fa._replicate_for_data_parallel()

@@ -96,3 +96,30 @@ def test_multi_crop_order_matches_torchvision():
             src = img.flip(-1) if fl else img
             assert torch.equal(src[:, t:t + ch, l:l + cw], ref)
     assert P.multi_crop_boxes(h, w, ch, cw, 1)[0] == P.multi_crop_boxes(h, w, ch, cw, 5)[4]
+
+
+@pytest.mark.parametrize("name", list(_cases.CONSUMER_CASES))
+def test_consumer_oracle_matches_reference_getitem(name, tmp_path):
+    """oracle/consumer.py == the reference's Dataset.__getitem__ (dataset.py:51-132) on the same files, bit for bit
+    (golden vectors from tests/golden/make_golden_consumer.py)."""
+    from oracle import consumer as C
+    G2 = np.load(_cases.CONSUMER_GOLDEN)
+    path = str(tmp_path / (name + ".npy"))
+    np.save(path, _cases.consumer_case_features(name))
+    feats = C.load_features(path)
+    assert feats.dtype == np.float32
+    assert np.array_equal(C.getitem_test(feats), G2[f"{name}/test"])
+    assert np.array_equal(C.getitem_train(feats), G2[f"{name}/train"])
+
+
+def test_crop_augmentations_match_torchvision_ten_crop():
+    """oracle dali_crop_augmentations (explicit box, optional h-flip) == torchvision ten_crop + antialiased resize."""
+    rs = np.random.RandomState(3)
+    h, w = 120, 160
+    v = rs.randint(0, 256, (2, h, w, 3)).astype(np.uint8)
+    ch, cw = P.crop_size(h, w)
+    vt = torch.from_numpy(v).float().permute(0, 3, 1, 2) / 255.
+    crops = TF.ten_crop(vt, (ch, cw))
+    for box, ref in zip(P.multi_crop_boxes(h, w, ch, cw, 10), crops):
+        mine = P.dali_crop_augmentations(v, box, (ch, cw), (112, 112))
+        assert np.abs(mine - TF.resize(ref, (112, 112), antialias=True).numpy()).max() < 2e-6
