@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define TEDSPAD_ABI_VERSION 5
+#define TEDSPAD_ABI_VERSION 6
 
 enum { TEDSPAD_ACT_NONE = 0, TEDSPAD_ACT_RELU = 1, TEDSPAD_ACT_SIGMOID = 2 };
 /* A-operand feed of the implicit GEMM: AUTO picks FLAT when legal. */
@@ -229,6 +229,21 @@ int tedspad_maxpool(const tedspad_tensor* x, const tedspad_tensor* y, int32_t kd
  * Replaces Up.forward's nn.Upsample + F.pad + torch.cat (aux_code/models/unet_parts.py:50,57-67).
  */
 int tedspad_upsample2x(const tedspad_tensor* x, const tedspad_tensor* y, void* stream);
+
+/*
+ * x2 nearest-neighbour up-sampling written into a channel slice of a concatenation buffer (y.H == 2 x.H,
+ * y.W == 2 x.W).  Replaces F.interpolate(scale_factor=2, mode="nearest") + torch.cat of smp 0.3.3's
+ * unetplusplus DecoderBlock.forward (the arch='unet++' anonymizer, aux_code/model_loaders.py:18-30).
+ */
+int tedspad_upsample2x_nearest(const tedspad_tensor* x, const tedspad_tensor* y, void* stream);
+
+/*
+ * Channels-last anonymizer output [B*T][1][H][W][>=3] (bf16; the UNet++ segmentation head, activation=None) ->
+ * encoder clip [B][T][H][W][4|8] through the raw-reshape glue of feature_extraction/dali_extraction.py:171-173
+ * (plane 3t+c of clip b -> encoder channel (3t+c)/T, time (3t+c)%T); pad channels written as zero.  `frames_out`
+ * (optional) receives the un-scattered fp32 frames [B*T][3][H][W], the fa_model return value.
+ */
+int tedspad_frames_to_clip(const tedspad_tensor* x, const tedspad_tensor* y, int32_t T, float* frames_out, void* stream);
 
 /*
  * OutConv (1x1, C->3) + sigmoid + the anonymizer->encoder raw-reshape glue: plane p = 3*t + c of

@@ -9,6 +9,10 @@ plain `state_dict` (name -> tensor) whose keys/shapes are those of the reference
   i3res50_extract_features  aux_code/models/large_i3d.py:249-263 (Bottleneck :61-84)
   r3d18_forward             aux_code/model_loaders.py:200-213 + torchvision video/resnet.py
                             (BasicStem :173-181, BasicBlock :87-121, VideoResNet.forward :251-263)
+  unetpp_forward            aux_code/model_loaders.py:18-30 -> segmentation_models_pytorch 0.3.3 UnetPlusPlus (third-party,
+                            NOT under /root/reference and not installable here: restated from the published source,
+                            **parity unpinned** for the decoder; the ResNet-18 encoder half is pinned against
+                            torchvision.models.resnet18, tests/test_oracle.py)
   anonymize_and_reshape     feature_extraction/dali_extraction.py:171-173 (raw reshape glue)
   snippet indexing          dali_extraction.py:58-76 (DALI reader) / shanghai_dl.py:43-98
 
@@ -45,6 +49,21 @@ I3RES50_LAYERS = [  # (planes, blocks, stride, temp_conv)
 ]
 
 
+# smp 0.3.3 UnetPlusPlus(resnet18, encoder_depth=4, decoder_channels=(256,128,64,32)) as model_loaders.py:19-30 builds it.
+# Encoder feature channels (3, 64, 64, 128, 256) at strides (1, 2, 4, 8, 16); the decoder drops the stride-1 feature,
+# reverses the rest (head first) and derives per block (smp decoders/unetplusplus/decoder.py, UnetPlusPlusDecoder.__init__):
+#   in_channels = [256, 256, 128, 64], skip_channels = [128, 64, 64, 0], out_channels = (256, 128, 64, 32)
+#   x_{d}_{l}:  d == 0: in = in_channels[l], skip = skip_channels[l] * (l + 1), out = out_channels[l]
+#               d  > 0: in = skip_channels[l - 1], skip = skip_channels[l] * (l + 1 - d), out = skip_channels[l]
+#   x_0_3: in = 64, skip = 0, out = 32
+UNETPP_BLOCKS = [  # (name, in (up-sampled) channels, skip channels, out channels)
+    ("x_0_0", 256, 128, 256), ("x_0_1", 256, 128, 128), ("x_1_1", 128, 64, 64),
+    ("x_0_2", 128, 192, 64), ("x_1_2", 64, 128, 64), ("x_2_2", 64, 64, 64), ("x_0_3", 64, 0, 32),
+]
+RESNET18_LAYERS = [(64, 1), (128, 2), (256, 2), (512, 2)]   # (planes, stride of the first block); layer4 exists in the
+#                                                             state_dict but is not run at encoder_depth=4
+
+
 def conv_bn_names(arch):
     """Ordered list of (conv_weight_key, conv_bias_key|None, bn_prefix|None, weight_shape) per arch."""
     out = []
@@ -59,6 +78,22 @@ def conv_bn_names(arch):
         for i, (ci, co) in enumerate([(1024, 256), (512, 128), (256, 64), (128, 64)], 1):
             dc(f"up{i}.conv.double_conv", ci, co, ci // 2)
         out.append(("outc.conv.weight", "outc.conv.bias", None, (3, 64, 1, 1)))
+    elif arch == "unet++":
+        out.append(("encoder.conv1.weight", None, "encoder.bn1", (64, 3, 7, 7)))
+        inpl = 64
+        for li, (planes, stride) in enumerate(RESNET18_LAYERS, 1):
+            for b in range(2):
+                p = f"encoder.layer{li}.{b}"
+                out.append((f"{p}.conv1.weight", None, f"{p}.bn1", (planes, inpl, 3, 3)))
+                out.append((f"{p}.conv2.weight", None, f"{p}.bn2", (planes, planes, 3, 3)))
+                if b == 0 and (stride != 1 or inpl != planes):
+                    out.append((f"{p}.downsample.0.weight", None, f"{p}.downsample.1", (planes, inpl, 1, 1)))
+                inpl = planes
+        for name, cin, cskip, cout in UNETPP_BLOCKS:
+            p = f"decoder.blocks.{name}"
+            out.append((f"{p}.conv1.0.weight", None, f"{p}.conv1.1", (cout, cin + cskip, 3, 3)))
+            out.append((f"{p}.conv2.0.weight", None, f"{p}.conv2.1", (cout, cout, 3, 3)))
+        out.append(("segmentation_head.0.weight", "segmentation_head.0.bias", None, (3, 32, 3, 3)))
     elif arch == "i3d":
         def u(name, cin, cout, k):
             out.append((f"{name}.conv3d.weight", None, f"{name}.bn", (cout, cin) + tuple(k)))
@@ -171,6 +206,75 @@ def unet_forward(sd, x, calibrate=False, taps=None):
     return c.tap("out", torch.sigmoid(F.conv2d(y, sd["outc.conv.weight"], sd["outc.conv.bias"])))
 
 
+def resnet18_encoder_features(sd, x, prefix="encoder.", ctx=None):
+    """smp ResNetEncoder.forward at depth 4 (encoders/resnet.py: stages = [identity, conv1+bn1+relu, maxpool+layer1,
+    layer2, layer3]) over torchvision's resnet18 (models/resnet.py BasicBlock.forward): [x, f1/2, f2/4, f3/8, f4/16]."""
+    c = ctx or _Ctx(sd, False, None, 1e-5)
+    P = prefix
+    feats = [x]
+    y = F.conv2d(x, sd[P + "conv1.weight"], None, stride=2, padding=3)
+    y = c.tap(P + "conv1", torch.relu(c.bn(y, P + "bn1")))
+    feats.append(y)
+    y = F.max_pool2d(y, 3, 2, 1)
+    inpl = 64
+    for li, (planes, stride) in enumerate(RESNET18_LAYERS[:3], 1):
+        for b in range(2):
+            p = f"{P}layer{li}.{b}"
+            st = stride if b == 0 else 1
+            out = F.conv2d(y, sd[p + ".conv1.weight"], None, stride=st, padding=1)
+            out = torch.relu(c.bn(out, p + ".bn1"))
+            out = c.bn(F.conv2d(out, sd[p + ".conv2.weight"], None, padding=1), p + ".bn2")
+            res = y
+            if b == 0 and (st != 1 or inpl != planes):
+                res = c.bn(F.conv2d(y, sd[p + ".downsample.0.weight"], None, stride=st), p + ".downsample.1")
+            y = c.tap(p, torch.relu(out + res))
+            inpl = planes
+        feats.append(y)
+    return feats
+
+
+def unetpp_forward(sd, x, calibrate=False, taps=None):
+    """x: fp32 [N,3,H,W] -> [N,3,H,W], UNBOUNDED (activation=None).  smp 0.3.3 UnetPlusPlus.forward =
+    segmentation_head(decoder(*encoder(x))) (base/model.py), H and W multiples of 16 (check_input_shape).
+    DecoderBlock.forward (decoders/unetplusplus/decoder.py): nearest x2 up-sampling, torch.cat([x, skip], 1),
+    then two Conv2dReLU = Conv2d(3x3, pad 1, bias=False) + BatchNorm2d + ReLU (base/modules.py; attention = Identity).
+    UnetPlusPlusDecoder.forward: dense nested skips x_{d}_{l}."""
+    if x.shape[2] % 16 or x.shape[3] % 16:
+        raise RuntimeError(f"Wrong input shape height={x.shape[2]}, width={x.shape[3]}: must be divisible by 16")
+    c = _Ctx(sd, calibrate, taps, 1e-5)
+    feats = resnet18_encoder_features(sd, x, "encoder.", c)
+    f = feats[1:][::-1]            # head first: (256@/16, 128@/8, 64@/4, 64@/2)
+
+    def block(name, x, skip=None):
+        p = f"decoder.blocks.{name}"
+        x = F.interpolate(x, scale_factor=2, mode="nearest")
+        if skip is not None:
+            x = torch.cat([x, skip], 1)
+        for cv in ("conv1", "conv2"):
+            x = F.conv2d(x, sd[f"{p}.{cv}.0.weight"], None, padding=1)
+            x = torch.relu(c.bn(x, f"{p}.{cv}.1"))
+            c.tap(f"{p}.{cv}", x)
+        return x
+
+    depth = 3
+    dense = {}
+    for layer_idx in range(depth):
+        for depth_idx in range(depth - layer_idx):
+            if layer_idx == 0:
+                dense[f"x_{depth_idx}_{depth_idx}"] = block(f"x_{depth_idx}_{depth_idx}", f[depth_idx], f[depth_idx + 1])
+            else:
+                dl = depth_idx + layer_idx
+                cat = [dense[f"x_{i}_{dl}"] for i in range(depth_idx + 1, dl + 1)]
+                cat = torch.cat(cat + [f[dl + 1]], 1)
+                dense[f"x_{depth_idx}_{dl}"] = block(f"x_{depth_idx}_{dl}", dense[f"x_{depth_idx}_{dl - 1}"], cat)
+    y = block(f"x_0_{depth}", dense[f"x_0_{depth - 1}"])
+    return c.tap("out", F.conv2d(y, sd["segmentation_head.0.weight"], sd["segmentation_head.0.bias"], padding=1))
+
+
+def anonymizer_forward(arch, sd, x, **kw):
+    return unetpp_forward(sd, x, **kw) if arch == "unet++" else unet_forward(sd, x, **kw)
+
+
 def same_pad(size, k, s):
     """TF-SAME total pad -> (front, back).  i3d.py:82-86,102-109."""
     p = max(k - s, 0) if size % s == 0 else max(k - size % s, 0)
@@ -272,10 +376,12 @@ def encoder_features(arch, sd, x, **kw):
 
 
 def anonymize_and_reshape(sd_fa, inputs, **kw):
-    """inputs: [1,T,3,H,W] -> anonymized [1,3,T,H,W] by the RAW reshape of dali_extraction.py:171-173."""
+    """inputs: [1,T,3,H,W] -> anonymized [1,3,T,H,W] by the RAW reshape of dali_extraction.py:171-173.  The
+    anonymizer architecture is read off the state_dict ('unet' or 'unet++')."""
     bs, t, ch, h, w = inputs.shape
     frames = inputs.reshape(-1, ch, h, w)
-    return unet_forward(sd_fa, frames, **kw).reshape(bs, ch, t, h, w)
+    arch = "unet++" if "segmentation_head.0.weight" in sd_fa else "unet"
+    return anonymizer_forward(arch, sd_fa, frames, **kw).reshape(bs, ch, t, h, w)
 
 
 def plane_map(T=16, C=3):
@@ -339,8 +445,8 @@ FINAL_BN = {
 
 def _calibrate(arch, sd, calib_input):
     with torch.no_grad():
-        if arch == "unet":
-            return unet_forward(sd, calib_input, calibrate=True)
+        if arch in ("unet", "unet++"):
+            return anonymizer_forward(arch, sd, calib_input, calibrate=True)
         return encoder_features(arch, sd, calib_input, calibrate=True)
 
 
@@ -392,6 +498,12 @@ def calibrated_state_dict(arch, seed, calib_input, num_classes=102, beta_over_ga
         elif kind == "nbt":
             sd[k] = torch.tensor(1, dtype=torch.long)
     out = _calibrate(arch, sd, calib_input)
+    if arch == "unet++":
+        # activation=None: the head is unbounded.  Rescale it so that the synthetic anonymizer emits image-like values
+        # (mean 0.5, std 0.25), the regime the encoder sees from a trained anonymizer (and from the sigmoid UNet).
+        sc = 0.25 / float(out.std())
+        sd["segmentation_head.0.bias"] = (sd["segmentation_head.0.bias"] - float(out.mean())) * sc + 0.5
+        sd["segmentation_head.0.weight"] = sd["segmentation_head.0.weight"] * sc
     if arch in FINAL_BN and feature_mean:
         s = feature_mean / float(out.mean())
         for bn in FINAL_BN[arch]:

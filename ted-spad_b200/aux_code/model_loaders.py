@@ -14,6 +14,7 @@ from aux_code._base import CudaModule
 from aux_code.models.i3d import InceptionI3d
 from aux_code.models.large_i3d import I3Res50
 from aux_code.models.unet_model import UNet
+from aux_code.models.unetpp import UnetPlusPlus
 from tedspad_b200.engine import R3D18Executor
 
 
@@ -26,10 +27,19 @@ def load_fa_model(saved_model_file=None, arch='unet++'):
     if arch == 'unet':
         fa_model = UNet(n_channels=3, n_classes=3)
     elif arch == 'unet++':
-        raise NotImplementedError(
-            "arch='unet++' is segmentation_models_pytorch 0.3.3's UnetPlusPlus (model_loaders.py:18-30); that "
-            "third-party source is not available to pin parity against, so it is scheduled after the in-tree "
-            "'unet' (SURVEY.md 8f rank 1). Use arch='unet'.")
+        # the same call the reference makes (model_loaders.py:19-30) on the drop-in for smp 0.3.3's UnetPlusPlus
+        fa_model = UnetPlusPlus(
+            encoder_name='resnet18',
+            encoder_depth=4,
+            encoder_weights="imagenet" if not saved_model_file else None,   # never downloaded: see UnetPlusPlus
+            decoder_channels=(256, 128, 64, 32),
+            decoder_attention_type=None,
+            decoder_use_batchnorm=True,
+            in_channels=3,
+            classes=3,
+            activation=None,
+            aux_params=None
+        )
     else:
         raise ValueError(f"Architecture {arch} invalid for fa_model. Try 'unet' or 'unet++'")
     if saved_model_file:

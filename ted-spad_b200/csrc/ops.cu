@@ -616,6 +616,78 @@ __global__ void __launch_bounds__(256) planes_to_clip_kernel(const P2CP p) {
   }
 }
 
+// ------------------------------------------------------------------ nearest x2 into a channel slice
+struct NearP {
+  TView x, y;
+  uint32_t c8_magic;
+  long long total;  // input rows N*H
+};
+
+// One block per INPUT row: a thread loads one 16-byte channel chunk of an input pixel once and stores it to the 2x2
+// output pixels it covers (F.interpolate(scale_factor=2, mode="nearest"): out[y][x] = in[y/2][x/2]).
+__global__ void __launch_bounds__(256) upsample2x_nearest_kernel(const NearP p) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int c8n = p.x.C >> 3;
+  const int items = p.x.W * c8n;
+  const long long y_row = static_cast<long long>(p.y.Wp) * p.y.ld;
+  for (long long row = blockIdx.x; row < p.total; row += gridDim.x) {
+    const int n = static_cast<int>(row / p.x.H), ih = static_cast<int>(row - static_cast<long long>(n) * p.x.H);
+    const __nv_bfloat16* xr = elem_ptr(p.x, pix_index(p.x, n, 0, ih, 0), 0);
+    __nv_bfloat16* yr = elem_ptr_w(p.y, pix_index(p.y, n, 0, 2 * ih, 0), 0);
+    for (int it = threadIdx.x; it < items; it += blockDim.x) {
+      const int iw = fast_div(it, p.c8_magic), c8 = it - iw * c8n;
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(xr + static_cast<long long>(iw) * p.x.ld + c8 * 8));
+      __nv_bfloat16* yp = yr + static_cast<long long>(2 * iw) * p.y.ld + c8 * 8;
+      *reinterpret_cast<uint4*>(yp) = q;
+      *reinterpret_cast<uint4*>(yp + p.y.ld) = q;
+      *reinterpret_cast<uint4*>(yp + y_row) = q;
+      *reinterpret_cast<uint4*>(yp + y_row + p.y.ld) = q;
+    }
+  }
+}
+
+// ------------------------------------- channels-last anonymizer output -> encoder clip (raw-reshape glue)
+struct F2CP {
+  TView x;          // [B*T][1][H][W][>=3] bf16 (the UNet++ head output: unbounded, activation=None)
+  TView y;          // [B][T][H][W][4|8]
+  float* frames;    // optional fp32 [B*T][3][H][W]
+  int T;
+  long long total;  // B*T*H*W clip pixels
+};
+
+// thread -> one ENCODER pixel (b, te, h, w): channel ce comes from plane ce*T + te of the clip's 3T anonymizer planes,
+// i.e. colour (ce*T + te) % 3 of frame (ce*T + te) / 3 (dali_extraction.py:171-173); one 8- or 16-byte store.
+__global__ void __launch_bounds__(256) frames_to_clip_kernel(const F2CP p) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long plane = static_cast<long long>(p.y.H) * p.y.W;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < p.total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    long long t = idx;
+    const int w = static_cast<int>(t % p.y.W); t /= p.y.W;
+    const int h = static_cast<int>(t % p.y.H); t /= p.y.H;
+    const int te = static_cast<int>(t % p.T);
+    const int b = static_cast<int>(t / p.T);
+    uint16_t v[3];
+#pragma unroll
+    for (int ce = 0; ce < 3; ++ce) {
+      const int pl = ce * p.T + te, tf = pl / 3, o = pl - 3 * tf;
+      v[ce] = __ldg(reinterpret_cast<const uint16_t*>(elem_ptr(p.x, pix_index(p.x, b * p.T + tf, 0, h, w), o)));
+    }
+    __nv_bfloat16* yp = elem_ptr_w(p.y, pix_index(p.y, b, te, h, w), 0);
+    const uint32_t lo = static_cast<uint32_t>(v[0]) | (static_cast<uint32_t>(v[1]) << 16), hi = static_cast<uint32_t>(v[2]);
+    if (p.y.C == 4) *reinterpret_cast<uint2*>(yp) = make_uint2(lo, hi);
+    else *reinterpret_cast<uint4*>(yp) = make_uint4(lo, hi, 0u, 0u);
+    if (p.frames != nullptr) {
+      // the un-scattered frames (the fa_model return value): frame b*T + te, its own three colours
+      const __nv_bfloat16* xp = elem_ptr(p.x, pix_index(p.x, b * p.T + te, 0, h, w), 0);
+      float* fo = p.frames + (static_cast<long long>(b * p.T + te) * 3) * plane + static_cast<long long>(h) * p.y.W + w;
+      fo[0] = __bfloat162float(xp[0]); fo[plane] = __bfloat162float(xp[1]); fo[2 * plane] = __bfloat162float(xp[2]);
+    }
+  }
+}
+
 static int grid_for(long long total, int threads) {
   const long long blocks = (total + threads - 1) / threads;
   const long long cap = static_cast<long long>(num_sms()) * 16;
@@ -693,6 +765,40 @@ extern "C" int tedspad_upsample2x(const tedspad_tensor* x, const tedspad_tensor*
   p.c8_magic = static_cast<uint32_t>((0x100000000ULL + (y->C / 8) - 1) / (y->C / 8));
   TSP_CHECK(static_cast<long long>(y->W) * (y->C / 8) < 65536, "upsample2x: row of %d x %d channels too long", y->W, y->C);
   TSP_CUDA(launch_kernel(upsample2x_kernel, dim3(rows_grid(p.total, y->W * (y->C / 8))), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), p));
+  TSP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tedspad_upsample2x_nearest(const tedspad_tensor* x, const tedspad_tensor* y, void* stream) {
+  TSP_CHECK(x && y, "upsample2x_nearest: null tensor");
+  if (check_tensor(*x, "upsample2x_nearest.x", 8) || check_tensor(*y, "upsample2x_nearest.y", 8)) return 1;
+  TSP_CHECK(x->C == y->C && x->C % 8 == 0 && x->N == y->N && x->D == 1 && y->D == 1 && y->H == 2 * x->H && y->W == 2 * x->W,
+            "upsample2x_nearest: [%d,%d,%d,%d] -> [%d,%d,%d,%d] is not an exact x2", x->N, x->H, x->W, x->C, y->N, y->H,
+            y->W, y->C);
+  NearP p;
+  p.x = make_view(*x); p.y = make_view(*y);
+  p.c8_magic = static_cast<uint32_t>((0x100000000ULL + (x->C / 8) - 1) / (x->C / 8));
+  TSP_CHECK(static_cast<long long>(x->W) * (x->C / 8) < 65536, "upsample2x_nearest: row of %d x %d channels too long", x->W, x->C);
+  p.total = static_cast<long long>(x->N) * x->H;
+  TSP_CUDA(launch_kernel(upsample2x_nearest_kernel, dim3(rows_grid(p.total, x->W * (x->C / 8))), dim3(256), 0,
+                         reinterpret_cast<cudaStream_t>(stream), p));
+  TSP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tedspad_frames_to_clip(const tedspad_tensor* x, const tedspad_tensor* y, int32_t T, float* frames_out,
+                                      void* stream) {
+  TSP_CHECK(x && y, "frames_to_clip: null argument");
+  if (check_tensor(*x, "frames_to_clip.x", 1) || check_tensor(*y, "frames_to_clip.y", 4)) return 1;
+  TSP_CHECK(x->C >= 3 && x->D == 1 && (y->C == 4 || y->C == 8) && y->ld % y->C == 0 && y->coff % y->C == 0,
+            "frames_to_clip: x needs >= 3 channels, y must be a [B,T,H,W,4|8] clip");
+  TSP_CHECK(T >= 1 && x->N % T == 0 && y->N == x->N / T && y->D == T && y->H == x->H && y->W == x->W,
+            "frames_to_clip: clip [%d,%d,%d,%d] does not match %d frames of T=%d", y->N, y->D, y->H, y->W, x->N, T);
+  F2CP p;
+  p.x = make_view(*x); p.y = make_view(*y);
+  p.frames = frames_out; p.T = T;
+  p.total = static_cast<long long>(x->N) * x->H * x->W;
+  TSP_CUDA(launch_kernel(frames_to_clip_kernel, dim3(grid_for(p.total, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), p));
   TSP_CUDA(cudaGetLastError());
   return 0;
 }

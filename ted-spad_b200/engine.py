@@ -252,6 +252,139 @@ class UNetExecutor:
         return enc_in
 
 
+# ===================================================================================== UNet++
+# smp 0.3.3 UnetPlusPlus(resnet18, encoder_depth=4, decoder_channels=(256,128,64,32)) as model_loaders.py:19-30 builds it
+RESNET18_LAYERS = [(64, 1), (128, 2), (256, 2), (512, 2)]   # (planes, stride of block 0); layer4 is parameters only
+UNETPP_BLOCKS = [  # (name, up-sampled input channels, skip channels, output channels); see oracle/models.py
+    ("x_0_0", 256, 128, 256), ("x_0_1", 256, 128, 128), ("x_1_1", 128, 64, 64),
+    ("x_0_2", 128, 192, 64), ("x_1_2", 64, 128, 64), ("x_2_2", 64, 64, 64), ("x_0_3", 64, 0, 32),
+]
+
+
+class UNetPPExecutor:
+    """arch='unet++' anonymizer (aux_code/model_loaders.py:18-30): ResNet-18 encoder to layer3 + the nested UNet++
+    decoder + 3x3 head, per frame.
+
+    Dense skips without copies: per resolution ONE buffer holds every tensor that is ever concatenated there, ordered
+    so that each decoder block's input is a contiguous channel range (the block's conv1 weights are packed with their
+    input channels permuted to that physical order), and every producer writes straight into its slice:
+
+        /8   P8  = [ up(f/16) 256 | f/8 128 ]                                   x_0_0 reads [0,384)
+        /4   P4  = [ up(x_0_0) 256 | x_1_1 64 | f/4 64 | up(f/8) 128 ]          x_1_1 reads [320,512), x_0_1 reads [0,384)
+        /2   P2  = [ up(x_0_1) 128 | x_1_2 64 | x_2_2 64 | f/2 64 | E 64 ]      x_2_2 reads [256,384) with E = up(f/4),
+                                                                                 x_1_2 reads [192,384) with E = up(x_1_1)
+                                                                                 (E is rewritten once x_2_2 is done),
+                                                                                 x_0_2 reads [0,320)
+        /1   P1  = up(x_0_2) 64
+
+    The only materialised glue is the nearest x2 up-sampling itself (tedspad_upsample2x_nearest)."""
+
+    HALO = (0, 1, 1)
+
+    def __init__(self, sd, device):
+        self.device = device
+        self.bufs = _Buffers(device)
+
+        def mk(wk, bnk, stride=(1, 1, 1), pad=(0, 1, 1), cin_pad=None, perm=None):
+            w = sd[wk]
+            if perm is not None:
+                w = w[:, perm]
+            pc = PackedConv(w, None, _bn(sd, bnk, 1e-5), stride=stride, pad_front=pad, cin_pad=cin_pad, device=device, n_align=32)
+            pc.slab = slab3x3(pc)
+            return pc
+
+        self.stem = PackedConv(sd["encoder.conv1.weight"], None, _bn(sd, "encoder.bn1", 1e-5), stride=(1, 2, 2),
+                               pad_front=(0, 3, 3), cin_pad=8, device=device, n_align=32)
+        self.stem_slab = stem3d(self.stem)
+        self.enc = []
+        inpl = 64
+        for li, (planes, stride) in enumerate(RESNET18_LAYERS[:3], 1):
+            for b in range(2):
+                p = f"encoder.layer{li}.{b}"
+                st = stride if b == 0 else 1
+                has_ds = b == 0 and (st != 1 or inpl != planes)
+                self.enc.append({
+                    "c1": mk(f"{p}.conv1.weight", f"{p}.bn1", (1, st, st)),
+                    "c2": mk(f"{p}.conv2.weight", f"{p}.bn2"),
+                    "ds": mk(f"{p}.downsample.0.weight", f"{p}.downsample.1", (1, st, st), (0, 0, 0)) if has_ds else None,
+                    "name": p, "li": li, "b": b, "planes": planes, "stride": st})
+                inpl = planes
+        r = lambda a, b: list(range(a, b))  # noqa: E731
+        # physical input-channel order of conv1 per block (None = smp's own [up-sampled | skips] order)
+        perms = {"x_1_1": r(128, 192) + r(0, 128),              # [f/4 | up(f/8)]
+                 "x_2_2": r(64, 128) + r(0, 64),                # [f/2 | up(f/4)]
+                 "x_1_2": r(64, 192) + r(0, 64)}                # [x_2_2 | f/2 | up(x_1_1)]
+        self.dec = {}
+        for name, cin, cskip, cout in UNETPP_BLOCKS:
+            p = f"decoder.blocks.{name}"
+            self.dec[name] = (mk(f"{p}.conv1.0.weight", f"{p}.conv1.1", perm=perms.get(name)),
+                              mk(f"{p}.conv2.0.weight", f"{p}.conv2.1", cin_pad=-(-cout // 64) * 64))
+        # 3x3 head 32 -> 3 with bias, no activation; run with 8 output channels (5 zero rows): one 16-byte pixel store
+        hw = sd["segmentation_head.0.weight"]
+        w8 = torch.zeros((8,) + tuple(hw.shape[1:]), dtype=hw.dtype, device=hw.device)
+        b8 = torch.zeros(8, dtype=hw.dtype, device=hw.device)
+        w8[:3], b8[:3] = hw, sd["segmentation_head.0.bias"]
+        self.head = PackedConv(w8, b8, None, pad_front=(0, 1, 1), cin_pad=64, device=device, n_align=32)
+        self.head.slab = slab3x3(self.head)
+
+    def input_buffer(self, n_frames, H, W):
+        """The [n_frames,1,H,W,4|8] bf16 buffer preprocessing / nchw_to_cl writes the frames into."""
+        return self.bufs.get("x0", n_frames, 1, H, W, 4 if self.stem_slab is not None else 8)
+
+    def run(self, x0, enc_in, T=16, frames_out=None):
+        """x0: input_buffer() filled with frames; enc_in: encoder input [B,T,H,W,4|8] (raw-reshape glue target)."""
+        N, H, W = x0.N, x0.H, x0.W
+        if H % 16 or W % 16:
+            raise RuntimeError(f"Wrong input shape height={H}, width={W}. Expected image height and width divisible by 16.")
+        g, hl = self.bufs.get, self.HALO
+        sz = {k: (H // k, W // k) for k in (1, 2, 4, 8, 16)}
+        P1 = g("P1", N, 1, *sz[1], 64, hl)
+        P2 = g("P2", N, 1, *sz[2], 384, hl)
+        P4 = g("P4", N, 1, *sz[4], 512, hl)
+        P8 = g("P8", N, 1, *sz[8], 384, hl)
+        f2, f4, f8 = P2.slice(256, 64), P4.slice(320, 64), P8.slice(256, 128)
+        f16 = g("f16", N, 1, *sz[16], 256, hl)
+        # ---- encoder: conv1 + bn1 + relu, maxpool 3x3 s2 p1 (post-ReLU input: zero padding == -inf padding), layer1..3
+        stem_conv(x0, self.stem, self.stem_slab, f2)
+        x = ops.maxpool(f2, g("mp", N, 1, *sz[4], 64, hl), (1, 3, 3), (1, 2, 2), (0, 1, 1), zero_pad=True)
+        outs = {1: f4, 2: f8, 3: f16}
+        for blk in self.enc:
+            n, li, planes = blk["name"], blk["li"], blk["planes"]
+            oh, ow = sz[4 << (li - 1)]
+            t = conv_auto(x, blk["c1"], g(n + ".t", N, 1, oh, ow, planes, hl))
+            res = x if blk["ds"] is None else conv_auto(x, blk["ds"], g(n + ".ds", N, 1, oh, ow, planes, hl), act=L.ACT_NONE)
+            y = outs[li] if blk["b"] == 1 else g(n + ".y", N, 1, oh, ow, planes, hl)
+            x = conv_auto(t, blk["c2"], y, res=res)      # bn2 + identity, then ReLU (torchvision BasicBlock.forward)
+        # ---- decoder
+        def block(name, x_in, out):
+            a, b = self.dec[name]
+            c = b.cin_pad                                   # x_0_3: 32 channels stored as 64 (pad channels zero)
+            t = g(name + ".t", N, 1, x_in.H, x_in.W, c, hl, zero=(c != a.cout))
+            conv_auto(x_in, a, t.slice(0, a.cout))
+            return conv_auto(t, b, out)
+
+        up = ops.upsample2x_nearest
+        up(f16, P8.slice(0, 256))
+        x00 = block("x_0_0", P8, g("x_0_0", N, 1, *sz[8], 256, hl))
+        up(f8, P4.slice(384, 128))
+        x11 = block("x_1_1", P4.slice(320, 192), P4.slice(256, 64))
+        up(f4, P2.slice(320, 64))
+        block("x_2_2", P2.slice(256, 128), P2.slice(192, 64))
+        up(x00, P4.slice(0, 256))
+        x01 = block("x_0_1", P4.slice(0, 384), g("x_0_1", N, 1, *sz[4], 128, hl))
+        up(x11, P2.slice(320, 64))                          # slot E again: x_2_2 has consumed up(f/4)
+        block("x_1_2", P2.slice(192, 192), P2.slice(128, 64))
+        up(x01, P2.slice(0, 128))
+        x02 = block("x_0_2", P2.slice(0, 320), g("x_0_2", N, 1, *sz[2], 64, hl))
+        up(x02, P1)
+        h = g("x_0_3", N, 1, *sz[1], 64, hl, zero=True)
+        block("x_0_3", P1, h.slice(0, 32))
+        # ---- segmentation head (activation=None) and the raw-reshape glue into the encoder clip
+        out8 = conv_auto(h, self.head, g("head", N, 1, *sz[1], 8, hl), act=L.ACT_NONE)
+        ops.frames_to_clip(out8, enc_in, T, frames_out)
+        return enc_in
+
+
 # ======================================================================================== I3D
 I3D_MIXED = [
     ("Mixed_3b", 192, [64, 96, 128, 16, 32, 32]),

@@ -353,6 +353,25 @@ def upsample2x(x, y):
     return y
 
 
+def upsample2x_nearest(x, y):
+    """y = nearest x2 of x, written into the channel slice y (smp DecoderBlock.forward's F.interpolate + torch.cat)."""
+    xd, yd = x.desc(), y.desc()
+    _count()
+    with _timed("upsample2x_nearest"):
+        L.check(L.lib().tedspad_upsample2x_nearest(C.byref(xd), C.byref(yd), _stream()), "tedspad_upsample2x_nearest")
+    return y
+
+
+def frames_to_clip(x, y, T, frames_out=None):
+    """channels-last anonymizer frames [B*T,1,H,W,>=3] -> encoder clip view y [B,T,H,W,4|8] (raw-reshape glue)."""
+    xd, yd = x.desc(), y.desc()
+    fo = frames_out.data_ptr() if frames_out is not None else None
+    _count()
+    with _timed("frames_to_clip"):
+        L.check(L.lib().tedspad_frames_to_clip(C.byref(xd), C.byref(yd), int(T), fo, _stream()), "tedspad_frames_to_clip")
+    return y
+
+
 def outconv_sigmoid(x, w, b, y, T, frames_out=None):
     """w: fp32 [3, C] cuda, b: fp32 [3] cuda; y: encoder-input CLTensor [B,T,H,W,>=3]."""
     xd, yd = x.desc(), y.desc()

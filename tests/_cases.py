@@ -17,7 +17,16 @@ CASES = {
     "unet_i3d_224": ("i3d", (240, 320), (224, 224), (1, 2), (100, 101, 102)),
     "unet_largei3d_224": ("largei3d", (240, 320), (224, 224), (1, 3), (100, 101, 102)),
     "unet_r3d18_112": ("r3d_18", (120, 160), (112, 112), (4, 5), (110, 111, 112)),
+    # the configuration both reference scripts request (dali_extraction.py:122-123): UNet++ anonymizer + I3D-ResNet50.
+    # smp is not installable here, so this case has NO golden vectors from the reference: its oracle is the
+    # restatement of smp 0.3.3's UnetPlusPlus in oracle/models.py (parity unpinned for the decoder half).
+    "unetpp_largei3d_224": ("largei3d", (240, 320), (224, 224), (6, 7), (100, 101, 102)),
 }
+FA_ARCH = {"unetpp_largei3d_224": "unet++"}   # anonymizer per case (default 'unet')
+
+
+def fa_arch(name):
+    return FA_ARCH.get(name, "unet")
 
 # Synthetic-init regime per encoder (oracle.models.calibrated_state_dict): BN beta/gamma range and the mean the
 # calibration features are scaled to.  The residual encoders pass the bf16 gate at beta/gamma in (0.5, 1.5); the
@@ -30,6 +39,7 @@ CASES = {
 # deviates from fp32 no more than stock PyTorch bf16 autocast (cuDNN) does on the very same network.
 INIT = {
     "unet": {"beta_over_gamma": (0.5, 1.5)},
+    "unet++": {"beta_over_gamma": (0.5, 1.5)},
     "i3d": {"beta_over_gamma": (1.5, 2.5), "feature_mean": 0.10},
     "largei3d": {"beta_over_gamma": (0.5, 1.5), "feature_mean": 0.5},
     "r3d_18": {"beta_over_gamma": (0.5, 1.5), "feature_mean": 0.5},
@@ -46,10 +56,10 @@ def case_weights(name, stress=False):
     arch, hw, reso, wseeds, cseeds = CASES[name]
     clip = M.structured_clip_u8(cseeds[0], 16, hw[0], hw[1])
     x = torch.from_numpy(P.dali_val_augmentations(clip, reso))
-    fa_init = STRESS_INIT if stress else INIT["unet"]
+    fa_init = STRESS_INIT if stress else INIT[fa_arch(name)]
     ft_init = dict(INIT[arch], **STRESS_INIT) if stress else INIT[arch]
     with torch.no_grad():
-        sd_fa = M.calibrated_state_dict("unet", wseeds[0], x, **fa_init)
+        sd_fa = M.calibrated_state_dict(fa_arch(name), wseeds[0], x, **fa_init)
         enc_in = M.anonymize_and_reshape(sd_fa, x.unsqueeze(0))
         sd_ft = M.calibrated_state_dict(arch, wseeds[1], enc_in, **ft_init)
     return sd_fa, sd_ft

@@ -181,6 +181,22 @@ def upsample2x(x, y):
     return y
 
 
+def upsample2x_nearest(x, y):
+    import torch.nn.functional as F
+    xi = x.interior().float()[:, 0].permute(0, 3, 1, 2)
+    up = F.interpolate(xi, scale_factor=2, mode="nearest")
+    y.interior()[:, 0] = up.permute(0, 2, 3, 1).to(y.buf.dtype)
+    return y
+
+
+def frames_to_clip(x, y, T, frames_out=None):
+    fr = x.interior().float()[:, 0, :, :, :3].permute(0, 3, 1, 2).contiguous()   # [F,3,H,W]
+    if frames_out is not None:
+        frames_out.copy_(fr)
+    y.interior()[...] = 0
+    return planes_to_clip_into(fr, y, T)
+
+
 def outconv_sigmoid(x, w, b, y, T, frames_out=None):
     xi = x.interior().float()[:, 0]  # [F,H,W,C]
     v = torch.sigmoid(xi @ w.T + b)  # [F,H,W,3]

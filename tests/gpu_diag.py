@@ -262,6 +262,46 @@ def group_ops():
         except Exception:
             RESULTS.append((name, False))
             print(f"[FAIL] {name}: EXCEPTION\n{traceback.format_exc()}", flush=True)
+    # nearest x2 into a concat slice (smp DecoderBlock.forward of the UNet++ anonymizer)
+    for name, (n, c, h, w), (ld, coff) in [("nearest x2 7x9 -> slice of 192", (3, 64, 7, 9), (192, 64)),
+                                           ("nearest x2 14x14 whole buffer", (2, 256, 14, 14), (256, 0))]:
+        try:
+            x = torch.randn(n, c, h, w, generator=g).to(DEV)
+            src = ops.CLTensor(n, 1, h, w, c + 64, (0, 1, 1), device=DEV)   # source is itself a channel slice
+            src.slice(64, c).interior()[:, 0] = x.permute(0, 2, 3, 1).to(torch.bfloat16)
+            cat = ops.CLTensor(n, 1, 2 * h, 2 * w, ld, (0, 1, 1), device=DEV)
+            cat.buf.fill_(5.0)
+            ops.upsample2x_nearest(src.slice(64, c), cat.slice(coff, c))
+            ref = F.interpolate(bf(x), scale_factor=2, mode="nearest").unsqueeze(2)
+            report(name, cat.slice(coff, c).to_ncdhw(), ref, tol_rel=0)
+            full = cat.buf.float().clone()
+            full[:, :, 1:1 + 2 * h, 1:1 + 2 * w, coff:coff + c] = 5.0
+            okk = bool((full == 5.0).all())
+            RESULTS.append((name + ":rest", okk))
+            print(f"[{'PASS' if okk else 'FAIL'}] {name}: halo and other channels untouched")
+        except Exception:
+            RESULTS.append((name, False))
+            print(f"[FAIL] {name}: EXCEPTION\n{traceback.format_exc()}", flush=True)
+    # channels-last head output -> encoder clip through the raw-reshape glue (+ fp32 frames)
+    try:
+        B, T, H, W = 2, 16, 10, 12
+        fr = (torch.randn(B * T, 3, H, W, generator=g) * 2).to(DEV)
+        ref = bf(fr).reshape(B, T, 3, H, W).reshape(B, 3, T, H, W)
+        for cpad, halo in ((4, (0, 0, 0)), (8, (0, 0, 0))):
+            xc = ops.CLTensor.from_ncdhw(fr, halo=(0, 1, 1))       # [B*T,1,H,W,8], channels 3..7 zero
+            xc.interior()[..., 3:] = 7.0                            # junk in the pad channels must not leak
+            enc = ops.CLTensor(B, T, H, W, cpad, device=DEV)
+            enc.buf.fill_(5.0)
+            out = torch.full((B * T, 3, H, W), 9.0, device=DEV)
+            ops.frames_to_clip(xc, enc, T, out)
+            report(f"frames_to_clip C={cpad}", enc.to_ncdhw()[:, :3], ref, tol_rel=0)
+            report(f"frames_to_clip C={cpad} fp32 frames", out, bf(fr), tol_rel=0)
+            okz = bool((enc.interior()[..., 3:] == 0).all())
+            RESULTS.append((f"frames_to_clip C={cpad} pad", okz))
+            print(f"[{'PASS' if okz else 'FAIL'}] frames_to_clip C={cpad}: pad channels zero")
+    except Exception:
+        RESULTS.append(("frames_to_clip", False))
+        print(f"[FAIL] frames_to_clip: EXCEPTION\n{traceback.format_exc()}", flush=True)
     # outconv + sigmoid + scatter
     try:
         B, T, H, W, Cc = 2, 16, 10, 12, 64
@@ -539,6 +579,10 @@ def group_slab3():
     run_slab_case("S7 64->64 112x112 x8 many tiles", K, 8, (1, 112, 112), 64, 64, 64, (1, 3, 3), halo=(0, 1, 1))
     run_slab_case("S8 64->32 odd 19x21", K, 2, (1, 19, 21), 64, 64, 32, (1, 3, 3), halo=(0, 1, 1))
     run_slab_case("S9 (1,3,3) D=3 64->64", K, 2, (3, 16, 16), 64, 64, 64, (1, 3, 3), halo=(0, 1, 1))
+    # UNet++ tail: 32 real input channels stored as 64, 8 output channels (the 3x3 head, 3 real + 5 zero rows)
+    run_slab_case("S10 32(64)->8 head 40x40 x3", K, 3, (1, 40, 40), 32, 64, 8, (1, 3, 3), halo=(0, 1, 1))
+    run_slab_case("S11 64->32 into a 64-wide buffer", K, 2, (1, 32, 32), 64, 64, 32, (1, 3, 3), halo=(0, 1, 1), out_ld=64, out_coff=0)
+    run_slab_case("S12 64->64 + residual (BasicBlock tail) 56x56 x3 stacked", K, 3, (1, 56, 56), 64, 64, 64, (1, 3, 3), halo=(0, 1, 1), res=True)
 
 
 def group_slabpair():
@@ -724,6 +768,11 @@ def group_slabstem():
                   pad_f=(1, 3, 3))
     run_slab_case("T7 stem3d i3d 16x64x64 x2", L.SLAB_STEM3D, 2, (16, 64, 64), 3, 4, 64, (7, 7, 7), stride=(2, 2, 2),
                   pad_f=(2, 2, 2), pad_b=(3, 3, 3))
+    # 2-D 7x7 stride-2 pad-3 stem (kd = 1): the ResNet-18 encoder conv1 of the UNet++ anonymizer, frames as [N][1][H][W][4]
+    run_slab_case("T8 stem 2-D 7x7 s2 p3 (resnet18 conv1) 32x48 x3", L.SLAB_STEM3D, 3, (1, 32, 48), 3, 4, 64, (1, 7, 7), stride=(1, 2, 2),
+                  pad_f=(0, 3, 3), out_halo=(0, 1, 1))
+    run_slab_case("T9 stem 2-D 7x7 s2 p3 112x112 x4 tm2 into a slice", L.SLAB_STEM3D, 4, (1, 112, 112), 3, 4, 64, (1, 7, 7), stride=(1, 2, 2),
+                  pad_f=(0, 3, 3), tm=2, out_halo=(0, 1, 1), out_ld=384, out_coff=256)
     # planar anonymizer output -> encoder clip (raw-reshape glue)
     try:
         g = torch.Generator(device="cpu").manual_seed(5)

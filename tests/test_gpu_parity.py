@@ -36,7 +36,7 @@ def _modules(name, stress=False):
     from aux_code.model_loaders import load_fa_model, load_ft_model
     arch = _cases.CASES[name][0]
     sd_fa, sd_ft = _cases.case_weights(name, stress)
-    fa = load_fa_model(arch="unet")
+    fa = load_fa_model(arch=_cases.fa_arch(name))
     ft = load_ft_model(arch=arch, num_classes=102)
     fa.load_state_dict(sd_fa, strict=True)
     ft.load_state_dict(sd_ft, strict=True)
@@ -82,16 +82,27 @@ def _tap_errors(fa, ft, arch, taps_fa, taps_ft, B=1):
     enc_mod = ft.i3d if hasattr(ft, "i3d") else ft
     ex_ft = enc_mod._exec(torch.empty(1, device=dev))
     pairs = []   # (label, CLTensor, oracle tensor [N,C,(D,)H,W])
-    lv = UNetExecutor.LEVELS
-    for i, p in enumerate(lv):
-        pairs.append((f"unet:{p}.0", ex_fa.bufs.find(f"t{i}"), taps_fa[f"{p}.0"]))
-        b = ex_fa.bufs.find(f"cat{i}") if i < 4 else ex_fa.bufs.find("x5")
-        pairs.append((f"unet:{p}.3", b.slice(0, taps_fa[f"{p}.3"].shape[1]) if i < 4 else b, taps_fa[f"{p}.3"]))
-    for j in range(4):
-        p = f"up{j + 1}.conv.double_conv"
-        pairs.append((f"unet:{p}.0", ex_fa.bufs.find(f"u{j}a"), taps_fa[f"{p}.0"]))
-        if j < 3:
-            pairs.append((f"unet:{p}.3", ex_fa.bufs.find(f"u{j}"), taps_fa[f"{p}.3"]))
+    if isinstance(ex_fa, UNetExecutor):
+        lv = UNetExecutor.LEVELS
+        for i, p in enumerate(lv):
+            pairs.append((f"unet:{p}.0", ex_fa.bufs.find(f"t{i}"), taps_fa[f"{p}.0"]))
+            b = ex_fa.bufs.find(f"cat{i}") if i < 4 else ex_fa.bufs.find("x5")
+            pairs.append((f"unet:{p}.3", b.slice(0, taps_fa[f"{p}.3"].shape[1]) if i < 4 else b, taps_fa[f"{p}.3"]))
+        for j in range(4):
+            p = f"up{j + 1}.conv.double_conv"
+            pairs.append((f"unet:{p}.0", ex_fa.bufs.find(f"u{j}a"), taps_fa[f"{p}.0"]))
+            if j < 3:
+                pairs.append((f"unet:{p}.3", ex_fa.bufs.find(f"u{j}"), taps_fa[f"{p}.3"]))
+    else:   # UNet++: encoder stages and every decoder block output, where the executor keeps them (engine.UNetPPExecutor)
+        P2, P4, P8 = (ex_fa.bufs.find(n) for n in ("P2", "P4", "P8"))
+        where = {"encoder.conv1": P2.slice(256, 64), "encoder.layer1.1": P4.slice(320, 64), "encoder.layer2.1": P8.slice(256, 128),
+                 "encoder.layer3.1": ex_fa.bufs.find("f16"), "decoder.blocks.x_0_0.conv2": ex_fa.bufs.find("x_0_0"),
+                 "decoder.blocks.x_1_1.conv2": P4.slice(256, 64), "decoder.blocks.x_2_2.conv2": P2.slice(192, 64),
+                 "decoder.blocks.x_0_1.conv2": ex_fa.bufs.find("x_0_1"), "decoder.blocks.x_1_2.conv2": P2.slice(128, 64),
+                 "decoder.blocks.x_0_2.conv2": ex_fa.bufs.find("x_0_2"),
+                 "decoder.blocks.x_0_3.conv2": ex_fa.bufs.find("x_0_3").slice(0, 32), "out": ex_fa.bufs.find("head").slice(0, 3)}
+        for k, b in where.items():
+            pairs.append((f"unetpp:{k}", b, taps_fa[k]))
     if arch == "i3d":
         for n in ["Conv3d_1a_7x7", "Conv3d_2b_1x1", "Conv3d_2c_3x3"] + [m[0] for m in M.I3D_MIXED]:
             pairs.append((f"i3d:{n}", ex_ft.bufs.find(n), taps_ft[n]))
@@ -151,7 +162,10 @@ def test_hot_path_parity(name):
             assert e.pow(2).mean().sqrt() < 0.012 and e.max() < 0.1
             yard = _cases.parity_metrics(_torch_autocast_bf16_features(name, x_ref), refs[which])
     m = _cases.parity_metrics(feats["test"], refs["test"])
-    mg = _cases.parity_metrics(feats["test"], torch.from_numpy(G[f"{name}/features"]))
+    # golden vectors of the unmodified reference exist for every case whose anonymizer the reference can build here
+    # (arch='unet'); the unet++ case is checked against the restated oracle only (smp not installable: parity unpinned)
+    has_golden = f"{name}/features" in G.files
+    mg = _cases.parity_metrics(feats["test"], torch.from_numpy(G[f"{name}/features"])) if has_golden else m
     ctrl = float(torch.nn.functional.cosine_similarity(refs["test"], refs["control"], dim=0))
     dcos = float(torch.nn.functional.cosine_similarity(feats["test"] - feats["control"], refs["test"] - refs["control"], dim=0))
     print(f"{name}: vs oracle cos={m['cos']:.6f} max_abs={m['max_abs']:.4f} (|f|max {m['ref_max']:.3f}); "
@@ -487,3 +501,47 @@ def test_second_device_after_first():
             clip = _cases.case_clip(name)
             rows.append(ext.extract_video(torch.from_numpy(np.ascontiguousarray(clip)).repeat(2, 1, 1, 1)))
     assert np.array_equal(rows[0], rows[1])
+
+
+def test_drop_in_reference_script_lines_unetpp_largei3d(tmp_path, monkeypatch):
+    """dali_extraction.py:109-110,122-123 (model construction from checkpoints, the DEFAULT arch='unet++' + 'largei3d'
+    with kin_pretrained=True) and :168-179 (loop body) run verbatim against this package: one checkpoint file holding
+    both state dicts, a DataParallel-style 'module.' prefix on the anonymizer's, the Kinetics file at
+    '../saved_models/i3d_r50_kinetics.pth' relative to the script's working directory."""
+    from aux_code.model_loaders import load_fa_model, load_ft_model
+    name = "unetpp_largei3d_224"
+    sd_fa, sd_ft = _cases.case_weights(name)
+    (tmp_path / "saved_models").mkdir()
+    (tmp_path / "feature_extraction").mkdir()
+    kin = {k[len("i3d."):]: v for k, v in sd_ft.items() if k.startswith("i3d.") and not k.startswith("i3d.fc.")}
+    kin["fc.weight"], kin["fc.bias"] = torch.zeros(400, 2048), torch.zeros(400)
+    torch.save(kin, tmp_path / "saved_models" / "i3d_r50_kinetics.pth")
+    torch.save({"fa_model_state_dict": {"module." + k: v for k, v in sd_fa.items()}, "ft_model_state_dict": sd_ft, "epoch": 20},
+               tmp_path / "saved_models" / "model_20_bestAcc_0.7504.pth")
+    monkeypatch.chdir(tmp_path / "feature_extraction")
+    anonymized = True
+    saved_fa_model = os.path.join('..', 'saved_models', 'model_20_bestAcc_0.7504.pth') if anonymized else None
+    saved_ft_model = os.path.join('..', 'saved_models', 'model_20_bestAcc_0.7504.pth')
+    fa_model = load_fa_model(arch='unet++', saved_model_file=saved_fa_model)
+    ft_model = load_ft_model(arch='largei3d', kin_pretrained=True, saved_model_file=saved_ft_model, num_classes=102)
+    ft_model.to(device=torch.device(0))
+    fa_model.to(device=torch.device(0))
+    ft_model.eval()
+    fa_model.eval()
+    clip = _cases.case_clip(name)
+    x_ref, enc_ref, f_ref = _cases.oracle_features(name, clip)
+    inputs = x_ref.unsqueeze(0).cuda()
+    with torch.no_grad():
+        ori_bs, ori_t, ori_c, ori_h, ori_w = inputs.permute(0, 2, 1, 3, 4).shape
+        inputs = inputs.view(-1, inputs.shape[2], inputs.shape[3], inputs.shape[4])
+        inputs = fa_model(inputs).reshape(ori_bs, ori_t, ori_c, ori_h, ori_w)
+        try:
+            output = ft_model.extract_features(inputs)
+        except:  # noqa: E722
+            output = ft_model.i3d.extract_features(inputs)
+        row = output.squeeze().cpu().numpy()
+    e = (inputs.cpu() - enc_ref).abs()
+    m = _cases.parity_metrics(torch.from_numpy(row), f_ref)
+    print(f"\nunet++ drop-in: anonymized err max={e.max():.4f}; features cos={m['cos']:.6f} max_abs={m['max_abs']:.4f}")
+    assert row.shape == (2048,) and e.max() < 0.1
+    assert m["cos"] >= COS_GATE and m["max_abs"] <= ABS_GATE, m

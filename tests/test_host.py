@@ -47,10 +47,12 @@ def test_library_has_blackwell_sass():
     assert "sm_100a" in out and "UTCHMMA" in out and "UTMALDG" in out and "LDTM" in out
 
 
-@pytest.mark.parametrize("arch", ["unet", "i3d", "largei3d", "r3d_18"])
+@pytest.mark.parametrize("arch", ["unet", "unet++", "i3d", "largei3d", "r3d_18"])
 def test_state_dict_matches_reference_tree(arch):
-    """keys + shapes equal the oracle's spec, which make_golden.py loaded strict=True into the real reference."""
-    mod = load_fa_model(arch="unet") if arch == "unet" else load_ft_model(arch=arch, num_classes=102)
+    """keys + shapes equal the oracle's spec, which make_golden.py loaded strict=True into the real reference
+    (unet++: smp is not installable here - the spec restates smp 0.3.3's published module tree; the encoder half is
+    checked against torchvision's resnet18 below)."""
+    mod = load_fa_model(arch=arch) if arch in ("unet", "unet++") else load_ft_model(arch=arch, num_classes=102)
     sd = mod.state_dict()
     want = {}
     for wk, bk, bn, shape in M.conv_bn_names(arch):
@@ -68,6 +70,15 @@ def test_state_dict_matches_reference_tree(arch):
         assert tuple(v.shape) == want[k], (k, tuple(v.shape), want[k])
     if arch == "i3d":
         assert list(sd)[0] == "logits.conv3d.weight"  # registered before the trunk (i3d.py:298-304)
+    if arch == "unet++":
+        # smp's ResNetEncoder IS torchvision's ResNet minus fc (avgpool has no parameters): same keys, same shapes
+        import torchvision
+        tv = {k: tuple(v.shape) for k, v in torchvision.models.resnet18().state_dict().items() if not k.startswith("fc.")}
+        mine = {k[len("encoder."):]: tuple(v.shape) for k, v in sd.items() if k.startswith("encoder.")}
+        assert mine == tv
+        assert [k for k in sd if not k.startswith("encoder.")][0] == "decoder.blocks.x_0_0.conv1.0.weight"
+        assert tuple(sd["decoder.blocks.x_0_2.conv1.0.weight"].shape) == (64, 320, 3, 3)
+        assert tuple(sd["segmentation_head.0.weight"].shape) == (3, 32, 3, 3) and "segmentation_head.0.bias" in sd
 
 
 def test_checkpoint_formats(tmp_path):
@@ -84,6 +95,13 @@ def test_checkpoint_formats(tmp_path):
     ft2 = load_ft_model(arch="largei3d", saved_model_file=str(p2), num_classes=102)
     assert torch.equal(ft2.i3d.conv1.weight, ft.i3d.conv1.weight)
     assert not hasattr(ft2, "extract_features") and hasattr(ft2.i3d, "extract_features")
+    # the default arch (what dali_extraction.py:122 / st_feature_extraction.py:72 request), DataParallel-saved
+    fpp = load_fa_model()
+    p3 = tmp_path / "fa_pp.pth"
+    torch.save({"fa_model_state_dict": {"module." + k: v for k, v in fpp.state_dict().items()}}, p3)
+    fpp2 = load_fa_model(saved_model_file=str(p3))
+    assert type(fpp2).__name__ == "UnetPlusPlus"
+    assert all(torch.equal(a, b) for a, b in zip(fpp.state_dict().values(), fpp2.state_dict().values()))
 
 
 def test_no_cpu_fallback():
@@ -93,8 +111,8 @@ def test_no_cpu_fallback():
     ft = load_ft_model(arch="i3d", num_classes=102).eval()
     with pytest.raises(RuntimeError, match="CUDA"):
         ft.extract_features(torch.zeros(1, 3, 16, 224, 224))
-    with pytest.raises(NotImplementedError):
-        load_fa_model(arch="unet++")
+    with pytest.raises(RuntimeError, match="CUDA"):
+        load_fa_model(arch="unet++").eval()(torch.zeros(1, 3, 32, 32))
 
 
 def test_packed_conv_layout():
@@ -119,7 +137,7 @@ def _emulated(monkeypatch, fp32=False):
     """Replace the CUDA operators by tests/_emu.py; fp32=True also stores activations/weights in fp32 so
     that executor wiring can be checked exactly (no rounding) against the oracle."""
     for n in ("conv_forward", "conv_slab_forward", "planes_to_clip", "maxpool", "upsample2x", "outconv_sigmoid",
-              "avgpool_features", "nchw_to_cl", "preprocess"):
+              "avgpool_features", "nchw_to_cl", "preprocess", "upsample2x_nearest", "frames_to_clip"):
         monkeypatch.setattr(ops, n, getattr(_emu, n))
     if fp32:
         orig = ops.CLTensor.__init__
@@ -188,6 +206,33 @@ def test_executor_wiring_unet_exact_odd_size(monkeypatch):
     out = torch.empty(2, 3, 40, 52)
     ue.run(x0, enc, 1, out)
     assert (out - ref).abs().max() < 1e-4
+
+
+def test_executor_wiring_unetpp_exact(monkeypatch):
+    """fp32-storage emulation of the UNet++ executor (shared per-resolution concat buffers, permuted conv1 input
+    channels, slot E re-use, 32-channel tail stored as 64, 8-row head) against the oracle restatement of smp's
+    UnetPlusPlus, to fp32 round-off; non-square frame."""
+    _emulated(monkeypatch, fp32=True)
+    g = torch.Generator().manual_seed(11)
+    x = torch.rand(4, 3, 48, 80, generator=g)
+    sd = M.calibrated_state_dict("unet++", 12, x)
+    taps = {}
+    ref = M.unetpp_forward(sd, x, taps=taps)
+    ex = engine.UNetPPExecutor(sd, "cpu")
+    x0 = ex.input_buffer(4, 48, 80)
+    ops.nchw_to_cl(x, x0)
+    enc = ops.CLTensor(2, 2, 48, 80, engine.ENC_IN_CHANNELS, device="cpu")
+    out = torch.empty(4, 3, 48, 80)
+    ex.run(x0, enc, 2, out)
+    assert (out - ref).abs().max() < 1e-4
+    for name, buf in (("decoder.blocks.x_1_2.conv2", ex.bufs.find("P2").slice(128, 64)),
+                      ("decoder.blocks.x_0_1.conv2", ex.bufs.find("x_0_1")), ("encoder.layer3.1", ex.bufs.find("f16"))):
+        assert (buf.to_ncdhw()[:, :, 0] - taps[name]).abs().max() < 1e-4, name
+    # glue: the clip is the RAW reshape of the frames (dali_extraction.py:171-173)
+    want = ref.reshape(2, 2, 3, 48, 80).reshape(2, 3, 2, 48, 80)
+    assert (enc.to_ncdhw()[:, :3] - want).abs().max() < 1e-4
+    with pytest.raises(RuntimeError, match="divisible by 16"):
+        ex.run(ex.input_buffer(1, 40, 52), ops.CLTensor(1, 1, 40, 52, engine.ENC_IN_CHANNELS, device="cpu"), 1)
 
 
 def test_executor_wiring_i3d_trunk_exact(monkeypatch):
