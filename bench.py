@@ -87,15 +87,98 @@ def synthetic_frames(seed, n_frames, hw):
     return torch.randint(0, 256, (n_frames, hw[0], hw[1], 3), generator=g, dtype=torch.uint8)
 
 
-def build_models(device):
+def build_models(device, fa_arch="unet", ft_arch="i3d"):
     """Random-init weights of the reference architecture (stock torch init of the boundary modules, seeded)."""
     import contextlib
     import io
+    import warnings
     from aux_code.model_loaders import load_fa_model, load_ft_model
     torch.manual_seed(0)
-    with contextlib.redirect_stdout(io.StringIO()):
-        fa, ft = load_fa_model(arch="unet"), load_ft_model(arch="i3d", num_classes=102)
+    with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        fa, ft = load_fa_model(arch=fa_arch), load_ft_model(arch=ft_arch, num_classes=102)
     return fa.to(device).eval(), ft.to(device).eval()
+
+
+def cudnn_reference_clips_per_s(device, batch_clips=8, steps=4):
+    """The existing-kernel bar on the SAME GPU: the reference architecture (UNet + InceptionI3d
+    .extract_features incl. the raw-reshape glue) run by stock PyTorch eager - cuDNN / ATen kernels, conv -> batch_norm
+    -> relu as separate calls like the reference modules, channels_last, cudnn.benchmark - in fp32 with TF32 allowed
+    and under torch.autocast(bfloat16).  The functional model is oracle/models.py with eval BatchNorm through
+    F.batch_norm (/root/reference does not exist on the GPU box); inputs are preprocessed float clips already in HBM.
+    A baseline leg like cpu_baseline: never on the measured path of this framework."""
+    from oracle import models as M
+    fa, ft = build_models("cpu")
+    sd_fa = {k: (v.to(device).contiguous(memory_format=torch.channels_last) if v.dim() == 4 else v.to(device)) for k, v in fa.state_dict().items()}
+    sd_ft = {k: (v.to(device).contiguous(memory_format=torch.channels_last_3d) if v.dim() == 5 else v.to(device)) for k, v in ft.state_dict().items()}
+    g = torch.Generator(device=device).manual_seed(3)
+    x = torch.rand((batch_clips, T, 3) + RESO, device=device, generator=g)
+    old = (torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, M.FUSED_BN)
+    torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, M.FUSED_BN = True, True, True, True
+    out = {"batch_clips": batch_clips, "unit": "clips/s",
+           "what": "stock PyTorch %s eager (cuDNN %s): UNet + InceptionI3d.extract_features, conv/batch_norm/relu as separate "
+                   "library calls, channels_last, cudnn.benchmark=True; float clips resident in HBM" % (torch.__version__, torch.backends.cudnn.version())}
+
+    def fwd():
+        frames = x.reshape(-1, 3, *RESO).contiguous(memory_format=torch.channels_last)
+        anon = M.unet_forward(sd_fa, frames).reshape(batch_clips, 3, T, *RESO)        # dali_extraction.py:171-173
+        return M.i3d_extract_features(sd_ft, anon.contiguous(memory_format=torch.channels_last_3d))
+
+    try:
+        for key, ctx in (("fp32_tf32", None), ("bf16_autocast", torch.autocast("cuda", dtype=torch.bfloat16))):
+            with torch.no_grad():
+                if ctx is not None:
+                    ctx.__enter__()
+                try:
+                    for _ in range(2):
+                        fwd()                                   # cudnn.benchmark autotuning + warm-up
+                    torch.cuda.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    for _ in range(steps):
+                        fwd()
+                    e1.record()
+                    torch.cuda.synchronize()
+                finally:
+                    if ctx is not None:
+                        ctx.__exit__(None, None, None)
+            out[key] = batch_clips * steps / (e0.elapsed_time(e1) / 1e3)
+    finally:
+        torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, M.FUSED_BN = old
+        del sd_fa, sd_ft, x
+        torch.cuda.empty_cache()
+    return out
+
+
+def dropin_batch1_clips_per_s(fa_model, ft_model, device, n_clips=24):
+    """What a reference user gets on day one: the loop body of dali_extraction.py:168-179 VERBATIM on the boundary
+    modules, one clip per iteration (params_feature_ex.py:4), fp32 tensors at every module boundary and the blocking
+    per-clip `.cpu().numpy()` + np.vstack of the reference."""
+    g = torch.Generator(device=device).manual_seed(5)
+    clips = [torch.rand((1, T, 3) + RESO, device=device, generator=g) for _ in range(4)]
+    vid_features = np.zeros(2048 if hasattr(ft_model, "i3d") else 1024)
+
+    def body(inputs, vid_features):
+        with torch.no_grad():
+            ori_bs, ori_t, ori_c, ori_h, ori_w = inputs.permute(0, 2, 1, 3, 4).shape
+            inputs = inputs.view(-1, inputs.shape[2], inputs.shape[3], inputs.shape[4])
+            inputs = fa_model(inputs).reshape(ori_bs, ori_t, ori_c, ori_h, ori_w)
+            try:
+                output = ft_model.extract_features(inputs)
+            except:  # noqa: E722  (the reference's own dispatch idiom)
+                output = ft_model.i3d.extract_features(inputs)
+            return np.vstack((vid_features, output.squeeze().cpu().numpy()))
+
+    for i in range(3):
+        body(clips[i % 4], vid_features)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(n_clips):
+        vid_features = body(clips[i % 4], vid_features)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    return {"value": n_clips / dt, "unit": "clips/s", "ms_per_clip": 1e3 * dt / n_clips, "clips": n_clips,
+            "what": "dali_extraction.py:168-179 verbatim, batch 1, blocking per-clip D2H + np.vstack"}
 
 
 def cpu_reference_clips_per_s(n_timed=3, threads=None):
@@ -119,6 +202,66 @@ def cpu_reference_clips_per_s(n_timed=3, threads=None):
             times.append(time.perf_counter() - t0)
     per_clip = float(np.mean(times[1:]))
     return 1.0 / per_clip, threads, f"{n_timed} clips of 16x240x320 uint8 frames, batch 1, fp32, after 1 warm-up"
+
+
+def sharded_dataset_run(ext_factory, device, rank, world, dist, n_videos=256, ncrops=10, seed=7):
+    """BASELINE configs[2]-shaped run of the REAL sharded driver (not replicas): `n_videos` synthetic variable-length
+    videos (log-uniform 64..2048 frames of 240x320 uint8, host memory) -> extract_dataset_distributed (LPT shards over
+    the ranks, 10-crop, snippets packed across videos, one .npy per video written by its owner, manifest gathered on the
+    host).  Frames come from a per-rank pinned pool (a video = a window of it) so that the synthetic generator is not
+    what is measured; H2D copies, preprocessing, both networks, D2H and the file writes are."""
+    import shutil
+    import tempfile
+    from tedspad_b200.extraction import extract_dataset_distributed, shard_videos
+    rs = np.random.RandomState(seed)
+    lengths = np.exp(rs.uniform(np.log(64), np.log(2048), n_videos)).astype(int)
+    pool_n = 2048
+    pool = synthetic_frames(2000 + rank, pool_n, SRC_HW).pin_memory()
+    offs = rs.randint(0, pool_n, n_videos)
+    videos = [(f"/synthetic/v{i:04d}_x264.mp4", int(n), (lambda i=i, n=n: pool[min(int(offs[i]), pool_n - int(n)):][:int(n)]))
+              for i, n in enumerate(lengths)]
+    shards = shard_videos([v[1] for v in videos], world)
+    loads = [int(sum(lengths[i] for i in s)) for s in shards]
+    snippets = int(sum(-(-int(n) // 32) for n in lengths))
+    folder = [tempfile.mkdtemp(prefix="tedspad_sharded_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None) if rank == 0 else None]
+    if dist is not None:
+        dist.broadcast_object_list(folder, src=0)
+    ext = ext_factory(ncrops)
+    # warm-up on a throw-away folder (buffer allocation for this crop count, plans)
+    warm = tempfile.mkdtemp(prefix="tedspad_warm_")
+    from tedspad_b200.extraction import extract_dataset
+    extract_dataset(ext, videos[:1], warm, 0, 1, log=lambda *_: None)
+    shutil.rmtree(warm, ignore_errors=True)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    t0 = time.perf_counter()
+    manifest = extract_dataset_distributed(ext, videos, folder[0], log=lambda *_: None)
+    e1.record()
+    torch.cuda.synchronize()
+    mine_s = time.perf_counter() - t0        # this rank's own shard (incl. the closing manifest gather)
+    ms = e0.elapsed_time(e1)
+    per_rank = [mine_s]
+    if dist is not None:
+        t = torch.tensor([ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine_s)
+    ok = len(manifest) == n_videos
+    if rank == 0:
+        first = np.load(os.path.join(folder[0], "v0000_x264.npy"))
+        ok = ok and first.shape == (-(-int(lengths[0]) // 32), ncrops, 1024) and first.dtype == np.float64
+        shutil.rmtree(folder[0], ignore_errors=True)
+    clip_forwards = snippets * ncrops
+    return {"value": clip_forwards / (ms / 1e3), "unit": "clips/s", "videos": n_videos, "snippets": snippets, "ncrops": ncrops,
+            "clip_forwards": clip_forwards, "seconds": ms / 1e3, "files_ok": bool(ok),
+            "lpt_imbalance_max_over_mean_frames": max(loads) / (sum(loads) / len(loads)),
+            "per_rank_seconds": [round(float(v), 3) for v in per_rank],
+            "what": "extract_dataset_distributed: log-uniform 64..2048-frame 240x320 videos from pinned host memory, 10-crop, "
+                    "LPT video shards, .npy per video; timed on the device, max over ranks"}
 
 
 def workload_config(batch_clips):
@@ -159,6 +302,8 @@ def main():
     ap.add_argument("--impl", default="tedspad_b200", choices=["tedspad_b200", "reference"])
     ap.add_argument("--batch-clips", type=int, default=BATCH_CLIPS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="headline line only (no cuDNN bar / other archs / sharded run)")
+    ap.add_argument("--sharded-videos", type=int, default=256)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -263,6 +408,24 @@ def main():
     n_conv = len(ops.CONV_EVENTS) // n_ev
     ops.CONV_EVENTS = None
 
+    # per-rank view of the same timed region (no collective on the data path: the slowest rank sets `value`)
+    ms_own = ms_total
+    ranks_info = None
+    if dist is not None:
+        own = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        own[0].record()
+        for i in range(args.steps):
+            step_resident(i)
+        own[1].record()
+        torch.cuda.synchronize()
+        ms_own = own[0].elapsed_time(own[1])
+        gathered = [None] * world
+        dist.all_gather_object(gathered, {"rank": rank, "ms_per_step": ms_own / args.steps, "sm_mhz": sampler.result()["sm_mhz"]})
+        per = [g["ms_per_step"] for g in gathered]
+        ranks_info = {"ms_per_step_min": min(per), "ms_per_step_mean": sum(per) / len(per), "ms_per_step_max": max(per),
+                      "per_rank": gathered, "note": "un-barriered per-rank loops run right after the timed region"}
+
     ms_step = ms_total / args.steps
     clips_per_s = world * B / (ms_step / 1e3)
     e2e_cps = world * B / (ms_e2e / args.steps / 1e3)
@@ -283,9 +446,39 @@ def main():
         "gpu_launches": launches,
         "clocks": sampler.result(),
     }
+    if ranks_info is not None:
+        line["ranks"] = ranks_info
+    if not args.no_extras:
+        def ext_factory(ncrops):
+            return SnippetExtractor(fa, ft, reso=RESO, batch_clips=B, ncrops=ncrops)
+        if world > 1:
+            line["sharded"] = sharded_dataset_run(ext_factory, device, rank, world, dist, n_videos=args.sharded_videos)
+            line["sharded"]["efficiency_vs_replicas"] = line["sharded"]["value"] / clips_per_s
+        else:
+            # other encoder / anonymizer pairs of the boundary, same step definition, fewer steps
+            archs = {}
+            for key, fa_arch, ft_arch in (("unet+largei3d", "unet", "largei3d"), ("unet++ +largei3d (reference scripts' default)", "unet++", "largei3d")):
+                fa2, ft2 = build_models(device, fa_arch, ft_arch)
+                ext2 = SnippetExtractor(fa2, ft2, reso=RESO, batch_clips=B)
+                for i in range(3):
+                    ext2.features_of_clips(dev_sets[i % 2], desc, (ch, cw))
+                k = max(3, args.steps // 2)
+                ms2 = timed(lambda i: ext2.features_of_clips(dev_sets[i % 2], desc, (ch, cw)), k)
+                archs[key] = {"value": B * k / (ms2 / 1e3), "unit": "clips/s", "ms_per_step": ms2 / k, "steps": k}
+                archs[key + " batch-1 drop-in loop"] = dropin_batch1_clips_per_s(fa2, ft2, device)
+                del ext2, fa2, ft2
+                torch.cuda.empty_cache()
+            line["other_archs"] = archs
+            del ext
+            fa.__dict__.pop("_tsp_executor", None); ft.__dict__.pop("_tsp_executor", None)
+            fa.__dict__.pop("_tsp_sig", None); ft.__dict__.pop("_tsp_sig", None)
+            torch.cuda.empty_cache()
+            line["cudnn_baseline"] = cudnn_reference_clips_per_s(device)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cps, threads, sample = cpu_reference_clips_per_s(n_timed=8)
-        line["cpu_baseline"] = {"value": cps, "unit": "clips/s", "cores": threads, "kind": "port", "sample": sample}
+        line["cpu_baseline"] = {"value": cps, "unit": "clips/s", "cores": threads, "kind": "port", "sample": sample,
+                                "note": "oracle port of the reference forward (the reference is Python/PyTorch; /root/reference "
+                                        "does not exist on the GPU box); pinned to the unmodified reference to 1e-6 by tests/test_oracle.py"}
     sys.stdout.flush()
     os.dup2(saved_stdout, 1)
     os.close(saved_stdout)

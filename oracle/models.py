@@ -153,6 +153,10 @@ def extra_params(arch, num_classes=102):
 
 
 # ----------------------------------------------------------------------------------- forward
+FUSED_BN = False   # True: eval-mode BatchNorm through F.batch_norm (what nn.BatchNorm does; one fused kernel on a GPU)
+#                    instead of the explicit formula below.  Set only by bench.py's cuDNN baseline leg.
+
+
 class _Ctx:
     """Forward context: state dict, optional BN calibration, optional activation taps."""
 
@@ -166,6 +170,9 @@ class _Ctx:
             dims = [0] + list(range(2, x.dim()))
             sd[prefix + ".running_mean"] = x.mean(dims).detach().clone()
             sd[prefix + ".running_var"] = x.var(dims, unbiased=True).detach().clone()
+        if FUSED_BN and not self.calibrate:
+            return F.batch_norm(x, sd[prefix + ".running_mean"], sd[prefix + ".running_var"], sd[prefix + ".weight"],
+                                sd[prefix + ".bias"], False, 0.0, eps)
         shape = [1, -1] + [1] * (x.dim() - 2)
         mean, var = sd[prefix + ".running_mean"].view(shape), sd[prefix + ".running_var"].view(shape)
         g, b = sd[prefix + ".weight"].view(shape), sd[prefix + ".bias"].view(shape)

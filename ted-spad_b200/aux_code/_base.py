@@ -20,6 +20,7 @@ class CudaModule(nn.Module):
 
     executor_cls = None
     executor_kwargs = {}
+    _serial = 0
 
     def _replicate_for_data_parallel(self):
         # nn.DataParallel (dali_extraction.py:126-141) broadcasts the parameters to per-device replicas whose
@@ -29,8 +30,28 @@ class CudaModule(nn.Module):
         raise RuntimeError(f"{type(self).__name__}: nn.DataParallel is not supported - run one process per GPU "
                            "(torchrun) and shard the video list with tedspad_b200.extraction.extract_dataset_distributed")
 
+    def __setattr__(self, name, value):
+        if isinstance(value, (nn.Module, nn.Parameter)):   # e.g. model.i3d.fc = nn.Linear(...) (model_loaders.py:194-195)
+            self.__dict__.pop("_tsp_tensors", None)
+        super().__setattr__(name, value)
+
+    def _apply(self, fn, *a, **k):
+        # .cuda() / .to() / .float(): parameters may be re-created - drop the cached tensor list
+        self.__dict__.pop("_tsp_tensors", None)
+        return super()._apply(fn, *a, **k)
+
     def _signature(self):
-        return tuple((k, v.data_ptr(), v._version, str(v.device)) for k, v in self.state_dict(keep_vars=True).items())
+        """Identity + in-place version of every parameter and buffer.  The tensor list is cached (walking the module
+        tree through state_dict() cost 0.5-0.7 ms per call, twice per clip in the batch-1 drop-in loop); it is rebuilt
+        whenever the number of registered tensors changes or _apply ran, and `_version` catches load_state_dict /
+        optimizer-style in-place updates."""
+        d = self.__dict__
+        ts = d.get("_tsp_tensors")
+        d["_tsp_calls"] = d.get("_tsp_calls", 0) + 1
+        if ts is None or d["_tsp_calls"] % 256 == 0:   # (periodic full walk: catches a swapped grand-child module)
+            ts = [v for _, v in self.state_dict(keep_vars=True).items()]
+            d["_tsp_tensors"] = ts
+        return tuple((v.data_ptr(), v._version) for v in ts) + (str(ts[0].device) if ts else "",)
 
     def _exec(self, x):
         if not (isinstance(x, torch.Tensor) and x.is_cuda):
@@ -45,9 +66,20 @@ class CudaModule(nn.Module):
         sig = self._signature()
         if getattr(self, "_tsp_sig", None) != sig:
             with torch.cuda.device(x.device):
-                self.__dict__["_tsp_executor"] = self.executor_cls(self.state_dict(), x.device, **self.executor_kwargs)
+                ex = self.executor_cls(self.state_dict(), x.device, **self.executor_kwargs)
+            CudaModule._serial += 1
+            ex.serial = CudaModule._serial      # identity of this weight snapshot (keys captured CUDA graphs)
+            self.__dict__["_tsp_executor"] = ex
             self.__dict__["_tsp_sig"] = sig
         return self.__dict__["_tsp_executor"]
+
+    def executor(self, device):
+        """The packed-weight executor for the current parameters on `device` (rebuilt when they changed)."""
+        return self._exec(torch.empty(1, device=device))
+
+    def _graphed(self, ex, key, fn):
+        """fn() over the executor's static buffers: eager on first use, a replayed CUDA graph afterwards."""
+        return ex.graphs.run(key, ex.bufs.generation, fn)
 
     def _to_cl(self, x, name="in"):
         """fp32 [B,3,T,H,W] / [N,3,H,W] -> channels-last bf16 [.., 4|8] (pad channels zero)."""

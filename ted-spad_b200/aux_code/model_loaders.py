@@ -172,8 +172,9 @@ class wrapper_r3d_18(CudaModule):
     def forward(self, x):
         ex = self._exec(x)
         with torch.cuda.device(x.device):
-            pred, feat = ex.run(self._to_cl(x))
-        return pred.clone(), feat.clone()
+            enc = self._to_cl(x)
+            pred, feat = self._graphed(ex, ("forward",) + tuple(x.shape), lambda: ex.run(enc))
+            return pred.clone(), feat.clone()
 
     def features_from_cl(self, enc_in):
         return self._exec(enc_in.buf).run(enc_in)[1].unsqueeze(1)

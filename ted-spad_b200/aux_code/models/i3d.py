@@ -59,8 +59,9 @@ class InceptionI3d(CudaModule):
     def extract_features(self, x):
         ex = self._exec(x)
         with torch.cuda.device(x.device):
-            feat = ex.run(self._to_cl(x))            # [B, T', 1024] fp32
-        return feat.permute(0, 2, 1).reshape(feat.shape[0], 1024, feat.shape[1], 1, 1)
+            enc = self._to_cl(x)
+            feat = self._graphed(ex, ("extract_features",) + tuple(x.shape), lambda: ex.run(enc))   # [B, T', 1024] fp32
+            return feat.permute(0, 2, 1).reshape(feat.shape[0], 1024, feat.shape[1], 1, 1).clone()
 
     def features_from_cl(self, enc_in):
         return self._exec(enc_in.buf).run(enc_in)

@@ -57,8 +57,9 @@ class I3Res50(CudaModule):
     def extract_features(self, x):
         ex = self._exec(x)
         with torch.cuda.device(x.device):
-            feat = ex.run(self._to_cl(x))  # [B,1,2048]
-        return feat.reshape(feat.shape[0], 2048, 1, 1, 1)
+            enc = self._to_cl(x)
+            feat = self._graphed(ex, ("extract_features",) + tuple(x.shape), lambda: ex.run(enc))  # [B,1,2048]
+            return feat.reshape(feat.shape[0], 2048, 1, 1, 1).clone()
 
     def features_from_cl(self, enc_in):
         return self._exec(enc_in.buf).run(enc_in)

@@ -31,9 +31,9 @@ class UNet(CudaModule):
             x0 = ex.input_buffer(n, h, w)
             self._fill(ex, x, x0)
             nhwc = ex.bufs.get("out_nhwc", n, 1, h, w, 8)
-            out = torch.empty((n, 3, h, w), device=x.device, dtype=torch.float32)
-            ex.run(x0, nhwc, T=1, frames_out=out)
-        return out
+            out = ex.bufs.raw("frames_out", (n, 3, h, w), torch.float32)
+            self._graphed(ex, ("forward", n, h, w), lambda: ex.run(x0, nhwc, T=1, frames_out=out))
+            return out.clone()
 
     @staticmethod
     def _fill(ex, x, x0):
@@ -46,5 +46,3 @@ class UNet(CudaModule):
         ex = self._exec(x0.buf)
         return ex.run(x0, enc_in, T=T)
 
-    def executor(self, device):
-        return self._exec(torch.empty(1, device=device))

@@ -93,14 +93,11 @@ class UnetPlusPlus(CudaModule):
             x0 = ex.input_buffer(n, h, w)
             ops.nchw_to_cl(x, x0)
             clip = ex.bufs.get("out_clip", n, 1, h, w, 4)
-            out = torch.empty((n, 3, h, w), device=x.device, dtype=torch.float32)
-            ex.run(x0, clip, T=1, frames_out=out)
-        return out
+            out = ex.bufs.raw("frames_out", (n, 3, h, w), torch.float32)
+            self._graphed(ex, ("forward", n, h, w), lambda: ex.run(x0, clip, T=1, frames_out=out))
+            return out.clone()
 
     def anonymize_into(self, x0, enc_in, T=16):
         """Fused path of the extraction driver: frames already in `ex.input_buffer` layout -> anonymized planes
         written straight into the encoder input through the raw-reshape glue (dali_extraction.py:171-173)."""
         return self._exec(x0.buf).run(x0, enc_in, T=T)
-
-    def executor(self, device):
-        return self._exec(torch.empty(1, device=device))

@@ -549,10 +549,11 @@ conv_slab_kernel(const __grid_constant__ SlabKParams p) {
   }
   if (warp == 10) {
     if (PAIR) {
-      // one warp of EACH CTA of the pair executes the collective cta_group::2 allocation; each passes its own slot
-      // (tmem_slot[rank]) so that the two instructions never name the same shared-memory word (compute-sanitizer
-      // racecheck otherwise reports the pair's two identical-value writes as a hazard)
-      tmem_alloc_pair(tmem_slot + rank, p.tmem_cols);
+      // one warp of EACH CTA of the pair executes the collective cta_group::2 allocation with the SAME shared-memory
+      // offset (per-rank slots were tried to silence compute-sanitizer racecheck, which reports the pair's two
+      // identical-value writes as a hazard: the hardware then leaves one CTA's slot unwritten -> misaligned-address
+      // trap in its epilogue.  The racecheck report on this line is a tool artefact, see profiles/r2_sanitizer.md)
+      tmem_alloc_pair(tmem_slot, p.tmem_cols);
       tmem_relinquish_pair();
     } else {
       tmem_alloc(tmem_slot, p.tmem_cols);
@@ -574,7 +575,7 @@ conv_slab_kernel(const __grid_constant__ SlabKParams p) {
   tc_fence_before();
   if (PAIR) cluster_sync_all(); else __syncthreads();   // PAIR: the peer's barriers are initialised before any remote arrive
   tc_fence_after();
-  const uint32_t tmem_base = tmem_slot[rank];
+  const uint32_t tmem_base = *tmem_slot;
   pdl_launch_dependents();   // the next kernel may start its prologue on SMs this grid has left (common.h)
 
   if (warp == 8) {

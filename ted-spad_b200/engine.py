@@ -36,6 +36,50 @@ ENC_IN_CHANNELS = 4 if USE_SLAB_STEM3D else 8   # channel padding of the encoder
 FUSE_UPSAMPLE_LEVELS = tuple(int(v) for v in os.environ.get("TEDSPAD_FUSE_UPSAMPLE", "").split(",") if v) if USE_SLAB else ()
 
 
+# CUDA graphs: a forward over fixed buffers is a fixed list of ~100 kernel launches whose host side (ctypes descriptors,
+# plans, tensor-map encodes, cudaLaunchKernelEx) costs 2-4 ms - more than the GPU needs for one clip.  The second call
+# with the same shapes captures the launches (programmatic-dependent-launch edges included) and every later call is
+# one cudaGraphLaunch.  TEDSPAD_GRAPHS=0 switches back to eager launches.
+USE_GRAPHS = os.environ.get("TEDSPAD_GRAPHS", "1") != "0"
+
+
+class GraphCache:
+    """key -> captured CUDA graph of a launch sequence over fixed device buffers.
+
+    run(key, gen, fn): `fn()` enqueues the launches on the current stream and returns its output tensor(s), which must
+    be the SAME device memory on every call (static buffers); `gen` is a hashable that changes whenever any buffer fn
+    touches may have moved (_Buffers.generation).  1st call with a key: eager.  2nd: capture + replay.  Later: replay."""
+
+    def __init__(self):
+        self.entries = {}
+
+    def run(self, key, gen, fn):
+        if not USE_GRAPHS or ops.CONV_EVENTS is not None or ops.OP_EVENTS is not None or torch.cuda.is_current_stream_capturing():
+            return fn()
+        ent = self.entries.get(key)
+        if ent is None or ent[0] != gen:
+            out = fn()                       # eager: allocates buffers, builds plans, opts kernels in to large smem
+            self.entries[key] = (gen, None, None, 1)
+            return out
+        _, graph, out, seen = ent
+        if graph is None:
+            graph = torch.cuda.CUDAGraph()
+            launches = ops.LAUNCHES
+            try:
+                with torch.cuda.graph(graph):
+                    out = fn()
+            except Exception:
+                ops.LAUNCHES = launches
+                self.entries[key] = (("eager-only", gen), None, None, 0)    # never matches: stays on eager launches
+                raise
+            self.entries[key] = (gen, graph, out, ops.LAUNCHES - launches)
+            ops.LAUNCHES = launches
+            seen = self.entries[key][3]
+        graph.replay()
+        ops.LAUNCHES += seen                 # kernels launched by the replay (bench.py's gpu_launches)
+        return out
+
+
 def slab3x3(pc, max_stream_cout=2048):
     """Best SLAB variant for a stride-1 same-padded (1|3) x (3x3 | 1x1) convolution with Cin % 64 == 0, or None:
     resident weights when they fit in shared memory (the 64-channel DoubleConv layers), streamed weight blocks
@@ -107,6 +151,7 @@ class _Buffers:
         self.device = device
         self.pool = {}      # name -> (spec, N allocated, CLTensor | torch.Tensor)
         self.views = {}     # (name, N) -> prefix view
+        self.generation = 0  # bumped by every (re)allocation: captured CUDA graphs over these buffers are then stale
 
     def get(self, name, N, D, H, W, C, halo=(0, 0, 0), dtype=ops.BF16, zero=False):
         """zero=True: cleared once at allocation (channel-padded buffers whose pad channels are never written)."""
@@ -120,6 +165,7 @@ class _Buffers:
                 del self.views[k]
             self.pool.pop(name, None)   # (freed before the replacement is allocated)
             ent = None
+            self.generation += 1
             t = CLTensor(N, D, H, W, C, halo, device=self.device, dtype=dtype)
             if zero:
                 t.buf.zero_()
@@ -135,6 +181,7 @@ class _Buffers:
         key = ("raw", name)
         ent = self.pool.get(key)
         if ent is None or ent[0] != (tuple(shape), dtype):
+            self.generation += 1
             ent = ((tuple(shape), dtype), 0, torch.empty(tuple(shape), device=self.device, dtype=dtype))
             self.pool[key] = ent
         return ent[2]
@@ -168,6 +215,7 @@ class UNetExecutor:
     def __init__(self, sd, device):
         self.device = device
         self.bufs = _Buffers(device)
+        self.graphs = GraphCache()
         self.convs = {}
         self.slabs = {}
 
@@ -284,6 +332,7 @@ class UNetPPExecutor:
     def __init__(self, sd, device):
         self.device = device
         self.bufs = _Buffers(device)
+        self.graphs = GraphCache()
 
         def mk(wk, bnk, stride=(1, 1, 1), pad=(0, 1, 1), cin_pad=None, perm=None):
             w = sd[wk]
@@ -406,6 +455,7 @@ class I3DExecutor:
     def __init__(self, sd, device):
         self.device = device
         self.bufs = _Buffers(device)
+        self.graphs = GraphCache()
         self.sd_w = {}
         self.specs = {}
 
@@ -549,6 +599,7 @@ class I3Res50Executor:
     def __init__(self, sd, device, prefix="i3d."):
         self.device = device
         self.bufs = _Buffers(device)
+        self.graphs = GraphCache()
         P = prefix
         def mk(wk, bnk, stride, pad, cin_pad=None):
             pc = PackedConv(sd[P + wk], None, _bn(sd, P + bnk, 1e-5), stride=stride, pad_front=pad, cin_pad=cin_pad,
@@ -603,6 +654,7 @@ class R3D18Executor:
     def __init__(self, sd, device):
         self.device = device
         self.bufs = _Buffers(device)
+        self.graphs = GraphCache()
         def mk(wk, bnk, stride, pad, cin_pad=None):
             pc = PackedConv(sd[wk], None, _bn(sd, bnk, 1e-5), stride=stride, pad_front=pad, cin_pad=cin_pad, device=device,
                             n_align=32)

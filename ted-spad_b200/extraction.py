@@ -96,6 +96,8 @@ class SnippetExtractor:
         self._copy_stream = None
         self._stage_bufs, self._stage_free = [None, None], [None, None]
         self._desc_ring, self._desc_i = [], 0   # pinned host staging of the per-image descriptors (+ device copy)
+        from .engine import GraphCache
+        self._graphs = GraphCache()
 
     def snippet_frames(self, n_frames):
         if self.source == "dali":
@@ -124,12 +126,14 @@ class SnippetExtractor:
         self._check_desc(desc_host, frames_dev.shape, crop_hw)
         with torch.cuda.device(self.device):
             desc = self._desc_to_device(desc_host)
-            ex_fa = self.fa.executor(self.device)
+            ex_fa, ex_ft = self.fa.executor(self.device), self.ft.executor(self.device)
             x0 = ex_fa.input_buffer(B * self.T, self.reso[0], self.reso[1])
             ops.preprocess(frames_dev, desc, crop_hw, x0, self.resample)
             enc_in = self._enc_in(B)
-            self.fa.anonymize_into(x0, enc_in, self.T)
-            return self.ft.features_from_cl(enc_in)
+            # anonymizer + glue + encoder over fixed buffers: ~100 launches, replayed as ONE CUDA graph per batch size
+            gen = (ex_fa.serial, ex_ft.serial, ex_fa.bufs.generation, ex_ft.bufs.generation, x0.buf.data_ptr(), enc_in.buf.data_ptr())
+            feats = self._graphs.run((B,), gen, lambda: self.ft.features_from_cl(self.fa.anonymize_into(x0, enc_in, self.T)))
+            return feats.clone()   # (the graph's output buffer is overwritten by the next batch)
 
     @staticmethod
     def _check_desc(desc, frames_shape, crop_hw):

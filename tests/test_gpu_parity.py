@@ -25,11 +25,14 @@ COS_GATE, ABS_GATE = 0.9995, 2e-2
 # Scale-free companions of the absolute gate (the absolute gate depends on the synthetic feature
 # scale).  REL_L2 = ||got - ref|| / ||ref|| (cos >= 0.9995 <=> <= 0.0316 for unbiased noise); REL_MAX = worst element
 # over the largest feature; TAP_REL = relative RMS error of every intermediate activation the executors keep, against
-# the oracle's taps of the same layer (a kernel bug shows up at ITS layer at the size of the signal, bf16 storage noise
-# stays at the 1e-2 level and grows slowly with depth).
+# the oracle's taps of the same layer.  Measured on B200 (profiles/r2_per_layer_errors.txt): bf16 storage noise starts at
+# 0.006-0.008 after the first convolution and grows SMOOTHLY with depth (x1.0-1.7 per layer; 0.024 at the UNet
+# bottleneck, 0.040 at Mixed_5c, 0.053 at I3Res50.layer4.0 after ~65 stacked convolutions).  A kernel bug shows up at
+# ITS layer at the size of the signal (0.1-1.0) and as a jump: gate = absolute cap + bounded growth per layer.
 REL_L2_GATE = 0.0316
 REL_MAX_GATE = {"i3d": 0.10, "largei3d": 0.03, "r3d_18": 0.03}
-TAP_REL_GATE = 0.03
+TAP_REL_GATE = 0.08
+TAP_GROWTH_GATE = (2.0, 0.004)     # err[layer] <= 2.0 * max(err of earlier layers) + 0.004
 
 
 def _modules(name, stress=False):
@@ -190,6 +193,10 @@ def test_hot_path_parity(name):
     print(f"{name}: per-layer relative RMS error: " + ", ".join(f"{k.split(':')[1]}={v:.4f}" for k, v in errs.items()))
     print(f"{name}: worst layer {worst} {errs[worst]:.4f} (gate {TAP_REL_GATE})")
     assert errs[worst] <= TAP_REL_GATE, (worst, errs[worst])
+    seen = 0.0
+    for k, v in errs.items():       # insertion order = network order
+        assert seen == 0.0 or v <= TAP_GROWTH_GATE[0] * seen + TAP_GROWTH_GATE[1], (k, v, seen)
+        seen = max(seen, v)
     assert ctrl < COS_GATE            # the gate can tell two clips apart ...
     assert dcos > 0.98                # ... and the response to changing the clip matches the reference's
     # no worse than the existing bf16 kernels on the same network
