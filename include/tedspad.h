@@ -267,6 +267,18 @@ int tedspad_outconv_sigmoid(const tedspad_tensor* x, const float* w, const float
 int tedspad_avgpool_features(const tedspad_tensor* x, int32_t kd, float* out, void* stream);
 
 /*
+ * The consumer's view of a feature matrix, computed on the device: what anomaly_detection_mgfn's
+ * Dataset.__getitem__ builds on the host from a loaded .npy (datasets/dataset.py:51-132, utils/utils.py:34-42).
+ * feats: fp32 [T][ncrops][F] (a [T][F] matrix is ncrops = 1: dataset.py:70-71 expand_dims).
+ *   train != 0: out fp32 [ncrops][seg][F+1]: every crop resampled to `seg` segments by process_feat (segment s = mean
+ *               of snippet rows bounds[s] .. bounds[s+1]-1, or the single row bounds[s] when empty; `bounds` = device
+ *               int32 [seg+1] = np.linspace(0, T, seg+1, dtype=int)), L2 magnitude of the segment row as column F.
+ *   train == 0: out fp32 [T][ncrops][F+1]: the rows and their L2 magnitude (test mode, dataset.py:68-86).
+ */
+int tedspad_mgfn_rows(const float* feats, int32_t T, int32_t ncrops, int32_t F, const int32_t* bounds, int32_t seg,
+                      int32_t train, float* out, void* stream);
+
+/*
  * Crop + resize + normalise decoded uint8 frames into the anonymizer's bf16 input layout.
  * Replaces DALIDataloader.val_augmentations (feature_extraction/dali_extraction.py:38-50) with
  * TEDSPAD_RESAMPLE_AA_FLOAT (antialiased bilinear on /255 floats) and

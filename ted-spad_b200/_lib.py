@@ -71,6 +71,7 @@ SYMBOLS = {
     "tedspad_frames_to_clip": (C.c_int, [_TP, _TP, _I, _V, _V]),
     "tedspad_outconv_sigmoid": (C.c_int, [_TP, _V, _V, _TP, _I, _V, _V]),
     "tedspad_avgpool_features": (C.c_int, [_TP, _I, _V, _V]),
+    "tedspad_mgfn_rows": (C.c_int, [_V, _I, _I, _I, _V, _I, _I, _V, _V]),
     "tedspad_preprocess": (C.c_int, [_V, _I, _I, _I, _V, _I, _I, _I, _TP, _I, _V, _V]),
     "tedspad_nchw_to_cl": (C.c_int, [_V, _I, _TP, _V]),
     "tedspad_abi_version": (C.c_int, []),

@@ -342,103 +342,177 @@ struct AvgP {
   TView x;
   int kd, OD;
   float* out;
+  long long total_warps;   // N * OD * (C / 8)
 };
 
-// one block per (n, od); thread -> 8 channels; loops over the kd*H*W window (coalesced 16-byte loads)
+// One WARP per (n, od, 8-channel group): the lanes split the kd*H*W window positions (98 for the [2,7,7] window of
+// i3d.py:293-294), each lane accumulates its positions' 8 channels from 16-byte loads, then five rounds of warp
+// shuffles reduce the 32 partial sums.  (The previous kernel walked the 98 positions serially in one thread per
+// channel group on N*OD blocks - 32 of the 148 SMs for a 32-clip batch.)
 __global__ void __launch_bounds__(256) avgpool_kernel(const AvgP p) {
   pdl_launch_dependents();   // programmatic dependent launch, see common.h
   pdl_wait();
-  const int n = blockIdx.x / p.OD, od = blockIdx.x - n * p.OD;
-  const float inv = 1.f / static_cast<float>(p.kd * p.x.H * p.x.W);
-  for (int c8 = threadIdx.x; c8 < (p.x.C >> 3); c8 += blockDim.x) {
+  const int lane = threadIdx.x & 31;
+  const int c8n = p.x.C >> 3;
+  const int hw = p.x.H * p.x.W, win = p.kd * hw;
+  const float inv = 1.f / static_cast<float>(win);
+  const long long wstride = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
+  for (long long wi = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5); wi < p.total_warps; wi += wstride) {
+    const int c8 = static_cast<int>(wi % c8n);
+    const long long t = wi / c8n;
+    const int od = static_cast<int>(t % p.OD), n = static_cast<int>(t / p.OD);
     float s[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) s[i] = 0.f;
-    for (int a = 0; a < p.kd; ++a)
-      for (int h = 0; h < p.x.H; ++h)
-        for (int w = 0; w < p.x.W; ++w) {
-          float f[8];
-          unpack8(__ldg(reinterpret_cast<const uint4*>(elem_ptr(p.x, pix_index(p.x, n, od + a, h, w), c8 * 8))), f);
+    for (int pos = lane; pos < win; pos += 32) {
+      const int a = pos / hw, r = pos - a * hw, h = r / p.x.W, w = r - h * p.x.W;
+      float f[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(elem_ptr(p.x, pix_index(p.x, n, od + a, h, w), c8 * 8))), f);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) s[i] += f[i];
-        }
-    float* o = p.out + (static_cast<long long>(n) * p.OD + od) * p.x.C + c8 * 8;
+      for (int i = 0; i < 8; ++i) s[i] += f[i];
+    }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = s[i] * inv;
+    for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s[i] += __shfl_xor_sync(0xffffffffu, s[i], off);
+    if (lane == 0) {
+      float4* o = reinterpret_cast<float4*>(p.out + (static_cast<long long>(n) * p.OD + od) * p.x.C + c8 * 8);
+      o[0] = make_float4(s[0] * inv, s[1] * inv, s[2] * inv, s[3] * inv);
+      o[1] = make_float4(s[4] * inv, s[5] * inv, s[6] * inv, s[7] * inv);
+    }
+  }
+}
+
+// ------------------------------------------- consumer-side view of a feature matrix (MGFN Dataset.__getitem__)
+struct MgfnP {
+  const float* feats;     // [T][ncrops][F] fp32
+  const int32_t* bounds;  // train: [seg + 1] segment boundaries (np.linspace(0, T, seg + 1, dtype=int)); test: unused
+  float* out;             // train: [ncrops][seg][F + 1]; test: [T][ncrops][F + 1]
+  int T, ncrops, F, seg, train;
+};
+
+// One block per output row.  train (dataset.py:87-99 + utils.py:34-42 process_feat): row (crop c, segment s) = mean of
+// snippet rows bounds[s] .. bounds[s+1]-1 of crop c (the single row bounds[s] when the segment is empty), then its L2
+// magnitude as column F.  test (dataset.py:68-86): row (t, c) = the snippet row and its magnitude.  The sum of squares
+// is reduced with warp shuffles, then across the block's warps through shared memory.
+__global__ void __launch_bounds__(256) mgfn_rows_kernel(const MgfnP p) {
+  __shared__ float warp_sums[8];
+  const int row = blockIdx.x;
+  int c, r0, r1;
+  float* o;
+  if (p.train) {
+    c = row / p.seg;
+    const int sgm = row - c * p.seg;
+    r0 = p.bounds[sgm]; r1 = p.bounds[sgm + 1];
+    if (r0 == r1) r1 = r0 + 1;
+    o = p.out + static_cast<long long>(row) * (p.F + 1);
+  } else {
+    const int t = row / p.ncrops;
+    c = row - t * p.ncrops;
+    r0 = t; r1 = t + 1;
+    o = p.out + static_cast<long long>(row) * (p.F + 1);
+  }
+  const float inv = 1.f / static_cast<float>(r1 - r0);
+  float sq = 0.f;
+  for (int f = threadIdx.x; f < p.F; f += blockDim.x) {
+    float acc = 0.f;
+    for (int r = r0; r < r1; ++r) acc += __ldg(p.feats + (static_cast<long long>(r) * p.ncrops + c) * p.F + f);
+    const float v = (r1 - r0) > 1 ? acc * inv : acc;
+    o[f] = v;
+    sq = fmaf(v, v, sq);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
+  if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = sq;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) tot += warp_sums[w];
+    o[p.F] = sqrtf(tot);
   }
 }
 
 // ----------------------------------------------------------------- preprocess
+// Crop + resize + normalise uint8 frames into the anonymizer's bf16 input (dali_extraction.py:38-50 /
+// shanghai_dl.py:27-40).  One block = one band of BH output rows of one output image:
+//   1. the block builds the resampling table of the x axis (Wo entries) and of ITS BH rows of the y axis;
+//   2. the source rows the band needs are staged in shared memory with coalesced 16-byte loads - as fp32 already
+//      divided by 255 (AA_FLOAT: every source byte is converted once, exactly, instead of once per tap through a
+//      bank-conflicting lookup table) or as raw bytes (PIL_U8: integer arithmetic);
+//   3. a thread per output pixel runs the 2-D taps out of shared memory (same operation order as torchvision's
+//      separable kernel: horizontal sum per source row, then the vertical sum) and writes ONE 16- or 8-byte pixel
+//      (3 real channels + zero padding to the 8 channels the UNet stem / 4 channels the 7x7 stems read).
 constexpr int PP_KMAX = 8;
 constexpr int PP_MAXOUT = 512;
+constexpr int PP_THREADS = 256;
 
 struct PrepP {
   const uint8_t* frames;
+  long long frames_bytes;
   int F, Hs, Ws;
   const int32_t* desc;
   int n_out, crop_h, crop_w, resample;
   TView y;
   float* frames_f32;
+  int BH, max_rows, pitch;   // output rows per block; staged source rows (bound); staged row pitch in elements
 };
 
-// Resampling tables for one axis, built by the block in shared memory.
+// One entry of a resampling table.
 // AA_FLOAT follows aten's _upsample_bilinear2d_aa (align_corners=False): support = max(scale,1),
 // taps j in [lo,hi) with w = 1 - |(j - center + 0.5)/support|, normalised.
 // PIL_U8 follows Pillow's precompute_coeffs + normalize_coeffs_8bpc (double weights -> 22-bit fixed).
-__device__ void build_axis_table(int in, int out, int resample, int* lo, int* cnt, float* wf, int* wi) {
-  for (int i = threadIdx.x; i < out; i += blockDim.x) {
-    if (resample == TEDSPAD_RESAMPLE_PIL_U8) {
-      const double scale = static_cast<double>(in) / out;
-      const double fscale = scale < 1.0 ? 1.0 : scale;
-      const double support = 1.0 * fscale;
-      const double center = (i + 0.5) * scale;
-      const double ss = 1.0 / fscale;
-      int xmin = static_cast<int>(center - support + 0.5);
-      if (xmin < 0) xmin = 0;
-      int xmax = static_cast<int>(center + support + 0.5);
-      if (xmax > in) xmax = in;
-      xmax -= xmin;
-      if (xmax > PP_KMAX) xmax = PP_KMAX;
-      double k[PP_KMAX];
-      double ww = 0.0;
-      for (int x = 0; x < xmax; ++x) {
-        double a = (x + xmin - center + 0.5) * ss;
-        if (a < 0.0) a = -a;
-        const double w = a < 1.0 ? 1.0 - a : 0.0;
-        k[x] = w;
-        ww += w;
-      }
-      for (int x = 0; x < xmax; ++x) {
-        if (ww != 0.0) k[x] /= ww;
-        const double v = k[x] * static_cast<double>(1 << 22);
-        wi[i * PP_KMAX + x] = static_cast<int>(k[x] < 0 ? -0.5 + v : 0.5 + v);
-      }
-      lo[i] = xmin;
-      cnt[i] = xmax;
-    } else {
-      const float scale = static_cast<float>(in) / static_cast<float>(out);
-      const float support = scale >= 1.f ? scale : 1.f;
-      const float invscale = scale >= 1.f ? 1.f / scale : 1.f;
-      const float center = scale * (i + 0.5f);
-      int xmin = static_cast<int>(center - support + 0.5f);
-      if (xmin < 0) xmin = 0;
-      int xmax = static_cast<int>(center + support + 0.5f);
-      if (xmax > in) xmax = in;
-      int n = xmax - xmin;
-      if (n > PP_KMAX) n = PP_KMAX;
-      float tot = 0.f;
-      for (int x = 0; x < n; ++x) {
-        float a = (x + xmin - center + 0.5f) * invscale;
-        if (a < 0.f) a = -a;
-        const float w = a < 1.f ? 1.f - a : 0.f;
-        wf[i * PP_KMAX + x] = w;
-        tot += w;
-      }
-      for (int x = 0; x < n; ++x)
-        if (tot != 0.f) wf[i * PP_KMAX + x] /= tot;
-      lo[i] = xmin;
-      cnt[i] = n;
+__device__ void axis_entry(int in, int out, int resample, int i, int* lo, int* cnt, float* wf, int* wi) {
+  if (resample == TEDSPAD_RESAMPLE_PIL_U8) {
+    const double scale = static_cast<double>(in) / out;
+    const double fscale = scale < 1.0 ? 1.0 : scale;
+    const double support = 1.0 * fscale;
+    const double center = (i + 0.5) * scale;
+    const double ss = 1.0 / fscale;
+    int xmin = static_cast<int>(center - support + 0.5);
+    if (xmin < 0) xmin = 0;
+    int xmax = static_cast<int>(center + support + 0.5);
+    if (xmax > in) xmax = in;
+    xmax -= xmin;
+    if (xmax > PP_KMAX) xmax = PP_KMAX;
+    double k[PP_KMAX];
+    double ww = 0.0;
+    for (int x = 0; x < xmax; ++x) {
+      double a = (x + xmin - center + 0.5) * ss;
+      if (a < 0.0) a = -a;
+      const double w = a < 1.0 ? 1.0 - a : 0.0;
+      k[x] = w;
+      ww += w;
     }
+    for (int x = 0; x < xmax; ++x) {
+      if (ww != 0.0) k[x] /= ww;
+      const double v = k[x] * static_cast<double>(1 << 22);
+      wi[x] = static_cast<int>(k[x] < 0 ? -0.5 + v : 0.5 + v);
+    }
+    *lo = xmin;
+    *cnt = xmax;
+  } else {
+    const float scale = static_cast<float>(in) / static_cast<float>(out);
+    const float support = scale >= 1.f ? scale : 1.f;
+    const float invscale = scale >= 1.f ? 1.f / scale : 1.f;
+    const float center = scale * (i + 0.5f);
+    int xmin = static_cast<int>(center - support + 0.5f);
+    if (xmin < 0) xmin = 0;
+    int xmax = static_cast<int>(center + support + 0.5f);
+    if (xmax > in) xmax = in;
+    int n = xmax - xmin;
+    if (n > PP_KMAX) n = PP_KMAX;
+    float tot = 0.f;
+    for (int x = 0; x < n; ++x) {
+      float a = (x + xmin - center + 0.5f) * invscale;
+      if (a < 0.f) a = -a;
+      const float w = a < 1.f ? 1.f - a : 0.f;
+      wf[x] = w;
+      tot += w;
+    }
+    for (int x = 0; x < n; ++x)
+      if (tot != 0.f) wf[x] /= tot;
+    *lo = xmin;
+    *cnt = n;
   }
 }
 
@@ -447,81 +521,131 @@ __device__ __forceinline__ int clip8_fixed(int v) {
   return v < 0 ? 0 : (v > 255 ? 255 : v);
 }
 
-// grid: (row bands, n_out); block: 256 threads; thread -> one output pixel (3 channels),
-// one 16-byte store of 8 bf16 channels (3 real + zeros).
-__global__ void __launch_bounds__(256) preprocess_kernel(const PrepP p) {
-  extern __shared__ uint8_t pp_smem[];
-  const int Ho = p.y.H, Wo = p.y.W;
+// b / 255.f, correctly rounded, without a division: q = b*r, one Newton step on the exact remainder (r = rn(1/255);
+// checked for all 256 bytes against IEEE division with exact rational arithmetic, tests/test_host.py)
+__device__ __forceinline__ float u8_over_255(uint32_t b) {
+  const float x = static_cast<float>(b), r = __uint_as_float(0x3b808081u);
+  const float q = x * r;
+  return fmaf(fmaf(-q, 255.f, x), r, q);
+}
+
+template <bool PIL>
+__global__ void __launch_bounds__(PP_THREADS) preprocess_kernel(const PrepP p) {
+  extern __shared__ __align__(16) uint8_t pp_smem[];
+  const int Ho = p.y.H, Wo = p.y.W, BH = p.BH;
   int* xlo = reinterpret_cast<int*>(pp_smem);
   int* xcnt = xlo + Wo;
   int* ylo = xcnt + Wo;
-  int* ycnt = ylo + Ho;
-  float* xwf = reinterpret_cast<float*>(ycnt + Ho);
+  int* ycnt = ylo + BH;
+  int* rsh = ycnt + BH;                                        // PIL: byte shift of every staged row
+  float* xwf = reinterpret_cast<float*>(rsh + p.max_rows);
   float* ywf = xwf + Wo * PP_KMAX;
   int* xwi = reinterpret_cast<int*>(xwf);
   int* ywi = reinterpret_cast<int*>(ywf);
-  float* lut = ywf + Ho * PP_KMAX;
-  build_axis_table(p.crop_w, Wo, p.resample, xlo, xcnt, xwf, xwi);
-  build_axis_table(p.crop_h, Ho, p.resample, ylo, ycnt, ywf, ywi);
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = static_cast<float>(i) / 255.f;
+  uint8_t* stage_raw = reinterpret_cast<uint8_t*>(ywf + BH * PP_KMAX);
+  stage_raw += (16 - (reinterpret_cast<uintptr_t>(stage_raw) & 15)) & 15;
+  float* stage_f = reinterpret_cast<float*>(stage_raw);
+
+  const int n = blockIdx.y;
+  const int oy0 = blockIdx.x * BH, nrow = min(BH, Ho - oy0);
+  for (int i = threadIdx.x; i < Wo; i += blockDim.x)
+    axis_entry(p.crop_w, Wo, p.resample, i, xlo + i, xcnt + i, xwf + i * PP_KMAX, xwi + i * PP_KMAX);
+  for (int i = threadIdx.x; i < nrow; i += blockDim.x)
+    axis_entry(p.crop_h, Ho, p.resample, oy0 + i, ylo + i, ycnt + i, ywf + i * PP_KMAX, ywi + i * PP_KMAX);
   pdl_launch_dependents();
   __syncthreads();
   pdl_wait();   // the tables above depend on the launch parameters only
 
-  const int n = blockIdx.y;
   const int32_t* d = p.desc + n * 4;
   const int src = d[0], top = d[1], left = d[2], flip = d[3];
-  const int band = (Ho * Wo + gridDim.x - 1) / gridDim.x;   // Ho, Wo <= PP_MAXOUT: 32-bit pixel arithmetic
-  const int p0 = blockIdx.x * band;
-  const int p1 = min(p0 + band, Ho * Wo);
-  const uint8_t* img = p.frames + static_cast<long long>(src < 0 ? 0 : src) * p.Hs * p.Ws * 3;
-  for (int q = p0 + threadIdx.x; q < p1; q += blockDim.x) {
-    const int oy = q / Wo, ox = q - oy * Wo;
+  const int r0 = ylo[0];
+  const int R = min(ylo[nrow - 1] + ycnt[nrow - 1] - r0, p.max_rows);
+  const int nb = p.crop_w * 3;                                 // bytes of one cropped source row
+  if (src >= 0) {
+    // stage rows [top + r0, top + r0 + R) x columns [col0, col0 + crop_w) (the mirrored window when flipped)
+    const int col0 = flip ? p.Ws - left - p.crop_w : left;
+    const int chunks = (nb + 15 + 15) >> 4;
+    const uint8_t* fend = p.frames + p.frames_bytes;
+    for (int it = threadIdx.x; it < R * chunks; it += blockDim.x) {
+      const int r = it / chunks, i = it - r * chunks;
+      const uint8_t* g = p.frames + ((static_cast<long long>(src) * p.Hs + top + r0 + r) * p.Ws + col0) * 3;
+      const int shift = static_cast<int>(reinterpret_cast<uintptr_t>(g) & 15);
+      const uint8_t* a = g - shift + 16 * i;
+      if (16 * i - shift >= nb) continue;
+      uint4 q;
+      if (a + 16 <= fend) {
+        q = __ldg(reinterpret_cast<const uint4*>(a));
+      } else {   // last bytes of the frame buffer: no read past its end
+        uint8_t* qb = reinterpret_cast<uint8_t*>(&q);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) qb[k] = (a + k < fend) ? a[k] : 0;
+      }
+      if (PIL) {
+        if (i == 0) rsh[r] = shift;
+        *reinterpret_cast<uint4*>(stage_raw + r * p.pitch + 16 * i) = q;
+      } else {
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+        float* dst = stage_f + r * p.pitch + 16 * i - shift;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const int idx = 16 * i - shift + k;
+          if (idx >= 0 && idx < nb) dst[k] = u8_over_255((w[k >> 2] >> (8 * (k & 3))) & 0xffu);
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  const int cpy = p.y.C;   // 8 (UNet stem) or 4 (7x7 stems) when vectorisable
+  const bool vec8 = cpy == 8 && ((p.y.ld | p.y.coff) & 7) == 0, vec4 = cpy == 4 && ((p.y.ld | p.y.coff) & 3) == 0;
+  for (int q = threadIdx.x; q < nrow * Wo; q += blockDim.x) {
+    const int ly = q / Wo, ox = q - ly * Wo, oy = oy0 + ly;
     float o[3] = {0.f, 0.f, 0.f};
     if (src >= 0) {
-      const int yl = ylo[oy], yn = ycnt[oy], xl = xlo[ox], xn = xcnt[ox];
-      if (p.resample == TEDSPAD_RESAMPLE_PIL_U8) {
+      const int yl = ylo[ly] - r0, yn = ycnt[ly], xl = xlo[ox], xn = xcnt[ox];
+      // staged column of tap b: xl + b, or mirrored inside the staged window when the crop comes from the flipped frame
+      const int j0 = flip ? p.crop_w - 1 - xl : xl, js = flip ? -3 : 3;
+      if (PIL) {
         int acc[3] = {1 << 21, 1 << 21, 1 << 21};
         for (int a = 0; a < yn; ++a) {
-          const uint8_t* rowp = img + static_cast<long long>(top + yl + a) * p.Ws * 3;
+          const uint8_t* rowp = stage_raw + (yl + a) * p.pitch + rsh[yl + a] + j0 * 3;
           int h[3] = {1 << 21, 1 << 21, 1 << 21};
           for (int b = 0; b < xn; ++b) {
-            const int cx = left + xl + b;
-            const uint8_t* px = rowp + (flip ? (p.Ws - 1 - cx) : cx) * 3;
+            const uint8_t* px = rowp + b * js;
             const int k = xwi[ox * PP_KMAX + b];
             h[0] += px[0] * k; h[1] += px[1] * k; h[2] += px[2] * k;
           }
-          const int ky = ywi[oy * PP_KMAX + a];
+          const int ky = ywi[ly * PP_KMAX + a];
           acc[0] += clip8_fixed(h[0]) * ky; acc[1] += clip8_fixed(h[1]) * ky; acc[2] += clip8_fixed(h[2]) * ky;
         }
 #pragma unroll
-        for (int c = 0; c < 3; ++c) o[c] = lut[clip8_fixed(acc[c])];
+        for (int c = 0; c < 3; ++c) o[c] = u8_over_255(static_cast<uint32_t>(clip8_fixed(acc[c])));
       } else {
         for (int a = 0; a < yn; ++a) {
-          const uint8_t* rowp = img + static_cast<long long>(top + yl + a) * p.Ws * 3;
-          const float wy = ywf[oy * PP_KMAX + a];
+          const float* rowp = stage_f + (yl + a) * p.pitch + j0 * 3;
+          const float wy = ywf[ly * PP_KMAX + a];
           float h[3] = {0.f, 0.f, 0.f};
           for (int b = 0; b < xn; ++b) {
-            const int cx = left + xl + b;
-            const uint8_t* px = rowp + (flip ? (p.Ws - 1 - cx) : cx) * 3;
+            const float* px = rowp + b * js;
             const float wx = xwf[ox * PP_KMAX + b];
-            h[0] = fmaf(wx, lut[px[0]], h[0]); h[1] = fmaf(wx, lut[px[1]], h[1]); h[2] = fmaf(wx, lut[px[2]], h[2]);
+            h[0] = fmaf(wx, px[0], h[0]); h[1] = fmaf(wx, px[1], h[1]); h[2] = fmaf(wx, px[2], h[2]);
           }
           o[0] = fmaf(wy, h[0], o[0]); o[1] = fmaf(wy, h[1], o[1]); o[2] = fmaf(wy, h[2], o[2]);
         }
       }
     }
-    float f[8] = {o[0], o[1], o[2], 0.f, 0.f, 0.f, 0.f, 0.f};
     __nv_bfloat16* yp = elem_ptr_w(p.y, pix_index(p.y, n, 0, oy, ox), 0);
-    if (p.y.C >= 8 && ((p.y.ld | p.y.coff) & 7) == 0) {
-      *reinterpret_cast<uint4*>(yp) = pack8(f);
-      for (int c = 8; c < p.y.C; ++c) yp[c] = __float2bfloat16_rn(0.f);
+    const uint32_t lo = cvt_bf16x2(o[0], o[1], false), hi = cvt_bf16x2(o[2], 0.f, false);
+    if (vec8) {
+      *reinterpret_cast<uint4*>(yp) = make_uint4(lo, hi, 0u, 0u);
+    } else if (vec4) {
+      *reinterpret_cast<uint2*>(yp) = make_uint2(lo, hi);
     } else {
-      for (int c = 0; c < p.y.C; ++c) yp[c] = __float2bfloat16_rn(c < 3 ? o[c] : 0.f);
+      for (int c = 0; c < cpy; ++c) yp[c] = __float2bfloat16_rn(c < 3 ? o[c] : 0.f);
     }
     if (p.frames_f32) {
       const long long plane = static_cast<long long>(Ho) * Wo;
-      float* fo = p.frames_f32 + static_cast<long long>(n) * 3 * plane + q;
+      float* fo = p.frames_f32 + static_cast<long long>(n) * 3 * plane + static_cast<long long>(oy) * Wo + ox;
       fo[0] = o[0]; fo[plane] = o[1]; fo[2 * plane] = o[2];
     }
   }
@@ -831,7 +955,21 @@ extern "C" int tedspad_avgpool_features(const tedspad_tensor* x, int32_t kd, flo
   TSP_CHECK(p.kd <= x->D, "avgpool: window %d larger than D=%d", p.kd, x->D);
   p.OD = x->D - p.kd + 1;
   p.out = out;
-  TSP_CUDA(launch_kernel(avgpool_kernel, dim3(x->N * p.OD), dim3(128), 0, reinterpret_cast<cudaStream_t>(stream), p));
+  TSP_CHECK((reinterpret_cast<uintptr_t>(out) & 15) == 0, "avgpool: out must be 16-byte aligned");
+  p.total_warps = static_cast<long long>(x->N) * p.OD * (x->C / 8);
+  TSP_CUDA(launch_kernel(avgpool_kernel, dim3(grid_for(p.total_warps * 32, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), p));
+  TSP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tedspad_mgfn_rows(const float* feats, int32_t T, int32_t ncrops, int32_t F, const int32_t* bounds, int32_t seg,
+                                 int32_t train, float* out, void* stream) {
+  TSP_CHECK(feats && out && T >= 1 && ncrops >= 1 && F >= 1, "mgfn_rows: bad arguments (T=%d ncrops=%d F=%d)", T, ncrops, F);
+  TSP_CHECK(!train || (bounds != nullptr && seg >= 1), "mgfn_rows: train mode needs the segment boundaries");
+  MgfnP p;
+  p.feats = feats; p.bounds = bounds; p.out = out; p.T = T; p.ncrops = ncrops; p.F = F; p.seg = seg; p.train = train;
+  const int rows = train ? ncrops * seg : T * ncrops;
+  TSP_CUDA(launch_kernel(mgfn_rows_kernel, dim3(rows), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), p));
   TSP_CUDA(cudaGetLastError());
   return 0;
 }
@@ -844,24 +982,36 @@ extern "C" int tedspad_preprocess(const uint8_t* frames, int32_t F, int32_t Hs, 
   TSP_CHECK(n_out >= 1 && y->N == n_out && y->D == 1 && y->C >= 3, "preprocess: y must be [n_out,1,Ho,Wo,>=3]");
   TSP_CHECK(y->H <= PP_MAXOUT && y->W <= PP_MAXOUT, "preprocess: output larger than %d", PP_MAXOUT);
   TSP_CHECK(resample == TEDSPAD_RESAMPLE_AA_FLOAT || resample == TEDSPAD_RESAMPLE_PIL_U8, "preprocess: bad resample");
-  TSP_CHECK(crop_h >= 1 && crop_w >= 1 && crop_h <= Hs && crop_w <= Ws, "preprocess: bad crop %dx%d of %dx%d", crop_h,
+  TSP_CHECK(crop_h >= 1 && crop_w >= 1 && crop_h <= Hs && crop_w <= Ws && F >= 1, "preprocess: bad crop %dx%d of %dx%d", crop_h,
             crop_w, Hs, Ws);
+  TSP_CHECK(y->C <= 8 || (y->C % 8 == 0), "preprocess: y.C=%d", y->C);
   const double sy = static_cast<double>(crop_h) / y->H, sx = static_cast<double>(crop_w) / y->W;
   TSP_CHECK(2 * static_cast<int>(ceil(sy < 1 ? 1 : sy)) + 1 <= PP_KMAX + 1 &&
                 2 * static_cast<int>(ceil(sx < 1 ? 1 : sx)) + 1 <= PP_KMAX + 1,
             "preprocess: down-scale factor too large for the %d-tap table", PP_KMAX);
+  const bool pil = resample == TEDSPAD_RESAMPLE_PIL_U8;
   PrepP p;
-  p.frames = frames; p.F = F; p.Hs = Hs; p.Ws = Ws; p.desc = desc; p.n_out = n_out;
+  p.frames = frames; p.frames_bytes = static_cast<long long>(F) * Hs * Ws * 3;
+  p.F = F; p.Hs = Hs; p.Ws = Ws; p.desc = desc; p.n_out = n_out;
   p.crop_h = crop_h; p.crop_w = crop_w; p.resample = resample;
   p.y = make_view(*y);
   p.frames_f32 = frames_f32;
-  const size_t smem = (2 * y->W + 2 * y->H) * sizeof(int) + (y->W + y->H) * PP_KMAX * sizeof(float) + 256 * sizeof(float);
-  // every block rebuilds the two resampling tables (~(H+W) entries): give it enough pixels to amortise that, but
-  // keep ~16 blocks per SM in the grid (a 512-frame batch gets 5 bands of ~10k pixels, a single clip 64 of 784)
-  const int want = (num_sms() * 16 + n_out - 1) / n_out;
-  const int bands = std::max(1, std::min(std::min(64, want), (y->H * y->W + 511) / 512));
-  dim3 grid(bands, n_out);
-  TSP_CUDA(launch_kernel(preprocess_kernel, grid, dim3(256), smem, reinterpret_cast<cudaStream_t>(stream), p));
+  // band height: as many output rows per block as keep the staged source rows + tables under 48 KB of shared memory
+  const int nb = crop_w * 3;
+  p.pitch = pil ? static_cast<int>(round_up(nb + 32, 16)) : nb + 1;
+  size_t smem = 0;
+  for (p.BH = 8; p.BH >= 1; p.BH >>= 1) {
+    p.max_rows = static_cast<int>(ceil((p.BH - 1) * sy + 2.0 * (sy < 1 ? 1 : sy) + 2.0));
+    if (p.max_rows > crop_h) p.max_rows = crop_h;
+    smem = (2 * y->W + 2 * p.BH + p.max_rows) * sizeof(int) + static_cast<size_t>(y->W + p.BH) * PP_KMAX * sizeof(float) + 16 +
+           static_cast<size_t>(p.max_rows) * p.pitch * (pil ? 1 : sizeof(float));
+    if (smem <= 48 * 1024) break;
+  }
+  TSP_CHECK(p.BH >= 1, "preprocess: a %d-pixel wide crop does not fit in shared memory", crop_w);
+  dim3 grid((y->H + p.BH - 1) / p.BH, n_out);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (pil) TSP_CUDA(launch_kernel(preprocess_kernel<true>, grid, dim3(PP_THREADS), smem, st, p));
+  else TSP_CUDA(launch_kernel(preprocess_kernel<false>, grid, dim3(PP_THREADS), smem, st, p));
   TSP_CUDA(cudaGetLastError());
   return 0;
 }

@@ -336,6 +336,11 @@ def group_ops():
         report("avgpool sliding D=4", out, ref, tol_rel=1e-5)
         out = ops.avgpool_features(ops.CLTensor.from_ncdhw(x), 0)
         report("avgpool global", out, bf(x).mean(dim=(2, 3, 4)).unsqueeze(1), tol_rel=1e-5)
+        x = torch.randn(5, 2048, 2, 7, 7, generator=g).to(DEV)       # I3Res50 head: sliced input, odd window count
+        wide = ops.CLTensor(5, 2, 7, 7, 2048 + 64, device=DEV)
+        wide.slice(64, 2048).interior()[...] = x.permute(0, 2, 3, 4, 1).to(torch.bfloat16)
+        out = ops.avgpool_features(wide.slice(64, 2048), 0)
+        report("avgpool global 2048 from a channel slice", out, bf(x).mean(dim=(2, 3, 4)).unsqueeze(1), tol_rel=1e-5)
     except Exception:
         RESULTS.append(("avgpool", False))
         print(f"[FAIL] avgpool: EXCEPTION\n{traceback.format_exc()}", flush=True)

@@ -552,3 +552,19 @@ def test_drop_in_reference_script_lines_unetpp_largei3d(tmp_path, monkeypatch):
     print(f"\nunet++ drop-in: anonymized err max={e.max():.4f}; features cos={m['cos']:.6f} max_abs={m['max_abs']:.4f}")
     assert row.shape == (2048,) and e.max() < 0.1
     assert m["cos"] >= COS_GATE and m["max_abs"] <= ABS_GATE, m
+
+
+@pytest.mark.parametrize("name", list(_cases.CONSUMER_CASES))
+def test_device_side_mgfn_consumer_matches_reference_getitem(name):
+    """tedspad_b200.consumer (process_feat + magnitude + [ncrops,T,F] layout on the device) against the
+    golden outputs of the reference's own Dataset.__getitem__ (tests/golden/consumer_v1.npz), fp32 tolerance 1e-6."""
+    from tedspad_b200 import consumer
+    G2 = np.load(_cases.CONSUMER_GOLDEN)
+    feats = torch.from_numpy(_cases.consumer_case_features(name)).cuda()      # float64, as the .npy files hold them
+    test_item = consumer.getitem_test(feats).cpu().numpy()
+    train_item = consumer.getitem_train(feats).cpu().numpy()
+    for got, want in ((test_item, G2[f"{name}/test"]), (train_item, G2[f"{name}/train"])):
+        assert got.shape == want.shape and got.dtype == np.float32
+        assert np.allclose(got, want, rtol=2e-6, atol=1e-6), float(np.abs(got - want).max())
+    with pytest.raises(RuntimeError, match="CUDA"):
+        consumer.getitem_test(torch.zeros(4, 8))

@@ -462,3 +462,22 @@ def test_data_parallel_is_rejected_explicitly():
     fa = load_fa_model(arch="unet")
     with pytest.raises(RuntimeError, match="one process per GPU"):
         fa._replicate_for_data_parallel()
+
+
+def test_u8_over_255_refinement_is_exact():
+    """csrc/ops.cu u8_over_255: q = b*r; q' = fma(fma(-q, 255, b), r, q) with r = rn(1/255) = 0x3b808081 equals the
+    IEEE division float(b)/255.f for all 256 bytes (exact rational arithmetic, correctly rounded at every step)."""
+    from fractions import Fraction
+
+    def rn(fr):
+        a = np.float32(float(fr))
+        cands = [np.nextafter(a, np.float32(-np.inf)), a, np.nextafter(a, np.float32(np.inf))]
+        return min(cands, key=lambda c: (abs(Fraction(float(c)) - fr), int(c.view(np.uint32)) & 1))
+
+    r = np.uint32(0x3b808081).view(np.float32)
+    assert rn(Fraction(1, 255)) == r
+    for b in range(256):
+        q = rn(Fraction(b) * Fraction(float(r)))
+        rem = rn(-Fraction(float(q)) * 255 + b)
+        q2 = rn(Fraction(float(rem)) * Fraction(float(r)) + Fraction(float(q)))
+        assert q2 == np.float32(b) / np.float32(255.0), b
