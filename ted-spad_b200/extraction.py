@@ -29,15 +29,28 @@ def dali_snippet_frames(n_frames, num_frames=16, stride=2):
     return out
 
 
-def shanghai_snippet_frames(n_frames, num_frames=16, fix_skip=2):
+def shanghai_snippet_frames(n_frames, num_frames=16, fix_skip=2, total_frames=None):
     """shanghai_dl.py:43-98: 1-based frame counter, keep when count % skip == 0, emit a clip when
-    count % (16*skip) == 0 (tail dropped); < 32 frames -> skip 1; < 16 frames -> last frame repeated."""
-    skip = 1 if n_frames < fix_skip * num_frames else fix_skip
+    count % (16*skip) == 0 (tail dropped); < 32 frames -> skip 1; < 16 frames -> last frame repeated.
+    `n_frames` = frames actually decoded; `total_frames` = the container's frame count, which is what the reference
+    bases the skip / repeat decisions on (cap.get(7), :50,59-64); None = the same number."""
+    total = n_frames if total_frames is None else int(total_frames)
+    skip = 1 if total < fix_skip * num_frames else fix_skip
     per = num_frames * skip
     full = n_frames // per
     out = [[i * per + skip * (j + 1) - 1 for j in range(num_frames)] for i in range(full)]
-    if 0 < n_frames < num_frames:
-        out.append(list(range(n_frames)) + [n_frames - 1] * (num_frames - n_frames))
+    if total < num_frames and n_frames > 0:
+        # repeat: the frame read at count == total is stacked until the clip holds 16 (shanghai_dl.py:84-94)
+        if n_frames < total:
+            raise RuntimeError(f"only {n_frames} of the {total} frames the container reports could be decoded "
+                               "(the reference's keep_frame is never set: the video 'could not process')")
+        left = list(range(full * per, n_frames))        # skip == 1 here: every decoded frame is kept
+        count = n_frames
+        while count % 16 != 0:
+            count += 1
+            left.append(total - 1)
+        if len(left) == num_frames:
+            out.append(left)
     return np.asarray(out, dtype=np.int64).reshape(-1, num_frames)
 
 
@@ -99,10 +112,10 @@ class SnippetExtractor:
         from .engine import GraphCache
         self._graphs = GraphCache()
 
-    def snippet_frames(self, n_frames):
+    def snippet_frames(self, n_frames, total_frames=None):
         if self.source == "dali":
             return dali_snippet_frames(n_frames, self.T, self.skip)
-        return shanghai_snippet_frames(n_frames, self.T, self.skip)
+        return shanghai_snippet_frames(n_frames, self.T, self.skip, total_frames)
 
     def _enc_in(self, B):
         """Encoder input clip [B,T,H,W,4|8]: one allocation for the largest batch seen, smaller batches (video tails)

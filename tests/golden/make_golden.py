@@ -112,6 +112,13 @@ def shanghai_index_golden():
             for gi, ii in zip(grey, idx):
                 assert all(abs((g - 10) / 2 - i) <= 1.5 for g, i in zip(gi, ii)), (gi, ii)
             res[f"shanghai_idx/{n}"] = np.asarray(idx, dtype=np.int64).reshape(-1, 16)
+            # the product's cv2 ingest + the oracle's Pillow restatement == the reference reader's clips, bit for bit
+            sys.path.insert(0, os.path.join(ROOT, "ted-spad_b200"))
+            from tedspad_b200 import ingest
+            frames, total = ingest.decode_video_cv2(path, pin=False)
+            for clip, ii in zip(full_vid, idx):
+                mine = np.stack([P.shanghai_augmentation(frames[i].numpy()) for i in ii])
+                assert np.array_equal(mine, clip.numpy()), n
             print(f"shanghai read_video n={n}: {len(idx)} clips; first {idx[0][:4] if idx else None}")
     return res
 

@@ -1,5 +1,5 @@
 """Per-launch timing table of one bench step (32 clips, UNet + I3D): CUDA events around every conv launch,
-and (under ncu) the launch list.  Usage: python tests/profile_step.py [batch_clips] [arch]"""
+and (under ncu) the launch list.  Usage: python tests/profile_step.py [batch_clips] [encoder arch] [anonymizer arch]"""
 import os
 import sys
 
@@ -14,13 +14,10 @@ from tedspad_b200 import ops  # noqa: E402
 from tedspad_b200.extraction import SnippetExtractor, crop_boxes  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
-ARCH = sys.argv[2] if len(sys.argv) > 2 else "i3d"
+ARCH = sys.argv[2] if len(sys.argv) > 2 else "i3d"       # e.g. largei3d (the encoder the reference scripts configure)
+FA_ARCH = sys.argv[3] if len(sys.argv) > 3 else "unet"   # or unet++ (the anonymizer the reference scripts configure)
 dev = torch.device("cuda", 0)
-fa, ft = bench.build_models(dev)
-if ARCH != "i3d":   # e.g. largei3d (the encoder the reference scripts configure) or r3d_18
-    from aux_code.model_loaders import load_ft_model
-    torch.manual_seed(0)
-    ft = load_ft_model(arch=ARCH, num_classes=102).to(dev).eval()
+fa, ft = bench.build_models(dev, FA_ARCH, ARCH)
 ext = SnippetExtractor(fa, ft, reso=bench.RESO, batch_clips=B)
 (ch, cw), boxes = crop_boxes(*bench.SRC_HW)
 desc = np.zeros((B * 16, 4), dtype=np.int32)
@@ -58,5 +55,5 @@ print("non-convolution launches (CUDA events, in-step):")
 for name, (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print(f"{ms:8.3f} ms  n={n:3d}  {name}")
 for a, b, name in ops.OP_EVENTS:
-    if name in ("upsample2x", "maxpool"):
+    if name in ("upsample2x", "maxpool", "upsample2x_nearest", "frames_to_clip"):
         print(f"   {a.elapsed_time(b):7.3f} ms {name}")

@@ -481,3 +481,43 @@ def test_u8_over_255_refinement_is_exact():
         rem = rn(-Fraction(float(q)) * 255 + b)
         q2 = rn(Fraction(float(rem)) * Fraction(float(r)) + Fraction(float(q)))
         assert q2 == np.float32(b) / np.float32(255.0), b
+
+
+def _write_mjpg(path, n, hw=(48, 64), bgr=(10, 90, 235)):
+    import cv2
+    wr = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"MJPG"), 25, (hw[1], hw[0]))
+    for i in range(n):
+        fr = np.empty((hw[0], hw[1], 3), dtype=np.uint8)
+        fr[..., 0], fr[..., 1], fr[..., 2] = bgr[0] + 3 * i, bgr[1], bgr[2] - 3 * i   # B ramps up, R down with the index
+        wr.write(fr)
+    wr.release()
+
+
+def test_cv2_ingest_decodes_every_frame_in_bgr_order(tmp_path):
+    """SURVEY 8f-2 (ShanghaiTech half): tedspad_b200.ingest.decode_video_cv2 = the decoding loop of
+    shanghai_dl.py:43-98 - all frames, in order, BGR untouched - and the snippet indexer fed with the container's
+    frame count reproduces the reference reader's clips (golden shanghai_idx/* came from its read_video)."""
+    from tedspad_b200 import ingest
+    G = _cases.golden()
+    for n in (10, 33, 70):
+        p = str(tmp_path / f"v{n}.avi")
+        _write_mjpg(p, n)
+        frames, total = ingest.decode_video_cv2(p)
+        assert frames.dtype == torch.uint8 and tuple(frames.shape) == (n, 48, 64, 3) and total == n
+        means = frames.float().mean(dim=(1, 2))                                  # [n, 3] in B, G, R order
+        ramp = torch.arange(n, dtype=torch.float32) * 3
+        # decoded in order, channel 0 is Blue (no RGB conversion); MJPG's chroma quantisation moves levels by a few units
+        assert float((means[:, 0] - (10 + ramp)).abs().max()) <= 6 and float((means[:, 2] - (235 - ramp)).abs().max()) <= 6
+        rgb, _ = ingest.decode_video_cv2(p, rgb=True)
+        assert torch.equal(rgb, frames.flip(-1))
+        idx = extraction.shanghai_snippet_frames(frames.shape[0], total_frames=total)
+        assert np.array_equal(idx, G[f"shanghai_idx/{n}"])
+    ds = ingest.cv2_dataset([str(tmp_path / "v70.avi"), str(tmp_path / "v33.avi")])
+    assert [d[1] for d in ds] == [70, 33] and tuple(ds[1][2]().shape) == (33, 48, 64, 3)
+    with pytest.raises(RuntimeError):
+        ingest.decode_video_cv2(str(tmp_path / "missing.avi"))
+    # container count and decodable frames may disagree: the reference decides skip / repeat on the container's number
+    assert extraction.shanghai_snippet_frames(40, total_frames=20).shape == (2, 16)       # skip 1 (total < 32): 40 // 16
+    assert extraction.shanghai_snippet_frames(12, total_frames=10).tolist()[0][-4:] == [9, 9, 9, 9]
+    with pytest.raises(RuntimeError, match="could not process"):
+        extraction.shanghai_snippet_frames(8, total_frames=10)
