@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define TEDSPAD_ABI_VERSION 6
+#define TEDSPAD_ABI_VERSION 7
 
 enum { TEDSPAD_ACT_NONE = 0, TEDSPAD_ACT_RELU = 1, TEDSPAD_ACT_SIGMOID = 2 };
 /* A-operand feed of the implicit GEMM: AUTO picks FLAT when legal. */
@@ -242,8 +242,11 @@ int tedspad_upsample2x_nearest(const tedspad_tensor* x, const tedspad_tensor* y,
  * encoder clip [B][T][H][W][4|8] through the raw-reshape glue of feature_extraction/dali_extraction.py:171-173
  * (plane 3t+c of clip b -> encoder channel (3t+c)/T, time (3t+c)%T); pad channels written as zero.  `frames_out`
  * (optional) receives the un-scattered fp32 frames [B*T][3][H][W], the fa_model return value.
+ * s2d != 0: x is the space-to-depth form [B*T][1][H/2][W/2][>=12] the UNet++ tail is computed in (channel
+ * (2*(h&1) + (w&1))*3 + c of low-resolution pixel (h/2, w/2) is colour c of pixel (h, w)).
  */
-int tedspad_frames_to_clip(const tedspad_tensor* x, const tedspad_tensor* y, int32_t T, float* frames_out, void* stream);
+int tedspad_frames_to_clip(const tedspad_tensor* x, const tedspad_tensor* y, int32_t T, int32_t s2d, float* frames_out,
+                           void* stream);
 
 /*
  * OutConv (1x1, C->3) + sigmoid + the anonymizer->encoder raw-reshape glue: plane p = 3*t + c of

@@ -461,7 +461,9 @@ struct PrepP {
 // AA_FLOAT follows aten's _upsample_bilinear2d_aa (align_corners=False): support = max(scale,1),
 // taps j in [lo,hi) with w = 1 - |(j - center + 0.5)/support|, normalised.
 // PIL_U8 follows Pillow's precompute_coeffs + normalize_coeffs_8bpc (double weights -> 22-bit fixed).
-__device__ void axis_entry(int in, int out, int resample, int i, int* lo, int* cnt, float* wf, int* wi) {
+// Weights of tap x are written at wf[x * ws] / wi[x * ws]: the tables are stored [tap][index] so that the threads of a
+// warp (consecutive output pixels) read consecutive words (an [index][tap] table is an 8-way bank conflict).
+__device__ void axis_entry(int in, int out, int resample, int i, int* lo, int* cnt, float* wf, int* wi, int ws) {
   if (resample == TEDSPAD_RESAMPLE_PIL_U8) {
     const double scale = static_cast<double>(in) / out;
     const double fscale = scale < 1.0 ? 1.0 : scale;
@@ -486,7 +488,7 @@ __device__ void axis_entry(int in, int out, int resample, int i, int* lo, int* c
     for (int x = 0; x < xmax; ++x) {
       if (ww != 0.0) k[x] /= ww;
       const double v = k[x] * static_cast<double>(1 << 22);
-      wi[x] = static_cast<int>(k[x] < 0 ? -0.5 + v : 0.5 + v);
+      wi[x * ws] = static_cast<int>(k[x] < 0 ? -0.5 + v : 0.5 + v);
     }
     *lo = xmin;
     *cnt = xmax;
@@ -506,11 +508,11 @@ __device__ void axis_entry(int in, int out, int resample, int i, int* lo, int* c
       float a = (x + xmin - center + 0.5f) * invscale;
       if (a < 0.f) a = -a;
       const float w = a < 1.f ? 1.f - a : 0.f;
-      wf[x] = w;
+      wf[x * ws] = w;
       tot += w;
     }
     for (int x = 0; x < n; ++x)
-      if (tot != 0.f) wf[x] /= tot;
+      if (tot != 0.f) wf[x * ws] /= tot;
     *lo = xmin;
     *cnt = n;
   }
@@ -549,9 +551,9 @@ __global__ void __launch_bounds__(PP_THREADS) preprocess_kernel(const PrepP p) {
   const int n = blockIdx.y;
   const int oy0 = blockIdx.x * BH, nrow = min(BH, Ho - oy0);
   for (int i = threadIdx.x; i < Wo; i += blockDim.x)
-    axis_entry(p.crop_w, Wo, p.resample, i, xlo + i, xcnt + i, xwf + i * PP_KMAX, xwi + i * PP_KMAX);
+    axis_entry(p.crop_w, Wo, p.resample, i, xlo + i, xcnt + i, xwf + i, xwi + i, Wo);
   for (int i = threadIdx.x; i < nrow; i += blockDim.x)
-    axis_entry(p.crop_h, Ho, p.resample, oy0 + i, ylo + i, ycnt + i, ywf + i * PP_KMAX, ywi + i * PP_KMAX);
+    axis_entry(p.crop_h, Ho, p.resample, oy0 + i, ylo + i, ycnt + i, ywf + i, ywi + i, BH);
   pdl_launch_dependents();
   __syncthreads();
   pdl_wait();   // the tables above depend on the launch parameters only
@@ -584,12 +586,16 @@ __global__ void __launch_bounds__(PP_THREADS) preprocess_kernel(const PrepP p) {
         if (i == 0) rsh[r] = shift;
         *reinterpret_cast<uint4*>(stage_raw + r * p.pitch + 16 * i) = q;
       } else {
+        // planar per row: [channel][column], so that the tap loads of a warp (consecutive output pixels, ~1.1 source
+        // columns apart) fall into consecutive banks (interleaved pixels were a 3-4-way conflict on every load)
         const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-        float* dst = stage_f + r * p.pitch + 16 * i - shift;
+        float* dst = stage_f + r * 3 * p.pitch;
+        const int idx0 = 16 * i - shift;
+        int col = idx0 >= 0 ? idx0 / 3 : -((2 - idx0) / 3), ch = idx0 - 3 * col;
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-          const int idx = 16 * i - shift + k;
-          if (idx >= 0 && idx < nb) dst[k] = u8_over_255((w[k >> 2] >> (8 * (k & 3))) & 0xffu);
+          if (idx0 + k >= 0 && idx0 + k < nb) dst[ch * p.pitch + col] = u8_over_255((w[k >> 2] >> (8 * (k & 3))) & 0xffu);
+          if (++ch == 3) { ch = 0; ++col; }
         }
       }
     }
@@ -604,31 +610,31 @@ __global__ void __launch_bounds__(PP_THREADS) preprocess_kernel(const PrepP p) {
     if (src >= 0) {
       const int yl = ylo[ly] - r0, yn = ycnt[ly], xl = xlo[ox], xn = xcnt[ox];
       // staged column of tap b: xl + b, or mirrored inside the staged window when the crop comes from the flipped frame
-      const int j0 = flip ? p.crop_w - 1 - xl : xl, js = flip ? -3 : 3;
+      const int j0 = flip ? p.crop_w - 1 - xl : xl, js = flip ? -1 : 1;   // in columns
       if (PIL) {
         int acc[3] = {1 << 21, 1 << 21, 1 << 21};
         for (int a = 0; a < yn; ++a) {
           const uint8_t* rowp = stage_raw + (yl + a) * p.pitch + rsh[yl + a] + j0 * 3;
           int h[3] = {1 << 21, 1 << 21, 1 << 21};
           for (int b = 0; b < xn; ++b) {
-            const uint8_t* px = rowp + b * js;
-            const int k = xwi[ox * PP_KMAX + b];
+            const uint8_t* px = rowp + b * js * 3;
+            const int k = xwi[b * Wo + ox];
             h[0] += px[0] * k; h[1] += px[1] * k; h[2] += px[2] * k;
           }
-          const int ky = ywi[ly * PP_KMAX + a];
+          const int ky = ywi[a * BH + ly];
           acc[0] += clip8_fixed(h[0]) * ky; acc[1] += clip8_fixed(h[1]) * ky; acc[2] += clip8_fixed(h[2]) * ky;
         }
 #pragma unroll
         for (int c = 0; c < 3; ++c) o[c] = u8_over_255(static_cast<uint32_t>(clip8_fixed(acc[c])));
       } else {
         for (int a = 0; a < yn; ++a) {
-          const float* rowp = stage_f + (yl + a) * p.pitch + j0 * 3;
-          const float wy = ywf[ly * PP_KMAX + a];
+          const float* rowp = stage_f + (yl + a) * 3 * p.pitch + j0;
+          const float wy = ywf[a * BH + ly];
           float h[3] = {0.f, 0.f, 0.f};
           for (int b = 0; b < xn; ++b) {
             const float* px = rowp + b * js;
-            const float wx = xwf[ox * PP_KMAX + b];
-            h[0] = fmaf(wx, px[0], h[0]); h[1] = fmaf(wx, px[1], h[1]); h[2] = fmaf(wx, px[2], h[2]);
+            const float wx = xwf[b * Wo + ox];
+            h[0] = fmaf(wx, px[0], h[0]); h[1] = fmaf(wx, px[p.pitch], h[1]); h[2] = fmaf(wx, px[2 * p.pitch], h[2]);
           }
           o[0] = fmaf(wy, h[0], o[0]); o[1] = fmaf(wy, h[1], o[1]); o[2] = fmaf(wy, h[2], o[2]);
         }
@@ -777,6 +783,7 @@ struct F2CP {
   TView y;          // [B][T][H][W][4|8]
   float* frames;    // optional fp32 [B*T][3][H][W]
   int T;
+  int s2d;          // x is [B*T][1][H/2][W/2][>=12]: channel (2*(h&1) + (w&1))*3 + c of pixel (h/2, w/2)
   long long total;  // B*T*H*W clip pixels
 };
 
@@ -794,10 +801,11 @@ __global__ void __launch_bounds__(256) frames_to_clip_kernel(const F2CP p) {
     const int te = static_cast<int>(t % p.T);
     const int b = static_cast<int>(t / p.T);
     uint16_t v[3];
+    const int xh = p.s2d ? h >> 1 : h, xw = p.s2d ? w >> 1 : w, xc = p.s2d ? (2 * (h & 1) + (w & 1)) * 3 : 0;
 #pragma unroll
     for (int ce = 0; ce < 3; ++ce) {
       const int pl = ce * p.T + te, tf = pl / 3, o = pl - 3 * tf;
-      v[ce] = __ldg(reinterpret_cast<const uint16_t*>(elem_ptr(p.x, pix_index(p.x, b * p.T + tf, 0, h, w), o)));
+      v[ce] = __ldg(reinterpret_cast<const uint16_t*>(elem_ptr(p.x, pix_index(p.x, b * p.T + tf, 0, xh, xw), xc + o)));
     }
     __nv_bfloat16* yp = elem_ptr_w(p.y, pix_index(p.y, b, te, h, w), 0);
     const uint32_t lo = static_cast<uint32_t>(v[0]) | (static_cast<uint32_t>(v[1]) << 16), hi = static_cast<uint32_t>(v[2]);
@@ -805,7 +813,7 @@ __global__ void __launch_bounds__(256) frames_to_clip_kernel(const F2CP p) {
     else *reinterpret_cast<uint4*>(yp) = make_uint4(lo, hi, 0u, 0u);
     if (p.frames != nullptr) {
       // the un-scattered frames (the fa_model return value): frame b*T + te, its own three colours
-      const __nv_bfloat16* xp = elem_ptr(p.x, pix_index(p.x, b * p.T + te, 0, h, w), 0);
+      const __nv_bfloat16* xp = elem_ptr(p.x, pix_index(p.x, b * p.T + te, 0, xh, xw), xc);
       float* fo = p.frames + (static_cast<long long>(b * p.T + te) * 3) * plane + static_cast<long long>(h) * p.y.W + w;
       fo[0] = __bfloat162float(xp[0]); fo[plane] = __bfloat162float(xp[1]); fo[2 * plane] = __bfloat162float(xp[2]);
     }
@@ -910,18 +918,19 @@ extern "C" int tedspad_upsample2x_nearest(const tedspad_tensor* x, const tedspad
   return 0;
 }
 
-extern "C" int tedspad_frames_to_clip(const tedspad_tensor* x, const tedspad_tensor* y, int32_t T, float* frames_out,
-                                      void* stream) {
+extern "C" int tedspad_frames_to_clip(const tedspad_tensor* x, const tedspad_tensor* y, int32_t T, int32_t s2d,
+                                      float* frames_out, void* stream) {
   TSP_CHECK(x && y, "frames_to_clip: null argument");
   if (check_tensor(*x, "frames_to_clip.x", 1) || check_tensor(*y, "frames_to_clip.y", 4)) return 1;
-  TSP_CHECK(x->C >= 3 && x->D == 1 && (y->C == 4 || y->C == 8) && y->ld % y->C == 0 && y->coff % y->C == 0,
-            "frames_to_clip: x needs >= 3 channels, y must be a [B,T,H,W,4|8] clip");
-  TSP_CHECK(T >= 1 && x->N % T == 0 && y->N == x->N / T && y->D == T && y->H == x->H && y->W == x->W,
+  const int f = s2d ? 2 : 1;
+  TSP_CHECK(x->C >= (s2d ? 12 : 3) && x->D == 1 && (y->C == 4 || y->C == 8) && y->ld % y->C == 0 && y->coff % y->C == 0,
+            "frames_to_clip: x needs >= %d channels, y must be a [B,T,H,W,4|8] clip", s2d ? 12 : 3);
+  TSP_CHECK(T >= 1 && x->N % T == 0 && y->N == x->N / T && y->D == T && y->H == f * x->H && y->W == f * x->W,
             "frames_to_clip: clip [%d,%d,%d,%d] does not match %d frames of T=%d", y->N, y->D, y->H, y->W, x->N, T);
   F2CP p;
   p.x = make_view(*x); p.y = make_view(*y);
-  p.frames = frames_out; p.T = T;
-  p.total = static_cast<long long>(x->N) * x->H * x->W;
+  p.frames = frames_out; p.T = T; p.s2d = s2d ? 1 : 0;
+  p.total = static_cast<long long>(x->N) * y->H * y->W;
   TSP_CUDA(launch_kernel(frames_to_clip_kernel, dim3(grid_for(p.total, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), p));
   TSP_CUDA(cudaGetLastError());
   return 0;
@@ -998,13 +1007,13 @@ extern "C" int tedspad_preprocess(const uint8_t* frames, int32_t F, int32_t Hs, 
   p.frames_f32 = frames_f32;
   // band height: as many output rows per block as keep the staged source rows + tables under 48 KB of shared memory
   const int nb = crop_w * 3;
-  p.pitch = pil ? static_cast<int>(round_up(nb + 32, 16)) : nb + 1;
+  p.pitch = pil ? static_cast<int>(round_up(nb + 32, 16)) : crop_w + 1;   // AA: three planes of `pitch` floats per row
   size_t smem = 0;
   for (p.BH = 8; p.BH >= 1; p.BH >>= 1) {
     p.max_rows = static_cast<int>(ceil((p.BH - 1) * sy + 2.0 * (sy < 1 ? 1 : sy) + 2.0));
     if (p.max_rows > crop_h) p.max_rows = crop_h;
     smem = (2 * y->W + 2 * p.BH + p.max_rows) * sizeof(int) + static_cast<size_t>(y->W + p.BH) * PP_KMAX * sizeof(float) + 16 +
-           static_cast<size_t>(p.max_rows) * p.pitch * (pil ? 1 : sizeof(float));
+           static_cast<size_t>(p.max_rows) * p.pitch * (pil ? 1 : 3 * sizeof(float));
     if (smem <= 48 * 1024) break;
   }
   TSP_CHECK(p.BH >= 1, "preprocess: a %d-pixel wide crop does not fit in shared memory", crop_w);

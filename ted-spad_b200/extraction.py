@@ -133,12 +133,13 @@ class SnippetExtractor:
             self._enc[B] = t
         return t
 
-    def features_of_clips(self, frames_dev, desc_host, crop_hw):
-        """frames_dev: cuda uint8 [F,H,W,3]; desc_host: int32 [B*T,4] numpy -> fp32 cuda [B, n_feat_rows, F]."""
+    def features_of_clips(self, frames_dev, desc_host, crop_hw, desc_dev=None):
+        """frames_dev: cuda uint8 [F,H,W,3]; desc_host: int32 [B*T,4] numpy -> fp32 cuda [B, n_feat_rows, F].
+        desc_dev: the same rows already on the device (features_stream ships them with the frames)."""
         B = desc_host.shape[0] // self.T
         self._check_desc(desc_host, frames_dev.shape, crop_hw)
         with torch.cuda.device(self.device):
-            desc = self._desc_to_device(desc_host)
+            desc = desc_dev if desc_dev is not None else self._desc_to_device(desc_host)
             ex_fa, ex_ft = self.fa.executor(self.device), self.ft.executor(self.device)
             x0 = ex_fa.input_buffer(B * self.T, self.reso[0], self.reso[1])
             ops.preprocess(frames_dev, desc, crop_hw, x0, self.resample)
@@ -184,13 +185,15 @@ class SnippetExtractor:
         slot[2].record()
         return dev
 
-    def _stage(self, frames, slot):
-        """Host frames -> one of two persistent device staging buffers, on the copy stream.  Returns the device view
-        and the event that marks its arrival.  (Fresh allocations per batch made the caching allocator cudaMalloc -
+    def _stage(self, frames, slot, desc_host=None):
+        """Host frames -> one of two persistent device staging buffers, on the copy stream.  Returns the device view,
+        the device copy of `desc_host` (shipped on the SAME stream right behind the frames: a pinned 8 KB copy issued
+        on the compute stream would queue on the copy engine behind the NEXT batch's 118 MB transfer and stall the
+        step by 2-5 ms) and the event that marks their arrival.  (Fresh allocations per batch made the caching allocator cudaMalloc -
         a device-wide synchronisation - whenever the previous batch's block was still in use.)"""
         chunks = list(frames) if isinstance(frames, (list, tuple)) else [frames]
         if all(c.is_cuda for c in chunks):
-            return (chunks[0] if len(chunks) == 1 else torch.cat(chunks, 0)).contiguous(), None
+            return (chunks[0] if len(chunks) == 1 else torch.cat(chunks, 0)).contiguous(), None, None
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
         chunks = [c.contiguous() for c in chunks]
@@ -213,9 +216,10 @@ class SnippetExtractor:
             for c in chunks:   # frame ranges of one or several videos, back to back in the staging buffer
                 dev[f0:f0 + c.shape[0]].copy_(c, non_blocking=True)
                 f0 += c.shape[0]
+            desc_dev = self._desc_to_device(desc_host) if desc_host is not None else None
             ev = torch.cuda.Event()
             ev.record(self._copy_stream)
-        return dev, ev
+        return dev, desc_dev, ev
 
     def features_stream(self, batches):
         """batches: iterable of (frames uint8 [F,H,W,3] on the host (pinned for a truly asynchronous copy) or on the
@@ -225,16 +229,16 @@ class SnippetExtractor:
         it = iter(batches)
         nxt = next(it, None)
         i = 0
-        staged = self._stage(nxt[0], 0) if nxt is not None else None
+        staged = self._stage(nxt[0], 0, nxt[1]) if nxt is not None else None
         while nxt is not None:
-            cur, (dev, ev) = nxt, staged
+            cur, (dev, desc_dev, ev) = nxt, staged
             nxt = next(it, None)
             if nxt is not None:
-                staged = self._stage(nxt[0], (i + 1) % 2)          # in flight while `cur` is computed
+                staged = self._stage(nxt[0], (i + 1) % 2, nxt[1])  # in flight while `cur` is computed
             compute = torch.cuda.current_stream(self.device)
             if ev is not None:
                 compute.wait_event(ev)
-            feats = self.features_of_clips(dev, cur[1], cur[2])
+            feats = self.features_of_clips(dev, cur[1], cur[2], desc_dev)
             if ev is not None:
                 done = torch.cuda.Event()
                 done.record(compute)

@@ -362,13 +362,15 @@ def upsample2x_nearest(x, y):
     return y
 
 
-def frames_to_clip(x, y, T, frames_out=None):
-    """channels-last anonymizer frames [B*T,1,H,W,>=3] -> encoder clip view y [B,T,H,W,4|8] (raw-reshape glue)."""
+def frames_to_clip(x, y, T, frames_out=None, s2d=False):
+    """channels-last anonymizer frames [B*T,1,H,W,>=3] (s2d: space-to-depth [B*T,1,H/2,W/2,>=12]) -> encoder clip view
+    y [B,T,H,W,4|8] (raw-reshape glue)."""
     xd, yd = x.desc(), y.desc()
     fo = frames_out.data_ptr() if frames_out is not None else None
     _count()
     with _timed("frames_to_clip"):
-        L.check(L.lib().tedspad_frames_to_clip(C.byref(xd), C.byref(yd), int(T), fo, _stream()), "tedspad_frames_to_clip")
+        L.check(L.lib().tedspad_frames_to_clip(C.byref(xd), C.byref(yd), int(T), int(s2d), fo, _stream()),
+                "tedspad_frames_to_clip")
     return y
 
 

@@ -189,8 +189,13 @@ def upsample2x_nearest(x, y):
     return y
 
 
-def frames_to_clip(x, y, T, frames_out=None):
-    fr = x.interior().float()[:, 0, :, :, :3].permute(0, 3, 1, 2).contiguous()   # [F,3,H,W]
+def frames_to_clip(x, y, T, frames_out=None, s2d=False):
+    if s2d:   # [F,h,w,(a,b,c)] -> [F,3,2h,2w]
+        v = x.interior().float()[:, 0, :, :, :12]
+        F_, h, w, _ = v.shape
+        fr = v.reshape(F_, h, w, 2, 2, 3).permute(0, 5, 1, 3, 2, 4).reshape(F_, 3, 2 * h, 2 * w).contiguous()
+    else:
+        fr = x.interior().float()[:, 0, :, :, :3].permute(0, 3, 1, 2).contiguous()   # [F,3,H,W]
     if frames_out is not None:
         frames_out.copy_(fr)
     y.interior()[...] = 0

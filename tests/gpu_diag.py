@@ -296,6 +296,16 @@ def group_ops():
             ops.frames_to_clip(xc, enc, T, out)
             report(f"frames_to_clip C={cpad}", enc.to_ncdhw()[:, :3], ref, tol_rel=0)
             report(f"frames_to_clip C={cpad} fp32 frames", out, bf(fr), tol_rel=0)
+            # the same frames handed over in space-to-depth form [B*T,1,H/2,W/2,16] (channel (2a+b)*3 + c)
+            s2d = fr.reshape(B * T, 3, H // 2, 2, W // 2, 2).permute(0, 2, 4, 3, 5, 1).reshape(B * T, H // 2, W // 2, 12)
+            xs = ops.CLTensor(B * T, 1, H // 2, W // 2, 16, (0, 1, 1), device=DEV)
+            xs.buf.fill_(7.0)
+            xs.interior()[:, 0, :, :, :12] = s2d.to(torch.bfloat16)
+            enc.buf.fill_(5.0)
+            out.fill_(9.0)
+            ops.frames_to_clip(xs, enc, T, out, s2d=True)
+            report(f"frames_to_clip s2d C={cpad}", enc.to_ncdhw()[:, :3], ref, tol_rel=0)
+            report(f"frames_to_clip s2d C={cpad} fp32 frames", out, bf(fr), tol_rel=0)
             okz = bool((enc.interior()[..., 3:] == 0).all())
             RESULTS.append((f"frames_to_clip C={cpad} pad", okz))
             print(f"[{'PASS' if okz else 'FAIL'}] frames_to_clip C={cpad}: pad channels zero")

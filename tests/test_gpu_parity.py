@@ -77,6 +77,23 @@ def _rel_l2(got, ref):
     return float((got - ref).norm() / ref.norm())
 
 
+def _depth_to_space(cl, C):
+    """CLTensor [N,1,h,w,>=4C] in space-to-depth form (channel (2a+b)*C + c) -> torch [N,C,2h,2w]."""
+    v = cl.to_ncdhw()[:, :4 * C, 0].cpu()                                 # [N,4C,h,w]
+    N, _, h, w = v.shape
+    return v.reshape(N, 2, 2, C, h, w).permute(0, 3, 4, 1, 5, 2).reshape(N, C, 2 * h, 2 * w)
+
+
+class _Dense:
+    """Adapter so that a plain [N,C,H,W] tensor passes through _tap_errors like a CLTensor."""
+
+    def __init__(self, t):
+        self.t = t
+
+    def to_ncdhw(self):
+        return self.t.unsqueeze(2)
+
+
 def _tap_errors(fa, ft, arch, taps_fa, taps_ft, B=1):
     """{layer: relative RMS error} of the activation buffers the executors keep after a run vs the oracle's taps."""
     from tedspad_b200.engine import UNetExecutor
@@ -103,7 +120,8 @@ def _tap_errors(fa, ft, arch, taps_fa, taps_ft, B=1):
                  "decoder.blocks.x_1_1.conv2": P4.slice(256, 64), "decoder.blocks.x_2_2.conv2": P2.slice(192, 64),
                  "decoder.blocks.x_0_1.conv2": ex_fa.bufs.find("x_0_1"), "decoder.blocks.x_1_2.conv2": P2.slice(128, 64),
                  "decoder.blocks.x_0_2.conv2": ex_fa.bufs.find("x_0_2"),
-                 "decoder.blocks.x_0_3.conv2": ex_fa.bufs.find("x_0_3").slice(0, 32), "out": ex_fa.bufs.find("head").slice(0, 3)}
+                 "decoder.blocks.x_0_3.conv2": _Dense(_depth_to_space(ex_fa.bufs.find("x_0_3"), 32)),
+                 "out": _Dense(_depth_to_space(ex_fa.bufs.find("head"), 3))}
         for k, b in where.items():
             pairs.append((f"unetpp:{k}", b, taps_fa[k]))
     if arch == "i3d":

@@ -210,8 +210,8 @@ def test_executor_wiring_unet_exact_odd_size(monkeypatch):
 
 def test_executor_wiring_unetpp_exact(monkeypatch):
     """fp32-storage emulation of the UNet++ executor (shared per-resolution concat buffers, permuted conv1 input
-    channels, slot E re-use, 32-channel tail stored as 64, 8-row head) against the oracle restatement of smp's
-    UnetPlusPlus, to fp32 round-off; non-square frame."""
+    channels, slot E re-use, the full-resolution tail + head computed at half resolution in space-to-depth form)
+    against the oracle restatement of smp's UnetPlusPlus, to fp32 round-off; non-square frame."""
     _emulated(monkeypatch, fp32=True)
     g = torch.Generator().manual_seed(11)
     x = torch.rand(4, 3, 48, 80, generator=g)
