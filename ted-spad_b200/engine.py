@@ -25,6 +25,10 @@ SLAB_1X1 = USE_SLAB and os.environ.get("TEDSPAD_SLAB_1X1", "1") != "0"
 PAD_SMALL_3X3 = USE_SLAB and os.environ.get("TEDSPAD_PAD_SMALL_3X3", "1") != "0"
 MERGE_1X1 = os.environ.get("TEDSPAD_MERGE_1X1", "1") != "0"  # Inception b0/b1a/b2a (same input) as one GEMM
 USE_STREAM_PAIR = USE_PAIR and os.environ.get("TEDSPAD_STREAM_PAIR", "1") != "0"
+# Inception blocks: the pool branch (reads the block input only) and the 5x5-slot branch on side streams next to the
+# heads GEMM / the 3x3 branch.  Inside a captured CUDA graph these are parallel branches (no host cost); the Mixed_4x /
+# 5x launches are 15-50 us kernels of 100-400 tiles that leave SMs idle in their tails.
+I3D_BRANCH_STREAMS = os.environ.get("TEDSPAD_I3D_BRANCH_STREAMS", "0") != "0"
 USE_SLAB_STEM3D = USE_SLAB and os.environ.get("TEDSPAD_SLAB_STEM3D", "1") != "0"
 SLAB_WEIGHT_LIMIT = 150 * 1024   # bytes of resident weights that still leave room for three slab stages
 ENC_IN_CHANNELS = 4 if USE_SLAB_STEM3D else 8   # channel padding of the encoder input clip
@@ -594,8 +598,18 @@ class I3DExecutor:
             t3 = self._pool(f"{name}.b3a", x, (3, 3, 3), (1, 1, 1))
             self._unit(f"{name}.b3b", t3, out=y.slice(oc[0] + oc[2] + oc[4], oc[5]))
 
-        # (running the four branches on side streams was measured on B200: no gain, the step is not latency-bound)
+        # (running the four branches on side streams was measured on B200 in round 1 with eager launches: no gain)
         heads = [y.slice(0, oc[0]), t1.slice(0, oc[1]), t2.slice(0, oc[3])]
+        fork = I3D_BRANCH_STREAMS and x.buf.is_cuda
+        if fork:
+            main = torch.cuda.current_stream()
+            if not hasattr(self, "_side"):
+                self._side = (torch.cuda.Stream(device=x.buf.device), torch.cuda.Stream(device=x.buf.device))
+            ev_x = torch.cuda.Event()
+            ev_x.record(main)
+            self._side[0].wait_event(ev_x)
+            with torch.cuda.stream(self._side[0]):
+                b3()                              # max-pool + 1x1x1: depends on the block input only
         if MERGE_1X1:
             # the three 1x1x1 convolutions that read x (i3d.py:144-148) as ONE GEMM over stacked weight rows: x crosses
             # L2->SM once instead of three times and two launches disappear per block
@@ -608,7 +622,17 @@ class I3DExecutor:
         else:
             for br, out in zip(("b0", "b1a", "b2a"), heads):
                 self._unit(f"{name}.{br}", x, out=out)
-        b1(); b2(); b3()
+        if fork:
+            ev_h = torch.cuda.Event()
+            ev_h.record(main)
+            self._side[1].wait_event(ev_h)
+            with torch.cuda.stream(self._side[1]):
+                b2()
+            b1()
+            main.wait_stream(self._side[0])
+            main.wait_stream(self._side[1])
+        else:
+            b1(); b2(); b3()
         return y
 
     def run_trunk(self, enc_in):

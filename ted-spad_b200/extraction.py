@@ -109,6 +109,7 @@ class SnippetExtractor:
         self._copy_stream = None
         self._stage_bufs, self._stage_free = [None, None], [None, None]
         self._desc_ring, self._desc_i = [], 0   # pinned host staging of the per-image descriptors (+ device copy)
+        self.h2d_bytes = 0                       # frame bytes staged host -> device so far (bench statistics)
         from .engine import GraphCache
         self._graphs = GraphCache()
 
@@ -198,6 +199,7 @@ class SnippetExtractor:
             self._copy_stream = torch.cuda.Stream(device=self.device)
         chunks = [c.contiguous() for c in chunks]
         n = sum(c.numel() for c in chunks)
+        self.h2d_bytes += n
         buf = self._stage_bufs[slot]
         if buf is None or buf.numel() < n:
             # allocated ON the copy stream (the stream that writes it); a block the caching allocator hands back from
@@ -246,6 +248,29 @@ class SnippetExtractor:
             i += 1
             yield feats
 
+    SPARSE_FRAME_BYTES = 400 * 1024   # per-frame copies pay off above this frame size (a copy call costs ~10 us)
+
+    def _needed_frames(self, frames, sn, base):
+        """Frames of `frames` a group of snippets `sn` (int64 [n, T], -1 = zero image) reads -> (chunks to stage, the
+        snippets' indices into the staged frames starting at `base`, number of staged frames).  Small frames: the
+        contiguous range [min, max] in one copy.  Large frames (480x856 ShanghaiTech: 1.2 MB each, of which the reader
+        keeps every second one, shanghai_dl.py:73): only the frames that are used, one copy per run of consecutive
+        frames - 20 instead of 38 MB of host->device traffic per clip, which at ~1000 clips/s is the difference between
+        fitting the PCIe link and saturating it."""
+        valid = sn[sn >= 0]
+        if not valid.size:
+            return [frames[0:1]], np.full(sn.shape, -1, dtype=np.int64), 1
+        f_lo, f_hi = int(valid.min()), int(valid.max()) + 1
+        frame_bytes = int(frames.shape[1]) * int(frames.shape[2]) * 3
+        uniq = np.unique(valid)
+        if frame_bytes < self.SPARSE_FRAME_BYTES or uniq.size > 0.75 * (f_hi - f_lo) or frames.is_cuda:
+            return [frames[f_lo:f_hi]], np.where(sn >= 0, sn - f_lo + base, -1), f_hi - f_lo
+        starts = np.flatnonzero(np.diff(uniq, prepend=uniq[0] - 2) != 1)          # first frame of every run
+        ends = np.append(starts[1:], uniq.size)
+        chunks = [frames[int(uniq[a]):int(uniq[b - 1]) + 1] for a, b in zip(starts, ends)]
+        pos = np.searchsorted(uniq, np.where(sn >= 0, sn, uniq[0]))
+        return chunks, np.where(sn >= 0, pos + base, -1), int(uniq.size)
+
     def extract_videos(self, videos):
         """videos: iterable of uint8 [F,H,W,3] tensors or of callables returning them.  Yields (index, features) in
         input order, features as extract_video returns them.  Snippets are packed into full batches ACROSS videos
@@ -281,16 +306,15 @@ class SnippetExtractor:
                 while s0 < snips.shape[0]:
                     take = min(per_batch - count, snips.shape[0] - s0)
                     sn = snips[s0:s0 + take]
-                    valid = sn[sn >= 0]
-                    f_lo, f_hi = (int(valid.min()), int(valid.max()) + 1) if valid.size else (0, 1)
+                    parts, rel, n_staged = self._needed_frames(frames, sn, base)
                     desc = np.empty((take, len(boxes), self.T, 4), dtype=np.int32)
-                    desc[..., 0] = np.where(sn >= 0, sn - f_lo + base, -1)[:, None, :]
+                    desc[..., 0] = rel[:, None, :]
                     for ci, (t, l, fl) in enumerate(boxes):
                         desc[:, ci, :, 1], desc[:, ci, :, 2], desc[:, ci, :, 3] = t, l, fl
-                    chunks.append(frames[f_lo:f_hi])
+                    chunks.extend(parts)
                     descs.append(desc.reshape(-1, 4))
                     meta.append((rec, take))
-                    base += f_hi - f_lo
+                    base += n_staged
                     count += take
                     s0 += take
                     if count == per_batch:
@@ -330,13 +354,12 @@ class SnippetExtractor:
         def batches():
             for s0 in range(0, n_snip, per_batch):
                 sn = snips[s0:s0 + per_batch]
-                valid = sn[sn >= 0]
-                f_lo, f_hi = (int(valid.min()), int(valid.max()) + 1) if valid.size else (0, 1)
+                parts, rel, _ = self._needed_frames(frames, sn, 0)
                 desc = np.empty((sn.shape[0], len(boxes), self.T, 4), dtype=np.int32)
-                desc[..., 0] = np.where(sn >= 0, sn - f_lo, -1)[:, None, :]
+                desc[..., 0] = rel[:, None, :]
                 for ci, (t, l, fl) in enumerate(boxes):
                     desc[:, ci, :, 1], desc[:, ci, :, 2], desc[:, ci, :, 3] = t, l, fl
-                yield frames[f_lo:f_hi], desc.reshape(-1, 4), crop_hw
+                yield parts, desc.reshape(-1, 4), crop_hw
 
         rows = [f.reshape(-1, len(boxes), f.shape[-1] * f.shape[-2]).clone() for f in self.features_stream(batches())]
         if not rows:
