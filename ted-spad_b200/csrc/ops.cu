@@ -434,14 +434,19 @@ __global__ void __launch_bounds__(256) mgfn_rows_kernel(const MgfnP p) {
 
 // ----------------------------------------------------------------- preprocess
 // Crop + resize + normalise uint8 frames into the anonymizer's bf16 input (dali_extraction.py:38-50 /
-// shanghai_dl.py:27-40).  One block = one band of BH output rows of one output image:
-//   1. the block builds the resampling table of the x axis (Wo entries) and of ITS BH rows of the y axis;
-//   2. the source rows the band needs are staged in shared memory with coalesced 16-byte loads - as fp32 already
-//      divided by 255 (AA_FLOAT: every source byte is converted once, exactly, instead of once per tap through a
-//      bank-conflicting lookup table) or as raw bytes (PIL_U8: integer arithmetic);
-//   3. a thread per output pixel runs the 2-D taps out of shared memory (same operation order as torchvision's
-//      separable kernel: horizontal sum per source row, then the vertical sum) and writes ONE 16- or 8-byte pixel
+// shanghai_dl.py:27-40).  One block = one band of BH output rows of one output image; a thread owns one output COLUMN:
+//   1. every thread computes the resampling entry of its column in registers (start, KX weights), the first BH threads
+//      those of the band's rows (shared memory);
+//   2. the source rows the band needs are staged as raw bytes with coalesced 16-byte loads;
+//   3. horizontal pass: for every staged row the thread interpolates its column (KX taps x 3 channels; AA_FLOAT:
+//      fp32 FMAs over the bytes in torchvision's tap order, the /255 applied to the sum; PIL_U8: Pillow's 22-bit
+//      fixed point, rounded to 8 bits) into a [row][channel][column] plane in shared memory;
+//   4. vertical pass: the thread walks down its column, KY taps per output row, and writes ONE 16- or 8-byte pixel
 //      (3 real channels + zero padding to the 8 channels the UNet stem / 4 channels the 7x7 stems read).
+// The separable form does each horizontal interpolation once per source row instead of once per output row that
+// touches it, there is no integer division and no table lookup in the loops, and tap counts are compile-time
+// (weights beyond a column's real tap count are zero, their indices clamped): ncu on the round-1 kernel and on the
+// first staged version showed both ISSUE-bound (86 % issue-active, 345 M warp instructions for 25.7 M pixels).
 constexpr int PP_KMAX = 8;
 constexpr int PP_MAXOUT = 512;
 constexpr int PP_THREADS = 256;
@@ -454,16 +459,17 @@ struct PrepP {
   int n_out, crop_h, crop_w, resample;
   TView y;
   float* frames_f32;
-  int BH, max_rows, pitch;   // output rows per block; staged source rows (bound); staged row pitch in elements
+  int BH, max_rows, pitch;   // output rows per block; staged source rows (bound); staged row pitch in bytes
 };
 
-// One entry of a resampling table.
+// One entry of a resampling table: first tap, tap count, K weights (zero beyond the count).
 // AA_FLOAT follows aten's _upsample_bilinear2d_aa (align_corners=False): support = max(scale,1),
 // taps j in [lo,hi) with w = 1 - |(j - center + 0.5)/support|, normalised.
 // PIL_U8 follows Pillow's precompute_coeffs + normalize_coeffs_8bpc (double weights -> 22-bit fixed).
-// Weights of tap x are written at wf[x * ws] / wi[x * ws]: the tables are stored [tap][index] so that the threads of a
-// warp (consecutive output pixels) read consecutive words (an [index][tap] table is an 8-way bank conflict).
-__device__ void axis_entry(int in, int out, int resample, int i, int* lo, int* cnt, float* wf, int* wi, int ws) {
+template <int K>
+__device__ __forceinline__ void axis_entry(int in, int out, int resample, int i, int& lo, int& cnt, float (&wf)[K], int (&wi)[K]) {
+#pragma unroll
+  for (int x = 0; x < K; ++x) { wf[x] = 0.f; wi[x] = 0; }
   if (resample == TEDSPAD_RESAMPLE_PIL_U8) {
     const double scale = static_cast<double>(in) / out;
     const double fscale = scale < 1.0 ? 1.0 : scale;
@@ -475,23 +481,25 @@ __device__ void axis_entry(int in, int out, int resample, int i, int* lo, int* c
     int xmax = static_cast<int>(center + support + 0.5);
     if (xmax > in) xmax = in;
     xmax -= xmin;
-    if (xmax > PP_KMAX) xmax = PP_KMAX;
-    double k[PP_KMAX];
+    if (xmax > K) xmax = K;
+    double k[K];
     double ww = 0.0;
-    for (int x = 0; x < xmax; ++x) {
+#pragma unroll
+    for (int x = 0; x < K; ++x) {
       double a = (x + xmin - center + 0.5) * ss;
       if (a < 0.0) a = -a;
-      const double w = a < 1.0 ? 1.0 - a : 0.0;
+      const double w = (x < xmax && a < 1.0) ? 1.0 - a : 0.0;
       k[x] = w;
       ww += w;
     }
-    for (int x = 0; x < xmax; ++x) {
+#pragma unroll
+    for (int x = 0; x < K; ++x) {
       if (ww != 0.0) k[x] /= ww;
       const double v = k[x] * static_cast<double>(1 << 22);
-      wi[x * ws] = static_cast<int>(k[x] < 0 ? -0.5 + v : 0.5 + v);
+      wi[x] = x < xmax ? static_cast<int>(k[x] < 0 ? -0.5 + v : 0.5 + v) : 0;
     }
-    *lo = xmin;
-    *cnt = xmax;
+    lo = xmin;
+    cnt = xmax;
   } else {
     const float scale = static_cast<float>(in) / static_cast<float>(out);
     const float support = scale >= 1.f ? scale : 1.f;
@@ -502,19 +510,21 @@ __device__ void axis_entry(int in, int out, int resample, int i, int* lo, int* c
     int xmax = static_cast<int>(center + support + 0.5f);
     if (xmax > in) xmax = in;
     int n = xmax - xmin;
-    if (n > PP_KMAX) n = PP_KMAX;
+    if (n > K) n = K;
     float tot = 0.f;
-    for (int x = 0; x < n; ++x) {
+#pragma unroll
+    for (int x = 0; x < K; ++x) {
       float a = (x + xmin - center + 0.5f) * invscale;
       if (a < 0.f) a = -a;
-      const float w = a < 1.f ? 1.f - a : 0.f;
-      wf[x * ws] = w;
-      tot += w;
+      const float w = (x < n && a < 1.f) ? 1.f - a : 0.f;
+      wf[x] = w;
+      if (x < n) tot += w;       // (summed in tap order, like aten)
     }
-    for (int x = 0; x < n; ++x)
-      if (tot != 0.f) wf[x * ws] /= tot;
-    *lo = xmin;
-    *cnt = n;
+#pragma unroll
+    for (int x = 0; x < K; ++x)
+      if (tot != 0.f && x < n) wf[x] /= tot;
+    lo = xmin;
+    cnt = n;
   }
 }
 
@@ -531,29 +541,35 @@ __device__ __forceinline__ float u8_over_255(uint32_t b) {
   return fmaf(fmaf(-q, 255.f, x), r, q);
 }
 
-template <bool PIL>
+// float(b) for a byte: 2^23 + b is exact in fp32 (OR the byte into the mantissa of 2^23), minus 2^23
+__device__ __forceinline__ float u8_to_float(uint32_t b) { return __uint_as_float(0x4b000000u | b) - 8388608.f; }
+
+template <bool PIL, int KX, int KY>
 __global__ void __launch_bounds__(PP_THREADS) preprocess_kernel(const PrepP p) {
   extern __shared__ __align__(16) uint8_t pp_smem[];
   const int Ho = p.y.H, Wo = p.y.W, BH = p.BH;
-  int* xlo = reinterpret_cast<int*>(pp_smem);
-  int* xcnt = xlo + Wo;
-  int* ylo = xcnt + Wo;
-  int* ycnt = ylo + BH;
-  int* rsh = ycnt + BH;                                        // PIL: byte shift of every staged row
-  float* xwf = reinterpret_cast<float*>(rsh + p.max_rows);
-  float* ywf = xwf + Wo * PP_KMAX;
-  int* xwi = reinterpret_cast<int*>(xwf);
+  int* ylo = reinterpret_cast<int*>(pp_smem);                   // [BH + 1]: first source row per output row, then the band's end
+  int* rsh = ylo + BH + 1;                                      // byte shift of every staged row
+  float* ywf = reinterpret_cast<float*>(rsh + p.max_rows);      // [KY][BH]
   int* ywi = reinterpret_cast<int*>(ywf);
-  uint8_t* stage_raw = reinterpret_cast<uint8_t*>(ywf + BH * PP_KMAX);
-  stage_raw += (16 - (reinterpret_cast<uintptr_t>(stage_raw) & 15)) & 15;
-  float* stage_f = reinterpret_cast<float*>(stage_raw);
+  uint8_t* raw = reinterpret_cast<uint8_t*>(ywf + KY * BH);
+  raw += (16 - (reinterpret_cast<uintptr_t>(raw) & 15)) & 15;
+  float* hf = reinterpret_cast<float*>(raw + static_cast<size_t>(p.max_rows) * p.pitch);   // [row][channel][column]
+  uint8_t* hb = reinterpret_cast<uint8_t*>(hf);
 
   const int n = blockIdx.y;
   const int oy0 = blockIdx.x * BH, nrow = min(BH, Ho - oy0);
-  for (int i = threadIdx.x; i < Wo; i += blockDim.x)
-    axis_entry(p.crop_w, Wo, p.resample, i, xlo + i, xcnt + i, xwf + i, xwi + i, Wo);
-  for (int i = threadIdx.x; i < nrow; i += blockDim.x)
-    axis_entry(p.crop_h, Ho, p.resample, oy0 + i, ylo + i, ycnt + i, ywf + i, ywi + i, BH);
+  if (threadIdx.x < nrow) {
+    int lo, cnt, wi[KY];
+    float wf[KY];
+    axis_entry<KY>(p.crop_h, Ho, p.resample, oy0 + threadIdx.x, lo, cnt, wf, wi);
+    ylo[threadIdx.x] = lo;
+#pragma unroll
+    for (int a = 0; a < KY; ++a) {
+      if (PIL) ywi[a * BH + threadIdx.x] = wi[a]; else ywf[a * BH + threadIdx.x] = wf[a];
+    }
+    if (threadIdx.x == nrow - 1) ylo[BH] = lo + cnt;            // end of the band's source rows (slot BH of ylo)
+  }
   pdl_launch_dependents();
   __syncthreads();
   pdl_wait();   // the tables above depend on the launch parameters only
@@ -561,98 +577,121 @@ __global__ void __launch_bounds__(PP_THREADS) preprocess_kernel(const PrepP p) {
   const int32_t* d = p.desc + n * 4;
   const int src = d[0], top = d[1], left = d[2], flip = d[3];
   const int r0 = ylo[0];
-  const int R = min(ylo[nrow - 1] + ycnt[nrow - 1] - r0, p.max_rows);
-  const int nb = p.crop_w * 3;                                 // bytes of one cropped source row
+  const int R = min(ylo[BH] - r0, p.max_rows);
+  const int nb = p.crop_w * 3;                                  // bytes of one cropped source row
   if (src >= 0) {
-    // stage rows [top + r0, top + r0 + R) x columns [col0, col0 + crop_w) (the mirrored window when flipped)
+    // stage rows [top + r0, top + r0 + R) x columns [col0, col0 + crop_w) (the mirrored window when flipped), raw bytes
     const int col0 = flip ? p.Ws - left - p.crop_w : left;
     const int chunks = (nb + 15 + 15) >> 4;
     const uint8_t* fend = p.frames + p.frames_bytes;
-    for (int it = threadIdx.x; it < R * chunks; it += blockDim.x) {
-      const int r = it / chunks, i = it - r * chunks;
+    for (int r = threadIdx.x / chunks, i = threadIdx.x - r * chunks; r < R;) {
       const uint8_t* g = p.frames + ((static_cast<long long>(src) * p.Hs + top + r0 + r) * p.Ws + col0) * 3;
       const int shift = static_cast<int>(reinterpret_cast<uintptr_t>(g) & 15);
       const uint8_t* a = g - shift + 16 * i;
-      if (16 * i - shift >= nb) continue;
-      uint4 q;
-      if (a + 16 <= fend) {
-        q = __ldg(reinterpret_cast<const uint4*>(a));
-      } else {   // last bytes of the frame buffer: no read past its end
-        uint8_t* qb = reinterpret_cast<uint8_t*>(&q);
+      if (16 * i - shift < nb) {
+        uint4 q;
+        if (a + 16 <= fend) {
+          q = __ldg(reinterpret_cast<const uint4*>(a));
+        } else {   // last bytes of the frame buffer: no read past its end
+          uint8_t* qb = reinterpret_cast<uint8_t*>(&q);
 #pragma unroll
-        for (int k = 0; k < 16; ++k) qb[k] = (a + k < fend) ? a[k] : 0;
-      }
-      if (PIL) {
-        if (i == 0) rsh[r] = shift;
-        *reinterpret_cast<uint4*>(stage_raw + r * p.pitch + 16 * i) = q;
-      } else {
-        // planar per row: [channel][column], so that the tap loads of a warp (consecutive output pixels, ~1.1 source
-        // columns apart) fall into consecutive banks (interleaved pixels were a 3-4-way conflict on every load)
-        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-        float* dst = stage_f + r * 3 * p.pitch;
-        const int idx0 = 16 * i - shift;
-        int col = idx0 >= 0 ? idx0 / 3 : -((2 - idx0) / 3), ch = idx0 - 3 * col;
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          if (idx0 + k >= 0 && idx0 + k < nb) dst[ch * p.pitch + col] = u8_over_255((w[k >> 2] >> (8 * (k & 3))) & 0xffu);
-          if (++ch == 3) { ch = 0; ++col; }
+          for (int k = 0; k < 16; ++k) qb[k] = (a + k < fend) ? a[k] : 0;
         }
+        if (i == 0) rsh[r] = shift;
+        *reinterpret_cast<uint4*>(raw + r * p.pitch + 16 * i) = q;
       }
+      i += PP_THREADS;   // next item of this thread: advance (r, i) without a division
+      while (i >= chunks) { i -= chunks; ++r; }
     }
   }
   __syncthreads();
 
+  const float inv255 = 1.f / 255.f;   // AA: pixels are /255 (dali_extraction.py:41); applied to the horizontal sums (the
+                                      // reference divides the bytes first: same value to ~1e-7, far below bf16)
   const int cpy = p.y.C;   // 8 (UNet stem) or 4 (7x7 stems) when vectorisable
   const bool vec8 = cpy == 8 && ((p.y.ld | p.y.coff) & 7) == 0, vec4 = cpy == 4 && ((p.y.ld | p.y.coff) & 3) == 0;
-  for (int q = threadIdx.x; q < nrow * Wo; q += blockDim.x) {
-    const int ly = q / Wo, ox = q - ly * Wo, oy = oy0 + ly;
-    float o[3] = {0.f, 0.f, 0.f};
+  for (int ox = threadIdx.x; ox < Wo; ox += PP_THREADS) {
     if (src >= 0) {
-      const int yl = ylo[ly] - r0, yn = ycnt[ly], xl = xlo[ox], xn = xcnt[ox];
-      // staged column of tap b: xl + b, or mirrored inside the staged window when the crop comes from the flipped frame
-      const int j0 = flip ? p.crop_w - 1 - xl : xl, js = flip ? -1 : 1;   // in columns
-      if (PIL) {
-        int acc[3] = {1 << 21, 1 << 21, 1 << 21};
-        for (int a = 0; a < yn; ++a) {
-          const uint8_t* rowp = stage_raw + (yl + a) * p.pitch + rsh[yl + a] + j0 * 3;
-          int h[3] = {1 << 21, 1 << 21, 1 << 21};
-          for (int b = 0; b < xn; ++b) {
-            const uint8_t* px = rowp + b * js * 3;
-            const int k = xwi[b * Wo + ox];
-            h[0] += px[0] * k; h[1] += px[1] * k; h[2] += px[2] * k;
-          }
-          const int ky = ywi[a * BH + ly];
-          acc[0] += clip8_fixed(h[0]) * ky; acc[1] += clip8_fixed(h[1]) * ky; acc[2] += clip8_fixed(h[2]) * ky;
-        }
+      // ---- horizontal pass: this column of every staged row
+      int xl, xn, xwi[KX];
+      float xwf[KX];
+      axis_entry<KX>(p.crop_w, Wo, p.resample, ox, xl, xn, xwf, xwi);
+      int off[KX];   // byte offset of tap b inside a staged row (mirrored when the crop comes from the flipped frame)
 #pragma unroll
-        for (int c = 0; c < 3; ++c) o[c] = u8_over_255(static_cast<uint32_t>(clip8_fixed(acc[c])));
-      } else {
-        for (int a = 0; a < yn; ++a) {
-          const float* rowp = stage_f + (yl + a) * 3 * p.pitch + j0;
-          const float wy = ywf[a * BH + ly];
-          float h[3] = {0.f, 0.f, 0.f};
-          for (int b = 0; b < xn; ++b) {
-            const float* px = rowp + b * js;
-            const float wx = xwf[b * Wo + ox];
-            h[0] = fmaf(wx, px[0], h[0]); h[1] = fmaf(wx, px[p.pitch], h[1]); h[2] = fmaf(wx, px[2 * p.pitch], h[2]);
+      for (int b = 0; b < KX; ++b) {
+        const int col = min(xl + b, p.crop_w - 1);
+        off[b] = (flip ? p.crop_w - 1 - col : col) * 3;
+      }
+      for (int r = 0; r < R; ++r) {
+        const uint8_t* rowp = raw + r * p.pitch + rsh[r];
+        if (PIL) {
+          int h0 = 1 << 21, h1 = 1 << 21, h2 = 1 << 21;
+#pragma unroll
+          for (int b = 0; b < KX; ++b) {
+            const uint8_t* px = rowp + off[b];
+            h0 += px[0] * xwi[b]; h1 += px[1] * xwi[b]; h2 += px[2] * xwi[b];
           }
-          o[0] = fmaf(wy, h[0], o[0]); o[1] = fmaf(wy, h[1], o[1]); o[2] = fmaf(wy, h[2], o[2]);
+          uint8_t* hp = hb + (r * 3) * Wo + ox;
+          hp[0] = static_cast<uint8_t>(clip8_fixed(h0)); hp[Wo] = static_cast<uint8_t>(clip8_fixed(h1));
+          hp[2 * Wo] = static_cast<uint8_t>(clip8_fixed(h2));
+        } else {
+          // sum of w_b * byte_b, the 1/255 applied to the sum; bytes turned into floats with the 2^23 trick (OR into
+          // the mantissa, one FADD) - I2F runs at a fraction of the FFMA rate
+          float h0 = 0.f, h1 = 0.f, h2 = 0.f;
+#pragma unroll
+          for (int b = 0; b < KX; ++b) {
+            const uint8_t* px = rowp + off[b];
+            h0 = fmaf(xwf[b], u8_to_float(px[0]), h0);
+            h1 = fmaf(xwf[b], u8_to_float(px[1]), h1);
+            h2 = fmaf(xwf[b], u8_to_float(px[2]), h2);
+          }
+          float* hp = hf + (r * 3) * Wo + ox;
+          hp[0] = h0 * inv255; hp[Wo] = h1 * inv255; hp[2 * Wo] = h2 * inv255;
         }
       }
     }
-    __nv_bfloat16* yp = elem_ptr_w(p.y, pix_index(p.y, n, 0, oy, ox), 0);
-    const uint32_t lo = cvt_bf16x2(o[0], o[1], false), hi = cvt_bf16x2(o[2], 0.f, false);
-    if (vec8) {
-      *reinterpret_cast<uint4*>(yp) = make_uint4(lo, hi, 0u, 0u);
-    } else if (vec4) {
-      *reinterpret_cast<uint2*>(yp) = make_uint2(lo, hi);
-    } else {
-      for (int c = 0; c < cpy; ++c) yp[c] = __float2bfloat16_rn(c < 3 ? o[c] : 0.f);
-    }
-    if (p.frames_f32) {
-      const long long plane = static_cast<long long>(Ho) * Wo;
-      float* fo = p.frames_f32 + static_cast<long long>(n) * 3 * plane + static_cast<long long>(oy) * Wo + ox;
-      fo[0] = o[0]; fo[plane] = o[1]; fo[2 * plane] = o[2];
+    // ---- vertical pass: down the column (only this thread wrote / reads column ox of the planes: no barrier needed)
+    __nv_bfloat16* yp = elem_ptr_w(p.y, pix_index(p.y, n, 0, oy0, ox), 0);
+    const long long y_row = static_cast<long long>(p.y.Wp) * p.y.ld;
+    const long long plane = static_cast<long long>(Ho) * Wo;
+    float* fo = p.frames_f32 ? p.frames_f32 + static_cast<long long>(n) * 3 * plane + static_cast<long long>(oy0) * Wo + ox : nullptr;
+    for (int ly = 0; ly < nrow; ++ly, yp += y_row) {
+      float o0 = 0.f, o1 = 0.f, o2 = 0.f;
+      if (src >= 0) {
+        const int yl = ylo[ly] - r0;
+        if (PIL) {
+          int a0 = 1 << 21, a1 = 1 << 21, a2 = 1 << 21;
+#pragma unroll
+          for (int a = 0; a < KY; ++a) {
+            const uint8_t* hp = hb + (min(yl + a, R - 1) * 3) * Wo + ox;
+            const int ky = ywi[a * BH + ly];
+            a0 += hp[0] * ky; a1 += hp[Wo] * ky; a2 += hp[2 * Wo] * ky;
+          }
+          o0 = u8_over_255(static_cast<uint32_t>(clip8_fixed(a0)));
+          o1 = u8_over_255(static_cast<uint32_t>(clip8_fixed(a1)));
+          o2 = u8_over_255(static_cast<uint32_t>(clip8_fixed(a2)));
+        } else {
+#pragma unroll
+          for (int a = 0; a < KY; ++a) {
+            const float* hp = hf + (min(yl + a, R - 1) * 3) * Wo + ox;
+            const float wy = ywf[a * BH + ly];
+            o0 = fmaf(wy, hp[0], o0); o1 = fmaf(wy, hp[Wo], o1); o2 = fmaf(wy, hp[2 * Wo], o2);
+          }
+        }
+      }
+      const uint32_t lo = cvt_bf16x2(o0, o1, false), hi = cvt_bf16x2(o2, 0.f, false);
+      if (vec8) {
+        *reinterpret_cast<uint4*>(yp) = make_uint4(lo, hi, 0u, 0u);
+      } else if (vec4) {
+        *reinterpret_cast<uint2*>(yp) = make_uint2(lo, hi);
+      } else {
+        const float o[3] = {o0, o1, o2};
+        for (int c = 0; c < cpy; ++c) yp[c] = __float2bfloat16_rn(c < 3 ? o[c] : 0.f);
+      }
+      if (fo) {
+        fo[0] = o0; fo[plane] = o1; fo[2 * plane] = o2;
+        fo += Wo;
+      }
     }
   }
 }
@@ -995,32 +1034,58 @@ extern "C" int tedspad_preprocess(const uint8_t* frames, int32_t F, int32_t Hs, 
             crop_w, Hs, Ws);
   TSP_CHECK(y->C <= 8 || (y->C % 8 == 0), "preprocess: y.C=%d", y->C);
   const double sy = static_cast<double>(crop_h) / y->H, sx = static_cast<double>(crop_w) / y->W;
-  TSP_CHECK(2 * static_cast<int>(ceil(sy < 1 ? 1 : sy)) + 1 <= PP_KMAX + 1 &&
-                2 * static_cast<int>(ceil(sx < 1 ? 1 : sx)) + 1 <= PP_KMAX + 1,
-            "preprocess: down-scale factor too large for the %d-tap table", PP_KMAX);
+  // taps per axis: hi - lo <= 2 * support + 1
+  const int tx = static_cast<int>(ceil(2.0 * (sx < 1 ? 1 : sx))) + 1, ty = static_cast<int>(ceil(2.0 * (sy < 1 ? 1 : sy))) + 1;
+  TSP_CHECK(tx <= PP_KMAX + 1 && ty <= PP_KMAX + 1, "preprocess: down-scale factor too large for the %d-tap table", PP_KMAX);
   const bool pil = resample == TEDSPAD_RESAMPLE_PIL_U8;
+  // exact maximum tap count per axis (the same arithmetic as axis_entry): the kernels unroll that many taps
+  auto max_taps = [&](int in, int out) {
+    int m = 1;
+    for (int i = 0; i < out; ++i) {
+      int lo, hi;
+      if (pil) {
+        const double scale = static_cast<double>(in) / out, support = scale < 1.0 ? 1.0 : scale, center = (i + 0.5) * scale;
+        lo = static_cast<int>(center - support + 0.5); hi = static_cast<int>(center + support + 0.5);
+      } else {
+        const float scale = static_cast<float>(in) / static_cast<float>(out), support = scale >= 1.f ? scale : 1.f;
+        const float center = scale * (i + 0.5f);
+        lo = static_cast<int>(center - support + 0.5f); hi = static_cast<int>(center + support + 0.5f);
+      }
+      lo = lo < 0 ? 0 : lo; hi = hi > in ? in : hi;
+      m = std::max(m, hi - lo);
+    }
+    return m;
+  };
+  const int mx = max_taps(crop_w, y->W), my = max_taps(crop_h, y->H);
+  TSP_CHECK(mx <= PP_KMAX && my <= PP_KMAX, "preprocess: %d x %d taps exceed the %d-tap kernels", mx, my, PP_KMAX);
+  const int KXs = mx <= 3 ? 3 : (mx <= 5 ? 5 : 8), KYs = my <= 2 ? 2 : (my <= 5 ? 5 : 8);
   PrepP p;
   p.frames = frames; p.frames_bytes = static_cast<long long>(F) * Hs * Ws * 3;
   p.F = F; p.Hs = Hs; p.Ws = Ws; p.desc = desc; p.n_out = n_out;
   p.crop_h = crop_h; p.crop_w = crop_w; p.resample = resample;
   p.y = make_view(*y);
   p.frames_f32 = frames_f32;
-  // band height: as many output rows per block as keep the staged source rows + tables under 48 KB of shared memory
-  const int nb = crop_w * 3;
-  p.pitch = pil ? static_cast<int>(round_up(nb + 32, 16)) : crop_w + 1;   // AA: three planes of `pitch` floats per row
+  // band height: as many output rows per block as keep the staged rows + the horizontal-pass planes under 48 KB
+  const int nb = crop_w * 3, KY = KYs;
+  p.pitch = static_cast<int>(round_up(nb + 32, 16));
   size_t smem = 0;
   for (p.BH = 8; p.BH >= 1; p.BH >>= 1) {
     p.max_rows = static_cast<int>(ceil((p.BH - 1) * sy + 2.0 * (sy < 1 ? 1 : sy) + 2.0));
     if (p.max_rows > crop_h) p.max_rows = crop_h;
-    smem = (2 * y->W + 2 * p.BH + p.max_rows) * sizeof(int) + static_cast<size_t>(y->W + p.BH) * PP_KMAX * sizeof(float) + 16 +
-           static_cast<size_t>(p.max_rows) * p.pitch * (pil ? 1 : 3 * sizeof(float));
+    smem = (p.BH + 1 + p.max_rows) * sizeof(int) + static_cast<size_t>(KY) * p.BH * sizeof(float) + 16 +
+           static_cast<size_t>(p.max_rows) * p.pitch + static_cast<size_t>(p.max_rows) * 3 * y->W * (pil ? 1 : sizeof(float)) + 16;
     if (smem <= 48 * 1024) break;
   }
   TSP_CHECK(p.BH >= 1, "preprocess: a %d-pixel wide crop does not fit in shared memory", crop_w);
   dim3 grid((y->H + p.BH - 1) / p.BH, n_out);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (pil) TSP_CUDA(launch_kernel(preprocess_kernel<true>, grid, dim3(PP_THREADS), smem, st, p));
-  else TSP_CUDA(launch_kernel(preprocess_kernel<false>, grid, dim3(PP_THREADS), smem, st, p));
+#define TSP_PREP(PIL_, KX_, KY_) TSP_CUDA(launch_kernel(preprocess_kernel<PIL_, KX_, KY_>, grid, dim3(PP_THREADS), smem, st, p))
+#define TSP_PREP_Y(PIL_, KX_) do { if (KYs == 2) TSP_PREP(PIL_, KX_, 2); else if (KYs == 5) TSP_PREP(PIL_, KX_, 5); else TSP_PREP(PIL_, KX_, 8); } while (0)
+#define TSP_PREP_X(PIL_) do { if (KXs == 3) TSP_PREP_Y(PIL_, 3); else if (KXs == 5) TSP_PREP_Y(PIL_, 5); else TSP_PREP_Y(PIL_, 8); } while (0)
+  if (pil) TSP_PREP_X(true); else TSP_PREP_X(false);
+#undef TSP_PREP_X
+#undef TSP_PREP_Y
+#undef TSP_PREP
   TSP_CUDA(cudaGetLastError());
   return 0;
 }

@@ -29,13 +29,13 @@ if arch != "i3d":
     ft = load_ft_model(arch=arch, num_classes=102).to(dev).eval()
 
 
-def videos(h, w, n, frames):
+def videos(h, w, n, frames, step=37):
     """n videos of ~`frames` frames each, all windows of ONE pinned pool of random frames (so that a run of several
     seconds does not need hundreds of GB of host memory; the frame bytes still cross PCIe for every video)."""
     g = torch.Generator().manual_seed(7)
-    longest = frames + 37 * (n - 1)
+    longest = frames + step * (n - 1)
     pool = torch.randint(0, 256, (longest, h, w, 3), generator=g, dtype=torch.uint8).pin_memory()
-    return [(f"/data/video_{i:03d}.mp4", frames + 37 * i, (lambda i=i: pool[:frames + 37 * i])) for i in range(n)]
+    return [(f"/data/video_{i:03d}.mp4", frames + step * i, (lambda i=i: pool[:frames + step * i])) for i in range(n)]
 
 
 def run(name, ext, vids):
@@ -63,4 +63,4 @@ run("UCF-Crime-shaped 10-crop (configs[2])", SnippetExtractor(fa, ft, source="da
 run("UCF-Crime-shaped single crop", SnippetExtractor(fa, ft, source="dali", ncrops=1, batch_clips=32),
     videos(240, 320, n_videos, n_frames))
 run("ShanghaiTech-shaped single crop, PIL path (configs[3])", SnippetExtractor(fa, ft, source="shanghai", ncrops=1, batch_clips=32),
-    videos(480, 856, n_videos * 4, max(64, n_frames // 4)))
+    videos(480, 856, int(os.environ.get("BENCH_ST_VIDEOS", n_videos * 4)), max(64, n_frames // 4), step=3))

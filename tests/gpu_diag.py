@@ -409,6 +409,32 @@ def group_prep():
     except Exception:
         RESULTS.append(("preprocess AA", False))
         print(f"[FAIL] preprocess AA: EXCEPTION\n{traceback.format_exc()}", flush=True)
+    # larger down-scale (XD-Violence-shaped 360x640, 10-crop boxes incl. a flipped corner) into 4-channel pixels (the
+    # UNet++ stem's input layout): the 5 / 8-tap instantiations of the kernel
+    try:
+        Fr, Hs, Ws = 3, 360, 640
+        frames = torch.randint(0, 256, (Fr, Hs, Ws, 3), generator=g, dtype=torch.uint8)
+        ch, cw = int(Hs * 0.8), int(Ws * 0.8)
+        desc = torch.tensor([[0, 0, Ws - cw, 0], [2, Hs - ch, 0, 1], [1, 36, 64, 0]], dtype=torch.int32)
+        for reso in ((224, 224), (112, 112)):
+            y = ops.CLTensor(3, 1, reso[0], reso[1], 4, device=DEV)
+            y.buf.fill_(9.0)
+            f32 = torch.empty(3, 3, reso[0], reso[1], device=DEV)
+            ops.preprocess(frames.to(DEV), desc.to(DEV), (ch, cw), y, L.RESAMPLE_AA_FLOAT, f32)
+            v = frames.permute(0, 3, 1, 2).float() / 255.0
+            refs = []
+            for s_, t, l, fl in desc.tolist():
+                img = v[s_].flip(-1) if fl else v[s_]
+                refs.append(TF.resize(img[:, t:t + ch, l:l + cw], reso, antialias=True))
+            ref = torch.stack(refs).to(DEV)
+            report(f"preprocess AA 360x640 -> {reso[0]} fp32 (down-scale taps)", f32, ref, tol_rel=3e-5)
+            report(f"preprocess AA 360x640 -> {reso[0]} bf16, 4-channel pixels", y.to_ncdhw()[:, :3, 0], bf(ref), tol_rel=8e-3)
+            okz = bool((y.interior()[..., 3] == 0).all())
+            RESULTS.append((f"preprocess C=4 pad {reso[0]}", okz))
+            print(f"[{'PASS' if okz else 'FAIL'}] preprocess 4-channel pixels: pad channel zero")
+    except Exception:
+        RESULTS.append(("preprocess AA downscale", False))
+        print(f"[FAIL] preprocess AA downscale: EXCEPTION\n{traceback.format_exc()}", flush=True)
     # ShanghaiTech path: 480x856 -> crop 384x384 -> PIL bilinear uint8
     try:
         Fr, Hs, Ws = 2, 480, 856
