@@ -223,7 +223,7 @@ def sharded_dataset_run(ext_factory, device, rank, world, dist, n_videos=256, nc
     shards = shard_videos([v[1] for v in videos], world)
     loads = [int(sum(lengths[i] for i in s)) for s in shards]
     snippets = int(sum(-(-int(n) // 32) for n in lengths))
-    folder = [tempfile.mkdtemp(prefix="tedspad_sharded_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None) if rank == 0 else None]
+    folder = [tempfile.mkdtemp(prefix="tedspad_sharded_") if rank == 0 else None]
     if dist is not None:
         dist.broadcast_object_list(folder, src=0)
     ext = ext_factory(ncrops)

@@ -74,7 +74,7 @@ class InceptionI3d(CudaModule):
             feat_map = ex.run_trunk(enc)                # Mixed_5c, then AdaptiveAvgPool3d(1)
             pooled = ops.avgpool_features(feat_map, 0)  # [B,1,1024]
             fin = ex.bufs.get("logits_in", x.shape[0], 1, 1, 1, 1024)
-            fin.buf.copy_(pooled.reshape(x.shape[0], 1, 1, 1, 1024))
+            ops.nchw_to_cl(pooled.reshape(x.shape[0], 1024, 1, 1, 1), fin)     # fp32 -> bf16 operand (own kernel)
             pc = PackedConv(self.logits.conv3d.weight, self.logits.conv3d.bias, None, device=x.device)
             out = ex.bufs.get("logits_out", x.shape[0], 1, 1, 1, self._num_classes, dtype=torch.float32)
             ops.conv_forward(fin, pc, out, act=0, y_fp32=True)

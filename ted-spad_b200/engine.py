@@ -764,7 +764,7 @@ class R3D18Executor:
             x = self._apply(n + ".c2", blk["c2"], o, res=res)
         feat = ops.avgpool_features(x, 0)  # [B,1,512] fp32
         fin = self.bufs.get("fc_in", x.N, 1, 1, 1, 512)
-        fin.buf.copy_(feat.reshape(x.N, 1, 1, 1, 512))  # fp32 -> bf16 operand of the head GEMM
+        ops.nchw_to_cl(feat.reshape(x.N, 512, 1, 1, 1), fin)  # fp32 -> bf16 operand of the head GEMM (own kernel, no ATen)
         pred = self.bufs.get("fc_out", x.N, 1, 1, 1, self.fc.cout, dtype=torch.float32)
         ops.conv_forward(fin, self.fc, pred, act=L.ACT_NONE, y_fp32=True)
         return pred.buf.reshape(x.N, self.fc.cout), feat.reshape(x.N, 512)

@@ -416,7 +416,7 @@ def group_prep():
         frames = torch.randint(0, 256, (Fr, Hs, Ws, 3), generator=g, dtype=torch.uint8)
         ch, cw = int(Hs * 0.8), int(Ws * 0.8)
         desc = torch.tensor([[0, 0, Ws - cw, 0], [2, Hs - ch, 0, 1], [1, 36, 64, 0]], dtype=torch.int32)
-        for reso in ((224, 224), (112, 112)):
+        for reso in ((224, 224), (160, 192)):      # 6 x 4 and 8 x 5 taps (anything beyond 8 taps per axis is refused)
             y = ops.CLTensor(3, 1, reso[0], reso[1], 4, device=DEV)
             y.buf.fill_(9.0)
             f32 = torch.empty(3, 3, reso[0], reso[1], device=DEV)

@@ -521,3 +521,53 @@ def test_cv2_ingest_decodes_every_frame_in_bgr_order(tmp_path):
     assert extraction.shanghai_snippet_frames(12, total_frames=10).tolist()[0][-4:] == [9, 9, 9, 9]
     with pytest.raises(RuntimeError, match="could not process"):
         extraction.shanghai_snippet_frames(8, total_frames=10)
+
+
+def test_graph_cache_protocol(monkeypatch):
+    """engine.GraphCache: first call with a key eager, second captured + replayed, later calls replayed; a changed
+    buffer generation (reallocation, new weights) forces a fresh eager call and a re-capture; profiling hooks and
+    TEDSPAD_GRAPHS=0 bypass it.  (CUDA graph objects are faked: the protocol is host logic.)"""
+    log = []
+
+    class FakeGraph:
+        def replay(self):
+            log.append("replay")
+
+    class FakeCapture:
+        def __init__(self, g):
+            pass
+
+        def __enter__(self):
+            log.append("capture")
+
+        def __exit__(self, *a):
+            return False
+
+    monkeypatch.setattr(torch.cuda, "CUDAGraph", FakeGraph)
+    monkeypatch.setattr(torch.cuda, "graph", FakeCapture)
+    monkeypatch.setattr(torch.cuda, "is_current_stream_capturing", lambda: False)
+    monkeypatch.setattr(engine, "USE_GRAPHS", True)
+    gc = engine.GraphCache()
+    calls = []
+
+    def fn():
+        calls.append(1)
+        ops.LAUNCHES += 3
+        return "out"
+
+    ops.LAUNCHES = 0
+    assert gc.run("k", 0, fn) == "out" and log == [] and len(calls) == 1            # eager
+    assert gc.run("k", 0, fn) == "out" and log == ["capture", "replay"] and len(calls) == 2
+    assert gc.run("k", 0, fn) == "out" and log == ["capture", "replay", "replay"] and len(calls) == 2
+    assert ops.LAUNCHES == 3 + 3 + 3                                                  # replays count their kernels
+    gc.run("k", 1, fn)                                                                # generation changed: eager again
+    assert len(calls) == 3 and log[-1] == "replay"
+    gc.run("k", 1, fn)
+    assert log[-2:] == ["capture", "replay"]
+    monkeypatch.setattr(ops, "CONV_EVENTS", [])                                       # per-launch timing: always eager
+    gc.run("k", 1, fn)
+    assert len(calls) == 5
+    monkeypatch.setattr(ops, "CONV_EVENTS", None)
+    monkeypatch.setattr(engine, "USE_GRAPHS", False)
+    gc.run("k", 1, fn)
+    assert len(calls) == 6
