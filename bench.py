@@ -57,11 +57,30 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
 
+    def _handle(self, pynvml):
+        """NVML handle of CUDA device `index`: NVML ignores CUDA_VISIBLE_DEVICES, so go through the device UUID (or the
+        visible-devices list) instead of assuming that the two enumerations agree."""
+        try:
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            return pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid if not uuid.startswith("GPU-") else uuid).encode())
+        except Exception:
+            pass
+        vis = [v for v in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if v]
+        if self.index < len(vis):
+            v = vis[self.index]
+            if v.isdigit():
+                return pynvml.nvmlDeviceGetHandleByIndex(int(v))
+            try:
+                return pynvml.nvmlDeviceGetHandleByUUID(v.encode())
+            except Exception:
+                pass
+        return pynvml.nvmlDeviceGetHandleByIndex(self.index)
+
     def run(self):
         try:
             import pynvml
             pynvml.nvmlInit()
-            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            h = self._handle(pynvml)
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
             names = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
                      0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
@@ -237,11 +256,12 @@ def sharded_dataset_run(ext_factory, device, rank, world, dist, n_videos=256, nc
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    stats = {}
     t0 = time.perf_counter()
-    manifest = extract_dataset_distributed(ext, videos, folder[0], log=lambda *_: None)
+    manifest = extract_dataset_distributed(ext, videos, folder[0], log=lambda *_: None, stats=stats)
     e1.record()
     torch.cuda.synchronize()
-    mine_s = time.perf_counter() - t0        # this rank's own shard (incl. the closing manifest gather)
+    mine_s = stats.get("extract_s", time.perf_counter() - t0)   # this rank's own shard, before the manifest gather
     ms = e0.elapsed_time(e1)
     per_rank = [mine_s]
     if dist is not None:
