@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define TEDSPAD_ABI_VERSION 7
+#define TEDSPAD_ABI_VERSION 8
 
 enum { TEDSPAD_ACT_NONE = 0, TEDSPAD_ACT_RELU = 1, TEDSPAD_ACT_SIGMOID = 2 };
 /* A-operand feed of the implicit GEMM: AUTO picks FLAT when legal. */
@@ -268,6 +268,10 @@ int tedspad_outconv_sigmoid(const tedspad_tensor* x, const float* w, const float
  * torchvision video/resnet.py:261).
  */
 int tedspad_avgpool_features(const tedspad_tensor* x, int32_t kd, float* out, void* stream);
+
+/* In-place row-wise L2 normalisation of an fp32 [rows][cols] matrix: x / max(||x||_2, eps).  Replaces
+ * nn.functional.normalize(x, p=2, dim=1) of the embedding head mlp.forward (aux_code/model_loaders.py:249-253). */
+int tedspad_l2_normalize_rows(float* x, int32_t rows, int32_t cols, float eps, void* stream);
 
 /*
  * The consumer's view of a feature matrix, computed on the device: what anomaly_detection_mgfn's

@@ -351,6 +351,21 @@ def i3res50_extract_features(sd, x, prefix="i3d.", calibrate=False, taps=None):
     return F.adaptive_avg_pool3d(x, 1)
 
 
+def wrapper_i3d_forward(sd, x):
+    """wrapper_i3d.forward (aux_code/model_loaders.py:265-268) in eval mode, fp32: (pred [B,nc], feature [B,128]).
+    I3Res50.forward (large_i3d.py:229-246): features -> dropout (identity) -> fc; mlp.forward (:249-253):
+    relu(bn1(fc1(feat))) -> normalize(bn2(fc2(.)), p=2, dim=1) (the reference wraps it in fp16 autocast on CUDA)."""
+    feat = i3res50_extract_features(sd, x).flatten(1)
+    pred = F.linear(feat, sd["i3d.fc.weight"], sd["i3d.fc.bias"])
+
+    def bn1d(v, p):
+        return F.batch_norm(v, sd[p + ".running_mean"], sd[p + ".running_var"], sd[p + ".weight"], sd[p + ".bias"], False, 0.0, 1e-5)
+
+    h = torch.relu(bn1d(F.linear(feat, sd["mlp.fc1.weight"], sd["mlp.fc1.bias"]), "mlp.bn1"))
+    e = F.normalize(bn1d(F.linear(h, sd["mlp.fc2.weight"]), "mlp.bn2"), p=2, dim=1)
+    return pred, e
+
+
 def r3d18_forward(sd, x, calibrate=False, taps=None):
     """x: fp32 [B,3,T,H,W] -> (pred [B,nc], feature [B,512]).  model_loaders.py:210-213."""
     c = _Ctx(sd, calibrate, taps, 1e-5)

@@ -15,7 +15,7 @@ FEED_AUTO, FEED_FLAT_TMA, FEED_GATHER = 0, 1, 2
 RESAMPLE_AA_FLOAT, RESAMPLE_PIL_U8 = 0, 1
 SLAB_3X3, SLAB_STEM2D, SLAB_STEM3D, SLAB_3X3_STREAM, SLAB_3X3_PAIR, SLAB_3X3_STREAM_PAIR = 0, 1, 2, 3, 4, 5
 SLAB_MAX_MMA = 112
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 
 class TensorDesc(C.Structure):
@@ -71,6 +71,7 @@ SYMBOLS = {
     "tedspad_frames_to_clip": (C.c_int, [_TP, _TP, _I, _I, _V, _V]),
     "tedspad_outconv_sigmoid": (C.c_int, [_TP, _V, _V, _TP, _I, _V, _V]),
     "tedspad_avgpool_features": (C.c_int, [_TP, _I, _V, _V]),
+    "tedspad_l2_normalize_rows": (C.c_int, [_V, _I, _I, C.c_float, _V]),
     "tedspad_mgfn_rows": (C.c_int, [_V, _I, _I, _I, _V, _I, _I, _V, _V]),
     "tedspad_preprocess": (C.c_int, [_V, _I, _I, _I, _V, _I, _I, _I, _TP, _I, _V, _V]),
     "tedspad_nchw_to_cl": (C.c_int, [_V, _I, _TP, _V]),

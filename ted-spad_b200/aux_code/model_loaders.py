@@ -109,8 +109,9 @@ def build_largei3d_classifier(num_classes=400, pretrained=True):
 
 
 class mlp(nn.Module):
-    """Parameter container of the training-time embedding head (model_loaders.py:235-254); kept so that
-    wrapper_i3d checkpoints load strict=True.  Not on the extraction path."""
+    """The embedding head (model_loaders.py:235-254): fc1 + bn1 + ReLU, fc2 + bn2, L2 normalisation.  Parameters
+    under the reference's names so that wrapper_i3d checkpoints load strict=True; not on the extraction path (the
+    scripts call .i3d.extract_features), but wrapper_i3d.forward uses it."""
 
     def __init__(self, final_embedding_size=128, use_normalization=True):
         super().__init__()
@@ -119,6 +120,21 @@ class mlp(nn.Module):
         self.bn1 = nn.BatchNorm1d(512)
         self.bn2 = nn.BatchNorm1d(128)
         self.fc2 = nn.Linear(512, final_embedding_size, bias=False)
+
+    def forward(self, x, bufs):
+        """x: fp32 cuda [B, 2048] -> [B, 128], eval mode (BatchNorm1d folded into the two linear layers)."""
+        from tedspad_b200 import _lib as L, ops
+        from tedspad_b200.ops import PackedConv
+        sig = tuple((p.data_ptr(), p._version) for p in list(self.parameters()) + list(self.buffers()))
+        if self.__dict__.get("_tsp_sig") != sig:
+            bn = lambda m: (m.weight, m.bias, m.running_mean, m.running_var, m.eps)  # noqa: E731
+            self.__dict__["_tsp_pcs"] = (PackedConv(self.fc1.weight, self.fc1.bias, bn(self.bn1), device=x.device),
+                                         PackedConv(self.fc2.weight, None, bn(self.bn2), device=x.device))
+            self.__dict__["_tsp_sig"] = sig
+        p1, p2 = self.__dict__["_tsp_pcs"]
+        h = ops.linear(x, p1, (bufs, "mlp.fc1"), act=L.ACT_RELU)
+        e = ops.linear(h, p2, (bufs, "mlp.fc2")).clone()
+        return ops.l2_normalize_rows(e)
 
 
 class wrapper_i3d(nn.Module):
@@ -131,8 +147,13 @@ class wrapper_i3d(nn.Module):
         self.mlp = mlp()
 
     def forward(self, x):
-        raise NotImplementedError("wrapper_i3d.forward (logits + contrastive embedding) is a training-time path; "
-                                  "feature extraction calls .i3d.extract_features (dali_extraction.py:178)")
+        """(pred [B, num_classes], feature [B, 128] L2-normalised) as model_loaders.py:265-268, eval mode."""
+        if self.training:
+            raise RuntimeError("wrapper_i3d: inference only; call .eval() first")
+        pred, feature = self.i3d(x)
+        with torch.cuda.device(x.device):
+            feature = self.mlp(feature.reshape(x.shape[0], 2048), self.i3d.executor(x.device).bufs)
+        return pred, feature
 
 
 def _r3d_trunk():

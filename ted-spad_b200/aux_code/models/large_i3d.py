@@ -65,5 +65,17 @@ class I3Res50(CudaModule):
         return self._exec(enc_in.buf).run(enc_in)
 
     def forward(self, x):
-        raise NotImplementedError("I3Res50.forward (classification logits + training feature, large_i3d.py:229-246) is "
-                                  "a training-time path; feature extraction calls extract_features (dali_extraction.py:178)")
+        """(logits [B, num_classes], feat) as large_i3d.py:229-246 in eval mode (dropout is the identity):
+        feat = pooled.squeeze() ([B,2048], or [2048] when B == 1, like the reference's `x.squeeze()`)."""
+        ex = self._exec(x)
+        with torch.cuda.device(x.device):
+            enc = self._to_cl(x)
+            feat = self._graphed(ex, ("extract_features",) + tuple(x.shape), lambda: ex.run(enc)).reshape(x.shape[0], 2048).clone()
+            pc = self.__dict__.get("_tsp_fc")
+            if pc is None or pc[0] != ex.serial:
+                from tedspad_b200.ops import PackedConv
+                pc = (ex.serial, PackedConv(self.fc.weight, self.fc.bias, None, device=x.device))
+                self.__dict__["_tsp_fc"] = pc
+            from tedspad_b200 import ops
+            logits = ops.linear(feat, pc[1], (ex.bufs, "fc")).clone()
+        return logits, feat.squeeze()

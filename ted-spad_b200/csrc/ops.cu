@@ -448,7 +448,7 @@ __global__ void __launch_bounds__(256) mgfn_rows_kernel(const MgfnP p) {
 // (weights beyond a column's real tap count are zero, their indices clamped): ncu on the round-1 kernel and on the
 // first staged version showed both ISSUE-bound (86 % issue-active, 345 M warp instructions for 25.7 M pixels).
 constexpr int PP_KMAX = 8;
-constexpr int PP_MAXOUT = 512;
+constexpr int PP_MAXOUT = 4096;   // (the band height shrinks until the staged rows + planes fit in shared memory)
 constexpr int PP_THREADS = 256;
 
 struct PrepP {
@@ -859,6 +859,30 @@ __global__ void __launch_bounds__(256) frames_to_clip_kernel(const F2CP p) {
   }
 }
 
+// ------------------------------------------------------------------ row-wise L2 normalisation (fp32, in place)
+struct NormP {
+  float* x;
+  int rows, cols;
+  float eps;
+};
+
+// nn.functional.normalize(x, p=2, dim=1) (aux_code/model_loaders.py:252): x / max(||x||_2, eps); one block per row,
+// warp-shuffle + shared-memory reduction of the sum of squares
+__global__ void __launch_bounds__(128) l2_normalize_rows_kernel(const NormP p) {
+  __shared__ float warp_sums[4];
+  pdl_launch_dependents();
+  pdl_wait();
+  float* row = p.x + static_cast<long long>(blockIdx.x) * p.cols;
+  float sq = 0.f;
+  for (int i = threadIdx.x; i < p.cols; i += blockDim.x) sq = fmaf(row[i], row[i], sq);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
+  if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = sq;
+  __syncthreads();
+  const float inv = 1.f / fmaxf(sqrtf(warp_sums[0] + warp_sums[1] + warp_sums[2] + warp_sums[3]), p.eps);
+  for (int i = threadIdx.x; i < p.cols; i += blockDim.x) row[i] *= inv;
+}
+
 static int grid_for(long long total, int threads) {
   const long long blocks = (total + threads - 1) / threads;
   const long long cap = static_cast<long long>(num_sms()) * 16;
@@ -1006,6 +1030,15 @@ extern "C" int tedspad_avgpool_features(const tedspad_tensor* x, int32_t kd, flo
   TSP_CHECK((reinterpret_cast<uintptr_t>(out) & 15) == 0, "avgpool: out must be 16-byte aligned");
   p.total_warps = static_cast<long long>(x->N) * p.OD * (x->C / 8);
   TSP_CUDA(launch_kernel(avgpool_kernel, dim3(grid_for(p.total_warps * 32, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), p));
+  TSP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tedspad_l2_normalize_rows(float* x, int32_t rows, int32_t cols, float eps, void* stream) {
+  TSP_CHECK(x && rows >= 1 && cols >= 1, "l2_normalize_rows: bad arguments");
+  NormP p;
+  p.x = x; p.rows = rows; p.cols = cols; p.eps = eps;
+  TSP_CUDA(launch_kernel(l2_normalize_rows_kernel, dim3(rows), dim3(128), 0, reinterpret_cast<cudaStream_t>(stream), p));
   TSP_CUDA(cudaGetLastError());
   return 0;
 }

@@ -70,7 +70,8 @@ class GraphCache:
             graph = torch.cuda.CUDAGraph()
             launches = ops.LAUNCHES
             try:
-                with torch.cuda.graph(graph):
+                # thread_local: CUDA calls of OTHER host threads (a pin-memory worker, NVML sampling) must not abort it
+                with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                     out = fn()
             except Exception:
                 ops.LAUNCHES = launches

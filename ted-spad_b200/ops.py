@@ -396,6 +396,28 @@ def avgpool_features(x, kd=0):
     return out
 
 
+def l2_normalize_rows(x, eps=1e-12):
+    """In-place x / max(||x||_2, eps) per row of a contiguous fp32 cuda [rows, cols] tensor (F.normalize(p=2, dim=1))."""
+    _require_cuda(x, "l2_normalize_rows")
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 2
+    _count()
+    L.check(L.lib().tedspad_l2_normalize_rows(x.data_ptr(), int(x.shape[0]), int(x.shape[1]), float(eps), _stream()),
+            "tedspad_l2_normalize_rows")
+    return x
+
+
+def linear(x_f32, pc, name_bufs, act=L.ACT_NONE):
+    """fp32 cuda [B, in] -> fp32 [B, out] through the convolution kernel as a 1x1x1 layer (nn.Linear, optionally with a
+    folded BatchNorm1d and ReLU): `pc` = PackedConv(weight [out,in], bias, bn); name_bufs = (_Buffers, name)."""
+    bufs, name = name_bufs
+    B, cin = x_f32.shape
+    fin = bufs.get(name + ".in", B, 1, 1, 1, pc.cin_pad)
+    nchw_to_cl(x_f32.reshape(B, cin, 1, 1, 1), fin)
+    out = bufs.get(name + ".out", B, 1, 1, 1, pc.cout, dtype=torch.float32)
+    conv_forward(fin, pc, out, act=act, y_fp32=True)
+    return out.buf.reshape(B, pc.cout)
+
+
 def preprocess(frames_u8, desc_i32, crop_hw, y, resample=L.RESAMPLE_AA_FLOAT, frames_f32=None):
     """frames_u8: cuda uint8 [F,Hs,Ws,3]; desc_i32: cuda int32 [n_out,4] = (src_frame, top, left, hflip)."""
     _require_cuda(frames_u8, "preprocess")

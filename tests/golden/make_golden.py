@@ -123,8 +123,27 @@ def shanghai_index_golden():
     return res
 
 
+def wrapper_forward_golden(load_ft_model):
+    """wrapper_i3d.forward / I3Res50.forward of the unmodified reference (model_loaders.py:265-268, large_i3d.py:229-246)
+    on a small seeded clip -> tests/golden/wrapper_i3d_v1.npz (the oracle restatement is asserted against it here)."""
+    x = torch.rand(2, 3, 8, 64, 64, generator=torch.Generator().manual_seed(17))
+    sd = M.calibrated_state_dict("largei3d", 3, x)
+    ft = load_ft_model(arch="largei3d", num_classes=102)
+    ft.load_state_dict(sd, strict=True)
+    ft.eval()
+    with torch.no_grad():
+        pred, emb = ft(x)
+        logits, feat = ft.i3d(x)
+        pred_o, emb_o = M.wrapper_i3d_forward(sd, x)
+    assert (pred - pred_o).abs().max() < 1e-4 and (emb.float() - emb_o).abs().max() < 1e-5 and torch.equal(logits, pred)
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "wrapper_i3d_v1.npz"), pred=pred.numpy(), emb=emb.float().numpy(),
+                        feat=feat.numpy())
+    print("wrapper_i3d.forward: oracle == reference; wrote wrapper_i3d_v1.npz")
+
+
 def main():
     load_fa_model, load_ft_model = import_reference()
+    wrapper_forward_golden(load_ft_model)
     torch.set_num_threads(os.cpu_count())
     out = {}
     for name, arch, hw, reso, wseeds, cseeds in CASES:

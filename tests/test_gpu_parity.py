@@ -586,3 +586,56 @@ def test_device_side_mgfn_consumer_matches_reference_getitem(name):
         assert np.allclose(got, want, rtol=2e-6, atol=1e-6), float(np.abs(got - want).max())
     with pytest.raises(RuntimeError, match="CUDA"):
         consumer.getitem_test(torch.zeros(4, 8))
+
+
+@pytest.mark.parametrize("arch,hw", [("unet", (104, 136)), ("unet++", (96, 144))])
+def test_anonymizer_only_streaming_at_native_resolution(arch, hw):
+    """SURVEY 8f-4 (visualization/visualize_anonymization.py:65-115): every frame of a video through the anonymizer at
+    its native resolution - sizes that are neither 112 nor 224, for the UNet not even a multiple of 16 (the F.pad branch
+    of unet_parts.py:57-63) - in chunks, against the fp32 oracle; then the script's colour flip and min-max uint8."""
+    from aux_code.model_loaders import load_fa_model
+    from tedspad_b200 import visualization as V
+    H, W = hw
+    frames = torch.from_numpy(M.structured_clip_u8(31, 10, H, W))                   # uint8 [10,H,W,3]
+    x = frames.permute(0, 3, 1, 2).float() / 255.0                                   # ToPILImage -> ToTensor
+    with torch.no_grad():
+        sd = M.calibrated_state_dict(arch, 21, x)
+        ref = M.anonymizer_forward(arch, sd, x)
+    fa = load_fa_model(arch=arch)
+    fa.load_state_dict(sd, strict=True)
+    fa = fa.cuda().eval()
+    got = V.anonymize_frames(fa, frames, chunk=4)
+    assert got.shape == (10, 3, H, W) and got.dtype == torch.float32 and got.is_cuda
+    want = torch.flip(ref, dims=[1])
+    err = (got.cpu() - want).abs()
+    scale = float(want.abs().max())
+    print(f"\n{arch} {H}x{W}: max err {err.max():.4f}, rms {err.pow(2).mean().sqrt():.5f}, |ref|max {scale:.3f}")
+    assert err.max() < 0.06 * max(scale, 1.0) and err.pow(2).mean().sqrt() < 0.012 * max(scale, 1.0)
+    vid = V.to_uint8_video(got)
+    ref_vid = V.to_uint8_video(want)
+    assert vid.shape == (10, H, W, 3) and vid.dtype == np.uint8
+    assert np.abs(vid.astype(np.int32) - ref_vid.astype(np.int32)).mean() < 2.0
+    # the module call the script itself makes (fa_model(inputs) on float frames) gives the same images
+    with torch.no_grad():
+        direct = fa(x[:3].cuda())
+    assert (direct - torch.flip(got[:3], dims=[1])).abs().max() < 0.02 * max(scale, 1.0)
+
+
+def test_wrapper_i3d_forward_logits_and_embedding():
+    """The module protocol remnants of VERDICT r1: wrapper_i3d.forward (model_loaders.py:265-268) and I3Res50.forward
+    (large_i3d.py:229-246) in eval mode - logits through the fc head, the 128-d L2-normalised mlp embedding."""
+    name = "unet_largei3d_224"
+    _, ft = _modules(name)
+    sd_ft = _cases.case_weights(name)[1]
+    clip = _cases.case_clip(name)
+    _, enc_ref, _ = _cases.oracle_features(name, clip)
+    with torch.no_grad():
+        pred_ref, emb_ref = M.wrapper_i3d_forward(sd_ft, enc_ref)
+        pred, emb = ft(enc_ref.cuda())
+        logits, feat = ft.i3d(enc_ref.cuda())
+    assert pred.shape == (1, 102) and emb.shape == (1, 128) and feat.shape == (2048,)
+    mp, me = _cases.parity_metrics(pred.cpu(), pred_ref), _cases.parity_metrics(emb.cpu(), emb_ref)
+    print(f"\nwrapper_i3d.forward: pred cos={mp['cos']:.6f} max_abs={mp['max_abs']:.4f}; embedding cos={me['cos']:.6f} "
+          f"max_abs={me['max_abs']:.4f} norm={float(emb.norm()):.5f}")
+    assert mp["cos"] >= 0.999 and me["cos"] >= 0.999 and abs(float(emb.norm()) - 1.0) < 1e-3
+    assert torch.equal(logits, pred)

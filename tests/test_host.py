@@ -534,8 +534,8 @@ def test_graph_cache_protocol(monkeypatch):
             log.append("replay")
 
     class FakeCapture:
-        def __init__(self, g):
-            pass
+        def __init__(self, g, capture_error_mode="global"):
+            assert capture_error_mode == "thread_local"
 
         def __enter__(self):
             log.append("capture")

@@ -153,3 +153,16 @@ def test_unetpp_oracle_encoder_matches_torchvision_resnet18_and_is_discriminativ
     f2 = _cases.oracle_features(name, _cases.case_clip(name, "control"))[2]
     ctrl = float(torch.nn.functional.cosine_similarity(f1, f2, dim=0))
     assert ctrl < 0.9995, ctrl
+
+
+def test_wrapper_i3d_forward_oracle_matches_reference_golden():
+    """oracle wrapper_i3d_forward == the unmodified reference's wrapper_i3d.forward / I3Res50.forward
+    (tests/golden/wrapper_i3d_v1.npz from make_golden.py), weights and clip regenerated from seeds."""
+    import os
+    G3 = np.load(os.path.join(os.path.dirname(_cases.GOLDEN), "wrapper_i3d_v1.npz"))
+    x = torch.rand(2, 3, 8, 64, 64, generator=torch.Generator().manual_seed(17))
+    sd = M.calibrated_state_dict("largei3d", 3, x)
+    with torch.no_grad():
+        pred, emb = M.wrapper_i3d_forward(sd, x)
+    assert np.abs(pred.numpy() - G3["pred"]).max() < 1e-4 and np.abs(emb.numpy() - G3["emb"]).max() < 1e-5
+    assert np.allclose(np.linalg.norm(G3["emb"], axis=1), 1.0, atol=1e-5)
