@@ -354,6 +354,23 @@ def group_ops():
     except Exception:
         RESULTS.append(("avgpool", False))
         print(f"[FAIL] avgpool: EXCEPTION\n{traceback.format_exc()}", flush=True)
+    # row-wise L2 normalisation (mlp embedding head) and the linear helper
+    try:
+        x = torch.randn(5, 128, generator=g).to(DEV)
+        x[3] = 0
+        want = F.normalize(x, p=2, dim=1)
+        got = ops.l2_normalize_rows(x.clone())
+        report("l2_normalize_rows", got, want, tol_rel=1e-6)
+        w = torch.randn(24, 40, generator=g).to(DEV)
+        b = torch.randn(24, generator=g).to(DEV)
+        pc = ops.PackedConv(w, b, None, device=DEV)
+        from tedspad_b200.engine import _Buffers
+        xin = torch.randn(7, 40, generator=g).to(DEV)
+        y = ops.linear(xin, pc, (_Buffers(DEV), "lin"))
+        report("linear 40->24 through the convolution kernel", y, F.linear(bf(xin), bf(w), b), tol_rel=1e-2)
+    except Exception:
+        RESULTS.append(("l2_normalize / linear", False))
+        print(f"[FAIL] l2_normalize / linear: EXCEPTION\n{traceback.format_exc()}", flush=True)
     # nchw -> channels-last
     try:
         x = torch.rand(4, 3, 20, 24, generator=g).to(DEV)
