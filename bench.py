@@ -249,10 +249,18 @@ def sharded_dataset_run(ext_factory, device, rank, world, dist, n_videos=256, nc
     # warm-up on a throw-away folder (buffer allocation for this crop count, plans)
     warm = tempfile.mkdtemp(prefix="tedspad_warm_")
     from tedspad_b200.extraction import extract_dataset
-    extract_dataset(ext, videos[:1], warm, 0, 1, log=lambda *_: None)
+    err = None
+    try:
+        extract_dataset(ext, videos[:1], warm, 0, 1, log=lambda *_: None)
+    except Exception as e:  # noqa: BLE001
+        err = f"rank {rank}: {type(e).__name__}: {e}"
     shutil.rmtree(warm, ignore_errors=True)
-    if dist is not None:
-        dist.barrier()
+    if dist is not None:    # fail on every rank or on none: a rank that leaves alone hangs the others in the next collective
+        errs = [None] * world
+        dist.all_gather_object(errs, err)
+        err = "; ".join(e for e in errs if e) or None
+    if err:
+        raise RuntimeError("sharded warm-up failed: " + err)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -471,29 +479,67 @@ def main():
     if not args.no_extras:
         def ext_factory(ncrops):
             return SnippetExtractor(fa, ft, reso=RESO, batch_clips=B, ncrops=ncrops)
-        if world > 1:
-            line["sharded"] = sharded_dataset_run(ext_factory, device, rank, world, dist, n_videos=args.sharded_videos)
-            line["sharded"]["efficiency_vs_replicas"] = line["sharded"]["value"] / clips_per_s
-        else:
-            # other encoder / anonymizer pairs of the boundary, same step definition, fewer steps
-            archs = {}
-            for key, fa_arch, ft_arch in (("unet+largei3d", "unet", "largei3d"), ("unet++ +largei3d (reference scripts' default)", "unet++", "largei3d")):
-                fa2, ft2 = build_models(device, fa_arch, ft_arch)
-                ext2 = SnippetExtractor(fa2, ft2, reso=RESO, batch_clips=B)
-                for i in range(3):
-                    ext2.features_of_clips(dev_sets[i % 2], desc, (ch, cw))
-                k = max(3, args.steps // 2)
-                ms2 = timed(lambda i: ext2.features_of_clips(dev_sets[i % 2], desc, (ch, cw)), k)
-                archs[key] = {"value": B * k / (ms2 / 1e3), "unit": "clips/s", "ms_per_step": ms2 / k, "steps": k}
-                archs[key + " batch-1 drop-in loop"] = dropin_batch1_clips_per_s(fa2, ft2, device)
-                del ext2, fa2, ft2
+
+        def guarded(key, fn):
+            """An extra must never cost the headline line: record the error instead of dying."""
+            try:
+                line[key] = fn()
+            except Exception as e:  # noqa: BLE001
+                line[key] = {"error": f"{type(e).__name__}: {e}"[:300]}
                 torch.cuda.empty_cache()
-            line["other_archs"] = archs
+
+        if world > 1:
+            def sharded():
+                out = sharded_dataset_run(ext_factory, device, rank, world, dist, n_videos=args.sharded_videos)
+                out["efficiency_vs_replicas"] = out["value"] / clips_per_s
+                return out
+            guarded("sharded", sharded)
+        else:
+            def other_archs():
+                # other encoder / anonymizer pairs of the boundary, same step definition, fewer steps
+                archs = {}
+                for key, fa_arch, ft_arch in (("unet+largei3d", "unet", "largei3d"), ("unet++ +largei3d (reference scripts' default)", "unet++", "largei3d")):
+                    fa2, ft2 = build_models(device, fa_arch, ft_arch)
+                    ext2 = SnippetExtractor(fa2, ft2, reso=RESO, batch_clips=B)
+                    for i in range(3):
+                        ext2.features_of_clips(dev_sets[i % 2], desc, (ch, cw))
+                    k = max(3, args.steps // 2)
+                    ms2 = timed(lambda i: ext2.features_of_clips(dev_sets[i % 2], desc, (ch, cw)), k)
+                    archs[key] = {"value": B * k / (ms2 / 1e3), "unit": "clips/s", "ms_per_step": ms2 / k, "steps": k}
+                    archs[key + " batch-1 drop-in loop"] = dropin_batch1_clips_per_s(fa2, ft2, device)
+                    del ext2, fa2, ft2
+                    torch.cuda.empty_cache()
+                return archs
+
+            def batch_sweep():
+                # BASELINE configs[4]: throughput over the batch size (8-128 clips per step, 5-crop: the five crop boxes
+                # of each snippet, so a step of B clips reads B/5 snippets' frames), same networks as the headline
+                sweep = {}
+                (ch5, cw5), boxes5 = crop_boxes(*SRC_HW, ncrops=5)
+                for Bs in (8, 16, 64, 128):
+                    ext_s = SnippetExtractor(fa, ft, reso=RESO, batch_clips=Bs, ncrops=5)
+                    d5 = np.zeros((Bs, T, 4), dtype=np.int32)
+                    for c_ in range(Bs):
+                        t_, l_, f_ = boxes5[c_ % 5]
+                        d5[c_, :, 0] = (c_ // 5) * T + np.arange(T)
+                        d5[c_, :, 1], d5[c_, :, 2], d5[c_, :, 3] = t_, l_, f_
+                    d5 = d5.reshape(-1, 4)
+                    for i in range(3):
+                        ext_s.features_of_clips(dev_sets[i % 2], d5, (ch5, cw5))
+                    k = 6 if Bs <= 64 else 4
+                    ms_s = timed(lambda i: ext_s.features_of_clips(dev_sets[i % 2], d5, (ch5, cw5)), k)
+                    sweep[str(Bs)] = round(Bs * k / (ms_s / 1e3), 1)
+                    del ext_s
+                return sweep
+
+            guarded("other_archs", other_archs)
+            guarded("batch_sweep_5crop_clips_per_s", batch_sweep)
             del ext
-            fa.__dict__.pop("_tsp_executor", None); ft.__dict__.pop("_tsp_executor", None)
-            fa.__dict__.pop("_tsp_sig", None); ft.__dict__.pop("_tsp_sig", None)
+            for m in (fa, ft):
+                m.__dict__.pop("_tsp_executor", None)
+                m.__dict__.pop("_tsp_sig", None)
             torch.cuda.empty_cache()
-            line["cudnn_baseline"] = cudnn_reference_clips_per_s(device)
+            guarded("cudnn_baseline", lambda: cudnn_reference_clips_per_s(device))
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cps, threads, sample = cpu_reference_clips_per_s(n_timed=8)
         line["cpu_baseline"] = {"value": cps, "unit": "clips/s", "cores": threads, "kind": "port", "sample": sample,

@@ -485,13 +485,21 @@ def extract_dataset_distributed(extractor, videos, save_folder, log=print, stats
     rank, world = dist.get_rank(), dist.get_world_size()
     import time
     t0 = time.perf_counter()
-    written = extract_dataset(extractor, videos, save_folder, rank, world, log)
+    written, err = [], None
+    try:
+        written = extract_dataset(extractor, videos, save_folder, rank, world, log)
+    except Exception as e:  # noqa: BLE001  (reported on EVERY rank below: a rank that dies alone leaves the others
+        err = f"rank {rank}: {type(e).__name__}: {e}"          # waiting in the gather forever)
     if stats is not None:   # this rank's own shard, before the closing manifest gather (which waits for the slowest rank)
-        if torch.cuda.is_available():
+        if torch.cuda.is_available() and err is None:
             torch.cuda.synchronize()
         stats["extract_s"] = time.perf_counter() - t0
     gathered = [None] * world
-    dist.all_gather_object(gathered, written)          # control plane only: file names, after the work is done
+    dist.all_gather_object(gathered, (written, err))   # control plane only: file names, after the work is done
+    errors = [e for _, e in gathered if e]
+    if errors:
+        raise RuntimeError("sharded extraction failed: " + "; ".join(errors))
+    gathered = [w for w, _ in gathered]
     manifest = {}
     for r, files in enumerate(gathered):
         for f in files:

@@ -329,6 +329,48 @@ def _stub_videos():
     return vids
 
 
+class _FailingExtractor(_StubExtractor):
+    def extract_video(self, frames):
+        import torch.distributed as dist
+        if dist.get_rank() == 1:
+            raise ValueError("decoder exploded")
+        return super().extract_video(frames)
+
+
+def _gloo_failing_worker(rank, world, port, folder, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        try:
+            extraction.extract_dataset_distributed(_FailingExtractor(), _stub_videos(), folder, log=lambda *_: None)
+            q.put((rank, "no error"))
+        except RuntimeError as e:
+            q.put((rank, str(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world_size_2_gloo_failure_is_reported_on_every_rank(tmp_path):
+    """A rank whose shard fails must not leave the others waiting in the manifest gather: the error travels with the
+    gather and every rank raises (bench.py relies on this to keep its JSON line when an extra fails)."""
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as s_:
+        s_.bind(("127.0.0.1", 0))
+        port = s_.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_failing_worker, args=(r, 2, port, str(tmp_path / "out"), q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    assert set(got) == {0, 1}
+    assert all("rank 1: ValueError: decoder exploded" in m for m in got.values()), got
+
+
 def _gloo_worker(rank, world, port, folder, q):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
