@@ -449,7 +449,7 @@ __global__ void __launch_bounds__(256) mgfn_rows_kernel(const MgfnP p) {
 // first staged version showed both ISSUE-bound (86 % issue-active, 345 M warp instructions for 25.7 M pixels).
 constexpr int PP_KMAX = 8;
 constexpr int PP_MAXOUT = 4096;   // (the band height shrinks until the staged rows + planes fit in shared memory)
-constexpr int PP_THREADS = 256;
+constexpr int PP_THREADS = 224;   // = the 224 output columns of the hot configuration: no idle thread in the compute phase
 
 struct PrepP {
   const uint8_t* frames;
@@ -460,7 +460,9 @@ struct PrepP {
   TView y;
   float* frames_f32;
   int BH, max_rows, pitch;   // output rows per block; staged source rows (bound); staged row pitch in bytes
+  float sx, supx, invx;      // AA_FLOAT x axis: scale = crop_w / Wo, support = max(scale, 1), 1 / support (host floats)
 };
+constexpr int PP_FAST_BH = 8;   // the FAST instantiations: bands of exactly 8 rows, vector stores, no fp32 copy
 
 // One entry of a resampling table: first tap, tap count, K weights (zero beyond the count).
 // AA_FLOAT follows aten's _upsample_bilinear2d_aa (align_corners=False): support = max(scale,1),
@@ -522,7 +524,7 @@ __device__ __forceinline__ void axis_entry(int in, int out, int resample, int i,
     }
 #pragma unroll
     for (int x = 0; x < K; ++x)
-      if (tot != 0.f && x < n) wf[x] /= tot;
+      if (tot != 0.f && x < n && wf[x] != 0.f) wf[x] /= tot;   // (0 / tot = 0, but through the division's slow path)
     lo = xmin;
     cnt = n;
   }
@@ -544,21 +546,27 @@ __device__ __forceinline__ float u8_over_255(uint32_t b) {
 // float(b) for a byte: 2^23 + b is exact in fp32 (OR the byte into the mantissa of 2^23), minus 2^23
 __device__ __forceinline__ float u8_to_float(uint32_t b) { return __uint_as_float(0x4b000000u | b) - 8388608.f; }
 
-template <bool PIL, int KX, int KY>
-__global__ void __launch_bounds__(PP_THREADS) preprocess_kernel(const PrepP p) {
+// FAST = 0: any band height / output layout / optional fp32 copy.  FAST = 4 | 8: the hot configuration - bands of
+// PP_FAST_BH full rows, pixels of FAST channels stored with one vector store, no fp32 copy: the vertical loop unrolls
+// completely and its addressing constant-folds (the generic loop spent 50 instructions per pixel, half of them uniform
+// bookkeeping).
+template <bool PIL, int KX, int KY, int FAST>
+__global__ void __launch_bounds__(PP_THREADS, (FAST != 0 && !PIL && KY == 2) ? 7 : 1) preprocess_kernel(const PrepP p) {
   extern __shared__ __align__(16) uint8_t pp_smem[];
-  const int Ho = p.y.H, Wo = p.y.W, BH = p.BH;
+  const int Ho = p.y.H, Wo = p.y.W, BH = FAST ? PP_FAST_BH : p.BH;
   int* ylo = reinterpret_cast<int*>(pp_smem);                   // [BH + 1]: first source row per output row, then the band's end
   int* rsh = ylo + BH + 1;                                      // byte shift of every staged row
   float* ywf = reinterpret_cast<float*>(rsh + p.max_rows);      // [KY][BH]
   int* ywi = reinterpret_cast<int*>(ywf);
-  uint8_t* raw = reinterpret_cast<uint8_t*>(ywf + KY * BH);
-  raw += (16 - (reinterpret_cast<uintptr_t>(raw) & 15)) & 15;
-  float* hf = reinterpret_cast<float*>(raw + static_cast<size_t>(p.max_rows) * p.pitch);   // [row][channel][column]
-  uint8_t* hb = reinterpret_cast<uint8_t*>(hf);
+  // (offsets computed in words: a pointer -> integer cast would lose the shared address space and make the compiler
+  // rebuild the shared-window base inside every loop)
+  const int raw_off = ((BH + 1 + p.max_rows + KY * BH + 3) & ~3) * 4;
+  uint8_t* raw = pp_smem + raw_off;                                                          // 16-byte aligned
+  float* hf = reinterpret_cast<float*>(pp_smem + raw_off + p.max_rows * p.pitch);            // [row][channel][column]
+  uint8_t* hb = pp_smem + raw_off + p.max_rows * p.pitch;
 
   const int n = blockIdx.y;
-  const int oy0 = blockIdx.x * BH, nrow = min(BH, Ho - oy0);
+  const int oy0 = blockIdx.x * BH, nrow = FAST ? PP_FAST_BH : min(BH, Ho - oy0);
   if (threadIdx.x < nrow) {
     int lo, cnt, wi[KY];
     float wf[KY];
@@ -582,13 +590,17 @@ __global__ void __launch_bounds__(PP_THREADS) preprocess_kernel(const PrepP p) {
   if (src >= 0) {
     // stage rows [top + r0, top + r0 + R) x columns [col0, col0 + crop_w) (the mirrored window when flipped), raw bytes
     const int col0 = flip ? p.Ws - left - p.crop_w : left;
-    const int chunks = (nb + 15 + 15) >> 4;
     const uint8_t* fend = p.frames + p.frames_bytes;
-    for (int r = threadIdx.x / chunks, i = threadIdx.x - r * chunks; r < R;) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int r = warp; r < R; r += PP_THREADS / 32) {          // a warp per source row: the row address once per warp
       const uint8_t* g = p.frames + ((static_cast<long long>(src) * p.Hs + top + r0 + r) * p.Ws + col0) * 3;
       const int shift = static_cast<int>(reinterpret_cast<uintptr_t>(g) & 15);
-      const uint8_t* a = g - shift + 16 * i;
-      if (16 * i - shift < nb) {
+      const uint8_t* a0 = g - shift;
+      const int nchunk = (shift + nb + 15) >> 4;
+      uint8_t* dst = raw + r * p.pitch;
+      if (lane == 0) rsh[r] = shift;
+      for (int i = lane; i < nchunk; i += 32) {
+        const uint8_t* a = a0 + 16 * i;
         uint4 q;
         if (a + 16 <= fend) {
           q = __ldg(reinterpret_cast<const uint4*>(a));
@@ -597,31 +609,87 @@ __global__ void __launch_bounds__(PP_THREADS) preprocess_kernel(const PrepP p) {
 #pragma unroll
           for (int k = 0; k < 16; ++k) qb[k] = (a + k < fend) ? a[k] : 0;
         }
-        if (i == 0) rsh[r] = shift;
-        *reinterpret_cast<uint4*>(raw + r * p.pitch + 16 * i) = q;
+        *reinterpret_cast<uint4*>(dst + 16 * i) = q;
       }
-      i += PP_THREADS;   // next item of this thread: advance (r, i) without a division
-      while (i >= chunks) { i -= chunks; ++r; }
     }
   }
   __syncthreads();
 
-  const float inv255 = 1.f / 255.f;   // AA: pixels are /255 (dali_extraction.py:41); applied to the horizontal sums (the
-                                      // reference divides the bytes first: same value to ~1e-7, far below bf16)
+  const float inv255 = 1.f / (255.f * 4194304.f);   // AA: pixels are /255 (dali_extraction.py:41) and the horizontal
+                                                    // weights are 22-bit fixed point: both applied to the sums
+  constexpr bool STREAM = FAST != 0 && !PIL && KY == 2;
   const int cpy = p.y.C;   // 8 (UNet stem) or 4 (7x7 stems) when vectorisable
   const bool vec8 = cpy == 8 && ((p.y.ld | p.y.coff) & 7) == 0, vec4 = cpy == 4 && ((p.y.ld | p.y.coff) & 3) == 0;
   for (int ox = threadIdx.x; ox < Wo; ox += PP_THREADS) {
     if (src >= 0) {
       // ---- horizontal pass: this column of every staged row
       int xl, xn, xwi[KX];
-      float xwf[KX];
-      axis_entry<KX>(p.crop_w, Wo, p.resample, ox, xl, xn, xwf, xwi);
+      if (PIL) {
+        float xwf[KX];
+        axis_entry<KX>(p.crop_w, Wo, p.resample, ox, xl, xn, xwf, xwi);
+      } else {
+        // aten's antialias weights of this column (same float arithmetic as axis_entry; scale / support / 1 / support
+        // come from the host), normalised and quantised to 22-bit fixed point with ONE division
+        const float center = p.sx * (ox + 0.5f);
+        xl = max(static_cast<int>(center - p.supx + 0.5f), 0);
+        xn = min(min(static_cast<int>(center + p.supx + 0.5f), p.crop_w) - xl, KX);
+        float w[KX], tot = 0.f;
+#pragma unroll
+        for (int b = 0; b < KX; ++b) {
+          const float a = fabsf((b + xl - center + 0.5f) * p.invx);
+          w[b] = (b < xn && a < 1.f) ? 1.f - a : 0.f;
+          tot += w[b];
+        }
+        const float q = tot != 0.f ? 4194304.f / tot : 0.f;
+#pragma unroll
+        for (int b = 0; b < KX; ++b) xwi[b] = static_cast<int>(w[b] * q + 0.5f);
+      }
       int off[KX];   // byte offset of tap b inside a staged row (mirrored when the crop comes from the flipped frame)
 #pragma unroll
       for (int b = 0; b < KX; ++b) {
         const int col = min(xl + b, p.crop_w - 1);
         off[b] = (flip ? p.crop_w - 1 - col : col) * 3;
       }
+      if (STREAM) {
+        // STREAMING form of the two passes (2 vertical taps: every up-scaling axis): the thread walks down its column
+        // with the horizontally interpolated source rows yl and yl + 1 of the current output row in registers; the next
+        // output row starts at the same source row (both re-used), the next one (one new row) or further down (two),
+        // which is the same for every thread of the block (uniform branches).  No plane in shared memory: 3 stores per
+        // source row and 6 loads + their addressing per output pixel less; the values and the order of the two FMAs
+        // are those of the generic path, bit for bit.
+        auto hrow = [&](int r, float& v0, float& v1, float& v2) {
+          const uint8_t* rowp = raw + r * p.pitch + rsh[r];
+          int h0 = 0, h1 = 0, h2 = 0;
+#pragma unroll
+          for (int b = 0; b < KX; ++b) {
+            const uint8_t* px = rowp + off[b];
+            h0 += px[0] * xwi[b]; h1 += px[1] * xwi[b]; h2 += px[2] * xwi[b];
+          }
+          v0 = static_cast<float>(h0) * inv255; v1 = static_cast<float>(h1) * inv255; v2 = static_cast<float>(h2) * inv255;
+        };
+        __nv_bfloat16* yq = elem_ptr_w(p.y, pix_index(p.y, n, 0, oy0, ox), 0);
+        const int y_row = p.y.Wp * p.y.ld;
+        const int rmax = R - 1;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f;
+        int base = -4;
+#pragma unroll
+        for (int ly = 0; ly < PP_FAST_BH; ++ly, yq += y_row) {
+          const int yl = ylo[ly] - r0;
+          if (yl == base + 1) {
+            a0 = b0; a1 = b1; a2 = b2;
+            hrow(min(yl + 1, rmax), b0, b1, b2);
+          } else if (yl != base) {
+            hrow(yl, a0, a1, a2);
+            hrow(min(yl + 1, rmax), b0, b1, b2);
+          }
+          base = yl;
+          const float w0 = ywf[ly], w1 = ywf[BH + ly];
+          const float o0 = fmaf(w1, b0, fmaf(w0, a0, 0.f)), o1 = fmaf(w1, b1, fmaf(w0, a1, 0.f)), o2 = fmaf(w1, b2, fmaf(w0, a2, 0.f));
+          const uint32_t lo = cvt_bf16x2(o0, o1, false), hi = cvt_bf16x2(o2, 0.f, false);
+          if (FAST == 8) *reinterpret_cast<uint4*>(yq) = make_uint4(lo, hi, 0u, 0u);
+          else *reinterpret_cast<uint2*>(yq) = make_uint2(lo, hi);
+        }
+      } else
       for (int r = 0; r < R; ++r) {
         const uint8_t* rowp = raw + r * p.pitch + rsh[r];
         if (PIL) {
@@ -635,27 +703,33 @@ __global__ void __launch_bounds__(PP_THREADS) preprocess_kernel(const PrepP p) {
           hp[0] = static_cast<uint8_t>(clip8_fixed(h0)); hp[Wo] = static_cast<uint8_t>(clip8_fixed(h1));
           hp[2 * Wo] = static_cast<uint8_t>(clip8_fixed(h2));
         } else {
-          // sum of w_b * byte_b, the 1/255 applied to the sum; bytes turned into floats with the 2^23 trick (OR into
-          // the mantissa, one FADD) - I2F runs at a fraction of the FFMA rate
-          float h0 = 0.f, h1 = 0.f, h2 = 0.f;
+          // sum of w_b * byte_b with the weights in 22-bit fixed point (|dw| <= 2^-23: 4e-7 on a [0,1] pixel, two
+          // orders below the 3e-5 the float kernel of aten itself is from exact arithmetic): one IMAD per byte, no
+          // byte -> float conversion; the sum (< 2^30) becomes a float once per channel, scaled by 1 / (255 * 2^22)
+          int h0 = 0, h1 = 0, h2 = 0;
 #pragma unroll
           for (int b = 0; b < KX; ++b) {
             const uint8_t* px = rowp + off[b];
-            h0 = fmaf(xwf[b], u8_to_float(px[0]), h0);
-            h1 = fmaf(xwf[b], u8_to_float(px[1]), h1);
-            h2 = fmaf(xwf[b], u8_to_float(px[2]), h2);
+            h0 += px[0] * xwi[b]; h1 += px[1] * xwi[b]; h2 += px[2] * xwi[b];
           }
           float* hp = hf + (r * 3) * Wo + ox;
-          hp[0] = h0 * inv255; hp[Wo] = h1 * inv255; hp[2 * Wo] = h2 * inv255;
+          hp[0] = static_cast<float>(h0) * inv255; hp[Wo] = static_cast<float>(h1) * inv255;
+          hp[2 * Wo] = static_cast<float>(h2) * inv255;
         }
       }
     }
+    if (STREAM && src >= 0) continue;   // (written by the streaming form above)
     // ---- vertical pass: down the column (only this thread wrote / reads column ox of the planes: no barrier needed)
     __nv_bfloat16* yp = elem_ptr_w(p.y, pix_index(p.y, n, 0, oy0, ox), 0);
-    const long long y_row = static_cast<long long>(p.y.Wp) * p.y.ld;
+    const int y_row = p.y.Wp * p.y.ld;                          // elements per output row (< 2^31: PP_MAXOUT x ld)
     const long long plane = static_cast<long long>(Ho) * Wo;
     float* fo = p.frames_f32 ? p.frames_f32 + static_cast<long long>(n) * 3 * plane + static_cast<long long>(oy0) * Wo + ox : nullptr;
-    for (int ly = 0; ly < nrow; ++ly, yp += y_row) {
+    const bool f32 = !FAST && fo != nullptr;
+    const int hstride = 3 * Wo, rmax = R - 1;
+    const float* hcol = hf + ox;
+    const uint8_t* bcol = hb + ox;
+#pragma unroll
+    for (int ly = 0; ly < (FAST ? PP_FAST_BH : nrow); ++ly) {
       float o0 = 0.f, o1 = 0.f, o2 = 0.f;
       if (src >= 0) {
         const int yl = ylo[ly] - r0;
@@ -663,7 +737,7 @@ __global__ void __launch_bounds__(PP_THREADS) preprocess_kernel(const PrepP p) {
           int a0 = 1 << 21, a1 = 1 << 21, a2 = 1 << 21;
 #pragma unroll
           for (int a = 0; a < KY; ++a) {
-            const uint8_t* hp = hb + (min(yl + a, R - 1) * 3) * Wo + ox;
+            const uint8_t* hp = bcol + min(yl + a, rmax) * hstride;
             const int ky = ywi[a * BH + ly];
             a0 += hp[0] * ky; a1 += hp[Wo] * ky; a2 += hp[2 * Wo] * ky;
           }
@@ -673,24 +747,25 @@ __global__ void __launch_bounds__(PP_THREADS) preprocess_kernel(const PrepP p) {
         } else {
 #pragma unroll
           for (int a = 0; a < KY; ++a) {
-            const float* hp = hf + (min(yl + a, R - 1) * 3) * Wo + ox;
+            const float* hp = hcol + min(yl + a, rmax) * hstride;
             const float wy = ywf[a * BH + ly];
             o0 = fmaf(wy, hp[0], o0); o1 = fmaf(wy, hp[Wo], o1); o2 = fmaf(wy, hp[2 * Wo], o2);
           }
         }
       }
       const uint32_t lo = cvt_bf16x2(o0, o1, false), hi = cvt_bf16x2(o2, 0.f, false);
-      if (vec8) {
-        *reinterpret_cast<uint4*>(yp) = make_uint4(lo, hi, 0u, 0u);
-      } else if (vec4) {
-        *reinterpret_cast<uint2*>(yp) = make_uint2(lo, hi);
+      __nv_bfloat16* yq = yp + ly * y_row;
+      if (FAST == 8 || (!FAST && vec8)) {
+        *reinterpret_cast<uint4*>(yq) = make_uint4(lo, hi, 0u, 0u);
+      } else if (FAST == 4 || (!FAST && vec4)) {
+        *reinterpret_cast<uint2*>(yq) = make_uint2(lo, hi);
       } else {
         const float o[3] = {o0, o1, o2};
-        for (int c = 0; c < cpy; ++c) yp[c] = __float2bfloat16_rn(c < 3 ? o[c] : 0.f);
+        for (int c = 0; c < cpy; ++c) yq[c] = __float2bfloat16_rn(c < 3 ? o[c] : 0.f);
       }
-      if (fo) {
-        fo[0] = o0; fo[plane] = o1; fo[2 * plane] = o2;
-        fo += Wo;
+      if (f32) {
+        float* fq = fo + ly * Wo;
+        fq[0] = o0; fq[plane] = o1; fq[2 * plane] = o2;
       }
     }
   }
@@ -1098,24 +1173,39 @@ extern "C" int tedspad_preprocess(const uint8_t* frames, int32_t F, int32_t Hs, 
   p.crop_h = crop_h; p.crop_w = crop_w; p.resample = resample;
   p.y = make_view(*y);
   p.frames_f32 = frames_f32;
+  p.sx = static_cast<float>(crop_w) / static_cast<float>(y->W);
+  p.supx = p.sx >= 1.f ? p.sx : 1.f;
+  p.invx = p.sx >= 1.f ? 1.f / p.sx : 1.f;
   // band height: as many output rows per block as keep the staged rows + the horizontal-pass planes under 48 KB
   const int nb = crop_w * 3, KY = KYs;
+  const bool v8 = y->C == 8 && ((y->ld | y->coff) & 7) == 0, v4 = y->C == 4 && ((y->ld | y->coff) & 3) == 0;
+  // the streaming instantiations (FAST, aten path, 2 vertical taps) keep the interpolated rows in registers: no planes,
+  // a quarter of the shared memory, twice the resident blocks to hide the staging loads behind
+  const bool maybe_stream = !pil && KXs == 3 && KYs == 2 && y->H % PP_FAST_BH == 0 && frames_f32 == nullptr && (v8 || v4);
   p.pitch = static_cast<int>(round_up(nb + 32, 16));
   size_t smem = 0;
   for (p.BH = 8; p.BH >= 1; p.BH >>= 1) {
     p.max_rows = static_cast<int>(ceil((p.BH - 1) * sy + 2.0 * (sy < 1 ? 1 : sy) + 2.0));
     if (p.max_rows > crop_h) p.max_rows = crop_h;
-    smem = (p.BH + 1 + p.max_rows) * sizeof(int) + static_cast<size_t>(KY) * p.BH * sizeof(float) + 16 +
-           static_cast<size_t>(p.max_rows) * p.pitch + static_cast<size_t>(p.max_rows) * 3 * y->W * (pil ? 1 : sizeof(float)) + 16;
+    smem = static_cast<size_t>((p.BH + 1 + p.max_rows + KY * p.BH + 3) & ~3) * 4 +
+           static_cast<size_t>(p.max_rows) * p.pitch +
+           (maybe_stream && p.BH == PP_FAST_BH ? 0 : static_cast<size_t>(p.max_rows) * 3 * y->W * (pil ? 1 : sizeof(float))) + 16;
     if (smem <= 48 * 1024) break;
   }
   TSP_CHECK(p.BH >= 1, "preprocess: a %d-pixel wide crop does not fit in shared memory", crop_w);
   dim3 grid((y->H + p.BH - 1) / p.BH, n_out);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-#define TSP_PREP(PIL_, KX_, KY_) TSP_CUDA(launch_kernel(preprocess_kernel<PIL_, KX_, KY_>, grid, dim3(PP_THREADS), smem, st, p))
-#define TSP_PREP_Y(PIL_, KX_) do { if (KYs == 2) TSP_PREP(PIL_, KX_, 2); else if (KYs == 5) TSP_PREP(PIL_, KX_, 5); else TSP_PREP(PIL_, KX_, 8); } while (0)
+#define TSP_PREP(PIL_, KX_, KY_, FAST_) TSP_CUDA(launch_kernel(preprocess_kernel<PIL_, KX_, KY_, FAST_>, grid, dim3(PP_THREADS), smem, st, p))
+#define TSP_PREP_Y(PIL_, KX_) do { if (KYs == 2) TSP_PREP(PIL_, KX_, 2, 0); else if (KYs == 5) TSP_PREP(PIL_, KX_, 5, 0); else TSP_PREP(PIL_, KX_, 8, 0); } while (0)
 #define TSP_PREP_X(PIL_) do { if (KXs == 3) TSP_PREP_Y(PIL_, 3); else if (KXs == 5) TSP_PREP_Y(PIL_, 5); else TSP_PREP_Y(PIL_, 8); } while (0)
-  if (pil) TSP_PREP_X(true); else TSP_PREP_X(false);
+  // the hot configurations (UCF-Crime / XD 240x320 -> 224: 3 x 2 taps; ShanghaiTech 384 -> 224: 5 x 5 taps) in full
+  // bands of 8 rows with vector pixel stores and no fp32 copy run the FAST instantiations
+  const bool fast = p.BH == PP_FAST_BH && y->H % PP_FAST_BH == 0 && frames_f32 == nullptr && (v8 || v4);
+  if (fast && !pil && KXs == 3 && KYs == 2) { if (v8) TSP_PREP(false, 3, 2, 8); else TSP_PREP(false, 3, 2, 4); }
+  else if (fast && !pil && KXs == 5 && KYs == 5) { if (v8) TSP_PREP(false, 5, 5, 8); else TSP_PREP(false, 5, 5, 4); }
+  else if (fast && pil && KXs == 5 && KYs == 5) { if (v8) TSP_PREP(true, 5, 5, 8); else TSP_PREP(true, 5, 5, 4); }
+  else if (pil) TSP_PREP_X(true);
+  else TSP_PREP_X(false);
 #undef TSP_PREP_X
 #undef TSP_PREP_Y
 #undef TSP_PREP

@@ -419,6 +419,17 @@ def group_prep():
         ref = torch.stack(refs).to(DEV)
         report("preprocess AA float fp32", f32, ref, tol_rel=3e-5)
         report("preprocess AA bf16 layout", y.to_ncdhw()[:, :3, 0], bf(ref), tol_rel=8e-3)
+        # the same call without the fp32 copy takes the FAST instantiation (compile-time band, vector stores): its
+        # pixels must equal the generic instantiation's bit for bit, for 8- and for 4-channel pixels
+        for cpad in (8, 4):
+            ya = ops.CLTensor(5, 1, 224, 224, cpad, device=DEV)
+            yb = ops.CLTensor(5, 1, 224, 224, cpad, device=DEV)
+            ya.buf.fill_(3.0); yb.buf.fill_(4.0)
+            ops.preprocess(frames.to(DEV), desc.to(DEV), (ch, cw), ya, L.RESAMPLE_AA_FLOAT, f32)
+            ops.preprocess(frames.to(DEV), desc.to(DEV), (ch, cw), yb, L.RESAMPLE_AA_FLOAT, None)
+            okf = bool(torch.equal(ya.buf, yb.buf))
+            RESULTS.append((f"preprocess fast == generic C={cpad}", okf))
+            print(f"[{'PASS' if okf else 'FAIL'}] preprocess AA: FAST instantiation == generic, {cpad}-channel pixels")
         cc = TF.center_crop(v[0:1], (ch, cw))
         ok = torch.equal(cc, v[0:1, :, top:top + ch, left:left + cw])
         RESULTS.append(("center_crop offsets", ok))
@@ -475,6 +486,11 @@ def group_prep():
         d = ((f32 - ref).abs() * 255).round()
         print(f"       PIL emulation: exact={float((d == 0).float().mean()):.6f} max_lsb={int(d.max())}")
         report("preprocess PIL u8 (bit-exact)", f32, ref, tol_rel=0)
+        yb = ops.CLTensor(2, 1, 224, 224, 8, device=DEV)
+        ops.preprocess(frames.to(DEV), desc.to(DEV), (ch, cw), yb, L.RESAMPLE_PIL_U8, None)     # FAST instantiation
+        okf = bool(torch.equal(y.buf, yb.buf))
+        RESULTS.append(("preprocess PIL fast == generic", okf))
+        print(f"[{'PASS' if okf else 'FAIL'}] preprocess PIL: FAST instantiation == generic")
     except Exception:
         RESULTS.append(("preprocess PIL", False))
         print(f"[FAIL] preprocess PIL: EXCEPTION\n{traceback.format_exc()}", flush=True)
