@@ -441,8 +441,9 @@ def shard_videos(lengths, world_size):
     return [sorted(s) for s in shards]
 
 
-def extract_dataset(extractor, videos, save_folder, rank=0, world_size=1, log=print, segment=False):
-    """videos: list of (path, n_frames, loader) with loader() -> uint8 [F,H,W,3].  The partition is computed
+def extract_dataset(extractor, videos, save_folder, rank=0, world_size=1, log=print, segment=False, prefetch_workers=0):
+    """videos: list of (path, n_frames, loader) with loader() -> uint8 [F,H,W,3].  prefetch_workers > 0: the loaders of
+    the next videos run on that many threads while the current one is extracted (ingest.prefetched; for file decoders).  The partition is computed
     over the FULL list (so every rank derives the same one no matter when it starts); within its shard a
     rank skips videos whose .npy already exists - the reference's resume rule (dali_extraction.py:121).
     Each file is written by exactly one rank (atomic rename); there is no collective."""
@@ -466,7 +467,11 @@ def extract_dataset(extractor, videos, save_folder, rank=0, world_size=1, log=pr
 
     if hasattr(extractor, "extract_videos"):
         # snippets packed into full batches across this rank's videos (same rows, see SnippetExtractor.extract_videos)
-        for k, feats in extractor.extract_videos((lambda i=i: load(i)) for i in todo):
+        sources = ((lambda i=i: load(i)) for i in todo)
+        if prefetch_workers > 0:
+            from .ingest import prefetched
+            sources = prefetched(sources, workers=prefetch_workers)      # decoded tensors instead of callables
+        for k, feats in extractor.extract_videos(sources):
             save(todo[k], feats)
     else:
         for i in todo:

@@ -62,3 +62,28 @@ def cv2_dataset(paths, rgb=False):
         cap.release()
         out.append((p, n, (lambda p=p: decode_video_cv2(p, rgb)[0])))
     return out
+
+
+def prefetched(loaders, workers=4, depth=None):
+    """Runs `loaders` (callables returning a decoded video) on a pool of `workers` threads, at most `depth` videos ahead
+    of the consumer, and yields their results IN ORDER.  cv2 releases the GIL while it decodes, so the next videos are
+    decoded while the GPU works on the current one (the reference decodes and augments on the main thread between two
+    videos: st_feature_extraction.py:87, shanghai_dl.py:43-98).  A loader's exception is re-raised at its position."""
+    import collections
+    from concurrent.futures import ThreadPoolExecutor
+    depth = depth or 2 * workers
+    it = iter(loaders)
+    pending = collections.deque()
+    with ThreadPoolExecutor(max_workers=workers) as pool:
+        def fill():
+            while len(pending) < depth:
+                fn = next(it, None)
+                if fn is None:
+                    return
+                pending.append(pool.submit(fn))
+        fill()
+        while pending:
+            fut = pending.popleft()
+            res = fut.result()
+            fill()
+            yield res

