@@ -26,6 +26,7 @@
 //   warp 10     TMEM allocator
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -334,11 +335,18 @@ __device__ __forceinline__ void epi_out(const EpiCtx& c, const uint32_t (&q)[16]
 // The epilogue role (warps 0-7).  Two warps per TMEM lane quarter.  tm == 2: warp group eg owns half eg of the tile
 // (all its columns, so the fused OutConv dot product stays inside one thread); tm == 1: the groups split the
 // 32-column chunks.
-template <bool HAS_UP, bool PAIR, int MODE, bool RELU>
+//
+// E16 (64-output CTA-pair layers: one K stage of MMAs per tile is SHORTER than the 8-warp epilogue of that tile, ncu
+// profiles/r2_ncu_64ch_layers.md): sixteen warps, four per TMEM lane quarter = four per scheduler, each owning ONE
+// 32-column chunk of one half (warp >> 2 = 2 * half + chunk).  A warp hands its accumulator back as soon as its single
+// tcgen05.ld has landed in registers, i.e. before any of the arithmetic; the fused OutConv dot product of a pixel is
+// completed by the chunk-0 warp from the chunk-1 warp's partial sums (shared-memory scratch, one named barrier per
+// warp pair and tile, double-buffered by tile parity).
+template <bool HAS_UP, bool PAIR, int MODE, bool RELU, bool E16>
 __device__ __forceinline__ void slab_epilogue(const SlabKParams& p, int warp, int lane, uint32_t tmem_base, const float* sm_bias,
-                                              const float* sm_ocw, uint64_t* tfull, uint64_t* tempty) {
+                                              const float* sm_ocw, uint64_t* tfull, uint64_t* tempty, float* sm_part) {
   pdl_wait();   // the previous kernel may still be reading the buffers this one writes
-  const int ew = warp & 3, eg = warp >> 2;
+  const int ew = warp & 3, eg = E16 ? (warp >> 3) : (warp >> 2);
   const int g = ew * 4 + (lane >> 3);
   const int r = lane & 7;
   const int tm = p.tm, n_tile = p.n_tile, OH = p.OH, OW = p.OW;
@@ -350,10 +358,11 @@ __device__ __forceinline__ void slab_epilogue(const SlabKParams& p, int warp, in
   c.wide_ok = ((p.y_ld | p.y_coff) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.y) & 31) == 0;
   c.res = p.res; c.res_ld = p.res_ld; c.res_coff = p.res_coff;
   int h, c_first, c_step, nch;
-  if (tm == 2) { h = eg; c_first = 0; c_step = 32; nch = nchunk_all; }
+  if (E16) { h = eg; c_first = 32 * ((warp >> 2) & 1); c_step = 64; nch = 1; }   // tm == 2, n_tile == 64
+  else if (tm == 2) { h = eg; c_first = 0; c_step = 32; nch = nchunk_all; }
   else if ((MODE == EPI_OC || MODE == EPI_OC_ONLY)) { h = 0; c_first = 0; c_step = 32; nch = eg == 0 ? nchunk_all : 0; }
   else { h = 0; c_first = 32 * eg; c_step = 64; nch = (nchunk_all + 1 - eg) >> 1; }
-  int as = 0;
+  int as = 0, tpar = 0;
   uint32_t aph = 0;
   for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
     int t = tile, q;
@@ -388,7 +397,34 @@ __device__ __forceinline__ void slab_epilogue(const SlabKParams& p, int warp, in
     mbar_wait(tfull + as, aph);
     tc_fence_after();
     uint4 ra[4], rb[4];   // EPI_RES only (dead otherwise)
-    if (HAS_UP) {   // 480-thread variant: 136 registers per thread, one chunk in flight
+    if (E16) {
+      uint32_t va[32], qa[16];
+      const int c0 = n0 + c_first;
+      tmem_ld32(t_row, va);
+      if (MODE == EPI_RES) epi_res_fetch(c, pix, c0, valid, ra);
+      tmem_ld_wait();
+      // this warp's only read of the accumulator is complete: hand it back before the arithmetic
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(tempty + as), 0));
+        else mbar_arrive(tempty + as);
+      }
+      epi_math<MODE, RELU>(c, va, c0, qa, oc, ra);
+      epi_out<MODE>(c, qa, c0, valid, pix, pool_writer, ppix);
+      if (MODE == EPI_OC || MODE == EPI_OC_ONLY) {
+        // partial 64 -> 3 dot products of the upper chunk travel to the lower chunk's warp (same pixels)
+        // (both warps block on the pair's barrier, so the writer is never more than one tile ahead of the reader:
+        // two scratch buffers alternating by tile parity are enough)
+        float* part = sm_part + ((tpar * 8 + h * 4 + ew) * 32 + lane) * 3;
+        const int bar_id = 1 + h * 4 + ew;
+        if (c_first != 0) { part[0] = oc[0]; part[1] = oc[1]; part[2] = oc[2]; }
+        __syncwarp();   // bar.sync is .aligned: the lanes diverged on `valid` above must have reconverged
+        named_bar_sync(bar_id, 64);
+        if (c_first == 0) { oc[0] += part[0]; oc[1] += part[1]; oc[2] += part[2]; }
+        tpar ^= 1;
+      }
+    } else if (HAS_UP) {   // 480-thread variant: 136 registers per thread, one chunk in flight
       uint32_t va[32], qa[16];
       for (int i = 0; i < nch; ++i) {
         const int c0 = n0 + c_first + i * c_step;
@@ -428,13 +464,15 @@ __device__ __forceinline__ void slab_epilogue(const SlabKParams& p, int warp, in
       }
     }
     // all TMEM reads of this accumulator are complete (wait::ld above): hand it back to the MMA warp
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) {
-      if (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(tempty + as), 0));
-      else mbar_arrive(tempty + as);
+    if (!E16) {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(tempty + as), 0));
+        else mbar_arrive(tempty + as);
+      }
     }
-    if ((MODE == EPI_OC || MODE == EPI_OC_ONLY) && valid && nch > 0) {
+    if ((MODE == EPI_OC || MODE == EPI_OC_ONLY) && valid && nch > 0 && (!E16 || c_first == 0)) {
       const long long plane = static_cast<long long>(OH) * OW;
       const long long o0 = static_cast<long long>(n) * 3 * plane + static_cast<long long>(oy) * OW + ox;
       const int bclip = fdiv(n, p.dv_T), tf = n - bclip * p.oc_T;   // frame n = clip bclip, time tf
@@ -487,6 +525,8 @@ __device__ __forceinline__ UpTaps up_fetch(const SlabKParams& p, int r, int iy0,
 
 constexpr int SLAB_THREADS = 352;      // warps 0-7 epilogue (two per TMEM lane quarter), 8 producer, 9 MMA, 10 TMEM alloc
 constexpr int SLAB_THREADS_UP = 480;   // + warps 11-14: up-sampling slab producers
+constexpr int SLAB_THREADS_E16 = 608;  // warps 0-15 epilogue (four per TMEM lane quarter), 16 producer, 17 MMA, 18 TMEM alloc
+constexpr int SLAB_E16_SCRATCH = 2 * 8 * 32 * 3 * 4;   // OutConv partial sums: [tile parity][half][quarter][lane][3] floats
 
 // HAS_UP: the input is the concatenation [skip | upsample2x(low-res)] of Up.forward (unet_parts.py:57-67) and the
 // up-sampled half is never materialised: for its channel blocks four producer warps interpolate the low-res
@@ -500,9 +540,11 @@ constexpr int SLAB_THREADS_UP = 480;   // + warps 11-14: up-sampling slab produc
 // with the B rows split over two SMs it is (128 + 32) rows = 80 %.  Only the leader issues MMAs; its `full`
 // barriers collect the TMA bytes of both CTAs, commits are multicast to both, the peer's epilogue warps
 // arrive remotely on the leader's `tempty`.
-template <bool HAS_UP, bool PAIR>
-__global__ void __launch_bounds__(HAS_UP ? SLAB_THREADS_UP : SLAB_THREADS, 1)
+template <bool HAS_UP, bool PAIR, bool E16>
+__global__ void __launch_bounds__(HAS_UP ? SLAB_THREADS_UP : (E16 ? SLAB_THREADS_E16 : SLAB_THREADS), 1)
 conv_slab_kernel(const __grid_constant__ SlabKParams p) {
+  constexpr int NEW = E16 ? 16 : 8;                      // epilogue warps
+  constexpr int W_PROD = NEW, W_MMA = NEW + 1, W_ALLOC = NEW + 2;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // round up inside the shared window (pointer arithmetic on the symbol keeps the shared address space,
   // so bias / OutConv weights are read with LDS instead of generic loads)
@@ -521,23 +563,24 @@ conv_slab_kernel(const __grid_constant__ SlabKParams p) {
   uint64_t* bfull = wbar + 1;
   uint64_t* bempty = bfull + SLAB_MAX_BSTAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bempty + SLAB_MAX_BSTAGES);
+  float* sm_part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full) + 512);   // E16 only (make_plan reserves it)
 
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);  // provably warp-uniform
   const int lane = threadIdx.x & 31;
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;   // == blockIdx.x & 1: the tile loops below need no change
 
-  if (warp == 8 && lane == 0) {
+  if (warp == W_PROD && lane == 0) {
     tma_prefetch_desc(&p.tmA);
     if (p.b_stream) tma_prefetch_desc(&p.tmB);
   }
-  if (warp == 9 && lane == 0) {
+  if (warp == W_MMA && lane == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(full + s, HAS_UP ? 1 + 4 : 1);
       mbar_init(empty + s, 1);
     }
     for (int a = 0; a < p.acc_stages; ++a) {
       mbar_init(tfull + a, 1);
-      mbar_init(tempty + a, PAIR ? 16 : 8);   // PAIR (leader): the epilogue warps of both CTAs
+      mbar_init(tempty + a, PAIR ? 2 * NEW : NEW);   // PAIR (leader): the epilogue warps of both CTAs
     }
     mbar_init(wbar, 1);
     if (PAIR && !p.b_stream) mbar_init(bfull, 1);   // leader: "the peer's weights are resident"
@@ -547,7 +590,7 @@ conv_slab_kernel(const __grid_constant__ SlabKParams p) {
     }
     fence_barrier_init();
   }
-  if (warp == 10) {
+  if (warp == W_ALLOC) {
     if (PAIR) {
       // one warp of EACH CTA of the pair executes the collective cta_group::2 allocation with the SAME shared-memory
       // offset (per-rank slots were tried to silence compute-sanitizer racecheck, which reports the pair's two
@@ -578,7 +621,7 @@ conv_slab_kernel(const __grid_constant__ SlabKParams p) {
   const uint32_t tmem_base = *tmem_slot;
   pdl_launch_dependents();   // the next kernel may start its prologue on SMs this grid has left (common.h)
 
-  if (warp == 8) {
+  if (warp == W_PROD) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
       if (!p.b_stream) {
@@ -635,7 +678,7 @@ conv_slab_kernel(const __grid_constant__ SlabKParams p) {
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == W_MMA) {
     // -------------------------------------------------------------- MMA issuer
     const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t wa = smem_u32(smW);
@@ -662,13 +705,13 @@ conv_slab_kernel(const __grid_constant__ SlabKParams p) {
       if (p.nk == 4) TSP_ISSUE(1, 4, false); else TSP_ISSUE(1, 2, false);
     }
 #undef TSP_ISSUE
-  } else if (warp < 8) {
+  } else if (warp < NEW) {
     // ---------------------------------------------------------------- epilogue (slab_epilogue above)
     const bool relu = p.act == TEDSPAD_ACT_RELU;
 #define TSP_EPI(MODE_) \
     do { \
-      if (relu) slab_epilogue<HAS_UP, PAIR, MODE_, true>(p, warp, lane, tmem_base, sm_bias, sm_ocw, tfull, tempty); \
-      else slab_epilogue<HAS_UP, PAIR, MODE_, false>(p, warp, lane, tmem_base, sm_bias, sm_ocw, tfull, tempty); \
+      if (relu) slab_epilogue<HAS_UP, PAIR, MODE_, true, E16>(p, warp, lane, tmem_base, sm_bias, sm_ocw, tfull, tempty, sm_part); \
+      else slab_epilogue<HAS_UP, PAIR, MODE_, false, E16>(p, warp, lane, tmem_base, sm_bias, sm_ocw, tfull, tempty, sm_part); \
     } while (0)
     if (p.res != nullptr) TSP_EPI(EPI_RES);
     else if (p.oc_w != nullptr && p.y == nullptr && p.pool == nullptr) TSP_EPI(EPI_OC_ONLY);
@@ -738,7 +781,7 @@ conv_slab_kernel(const __grid_constant__ SlabKParams p) {
   tc_fence_before();
   if (PAIR) cluster_sync_all(); else __syncthreads();   // PAIR: the leader's MMAs read the peer's shared memory to the end
   tc_fence_after();
-  if (warp == 10) {
+  if (warp == W_ALLOC) {
     if (PAIR) tmem_dealloc_pair(tmem_base, p.tmem_cols);
     else tmem_dealloc(tmem_base, p.tmem_cols);
   }
@@ -804,6 +847,16 @@ static long long slab_image_bytes(int kind, int n_tile, int cin_pad, int kd, int
 }
 
 // ------------------------------------------------------------------------------------------- plan
+// The sixteen-warp epilogue (slab_epilogue, E16): resident-weight CTA-pair layers with 64 outputs and 16x16 tiles.
+// TEDSPAD_SLAB_E16=0 falls back to the eight-warp epilogue (same arithmetic, for A/B timing).
+static bool plan_e16(const tedspad_slab_plan& P, bool fused_oc) {
+  static const int mode = [] {   // 0 = never, 1 = layers with a fused OutConv (default), 2 = every eligible layer
+    const char* e = getenv("TEDSPAD_SLAB_E16");
+    return e == nullptr ? 1 : atoi(e);
+  }();
+  return (mode >= 2 || (mode == 1 && fused_oc)) && P.pair && !P.b_stream && P.n_tile == 64 && P.tm == 2;
+}
+
 static int make_plan(const tedspad_conv_slab& c, tedspad_slab_plan& P) {
   memset(&P, 0, sizeof(P));
   const tedspad_tensor& x = c.x;
@@ -1049,7 +1102,7 @@ static int make_plan(const tedspad_conv_slab& c, tedspad_slab_plan& P) {
   }
   // the bias of every N tile lives in shared memory: 512 floats by default, more for the 1024 / 2048-output convolutions
   const int bias_floats = std::max(512, c.Cout_pad);
-  const int tail_bytes = SLAB_TAIL_BYTES + (bias_floats - 512) * 4;
+  const int tail_bytes = SLAB_TAIL_BYTES + (bias_floats - 512) * 4 + (plan_e16(P, c.oc_w != nullptr) ? SLAB_E16_SCRATCH : 0);
   P.slab_bytes = 2 * P.box[0] * P.box[1] * P.box[2] * P.box[3] * P.box[4];
   P.slab_stride = static_cast<int>(round_up(P.slab_bytes + pad_bytes, 1024));
   int w_stride = static_cast<int>(round_up(P.w_bytes, 1024));
@@ -1247,11 +1300,13 @@ extern "C" int tedspad_conv_slab_forward(const tedspad_conv_slab* c, void* strea
   }
 
   if (device_once(ONCE_SLAB_ATTR)) {   // per device: the opt-in to > 48 KB of dynamic shared memory
-    cudaError_t e = cudaFuncSetAttribute(conv_slab_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SLAB_SMEM_BUDGET);
+    cudaError_t e = cudaFuncSetAttribute(conv_slab_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SLAB_SMEM_BUDGET);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(conv_slab_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SLAB_SMEM_BUDGET);
+      e = cudaFuncSetAttribute(conv_slab_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SLAB_SMEM_BUDGET);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(conv_slab_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SLAB_SMEM_BUDGET);
+      e = cudaFuncSetAttribute(conv_slab_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SLAB_SMEM_BUDGET);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_slab_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SLAB_SMEM_BUDGET);
     if (e != cudaSuccess) {
       device_once_reset(ONCE_SLAB_ATTR);
       set_error("cudaFuncSetAttribute(slab smem) failed: %s", cudaGetErrorString(e));
@@ -1265,11 +1320,14 @@ extern "C" int tedspad_conv_slab_forward(const tedspad_conv_slab* c, void* strea
     // clusters of two CTAs (one TPC); an even grid keeps the two tile loops of a pair in lock step
     ctas &= ~1;
     TSP_CHECK(ctas >= 2 && !has_up, "slab pair: needs at least two CTAs and no fused up-sampling");
-    TSP_CUDA(launch_kernel(conv_slab_kernel<false, true>, dim3(ctas), dim3(SLAB_THREADS), P.smem_bytes, st, p, 2));
+    if (plan_e16(P, fused_oc))
+      TSP_CUDA(launch_kernel(conv_slab_kernel<false, true, true>, dim3(ctas), dim3(SLAB_THREADS_E16), P.smem_bytes, st, p, 2));
+    else
+      TSP_CUDA(launch_kernel(conv_slab_kernel<false, true, false>, dim3(ctas), dim3(SLAB_THREADS), P.smem_bytes, st, p, 2));
   } else if (has_up) {
-    TSP_CUDA(launch_kernel(conv_slab_kernel<true, false>, dim3(ctas), dim3(SLAB_THREADS_UP), P.smem_bytes, st, p));
+    TSP_CUDA(launch_kernel(conv_slab_kernel<true, false, false>, dim3(ctas), dim3(SLAB_THREADS_UP), P.smem_bytes, st, p));
   } else {
-    TSP_CUDA(launch_kernel(conv_slab_kernel<false, false>, dim3(ctas), dim3(SLAB_THREADS), P.smem_bytes, st, p));
+    TSP_CUDA(launch_kernel(conv_slab_kernel<false, false, false>, dim3(ctas), dim3(SLAB_THREADS), P.smem_bytes, st, p));
   }
   TSP_CUDA(cudaGetLastError());
   return 0;

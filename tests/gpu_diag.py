@@ -764,6 +764,16 @@ def group_pairperf():
         time_slab(f"64->128 @112 x128 {nm}", K, 128, (1, 112, 112), 64, 128, (1, 3, 3))
 
 
+def group_e16perf():
+    """Sixteen- against eight-warp epilogue on the 64-output CTA-pair layers (run with TEDSPAD_SLAB_E16=0/1/2)."""
+    K = L.SLAB_3X3_PAIR
+    for _ in range(2):
+        time_slab("64->64 @224 x128 pair", K, 128, (1, 224, 224), 64, 64, (1, 3, 3))
+        time_slab("64->64 @224 x128 +pool pair", K, 128, (1, 224, 224), 64, 64, (1, 3, 3), pool=True)
+        time_slab("64->64 @224 x128 OutConv-only pair", K, 128, (1, 224, 224), 64, 64, (1, 3, 3), outconv=True)
+        time_slab("128->64 @224 x128 pair", K, 128, (1, 224, 224), 128, 64, (1, 3, 3))
+
+
 def group_slabstream():
     K = L.SLAB_3X3_STREAM
     run_slab_case("R1 128->128 20x24 haloed", K, 2, (1, 20, 24), 128, 128, 128, (1, 3, 3), halo=(0, 1, 1))
@@ -867,7 +877,7 @@ def group_slabstem():
 
 
 def time_slab(name, kind, N, dhw, cin_buf, cout, k, stride=(1, 1, 1), pad_f=(0, 1, 1), pad_b=None, tm=0, iters=10, pool=False,
-              cin_real=None, n_tile=0):
+              cin_real=None, n_tile=0, outconv=False):
     try:
         D, H, W = dhw
         cin_real = cin_real or cin_buf
@@ -881,13 +891,18 @@ def time_slab(name, kind, N, dhw, cin_buf, cout, k, stride=(1, 1, 1), pad_f=(0, 
         od, oh, ow = pc.out_extent((D, H, W), pad_b)
         y = ops.CLTensor(N, od, oh, ow, cout, (0, 1, 1) if od == 1 else (0, 0, 0), device=DEV)
         pv = ops.CLTensor(N, 1, oh // 2, ow // 2, cout, (0, 1, 1), device=DEV) if pool else None
+        oc, yo = None, y
+        if outconv:   # the last UNet layer: OutConv + sigmoid + glue fused, the 64-channel tensor is never written
+            clip = ops.CLTensor(N // 16, 16, oh, ow, 4, device=DEV)
+            oc = (torch.randn(3, cout, device=DEV) / 8, torch.randn(3, device=DEV), None, None, clip, 16)
+            yo = None
         for _ in range(3):
-            ops.conv_slab_forward(x, psc, y, pool=pv, tm=tm)
+            ops.conv_slab_forward(x, psc, yo, pool=pv, tm=tm, outconv=oc)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(iters):
-            ops.conv_slab_forward(x, psc, y, pool=pv, tm=tm)
+            ops.conv_slab_forward(x, psc, yo, pool=pv, tm=tm, outconv=oc)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / iters
