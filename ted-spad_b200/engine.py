@@ -29,6 +29,11 @@ USE_STREAM_PAIR = USE_PAIR and os.environ.get("TEDSPAD_STREAM_PAIR", "1") != "0"
 # heads GEMM / the 3x3 branch.  Inside a captured CUDA graph these are parallel branches (no host cost); the Mixed_4x /
 # 5x launches are 15-50 us kernels of 100-400 tiles that leave SMs idle in their tails.
 I3D_BRANCH_STREAMS = os.environ.get("TEDSPAD_I3D_BRANCH_STREAMS", "0") != "0"
+# Inception heads (b0 / b1a / b2a: the three 1x1x1 convolutions that read the block input, i3d.py:144-148) as ONE
+# single-destination convolution through the slab kernel: the block buffer is laid out physically as
+# [b1b | b2b | b3b | b0 | b1a (padded) | b2a (padded)], so the heads' outputs are one contiguous channel range and the
+# next block's weights are packed with their input channels permuted to that order (I3DExecutor._mixed_packed).
+I3D_HEADS_SLAB = SLAB_1X1 and PAD_SMALL_3X3 and os.environ.get("TEDSPAD_I3D_HEADS_SLAB", "1") != "0"
 USE_SLAB_STEM3D = USE_SLAB and os.environ.get("TEDSPAD_SLAB_STEM3D", "1") != "0"
 SLAB_WEIGHT_LIMIT = 150 * 1024   # bytes of resident weights that still leave room for three slab stages
 ENC_IN_CHANNELS = 4 if USE_SLAB_STEM3D else 8   # channel padding of the encoder input clip
@@ -529,6 +534,45 @@ class I3DExecutor:
             for br, k in (("b0", 1), ("b1a", 1), ("b1b", 3), ("b2a", 1), ("b2b", 3), ("b3b", 1)):
                 unit(f"{name}.{br}", (k, k, k))
         self.packed = {}
+        self.in_layout = {}   # unit name -> (physical->logical input channel list | None, physical input channels)
+        self.layout = {}      # block name -> (logical channels, physical->logical list | None) of its output buffer
+        self.heads_slab = I3D_HEADS_SLAB
+        if self.heads_slab:
+            perm_in = None
+            for i, (name, cin, oc) in enumerate(I3D_MIXED):
+                for br in ("b0", "b1a", "b2a", "b3b"):   # the units that read the block input (or its max-pool)
+                    self.in_layout[f"{name}.{br}"] = (perm_in, -(-cin // 64) * 64)
+                total = oc[0] + oc[2] + oc[4] + oc[5]
+                # physical [b1b | b2b | b3b | b0]: channel p of the buffer is logical channel perm[p]; the last block
+                # keeps the reference's order (its output is the feature map)
+                perm_in = None if i == len(I3D_MIXED) - 1 else list(range(oc[0], total)) + list(range(oc[0]))
+                self.layout[name] = (total, perm_in)
+
+    def _weight(self, name):
+        """Unit3D weight [Cout, Cin_phys, kd, kh, kw] for the physical channel order / padding of its input buffer."""
+        w = self.specs[name][0]
+        perm, cphys = self.in_layout.get(name, (None, None))
+        if cphys is None:
+            return w
+        wl = w.detach().float()
+        if perm is not None:
+            wl = wl.index_select(1, torch.as_tensor(perm, dtype=torch.long, device=wl.device))
+        out = wl.new_zeros((wl.shape[0], cphys) + tuple(wl.shape[2:]))
+        out[:, :wl.shape[1]] = wl
+        return out
+
+    def tap(self, name):
+        """Block output in the reference's channel order (fp32 [N,C,D,H,W]) - for the per-layer parity tests."""
+        buf = self.bufs.find(name)
+        if buf is None or name not in self.layout:
+            return None if buf is None else buf.to_ncdhw()
+        total, perm = self.layout[name]
+        t = buf.slice(0, total).to_ncdhw()
+        if perm is None:
+            return t
+        inv = torch.empty(total, dtype=torch.long)
+        inv[torch.as_tensor(perm)] = torch.arange(total)
+        return t.index_select(1, inv.to(t.device))
 
     def _packed_unit(self, name, x):
         """PackedConv of a Unit3D for this input extent (1x1x1 units: no padding involved)."""
@@ -537,7 +581,8 @@ class I3DExecutor:
         pc = self.packed.get(key)
         if pc is None:
             assert k == (1, 1, 1)
-            pc = PackedConv(w, None, bn, stride=s, pad_front=(0, 0, 0), cin_pad=cin_pad, device=self.device, n_align=16)
+            pc = PackedConv(self._weight(name), None, bn, stride=s, pad_front=(0, 0, 0), cin_pad=cin_pad, device=self.device, n_align=16)
+            pc.cin = w.shape[1]
             pc.slab = None
             self.packed[key] = pc
         return pc
@@ -551,8 +596,9 @@ class I3DExecutor:
         pc = self.packed.get(key)
         if pc is None:
             heads = name.rsplit(".", 1)[-1] in ("b0", "b1a", "b2a") and MERGE_1X1   # merged: general kernel
-            pc = PackedConv(w, None, bn, stride=s, pad_front=pf, cin_pad=cin_pad, device=self.device,
+            pc = PackedConv(self._weight(name), None, bn, stride=s, pad_front=pf, cin_pad=cin_pad, device=self.device,
                             n_align=16 if (k == (1, 1, 1) and (heads or w.shape[0] % 8)) else 32)
+            pc.cin = w.shape[1]
             self.packed[key] = pc
             if cin_pad == 8:
                 self.packed[key + ("slab",)] = stem3d(pc)
@@ -580,7 +626,44 @@ class I3DExecutor:
             out = self.bufs.get(name, x.N, od, oh, ow, cout)
         return self._conv(name, x, out)
 
+    def _mixed_packed(self, name, x, oc):
+        """InceptionModule.forward (i3d.py:142-149) with the heads as ONE single-destination slab convolution: the block
+        buffer is physically [b1b | b2b | b3b | b0 | b1a (c1) | b2a (c2)], the heads write the contiguous range
+        [b0 | b1a | b2a] (pad rows of b1a / b2a have zero weights and zero bias: they store zeros), the 3x3x3 branches
+        read their padded inputs from the tail of the same buffer.  Returns the view the next layer reads: the first
+        ceil64(total) physical channels (what lies beyond `total` meets zero weights)."""
+        total = oc[0] + oc[2] + oc[4] + oc[5]
+        c1, c2 = self.specs[f"{name}.b1b"][4], self.specs[f"{name}.b2b"][4]
+        rows = oc[0] + c1 + c2
+        y = self.bufs.get(name, x.N, x.D, x.H, x.W, total + c1 + c2)
+        key = (name, "heads_slab")
+        pc = self.packed.get(key)
+        if pc is None:
+            ws = [self._weight(f"{name}.{br}").detach().float() for br in ("b0", "b1a", "b2a")]
+            begins = (0, oc[0], oc[0] + c1)
+            w = ws[0].new_zeros((rows,) + tuple(ws[0].shape[1:]))
+            g, b, m, v = (torch.ones(rows), torch.zeros(rows), torch.zeros(rows), torch.ones(rows))
+            g, b, m, v = (t.to(ws[0].device) for t in (g, b, m, v))
+            for br, wi, r0 in zip(("b0", "b1a", "b2a"), ws, begins):
+                gi, bi, mi, vi, eps = self.specs[f"{name}.{br}"][1]
+                n = wi.shape[0]
+                w[r0:r0 + n] = wi
+                g[r0:r0 + n], b[r0:r0 + n], m[r0:r0 + n], v[r0:r0 + n] = (t.detach().float() for t in (gi, bi, mi, vi))
+            pc = PackedConv(w, None, (g, b, m, v, eps), pad_front=(0, 0, 0), cin_pad=w.shape[1], device=self.device, n_align=32)
+            pc.cin = self.specs[f"{name}.b0"][0].shape[1]
+            pc.slab = slab3x3(pc)
+            assert pc.slab is not None, (name, pc.cout, pc.cout_pad, pc.n_tile)
+            self.packed[key] = pc
+        conv_auto(x, pc, y.slice(total - oc[0], rows))
+        self._unit(f"{name}.b1b", y.slice(total, c1), out=y.slice(0, oc[2]))
+        self._unit(f"{name}.b2b", y.slice(total + c1, c2), out=y.slice(oc[2], oc[4]))
+        t3 = self._pool(f"{name}.b3a", x, (3, 3, 3), (1, 1, 1))
+        self._unit(f"{name}.b3b", t3, out=y.slice(oc[2] + oc[4], oc[5]))
+        return y.slice(0, -(-total // 64) * 64)
+
     def _mixed(self, name, x, oc):
+        if self.heads_slab and self.layout[name][1] is not None:
+            return self._mixed_packed(name, x, oc)
         total = oc[0] + oc[2] + oc[4] + oc[5]
         y = self.bufs.get(name, x.N, x.D, x.H, x.W, total)
         # b1a's output is stored with the channel padding b1b's feed wants (pad channels zero, never written)

@@ -94,6 +94,16 @@ class _Dense:
         return self.t.unsqueeze(2)
 
 
+class _Dense5:
+    """The same for a tensor that already is [N,C,D,H,W]."""
+
+    def __init__(self, t):
+        self.t = t
+
+    def to_ncdhw(self):
+        return self.t
+
+
 def _tap_errors(fa, ft, arch, taps_fa, taps_ft, B=1):
     """{layer: relative RMS error} of the activation buffers the executors keep after a run vs the oracle's taps."""
     from tedspad_b200.engine import UNetExecutor
@@ -126,7 +136,8 @@ def _tap_errors(fa, ft, arch, taps_fa, taps_ft, B=1):
             pairs.append((f"unetpp:{k}", b, taps_fa[k]))
     if arch == "i3d":
         for n in ["Conv3d_1a_7x7", "Conv3d_2b_1x1", "Conv3d_2c_3x3"] + [m[0] for m in M.I3D_MIXED]:
-            pairs.append((f"i3d:{n}", ex_ft.bufs.find(n), taps_ft[n]))
+            t = ex_ft.tap(n)   # reference channel order (the Mixed buffers are stored permuted, engine.I3D_HEADS_SLAB)
+            pairs.append((f"i3d:{n}", None if t is None else _Dense5(t), taps_ft[n]))
     elif arch == "largei3d":
         pairs.append(("i3res50:conv1", ex_ft.bufs.find("conv1"), taps_ft["conv1"]))
         for blk in ex_ft.blocks:
