@@ -130,8 +130,11 @@ __device__ __forceinline__ void slab_issue(const SlabKParams& p, uint8_t* smS, u
   const uint32_t a_hi = static_cast<uint32_t>(p.a_desc >> 32), a_lo0 = static_cast<uint32_t>(p.a_desc);
   const uint32_t b_hi = static_cast<uint32_t>(p.b_desc >> 32);
   const uint32_t b_lo0 = static_cast<uint32_t>(p.b_desc) + (w_addr >> 4);
-  const uint32_t half_step = static_cast<uint32_t>(p.half_a_off >> 4);
-  const uint32_t a_ks = static_cast<uint32_t>(p.a_kstep >> 4), b_ks = static_cast<uint32_t>(p.b_kstep >> 4);
+  // swizzled kinds (every 3x3 / 1x1 kind: 128-byte pixel rows): K=16 step = 32 B, second half = 8 pixels further.  As
+  // compile-time constants they fold into the descriptor adds (the issuer of an N = 64 layer has ~32 clocks per MMA)
+  constexpr bool SWZ = PAIR || STREAM || NK == 4;
+  const uint32_t half_step = SWZ ? 64u : static_cast<uint32_t>(p.half_a_off >> 4);
+  const uint32_t a_ks = SWZ ? 2u : static_cast<uint32_t>(p.a_kstep >> 4), b_ks = SWZ ? 2u : static_cast<uint32_t>(p.b_kstep >> 4);
   const int S = p.stages, NG = p.n_grp, KS = p.k_stages, total = p.total_tiles;
   const uint32_t n_tile = static_cast<uint32_t>(p.n_tile);
   const uint32_t slab_step = static_cast<uint32_t>(p.slab_stride >> 4);
