@@ -225,6 +225,9 @@ def group_ops():
         ("maxpool (1,3,3)s(1,2,2) SAME", (2, 64, 4, 14, 14), (1, 3, 3), (1, 2, 2), (0, 0, 0), (0, 1, 1), True),
         ("maxpool 3s2 SAME", (2, 32, 8, 14, 14), (3, 3, 3), (2, 2, 2), (0, 0, 0), (1, 1, 1), True),
         ("maxpool 3s1 SAME", (2, 32, 4, 7, 7), (3, 3, 3), (1, 1, 1), (1, 1, 1), (1, 1, 1), True),
+        ("maxpool 3s1 SAME odd D/H/W", (3, 64, 3, 5, 9), (3, 3, 3), (1, 1, 1), (1, 1, 1), (1, 1, 1), True),
+        ("maxpool 3s1 -inf pad", (2, 72, 2, 6, 4), (3, 3, 3), (1, 1, 1), (1, 1, 1), (1, 1, 1), False),
+        ("maxpool 3s1 SAME D=1", (2, 32, 1, 4, 1), (3, 3, 3), (1, 1, 1), (1, 1, 1), (1, 1, 1), True),
         ("maxpool 2s2", (2, 32, 4, 14, 14), (2, 2, 2), (2, 2, 2), (0, 0, 0), (0, 0, 0), True),
         ("maxpool (2,3,3)s2 p0 floor", (2, 64, 8, 23, 23), (2, 3, 3), (2, 2, 2), (0, 0, 0), (0, 0, 0), False),
         ("maxpool (2,1,1)", (2, 256, 4, 9, 9), (2, 1, 1), (2, 1, 1), (0, 0, 0), (0, 0, 0), False),
