@@ -125,6 +125,9 @@ int tedspad_conv_forward(const tedspad_conv* p, void* stream);
  *   TEDSPAD_SLAB_3X3_STREAM_PAIR  TEDSPAD_SLAB_3X3_STREAM executed by CTA pairs: every CTA streams HALF of each weight
  *                        block's rows.  One N tile (Cout_pad <= 256, multiple of 32), even tile count.  The N = 128
  *                        layers, whose single-CTA MMA reads shared memory at exactly its 128 B/clk limit.
+ *   TEDSPAD_SLAB_STEM3D_PAIR  TEDSPAD_SLAB_STEM3D executed by CTA pairs (same reason as 3X3_PAIR: the stems have
+ *                        N = 64): each CTA holds the weight image of HALF the output channels.  Even tile count;
+ *                        tedspad_conv_slab_pack(kind = STEM3D_PAIR) writes the two halves back to back.
  * Optional fused producer (single-CTA 3X3 kinds, 2-D): `up` = the low-resolution tensor of Up.forward; its x2 bilinear
  * (align_corners=True) up-sampling is computed by four producer warps straight into the shared-memory slab,
  * so the up-sampled half of torch.cat([x2, x1]) (unet_parts.py:67) is never written to or read from HBM.
@@ -135,7 +138,7 @@ int tedspad_conv_forward(const tedspad_conv* p, void* stream);
  * tedspad_conv_slab_pack() from the standard packed layout of tedspad_conv.
  */
 enum { TEDSPAD_SLAB_3X3 = 0, TEDSPAD_SLAB_STEM2D = 1, TEDSPAD_SLAB_STEM3D = 2, TEDSPAD_SLAB_3X3_STREAM = 3,
-       TEDSPAD_SLAB_3X3_PAIR = 4, TEDSPAD_SLAB_3X3_STREAM_PAIR = 5 };
+       TEDSPAD_SLAB_3X3_PAIR = 4, TEDSPAD_SLAB_3X3_STREAM_PAIR = 5, TEDSPAD_SLAB_STEM3D_PAIR = 6 };
 
 typedef struct tedspad_conv_slab {
   tedspad_tensor x;         /* bf16 input view (see kinds above) */

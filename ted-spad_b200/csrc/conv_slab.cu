@@ -132,7 +132,7 @@ __device__ __forceinline__ void slab_issue(const SlabKParams& p, uint8_t* smS, u
   const uint32_t b_lo0 = static_cast<uint32_t>(p.b_desc) + (w_addr >> 4);
   // swizzled kinds (every 3x3 / 1x1 kind: 128-byte pixel rows): K=16 step = 32 B, second half = 8 pixels further.  As
   // compile-time constants they fold into the descriptor adds (the issuer of an N = 64 layer has ~32 clocks per MMA)
-  constexpr bool SWZ = PAIR || STREAM || NK == 4;
+  constexpr bool SWZ = STREAM || NK == 4;
   const uint32_t half_step = SWZ ? 64u : static_cast<uint32_t>(p.half_a_off >> 4);
   const uint32_t a_ks = SWZ ? 2u : static_cast<uint32_t>(p.a_kstep >> 4), b_ks = SWZ ? 2u : static_cast<uint32_t>(p.b_kstep >> 4);
   const int S = p.stages, NG = p.n_grp, KS = p.k_stages, total = p.total_tiles;
@@ -652,8 +652,12 @@ conv_slab_kernel(const __grid_constant__ SlabKParams p) {
           } else if (PAIR) {
             // both slabs complete on the LEADER's barrier (its issuer reads both shared memories)
             if (rank == 0) mbar_arrive_expect_tx(full + s, 2u * static_cast<uint32_t>(p.slab_bytes));
-            tma_load_5d_pair(smS + s * p.slab_stride, &p.tmA, mapa_u32(smem_u32(full + s), 0), cb * p.c_step, cx, cy,
-                             cz + kt * p.z_kstep, n);
+            if (p.merged_cw)   // stems (STEM3D_PAIR): (pixel, channel) merged into one contiguous inner dimension
+              tma_load_5d_pair(smS + s * p.slab_stride, &p.tmA, mapa_u32(smem_u32(full + s), 0), cx * 8, cy,
+                               cz + kt * p.z_kstep, n, 0);
+            else
+              tma_load_5d_pair(smS + s * p.slab_stride, &p.tmA, mapa_u32(smem_u32(full + s), 0), cb * p.c_step, cx, cy,
+                               cz + kt * p.z_kstep, n);
           } else {
             mbar_arrive_expect_tx(full + s, static_cast<uint32_t>(p.slab_bytes));
             if (p.merged_cw)  // stems: (pixel, channel) merged into one contiguous inner dimension of 8-element pixels
@@ -691,6 +695,9 @@ conv_slab_kernel(const __grid_constant__ SlabKParams p) {
 #define TSP_ISSUE_PAIR(TM_, ST_) slab_issue<TM_, 4, ST_, true>(p, smS, wa, tb, full, empty, tfull, tempty, wbar, bfull, bempty)
         if (p.b_stream) {
           if (p.tm == 2) TSP_ISSUE_PAIR(2, true); else TSP_ISSUE_PAIR(1, true);
+        } else if (p.nk == 2) {   // un-swizzled stem (STEM3D_PAIR): two K = 16 steps per filter row
+          if (p.tm == 2) slab_issue<2, 2, false, true>(p, smS, wa, tb, full, empty, tfull, tempty, wbar, bfull, bempty);
+          else slab_issue<1, 2, false, true>(p, smS, wa, tb, full, empty, tfull, tempty, wbar, bfull, bempty);
         } else {
           TSP_ISSUE_PAIR(2, false);
         }
@@ -857,7 +864,7 @@ static bool plan_e16(const tedspad_slab_plan& P, bool fused_oc) {
     const char* e = getenv("TEDSPAD_SLAB_E16");
     return e == nullptr ? 1 : atoi(e);
   }();
-  return (mode >= 2 || (mode == 1 && fused_oc)) && P.pair && !P.b_stream && P.n_tile == 64 && P.tm == 2;
+  return (mode >= 2 || (mode == 1 && fused_oc)) && P.pair && !P.b_stream && P.swizzle128 && P.n_tile == 64 && P.tm == 2;
 }
 
 static int make_plan(const tedspad_conv_slab& c, tedspad_slab_plan& P) {
@@ -865,7 +872,7 @@ static int make_plan(const tedspad_conv_slab& c, tedspad_slab_plan& P) {
   const tedspad_tensor& x = c.x;
   const tedspad_tensor& y = c.y;
   const bool stream = c.kind == TEDSPAD_SLAB_3X3_STREAM || c.kind == TEDSPAD_SLAB_3X3_STREAM_PAIR;
-  const bool pair = c.kind == TEDSPAD_SLAB_3X3_PAIR || c.kind == TEDSPAD_SLAB_3X3_STREAM_PAIR;
+  const bool pair = c.kind == TEDSPAD_SLAB_3X3_PAIR || c.kind == TEDSPAD_SLAB_3X3_STREAM_PAIR || c.kind == TEDSPAD_SLAB_STEM3D_PAIR;
   P.pair = pair ? 1 : 0;
   TSP_CHECK(c.Cout_pad % 32 == 0 && c.Cout_pad >= 32 && c.Cout_pad <= (stream ? 2048 : 256) && c.Cout <= c.Cout_pad &&
                 c.Cout >= 1 && c.Cout % 8 == 0,
@@ -1033,7 +1040,7 @@ static int make_plan(const tedspad_conv_slab& c, tedspad_slab_plan& P) {
       P.tab[2 * tap] = static_cast<uint32_t>(((tap / c.kw) * slab_w + (tap % c.kw)) * 128);
       P.tab[2 * tap + 1] = 0;
     }
-  } else if (c.kind == TEDSPAD_SLAB_STEM3D) {
+  } else if (c.kind == TEDSPAD_SLAB_STEM3D || c.kind == TEDSPAD_SLAB_STEM3D_PAIR) {
     TSP_CHECK(c.kh == 7 && c.kw == 7 && c.sh == 2 && c.sw == 2 && c.kd >= 1 && c.kd <= 7 && c.sd >= 1,
               "slab stem3d: needs a (kd,7,7) stride (sd,2,2) convolution");
     TSP_CHECK(x.C == 4 && x.ld == 4 && x.coff == 0 && x.pd == 0 && x.ph == 0 && x.pw == 0 && x.W % 2 == 0,
@@ -1042,7 +1049,9 @@ static int make_plan(const tedspad_conv_slab& c, tedspad_slab_plan& P) {
     const int shift = c.pw & 1;          // odd front pad: one extra (zero-weight) leading tap
     const int pwe = c.pw + shift;        // even front pad in pixels
     TSP_CHECK(7 + shift <= 8, "slab stem3d: window exceeds 8 pixels");
-    P.w_bytes = static_cast<int>(slab_image_bytes(c.kind, P.n_tile, 4, c.kd, 7, 7));
+    const int b_rows = pair ? P.n_tile / 2 : P.n_tile;   // weight rows (output channels) held by one CTA
+    TSP_CHECK(!pair || P.n_tile % 32 == 0, "slab stem3d pair: Cout_pad=%d must be a multiple of 32", P.n_tile);
+    P.w_bytes = static_cast<int>(slab_image_bytes(TEDSPAD_SLAB_STEM3D, b_rows, 4, c.kd, 7, 7));
     int tm = c.tm;
     if (tm == 0) tm = 1;
     TSP_CHECK(tm == 1 || tm == 2, "slab: tm=%d", tm);
@@ -1073,8 +1082,8 @@ static int make_plan(const tedspad_conv_slab& c, tedspad_slab_plan& P) {
     P.tiles_z = y.D;
     P.half_a_off = 8 * 16;
     P.a_layout = 0; P.a_lbo = 16; P.a_sbo = 2 * pairs * 16;
-    P.b_layout = 0; P.b_lbo = P.n_tile * 16; P.b_sbo = 128;
-    P.a_kstep = 32; P.b_kstep = 2 * P.n_tile * 16;
+    P.b_layout = 0; P.b_lbo = b_rows * 16; P.b_sbo = 128;
+    P.a_kstep = 32; P.b_kstep = 2 * b_rows * 16;
     for (int kt = 0; kt < c.kd; ++kt)
       for (int ky = 0; ky < 7; ++ky) {
         const int e = kt * 7 + ky;
@@ -1093,7 +1102,7 @@ static int make_plan(const tedspad_conv_slab& c, tedspad_slab_plan& P) {
   // the halo rows themselves are computed in vain (58/56, 30/28).  Tile row 0 = stacked row ph, so that with an
   // even padded height the 2x2 pooling pairs of the fused MaxPool2d never straddle tiles or images.
   int64_t batch = x.N;
-  const bool kind3x3 = c.kind == TEDSPAD_SLAB_3X3 || stream || pair;
+  const bool kind3x3 = c.kind == TEDSPAD_SLAB_3X3 || stream || c.kind == TEDSPAD_SLAB_3X3_PAIR;
   if (kind3x3 && c.stack_rows >= 0 && x.D == 1 && x.pd == 0 && c.kd == 1 && x.ph >= 1 && !has_up && x.N > 1 &&
       (c.stack_rows > 0 || Hp < round_up(x.H, 16)) && (c.pool.ptr == nullptr || Hp % 2 == 0)) {
     P.stack_hp = Hp; P.stack_ph = x.ph; P.stack_n = x.N;
@@ -1151,10 +1160,12 @@ extern "C" int tedspad_conv_slab_plan(const tedspad_conv_slab* c, tedspad_slab_p
 extern "C" int tedspad_conv_slab_pack(int32_t kind, const void* w_std, int32_t Cout_pad, int32_t K_pad, int32_t cin_pad,
                                       int32_t kd, int32_t kh, int32_t kw, int32_t pw_front, void* image,
                                       int64_t* image_bytes, void* stream) {
-  TSP_CHECK((kind >= TEDSPAD_SLAB_3X3 && kind <= TEDSPAD_SLAB_STEM3D) || kind == TEDSPAD_SLAB_3X3_PAIR, "slab pack: unknown kind %d", kind);
-  const bool pair = kind == TEDSPAD_SLAB_3X3_PAIR;
+  TSP_CHECK((kind >= TEDSPAD_SLAB_3X3 && kind <= TEDSPAD_SLAB_STEM3D) || kind == TEDSPAD_SLAB_3X3_PAIR || kind == TEDSPAD_SLAB_STEM3D_PAIR,
+            "slab pack: unknown kind %d", kind);
+  const bool pair = kind == TEDSPAD_SLAB_3X3_PAIR || kind == TEDSPAD_SLAB_STEM3D_PAIR;
   if (pair) {
-    kind = TEDSPAD_SLAB_3X3;   // two 3X3 images of Cout_pad / 2 rows each, the leader's first
+    // two single-CTA images of Cout_pad / 2 rows each, the leader's first
+    kind = kind == TEDSPAD_SLAB_3X3_PAIR ? TEDSPAD_SLAB_3X3 : TEDSPAD_SLAB_STEM3D;
     TSP_CHECK(Cout_pad % 32 == 0, "slab pack pair: Cout_pad=%d must be a multiple of 32", Cout_pad);
   }
   const int halves = pair ? 2 : 1, rows = Cout_pad / halves;
@@ -1185,7 +1196,7 @@ extern "C" int tedspad_conv_slab_forward(const tedspad_conv_slab* c, void* strea
   TSP_CHECK(c != nullptr, "slab: null descriptor");
   const tedspad_tensor& x = c->x;
   const tedspad_tensor& y = c->y;
-  if (check_tensor(x, "slab.x", c->kind == TEDSPAD_SLAB_STEM3D ? 4 : 8)) return 1;
+  if (check_tensor(x, "slab.x", (c->kind == TEDSPAD_SLAB_STEM3D || c->kind == TEDSPAD_SLAB_STEM3D_PAIR) ? 4 : 8)) return 1;
   const bool fused_oc = c->oc_w != nullptr;
   tedspad_tensor ychk = y;
   if (y.ptr == nullptr) {

@@ -220,7 +220,7 @@ class PackedSlabConv:
         self.n_tile = int(n_tile) or pc.n_tile
         self.cout, self.cout_pad = pc.cout, pc.cout_pad
         self.bias = pc.bias
-        self.cin_pad = 4 if kind == L.SLAB_STEM3D else pc.cin_pad
+        self.cin_pad = 4 if kind in (L.SLAB_STEM3D, L.SLAB_STEM3D_PAIR) else pc.cin_pad
         self.fallback = None
         if kind in (L.SLAB_3X3_STREAM, L.SLAB_3X3_STREAM_PAIR):
             # weights stream from the standard packed layout: nothing to re-pack
@@ -235,6 +235,8 @@ class PackedSlabConv:
         # CTA-pair kind: layers it cannot tile (W <= 8, odd tile count) run through the single-CTA kind
         if kind == L.SLAB_3X3_PAIR:
             self.fallback = PackedSlabConv(pc, L.SLAB_3X3)
+        if kind == L.SLAB_STEM3D_PAIR:
+            self.fallback = PackedSlabConv(pc, L.SLAB_STEM3D)
         nbytes = C.c_int64(0)
         args = (self.kind, None, pc.cout_pad, pc.k_pad, pc.cin_pad, *pc.k, pc.pad_front[2])
         L.check(L.lib().tedspad_conv_slab_pack(*args, None, C.byref(nbytes), None), "tedspad_conv_slab_pack(size)")
@@ -282,12 +284,16 @@ class PackedSlabConv:
         d.n_tile, d.K_pad = (self.n_tile if self.kind in (L.SLAB_3X3_STREAM, L.SLAB_3X3_STREAM_PAIR) else 0), pc.k_pad
         return d
 
-    def resolve(self, x, tm=0, up=None, stack_rows=0):
+    def resolve(self, x, tm=0, up=None, stack_rows=0, y=None):
         """The PackedSlabConv that runs this input: the CTA-pair kind needs 16x16 tiles (W > 8) in an even number
         (per-image row tiles: the pair layers run at 224 / 112 where those are exact)."""
         if self.kind == L.SLAB_3X3_PAIR and (up is not None or tm == 1 or x.W <= 8 or stack_rows > 0 or x.H % 16 or
                                              (x.N * x.D * (x.H // 16) * (-(-x.W // 16))) % 2):
             return self.fallback
+        if self.kind == L.SLAB_STEM3D_PAIR and y is not None:
+            # an odd tile count cannot be split over CTA pairs (tiles = 16 rows x 8*tm columns of one output plane)
+            if (y.N * y.D * (-(-y.H // 16)) * (-(-y.W // (8 * (tm or 1))))) % 2:
+                return self.fallback
         if self.kind == L.SLAB_3X3_STREAM_PAIR:
             # the plan knows (stacked rows, tile shape): an odd tile count cannot be split over CTA pairs; 3-D tensors
             # (few tiles per launch) were measured 0-5 % slower on pairs
@@ -301,7 +307,7 @@ class PackedSlabConv:
     def plan(self, x, y, **kw):
         """The kernel's tiling / descriptor plan (host-only call; used by the CPU simulator tests)."""
         plan = L.SlabPlan()
-        d = self.resolve(x, kw.get("tm", 0), kw.get("up"), kw.get("stack_rows", 0)).desc(x, y, **kw)
+        d = self.resolve(x, kw.get("tm", 0), kw.get("up"), kw.get("stack_rows", 0), y).desc(x, y, **kw)
         L.check(L.lib().tedspad_conv_slab_plan(C.byref(d), C.byref(plan)), "tedspad_conv_slab_plan")
         return plan
 
@@ -309,7 +315,7 @@ class PackedSlabConv:
 def conv_slab_forward(x, psc, y, act=L.ACT_RELU, pool=None, outconv=None, tm=0, max_ctas=0, up=None, stack_rows=0, res=None):
     """y = act(conv(x) + bias) through the SLAB feed; optional fused MaxPool2d(2) -> pool, OutConv 1x1 + sigmoid
     -> planar images (y may then be None), and fused Up.forward input: conv([x | upsample2x(up)])."""
-    psc = psc.resolve(x, tm, up, stack_rows)
+    psc = psc.resolve(x, tm, up, stack_rows, y)
     d = psc.desc(x, y, act=act, pool=pool, outconv=outconv, tm=tm, max_ctas=max_ctas, up=up, stack_rows=stack_rows, res=res)
     _count()
     if CONV_EVENTS is not None:

@@ -35,9 +35,10 @@ def pack_image(kind, w_std, n_tile, k_pad, cin_pad, k, pw_front):
     """numpy restatement of slab_pack_kernel: w_std uint16 [Cout_pad*K_pad] -> image uint16."""
     kd, kh, kw = k
     w = w_std.reshape(n_tile, k_pad)
-    if kind == L.SLAB_3X3_PAIR:   # two SLAB_3X3 images of n_tile / 2 rows each, the leader CTA's first
+    if kind in (L.SLAB_3X3_PAIR, L.SLAB_STEM3D_PAIR):   # two single-CTA images of n_tile / 2 rows each, the leader CTA's first
         half = n_tile // 2
-        return np.concatenate([pack_image(L.SLAB_3X3, w[h * half:(h + 1) * half].reshape(-1), half, k_pad, cin_pad, k, pw_front)
+        single = L.SLAB_3X3 if kind == L.SLAB_3X3_PAIR else L.SLAB_STEM3D
+        return np.concatenate([pack_image(single, w[h * half:(h + 1) * half].reshape(-1), half, k_pad, cin_pad, k, pw_front)
                                for h in (0, 1)])
     if kind == L.SLAB_3X3:
         total = 9 * (cin_pad // 64) * n_tile * 128 // 2

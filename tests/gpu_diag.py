@@ -777,6 +777,16 @@ def group_e16perf():
         time_slab("128->64 @224 x128 pair", K, 128, (1, 224, 224), 128, 64, (1, 3, 3))
 
 
+def group_stempairperf():
+    for tm in (1, 2):
+        for K, nm in ((L.SLAB_STEM3D, "single"), (L.SLAB_STEM3D_PAIR, "pair")):
+            time_slab(f"stem3d i3d 7x7x7 s2 x32 tm{tm} {nm}", K, 32, (16, 224, 224), 4, 64, (7, 7, 7), stride=(2, 2, 2),
+                      pad_f=(2, 2, 2), pad_b=(3, 3, 3), tm=tm, cin_real=3)
+    for K, nm in ((L.SLAB_STEM3D, "single"), (L.SLAB_STEM3D_PAIR, "pair")):
+        time_slab(f"stem3d i3res50 5x7x7 s2 x32 {nm}", K, 32, (16, 224, 224), 4, 64, (5, 7, 7), stride=(2, 2, 2), pad_f=(2, 3, 3),
+                  cin_real=3)
+
+
 def group_slabstream():
     K = L.SLAB_3X3_STREAM
     run_slab_case("R1 128->128 20x24 haloed", K, 2, (1, 20, 24), 128, 128, 128, (1, 3, 3), halo=(0, 1, 1))
@@ -859,6 +869,20 @@ def group_slabstem():
     run_slab_case("T8 stem 2-D 7x7 s2 p3 (resnet18 conv1) 32x48 x3", L.SLAB_STEM3D, 3, (1, 32, 48), 3, 4, 64, (1, 7, 7), stride=(1, 2, 2),
                   pad_f=(0, 3, 3), out_halo=(0, 1, 1))
     run_slab_case("T9 stem 2-D 7x7 s2 p3 112x112 x4 tm2 into a slice", L.SLAB_STEM3D, 4, (1, 112, 112), 3, 4, 64, (1, 7, 7), stride=(1, 2, 2),
+                  pad_f=(0, 3, 3), tm=2, out_halo=(0, 1, 1), out_ld=384, out_coff=256)
+    # the same stems on CTA pairs (cta_group::2, half of the weight rows per CTA); TP5 has an odd tile count -> fallback
+    KP = L.SLAB_STEM3D_PAIR
+    run_slab_case("TP1 stem3d pair i3d 7x7x7 s2 SAME", KP, 1, (8, 20, 24), 3, 4, 64, (7, 7, 7), stride=(2, 2, 2),
+                  pad_f=(2, 2, 2), pad_b=(3, 3, 3))
+    run_slab_case("TP2 stem3d pair i3res50 5x7x7 s2 p(2,3,3) tm2", KP, 2, (8, 32, 32), 3, 4, 64, (5, 7, 7), stride=(2, 2, 2),
+                  pad_f=(2, 3, 3), tm=2)
+    run_slab_case("TP3 stem3d pair r3d (3,7,7) s(1,2,2)", KP, 2, (4, 28, 28), 3, 4, 64, (3, 7, 7), stride=(1, 2, 2),
+                  pad_f=(1, 3, 3))
+    run_slab_case("TP4 stem3d pair i3d 16x64x64 x2", KP, 2, (16, 64, 64), 3, 4, 64, (7, 7, 7), stride=(2, 2, 2),
+                  pad_f=(2, 2, 2), pad_b=(3, 3, 3))
+    run_slab_case("TP5 stem pair 2-D 7x7 s2 p3 32x48 x3 (odd tiles: single-CTA fallback)", KP, 3, (1, 32, 48), 3, 4, 64, (1, 7, 7),
+                  stride=(1, 2, 2), pad_f=(0, 3, 3), out_halo=(0, 1, 1))
+    run_slab_case("TP6 stem pair 2-D 7x7 s2 p3 112x112 x4 tm2 into a slice", KP, 4, (1, 112, 112), 3, 4, 64, (1, 7, 7), stride=(1, 2, 2),
                   pad_f=(0, 3, 3), tm=2, out_halo=(0, 1, 1), out_ld=384, out_coff=256)
     # planar anonymizer output -> encoder clip (raw-reshape glue)
     try:
@@ -952,6 +976,8 @@ def group_slabperf():
     for tm in (1, 2):
         time_slab(f"stem2d 3->64 @224 x128 tm{tm}", L.SLAB_STEM2D, 128, (1, 224, 224), 8, 64, (1, 3, 3), tm=tm, cin_real=3)
         time_slab(f"stem3d i3d 7x7x7 s2 x8 tm{tm}", L.SLAB_STEM3D, 8, (16, 224, 224), 4, 64, (7, 7, 7), stride=(2, 2, 2),
+                  pad_f=(2, 2, 2), pad_b=(3, 3, 3), tm=tm, cin_real=3)
+        time_slab(f"stem3d PAIR i3d 7x7x7 s2 x8 tm{tm}", L.SLAB_STEM3D_PAIR, 8, (16, 224, 224), 4, 64, (7, 7, 7), stride=(2, 2, 2),
                   pad_f=(2, 2, 2), pad_b=(3, 3, 3), tm=tm, cin_real=3)
     time_conv("FLAT 64->64 @224 x128 (old feed)", 128, (224, 224), 64, 64)
 
