@@ -169,7 +169,7 @@ def cudnn_reference_clips_per_s(device, batch_clips=8, steps=4):
     return out
 
 
-def dropin_batch1_clips_per_s(fa_model, ft_model, device, n_clips=24):
+def dropin_batch1_clips_per_s(fa_model, ft_model, device, n_clips=64):
     """What a reference user gets on day one: the loop body of dali_extraction.py:168-179 VERBATIM on the boundary
     modules, one clip per iteration (params_feature_ex.py:4), fp32 tensors at every module boundary and the blocking
     per-clip `.cpu().numpy()` + np.vstack of the reference."""

@@ -36,6 +36,7 @@ I3D_BRANCH_STREAMS = os.environ.get("TEDSPAD_I3D_BRANCH_STREAMS", "0") != "0"
 I3D_HEADS_SLAB = SLAB_1X1 and PAD_SMALL_3X3 and os.environ.get("TEDSPAD_I3D_HEADS_SLAB", "1") != "0"
 USE_SLAB_STEM3D = USE_SLAB and os.environ.get("TEDSPAD_SLAB_STEM3D", "1") != "0"
 USE_STEM_PAIR = USE_PAIR and os.environ.get("TEDSPAD_STEM_PAIR", "1") != "0"   # cta_group::2 for the 64-output 7x7 stems
+STEM_PAIR_MIN_KD = int(os.environ.get("TEDSPAD_STEM_PAIR_MIN_KD", "1"))
 SLAB_WEIGHT_LIMIT = 150 * 1024   # bytes of resident weights that still leave room for three slab stages
 ENC_IN_CHANNELS = 4 if USE_SLAB_STEM3D else 8   # channel padding of the encoder input clip
 # Up.forward inside the convolution: decoder levels (1 = deepest, up1) whose up-sampled input is interpolated by the
@@ -129,8 +130,11 @@ def stem3d(pc):
     """PackedSlabConv for a (kd,7,7) stride-(sd,2,2) Cin=3 stem fed from a 4-channel clip, else None."""
     if not USE_SLAB_STEM3D or pc.k[1:] != (7, 7) or pc.stride[1:] != (2, 2) or pc.cin > 4 or pc.cout_pad > 256:
         return None
-    # N = 64 stems are bound by shared-memory operand reads on one SM like every 64-output layer: CTA pairs
-    return ops.PackedSlabConv(pc, L.SLAB_STEM3D_PAIR if (USE_STEM_PAIR and pc.cout_pad == 64) else L.SLAB_STEM3D)
+    # N = 64 stems are bound by shared-memory operand reads on one SM like every 64-output layer: CTA pairs.  Measured per
+    # 32 clips (profiles/r2b_stem3d_pair.txt): 7x7x7 0.56 -> 0.43 ms, 5x7x7 0.41 -> 0.32, (3,7,7) 0.59 -> 0.50-0.57, the
+    # 2-D 7x7 stem of the UNet++ encoder (one K stage per tile) 0.29-0.31 -> 0.27-0.28
+    pair = USE_STEM_PAIR and pc.cout_pad == 64 and pc.k[0] >= STEM_PAIR_MIN_KD
+    return ops.PackedSlabConv(pc, L.SLAB_STEM3D_PAIR if pair else L.SLAB_STEM3D)
 
 
 def stem_conv(x, pc, ps, y, act=L.ACT_RELU):
