@@ -203,9 +203,10 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constan
       mbar_wait(tfull + as, aph);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(as * p.n_tile);
-      // software pipeline over the 16-column chunks: the next chunk's tcgen05.ld is in flight while one is processed
-      // (the loop used to wait out every load: ~27k clocks for a 128 x 256 tile, profiles/README.md finding 7)
-      auto chunk = [&](const uint32_t (&v)[16], int c) {
+      for (int c = 0; c < p.n_tile; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(t_row + c, v);
+        tmem_ld_wait();
         const int cg = n0 + c;
         // destination of this 16-column chunk (segments start at multiples of 16)
         int sg = 0;
@@ -215,12 +216,9 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constan
         const bool vec_ok = seg_vec[sg];
         const long long yoff = pix * p.seg_ld[sg] + p.seg_coff[sg];
         if (row_ok && cl < s_cout) {
-          float f[16], bv[16];
+          float f[16];
 #pragma unroll
-          for (int i = 0; i < 4; ++i)   // cg is a multiple of 16: four aligned 16-byte loads instead of 16 scalar ones
-            *reinterpret_cast<float4*>(bv + 4 * i) = __ldg(reinterpret_cast<const float4*>(p.bias + cg) + i);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) + bv[i];
+          for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) + __ldg(p.bias + cg + i);
           if (p.res != nullptr) {
             if (rvec_ok && cl + 16 <= s_cout) {
               const uint4* rp = reinterpret_cast<const uint4*>(p.res + roff + cg);
@@ -262,19 +260,6 @@ __global__ void __launch_bounds__(384, 1) conv_igemm_kernel(const __grid_constan
               }
             }
           }
-        }
-      };
-      uint32_t va[16], vb[16];
-      tmem_ld16(t_row, va);
-      for (int c = 0; c < p.n_tile; c += 32) {
-        tmem_ld_wait();
-        const bool more = c + 16 < p.n_tile;
-        if (more) tmem_ld16(t_row + c + 16, vb);
-        chunk(va, c);
-        if (more) {
-          tmem_ld_wait();
-          if (c + 32 < p.n_tile) tmem_ld16(t_row + c + 32, va);
-          chunk(vb, c + 16);
         }
       }
       tc_fence_before();

@@ -74,7 +74,11 @@ struct SlabKParams {
   int half_a_off;
   int c_step, x_step, x_off, y_step, y_off, z_step, z_off, z_kstep, merged_cw;
   int tiles_x, tiles_y, tiles_z, total_tiles;
-  DivMagic dv_nt, dv_tx, dv_ty, dv_tz, dv_hp;   // divisors: num_n_tiles, tiles_x, tiles_y, tiles_z, stack_hp
+  // tile index -> (n_tile, a, b, tz, image) with a fastest; (a, b) = (tx, ty), or (ty, tx) when ty_first: CTA pairs
+  // then work on tiles of the SAME column block, so that a last column block whose second 8-column half lies outside
+  // the image (W = 56: 7 groups) can skip that half's MMAs for both CTAs of the pair at once
+  int ty_first, dim_a, dim_b;
+  DivMagic dv_nt, dv_tx, dv_ty, dv_tz, dv_hp;   // divisors: num_n_tiles, dim_a, dim_b, tiles_z, stack_hp
   int stack_hp, stack_ph, stack_n;   // stacked rows (see make_plan): padded image height, halo rows, batch; 0 = off
   uint64_t a_desc, b_desc;
   // epilogue
@@ -154,6 +158,12 @@ __device__ __forceinline__ void slab_issue(const SlabKParams& p, uint8_t* smS, u
     // its MMAs are skipped (its epilogue warps find nothing valid to store)
     bool h1 = TM == 2;
     if (TM == 2 && !PAIR) h1 = ((tile / p.num_n_tiles) % p.tiles_x) * 16 + 8 < p.OW;
+    if (TM == 2 && PAIR && p.ty_first) {
+      // one M = 256 instruction covers half 1 of BOTH tiles of the pair (tile, tile + 1): skip it when neither has one
+      const int t0 = tile / p.num_n_tiles, t1 = (tile + 1) / p.num_n_tiles;
+      const int tx0 = (t0 / p.dim_a) % p.dim_b, tx1 = (t1 / p.dim_a) % p.dim_b;
+      h1 = tx0 * 16 + 8 < p.OW || tx1 * 16 + 8 < p.OW;
+    }
     for (int ks = 0; ks < KS; ++ks) {
       const uint2* tab = p.tab + (tab_ps ? ks * NG : 0);
       uint2 cur = tab[0];
@@ -372,9 +382,10 @@ __device__ __forceinline__ void slab_epilogue(const SlabKParams& p, int warp, in
     q = fdiv(t, p.dv_nt);
     const int n0 = (t - q * p.dv_nt.d) * n_tile; t = q;   // first output channel of this N tile
     q = fdiv(t, p.dv_tx);
-    const int tx = t - q * p.dv_tx.d; t = q;
+    const int ta = t - q * p.dv_tx.d; t = q;
     q = fdiv(t, p.dv_ty);
-    const int ty = t - q * p.dv_ty.d; t = q;
+    const int tb = t - q * p.dv_ty.d; t = q;
+    const int tx = p.ty_first ? tb : ta, ty = p.ty_first ? ta : tb;
     q = fdiv(t, p.dv_tz);
     const int tz = t - q * p.dv_tz.d;
     int n = q;
@@ -639,8 +650,9 @@ conv_slab_kernel(const __grid_constant__ SlabKParams p) {
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         int t = tile;
         const int nt = t % p.num_n_tiles; t /= p.num_n_tiles;
-        const int tx = t % p.tiles_x; t /= p.tiles_x;
-        const int ty = t % p.tiles_y; t /= p.tiles_y;
+        const int ta = t % p.dim_a; t /= p.dim_a;
+        const int tb = t % p.dim_b; t /= p.dim_b;
+        const int tx = p.ty_first ? tb : ta, ty = p.ty_first ? ta : tb;
         const int tz = t % p.tiles_z;
         const int n = t / p.tiles_z;
         const int cx = tx * p.x_step + p.x_off, cy = ty * p.y_step + p.y_off, cz = tz * p.z_step + p.z_off;
@@ -1240,7 +1252,11 @@ extern "C" int tedspad_conv_slab_forward(const tedspad_conv_slab* c, void* strea
   p.z_step = P.z_step; p.z_off = P.z_off; p.z_kstep = P.z_kstep; p.merged_cw = P.merged_cw;
   p.tiles_x = P.tiles_x; p.tiles_y = P.tiles_y; p.tiles_z = P.tiles_z; p.total_tiles = P.total_tiles;
   p.stack_hp = P.stack_hp; p.stack_ph = P.stack_ph; p.stack_n = P.stack_n;
-  p.dv_nt = make_div(P.num_n_tiles); p.dv_tx = make_div(P.tiles_x); p.dv_ty = make_div(P.tiles_y);
+  // CTA pairs with a last column block whose second half is empty (OW % 16 in 1..8): column-major tile order
+  p.ty_first = (P.pair && P.tm == 2 && ((y.W - 1) % 16) < 8) ? 1 : 0;
+  p.dim_a = p.ty_first ? P.tiles_y : P.tiles_x;
+  p.dim_b = p.ty_first ? P.tiles_x : P.tiles_y;
+  p.dv_nt = make_div(P.num_n_tiles); p.dv_tx = make_div(p.dim_a); p.dv_ty = make_div(p.dim_b);
   p.dv_tz = make_div(P.tiles_z); p.dv_hp = make_div(P.stack_hp > 0 ? P.stack_hp : 1);
   p.a_desc = umma_desc_template(P.a_layout, P.a_lbo, P.a_sbo);
   p.b_desc = umma_desc_template(P.b_layout, P.b_lbo, P.b_sbo);

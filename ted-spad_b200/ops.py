@@ -284,12 +284,16 @@ class PackedSlabConv:
         d.n_tile, d.K_pad = (self.n_tile if self.kind in (L.SLAB_3X3_STREAM, L.SLAB_3X3_STREAM_PAIR) else 0), pc.k_pad
         return d
 
-    def resolve(self, x, tm=0, up=None, stack_rows=0, y=None):
+    def resolve(self, x, tm=0, up=None, stack_rows=0, y=None, pool=None):
         """The PackedSlabConv that runs this input: the CTA-pair kind needs 16x16 tiles (W > 8) in an even number
         (per-image row tiles: the pair layers run at 224 / 112 where those are exact)."""
-        if self.kind == L.SLAB_3X3_PAIR and (up is not None or tm == 1 or x.W <= 8 or stack_rows > 0 or x.H % 16 or
-                                             (x.N * x.D * (x.H // 16) * (-(-x.W // 16))) % 2):
-            return self.fallback
+        if self.kind == L.SLAB_3X3_PAIR:
+            if up is not None or tm == 1 or x.W <= 8:
+                return self.fallback
+            # the plan knows the tile count (stacked rows or per-image row tiles): an odd one cannot be split over pairs
+            d = self.desc(x, None, tm=tm, stack_rows=stack_rows, pool=pool)   # (a fused pool constrains the row stacking)
+            if L.lib().tedspad_conv_slab_plan(C.byref(d), C.byref(L.SlabPlan())) != 0:
+                return self.fallback
         if self.kind == L.SLAB_STEM3D_PAIR and y is not None:
             # an odd tile count cannot be split over CTA pairs (tiles = 16 rows x 8*tm columns of one output plane)
             if (y.N * y.D * (-(-y.H // 16)) * (-(-y.W // (8 * (tm or 1))))) % 2:
@@ -307,7 +311,7 @@ class PackedSlabConv:
     def plan(self, x, y, **kw):
         """The kernel's tiling / descriptor plan (host-only call; used by the CPU simulator tests)."""
         plan = L.SlabPlan()
-        d = self.resolve(x, kw.get("tm", 0), kw.get("up"), kw.get("stack_rows", 0), y).desc(x, y, **kw)
+        d = self.resolve(x, kw.get("tm", 0), kw.get("up"), kw.get("stack_rows", 0), y, kw.get("pool")).desc(x, y, **kw)
         L.check(L.lib().tedspad_conv_slab_plan(C.byref(d), C.byref(plan)), "tedspad_conv_slab_plan")
         return plan
 
@@ -315,7 +319,7 @@ class PackedSlabConv:
 def conv_slab_forward(x, psc, y, act=L.ACT_RELU, pool=None, outconv=None, tm=0, max_ctas=0, up=None, stack_rows=0, res=None):
     """y = act(conv(x) + bias) through the SLAB feed; optional fused MaxPool2d(2) -> pool, OutConv 1x1 + sigmoid
     -> planar images (y may then be None), and fused Up.forward input: conv([x | upsample2x(up)])."""
-    psc = psc.resolve(x, tm, up, stack_rows, y)
+    psc = psc.resolve(x, tm, up, stack_rows, y, pool)
     d = psc.desc(x, y, act=act, pool=pool, outconv=outconv, tm=tm, max_ctas=max_ctas, up=up, stack_rows=stack_rows, res=res)
     _count()
     if CONV_EVENTS is not None:
