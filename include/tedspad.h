@@ -128,6 +128,12 @@ int tedspad_conv_forward(const tedspad_conv* p, void* stream);
  *   TEDSPAD_SLAB_STEM3D_PAIR  TEDSPAD_SLAB_STEM3D executed by CTA pairs (same reason as 3X3_PAIR: the stems have
  *                        N = 64): each CTA holds the weight image of HALF the output channels.  Even tile count;
  *                        tedspad_conv_slab_pack(kind = STEM3D_PAIR) writes the two halves back to back.
+ *   TEDSPAD_SLAB_3X3_KX_PAIR  Conv2d 3x3 stride 1 pad 1 with Cout_pad 32 or 64 on CTA pairs, the three taps of a filter ROW
+ *                        sharing one A-operand fetch: B stacks the weights of filter columns kx = 0, 1, 2 along N
+ *                        (N = 3 * Cout_pad), a tile is 8 rows x 16 slab columns (14 output columns) and the epilogue adds
+ *                        the three column blocks of neighbouring lanes.  3 instead of 9 shared-memory reads of every
+ *                        slab pixel: for the layers whose tensor-core rate is bound by exactly those reads (N <= 64).
+ *                        No fused pool / OutConv / residual / up-sampling.
  * Optional fused producer (single-CTA 3X3 kinds, 2-D): `up` = the low-resolution tensor of Up.forward; its x2 bilinear
  * (align_corners=True) up-sampling is computed by four producer warps straight into the shared-memory slab,
  * so the up-sampled half of torch.cat([x2, x1]) (unet_parts.py:67) is never written to or read from HBM.
@@ -138,7 +144,8 @@ int tedspad_conv_forward(const tedspad_conv* p, void* stream);
  * tedspad_conv_slab_pack() from the standard packed layout of tedspad_conv.
  */
 enum { TEDSPAD_SLAB_3X3 = 0, TEDSPAD_SLAB_STEM2D = 1, TEDSPAD_SLAB_STEM3D = 2, TEDSPAD_SLAB_3X3_STREAM = 3,
-       TEDSPAD_SLAB_3X3_PAIR = 4, TEDSPAD_SLAB_3X3_STREAM_PAIR = 5, TEDSPAD_SLAB_STEM3D_PAIR = 6 };
+       TEDSPAD_SLAB_3X3_PAIR = 4, TEDSPAD_SLAB_3X3_STREAM_PAIR = 5, TEDSPAD_SLAB_STEM3D_PAIR = 6,
+       TEDSPAD_SLAB_3X3_KX_PAIR = 7 };
 
 typedef struct tedspad_conv_slab {
   tedspad_tensor x;         /* bf16 input view (see kinds above) */

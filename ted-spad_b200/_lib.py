@@ -14,6 +14,7 @@ ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
 FEED_AUTO, FEED_FLAT_TMA, FEED_GATHER = 0, 1, 2
 RESAMPLE_AA_FLOAT, RESAMPLE_PIL_U8 = 0, 1
 SLAB_3X3, SLAB_STEM2D, SLAB_STEM3D, SLAB_3X3_STREAM, SLAB_3X3_PAIR, SLAB_3X3_STREAM_PAIR, SLAB_STEM3D_PAIR = 0, 1, 2, 3, 4, 5, 6
+SLAB_3X3_KX_PAIR = 7
 SLAB_MAX_MMA = 112
 ABI_VERSION = 8
 

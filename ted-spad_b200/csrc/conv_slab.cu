@@ -78,6 +78,8 @@ struct SlabKParams {
   // then work on tiles of the SAME column block, so that a last column block whose second 8-column half lies outside
   // the image (W = 56: 7 groups) can skip that half's MMAs for both CTAs of the pair at once
   int ty_first, dim_a, dim_b;
+  // KX kind: accumulator columns = 3 filter columns x kx_cp output channels (slab_epilogue_kx); bias_n = bias floats
+  int kx, kx_cp, bias_n;
   DivMagic dv_nt, dv_tx, dv_ty, dv_tz, dv_hp;   // divisors: num_n_tiles, dim_a, dim_b, tiles_z, stack_hp
   int stack_hp, stack_ph, stack_n;   // stacked rows (see make_plan): padded image height, halo rows, batch; 0 = off
   uint64_t a_desc, b_desc;
@@ -508,6 +510,85 @@ __device__ __forceinline__ void slab_epilogue(const SlabKParams& p, int warp, in
   }
 }
 
+// KX kinds (TEDSPAD_SLAB_3X3_KX_PAIR).  At N <= 64 outputs the MMA is bound by its A-operand reads: a 3x3 layer reads
+// every slab pixel nine times from shared memory, once per tap.  Here the three taps of one filter ROW share a fetch:
+// B stacks the weights of kx = 0, 1, 2 along N (N = 3 * CP), so one K step of filter row ky computes, for slab pixel
+// q = (row, s), the three partial sums  D_kx[q] = sum_c w[ky][kx][c] * x[row + ky - 1][s][c]  - 3 fetches per pixel
+// instead of 9 - and the output pixel (row, j) is  D_0[(row, j)] + D_1[(row, j + 1)] + D_2[(row, j + 2)]:  a tile is
+// 8 rows x 16 slab columns (128 GEMM rows, flat: the slab is exactly 16 pixels wide, so an 8-pixel core group is half
+// a slab row and SBO = 1024 B) and yields 14 output columns; the two neighbour terms come from the next lanes of
+// the warp (a warp holds two slab rows of 16 lanes each).  Warp >> 2 selects the half of the CP channels.
+template <bool PAIR, bool RELU>
+__device__ __forceinline__ void slab_epilogue_kx(const SlabKParams& p, int warp, int lane, uint32_t tmem_base, const float* sm_bias,
+                                                 uint64_t* tfull, uint64_t* tempty) {
+  pdl_wait();   // the previous kernel may still be reading the buffers this one writes
+  const int ew = warp & 3, eg = warp >> 2;
+  const int CP = p.kx_cp, CH = CP >> 1, c_lo = eg * CH;   // channels per filter column block / per warp; first channel
+  const int row = 2 * ew + (lane >> 4), s = lane & 15;
+  const bool wide_ok = ((p.y_ld | p.y_coff) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.y) & 31) == 0;
+  int as = 0;
+  uint32_t aph = 0;
+  for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    int t = tile, q;
+    q = fdiv(t, p.dv_tx);
+    const int tx = t - q * p.dv_tx.d; t = q;
+    q = fdiv(t, p.dv_ty);
+    const int ty = t - q * p.dv_ty.d;
+    int n = q;                      // 2-D layers: tiles_z == 1
+    int oy = ty * 8 + row;
+    const int ox = tx * 14 + s;
+    bool valid = s < 14 && ox < p.OW;
+    if (p.stack_hp) {
+      const int R = oy + p.stack_ph;
+      n = fdiv(R, p.dv_hp);
+      oy = R - n * p.stack_hp - p.stack_ph;
+      valid = valid && n < p.stack_n;
+    }
+    valid = valid && static_cast<unsigned>(oy) < static_cast<unsigned>(p.OH);
+    const long long pix = ((static_cast<long long>(n) * p.yDp + p.ypd) * p.yHp + oy + p.yph) * p.yWp + ox + p.ypw;
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(as * p.n_tile + c_lo);
+    mbar_wait(tfull + as, aph);
+    tc_fence_after();
+    for (int c = 0; c < CH; c += 16) {
+      uint32_t d0[16], d1[16], d2[16];
+      tmem_ld16(t_row + c, d0);
+      tmem_ld16(t_row + CP + c, d1);
+      tmem_ld16(t_row + 2 * CP + c, d2);
+      tmem_ld_wait();
+      if (c + 16 >= CH) {   // last read of this accumulator: hand it back before the arithmetic
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(tempty + as), 0));
+          else mbar_arrive(tempty + as);
+        }
+      }
+      uint32_t o[8];
+#pragma unroll
+      for (int i = 0; i < 16; i += 2) {
+        float f0 = __uint_as_float(d0[i]) + __shfl_down_sync(0xffffffffu, __uint_as_float(d1[i]), 1, 16) +
+                   __shfl_down_sync(0xffffffffu, __uint_as_float(d2[i]), 2, 16);
+        float f1 = __uint_as_float(d0[i + 1]) + __shfl_down_sync(0xffffffffu, __uint_as_float(d1[i + 1]), 1, 16) +
+                   __shfl_down_sync(0xffffffffu, __uint_as_float(d2[i + 1]), 2, 16);
+        const float2 b2 = *reinterpret_cast<const float2*>(sm_bias + c_lo + c + i);
+        f0 += b2.x; f1 += b2.y;
+        o[i >> 1] = cvt_bf16x2(f0, f1, RELU);
+      }
+      const int cg = c_lo + c;   // first output channel of this chunk
+      if (valid && cg < p.Cout) {
+        __nv_bfloat16* yp = p.y + pix * p.y_ld + p.y_coff + cg;
+        if (wide_ok && cg + 16 <= p.Cout) {
+          st_global_256(yp, o);
+        } else {
+          *reinterpret_cast<uint4*>(yp) = make_uint4(o[0], o[1], o[2], o[3]);
+          if (cg + 8 < p.Cout) *reinterpret_cast<uint4*>(yp + 8) = make_uint4(o[4], o[5], o[6], o[7]);
+        }
+      }
+    }
+    if (++as == p.acc_stages) { as = 0; aph ^= 1; }
+  }
+}
+
 // The four bilinear taps (16 bytes = 8 channels each) and weights of slab pixel r of the up-sampled half.
 struct UpTaps {
   uint4 qa, qb, qc, qd;
@@ -617,7 +698,7 @@ conv_slab_kernel(const __grid_constant__ SlabKParams p) {
       tmem_relinquish();
     }
   }
-  for (int i = threadIdx.x; i < p.n_tile * p.num_n_tiles; i += blockDim.x) sm_bias[i] = p.bias[i];
+  for (int i = threadIdx.x; i < p.bias_n; i += blockDim.x) sm_bias[i] = p.bias[i];
   if (p.oc_w != nullptr) {
     for (int i = threadIdx.x; i < 3 * p.Cout; i += blockDim.x) sm_ocw[i] = p.oc_w[i];
     if (threadIdx.x < 3) sm_ocw[3 * p.Cout + threadIdx.x] = p.oc_b[threadIdx.x];
@@ -707,6 +788,8 @@ conv_slab_kernel(const __grid_constant__ SlabKParams p) {
 #define TSP_ISSUE_PAIR(TM_, ST_) slab_issue<TM_, 4, ST_, true>(p, smS, wa, tb, full, empty, tfull, tempty, wbar, bfull, bempty)
         if (p.b_stream) {
           if (p.tm == 2) TSP_ISSUE_PAIR(2, true); else TSP_ISSUE_PAIR(1, true);
+        } else if (p.kx) {        // KX kind: one 128-row tile per CTA, three filter-row groups per K stage
+          slab_issue<1, 4, false, true>(p, smS, wa, tb, full, empty, tfull, tempty, wbar, bfull, bempty);
         } else if (p.nk == 2) {   // un-swizzled stem (STEM3D_PAIR): two K = 16 steps per filter row
           if (p.tm == 2) slab_issue<2, 2, false, true>(p, smS, wa, tb, full, empty, tfull, tempty, wbar, bfull, bempty);
           else slab_issue<1, 2, false, true>(p, smS, wa, tb, full, empty, tfull, tempty, wbar, bfull, bempty);
@@ -730,6 +813,10 @@ conv_slab_kernel(const __grid_constant__ SlabKParams p) {
   } else if (warp < NEW) {
     // ---------------------------------------------------------------- epilogue (slab_epilogue above)
     const bool relu = p.act == TEDSPAD_ACT_RELU;
+    if (!E16 && !HAS_UP && p.kx) {
+      if (relu) slab_epilogue_kx<PAIR, true>(p, warp, lane, tmem_base, sm_bias, tfull, tempty);
+      else slab_epilogue_kx<PAIR, false>(p, warp, lane, tmem_base, sm_bias, tfull, tempty);
+    } else {
 #define TSP_EPI(MODE_) \
     do { \
       if (relu) slab_epilogue<HAS_UP, PAIR, MODE_, true, E16>(p, warp, lane, tmem_base, sm_bias, sm_ocw, tfull, tempty, sm_part); \
@@ -741,6 +828,7 @@ conv_slab_kernel(const __grid_constant__ SlabKParams p) {
     else if (p.pool != nullptr) TSP_EPI(EPI_POOL);
     else TSP_EPI(EPI_PLAIN);
 #undef TSP_EPI
+    }
   }
 
   if (HAS_UP && warp >= 11) {
@@ -814,6 +902,7 @@ struct PackP {
   const __nv_bfloat16* w_std;
   __nv_bfloat16* image;
   int kind, n_tile, K_pad, cin_pad, kd, kh, kw, shift;
+  int kx_cp, kx_row0;   // KX kind: channels per filter-column block, first GEMM column of this CTA's half
   long long total;  // image elements
 };
 
@@ -823,7 +912,22 @@ __global__ void __launch_bounds__(256) slab_pack_kernel(const PackP p) {
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
     long long src = -1;
     int n = 0;
-    if (p.kind == TEDSPAD_SLAB_3X3) {
+    if (p.kind == TEDSPAD_SLAB_3X3_KX_PAIR) {
+      // image of one CTA: [ky*CB + cb] blocks of n_tile (= 3*CP/2) rows x 128 B, SWIZZLE_128B; GEMM column
+      // kx_row0 + row = filter column kx = col / CP, output channel col % CP
+      const long long byte = idx * 2;
+      const int blk_bytes = p.n_tile * 128;
+      const int blk = static_cast<int>(byte / blk_bytes);
+      const int o = static_cast<int>(byte - static_cast<long long>(blk) * blk_bytes);
+      const int grp = o >> 10, row = (o >> 7) & 7, chunk_sw = (o >> 4) & 7, within = (o & 15) >> 1;
+      const int col = p.kx_row0 + grp * 8 + row;
+      const int kxi = col / p.kx_cp;
+      n = col - kxi * p.kx_cp;
+      const int k = ((chunk_sw ^ row) << 3) + within;
+      const int cin = p.cin_pad, cb_n = cin / 64;
+      const int ky = blk / cb_n, cb = blk - ky * cb_n;
+      src = static_cast<long long>(ky * 3 + kxi) * cin + cb * 64 + k;
+    } else if (p.kind == TEDSPAD_SLAB_3X3) {
       // image: [tap*CB + cb] blocks of n_tile rows x 128 B, SWIZZLE_128B, 8-row groups 1024 B apart
       const long long byte = idx * 2;
       const int blk_bytes = p.n_tile * 128;
@@ -884,7 +988,8 @@ static int make_plan(const tedspad_conv_slab& c, tedspad_slab_plan& P) {
   const tedspad_tensor& x = c.x;
   const tedspad_tensor& y = c.y;
   const bool stream = c.kind == TEDSPAD_SLAB_3X3_STREAM || c.kind == TEDSPAD_SLAB_3X3_STREAM_PAIR;
-  const bool pair = c.kind == TEDSPAD_SLAB_3X3_PAIR || c.kind == TEDSPAD_SLAB_3X3_STREAM_PAIR || c.kind == TEDSPAD_SLAB_STEM3D_PAIR;
+  const bool kx = c.kind == TEDSPAD_SLAB_3X3_KX_PAIR;
+  const bool pair = c.kind == TEDSPAD_SLAB_3X3_PAIR || c.kind == TEDSPAD_SLAB_3X3_STREAM_PAIR || c.kind == TEDSPAD_SLAB_STEM3D_PAIR || kx;
   P.pair = pair ? 1 : 0;
   TSP_CHECK(c.Cout_pad % 32 == 0 && c.Cout_pad >= 32 && c.Cout_pad <= (stream ? 2048 : 256) && c.Cout <= c.Cout_pad &&
                 c.Cout >= 1 && c.Cout % 8 == 0,
@@ -914,7 +1019,49 @@ static int make_plan(const tedspad_conv_slab& c, tedspad_slab_plan& P) {
   }
   const int cin_total = x.C + (has_up ? c.up.C : 0);
   P.up_cb_first = has_up ? x.C / 64 : 1 << 20;
-  if (c.kind == TEDSPAD_SLAB_3X3 || c.kind == TEDSPAD_SLAB_STEM2D || c.kind == TEDSPAD_SLAB_3X3_PAIR) {
+  if (kx) {
+    // three filter columns stacked along N (slab_epilogue_kx): tile = 8 rows x 16 slab columns -> 14 output columns
+    TSP_CHECK(c.kd == 1 && c.kh == 3 && c.kw == 3 && c.sd == 1 && c.sh == 1 && c.sw == 1 && c.pd == 0 && c.ph == 1 && c.pw == 1,
+              "slab kx: needs a (1,3,3) stride-1 pad-1 convolution");
+    TSP_CHECK(x.D == 1 && y.D == 1 && x.H == y.H && x.W == y.W, "slab kx: 2-D layers with equal input / output extents only");
+    TSP_CHECK(x.C % 64 == 0 && x.C >= 64 && !has_up, "slab kx: x.C=%d must be a multiple of 64 (no fused up-sampling)", x.C);
+    TSP_CHECK(c.Cout_pad == 32 || c.Cout_pad == 64, "slab kx: Cout_pad=%d must be 32 or 64", c.Cout_pad);
+    TSP_CHECK(c.pool.ptr == nullptr && c.oc_w == nullptr && c.res == nullptr, "slab kx: no fused pool / OutConv / residual");
+    const int cp = c.Cout_pad, cb_n = x.C / 64;
+    P.n_tile = 3 * cp;
+    const int b_rows = P.n_tile / 2;                       // weight rows held by one CTA of the pair
+    P.w_bytes = 3 * cb_n * b_rows * 128;
+    P.swizzle128 = 1;
+    P.k_stages = cb_n; P.cb_n = cb_n;
+    P.n_grp = 3; P.nk = 4; P.n_mma = 12;
+    P.tm = 1;
+    slab_w = 16; slab_h = 10;
+    P.box[0] = 64; P.box[1] = slab_w; P.box[2] = slab_h; P.box[3] = 1; P.box[4] = 1;
+    P.tdim[0] = x.C; P.tdim[1] = Wp; P.tdim[2] = Hp; P.tdim[3] = Dp; P.tdim[4] = x.N;
+    P.tstride[0] = static_cast<int64_t>(x.ld) * 2;
+    P.tstride[1] = P.tstride[0] * Wp;
+    P.tstride[2] = P.tstride[1] * Hp;
+    P.tstride[3] = P.tstride[2] * Dp;
+    P.tbase_off = static_cast<int64_t>(x.coff) * 2;
+    P.c_step = 64;
+    P.x_step = 14; P.x_off = x.pw - 1;
+    P.y_step = 8; P.y_off = x.ph - 1;
+    P.z_step = 1; P.z_off = x.pd; P.z_kstep = 0;
+    P.tiles_x = (x.W + 13) / 14;
+    P.tiles_y = (x.H + 7) / 8;
+    P.tiles_z = 1;
+    P.half_a_off = 0;
+    P.a_layout = 2; P.a_lbo = 16; P.a_sbo = 1024;   // the slab is 16 pixels wide: consecutive 8-pixel groups are 1024 B apart
+    P.b_layout = 2; P.b_lbo = 16; P.b_sbo = 1024;
+    P.a_kstep = 32; P.b_kstep = 32;
+    for (int cb = 0; cb < cb_n; ++cb)
+      for (int ky = 0; ky < 3; ++ky) {
+        const int i = cb * 3 + ky;
+        TSP_CHECK(i < TEDSPAD_SLAB_MAX_MMA, "slab kx: table overflow");
+        P.tab[2 * i] = static_cast<uint32_t>(ky * slab_w * 128);
+        P.tab[2 * i + 1] = static_cast<uint32_t>((ky * cb_n + cb) * b_rows * 128);
+      }
+  } else if (c.kind == TEDSPAD_SLAB_3X3 || c.kind == TEDSPAD_SLAB_STEM2D || c.kind == TEDSPAD_SLAB_3X3_PAIR) {
     TSP_CHECK(c.kd == 1 && c.kh == 3 && c.kw == 3 && c.sd == 1 && c.sh == 1 && c.sw == 1 && c.pd == 0 && c.ph == 1 &&
                   c.pw == 1,
               "slab: kind %d needs a (1,3,3) stride-1 pad-1 convolution", c.kind);
@@ -1114,14 +1261,14 @@ static int make_plan(const tedspad_conv_slab& c, tedspad_slab_plan& P) {
   // the halo rows themselves are computed in vain (58/56, 30/28).  Tile row 0 = stacked row ph, so that with an
   // even padded height the 2x2 pooling pairs of the fused MaxPool2d never straddle tiles or images.
   int64_t batch = x.N;
-  const bool kind3x3 = c.kind == TEDSPAD_SLAB_3X3 || stream || c.kind == TEDSPAD_SLAB_3X3_PAIR;
+  const bool kind3x3 = c.kind == TEDSPAD_SLAB_3X3 || stream || c.kind == TEDSPAD_SLAB_3X3_PAIR || kx;
   if (kind3x3 && c.stack_rows >= 0 && x.D == 1 && x.pd == 0 && c.kd == 1 && x.ph >= 1 && !has_up && x.N > 1 &&
-      (c.stack_rows > 0 || Hp < round_up(x.H, 16)) && (c.pool.ptr == nullptr || Hp % 2 == 0)) {
+      (c.stack_rows > 0 || Hp < round_up(x.H, P.y_step)) && (c.pool.ptr == nullptr || Hp % 2 == 0)) {
     P.stack_hp = Hp; P.stack_ph = x.ph; P.stack_n = x.N;
     P.tdim[2] = Hp * x.N; P.tdim[3] = 1; P.tdim[4] = 1;
     P.tstride[2] = P.tstride[1] * Hp * x.N;
     P.tstride[3] = P.tstride[2];
-    P.tiles_y = (Hp * x.N - 2 * x.ph + 15) / 16;
+    P.tiles_y = (Hp * x.N - 2 * x.ph + P.y_step - 1) / P.y_step;
     batch = 1;
   }
   // the bias of every N tile lives in shared memory: 512 floats by default, more for the 1024 / 2048-output convolutions
@@ -1172,6 +1319,28 @@ extern "C" int tedspad_conv_slab_plan(const tedspad_conv_slab* c, tedspad_slab_p
 extern "C" int tedspad_conv_slab_pack(int32_t kind, const void* w_std, int32_t Cout_pad, int32_t K_pad, int32_t cin_pad,
                                       int32_t kd, int32_t kh, int32_t kw, int32_t pw_front, void* image,
                                       int64_t* image_bytes, void* stream) {
+  if (kind == TEDSPAD_SLAB_3X3_KX_PAIR) {
+    TSP_CHECK((Cout_pad == 32 || Cout_pad == 64) && cin_pad % 64 == 0 && kd == 1 && kh == 3 && kw == 3 && K_pad >= 9 * cin_pad,
+              "slab pack kx: bad geometry (Cout_pad=%d cin_pad=%d)", Cout_pad, cin_pad);
+    const int rows = 3 * Cout_pad / 2;   // GEMM columns (weight rows) per CTA
+    const long long half_bytes = 3LL * (cin_pad / 64) * rows * 128;
+    if (image_bytes) *image_bytes = 2 * half_bytes;
+    if (image == nullptr) return 0;
+    TSP_CHECK(w_std != nullptr, "slab pack: null weights");
+    for (int h = 0; h < 2; ++h) {
+      PackP p;
+      memset(&p, 0, sizeof(p));
+      p.w_std = reinterpret_cast<const __nv_bfloat16*>(w_std);
+      p.image = reinterpret_cast<__nv_bfloat16*>(image) + h * (half_bytes / 2);
+      p.kind = kind; p.n_tile = rows; p.K_pad = K_pad; p.cin_pad = cin_pad; p.kd = 1; p.kh = 3; p.kw = 3;
+      p.kx_cp = Cout_pad; p.kx_row0 = h * rows;
+      p.total = half_bytes / 2;
+      const int blocks = static_cast<int>(std::min<long long>((p.total + 255) / 256, 4096));
+      slab_pack_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+      TSP_CUDA(cudaGetLastError());
+    }
+    return 0;
+  }
   TSP_CHECK((kind >= TEDSPAD_SLAB_3X3 && kind <= TEDSPAD_SLAB_STEM3D) || kind == TEDSPAD_SLAB_3X3_PAIR || kind == TEDSPAD_SLAB_STEM3D_PAIR,
             "slab pack: unknown kind %d", kind);
   const bool pair = kind == TEDSPAD_SLAB_3X3_PAIR || kind == TEDSPAD_SLAB_STEM3D_PAIR;
@@ -1257,6 +1426,9 @@ extern "C" int tedspad_conv_slab_forward(const tedspad_conv_slab* c, void* strea
   p.dim_a = p.ty_first ? P.tiles_y : P.tiles_x;
   p.dim_b = p.ty_first ? P.tiles_x : P.tiles_y;
   p.dv_nt = make_div(P.num_n_tiles); p.dv_tx = make_div(p.dim_a); p.dv_ty = make_div(p.dim_b);
+  p.kx = c->kind == TEDSPAD_SLAB_3X3_KX_PAIR ? 1 : 0;
+  p.kx_cp = c->Cout_pad;
+  p.bias_n = p.kx ? c->Cout_pad : P.n_tile * P.num_n_tiles;
   p.dv_tz = make_div(P.tiles_z); p.dv_hp = make_div(P.stack_hp > 0 ? P.stack_hp : 1);
   p.a_desc = umma_desc_template(P.a_layout, P.a_lbo, P.a_sbo);
   p.b_desc = umma_desc_template(P.b_layout, P.b_lbo, P.b_sbo);

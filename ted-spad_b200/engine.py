@@ -35,6 +35,8 @@ I3D_BRANCH_STREAMS = os.environ.get("TEDSPAD_I3D_BRANCH_STREAMS", "0") != "0"
 # next block's weights are packed with their input channels permuted to that order (I3DExecutor._mixed_packed).
 I3D_HEADS_SLAB = SLAB_1X1 and PAD_SMALL_3X3 and os.environ.get("TEDSPAD_I3D_HEADS_SLAB", "1") != "0"
 USE_SLAB_STEM3D = USE_SLAB and os.environ.get("TEDSPAD_SLAB_STEM3D", "1") != "0"
+USE_KX = USE_PAIR and os.environ.get("TEDSPAD_KX", "1") != "0"      # 3x3 layers with few outputs through the KX kind
+KX_COUT_PADS = tuple(int(v) for v in os.environ.get("TEDSPAD_KX_COUT_PADS", "32").split(",") if v)
 USE_STEM_PAIR = USE_PAIR and os.environ.get("TEDSPAD_STEM_PAIR", "1") != "0"   # cta_group::2 for the 64-output 7x7 stems
 STEM_PAIR_MIN_KD = int(os.environ.get("TEDSPAD_STEM_PAIR_MIN_KD", "1"))
 SLAB_WEIGHT_LIMIT = 150 * 1024   # bytes of resident weights that still leave room for three slab stages
@@ -104,6 +106,12 @@ def slab3x3(pc, max_stream_cout=2048):
         return None
     if pc.cin_pad % 64 or pc.cout % 8 or pc.cout_pad % 32 or pc.k_pad != kd * sp[0] * sp[1] * pc.cin_pad:
         return None
+    if USE_KX and kd == 1 and sp == (3, 3) and pc.cout_pad in KX_COUT_PADS and 9 * pc.cin_pad * pc.cout_pad * 2 <= SLAB_WEIGHT_LIMIT:
+        # few outputs: the MMA is bound by its A-operand reads; the KX kind fetches every slab pixel 3 instead of 9 times
+        # (its fallback chain covers the fused-epilogue layers and the shapes it cannot tile).  Measured on B200
+        # (profiles/r2d_kx_kind.txt): the 128 -> 12(16) head of the UNet++ anonymizer 0.72 -> 0.42 ms per 32 clips; at 64
+        # outputs (N = 192) it is NOT faster than the CTA-pair kind - an N = 192 MMA costs what N = 256 does
+        return ops.PackedSlabConv(pc, L.SLAB_3X3_KX_PAIR)
     if kd == 1 and sp == (3, 3) and pc.cout_pad <= 256 and 9 * pc.cin_pad * pc.cout_pad * 2 <= SLAB_WEIGHT_LIMIT:
         # N = 64 is shared-memory-read bound on one SM (67 % of the tensor peak): CTA pairs split the weight rows.
         # At N = 128 the halved weight image makes room for 16x16 tiles (measured +7 %).

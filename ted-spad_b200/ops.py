@@ -237,6 +237,9 @@ class PackedSlabConv:
             self.fallback = PackedSlabConv(pc, L.SLAB_3X3)
         if kind == L.SLAB_STEM3D_PAIR:
             self.fallback = PackedSlabConv(pc, L.SLAB_STEM3D)
+        if kind == L.SLAB_3X3_KX_PAIR:
+            # whatever the KX kind cannot run (fused pool / OutConv / residual, odd tile counts) takes the plain kinds
+            self.fallback = PackedSlabConv(pc, L.SLAB_3X3_PAIR if pc.cout_pad in (64, 128) else L.SLAB_3X3)
         nbytes = C.c_int64(0)
         args = (self.kind, None, pc.cout_pad, pc.k_pad, pc.cin_pad, *pc.k, pc.pad_front[2])
         L.check(L.lib().tedspad_conv_slab_pack(*args, None, C.byref(nbytes), None), "tedspad_conv_slab_pack(size)")
@@ -294,6 +297,12 @@ class PackedSlabConv:
             d = self.desc(x, None, tm=tm, stack_rows=stack_rows, pool=pool)   # (a fused pool constrains the row stacking)
             if L.lib().tedspad_conv_slab_plan(C.byref(d), C.byref(L.SlabPlan())) != 0:
                 return self.fallback
+        if self.kind == L.SLAB_3X3_KX_PAIR:
+            if up is not None or pool is not None or tm != 0 or stack_rows > 0:
+                return self.fallback.resolve(x, tm, up, stack_rows, y, pool)
+            d = self.desc(x, None)
+            if L.lib().tedspad_conv_slab_plan(C.byref(d), C.byref(L.SlabPlan())) != 0:
+                return self.fallback.resolve(x, tm, up, stack_rows, y, pool)
         if self.kind == L.SLAB_STEM3D_PAIR and y is not None:
             # an odd tile count cannot be split over CTA pairs (tiles = 16 rows x 8*tm columns of one output plane)
             if (y.N * y.D * (-(-y.H // 16)) * (-(-y.W // (8 * (tm or 1))))) % 2:
@@ -319,6 +328,8 @@ class PackedSlabConv:
 def conv_slab_forward(x, psc, y, act=L.ACT_RELU, pool=None, outconv=None, tm=0, max_ctas=0, up=None, stack_rows=0, res=None):
     """y = act(conv(x) + bias) through the SLAB feed; optional fused MaxPool2d(2) -> pool, OutConv 1x1 + sigmoid
     -> planar images (y may then be None), and fused Up.forward input: conv([x | upsample2x(up)])."""
+    if psc.kind == L.SLAB_3X3_KX_PAIR and (outconv is not None or res is not None):
+        psc = psc.fallback
     psc = psc.resolve(x, tm, up, stack_rows, y, pool)
     d = psc.desc(x, y, act=act, pool=pool, outconv=outconv, tm=tm, max_ctas=max_ctas, up=up, stack_rows=stack_rows, res=res)
     _count()

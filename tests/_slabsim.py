@@ -40,6 +40,23 @@ def pack_image(kind, w_std, n_tile, k_pad, cin_pad, k, pw_front):
         single = L.SLAB_3X3 if kind == L.SLAB_3X3_PAIR else L.SLAB_STEM3D
         return np.concatenate([pack_image(single, w[h * half:(h + 1) * half].reshape(-1), half, k_pad, cin_pad, k, pw_front)
                                for h in (0, 1)])
+    if kind == L.SLAB_3X3_KX_PAIR:
+        # per CTA half: [ky*CB + cb] blocks of 3*CP/2 rows x 128 B; GEMM column = kx*CP + output channel
+        cp, rows, cb_n = n_tile, 3 * n_tile // 2, cin_pad // 64
+        halves = []
+        for h in (0, 1):
+            total = 3 * cb_n * rows * 128 // 2
+            idx = np.arange(total, dtype=np.int64)
+            byte = idx * 2
+            blk_bytes = rows * 128
+            blk, o = byte // blk_bytes, byte % blk_bytes
+            grp, row, chunk_sw, within = o >> 10, (o >> 7) & 7, (o >> 4) & 7, (o & 15) >> 1
+            col = h * rows + grp * 8 + row
+            kx, n = col // cp, col % cp
+            kk = ((chunk_sw ^ row) << 3) + within
+            ky, cb = blk // cb_n, blk % cb_n
+            halves.append(w[n, (ky * 3 + kx) * cin_pad + cb * 64 + kk])
+        return np.concatenate(halves)
     if kind == L.SLAB_3X3:
         total = 9 * (cin_pad // 64) * n_tile * 128 // 2
         idx = np.arange(total, dtype=np.int64)

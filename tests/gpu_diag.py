@@ -551,7 +551,7 @@ def run_slab_case(name, kind, N, dhw, cin_real, cin_buf, cout, k, stride=(1, 1, 
         b = (torch.rand(cout, generator=g) - 0.5).to(DEV)
         bnp = ((torch.rand(cout, generator=g) + 0.5).to(DEV), (torch.rand(cout, generator=g) - 0.5).to(DEV),
                (torch.rand(cout, generator=g) - 0.5).to(DEV), (torch.rand(cout, generator=g) + 0.5).to(DEV), 1e-3)
-        std_cin = cin_buf if kind in (L.SLAB_3X3, L.SLAB_3X3_STREAM, L.SLAB_3X3_PAIR, L.SLAB_3X3_STREAM_PAIR) else 8
+        std_cin = cin_buf if kind in (L.SLAB_3X3, L.SLAB_3X3_STREAM, L.SLAB_3X3_PAIR, L.SLAB_3X3_STREAM_PAIR, L.SLAB_3X3_KX_PAIR) else 8
         pc = ops.PackedConv(w, b, bnp, stride=stride, pad_front=pad_f, cin_pad=std_cin, device=DEV, n_align=32)
         psc = ops.PackedSlabConv(pc, kind)
         if kind not in (L.SLAB_3X3_STREAM, L.SLAB_3X3_STREAM_PAIR):
@@ -676,6 +676,35 @@ def group_slabpair():
     run_slab_case("P7 64->64 odd 19x21 x2 pair", K, 2, (1, 19, 21), 64, 64, 64, (1, 3, 3), halo=(0, 1, 1))
     run_slab_case("P8 64->64 odd tile count -> single-CTA fallback", K, 1, (1, 16, 48), 64, 64, 64, (1, 3, 3), halo=(0, 1, 1))
     run_slab_case("P9 64->128 28x28 pair (N=128)", K, 2, (1, 28, 28), 64, 64, 128, (1, 3, 3), halo=(0, 1, 1))
+
+
+def group_slabkx():
+    """KX kind: the three taps of a filter row share one A-operand fetch (N = 3 * Cout_pad), 8 x 16 tiles, 14 output columns."""
+    K = L.SLAB_3X3_KX_PAIR
+    run_slab_case("K1 64->64 16x28 kx", K, 2, (1, 16, 28), 64, 64, 64, (1, 3, 3), halo=(0, 1, 1))
+    run_slab_case("K2 64->64 20x24 kx (ragged rows / columns)", K, 2, (1, 20, 24), 64, 64, 64, (1, 3, 3), halo=(0, 1, 1))
+    run_slab_case("K3 128->64 slices kx", K, 4, (1, 32, 32), 128, 128, 64, (1, 3, 3), halo=(0, 1, 1), in_ld=192, in_coff=64,
+                  out_ld=128, out_coff=64)
+    run_slab_case("K4 64->64 112x112 x8 many tiles kx", K, 8, (1, 112, 112), 64, 64, 64, (1, 3, 3), halo=(0, 1, 1))
+    run_slab_case("K5 64->64 odd 19x21 x2 kx (stacked rows)", K, 2, (1, 19, 21), 64, 64, 64, (1, 3, 3), halo=(0, 1, 1))
+    run_slab_case("K6 128->16 head 40x42 x4 kx (Cout_pad 32)", K, 4, (1, 40, 42), 128, 128, 16, (1, 3, 3), halo=(0, 1, 1))
+    run_slab_case("K6b 128->16 head 40x42 x3 kx (odd tile count -> fallback)", K, 3, (1, 40, 42), 128, 128, 16, (1, 3, 3), halo=(0, 1, 1))
+    run_slab_case("K6c 64->8 kx (Cout 8 of 32), no activation", K, 2, (1, 24, 28), 64, 64, 8, (1, 3, 3), halo=(0, 1, 1))
+    run_slab_case("K7 64->64 pool fused -> fallback", K, 3, (1, 32, 48), 64, 64, 64, (1, 3, 3), halo=(0, 1, 1), pool=True,
+                  out_ld=128, out_coff=0)
+    run_slab_case("K8 64->64 + residual -> fallback", K, 3, (1, 56, 56), 64, 64, 64, (1, 3, 3), halo=(0, 1, 1), res=True)
+    run_slab_case("K9 64->40 kx (Cout 40 of 64)", K, 2, (1, 24, 30), 64, 64, 40, (1, 3, 3), halo=(0, 1, 1))
+
+
+def group_kxperf():
+    for K, nm in ((L.SLAB_3X3_PAIR, "pair"), (L.SLAB_3X3_KX_PAIR, "kx")):
+        time_slab(f"64->64 @224 x128 {nm}", K, 128, (1, 224, 224), 64, 64, (1, 3, 3))
+        time_slab(f"128->64 @224 x128 {nm}", K, 128, (1, 224, 224), 128, 64, (1, 3, 3))
+        time_slab(f"128->64 @112 x128 {nm}", K, 128, (1, 112, 112), 128, 64, (1, 3, 3))
+        time_slab(f"64->64 @112 x512 {nm}", K, 512, (1, 112, 112), 64, 64, (1, 3, 3))
+        time_slab(f"64->64 @56 x512 {nm}", K, 512, (1, 56, 56), 64, 64, (1, 3, 3))
+    time_slab("128->16 head @112 x512 3x3", L.SLAB_3X3, 512, (1, 112, 112), 128, 16, (1, 3, 3))
+    time_slab("128->16 head @112 x512 kx", L.SLAB_3X3_KX_PAIR, 512, (1, 112, 112), 128, 16, (1, 3, 3))
 
 
 def group_slab1x1():
@@ -908,12 +937,12 @@ def time_slab(name, kind, N, dhw, cin_buf, cout, k, stride=(1, 1, 1), pad_f=(0, 
     try:
         D, H, W = dhw
         cin_real = cin_real or cin_buf
-        halo = (0, 1, 1) if (kind in (L.SLAB_3X3, L.SLAB_3X3_STREAM, L.SLAB_3X3_PAIR, L.SLAB_3X3_STREAM_PAIR) and D == 1) else (0, 0, 0)
+        halo = (0, 1, 1) if (kind in (L.SLAB_3X3, L.SLAB_3X3_STREAM, L.SLAB_3X3_PAIR, L.SLAB_3X3_STREAM_PAIR, L.SLAB_3X3_KX_PAIR) and D == 1) else (0, 0, 0)
         x = ops.CLTensor(N, D, H, W, cin_buf, halo, device=DEV)
         x.interior().normal_()
         wt = torch.randn(cout, cin_real, *k, device=DEV) / (cin_real * k[0] * k[1] * k[2]) ** 0.5
         pc = ops.PackedConv(wt, None, None, stride=stride, pad_front=pad_f,
-                            cin_pad=cin_buf if kind in (L.SLAB_3X3, L.SLAB_3X3_STREAM, L.SLAB_3X3_PAIR, L.SLAB_3X3_STREAM_PAIR) else 8, device=DEV, n_align=32)
+                            cin_pad=cin_buf if kind in (L.SLAB_3X3, L.SLAB_3X3_STREAM, L.SLAB_3X3_PAIR, L.SLAB_3X3_STREAM_PAIR, L.SLAB_3X3_KX_PAIR) else 8, device=DEV, n_align=32)
         psc = ops.PackedSlabConv(pc, kind, n_tile=n_tile)
         od, oh, ow = pc.out_extent((D, H, W), pad_b)
         y = ops.CLTensor(N, od, oh, ow, cout, (0, 1, 1) if od == 1 else (0, 0, 0), device=DEV)

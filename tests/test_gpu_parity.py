@@ -47,7 +47,7 @@ def _modules(name, stress=False):
 
 
 @pytest.mark.parametrize("group", ["flat", "gather", "multi", "ops", "prep", "slab3", "slabpair", "slabstream", "streampair",
-                                   "slab1x1", "slabstem", "slabup", "fuzz"])
+                                   "slab1x1", "slabstem", "slabup", "slabkx", "fuzz"])
 def test_operator_battery(group):
     """tests/gpu_diag.py: each operator vs torch fp32 on bf16-rounded operands (conv tolerance 2e-2 of the
     output range, i.e. bf16 output rounding; pooling / layout / PIL preprocessing bit-exact)."""
