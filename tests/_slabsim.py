@@ -151,6 +151,9 @@ def simulate_tiles(plan, xbits, image_bits, bias, tiles, k_pad=0):
     out = {}
     nt = plan.n_tile
     img = np.concatenate([image_bits, np.zeros(64, np.uint16)])
+    if plan.pair and not plan.b_stream:   # CTA pairs: two per-CTA images of n_tile / 2 rows, read at the same offset
+        half = plan.w_bytes // 2
+        imgs = [np.concatenate([image_bits[h * half:(h + 1) * half], np.zeros(64, np.uint16)]) for h in (0, 1)]
     for tile in tiles:
         t = tile
         ntile = t % plan.num_n_tiles; t //= plan.num_n_tiles
@@ -175,7 +178,11 @@ def simulate_tiles(plan, xbits, image_bits, bias, tiles, k_pad=0):
                     B = umma_operand(slot, kk * plan.b_kstep, nt, plan.b_layout, plan.b_lbo, plan.b_sbo).astype(np.float64)
                 else:
                     b_off = plan.tab[2 * (tbase + grp) + 1] + kk * plan.b_kstep
-                    B = umma_operand(img, b_off, nt, plan.b_layout, plan.b_lbo, plan.b_sbo).astype(np.float64)
+                    if plan.pair:
+                        B = np.concatenate([umma_operand(im, b_off, nt // 2, plan.b_layout, plan.b_lbo, plan.b_sbo)
+                                            for im in imgs]).astype(np.float64)
+                    else:
+                        B = umma_operand(img, b_off, nt, plan.b_layout, plan.b_lbo, plan.b_sbo).astype(np.float64)
                 for h in range(plan.tm):
                     A = umma_operand(slab, a_off + h * plan.half_a_off, 128, plan.a_layout, plan.a_lbo, plan.a_sbo)
                     acc[h] += A.astype(np.float64) @ B.T
@@ -191,4 +198,46 @@ def simulate_tiles(plan, xbits, image_bits, bias, tiles, k_pad=0):
             oy = np.where(nn < plan.stack_n, oy, -1)   # rows past the last image are never stored
             nn = np.minimum(nn, plan.stack_n - 1)
         out[tile] = (nn, tz, oy, ox, acc.reshape(plan.tm * 128, nt) + bias[None, n0:n0 + nt].astype(np.float64), n0)
+    return out
+
+
+def simulate_tiles_kx(plan, xbits, image_bits, bias, tiles, cp):
+    """The KX kind (TEDSPAD_SLAB_3X3_KX_PAIR): replay the plan for the given tiles and apply slab_epilogue_kx's
+    neighbour sums.  image_bits: the two per-CTA halves back to back (each plan.w_bytes); the pair's MMA reads GEMM
+    columns [0, N/2) from the leader's image and [N/2, N) from the peer's at the SAME offset.
+    Returns {tile: (n[112], oy[112], ox[112], out[112, cp])} for the 8 x 14 output pixels of the tile."""
+    assert plan.tm == 1 and plan.n_tile == 3 * cp and plan.pair == 1 and plan.a_sbo == 1024
+    half = plan.w_bytes // 2
+    imgs = [np.concatenate([image_bits[h * half:(h + 1) * half], np.zeros(64, np.uint16)]) for h in (0, 1)]
+    rows = plan.n_tile // 2
+    out = {}
+    for tile in tiles:
+        t = tile
+        tx = t % plan.tiles_x; t //= plan.tiles_x
+        ty = t % plan.tiles_y; t //= plan.tiles_y
+        n = t
+        acc = np.zeros((128, plan.n_tile), dtype=np.float64)
+        for ks in range(plan.k_stages):
+            coords = (ks * plan.c_step, tx * plan.x_step + plan.x_off, ty * plan.y_step + plan.y_off, plan.z_off, n)
+            slab = tma_box(xbits, plan, coords)
+            for i in range(plan.n_grp * plan.nk):
+                grp, kk = divmod(i, plan.nk)
+                a_off = plan.tab[2 * (ks * plan.n_grp + grp)] + kk * plan.a_kstep
+                b_off = plan.tab[2 * (ks * plan.n_grp + grp) + 1] + kk * plan.b_kstep
+                A = umma_operand(slab, a_off, 128, plan.a_layout, plan.a_lbo, plan.a_sbo).astype(np.float64)
+                B = np.concatenate([umma_operand(img, b_off, rows, plan.b_layout, plan.b_lbo, plan.b_sbo) for img in imgs])
+                acc += A @ B.astype(np.float64).T
+        d = acc.reshape(8, 16, 3, cp)                       # [tile row][slab column][filter column][channel]
+        res = d[:, 0:14, 0] + d[:, 1:15, 1] + d[:, 2:16, 2] + bias[None, None, :cp].astype(np.float64)
+        row, j = np.meshgrid(np.arange(8), np.arange(14), indexing="ij")
+        oy = (ty * 8 + row).reshape(-1)
+        ox = (tx * 14 + j).reshape(-1)
+        nn = np.full(oy.shape, n, dtype=np.int64)
+        if plan.stack_hp:
+            R = oy + plan.stack_ph
+            nn = R // plan.stack_hp
+            oy = R - nn * plan.stack_hp - plan.stack_ph
+            oy = np.where(nn < plan.stack_n, oy, -1)
+            nn = np.minimum(nn, plan.stack_n - 1)
+        out[tile] = (nn, oy, ox, res.reshape(112, cp))
     return out

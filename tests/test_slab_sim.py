@@ -32,7 +32,7 @@ def _run(kind, x_cl, x_ref, w, stride, pad_f, pad_b, y_shape, tm, tiles=None, ci
         image = S.bf16_bits(pc.w)
     else:
         image = S.pack_image(kind, S.bf16_bits(pc.w), pc.cout_pad, pc.k_pad, pc.cin_pad, pc.k, pad_f[2])
-        assert image.size * 2 == psc.image_bytes == plan.w_bytes
+        assert image.size * 2 == psc.image_bytes == plan.w_bytes * (2 if plan.pair else 1)
     wq = pc.w[:cout, :pc.k[0] * pc.k[1] * pc.k[2] * pc.cin_pad].float().reshape(cout, *pc.k, pc.cin_pad)
     wq = wq[..., :w.shape[1]].permute(0, 4, 1, 2, 3).contiguous()
     pad6 = (pad_f[2], pad_b[2], pad_f[1], pad_b[1], pad_f[0], pad_b[0])
@@ -135,6 +135,14 @@ def test_slab_stem3d_plan_reproduces_conv(name, kd, sd, pad_f, pad_b, dhw):
         err, seen, plan = _run(L.SLAB_STEM3D, xc, x, w, (sd, 2, 2), pad_f, pad_b, (N, od, oh, ow), tm)
         assert plan.k_stages == kd and plan.n_mma == 14
         assert seen == N * od * oh * ow and err < 2e-5, (name, tm, err)
+    # the same stem on CTA pairs: two per-CTA weight images of 32 rows (when the tile count is even)
+    psc = ops.PackedSlabConv(ops.PackedConv(w, None, None, stride=(sd, 2, 2), pad_front=pad_f, cin_pad=8, device="cpu", n_align=32),
+                             L.SLAB_STEM3D_PAIR)
+    y = ops.CLTensor(N, od, oh, ow, 64, device="cpu")
+    if psc.resolve(xc, y=y) is psc:
+        err, seen, plan = _run(L.SLAB_STEM3D_PAIR, xc, x, w, (sd, 2, 2), pad_f, pad_b, (N, od, oh, ow), 0)
+        assert plan.pair == 1 and plan.b_lbo == 32 * 16
+        assert seen == N * od * oh * ow and err < 2e-5, (name, "pair", err)
 
 
 def test_slab_plan_rejects_what_it_cannot_run():
@@ -148,3 +156,46 @@ def test_slab_plan_rejects_what_it_cannot_run():
     x = ops.CLTensor(1, 1, 16, 16, 128, (0, 1, 1), device="cpu")
     with pytest.raises(RuntimeError, match="do not fit"):
         ops.PackedSlabConv(big, L.SLAB_3X3).plan(x, ops.CLTensor(1, 1, 16, 16, 128, device="cpu"))
+
+
+@pytest.mark.parametrize("cin,cout,N,H,W", [(64, 64, 2, 20, 24), (128, 16, 4, 16, 30), (64, 40, 2, 19, 21)])
+def test_slab_kx_plan_reproduces_conv(cin, cout, N, H, W):
+    """KX kind: plan (16-pixel-wide slab, SBO 1024, three filter-row groups, N = 3 x Cout_pad), numpy packer and the
+    epilogue's neighbour sums reproduce the convolution on every pixel (ragged rows / columns, stacked rows)."""
+    g = torch.Generator().manual_seed(cin + cout + H)
+    x = torch.randn(N, cin, 1, H, W, generator=g)
+    w = torch.randn(cout, cin, 1, 3, 3, generator=g) / (9 * cin) ** 0.5
+    b = torch.linspace(-0.5, 0.5, cout)
+    xc = ops.CLTensor(N, 1, H, W, cin, (0, 1, 1), device="cpu")
+    xc.interior()[...] = x.permute(0, 2, 3, 4, 1).to(torch.bfloat16)
+    pc = ops.PackedConv(w, b, None, pad_front=(0, 1, 1), cin_pad=cin, device="cpu", n_align=32)
+    psc = ops.PackedSlabConv(pc, L.SLAB_3X3_KX_PAIR)
+    y = ops.CLTensor(N, 1, H, W, cout, (0, 1, 1), device="cpu")
+    plan = psc.plan(xc, y)
+    assert plan.pair == 1 and plan.tm == 1 and plan.n_tile == 3 * pc.cout_pad and plan.n_grp == 3 and plan.total_tiles % 2 == 0
+    image = S.pack_image(L.SLAB_3X3_KX_PAIR, S.bf16_bits(pc.w), pc.cout_pad, pc.k_pad, pc.cin_pad, pc.k, 1)
+    assert image.size * 2 == psc.image_bytes == 2 * plan.w_bytes
+    wq = pc.w[:cout, :9 * cin].float().reshape(cout, 1, 3, 3, cin).permute(0, 4, 1, 2, 3).contiguous()
+    ref = F.conv3d(F.pad(_bf(x), (1, 1, 1, 1, 0, 0)), wq, pc.bias[:cout])[:, :, 0]   # [N,Cout,H,W]
+    res = S.simulate_tiles_kx(plan, S.bf16_bits(xc.buf), image, pc.bias.numpy(), range(plan.total_tiles), pc.cout_pad)
+    worst, seen = 0.0, 0
+    for tile, (n, oy, ox, out) in res.items():
+        ok = (oy >= 0) & (oy < H) & (ox < W)
+        want = ref[torch.from_numpy(n[ok]), :, torch.from_numpy(oy[ok]), torch.from_numpy(ox[ok])].numpy()
+        worst = max(worst, float(np.abs(out[ok][:, :cout] - want).max()))
+        seen += int(ok.sum())
+    assert seen == N * H * W and worst < 3e-5, (worst, seen)
+
+
+@pytest.mark.parametrize("cin,cout", [(64, 64), (128, 64), (64, 128)])
+def test_slab_3x3_pair_plan_reproduces_conv(cin, cout):
+    """CTA-pair kind: per-CTA weight images of Cout_pad / 2 rows at the same table offsets (stacked rows, 20 x 24)."""
+    g = torch.Generator().manual_seed(3 * cin + cout)
+    N, H, W = 2, 20, 24
+    x = torch.randn(N, cin, 1, H, W, generator=g)
+    w = torch.randn(cout, cin, 1, 3, 3, generator=g) / (9 * cin) ** 0.5
+    xc = ops.CLTensor(N, 1, H, W, cin, (0, 1, 1), device="cpu")
+    xc.interior()[...] = x.permute(0, 2, 3, 4, 1).to(torch.bfloat16)
+    err, seen, plan = _run(L.SLAB_3X3_PAIR, xc, x, w, (1, 1, 1), (0, 1, 1), (0, 1, 1), (N, 1, H, W), 0, cin_pad=cin)
+    assert plan.pair == 1 and plan.tm == 2 and plan.total_tiles % 2 == 0
+    assert seen == N * H * W and err < 2e-5, (err, seen)
