@@ -575,7 +575,28 @@ __device__ __forceinline__ void slab_epilogue_kx(const SlabKParams& p, int warp,
         o[i >> 1] = cvt_bf16x2(f0, f1, RELU);
       }
       const int cg = c_lo + c;   // first output channel of this chunk
-      if (valid && cg < p.Cout) {
+      if (p.oc_clip != nullptr && valid && cg == 0) {
+        // space-to-depth head of the UNet++ anonymizer -> encoder clip through the raw-reshape glue (dali_extraction.py:
+        // 171-173), what frames_to_clip_kernel(s2d) does from memory: channel (2a + b) * 3 + colour of low-res pixel
+        // (oy, ox) of frame n is colour `colour` of pixel (2 oy + a, 2 ox + b); plane 3 tf + colour of the clip's 3T
+        // planes is encoder channel ce at time te
+        const int bclip = fdiv(n, p.dv_T), tf = n - bclip * p.oc_T;
+        long long cbase[3];
+#pragma unroll
+        for (int col = 0; col < 3; ++col) {
+          const int pl = 3 * tf + col, ce = fdiv(pl, p.dv_T), te = pl - ce * p.oc_T;
+          cbase[col] = (((static_cast<long long>(bclip) * p.cDp + te + p.cpd) * p.cHp + 2 * oy + p.cph) * p.cWp + 2 * ox + p.cpw) *
+                           p.c_ld + p.c_coff + ce;
+        }
+        const long long row_step = static_cast<long long>(p.cWp) * p.c_ld;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) {
+          const int ab = k / 3, col = k - 3 * ab;
+          const uint16_t v = static_cast<uint16_t>((k & 1) ? (o[k >> 1] >> 16) : (o[k >> 1] & 0xffffu));
+          reinterpret_cast<uint16_t*>(p.oc_clip)[cbase[col] + (ab >> 1) * row_step + (ab & 1) * p.c_ld] = v;
+        }
+      }
+      if (p.y != nullptr && valid && cg < p.Cout) {
         __nv_bfloat16* yp = p.y + pix * p.y_ld + p.y_coff + cg;
         if (wide_ok && cg + 16 <= p.Cout) {
           st_global_256(yp, o);
@@ -1027,6 +1048,8 @@ static int make_plan(const tedspad_conv_slab& c, tedspad_slab_plan& P) {
     TSP_CHECK(x.C % 64 == 0 && x.C >= 64 && !has_up, "slab kx: x.C=%d must be a multiple of 64 (no fused up-sampling)", x.C);
     TSP_CHECK(c.Cout_pad == 32 || c.Cout_pad == 64, "slab kx: Cout_pad=%d must be 32 or 64", c.Cout_pad);
     TSP_CHECK(c.pool.ptr == nullptr && c.oc_w == nullptr && c.res == nullptr, "slab kx: no fused pool / OutConv / residual");
+    TSP_CHECK(c.oc_clip.ptr == nullptr || (c.Cout_pad == 32 && c.Cout >= 12),
+              "slab kx: the space-to-depth clip glue needs the 12-channel head (Cout_pad 32), got Cout=%d", c.Cout);
     const int cp = c.Cout_pad, cb_n = x.C / 64;
     P.n_tile = 3 * cp;
     const int b_rows = P.n_tile / 2;                       // weight rows held by one CTA of the pair
@@ -1379,9 +1402,10 @@ extern "C" int tedspad_conv_slab_forward(const tedspad_conv_slab* c, void* strea
   const tedspad_tensor& y = c->y;
   if (check_tensor(x, "slab.x", (c->kind == TEDSPAD_SLAB_STEM3D || c->kind == TEDSPAD_SLAB_STEM3D_PAIR) ? 4 : 8)) return 1;
   const bool fused_oc = c->oc_w != nullptr;
+  const bool s2d_clip = c->kind == TEDSPAD_SLAB_3X3_KX_PAIR && !fused_oc && c->oc_clip.ptr != nullptr;
   tedspad_tensor ychk = y;
   if (y.ptr == nullptr) {
-    TSP_CHECK(fused_oc, "slab: y.ptr is NULL without a fused OutConv");
+    TSP_CHECK(fused_oc || s2d_clip, "slab: y.ptr is NULL without a fused OutConv / clip glue");
     ychk.ptr = const_cast<void*>(c->w_image);  // extents are still validated
   }
   if (check_tensor(ychk, "slab.y", 8)) return 1;
@@ -1482,6 +1506,18 @@ extern "C" int tedspad_conv_slab_forward(const tedspad_conv_slab* c, void* strea
     }
   }
 
+  if (s2d_clip) {
+    const tedspad_tensor& e = c->oc_clip;
+    if (check_tensor(e, "slab.oc_clip", 1)) return 1;
+    TSP_CHECK(c->oc_T >= 1 && x.N % c->oc_T == 0 && e.N == x.N / c->oc_T && e.D == c->oc_T && e.H == 2 * y.H && e.W == 2 * y.W &&
+                  e.C >= 3,
+              "slab kx: clip [%d,%d,%d,%d,%d] does not match %d space-to-depth frames of T=%d", e.N, e.D, e.H, e.W, e.C, x.N, c->oc_T);
+    p.oc_clip = reinterpret_cast<__nv_bfloat16*>(e.ptr);
+    p.oc_T = c->oc_T;
+    p.dv_T = make_div(c->oc_T);
+    p.cDp = e.D + 2 * e.pd; p.cHp = e.H + 2 * e.ph; p.cWp = e.W + 2 * e.pw;
+    p.cpd = e.pd; p.cph = e.ph; p.cpw = e.pw; p.c_ld = e.ld; p.c_coff = e.coff;
+  }
   const bool has_up = c->up.ptr != nullptr;
   if (has_up) {
     const tedspad_tensor& u = c->up;

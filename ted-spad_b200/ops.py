@@ -252,7 +252,8 @@ class PackedSlabConv:
             L.check(L.lib().tedspad_conv_slab_pack(*args, self.image.data_ptr(), C.byref(nbytes), _stream()),
                     "tedspad_conv_slab_pack")
 
-    def desc(self, x, y, act=L.ACT_RELU, pool=None, outconv=None, tm=0, max_ctas=0, up=None, stack_rows=0, res=None):
+    def desc(self, x, y, act=L.ACT_RELU, pool=None, outconv=None, tm=0, max_ctas=0, up=None, stack_rows=0, res=None,
+             s2d_clip=None):
         """outconv = (w fp32 [3,Cout], b fp32 [3], planes bf16 [N,3,H,W] | None, frames fp32 [N,3,H,W] | None
         [, clip CLTensor [B,T,H,W,>=3], T]): with `clip` the sigmoid images go straight into the encoder input
         through the raw-reshape glue"""
@@ -279,6 +280,8 @@ class PackedSlabConv:
             d.oc_frames = frames.data_ptr() if frames is not None else None
             if len(outconv) > 4:
                 d.oc_clip, d.oc_T = outconv[4].desc(), int(outconv[5])
+        if s2d_clip is not None:   # KX kind: (clip CLTensor [B,T,2H,2W,>=3], T) - the space-to-depth head's glue, fused
+            d.oc_clip, d.oc_T = s2d_clip[0].desc(), int(s2d_clip[1])
         d.kind, d.Cout, d.Cout_pad = self.kind, pc.cout, pc.cout_pad
         d.kd, d.kh, d.kw = pc.k
         d.sd, d.sh, d.sw = pc.stride
@@ -325,13 +328,19 @@ class PackedSlabConv:
         return plan
 
 
-def conv_slab_forward(x, psc, y, act=L.ACT_RELU, pool=None, outconv=None, tm=0, max_ctas=0, up=None, stack_rows=0, res=None):
+def conv_slab_forward(x, psc, y, act=L.ACT_RELU, pool=None, outconv=None, tm=0, max_ctas=0, up=None, stack_rows=0, res=None,
+                      s2d_clip=None):
     """y = act(conv(x) + bias) through the SLAB feed; optional fused MaxPool2d(2) -> pool, OutConv 1x1 + sigmoid
-    -> planar images (y may then be None), and fused Up.forward input: conv([x | upsample2x(up)])."""
+    -> planar images (y may then be None), and fused Up.forward input: conv([x | upsample2x(up)]).  s2d_clip = (clip,
+    T): the KX kind scatters its 12-channel space-to-depth output straight into the encoder clip (y may be None); the
+    caller checks with slab_runs_kx() that the KX kind really runs this input."""
     if psc.kind == L.SLAB_3X3_KX_PAIR and (outconv is not None or res is not None):
         psc = psc.fallback
     psc = psc.resolve(x, tm, up, stack_rows, y, pool)
-    d = psc.desc(x, y, act=act, pool=pool, outconv=outconv, tm=tm, max_ctas=max_ctas, up=up, stack_rows=stack_rows, res=res)
+    if s2d_clip is not None and psc.kind != L.SLAB_3X3_KX_PAIR:
+        raise RuntimeError("conv_slab_forward: the fused space-to-depth clip glue needs the KX kind (check slab_runs_kx first)")
+    d = psc.desc(x, y, act=act, pool=pool, outconv=outconv, tm=tm, max_ctas=max_ctas, up=up, stack_rows=stack_rows, res=res,
+                 s2d_clip=s2d_clip)
     _count()
     if CONV_EVENTS is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -344,6 +353,11 @@ def conv_slab_forward(x, psc, y, act=L.ACT_RELU, pool=None, outconv=None, tm=0, 
         return y
     L.check(L.lib().tedspad_conv_slab_forward(C.byref(d), _stream()), "tedspad_conv_slab_forward")
     return y
+
+
+def slab_runs_kx(x, psc):
+    """True when `psc` is a KX-kind convolution that runs input x as such (even tile count, no fallback)."""
+    return psc is not None and psc.kind == L.SLAB_3X3_KX_PAIR and psc.resolve(x) is psc
 
 
 def planes_to_clip(planes, y, T):

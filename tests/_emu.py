@@ -105,7 +105,12 @@ def _gather_acc(x, pc, out_shape):
     return acc.reshape(N, OD, OH, OW, pc.cout)
 
 
-def conv_slab_forward(x, psc, y, act=L.ACT_RELU, pool=None, outconv=None, tm=0, max_ctas=0, up=None, stack_rows=0, res=None):
+def slab_runs_kx(x, psc):
+    return psc is not None and psc.kind == L.SLAB_3X3_KX_PAIR and psc.resolve(x) is psc
+
+
+def conv_slab_forward(x, psc, y, act=L.ACT_RELU, pool=None, outconv=None, tm=0, max_ctas=0, up=None, stack_rows=0, res=None,
+                      s2d_clip=None):
     """SLAB feed (csrc/conv_slab.cu): same arithmetic as the gather restatement; the fused MaxPool2d(2) pools the
     ROUNDED output (as the kernel does), the fused OutConv consumes the un-rounded fp32 activations; with `up` the
     convolution input is [x | upsample2x(up)] (the up-sampled half rounded to the storage dtype, as the kernel does)."""
@@ -122,6 +127,12 @@ def conv_slab_forward(x, psc, y, act=L.ACT_RELU, pool=None, outconv=None, tm=0, 
         acc = acc + res.interior().float()
     acc = _act(acc, act)
     store_dtype = y.buf.dtype if y is not None else (pool.buf.dtype if pool is not None else torch.float32)
+    if s2d_clip is not None:   # KX kind: 12 space-to-depth channels -> encoder clip (rounded to the storage dtype first)
+        clip, T = s2d_clip
+        v = acc.to(clip.buf.dtype).float()[:, 0, :, :, :12]
+        F_, hh, ww, _ = v.shape
+        fr = v.reshape(F_, hh, ww, 2, 2, 3).permute(0, 5, 1, 3, 2, 4).reshape(F_, 3, 2 * hh, 2 * ww).contiguous()
+        planes_to_clip_into(fr, clip, T)
     if y is not None:
         y.interior()[...] = acc.to(y.buf.dtype)
     if pool is not None:

@@ -696,6 +696,39 @@ def group_slabkx():
     run_slab_case("K9 64->40 kx (Cout 40 of 64)", K, 2, (1, 24, 30), 64, 64, 40, (1, 3, 3), halo=(0, 1, 1))
 
 
+    # the head's raw-reshape glue fused into the KX epilogue == frames_to_clip(s2d) of the stored head tensor, bit for bit
+    try:
+        g = torch.Generator(device="cpu").manual_seed(9)
+        N, T, H, W = 8, 4, 24, 28
+        x = ops.CLTensor(N, 1, H, W, 128, (0, 1, 1), device=DEV)
+        x.interior().normal_(generator=None)
+        wt = torch.randn(16, 128, 1, 3, 3, generator=g).to(DEV) / 34.0
+        wt[12:] = 0
+        pc = ops.PackedConv(wt, torch.randn(16, generator=g).to(DEV) * 0.1, None, pad_front=(0, 1, 1), cin_pad=128, device=DEV, n_align=32)
+        psc = ops.PackedSlabConv(pc, K)
+        okk = ops.slab_runs_kx(x, psc)
+        y = ops.CLTensor(N, 1, H, W, 16, (0, 1, 1), device=DEV)
+        clips = []
+        for fused in (True, False):
+            clip = ops.CLTensor(N // T, T, 2 * H, 2 * W, 4, device=DEV)
+            clip.buf.zero_()
+            if fused:
+                ops.conv_slab_forward(x, psc, y, act=L.ACT_NONE, s2d_clip=(clip, T))
+            else:
+                ops.frames_to_clip(y, clip, T, None, s2d=True)
+            clips.append(clip.buf.clone())
+        clip_only = ops.CLTensor(N // T, T, 2 * H, 2 * W, 4, device=DEV)
+        clip_only.buf.zero_()
+        ops.conv_slab_forward(x, psc, None, act=L.ACT_NONE, s2d_clip=(clip_only, T))   # no head tensor at all
+        torch.cuda.synchronize()
+        ok = okk and bool(torch.equal(clips[0], clips[1])) and bool(torch.equal(clip_only.buf, clips[1])) and float(clips[1].abs().sum()) > 0
+        RESULTS.append(("K10 kx fused s2d clip glue", ok))
+        print(f"[{'PASS' if ok else 'FAIL'}] K10 kx head: fused clip glue == frames_to_clip(s2d) bit for bit (with and without the head tensor), kx={okk}")
+    except Exception:
+        RESULTS.append(("K10 kx fused s2d clip glue", False))
+        print(f"[FAIL] K10: EXCEPTION\n{traceback.format_exc()}", flush=True)
+
+
 def group_kxperf():
     for K, nm in ((L.SLAB_3X3_PAIR, "pair"), (L.SLAB_3X3_KX_PAIR, "kx")):
         time_slab(f"64->64 @224 x128 {nm}", K, 128, (1, 224, 224), 64, 64, (1, 3, 3))

@@ -131,7 +131,8 @@ def _tap_errors(fa, ft, arch, taps_fa, taps_ft, B=1):
                  "decoder.blocks.x_0_1.conv2": ex_fa.bufs.find("x_0_1"), "decoder.blocks.x_1_2.conv2": P2.slice(128, 64),
                  "decoder.blocks.x_0_2.conv2": ex_fa.bufs.find("x_0_2"),
                  "decoder.blocks.x_0_3.conv2": _Dense(_depth_to_space(ex_fa.bufs.find("x_0_3"), 32)),
-                 "out": _Dense(_depth_to_space(ex_fa.bufs.find("head"), 3))}
+                 "out": _Dense(_depth_to_space(ex_fa.bufs.find("head"), 3)) if ex_fa.bufs.find("head") is not None else None}
+        where = {k: b for k, b in where.items() if b is not None}   # (the head tensor does not exist when its glue is fused)
         for k, b in where.items():
             pairs.append((f"unetpp:{k}", b, taps_fa[k]))
     if arch == "i3d":

@@ -231,6 +231,12 @@ def test_executor_wiring_unetpp_exact(monkeypatch):
     # glue: the clip is the RAW reshape of the frames (dali_extraction.py:171-173)
     want = ref.reshape(2, 2, 3, 48, 80).reshape(2, 3, 2, 48, 80)
     assert (enc.to_ncdhw()[:, :3] - want).abs().max() < 1e-4
+    # without frames_out the head's KX epilogue scatters straight into the clip (no head tensor, no glue kernel): same clip
+    assert ops.slab_runs_kx(ex.bufs.find("x_0_3"), ex.head.slab)
+    enc2 = ops.CLTensor(2, 2, 48, 80, engine.ENC_IN_CHANNELS, device="cpu")
+    enc2.buf.zero_()
+    ex.run(x0, enc2, 2)
+    assert torch.equal(enc2.interior()[..., :3], enc.interior()[..., :3]) and bool((enc2.interior()[..., 3:] == 0).all())
     with pytest.raises(RuntimeError, match="divisible by 16"):
         ex.run(ex.input_buffer(1, 40, 52), ops.CLTensor(1, 1, 40, 52, engine.ENC_IN_CHANNELS, device="cpu"), 1)
 
