@@ -288,7 +288,7 @@ def sharded_dataset_run(ext_factory, device, rank, world, dist, n_videos=256, nc
             "clip_forwards": clip_forwards, "seconds": ms / 1e3, "files_ok": bool(ok),
             "lpt_imbalance_max_over_mean_frames": max(loads) / (sum(loads) / len(loads)),
             "per_rank_seconds": [round(float(v), 3) for v in per_rank],
-            "what": "extract_dataset_distributed: log-uniform 64..2048-frame 240x320 videos from pinned host memory, 10-crop, "
+            "what": f"extract_dataset_distributed: log-uniform 64..2048-frame 240x320 videos from pinned host memory, {ncrops}-crop, "
                     "LPT video shards, .npy per video; timed on the device, max over ranks"}
 
 
@@ -488,12 +488,36 @@ def main():
                 line[key] = {"error": f"{type(e).__name__}: {e}"[:300]}
                 torch.cuda.empty_cache()
 
+        def batch_sweep():
+            # BASELINE configs[4]: throughput over the batch size (8-128 clips per step, 5-crop: the five crop boxes
+            # of each snippet, so a step of B clips reads B/5 snippets' frames), same networks as the headline; under
+            # torchrun every rank sweeps its own batches (barrier + max over ranks like the headline), value = all ranks
+            sweep = {}
+            (ch5, cw5), boxes5 = crop_boxes(*SRC_HW, ncrops=5)
+            for Bs in (8, 16, 64, 128):
+                ext_s = SnippetExtractor(fa, ft, reso=RESO, batch_clips=Bs, ncrops=5)
+                d5 = np.zeros((Bs, T, 4), dtype=np.int32)
+                for c_ in range(Bs):
+                    t_, l_, f_ = boxes5[c_ % 5]
+                    d5[c_, :, 0] = (c_ // 5) * T + np.arange(T)
+                    d5[c_, :, 1], d5[c_, :, 2], d5[c_, :, 3] = t_, l_, f_
+                d5 = d5.reshape(-1, 4)
+                for i in range(3):
+                    ext_s.features_of_clips(dev_sets[i % 2], d5, (ch5, cw5))
+                k = 6 if Bs <= 64 else 4
+                ms_s = timed(lambda i: ext_s.features_of_clips(dev_sets[i % 2], d5, (ch5, cw5)), k)
+                sweep[str(Bs)] = round(world * Bs * k / (ms_s / 1e3), 1)
+                del ext_s
+            return sweep
+
         if world > 1:
-            def sharded():
-                out = sharded_dataset_run(ext_factory, device, rank, world, dist, n_videos=args.sharded_videos)
+            def sharded(ncrops, n_videos):
+                out = sharded_dataset_run(ext_factory, device, rank, world, dist, n_videos=n_videos, ncrops=ncrops)
                 out["efficiency_vs_replicas"] = out["value"] / clips_per_s
                 return out
-            guarded("sharded", sharded)
+            guarded("sharded", lambda: sharded(10, args.sharded_videos))               # BASELINE configs[2] shape (10-crop)
+            guarded("sharded_5crop", lambda: sharded(5, max(world, args.sharded_videos // 2)))   # configs[4] shape (5-crop)
+            guarded("batch_sweep_5crop_clips_per_s", batch_sweep)
         else:
             def other_archs():
                 # other encoder / anonymizer pairs of the boundary, same step definition, fewer steps
@@ -510,27 +534,6 @@ def main():
                     del ext2, fa2, ft2
                     torch.cuda.empty_cache()
                 return archs
-
-            def batch_sweep():
-                # BASELINE configs[4]: throughput over the batch size (8-128 clips per step, 5-crop: the five crop boxes
-                # of each snippet, so a step of B clips reads B/5 snippets' frames), same networks as the headline
-                sweep = {}
-                (ch5, cw5), boxes5 = crop_boxes(*SRC_HW, ncrops=5)
-                for Bs in (8, 16, 64, 128):
-                    ext_s = SnippetExtractor(fa, ft, reso=RESO, batch_clips=Bs, ncrops=5)
-                    d5 = np.zeros((Bs, T, 4), dtype=np.int32)
-                    for c_ in range(Bs):
-                        t_, l_, f_ = boxes5[c_ % 5]
-                        d5[c_, :, 0] = (c_ // 5) * T + np.arange(T)
-                        d5[c_, :, 1], d5[c_, :, 2], d5[c_, :, 3] = t_, l_, f_
-                    d5 = d5.reshape(-1, 4)
-                    for i in range(3):
-                        ext_s.features_of_clips(dev_sets[i % 2], d5, (ch5, cw5))
-                    k = 6 if Bs <= 64 else 4
-                    ms_s = timed(lambda i: ext_s.features_of_clips(dev_sets[i % 2], d5, (ch5, cw5)), k)
-                    sweep[str(Bs)] = round(Bs * k / (ms_s / 1e3), 1)
-                    del ext_s
-                return sweep
 
             guarded("other_archs", other_archs)
             guarded("batch_sweep_5crop_clips_per_s", batch_sweep)
