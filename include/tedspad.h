@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define TEDSPAD_ABI_VERSION 8
+#define TEDSPAD_ABI_VERSION 9
 
 enum { TEDSPAD_ACT_NONE = 0, TEDSPAD_ACT_RELU = 1, TEDSPAD_ACT_SIGMOID = 2 };
 /* A-operand feed of the implicit GEMM: AUTO picks FLAT when legal. */

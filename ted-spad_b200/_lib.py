@@ -16,7 +16,7 @@ RESAMPLE_AA_FLOAT, RESAMPLE_PIL_U8 = 0, 1
 SLAB_3X3, SLAB_STEM2D, SLAB_STEM3D, SLAB_3X3_STREAM, SLAB_3X3_PAIR, SLAB_3X3_STREAM_PAIR, SLAB_STEM3D_PAIR = 0, 1, 2, 3, 4, 5, 6
 SLAB_3X3_KX_PAIR = 7
 SLAB_MAX_MMA = 112
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 
 class TensorDesc(C.Structure):
