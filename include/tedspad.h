@@ -115,7 +115,9 @@ int tedspad_conv_forward(const tedspad_conv* p, void* stream);
  *                        layout: pass it as `w_image`, with K_pad).  A K stage = (temporal tap, 64-channel
  *                        block).  The 128-channel DoubleConv layers (unet_parts.py:15-22), Conv3d_2c_3x3
  *                        and the Inception 3x3x3 branches (aux_code/models/i3d.py:244,132-136).  Taps
- *                        outside the tensor are zero-filled by TMA: no halo required.
+ *                        outside the tensor are zero-filled by TMA: no halo required.  1x1x1 convolutions may also be
+ *                        STRIDED (strides <= 2, pads 0: the down-sample projections of the ResNet encoders): the TMA box
+ *                        then walks the input with the convolution's stride.
  *   TEDSPAD_SLAB_3X3_PAIR  TEDSPAD_SLAB_3X3 executed by CTA PAIRS (clusters of two CTAs on the SMs of one TPC,
  *                        tcgen05.mma.cta_group::2, M = 256): each CTA owns one tile and HALF of the weight rows, so
  *                        the shared-memory operand reads that bound the N = 64 tensor-core rate at 67 % drop to

@@ -107,7 +107,7 @@ int encode_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint
 }
 
 int encode_tmap_5d_bf16(CUtensorMap* out, const void* base, const uint64_t dims[5], const uint64_t strides_bytes[4],
-                        const uint32_t box[5], bool swizzle128) {
+                        const uint32_t box[5], bool swizzle128, const uint32_t* elem_strides) {
   EncodeTiledFn fn = get_encode_fn();
   TSP_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
   TSP_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "tensor map: base %p must be 16-byte aligned", base);
@@ -116,6 +116,7 @@ int encode_tmap_5d_bf16(CUtensorMap* out, const void* base, const uint64_t dims[
   for (int i = 0; i < 5; ++i) {
     d[i] = dims[i];
     b[i] = box[i];
+    if (elem_strides != nullptr) es[i] = elem_strides[i];   // traversal stride: ceil(box / stride) elements are loaded
     TSP_CHECK(dims[i] >= 1 && box[i] >= 1 && box[i] <= 256, "tensor map: bad dim/box %d: %llu / %u", i,
               (unsigned long long)dims[i], box[i]);
   }

@@ -37,7 +37,7 @@ int encode_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint
 // 5-D bf16 tensor map (dims/box innermost first, strides of dims 1..4 in bytes), zero fill out of
 // bounds, optional 128-byte swizzle (box[0] * 2 must then be 128 bytes).
 int encode_tmap_5d_bf16(CUtensorMap* out, const void* base, const uint64_t dims[5], const uint64_t strides_bytes[4],
-                        const uint32_t box[5], bool swizzle128);
+                        const uint32_t box[5], bool swizzle128, const uint32_t* elem_strides = nullptr);
 
 int num_sms();   // of the CURRENT device (cached per device)
 

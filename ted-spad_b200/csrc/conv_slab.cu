@@ -1173,10 +1173,19 @@ static int make_plan(const tedspad_conv_slab& c, tedspad_slab_plan& P) {
   } else if (stream) {
     const bool k33 = c.kh == 3 && c.kw == 3 && c.ph == 1 && c.pw == 1;
     const bool k11 = c.kh == 1 && c.kw == 1 && c.ph == 0 && c.pw == 0;   // 1x1x1 and (3,1,1): one tap per K stage
-    TSP_CHECK((c.kd == 1 || c.kd == 3) && (k33 || k11) && c.sd == 1 && c.sh == 1 && c.sw == 1 && c.pd == c.kd / 2,
-              "slab stream: needs a (1|3) x (3x3 | 1x1) stride-1 same-padded convolution");
+    // strided 1x1x1 (the down-sample projections of the ResNet encoders: torchvision resnet.py:96-99, large_i3d.py:
+    // 150-156, video/resnet.py): the slab of a tile IS the tile, so a stride is nothing but the traversal stride of the
+    // TMA box (cuTensorMapEncodeTiled elementStrides) - the slab holds every sh-th / sw-th pixel of a 2x larger window
+    const bool strided = k11 && c.kd == 1 && (c.sd > 1 || c.sh > 1 || c.sw > 1);
+    TSP_CHECK((c.kd == 1 || c.kd == 3) && (k33 || k11) && c.pd == c.kd / 2 &&
+                  ((c.sd == 1 && c.sh == 1 && c.sw == 1) || (strided && c.sd <= 2 && c.sh <= 2 && c.sw <= 2 && !has_up && !pair)),
+              "slab stream: needs a (1|3) x (3x3 | 1x1) stride-1 same-padded convolution, or a 1x1x1 one with strides <= 2");
     const int ntap = c.kh * c.kw, hw = c.kw / 2;   // spatial taps per K stage, halo of the slab
-    TSP_CHECK(x.D == y.D && x.H == y.H && x.W == y.W, "slab: output extents must equal input extents");
+    if (strided)
+      TSP_CHECK(y.D == (x.D - 1) / c.sd + 1 && y.H == (x.H - 1) / c.sh + 1 && y.W == (x.W - 1) / c.sw + 1 && c.pool.ptr == nullptr,
+                "slab stream: strided 1x1x1 output [%d,%d,%d] does not match input [%d,%d,%d]", y.D, y.H, y.W, x.D, x.H, x.W);
+    else
+      TSP_CHECK(x.D == y.D && x.H == y.H && x.W == y.W, "slab: output extents must equal input extents");
     TSP_CHECK(x.C % 64 == 0 && x.C >= 64, "slab stream: x.C=%d must be a multiple of 64", x.C);
     TSP_CHECK(c.K_pad == c.kd * ntap * cin_total, "slab stream: K_pad=%d != %d taps x %d channels", c.K_pad, c.kd * ntap, cin_total);
     TSP_CHECK(c.oc_w == nullptr, "slab stream: fused OutConv needs the resident-weight kind");
@@ -1208,12 +1217,13 @@ static int make_plan(const tedspad_conv_slab& c, tedspad_slab_plan& P) {
     P.tbase_off = static_cast<int64_t>(x.coff) * 2;
     // no halo needed: taps outside the tensor are zero-filled by TMA (a zero halo works just as well)
     P.c_step = 64;
-    P.x_step = 8 * tm; P.x_off = x.pw - hw;
-    P.y_step = 16; P.y_off = x.ph - hw;
-    P.z_step = 1; P.z_off = x.pd - c.kd / 2; P.z_kstep = 1;
-    P.tiles_x = (x.W + 8 * tm - 1) / (8 * tm);
-    P.tiles_y = (x.H + 15) / 16;
-    P.tiles_z = x.D;
+    // (x_step / y_step / z_step are in INPUT pixels: a strided tile starts sw * 8 * tm columns after its neighbour)
+    P.x_step = 8 * tm * c.sw; P.x_off = x.pw - hw;
+    P.y_step = 16 * c.sh; P.y_off = x.ph - hw;
+    P.z_step = c.sd; P.z_off = x.pd - c.kd / 2; P.z_kstep = 1;
+    P.tiles_x = (y.W + 8 * tm - 1) / (8 * tm);
+    P.tiles_y = (y.H + 15) / 16;
+    P.tiles_z = y.D;
     P.half_a_off = 8 * 128;
     P.a_layout = 2; P.a_lbo = 16; P.a_sbo = slab_w * 128;
     P.b_layout = 2; P.b_lbo = 16; P.b_sbo = 1024;
@@ -1285,7 +1295,7 @@ static int make_plan(const tedspad_conv_slab& c, tedspad_slab_plan& P) {
   // even padded height the 2x2 pooling pairs of the fused MaxPool2d never straddle tiles or images.
   int64_t batch = x.N;
   const bool kind3x3 = c.kind == TEDSPAD_SLAB_3X3 || stream || c.kind == TEDSPAD_SLAB_3X3_PAIR || kx;
-  if (kind3x3 && c.stack_rows >= 0 && x.D == 1 && x.pd == 0 && c.kd == 1 && x.ph >= 1 && !has_up && x.N > 1 &&
+  if (kind3x3 && c.stack_rows >= 0 && x.D == 1 && x.pd == 0 && c.kd == 1 && x.ph >= 1 && !has_up && x.N > 1 && c.sh == 1 && c.sw == 1 &&
       (c.stack_rows > 0 || Hp < round_up(x.H, P.y_step)) && (c.pool.ptr == nullptr || Hp % 2 == 0)) {
     P.stack_hp = Hp; P.stack_ph = x.ph; P.stack_n = x.N;
     P.tdim[2] = Hp * x.N; P.tdim[3] = 1; P.tdim[4] = 1;
@@ -1422,7 +1432,14 @@ extern "C" int tedspad_conv_slab_forward(const tedspad_conv_slab* c, void* strea
   for (int i = 0; i < 5; ++i) { dims[i] = (uint64_t)P.tdim[i]; box[i] = (uint32_t)P.box[i]; }
   for (int i = 0; i < 4; ++i) strides[i] = (uint64_t)P.tstride[i];
   const uint8_t* base = reinterpret_cast<const uint8_t*>(x.ptr) + P.tbase_off;
-  if (encode_tmap_5d_bf16(&p.tmA, base, dims, strides, box, P.swizzle128 != 0)) return 3;
+  uint32_t estr[5] = {1, 1, 1, 1, 1};
+  if (P.b_stream && (c->sd > 1 || c->sh > 1 || c->sw > 1)) {
+    // strided 1x1x1: the box spans s x as many input pixels, the TMA keeps every s-th one (box[] counts what it keeps);
+    // one tile covers ONE output depth, so the depth stride is in the tile origin (z_step), not in the box
+    estr[1] = (uint32_t)c->sw; estr[2] = (uint32_t)c->sh;
+    box[1] = box[1] * estr[1]; box[2] = box[2] * estr[2];
+  }
+  if (encode_tmap_5d_bf16(&p.tmA, base, dims, strides, box, P.swizzle128 != 0, estr)) return 3;
   p.w_image = reinterpret_cast<const uint8_t*>(c->w_image);
   p.bias = c->bias;
   p.b_stream = P.b_stream; p.b_stages = P.b_stages; p.b_stride = P.b_stride; p.cb_n = P.cb_n; p.cin = P.cin;

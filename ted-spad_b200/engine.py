@@ -36,6 +36,7 @@ I3D_BRANCH_STREAMS = os.environ.get("TEDSPAD_I3D_BRANCH_STREAMS", "0") != "0"
 I3D_HEADS_SLAB = SLAB_1X1 and PAD_SMALL_3X3 and os.environ.get("TEDSPAD_I3D_HEADS_SLAB", "1") != "0"
 USE_SLAB_STEM3D = USE_SLAB and os.environ.get("TEDSPAD_SLAB_STEM3D", "1") != "0"
 UNETPP_FUSE_GLUE = os.environ.get("TEDSPAD_UNETPP_FUSE_GLUE", "1") != "0"   # raw-reshape glue in the head's KX epilogue
+SLAB_STRIDED_1X1 = os.environ.get("TEDSPAD_SLAB_STRIDED_1X1", "1") != "0"   # down-sample projections through the slab kernel
 USE_KX = USE_PAIR and os.environ.get("TEDSPAD_KX", "1") != "0"      # 3x3 layers with few outputs through the KX kind
 KX_COUT_PADS = tuple(int(v) for v in os.environ.get("TEDSPAD_KX_COUT_PADS", "32").split(",") if v)
 USE_STEM_PAIR = USE_PAIR and os.environ.get("TEDSPAD_STEM_PAIR", "1") != "0"   # cta_group::2 for the 64-output 7x7 stems
@@ -100,6 +101,11 @@ def slab3x3(pc, max_stream_cout=2048):
     resident weights when they fit in shared memory (the 64-channel DoubleConv layers), streamed weight blocks
     otherwise (128-channel DoubleConv layers, Conv3d_2c_3x3, Inception 3x3x3 branches, ResNet (1,3,3)/3x3x3)."""
     kd, sp = pc.k[0], pc.k[1:]
+    if USE_SLAB and SLAB_1X1 and SLAB_STRIDED_1X1 and pc.k == (1, 1, 1) and pc.stride != (1, 1, 1) and max(pc.stride) <= 2 and \
+            pc.pad_front == (0, 0, 0) and pc.cin_pad % 64 == 0 and pc.cout % 8 == 0 and pc.cout_pad % 32 == 0 and \
+            pc.n_tile % 32 == 0 and pc.cout_pad <= max_stream_cout and pc.k_pad == pc.cin_pad:
+        # strided 1x1x1 (the ResNets' down-sample projections): the streaming kind with a strided TMA box
+        return ops.PackedSlabConv(pc, L.SLAB_3X3_STREAM)
     if not USE_SLAB or kd not in (1, 3) or sp not in ((3, 3), (1, 1)) or pc.stride != (1, 1, 1) or \
             pc.pad_front != (kd // 2, sp[0] // 2, sp[1] // 2):
         return None

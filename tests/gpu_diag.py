@@ -754,6 +754,17 @@ def group_slab1x1():
     run_slab_case("T8 2-D 1x1 128->128 haloed (stacked rows)", K, 3, (1, 20, 24), 128, 128, 128, (1, 1, 1), pad_f=(0, 0, 0),
                   halo=(0, 1, 1))
     run_slab_case("T9 1x1x1 832->128 7x7", K, 4, (2, 7, 7), 832, 832, 128, (1, 1, 1), pad_f=(0, 0, 0))
+    # strided 1x1x1 (down-sample projections): the TMA box walks the input with the convolution's stride
+    run_slab_case("T10 2-D 1x1 s2 64->128 56x56 haloed (resnet18 layer2.0.downsample)", K, 3, (1, 56, 56), 64, 64, 128, (1, 1, 1),
+                  stride=(1, 2, 2), pad_f=(0, 0, 0), halo=(0, 1, 1), out_halo=(0, 1, 1))
+    run_slab_case("T11 2-D 1x1 s2 128->256 odd 23x21, slice in / out", K, 2, (1, 23, 21), 128, 128, 256, (1, 1, 1), stride=(1, 2, 2),
+                  pad_f=(0, 0, 0), halo=(0, 1, 1), in_ld=192, in_coff=64, out_ld=320, out_coff=64, out_halo=(0, 1, 1))
+    run_slab_case("T12 1x1x1 s(1,2,2) 256->512 odd 55x55 (i3res50 layer2.0.downsample)", K, 2, (2, 55, 55), 256, 256, 512, (1, 1, 1),
+                  stride=(1, 2, 2), pad_f=(0, 0, 0))
+    run_slab_case("T13 1x1x1 s(2,2,2) 64->128 (r3d layer2.0.downsample)", K, 2, (4, 28, 28), 64, 64, 128, (1, 1, 1), stride=(2, 2, 2),
+                  pad_f=(0, 0, 0))
+    run_slab_case("T14 1x1x1 s(2,2,2) 128->256 odd depth 5x14x14", K, 2, (5, 14, 14), 128, 128, 256, (1, 1, 1), stride=(2, 2, 2),
+                  pad_f=(0, 0, 0))
 
 
 def group_fuzz():
