@@ -99,8 +99,10 @@ def pack_image(kind, w_std, n_tile, k_pad, cin_pad, k, pw_front):
 
 
 # ------------------------------------------------------------------------------------- hardware
-def tma_box(xbits, plan, coords):
-    """Emulate one 5-D tiled TMA load: returns the shared-memory image (uint16, slab_stride bytes, zero padded)."""
+def tma_box(xbits, plan, coords, estr=None):
+    """Emulate one 5-D tiled TMA load: returns the shared-memory image (uint16, slab_stride bytes, zero padded).
+    estr: cuTensorMapEncodeTiled elementStrides (innermost first) - element i of the box along dimension d is tensor
+    element coords[d] + i * estr[d] (plan.box counts the elements KEPT, as conv_slab.cu's forward passes them)."""
     box = list(plan.box)
     dims = list(plan.tdim)
     strides = [2] + list(plan.tstride)  # bytes
@@ -109,7 +111,7 @@ def tma_box(xbits, plan, coords):
     ok = np.ones(ii[0].shape, dtype=bool)
     off = np.full(ii[0].shape, plan.tbase_off, dtype=np.int64)
     for d in range(5):
-        g = ii[d] + coords[d]
+        g = ii[d] * (1 if estr is None else int(estr[d])) + coords[d]
         ok &= (g >= 0) & (g < dims[d])
         off += g.astype(np.int64) * strides[d]
     vals = np.where(ok, xbits[np.where(ok, off // 2, 0)], np.uint16(0))
@@ -144,10 +146,11 @@ def stream_block(w_std, k_pad, n0, n_tile, k0):
     return slot
 
 
-def simulate_tiles(plan, xbits, image_bits, bias, tiles, k_pad=0):
+def simulate_tiles(plan, xbits, image_bits, bias, tiles, k_pad=0, estr=None):
     """Run the plan for the given tile indices; returns {tile: (n[128*tm], tz, oy[128*tm], ox[128*tm], acc[128*tm, n_tile], n0)}
     (oy < 0 or >= OH marks rows the epilogue does not store).
-    image_bits: the weight image (resident kinds) or the standard packed weights (streaming kind, with k_pad)."""
+    image_bits: the weight image (resident kinds) or the standard packed weights (streaming kind, with k_pad).
+    estr: TMA element strides of a strided 1x1x1 streaming convolution (see tma_box)."""
     out = {}
     nt = plan.n_tile
     img = np.concatenate([image_bits, np.zeros(64, np.uint16)])
@@ -168,7 +171,7 @@ def simulate_tiles(plan, xbits, image_bits, bias, tiles, k_pad=0):
             cx, cy = tx * plan.x_step + plan.x_off, ty * plan.y_step + plan.y_off
             cz = tz * plan.z_step + plan.z_off + kt * plan.z_kstep
             coords = (cx * 8, cy, cz, n, 0) if plan.merged_cw else (cb * plan.c_step, cx, cy, cz, n)
-            slab = tma_box(xbits, plan, coords)
+            slab = tma_box(xbits, plan, coords, estr)
             tbase = ks * plan.n_grp if plan.tab_per_stage else 0
             for i in range(plan.n_grp * plan.nk):
                 grp, kk = divmod(i, plan.nk)

@@ -20,7 +20,7 @@ def _bf(t):
     return t.to(torch.bfloat16).float()
 
 
-def _run(kind, x_cl, x_ref, w, stride, pad_f, pad_b, y_shape, tm, tiles=None, cin_pad=8):
+def _run(kind, x_cl, x_ref, w, stride, pad_f, pad_b, y_shape, tm, tiles=None, cin_pad=8, estr=None):
     """x_cl: CLTensor view (cpu) holding x_ref's data; returns max abs error over the simulated tiles."""
     cout = w.shape[0]
     b = torch.linspace(-0.5, 0.5, cout)
@@ -39,7 +39,7 @@ def _run(kind, x_cl, x_ref, w, stride, pad_f, pad_b, y_shape, tm, tiles=None, ci
     ref = F.conv3d(F.pad(_bf(x_ref), pad6), wq, pc.bias[:cout], stride=stride)  # [N,Cout,OD,OH,OW]
     assert tuple(ref.shape[2:]) == tuple(y_shape[1:]), (ref.shape, y_shape)
     tiles = list(range(plan.total_tiles)) if tiles is None else [t % plan.total_tiles for t in tiles]
-    res = S.simulate_tiles(plan, S.bf16_bits(x_cl.buf), image, pc.bias.numpy(), tiles, k_pad=pc.k_pad)
+    res = S.simulate_tiles(plan, S.bf16_bits(x_cl.buf), image, pc.bias.numpy(), tiles, k_pad=pc.k_pad, estr=estr)
     worst, seen = 0.0, 0
     OH, OW = y_shape[2], y_shape[3]
     for tile, (n, tz, oy, ox, acc, n0) in res.items():
@@ -98,6 +98,29 @@ def test_slab_stream_plan_reproduces_conv(name, dhw, cin, cout, kd, halo, tm):
     if tiles is None:
         assert seen == N * D * H * W
     assert err < 3e-5, (name, err)
+
+
+@pytest.mark.parametrize("name,dhw,cin,cout,stride", [
+    ("i3res50 layer2.0.downsample 256->512 s(1,2,2) odd 13x11", (2, 13, 11), 256, 512, (1, 2, 2)),
+    ("r3d layer2.0.downsample 64->128 s(2,2,2) odd depth", (5, 14, 10), 64, 128, (2, 2, 2)),
+    ("resnet18 layer2.0.downsample 2-D 64->128 s2, 23x21", (1, 23, 21), 64, 128, (1, 2, 2)),
+])
+def test_slab_stream_strided_1x1_plan_reproduces_conv(name, dhw, cin, cout, stride):
+    """Strided 1x1x1 (the ResNet down-sample projections): the plan's tile origins are in INPUT pixels and the TMA box
+    walks the input with the convolution's stride (conv_slab.cu forward: elementStrides = (1, sw, sh, 1, 1))."""
+    g = torch.Generator().manual_seed(cin + cout + sum(stride))
+    N = 2
+    D, H, W = dhw
+    x = torch.randn(N, cin, D, H, W, generator=g)
+    w = torch.randn(cout, cin, 1, 1, 1, generator=g) / cin ** 0.5
+    xc = ops.CLTensor(N, D, H, W, cin, (0, 0, 0), device="cpu")
+    xc.interior()[...] = x.permute(0, 2, 3, 4, 1).to(torch.bfloat16)
+    oshape = (N, (D - 1) // stride[0] + 1, (H - 1) // stride[1] + 1, (W - 1) // stride[2] + 1)
+    err, seen, plan = _run(L.SLAB_3X3_STREAM, xc, x, w, stride, (0, 0, 0), (0, 0, 0), oshape, 0, cin_pad=cin,
+                           estr=(1, stride[2], stride[1], 1, 1))
+    assert plan.b_stream == 1 and plan.k_stages == cin // 64 and plan.stack_hp == 0
+    assert plan.x_step == 8 * plan.tm * stride[2] and plan.y_step == 16 * stride[1] and plan.z_step == stride[0]
+    assert seen == oshape[0] * oshape[1] * oshape[2] * oshape[3] and err < 3e-5, (name, err, seen)
 
 
 def test_slab_stem2d_plan_reproduces_conv():
