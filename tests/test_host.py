@@ -481,6 +481,41 @@ def test_extract_videos_packing_bookkeeping_on_cpu():
         assert n_batches_packed <= per_video      # packing never issues more batches than the per-video path
 
 
+def test_needed_frames_staging_property():
+    """SnippetExtractor._needed_frames, both branches (contiguous range for small frames; only the frames a snippet
+    keeps, one chunk per run of consecutive frames, for large ones - the ShanghaiTech reader keeps every second frame,
+    shanghai_dl.py:73): the staged chunks indexed by the returned positions are exactly the frames the snippets name,
+    zero-image slots (-1, the DALI tail padding) stay -1, and the staged-frame count is what the chunks hold."""
+    class Bare(extraction.SnippetExtractor):
+        def __init__(self):
+            pass
+    ext = Bare()
+    rs = np.random.RandomState(3)
+    frames = torch.from_numpy(rs.randint(0, 256, (300, 6, 5, 3)).astype(np.uint8))
+    cases = 0
+    for sparse_bytes in (10 ** 9, 1):           # never sparse / always sparse (when the index set has gaps)
+        ext.SPARSE_FRAME_BYTES = sparse_bytes
+        for source, n in (("dali", 300), ("dali", 47), ("shanghai", 300), ("shanghai", 100), ("dali", 16)):
+            snips = (extraction.dali_snippet_frames(n) if source == "dali" else extraction.shanghai_snippet_frames(n))
+            for s0 in range(0, snips.shape[0], 3):
+                sn = snips[s0:s0 + 3]
+                for base in (0, 17):
+                    chunks, rel, n_staged = ext._needed_frames(frames[:n], sn, base)
+                    staged = torch.cat(list(chunks), 0)
+                    assert staged.shape[0] == n_staged
+                    assert np.array_equal(rel == -1, sn == -1)
+                    ok = sn >= 0
+                    assert rel[ok].min() >= base and rel[ok].max() < base + n_staged
+                    assert torch.equal(staged[torch.from_numpy(rel[ok] - base)], frames[torch.from_numpy(sn[ok])])
+                    if sparse_bytes == 1 and source == "shanghai":
+                        assert n_staged == int(ok.sum())            # every second frame only: nothing unused is staged
+                    cases += 1
+    # an all-padding group (cannot come from the readers, but the packer must survive it)
+    chunks, rel, n_staged = ext._needed_frames(frames, np.full((1, 16), -1, dtype=np.int64), 5)
+    assert n_staged == 1 and (rel == -1).all() and chunks[0].shape[0] == 1
+    assert cases >= 40
+
+
 def test_activation_buffers_are_bounded_by_the_largest_batch():
     """every distinct batch size used to get its own full buffer set (OOM over a dataset's video tails).
     One allocation per name now; smaller batches are N-prefix views of it, a larger batch replaces it."""
