@@ -772,8 +772,17 @@ def group_fuzz():
     rows, odd extents, slices, fused pool, residual) against torch."""
     import random
     from tedspad_b200 import engine
-    rnd = random.Random(1234)
-    for i in range(48):
+    # TEDSPAD_FUZZ_SEED / TEDSPAD_FUZZ_N: other seeds and longer runs (profiles/r2j_fuzz_extended.txt); the defaults are the
+    # battery of the driver-run GPU suite
+    for seed0 in [int(v) for v in os.environ.get("TEDSPAD_FUZZ_SEED", "1234").split(",")]:
+        _fuzz_seed(seed0, int(os.environ.get("TEDSPAD_FUZZ_N", "48")), random, engine)
+
+
+def _fuzz_seed(seed0, count, random, engine):
+    rnd = random.Random(seed0)
+    rnd_s = random.Random(seed0 ^ 0x5151)   # strides come from their own stream: the shapes of a seed do not depend on them
+    tag = "" if seed0 == 1234 else f"s{seed0}."
+    for i in range(count):
         threeD = rnd.random() < 0.35
         sp = rnd.choice([(3, 3), (3, 3), (1, 1)])
         kd = rnd.choice([1, 3]) if threeD else 1
@@ -787,18 +796,24 @@ def group_fuzz():
         res = rnd.random() < 0.25
         pool = (not res) and (not threeD) and sp == (3, 3) and H % 2 == 0 and W % 2 == 0 and rnd.random() < 0.4
         pad = (kd // 2, sp[0] // 2, sp[1] // 2)
+        # strided 1x1x1 (ResNet down-sample projections: the streaming kind with a strided TMA box)
+        stride = (1, 1, 1)
+        if k == (1, 1, 1) and rnd_s.random() < 0.5:
+            stride = (2, 2, 2) if (threeD and rnd_s.random() < 0.5) else (1, 2, 2)
+            pool = False
         # pick the kind the executors would pick for this layer
         g = torch.Generator(device="cpu").manual_seed(i)
         wtmp = torch.zeros(cout, cin, *k)
-        pc = ops.PackedConv(wtmp, None, None, pad_front=pad, cin_pad=cin, device=DEV, n_align=32)
+        pc = ops.PackedConv(wtmp, None, None, stride=stride, pad_front=pad, cin_pad=cin, device=DEV, n_align=32)
         ps = engine.slab3x3(pc)
         if ps is None:
             print(f"[SKIP] fuzz {i}: no slab kind for k={k} {cin}->{cout}")
             continue
         slice_out = rnd.random() < 0.3
-        run_slab_case(f"Z{i} k={k} {cin}->{cout} N={N} D={D} {H}x{W} halo={halo[1]} kind={ps.kind}"
+        run_slab_case(f"Z{tag}{i} k={k} {cin}->{cout} N={N} D={D} {H}x{W} halo={halo[1]} kind={ps.kind}"
+                      f"{' s=' + str(stride) if stride != (1, 1, 1) else ''}"
                       f"{' +pool' if pool else ''}{' +res' if res else ''}{' slice' if slice_out else ''}",
-                      ps.kind, N, (D, H, W), cin, cin, cout, k, pad_f=pad, halo=halo, pool=pool, res=res, seed=100 + i,
+                      ps.kind, N, (D, H, W), cin, cin, cout, k, stride=stride, pad_f=pad, halo=halo, pool=pool, res=res, seed=100 + i,
                       out_ld=(cout + 32) if slice_out else None, out_coff=16 if slice_out else 0)
 
 
