@@ -93,7 +93,8 @@ struct SlabKParams {
   __nv_bfloat16* oc_planes;
   float* oc_frames;
   const __nv_bfloat16* res;    // optional bf16 residual with y's geometry (added before the activation)
-  int res_ld, res_coff;
+  int res_ld, res_coff, res_wide;   // res_wide: every 32-channel chunk of a pixel is 32-byte aligned (256-bit loads)
+  int res_prefetch;                 // L2 prefetch of the next tile's residual rows (epi_res_prefetch_tile)
   __nv_bfloat16* oc_clip;      // encoder clip written through the raw-reshape glue (NULL = planes only)
   int oc_T, cDp, cHp, cWp, cpd, cph, cpw, c_ld, c_coff;
   DivMagic dv_T;
@@ -223,7 +224,7 @@ struct EpiCtx {
   __nv_bfloat16* y;
   __nv_bfloat16* pool;
   int Cout, act, y_ld, y_coff, p_ld, p_coff;
-  bool fuse_oc, wide_ok;
+  bool fuse_oc, wide_ok, res_wide;
   const __nv_bfloat16* res;   // EPI_RES: bf16 residual with y's pixel geometry
   int res_ld, res_coff;
 };
@@ -241,6 +242,17 @@ enum { EPI_PLAIN = 0, EPI_POOL = 1, EPI_OC = 2, EPI_OC_ONLY = 3, EPI_RES = 4 }; 
 // accumulator load is issued (so that the DRAM round trip overlaps the previous chunk's arithmetic).
 __device__ __forceinline__ void epi_res_fetch(const EpiCtx& c, long long pix, int c0, bool valid, uint4 (&r)[4]) {
   const __nv_bfloat16* rp = c.res + pix * c.res_ld + c.res_coff + c0;
+  if (c.res_wide && c0 + 32 <= c.Cout) {
+    // two 32-byte loads: a warp load instruction touches 32 cache lines whatever its width (one pixel per lane), so the
+    // residual costs half the L1 wavefronts of four 16-byte loads - the epilogue of the K = 64 bottleneck tails is
+    // bound by exactly those (1x1 64 -> 256 + residual: 2.3x the time of the same layer without)
+    r[0] = r[1] = r[2] = r[3] = make_uint4(0u, 0u, 0u, 0u);
+    if (valid) {
+      ld_nc_256_pinned(rp, r[0], r[1]);
+      ld_nc_256_pinned(rp + 16, r[2], r[3]);
+    }
+    return;
+  }
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     r[j] = make_uint4(0u, 0u, 0u, 0u);
@@ -357,6 +369,41 @@ __device__ __forceinline__ void epi_out(const EpiCtx& c, const uint32_t (&q)[16]
 // tcgen05.ld has landed in registers, i.e. before any of the arithmetic; the fused OutConv dot product of a pixel is
 // completed by the chunk-0 warp from the chunk-1 warp's partial sums (shared-memory scratch, one named barrier per
 // warp pair and tile, double-buffered by tile parity).
+// EPI_RES: L2 prefetch of the residual rows of `tile` (this lane's pixel, the tile's N-tile channel range), issued one
+// tile ahead of their use.  The bottleneck tails (1x1, K = 64..512) have an epilogue that is never idle, so the
+// two-chunk register prefetch of epi_res_fetch covers only a fraction of a DRAM round trip; an L2 prefetch needs no
+// registers and turns those loads into L2 hits.  Tile decode as in slab_epilogue.
+__device__ __forceinline__ void epi_res_prefetch_tile(const SlabKParams& p, int tile, int g, int r, int h, int eg, int tm) {
+  int t = tile, q;
+  q = fdiv(t, p.dv_nt);
+  const int n0 = (t - q * p.dv_nt.d) * p.n_tile; t = q;
+  q = fdiv(t, p.dv_tx);
+  const int ta = t - q * p.dv_tx.d; t = q;
+  q = fdiv(t, p.dv_ty);
+  const int tb = t - q * p.dv_ty.d; t = q;
+  const int tx = p.ty_first ? tb : ta, ty = p.ty_first ? ta : tb;
+  q = fdiv(t, p.dv_tz);
+  const int tz = t - q * p.dv_tz.d;
+  int n = q;
+  int oy = ty * 16 + g;
+  const int ox = (tx * tm + h) * 8 + r;
+  bool valid = ox < p.OW;
+  if (p.stack_hp) {
+    const int R = oy + p.stack_ph;
+    n = fdiv(R, p.dv_hp);
+    oy = R - n * p.stack_hp - p.stack_ph;
+    valid = valid && n < p.stack_n;
+  }
+  valid = valid && static_cast<unsigned>(oy) < static_cast<unsigned>(p.OH);
+  if (!valid) return;
+  const long long pix = ((static_cast<long long>(n) * p.yDp + tz + p.ypd) * p.yHp + oy + p.yph) * p.yWp + ox + p.ypw;
+  const __nv_bfloat16* rp = p.res + pix * p.res_ld + p.res_coff + n0;
+  const int nc = min(p.n_tile, p.Cout - n0);                  // real channels of this N tile
+  // tm == 1: the two warp groups share the pixels (alternate 32-channel chunks): each takes every second line
+  const int first = tm == 1 ? 64 * eg : 0, step = tm == 1 ? 128 : 64;
+  for (int ch = first; ch < nc; ch += step) prefetch_l2(rp + ch);
+}
+
 template <bool HAS_UP, bool PAIR, int MODE, bool RELU, bool E16>
 __device__ __forceinline__ void slab_epilogue(const SlabKParams& p, int warp, int lane, uint32_t tmem_base, const float* sm_bias,
                                               const float* sm_ocw, uint64_t* tfull, uint64_t* tempty, float* sm_part) {
@@ -372,6 +419,7 @@ __device__ __forceinline__ void slab_epilogue(const SlabKParams& p, int warp, in
   // 32-byte stores need 32-byte aligned pixel chunks
   c.wide_ok = ((p.y_ld | p.y_coff) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.y) & 31) == 0;
   c.res = p.res; c.res_ld = p.res_ld; c.res_coff = p.res_coff;
+  c.res_wide = p.res_wide != 0;
   int h, c_first, c_step, nch;
   if (E16) { h = eg; c_first = 32 * ((warp >> 2) & 1); c_step = 64; nch = 1; }   // tm == 2, n_tile == 64
   else if (tm == 2) { h = eg; c_first = 0; c_step = 32; nch = nchunk_all; }
@@ -379,7 +427,11 @@ __device__ __forceinline__ void slab_epilogue(const SlabKParams& p, int warp, in
   else { h = 0; c_first = 32 * eg; c_step = 64; nch = (nchunk_all + 1 - eg) >> 1; }
   int as = 0, tpar = 0;
   uint32_t aph = 0;
+  const bool res_pf = MODE == EPI_RES && !E16 && p.res_prefetch != 0;
+  if (res_pf && static_cast<int>(blockIdx.x) < p.total_tiles) epi_res_prefetch_tile(p, blockIdx.x, g, r, h, eg, tm);
   for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    if (res_pf && tile + static_cast<int>(gridDim.x) < p.total_tiles)
+      epi_res_prefetch_tile(p, tile + gridDim.x, g, r, h, eg, tm);   // one tile ahead
     int t = tile, q;
     q = fdiv(t, p.dv_nt);
     const int n0 = (t - q * p.dv_nt.d) * n_tile; t = q;   // first output channel of this N tile
@@ -1486,6 +1538,10 @@ extern "C" int tedspad_conv_slab_forward(const tedspad_conv_slab* c, void* strea
                   (reinterpret_cast<uintptr_t>(c->res) & 15) == 0,
               "slab: a residual excludes the fused pool / OutConv / up-sampling and must be 16-byte aligned per pixel chunk");
     p.res = reinterpret_cast<const __nv_bfloat16*>(c->res);
+    static const bool res_wide_on = [] { const char* e = getenv("TEDSPAD_RES_WIDE"); return e == nullptr || e[0] != '0'; }();
+    static const bool res_pf_on = [] { const char* e = getenv("TEDSPAD_RES_PREFETCH"); return e == nullptr || e[0] != '0'; }();
+    p.res_prefetch = res_pf_on ? 1 : 0;
+    p.res_wide = res_wide_on && ((c->res_ld | c->res_coff) & 15) == 0 && (reinterpret_cast<uintptr_t>(c->res) & 31) == 0;
     p.res_ld = c->res_ld; p.res_coff = c->res_coff;
   }
   if (c->pool.ptr != nullptr) {

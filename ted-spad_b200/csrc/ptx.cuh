@@ -318,6 +318,17 @@ __device__ __forceinline__ uint4 ld_nc_v4_pinned(const void* p) {
   asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
   return r;
 }
+// L2 prefetch of the 128-byte line that holds p (no destination register: any number may be in flight)
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+// 32-byte read-only load (address 32-byte aligned), pinned like ld_nc_v4_pinned: half as many load instructions / L1
+// wavefronts per byte (sm_100: LDG.E.256)
+__device__ __forceinline__ void ld_nc_256_pinned(const void* p, uint4& a, uint4& b) {
+  asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+               : "l"(p));
+}
 // 32-byte store (address 32-byte aligned): half as many store instructions / L1 wavefronts per byte as v4
 __device__ __forceinline__ void st_global_256(void* p, const uint32_t* q) {
   asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
