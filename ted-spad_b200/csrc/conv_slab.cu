@@ -95,6 +95,11 @@ struct SlabKParams {
   const __nv_bfloat16* res;    // optional bf16 residual with y's geometry (added before the activation)
   int res_ld, res_coff, res_wide;   // res_wide: every 32-channel chunk of a pixel is 32-byte aligned (256-bit loads)
   int res_prefetch;                 // L2 prefetch of the next tile's residual rows (epi_res_prefetch_tile)
+  // staged stores (EPI_PLAIN, tm == 2, n_tile == 64, single CTA): every epilogue warp writes its 32 pixels x 128 B into a
+  // swizzled shared-memory tile and one lane issues a TMA tensor store of full 128-byte lines (profiles/
+  // r2j_hbm_write_probe.md: one-row-per-lane st.global tops out at 4.8 TB/s, TMA bulk stores reach 6.3)
+  CUtensorMap tmY;
+  int tst, tst_off;                 // on / byte offset of the 8 warps x 2 x 4 KB staging area in shared memory
   __nv_bfloat16* oc_clip;      // encoder clip written through the raw-reshape glue (NULL = planes only)
   int oc_T, cDp, cHp, cWp, cpd, cph, cpw, c_ld, c_coff;
   DivMagic dv_T;
@@ -227,6 +232,8 @@ struct EpiCtx {
   bool fuse_oc, wide_ok, res_wide;
   const __nv_bfloat16* res;   // EPI_RES: bf16 residual with y's pixel geometry
   int res_ld, res_coff;
+  uint8_t* stg;               // EPI_PLAIN staged stores: this warp's 4 KB tile (row = lane), or nullptr
+  int stg_c0;                 // first channel of the N tile (staging column 0)
 };
 
 // MODE: 0 = bf16 stores only, 1 = + fused MaxPool2d(2), 2 = fused OutConv (stores / pool optional at run time),
@@ -322,6 +329,17 @@ template <int MODE>
 __device__ __forceinline__ void epi_out(const EpiCtx& c, const uint32_t (&q)[16], int c0, bool valid, long long pix,
                                         bool pool_writer, long long ppix) {
   if (MODE == EPI_OC_ONLY) return;
+  if (MODE == EPI_PLAIN && c.stg != nullptr) {
+    // row = lane (128 bytes = 64 channels), 16-byte chunk k at position k ^ (row & 7): the SWIZZLE_128B image the
+    // tensor map of the store expects, and conflict-free for the 8 lanes of a quarter warp
+    const uint32_t lane = threadIdx.x & 31u;
+    uint8_t* row = c.stg + lane * 128u;
+    const uint32_t k0 = static_cast<uint32_t>(c0 - c.stg_c0) >> 3;
+#pragma unroll
+    for (uint32_t j = 0; j < 4; ++j)
+      *reinterpret_cast<uint4*>(row + (((k0 + j) ^ (lane & 7u)) << 4)) = make_uint4(q[4 * j], q[4 * j + 1], q[4 * j + 2], q[4 * j + 3]);
+    return;
+  }
   if ((MODE != EPI_OC || c.y != nullptr) && valid) {
     // each lane owns 64 contiguous bytes of its pixel: two 32-byte stores (a warp store instruction touches 32
     // cache lines whatever its width, so wider stores halve the L1 wavefronts per byte)
@@ -406,7 +424,8 @@ __device__ __forceinline__ void epi_res_prefetch_tile(const SlabKParams& p, int 
 
 template <bool HAS_UP, bool PAIR, int MODE, bool RELU, bool E16>
 __device__ __forceinline__ void slab_epilogue(const SlabKParams& p, int warp, int lane, uint32_t tmem_base, const float* sm_bias,
-                                              const float* sm_ocw, uint64_t* tfull, uint64_t* tempty, float* sm_part) {
+                                              const float* sm_ocw, uint64_t* tfull, uint64_t* tempty, float* sm_part,
+                                              uint8_t* sm_stage) {
   pdl_wait();   // the previous kernel may still be reading the buffers this one writes
   const int ew = warp & 3, eg = E16 ? (warp >> 3) : (warp >> 2);
   const int g = ew * 4 + (lane >> 3);
@@ -420,6 +439,9 @@ __device__ __forceinline__ void slab_epilogue(const SlabKParams& p, int warp, in
   c.wide_ok = ((p.y_ld | p.y_coff) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.y) & 31) == 0;
   c.res = p.res; c.res_ld = p.res_ld; c.res_coff = p.res_coff;
   c.res_wide = p.res_wide != 0;
+  c.stg = nullptr; c.stg_c0 = 0;
+  const bool tst = MODE == EPI_PLAIN && !HAS_UP && !PAIR && !E16 && p.tst != 0;   // (host: tm == 2, n_tile == 64, no stacking)
+  int tst_buf = 0;
   int h, c_first, c_step, nch;
   if (E16) { h = eg; c_first = 32 * ((warp >> 2) & 1); c_step = 64; nch = 1; }   // tm == 2, n_tile == 64
   else if (tm == 2) { h = eg; c_first = 0; c_step = 32; nch = nchunk_all; }
@@ -462,6 +484,13 @@ __device__ __forceinline__ void slab_epilogue(const SlabKParams& p, int warp, in
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) +
                            static_cast<uint32_t>((as * tm + h) * n_tile + c_first);
     float oc[3] = {0.f, 0.f, 0.f};
+    if (tst) {
+      // the store that read this staging buffer two tiles ago must have finished reading it
+      if (lane == 0) bulk_wait_read<1>();
+      __syncwarp();
+      c.stg = sm_stage + (warp * 2 + tst_buf) * 4096;
+      c.stg_c0 = n0;
+    }
     mbar_wait(tfull + as, aph);
     tc_fence_after();
     uint4 ra[4], rb[4];   // EPI_RES only (dead otherwise)
@@ -540,6 +569,14 @@ __device__ __forceinline__ void slab_epilogue(const SlabKParams& p, int warp, in
         else mbar_arrive(tempty + as);
       }
     }
+    if (tst) {
+      // the warp's 4 rows x 8 columns x 64 channels leave as ONE tensor store (box {64, 8, 4, 1, 1}); pixels outside the
+      // image are outside the tensor map and are not written
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) tma_store_5d(&p.tmY, c.stg, n0, (tx * tm + h) * 8, ty * 16 + ew * 4, tz, n);
+      tst_buf ^= 1;
+    }
     if ((MODE == EPI_OC || MODE == EPI_OC_ONLY) && valid && nch > 0 && (!E16 || c_first == 0)) {
       const long long plane = static_cast<long long>(OH) * OW;
       const long long o0 = static_cast<long long>(n) * 3 * plane + static_cast<long long>(oy) * OW + ox;
@@ -560,6 +597,7 @@ __device__ __forceinline__ void slab_epilogue(const SlabKParams& p, int warp, in
     }
     if (++as == p.acc_stages) { as = 0; aph ^= 1; }
   }
+  if (tst && lane == 0) bulk_wait_all<0>();   // the staging area must outlive the stores that read it
 }
 
 // KX kinds (TEDSPAD_SLAB_3X3_KX_PAIR).  At N <= 64 outputs the MMA is bound by its A-operand reads: a 3x3 layer reads
@@ -738,6 +776,7 @@ conv_slab_kernel(const __grid_constant__ SlabKParams p) {
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;   // == blockIdx.x & 1: the tile loops below need no change
 
   if (warp == W_PROD && lane == 0) {
+    if (p.tst) tma_prefetch_desc(&p.tmY);
     tma_prefetch_desc(&p.tmA);
     if (p.b_stream) tma_prefetch_desc(&p.tmB);
   }
@@ -892,8 +931,8 @@ conv_slab_kernel(const __grid_constant__ SlabKParams p) {
     } else {
 #define TSP_EPI(MODE_) \
     do { \
-      if (relu) slab_epilogue<HAS_UP, PAIR, MODE_, true, E16>(p, warp, lane, tmem_base, sm_bias, sm_ocw, tfull, tempty, sm_part); \
-      else slab_epilogue<HAS_UP, PAIR, MODE_, false, E16>(p, warp, lane, tmem_base, sm_bias, sm_ocw, tfull, tempty, sm_part); \
+      if (relu) slab_epilogue<HAS_UP, PAIR, MODE_, true, E16>(p, warp, lane, tmem_base, sm_bias, sm_ocw, tfull, tempty, sm_part, smem + p.tst_off); \
+      else slab_epilogue<HAS_UP, PAIR, MODE_, false, E16>(p, warp, lane, tmem_base, sm_bias, sm_ocw, tfull, tempty, sm_part, smem + p.tst_off); \
     } while (0)
     if (p.res != nullptr) TSP_EPI(EPI_RES);
     else if (p.oc_w != nullptr && p.y == nullptr && p.pool == nullptr) TSP_EPI(EPI_OC_ONLY);
@@ -1610,6 +1649,28 @@ extern "C" int tedspad_conv_slab_forward(const tedspad_conv_slab* c, void* strea
     p.up_cb_first = 1 << 20;
   }
 
+  // staged TMA stores (see SlabKParams::tmY): plain epilogue, single CTA, 16 x 16 tiles of 64 output channels, tiles that
+  // do not run across images; the staging area (8 warps x 2 x 4 KB) sits behind everything make_plan laid out
+  int smem_bytes = P.smem_bytes;
+  {
+    static const bool tst_on = [] { const char* e = getenv("TEDSPAD_TMA_STORE"); return e == nullptr || e[0] != '0'; }();
+    const int tst_off = static_cast<int>(round_up(P.smem_bytes - 1024, 1024));   // offset from the 1024-aligned base
+    if (tst_on && !P.pair && !has_up && !fused_oc && c->res == nullptr && c->pool.ptr == nullptr && P.tm == 2 &&
+        P.n_tile == 64 && c->Cout == 64 && P.num_n_tiles == 1 && P.stack_hp == 0 && y.ld % 8 == 0 && y.coff % 8 == 0 &&
+        1024 + tst_off + 8 * 2 * 4096 <= SLAB_SMEM_BUDGET) {
+      const uint64_t ydims[5] = {(uint64_t)c->Cout, (uint64_t)y.W, (uint64_t)y.H, (uint64_t)y.D, (uint64_t)y.N};
+      const uint64_t px = (uint64_t)y.ld * 2;
+      const uint64_t ystr[4] = {px, px * p.yWp, px * p.yWp * p.yHp, px * p.yWp * p.yHp * p.yDp};
+      const uint32_t ybox[5] = {64, 8, 4, 1, 1};
+      const uint8_t* ybase = reinterpret_cast<const uint8_t*>(y.ptr) +
+                             2 * ((((int64_t)y.pd * p.yHp + y.ph) * p.yWp + y.pw) * y.ld + y.coff);
+      if (encode_tmap_5d_bf16(&p.tmY, ybase, ydims, ystr, ybox, true)) return 3;
+      p.tst = 1;
+      p.tst_off = tst_off;
+      smem_bytes = 1024 + tst_off + 8 * 2 * 4096;
+    }
+  }
+
   if (device_once(ONCE_SLAB_ATTR)) {   // per device: the opt-in to > 48 KB of dynamic shared memory
     cudaError_t e = cudaFuncSetAttribute(conv_slab_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SLAB_SMEM_BUDGET);
     if (e == cudaSuccess)
@@ -1638,7 +1699,7 @@ extern "C" int tedspad_conv_slab_forward(const tedspad_conv_slab* c, void* strea
   } else if (has_up) {
     TSP_CUDA(launch_kernel(conv_slab_kernel<true, false, false>, dim3(ctas), dim3(SLAB_THREADS_UP), P.smem_bytes, st, p));
   } else {
-    TSP_CUDA(launch_kernel(conv_slab_kernel<false, false, false>, dim3(ctas), dim3(SLAB_THREADS), P.smem_bytes, st, p));
+    TSP_CUDA(launch_kernel(conv_slab_kernel<false, false, false>, dim3(ctas), dim3(SLAB_THREADS), smem_bytes, st, p));
   }
   TSP_CUDA(cudaGetLastError());
   return 0;

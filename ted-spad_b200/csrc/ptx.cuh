@@ -86,6 +86,24 @@ __device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* m
       ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
+// 5-D tiled TMA STORE shared -> global (bulk async-group completion; elements of the box outside the tensor are not
+// written).  The shared-memory image must have been made visible to the async proxy (fence_proxy_async_smem).
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, const void* smem_src, int32_t c0, int32_t c1, int32_t c2,
+                                             int32_t c3, int32_t c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+               ::"l"(map), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// wait until at most N of this thread's bulk groups still READ their shared-memory source / are still pending at all
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_all() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
 // contiguous global -> shared bulk copy (bytes % 16 == 0, both addresses 16-byte aligned)
 __device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
