@@ -244,3 +244,26 @@ def simulate_tiles_kx(plan, xbits, image_bits, bias, tiles, cp):
             nn = np.minimum(nn, plan.stack_n - 1)
         out[tile] = (nn, oy, ox, res.reshape(112, cp))
     return out
+
+
+# --------------------------------------------------------------------- staged epilogue stores
+def stage_rows(q_rows):
+    """conv_slab.cu epi_out, staged form: lane r of an epilogue warp writes the 64 bf16 of its pixel as eight 16-byte
+    chunks, chunk k at position k ^ (r & 7) of shared-memory row r.  q_rows: uint16 [32, 64] -> the warp's 4 KB tile."""
+    smem = np.zeros(32 * 64, dtype=np.uint16)
+    for lane in range(32):
+        for k in range(8):
+            pos = k ^ (lane & 7)
+            smem[lane * 64 + pos * 8: lane * 64 + pos * 8 + 8] = q_rows[lane, k * 8:(k + 1) * 8]
+    return smem
+
+
+def tma_store_box(smem_bits, box=(64, 8, 4)):
+    """What a SWIZZLE_128B tiled TMA store reads for box element (c, x, y): the same address rule as tma_box (the
+    linear offset of the element with bits 4-6 XORed by bits 7-9).  Returns uint16 [y, x, c]."""
+    C, X, Y = box
+    c, x, y = np.meshgrid(np.arange(C), np.arange(X), np.arange(Y), indexing="ij")
+    lin = (((y * X + x) * C + c) * 2).astype(np.int64)
+    lin ^= ((lin >> 7) & 7) << 4
+    return smem_bits[lin // 2].transpose(2, 1, 0)
+

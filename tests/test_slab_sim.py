@@ -222,3 +222,21 @@ def test_slab_3x3_pair_plan_reproduces_conv(cin, cout):
     err, seen, plan = _run(L.SLAB_3X3_PAIR, xc, x, w, (1, 1, 1), (0, 1, 1), (0, 1, 1), (N, 1, H, W), 0, cin_pad=cin)
     assert plan.pair == 1 and plan.tm == 2 and plan.total_tiles % 2 == 0
     assert seen == N * H * W and err < 2e-5, (err, seen)
+
+
+def test_staged_store_tile_is_the_swizzle_128b_image_of_the_box():
+    """The staged epilogue store (conv_slab.cu: SlabKParams::tmY): a warp's 32 pixels (4 tile rows x 8 columns, lane =
+    row * 8 + column) x 64 channels, written chunk-swizzled by the lanes, must be exactly what a SWIZZLE_128B tensor store
+    of box {64, 8, 4} reads back as [row][column][channel]; and the eight lanes of a quarter warp must hit eight distinct
+    16-byte bank groups (conflict-free shared-memory stores)."""
+    rs = np.random.RandomState(5)
+    q = rs.randint(0, 65536, (32, 64)).astype(np.uint16)
+    out = S.tma_store_box(S.stage_rows(q))
+    assert out.shape == (4, 8, 64)
+    assert np.array_equal(out.reshape(32, 64), q)
+    for k in range(8):
+        for quarter in range(4):
+            lanes = np.arange(quarter * 8, quarter * 8 + 8)
+            groups = (k ^ (lanes & 7)) % 8          # 16-byte column of the 128-byte row = bank group
+            assert len(set(groups.tolist())) == 8
+
