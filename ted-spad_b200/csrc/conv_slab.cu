@@ -1664,10 +1664,13 @@ extern "C" int tedspad_conv_slab_forward(const tedspad_conv_slab* c, void* strea
       const uint32_t ybox[5] = {64, 8, 4, 1, 1};
       const uint8_t* ybase = reinterpret_cast<const uint8_t*>(y.ptr) +
                              2 * ((((int64_t)y.pd * p.yHp + y.ph) * p.yWp + y.pw) * y.ld + y.coff);
-      if (encode_tmap_5d_bf16(&p.tmY, ybase, ydims, ystr, ybox, true)) return 3;
-      p.tst = 1;
-      p.tst_off = tst_off;
-      smem_bytes = 1024 + tst_off + 8 * 2 * 4096;
+      // (a tensor the map cannot describe - base not 16-byte aligned, a stride beyond 2^40 - keeps the direct stores)
+      if ((reinterpret_cast<uintptr_t>(ybase) & 15) == 0 && px * p.yWp * p.yHp * p.yDp < (1ULL << 40) &&
+          encode_tmap_5d_bf16(&p.tmY, ybase, ydims, ystr, ybox, true) == 0) {
+        p.tst = 1;
+        p.tst_off = tst_off;
+        smem_bytes = 1024 + tst_off + 8 * 2 * 4096;
+      }
     }
   }
 
