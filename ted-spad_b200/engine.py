@@ -47,7 +47,7 @@ ENC_IN_CHANNELS = 4 if USE_SLAB_STEM3D else 8   # channel padding of the encoder
 # conv's slab producers instead of being materialised by tedspad_upsample2x.  Bit-identical to the two-kernel path
 # (tests/gpu_diag.py slabup) but MEASURED SLOWER on B200 at every level (905 clips/s unfused; 890 / 881 / 845 / 751
 # with levels 1 / 1-2 / 1-3 / 1-4 fused): the interpolation competes with the epilogue warps for issue slots while the
-# stand-alone kernel already runs at the HBM write ceiling.  Off by default; kept as an option for narrower batches.
+# stand-alone kernel streams its coalesced stores independently of the tensor pipe.  Off by default; kept as an option for narrower batches.
 FUSE_UPSAMPLE_LEVELS = tuple(int(v) for v in os.environ.get("TEDSPAD_FUSE_UPSAMPLE", "").split(",") if v) if USE_SLAB else ()
 
 
