@@ -113,6 +113,19 @@ class SnippetExtractor:
         from .engine import GraphCache
         self._graphs = GraphCache()
 
+    @classmethod
+    def from_params(cls, fa_model, ft_model, params, **overrides):
+        """Build from a `params_feature_ex`-style module / namespace (feature_extraction/params_feature_ex.py:2-9, read by
+        dali_extraction.py:36-50,56-76 and shanghai_dl.py:22-40): num_frames, fix_skip, reso_h, reso_w, cropping_factor,
+        no_ar_distortion.  The reference's `batch_size` (1: one clip per DALI batch) and `num_workers` describe ITS loop,
+        not the result, and are not taken over - snippets are batched `batch_clips` at a time here, every clip computed
+        independently of its neighbours; pass batch_clips / ncrops / source / device as keyword overrides."""
+        kw = dict(reso=(int(params.reso_h), int(params.reso_w)), num_frames=int(params.num_frames),
+                  fix_skip=int(params.fix_skip), cropping_factor=float(params.cropping_factor),
+                  no_ar_distortion=bool(params.no_ar_distortion))
+        kw.update(overrides)
+        return cls(fa_model, ft_model, **kw)
+
     def snippet_frames(self, n_frames, total_frames=None):
         if self.source == "dali":
             return dali_snippet_frames(n_frames, self.T, self.skip)

@@ -516,6 +516,28 @@ def test_needed_frames_staging_property():
     assert cases >= 40
 
 
+def test_extractor_from_reference_params_module():
+    """SnippetExtractor.from_params reads the reference's own parameter file (feature_extraction/params_feature_ex.py
+    restated: the GPU box has no /root/reference) and lets keyword overrides win."""
+    import types
+    params = types.SimpleNamespace(num_classes=102, num_frames=16, fix_skip=2, batch_size=1, reso_h=224, reso_w=224,
+                                   cropping_factor=0.8, no_ar_distortion=False, num_workers=4)   # params_feature_ex.py:1-9
+    ref_params = "/root/reference/feature_extraction/params_feature_ex.py"
+    if os.path.exists(ref_params):   # in the build container: the restatement above IS the reference's file
+        ns = {}
+        exec(open(ref_params).read(), ns)
+        assert {k: ns[k] for k in vars(params)} == vars(params)
+
+    class Capture(extraction.SnippetExtractor):
+        def __init__(self, fa, ft, **kw):
+            self.args = (fa, ft, kw)
+
+    ext = Capture.from_params("fa", "ft", params, ncrops=10, batch_clips=40, source="shanghai")
+    assert ext.args == ("fa", "ft", dict(reso=(224, 224), num_frames=16, fix_skip=2, cropping_factor=0.8,
+                                         no_ar_distortion=False, ncrops=10, batch_clips=40, source="shanghai"))
+    assert Capture.from_params("fa", "ft", params, fix_skip=1).args[2]["fix_skip"] == 1
+
+
 def test_activation_buffers_are_bounded_by_the_largest_batch():
     """every distinct batch size used to get its own full buffer set (OOM over a dataset's video tails).
     One allocation per name now; smaller batches are N-prefix views of it, a larger batch replaces it."""
